@@ -1,0 +1,152 @@
+/* mvin_b200.h -- C ABI of libmvin_b200.so: the MVIN hot path (multi-hop KG neighbour gather + attention
+ * aggregation + RippleNet-style user o-set propagation, forward and backward) as sm_100a CUDA kernels.
+ *
+ * The reference (johnnyjana730/MVIN) has no FFI: its only boundary is the Python class `MVIN`
+ * (src/model/MVIN/model.py:6-11) driven through `tf.Session.run`.  Every entry point below replaces the TF1
+ * sub-graph named beside it; `mvin_b200/model.py` is the Python face that keeps the reference's
+ * ctor / feed-dict / train / eval / get_scores API on top of this ABI.
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA-runtime types in signatures: streams are passed as `void*` (a cudaStream_t).
+ *   - the CALLER owns every buffer (torch tensors in the Python face); the library allocates nothing on the
+ *     device after mvin_create().  All device pointers must be 16-byte aligned, row-major, contiguous.
+ *   - all work is enqueued on the caller's stream; no hidden synchronisation except in the *_host entry
+ *     points, which are documented as blocking.
+ *   - return value 0 = success, negative = error; message via mvin_last_error() (thread-local).
+ *   - a handle is not thread-safe; use one per device / per stream.
+ *   - supported model configuration: --ablation all (parameter_ablation.py:4-12), n_mix_hop = 1,
+ *     1 <= h_hop <= 3, dim in {8,16,32,64,128}, neighbor_sample_size <= 64, p_hop >= 0.
+ *     Anything else returns MVIN_ERR_UNSUPPORTED (the product never falls back to a CPU path).
+ */
+#ifndef MVIN_B200_H
+#define MVIN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVIN_OK 0
+#define MVIN_ERR_INVALID -1
+#define MVIN_ERR_UNSUPPORTED -2
+#define MVIN_ERR_CUDA -3
+#define MVIN_ERR_STATE -4
+
+#define MVIN_ABI_VERSION 1
+
+typedef struct mvin_handle_s* mvin_handle_t;
+
+/* Mirrors the fields MVIN._parse_args reads (model.py:17-47) plus the table sizes of the ctor (model.py:7). */
+typedef struct mvin_config {
+  int32_t dim;                  /* --dim                    d */
+  int32_t neighbor_sample_size; /* --neighbor_sample_size   K */
+  int32_t h_hop;                /* --h_hop                  H (= L when n_mix_hop = 1) */
+  int32_t n_mix_hop;            /* --n_mix_hop              M, must be 1 */
+  int32_t p_hop;                /* --p_hop                  p */
+  int32_t n_memory;             /* --n_memory               m */
+  int32_t n_user, n_entity, n_relation;
+  int32_t max_batch;            /* largest B that will be passed (the reference bakes B into the graph) */
+  float l2_weight;              /* --l2_weight     (model.py:412) */
+  float l2_agg_weight;          /* --l2_agg_weight (model.py:412) */
+  int32_t flags;                /* bit0 User_orient, bit1 User_orient_rela, bit2 User_orient_kg_eh, bit3 PS_O_ft,
+                                   bit4 wide_deep, bit5 PS_only, bit6 HO_only; 'all' = 0x1f */
+} mvin_config_t;
+
+#define MVIN_FLAGS_ALL 0x1f
+
+/* The parameter set of MVIN._build_model (model.py:72-122) + the aggregators (aggregators.py:83-93), fp32,
+ * device pointers.  The same struct describes a gradient set (same shapes) and Adam moment sets.
+ * With n_mix_hop = 1: L = h_hop. */
+typedef struct mvin_params {
+  float* user_emb;      /* [n_user, d]            user_emb_matrix_STWS        model.py:72-74   */
+  float* entity_emb;    /* [n_entity, d]          entity_emb_matrix_STWS      model.py:76-78   */
+  float* relation_emb;  /* [n_relation, d]        relation_emb_matrix_STWS    model.py:80-82   */
+  float* relation_kge;  /* [n_relation, d, d]     relation_emb_KGE_matrix_STWS model.py:84-86  */
+  float* mix_w;         /* [(H+1) d, d]           enti_transfer_matrix_list[0] model.py:91-98  */
+  float* mix_b;         /* [d]                    enti_transfer_bias_list[0]                   */
+  float* user_mlp_w;    /* [(p+1) d, d]           user_mlp_matrix             model.py:100-104 */
+  float* user_mlp_b;    /* [d]                    user_mlp_bias               model.py:105-106 */
+  float* transfer_w;    /* [L+1, d, d]            transfer_matrix_list[e]     model.py:107-116 */
+  float* transfer_b;    /* [L+1, d]               transfer_matrix_bias[e]                      */
+  float* h_item_w;      /* [2 d]                  h_emb_item_mlp_matrix       model.py:118-120 */
+  float* h_item_b;      /* [1]                    h_emb_item_mlp_bias         model.py:121-122 */
+  float* agg_w;         /* [H, d, d]              aggregator i: weights       aggregators.py:83-85 */
+  float* agg_b;         /* [H, d]                 aggregator i: bias          aggregators.py:86-87 */
+  float* agg_urh_w;     /* [H, 3 d]               aggregator i: urh_weights   aggregators.py:89-91 */
+  float* agg_urh_b;     /* [H]                    aggregator i: urh_bias (created, never used) :92-93 */
+} mvin_params_t;
+
+int mvin_abi_version(void);
+const char* mvin_last_error(void);
+
+/* Lifetime.  mvin_create validates the configuration (MVIN_ERR_UNSUPPORTED for anything outside the
+ * supported set) and records the device that is current on the calling thread. */
+int mvin_create(const mvin_config_t* cfg, mvin_handle_t* out);
+int mvin_destroy(mvin_handle_t h);
+
+/* Bind the parameter tables (read by forward, updated by mvin_adam_step), the gradient buffers (written by
+ * mvin_backward) and the packed adjacency built by mvin_pack_adjacency. */
+int mvin_bind_params(mvin_handle_t h, const mvin_params_t* params);
+int mvin_bind_grads(mvin_handle_t h, const mvin_params_t* grads);
+int mvin_bind_adjacency(mvin_handle_t h, const int32_t* adj_packed /* [n_entity, 2, K] */);
+
+/* adj_entity / adj_relation int64 [n_entity, K] (MVIN.__init__ args, model.py:7,19-20; built by
+ * data_loader_user_set.py:375-388) -> packed int32 [n_entity][2][K]: row e = K neighbour ids then K relation
+ * ids, one contiguous 8K-byte record per entity.  Device pointers. */
+int mvin_pack_adjacency(const int64_t* adj_entity, const int64_t* adj_relation, int32_t n_entity, int32_t K,
+                        int32_t* adj_packed, void* stream);
+
+/* Workspace (activations kept for backward + scratch), in bytes, for batch size B. */
+size_t mvin_workspace_bytes(mvin_handle_t h, int32_t B);
+
+/* MVIN.get_neighbors (model.py:243-256): entities[i] int64 [B, K^i] for i = 0..n_levels, relations[i] int64
+ * [B, K^(i+1)] for i < n_levels, child k of node j at flat position j*K+k.  `entities` / `relations` are HOST
+ * arrays of DEVICE pointers.  Bit-exact integer path. */
+int mvin_get_neighbors(mvin_handle_t h, const int64_t* item_indices, int32_t B, int32_t n_levels,
+                       int64_t* const* entities, int64_t* const* relations, void* stream);
+
+/* Forward pass = model.py:125-159 (ripple-memory lookups, get_neighbors, _key_addressing,
+ * aggregate_delta_whole, score).  Feed contract = model.py:49-64 with the memories stacked per hop:
+ *   user_indices, item_indices int64 [B]; mem_h / mem_r / mem_t int32 [max(1,p), B, m].
+ * Outputs: scores [B] (model.py:158) and scores_normalized [B] (model.py:159); either may be NULL.
+ * Activations needed by mvin_backward stay in `workspace`. */
+int mvin_forward(mvin_handle_t h, const int64_t* user_indices, const int64_t* item_indices,
+                 const int32_t* mem_h, const int32_t* mem_r, const int32_t* mem_t, int32_t B, float* scores,
+                 float* scores_normalized, void* workspace, void* stream);
+
+/* importance_list_0 [B,1,K] and importance_list_1 [B,K,K] (model.py:319-323; aggregators.py:139): attention
+ * of aggregator i=0 at hops 0 and 1, for the batch of the last mvin_forward.  imp1 may be NULL (and is unused
+ * when h_hop = 1). */
+int mvin_importance(mvin_handle_t h, float* imp0, float* imp1, void* workspace, void* stream);
+
+/* Loss (model.py:378-412) and the gradient of every parameter (TF autodiff behind model.py:414) for the batch
+ * of the last mvin_forward on the same workspace.  Gradient buffers are overwritten (zero-filled first, so an
+ * unused row has gradient 0, matching TF's dense-equivalent sparse Adam).  losses_out (device, 4 floats):
+ * loss, base_loss, l2_loss, l2_agg_loss. */
+int mvin_backward(mvin_handle_t h, const float* labels, int32_t B, float* losses_out, void* workspace,
+                  void* stream);
+
+/* tf.train.AdamOptimizer(lr).minimize (model.py:414) with TF1 defaults and epsilon placement:
+ * lr_t = lr sqrt(1-b2^t)/(1-b1^t); var -= lr_t m / (sqrt(v)+eps), dense over every bound parameter. */
+int mvin_adam_step(mvin_handle_t h, const mvin_params_t* m, const mvin_params_t* v, float lr, float beta1,
+                   float beta2, float eps, int32_t step /* t, 1-based */, void* stream);
+
+/* One training step from HOST buffers (what `MVIN.train(sess, feed_dict)` does, model.py:416-417, including
+ * the host->device feed copy TF performs inside Session.run): copies the feed H2D on `stream`, runs forward +
+ * backward (+ Adam when adam_m != NULL), copies the 4 loss scalars back to losses_host and synchronises the
+ * stream.  `staging` is a device buffer of at least mvin_feed_bytes(h, B) bytes. */
+size_t mvin_feed_bytes(mvin_handle_t h, int32_t B);
+int mvin_train_step_host(mvin_handle_t h, const int64_t* user_indices, const int64_t* item_indices,
+                         const float* labels, const int32_t* mem_h, const int32_t* mem_r, const int32_t* mem_t,
+                         int32_t B, void* staging, void* workspace, const mvin_params_t* adam_m,
+                         const mvin_params_t* adam_v, float lr, int32_t step, float* losses_host, void* stream);
+
+/* Number of kernels the library has launched on behalf of this handle since creation (bench evidence). */
+int64_t mvin_launch_count(mvin_handle_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVIN_B200_H */

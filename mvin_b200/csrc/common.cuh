@@ -1,0 +1,61 @@
+// common.cuh -- device helpers shared by the MVIN sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MVIN_DEV __device__ __forceinline__
+#define FULL_MASK 0xffffffffu
+
+namespace mvin {
+
+MVIN_DEV float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o));
+  return v;
+}
+MVIN_DEV float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+// sum over the lanes of a power-of-two sub-group of width W (lanes share the high bits of the lane id)
+template <int W>
+MVIN_DEV float group_sum(float v) {
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+// sum across the 32/W sub-groups of a warp (lanes with the same low bits)
+template <int W>
+MVIN_DEV float cross_group_sum(float v) {
+#pragma unroll
+  for (int o = 16; o >= W; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+template <int W>
+MVIN_DEV float4 cross_group_sum4(float4 v) {
+  v.x = cross_group_sum<W>(v.x);
+  v.y = cross_group_sum<W>(v.y);
+  v.z = cross_group_sum<W>(v.z);
+  v.w = cross_group_sum<W>(v.w);
+  return v;
+}
+
+MVIN_DEV float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+MVIN_DEV float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+MVIN_DEV void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+MVIN_DEV float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+MVIN_DEV float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+MVIN_DEV float4 f4scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+MVIN_DEV float4 f4fma(float s, float4 a, float4 c) {
+  return make_float4(fmaf(s, a.x, c.x), fmaf(s, a.y, c.y), fmaf(s, a.z, c.z), fmaf(s, a.w, c.w));
+}
+MVIN_DEV float f4dot(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+
+// vectorised reduction to global memory: one 16-byte red instead of four scalar atomics (sm_90+)
+MVIN_DEV void red_add4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+}  // namespace mvin

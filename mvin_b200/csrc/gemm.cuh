@@ -1,0 +1,103 @@
+// gemm.cuh -- small generic fp32 SIMT GEMM used for the dense side-maps of the MVIN path
+// (Q = V.RK[r], user_o = O.W_user + b, item = concat.W_mix + b and their backward counterparts).
+// FP32 FFMA on purpose: parity is 1e-4 relative on the final scores versus an fp32 reference, which plain
+// TF32 tensor-core math does not meet (hard part 1).  These maps are < 10 % of the
+// step; the HBM/L2-bound gather kernels in level.cuh / ripple.cuh are the hot part.
+#pragma once
+#include "common.cuh"
+
+namespace mvin {
+
+struct GemmArgs {
+  const float* A;         // A(m,k) = A[rowA(m) * sa_m + k * sa_k + batch * bsA], rowA(m) = a_rows ? a_rows[m] : m
+  long sa_m, sa_k, bsA;
+  const int32_t* a_rows;
+  const float* B;         // B(k,n) = B[k * sb_k + n * sb_n + batch * bsB]
+  long sb_k, sb_n, bsB;
+  float* C;               // C(m,n) = C[rowC(m) * ldc + n + batch * bsC]
+  long ldc, bsC;
+  const int32_t* c_rows;
+  const float* bias;      // [N] or nullptr; added once (k-split 0)
+  int M, N, K;
+  int nbatch, ksplit;
+  int accumulate;         // 1: atomicAdd into C (required when ksplit > 1 or c_rows has duplicates)
+  float alpha;
+};
+
+constexpr int GEMM_BM = 64, GEMM_BN = 64, GEMM_BK = 16, GEMM_THREADS = 256;
+
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(GemmArgs g) {
+  __shared__ float As[GEMM_BK][GEMM_BM + 4];
+  __shared__ float Bs[GEMM_BK][GEMM_BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const int batch = blockIdx.z / g.ksplit, split = blockIdx.z % g.ksplit;
+  const int m0 = blockIdx.y * GEMM_BM, n0 = blockIdx.x * GEMM_BN;
+  int kchunk = (g.K + g.ksplit - 1) / g.ksplit;
+  kchunk = (kchunk + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
+  const int k_begin = split * kchunk;
+  const int k_end = min(g.K, k_begin + kchunk);
+  const float* A = g.A + (long)batch * g.bsA;
+  const float* B = g.B + (long)batch * g.bsB;
+  const bool a_kfast = (g.sa_k == 1), b_nfast = (g.sb_n == 1);
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int kt = k_begin; kt < k_end; kt += GEMM_BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * GEMM_THREADS;
+      int mm, kk;
+      if (a_kfast) { mm = idx / GEMM_BK; kk = idx % GEMM_BK; } else { mm = idx % GEMM_BM; kk = idx / GEMM_BM; }
+      const int m = m0 + mm, k = kt + kk;
+      float v = 0.f;
+      if (m < g.M && k < k_end) {
+        const long row = g.a_rows ? (long)g.a_rows[m] : (long)m;
+        v = A[row * g.sa_m + (long)k * g.sa_k];
+      }
+      As[kk][mm] = v;
+      int nn, kb;
+      if (b_nfast) { nn = idx % GEMM_BN; kb = idx / GEMM_BN; } else { nn = idx / GEMM_BK; kb = idx % GEMM_BK; }
+      const int n = n0 + nn, k2 = kt + kb;
+      float w = 0.f;
+      if (n < g.N && k2 < k_end) w = B[(long)k2 * g.sb_k + (long)n * g.sb_n];
+      Bs[kb][nn] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GEMM_BK; ++kk) {
+      const float4 a = ld4(&As[kk][ty * 4]);
+      const float4 b = ld4(&Bs[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  float* C = g.C + (long)batch * g.bsC;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= g.M) continue;
+    const long row = g.c_rows ? (long)g.c_rows[m] : (long)m;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= g.N) continue;
+      float v = g.alpha * acc[i][j];
+      if (g.bias && split == 0) v += g.bias[n];
+      float* dst = &C[row * g.ldc + n];
+      if (g.accumulate) atomicAdd(dst, v); else *dst = v;
+    }
+  }
+}
+
+}  // namespace mvin
