@@ -1,0 +1,258 @@
+// misc.cuh -- integer neighbour expansion (get_neighbors), score / loss, dense L2 terms, Adam and other small
+// kernels of the MVIN path.  Reference citations are relative to src/model/MVIN/.
+#pragma once
+#include "common.cuh"
+
+namespace mvin {
+
+// ---- adjacency packing: int64 [n_entity, K] x 2 (model.py:7,19-20) -> int32 [n_entity][2][K] -----------
+__global__ void pack_adj_kernel(const int64_t* __restrict__ adjE, const int64_t* __restrict__ adjR, long n_entity,
+                                int K, int32_t* __restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_entity * K) return;
+  const long e = i / K;
+  const int k = (int)(i % K);
+  out[e * 2 * K + k] = (int32_t)adjE[i];
+  out[e * 2 * K + K + k] = (int32_t)adjR[i];
+}
+
+// ---- get_neighbors (model.py:243-256): one level of expansion, child k of node j at j*K+k -------------
+__global__ void expand_kernel(const int32_t* __restrict__ ent, const int32_t* __restrict__ adj, long rows, int K,
+                              int32_t* __restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * K) return;
+  const long j = i / K;
+  const int k = (int)(i % K);
+  out[i] = __ldg(adj + (long)ent[j] * 2 * K + k);
+}
+
+__global__ void expand_i64_kernel(const int64_t* __restrict__ ent, const int32_t* __restrict__ adj, long rows,
+                                  int K, int64_t* __restrict__ out_e, int64_t* __restrict__ out_r) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * K) return;
+  const long j = i / K;
+  const int k = (int)(i % K);
+  const int32_t* rec = adj + ent[j] * 2 * K;
+  out_e[i] = (int64_t)__ldg(rec + k);
+  out_r[i] = (int64_t)__ldg(rec + K + k);
+}
+
+__global__ void copy_i64_kernel(const int64_t* __restrict__ src, long n, int64_t* __restrict__ dst) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+// ---- seeds: ent[0] = item (int32) and Vbuf = E[item]  (model.py:199) -----------------------------------
+template <int D>
+__global__ void prep_items_kernel(const int64_t* __restrict__ item, const float* __restrict__ E, int B,
+                                  int32_t* __restrict__ ent0, float* __restrict__ Vbuf) {
+  constexpr int LPR = D / 4;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)B * LPR) return;
+  const long b = i / LPR;
+  const int c = (int)(i % LPR);
+  const long e = item[b];
+  if (c == 0) ent0[b] = (int32_t)e;
+  st4(Vbuf + b * D + c * 4, ldg4(E + e * D + c * 4));
+}
+
+// ---- relation scores s[i][r] = Rel[r] . urh_weights_i[D:2D]  (aggregators.py:130-133, relation third) --
+__global__ void rel_scores_kernel(const float* __restrict__ Rel, const float* __restrict__ urh, int n_rel, int D,
+                                  int H, float* __restrict__ s) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+  if (w >= H * n_rel) return;
+  const int i = w / n_rel, r = w % n_rel;
+  float acc = 0.f;
+  for (int j = lane; j < D; j += 32) acc += Rel[(long)r * D + j] * urh[(long)i * 3 * D + D + j];
+  acc = warp_sum(acc);
+  if (lane == 0) s[w] = acc;
+}
+
+// dRel[r] += sum_i ds[i][r] w_i ;  durh_i[D:2D] += sum_r ds[i][r] Rel[r]     (one CTA per aggregator i)
+__global__ void rel_scores_bwd_kernel(const float* __restrict__ Rel, const float* __restrict__ urh,
+                                      const float* __restrict__ ds, int n_rel, int D, float* __restrict__ dRel,
+                                      float* __restrict__ durh) {
+  const int i = blockIdx.x;
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    const float wj = urh[(long)i * 3 * D + D + j];
+    float acc = 0.f;
+    for (int r = 0; r < n_rel; ++r) {
+      const float d = ds[i * n_rel + r];
+      acc += d * Rel[(long)r * D + j];
+      atomicAdd(dRel + (long)r * D + j, d * wj);
+    }
+    atomicAdd(durh + (long)i * 3 * D + D + j, acc);
+  }
+}
+
+// ---- score (model.py:158-159) -------------------------------------------------------------------------
+template <int D>
+__global__ void score_kernel(const float* __restrict__ u, const float* __restrict__ item, int B,
+                             float* __restrict__ scores, float* __restrict__ scores_norm) {
+  constexpr int LPR = D / 4;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long b = i / LPR;
+  const int c = (int)(i % LPR);
+  float part = 0.f;
+  if (b < B) part = f4dot(ld4(u + b * D + c * 4), ld4(item + b * D + c * 4));
+  part = group_sum<LPR>(part);
+  if (b < B && c == 0) {
+    if (scores) scores[b] = part;
+    if (scores_norm) scores_norm[b] = 1.f / (1.f + expf(-part));
+  }
+}
+
+// base loss (model.py:379-380) and its gradient: g = (sigmoid(x) - z) / B ; ditem = g u ; du = g item
+template <int D>
+__global__ void loss_bwd_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
+                                const float* __restrict__ u, const float* __restrict__ item, int B,
+                                float* __restrict__ ditem, float* __restrict__ du, float* __restrict__ bce_acc) {
+  constexpr int LPR = D / 4;
+  __shared__ float red;
+  if (threadIdx.x == 0) red = 0.f;
+  __syncthreads();
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long b = i / LPR;
+  const int c = (int)(i % LPR);
+  float bce = 0.f;
+  if (b < B) {
+    const float x = scores[b], z = labels[b];
+    const float gsc = (1.f / (1.f + expf(-x)) - z) / (float)B;
+    st4(ditem + b * D + c * 4, f4scale(ld4(u + b * D + c * 4), gsc));
+    st4(du + b * D + c * 4, f4scale(ld4(item + b * D + c * 4), gsc));
+    if (c == 0) bce = fmaxf(x, 0.f) - x * z + log1pf(expf(-fabsf(x)));
+  }
+  bce = warp_sum(bce);
+  if (threadIdx.x % 32 == 0 && bce != 0.f) atomicAdd(&red, bce);
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(bce_acc, red / (float)B);
+}
+
+// ---- dense L2 terms (model.py:388-410): grad = coef * mult * param (store: this also zero-fills buffers
+// whose coef is 0), loss accumulators += mult * 0.5 * |param|^2 -------------------------------------------
+constexpr int MAX_SEG = 24;
+struct L2Segments {
+  const float* param[MAX_SEG];
+  float* grad[MAX_SEG];
+  long n[MAX_SEG];
+  float coef[MAX_SEG];   // l2_weight or l2_agg_weight (times multiplicity), 0 = no regulariser
+  float mult[MAX_SEG];   // multiplicity in the loss value
+  int which[MAX_SEG];    // 0 -> l2_loss accumulator, 1 -> l2_agg_loss accumulator
+  int count;
+};
+
+__global__ void l2_dense_kernel(L2Segments sg, float* __restrict__ acc /* [1]=l2, [2]=l2_agg */) {
+  __shared__ float red[2];
+  if (threadIdx.x < 2) red[threadIdx.x] = 0.f;
+  __syncthreads();
+  for (int sidx = 0; sidx < sg.count; ++sidx) {
+    const float* p = sg.param[sidx];
+    float* gr = sg.grad[sidx];
+    const float coef = sg.coef[sidx];
+    float sq = 0.f;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < sg.n[sidx]; i += (long)gridDim.x * blockDim.x) {
+      const float v = p[i];
+      gr[i] = coef * v;
+      sq = fmaf(v, v, sq);
+    }
+    if (sg.mult[sidx] != 0.f) {
+      sq = warp_sum(sq);
+      if (threadIdx.x % 32 == 0 && sq != 0.f) atomicAdd(&red[sg.which[sidx]], 0.5f * sg.mult[sidx] * sq);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 && red[threadIdx.x] != 0.f) atomicAdd(acc + 1 + threadIdx.x, red[threadIdx.x]);
+}
+
+// ---- un-normalised L2 over the gathered relation-KGE matrices (model.py:386): sum_r cnt[r] |RK[r]|^2 -----
+__global__ void hist_r_kernel(const int32_t* __restrict__ mem_r, long n, int n_rel, float* __restrict__ cnt) {
+  extern __shared__ float h[];
+  for (int i = threadIdx.x; i < n_rel; i += blockDim.x) h[i] = 0.f;
+  __syncthreads();
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    atomicAdd(&h[mem_r[i]], 1.f);
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_rel; i += blockDim.x)
+    if (h[i] != 0.f) atomicAdd(cnt + i, h[i]);
+}
+
+__global__ void rk_l2_kernel(const float* __restrict__ RK, const float* __restrict__ cnt, int DD, float two_l2,
+                             float* __restrict__ dRK, float* __restrict__ l2_acc) {
+  const int r = blockIdx.x;
+  const float cr = cnt[r];
+  float sq = 0.f;
+  for (int i = threadIdx.x; i < DD; i += blockDim.x) {
+    const float v = RK[(long)r * DD + i];
+    sq = fmaf(v, v, sq);
+    if (cr != 0.f) atomicAdd(dRK + (long)r * DD + i, two_l2 * cr * v);
+  }
+  sq = warp_sum(sq);
+  if (threadIdx.x % 32 == 0 && cr != 0.f) atomicAdd(l2_acc, cr * sq);
+}
+
+// losses_out = {loss, base_loss, l2_loss, l2_agg_loss}  (model.py:412)
+__global__ void finalize_loss_kernel(const float* __restrict__ acc, float l2w, float l2a, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    out[0] = acc[0] + l2w * acc[1] + l2a * acc[2];
+    out[1] = acc[0];
+    out[2] = acc[1];
+    out[3] = acc[2];
+  }
+}
+
+// ---- [nmat, D, D] -> transposed copies -------------------------------------------------------------------
+__global__ void transpose_kernel(const float* __restrict__ src, int D, float* __restrict__ dst) {
+  const float* s = src + (long)blockIdx.x * D * D;
+  float* d = dst + (long)blockIdx.x * D * D;
+  for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
+    const int r = i / D, c = i % D;
+    d[c * D + r] = s[i];
+  }
+}
+
+// ---- importance_list (model.py:319-323): p = softmax_k(s_0[rel_k]) for the nodes of one level ------------
+__global__ void importance_kernel(const int32_t* __restrict__ ent, const int32_t* __restrict__ adj,
+                                  const float* __restrict__ s, long rows, int K, float* __restrict__ probs) {
+  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  const int lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  const int32_t* arow = adj + (long)ent[row] * 2 * K;
+  float l0 = -INFINITY, l1 = -INFINITY;
+  if (lane < K) l0 = s[__ldg(arow + K + lane)];
+  if (lane + 32 < K) l1 = s[__ldg(arow + K + lane + 32)];
+  const float mx = warp_max(fmaxf(l0, l1));
+  const float e0 = lane < K ? expf(l0 - mx) : 0.f;
+  const float e1 = lane + 32 < K ? expf(l1 - mx) : 0.f;
+  const float inv = 1.f / warp_sum(e0 + e1);
+  if (lane < K) probs[row * K + lane] = e0 * inv;
+  if (lane + 32 < K) probs[row * K + lane + 32] = e1 * inv;
+}
+
+// ---- Adam, TF1 semantics (model.py:414): dense over every segment ---------------------------------------
+struct AdamSegments {
+  float* param[MAX_SEG];
+  const float* grad[MAX_SEG];
+  float* m[MAX_SEG];
+  float* v[MAX_SEG];
+  long n[MAX_SEG];
+  int count;
+};
+
+__global__ void adam_kernel(AdamSegments sg, float lr_t, float beta1, float beta2, float eps) {
+  for (int sidx = 0; sidx < sg.count; ++sidx) {
+    float* p = sg.param[sidx];
+    const float* g = sg.grad[sidx];
+    float* m = sg.m[sidx];
+    float* v = sg.v[sidx];
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < sg.n[sidx]; i += (long)gridDim.x * blockDim.x) {
+      const float gi = g[i];
+      const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+      const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+      m[i] = mi;
+      v[i] = vi;
+      p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    }
+  }
+}
+
+}  // namespace mvin

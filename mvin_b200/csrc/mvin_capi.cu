@@ -1,0 +1,767 @@
+// mvin_capi.cu -- libmvin_b200.so: C ABI (include/mvin_b200.h) and the host-side orchestration of the kernels.
+//
+// Forward  = model.py:125-159 of the reference (src/model/MVIN/), backward = TF autodiff of model.py:378-412,
+// Adam = model.py:414.  The factorisation the kernels implement is spelled out in DESIGN.md section 3 and has a
+// CPU twin in tests/fused_model.py.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/mvin_b200.h"
+#include "gemm.cuh"
+#include "level.cuh"
+#include "misc.cuh"
+#include "ripple.cuh"
+
+using namespace mvin;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) return fail(MVIN_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                       __FILE__, __LINE__);                                         \
+  } while (0)
+
+#define LAUNCH_CHECK(h, name)                                                                       \
+  do {                                                                                              \
+    (h)->launches++;                                                                                \
+    cudaError_t _e = cudaGetLastError();                                                            \
+    if (_e != cudaSuccess) return fail(MVIN_ERR_CUDA, "launch %s: %s", name, cudaGetErrorString(_e)); \
+  } while (0)
+
+constexpr int MAX_L = 3;
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Workspace layout for batch size B (all offsets in bytes from the workspace base).
+struct Layout {
+  size_t ent[MAX_L];                      // int32 [B K^h], h < L
+  size_t Vbuf, Q, probs, O, u, s;         // ripple side + relation scores
+  size_t XU[MAX_L], T[MAX_L], SU;         // user-oriented transform
+  size_t Y[MAX_L][MAX_L];                 // Y[i][h], i < H, h < L - i
+  size_t V[MAX_L + 1][MAX_L];             // V[j][h], 1 <= j <= H, h < L - j + 1   (V[0] aliases T)
+  size_t item, scores;
+  // backward
+  size_t dV[MAX_L + 1][MAX_L];            // dV[0][h] = dT[h]
+  size_t GROW, du, ditem, dO, wT;         // wT: [H + L + 1][D][D] transposed weights
+  size_t zero_begin, dQ, ds, cnt, acc, zero_end;   // region cleared at the start of every backward
+  size_t total;
+  long rows[MAX_L + 1];
+};
+
+}  // namespace
+
+struct mvin_handle_s {
+  mvin_config_t cfg;
+  mvin_params_t P, G;
+  bool has_params = false, has_grads = false;
+  const int32_t* adj = nullptr;
+  int device = 0, sm_count = 148;
+  int64_t launches = 0;
+  // batch of the last forward (pointers owned by the caller, must stay valid until backward)
+  const int64_t* user = nullptr;
+  const int64_t* item = nullptr;
+  const int32_t *mem_h = nullptr, *mem_r = nullptr, *mem_t = nullptr;
+  int B = 0;
+  void* fwd_workspace = nullptr;
+};
+
+namespace {
+
+Layout make_layout(const mvin_config_t& c, long B) {
+  Layout L;
+  memset(&L, 0, sizeof(L));
+  const long D = c.dim, K = c.neighbor_sample_size, H = c.h_hop, p = c.p_hop, m = c.n_memory, nr = c.n_relation;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes);
+    return o;
+  };
+  long r = B;
+  for (int h = 0; h <= H; ++h) { L.rows[h] = r; r *= K; }
+  for (int h = 0; h < H; ++h) L.ent[h] = take(sizeof(int32_t) * L.rows[h]);
+  const size_t f = sizeof(float);
+  L.Vbuf = take(f * B * D);
+  L.Q = take(f * B * nr * D);
+  L.probs = take(f * (p + 1) * B * m);
+  L.O = take(f * B * (p + 1) * D);
+  L.u = take(f * B * D);
+  L.s = take(f * H * nr);
+  for (int h = 0; h < H; ++h) { L.XU[h] = take(f * L.rows[h] * D); L.T[h] = take(f * L.rows[h] * D); }
+  L.SU = take(f * L.rows[H - 1] * D);
+  for (int i = 0; i < H; ++i)
+    for (int h = 0; h < H - i; ++h) L.Y[i][h] = take(f * L.rows[h] * D);
+  for (int h = 0; h < H; ++h) L.V[0][h] = L.T[h];
+  for (int j = 1; j <= H; ++j)
+    for (int h = 0; h < H - j + 1; ++h) L.V[j][h] = take(f * L.rows[h] * D);
+  L.item = take(f * B * D);
+  L.scores = take(f * B);
+  for (int j = 0; j <= H; ++j)
+    for (int h = 0; h < (j == 0 ? H : H - j + 1); ++h) L.dV[j][h] = take(f * L.rows[h] * D);
+  L.GROW = take(f * L.rows[H - 1] * D);
+  L.du = take(f * B * D);
+  L.ditem = take(f * B * D);
+  L.dO = take(f * B * (p + 1) * D);
+  L.wT = take(f * (2 * H + 1) * D * D);
+  L.zero_begin = off;
+  L.dQ = take(f * B * nr * D);
+  L.ds = take(f * H * nr);
+  L.cnt = take(f * nr);
+  L.acc = take(f * 8);
+  L.zero_end = off;
+  L.total = off;
+  return L;
+}
+
+template <typename T>
+T* at(void* ws, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(ws) + off); }
+
+int run_gemm(mvin_handle_t h, cudaStream_t st, const GemmArgs& g) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return MVIN_OK;
+  dim3 grid((g.N + GEMM_BN - 1) / GEMM_BN, (g.M + GEMM_BM - 1) / GEMM_BM, g.nbatch * g.ksplit);
+  gemm_kernel<<<grid, GEMM_THREADS, 0, st>>>(g);
+  LAUNCH_CHECK(h, "gemm");
+  return MVIN_OK;
+}
+
+GemmArgs gemm_args() {
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.nbatch = 1;
+  g.ksplit = 1;
+  g.alpha = 1.f;
+  return g;
+}
+
+int pick_ksplit(long K) {
+  long s = K / 512;
+  if (s < 1) s = 1;
+  if (s > 64) s = 64;
+  return (int)s;
+}
+
+template <typename KernelT>
+int set_smem(KernelT k, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail(MVIN_ERR_CUDA, "cudaFuncSetAttribute(%zu B): %s", bytes, cudaGetErrorString(e));
+  }
+  return MVIN_OK;
+}
+
+int tile_grid(mvin_handle_t h, long rows, int per_sm) {
+  long tiles = (rows + 63) / 64;
+  long cap = (long)h->sm_count * per_sm;
+  return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
+}
+
+// CTAs per SM to aim for, from the kernel's shared-memory footprint
+int ctas_per_sm(size_t smem_bytes, int threads) {
+  int by_smem = (int)((220 * 1024) / (smem_bytes + 1024));
+  int by_thr = 2048 / threads;
+  int n = by_smem < by_thr ? by_smem : by_thr;
+  return n < 1 ? 1 : (n > 8 ? 8 : n);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------
+template <int D>
+int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, const int32_t* mem_r,
+                 const int32_t* mem_t, int B, float* scores, float* scores_norm, void* ws, cudaStream_t st) {
+  using C = TC<D>;
+  const mvin_config_t& c = h->cfg;
+  const int K = c.neighbor_sample_size, H = c.h_hop, p = c.p_hop, m = c.n_memory, nr = c.n_relation;
+  const Layout L = make_layout(c, B);
+  const mvin_params_t& P = h->P;
+  int rc;
+
+  // seeds + integer expansion (model.py:243-256); level L ids are never materialised
+  {
+    const long n = (long)B * C::LPR;
+    prep_items_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(item, P.entity_emb, B, at<int32_t>(ws, L.ent[0]),
+                                                                      at<float>(ws, L.Vbuf));
+    LAUNCH_CHECK(h, "prep_items");
+  }
+  for (int lv = 0; lv + 1 < H; ++lv) {
+    const long n = L.rows[lv] * K;
+    expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(at<int32_t>(ws, L.ent[lv]), h->adj, L.rows[lv], K,
+                                                               at<int32_t>(ws, L.ent[lv + 1]));
+    LAUNCH_CHECK(h, "expand");
+  }
+  // Q[b, r, :] = RK[r]^T v_b      (model.py:211-220 refactored)
+  if (p > 0) {
+    GemmArgs g = gemm_args();
+    g.A = at<float>(ws, L.Vbuf); g.sa_m = D; g.sa_k = 1; g.bsA = 0;
+    g.B = P.relation_kge; g.sb_k = D; g.sb_n = 1; g.bsB = (long)D * D;
+    g.C = at<float>(ws, L.Q); g.ldc = (long)nr * D; g.bsC = D;
+    g.M = B; g.N = D; g.K = D; g.nbatch = nr;
+    if ((rc = run_gemm(h, st, g))) return rc;
+  }
+  // ripple attention (model.py:162-229)
+  {
+    RippleArgs a;
+    a.E = P.entity_emb; a.Q = at<float>(ws, L.Q); a.w_hi = P.h_item_w;
+    a.mem_h = mem_h; a.mem_r = mem_r; a.mem_t = mem_t;
+    a.probs = at<float>(ws, L.probs); a.O = at<float>(ws, L.O);
+    a.B = B; a.m = m; a.p = p; a.n_rel = nr;
+    const size_t sm = ripple_smem(m, D);
+    if ((rc = set_smem(ripple_fwd_kernel<D>, sm))) return rc;
+    const long warps = (long)B * (p + 1);
+    ripple_fwd_kernel<D><<<(unsigned)((warps + RIPPLE_NW - 1) / RIPPLE_NW), RIPPLE_NT, sm, st>>>(a);
+    LAUNCH_CHECK(h, "ripple_fwd");
+  }
+  // user_o = O . W_user + b      (model.py:232-234)
+  {
+    GemmArgs g = gemm_args();
+    g.A = at<float>(ws, L.O); g.sa_m = (long)(p + 1) * D; g.sa_k = 1;
+    g.B = P.user_mlp_w; g.sb_k = D; g.sb_n = 1;
+    g.C = at<float>(ws, L.u); g.ldc = D; g.bias = P.user_mlp_b;
+    g.M = B; g.N = D; g.K = (p + 1) * D;
+    if ((rc = run_gemm(h, st, g))) return rc;
+  }
+  // relation scores of every aggregator
+  {
+    const int warps = H * nr;
+    rel_scores_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(P.relation_emb, P.agg_urh_w, nr, D, H,
+                                                               at<float>(ws, L.s));
+    LAUNCH_CHECK(h, "rel_scores");
+  }
+  // user-oriented transform of levels 0..L-1   (model.py:270-283)
+  {
+    const size_t sm = sizeof(float) * (D * D + C::R * C::LD);
+    if ((rc = set_smem(transform_fwd_kernel<D>, sm))) return rc;
+    for (int lv = 0; lv < H; ++lv) {
+      TransformArgs a;
+      a.ent = at<int32_t>(ws, L.ent[lv]); a.E = P.entity_emb; a.u = at<float>(ws, L.u);
+      a.W = P.transfer_w + (long)lv * D * D; a.b = P.transfer_b + (long)lv * D;
+      a.XU = at<float>(ws, L.XU[lv]); a.T = at<float>(ws, L.T[lv]);
+      a.rows = L.rows[lv]; a.rpp = (int)(L.rows[lv] / B);
+      transform_fwd_kernel<D><<<tile_grid(h, a.rows, ctas_per_sm(sm, C::NT)), C::NT, sm, st>>>(a);
+      LAUNCH_CHECK(h, "transform_fwd");
+    }
+  }
+  // aggregation iterations (model.py:286-307)
+  {
+    const size_t sm_leaf = agg_fwd_smem<D, true>(nr), sm_in = agg_fwd_smem<D, false>(nr);
+    if ((rc = set_smem(agg_fwd_kernel<D, true>, sm_leaf))) return rc;
+    if ((rc = set_smem(agg_fwd_kernel<D, false>, sm_in))) return rc;
+    for (int i = 0; i < H; ++i) {
+      for (int lv = 0; lv < H - i; ++lv) {
+        const bool leaf = (i == 0 && lv == H - 1);
+        AggArgs a;
+        memset(&a, 0, sizeof(a));
+        a.ent = at<int32_t>(ws, L.ent[lv]); a.adj = h->adj; a.s = at<float>(ws, L.s) + (long)i * nr;
+        a.self = at<float>(ws, L.V[i][lv]);
+        a.Wa = P.agg_w + (long)i * D * D; a.ba = P.agg_b + (long)i * D;
+        a.Y = at<float>(ws, L.Y[i][lv]); a.V = at<float>(ws, L.V[i + 1][lv]);
+        a.probs = nullptr;
+        a.rows = L.rows[lv]; a.rpp = (int)(L.rows[lv] / B); a.K = K; a.n_rel = nr;
+        if (leaf) {
+          a.E = P.entity_emb; a.u = at<float>(ws, L.u);
+          a.Wt = P.transfer_w + (long)H * D * D; a.bt = P.transfer_b + (long)H * D;
+          a.SU = at<float>(ws, L.SU);
+          agg_fwd_kernel<D, true><<<tile_grid(h, a.rows, ctas_per_sm(sm_leaf, C::NT)), C::NT, sm_leaf, st>>>(a);
+        } else {
+          a.child = at<float>(ws, L.V[i][lv + 1]);
+          agg_fwd_kernel<D, false><<<tile_grid(h, a.rows, ctas_per_sm(sm_in, C::NT)), C::NT, sm_in, st>>>(a);
+        }
+        LAUNCH_CHECK(h, "agg_fwd");
+      }
+    }
+  }
+  // wide&deep mix (model.py:309-315): item = concat(V[0][0] .. V[H][0]) . W_mix + b_mix
+  for (int j = 0; j <= H; ++j) {
+    GemmArgs g = gemm_args();
+    g.A = at<float>(ws, L.V[j][0]); g.sa_m = D; g.sa_k = 1;
+    g.B = P.mix_w + (long)j * D * D; g.sb_k = D; g.sb_n = 1;
+    g.C = at<float>(ws, L.item); g.ldc = D;
+    g.bias = j == 0 ? P.mix_b : nullptr;
+    g.accumulate = j > 0;
+    g.M = B; g.N = D; g.K = D;
+    if ((rc = run_gemm(h, st, g))) return rc;
+  }
+  // score (model.py:158-159)
+  {
+    const long n = (long)B * C::LPR;
+    score_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(at<float>(ws, L.u), at<float>(ws, L.item), B,
+                                                                 at<float>(ws, L.scores), scores_norm);
+    LAUNCH_CHECK(h, "score");
+    if (scores) CUDA_TRY(cudaMemcpyAsync(scores, at<float>(ws, L.scores), sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
+  }
+  return MVIN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------------
+template <int D>
+int launch_dw(mvin_handle_t h, cudaStream_t st, const float* A, long lda, const float* G, long rows, float* dW,
+              float* db) {
+  using C = TC<D>;
+  const size_t sm = sizeof(float) * 2 * C::R * C::LD;
+  int rc;
+  if ((rc = set_smem(dw_kernel<D>, sm))) return rc;
+  long tiles = (rows + C::R - 1) / C::R;
+  int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
+  dw_kernel<D><<<grid, C::NT, sm, st>>>(A, lda, G, rows, dW, db);
+  LAUNCH_CHECK(h, "dw");
+  return MVIN_OK;
+}
+
+template <int D>
+int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out, void* ws, cudaStream_t st) {
+  using C = TC<D>;
+  const mvin_config_t& c = h->cfg;
+  const int K = c.neighbor_sample_size, H = c.h_hop, p = c.p_hop, m = c.n_memory, nr = c.n_relation;
+  const Layout L = make_layout(c, B);
+  const mvin_params_t& P = h->P;
+  const mvin_params_t& G = h->G;
+  const float l2w = c.l2_weight, l2a = c.l2_agg_weight;
+  int rc;
+  float* acc = at<float>(ws, L.acc);
+
+  CUDA_TRY(cudaMemsetAsync(at<char>(ws, L.zero_begin), 0, L.zero_end - L.zero_begin, st));
+  CUDA_TRY(cudaMemsetAsync(G.entity_emb, 0, sizeof(float) * (size_t)c.n_entity * D, st));
+  // dense L2 terms: initialise every other gradient buffer with coef * param (model.py:388-410)
+  {
+    L2Segments sg;
+    memset(&sg, 0, sizeof(sg));
+    int n = 0;
+    auto add = [&](const float* prm, float* grd, long cnt, float coef, float mult, int which) {
+      sg.param[n] = prm; sg.grad[n] = grd; sg.n[n] = cnt; sg.coef[n] = coef * mult; sg.mult[n] = mult; sg.which[n] = which;
+      ++n;
+    };
+    const float pm = p > 0 ? 1.f : 0.f;
+    add(P.user_emb, G.user_emb, (long)c.n_user * D, l2a, 1.f, 1);                 // model.py:392
+    add(P.relation_emb, G.relation_emb, (long)nr * D, l2w, 1.f, 0);               // :388
+    add(P.relation_kge, G.relation_kge, (long)nr * D * D, 0.f, 0.f, 0);
+    add(P.mix_w, G.mix_w, (long)(H + 1) * D * D, l2a, 1.f, 1);                    // :400-401
+    add(P.mix_b, G.mix_b, D, l2a, 1.f, 1);
+    add(P.user_mlp_w, G.user_mlp_w, (long)(p + 1) * D * D, l2w, pm, 0);           // :404
+    add(P.user_mlp_b, G.user_mlp_b, D, l2w, pm, 0);
+    if (H > 0) {
+      add(P.transfer_w, G.transfer_w, (long)H * D * D, l2w, pm, 0);               // :407-408
+      add(P.transfer_b, G.transfer_b, (long)H * D, l2w, pm, 0);
+    }
+    add(P.transfer_w + (long)H * D * D, G.transfer_w + (long)H * D * D, (long)D * D, l2w, 2.f * pm, 0);   // :405 + :408
+    add(P.transfer_b + (long)H * D, G.transfer_b + (long)H * D, D, l2w, 2.f * pm, 0);
+    add(P.h_item_w, G.h_item_w, 2 * D, l2w, 1.f, 0);                              // :410
+    add(P.h_item_b, G.h_item_b, 1, l2w, 1.f, 0);
+    add(P.agg_w, G.agg_w, (long)H * D * D, l2a, 1.f, 1);                          // :394-396
+    add(P.agg_b, G.agg_b, (long)H * D, 0.f, 0.f, 1);
+    add(P.agg_urh_w, G.agg_urh_w, (long)H * 3 * D, l2a, 1.f, 1);
+    add(P.agg_urh_b, G.agg_urh_b, H, 0.f, 0.f, 1);
+    sg.count = n;
+    l2_dense_kernel<<<h->sm_count * 2, 256, 0, st>>>(sg, acc);
+    LAUNCH_CHECK(h, "l2_dense");
+  }
+  // transposed weights: wT[i] = W_a[i]^T (i < H), wT[H + e] = W_t[e]^T (e <= H)
+  float* wT = at<float>(ws, L.wT);
+  transpose_kernel<<<H, 256, 0, st>>>(P.agg_w, D, wT);
+  LAUNCH_CHECK(h, "transpose");
+  transpose_kernel<<<H + 1, 256, 0, st>>>(P.transfer_w, D, wT + (long)H * D * D);
+  LAUNCH_CHECK(h, "transpose");
+
+  float* du = at<float>(ws, L.du);
+  float* ditem = at<float>(ws, L.ditem);
+  {
+    const long n = (long)B * C::LPR;
+    loss_bwd_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(at<float>(ws, L.scores), labels, at<float>(ws, L.u),
+                                                                    at<float>(ws, L.item), B, ditem, du, acc);
+    LAUNCH_CHECK(h, "loss_bwd");
+  }
+  // mix backward
+  for (int j = 0; j <= H; ++j) {
+    if ((rc = launch_dw<D>(h, st, at<float>(ws, L.V[j][0]), D, ditem, B, G.mix_w + (long)j * D * D,
+                           j == 0 ? G.mix_b : nullptr)))
+      return rc;
+    GemmArgs g = gemm_args();
+    g.A = ditem; g.sa_m = D; g.sa_k = 1;
+    g.B = P.mix_w + (long)j * D * D; g.sb_k = 1; g.sb_n = D;      // W_mix[jD + n][k] -> transposed use
+    g.C = at<float>(ws, L.dV[j][0]); g.ldc = D;
+    g.M = B; g.N = D; g.K = D;
+    if ((rc = run_gemm(h, st, g))) return rc;
+  }
+  // aggregation iterations, reversed
+  {
+    const size_t sm_leaf = agg_bwd_smem<D, true>(nr), sm_in = agg_bwd_smem<D, false>(nr);
+    if ((rc = set_smem(agg_bwd_kernel<D, true>, sm_leaf))) return rc;
+    if ((rc = set_smem(agg_bwd_kernel<D, false>, sm_in))) return rc;
+    for (int i = H - 1; i >= 0; --i) {
+      for (int lv = 0; lv < H - i; ++lv) {
+        const bool leaf = (i == 0 && lv == H - 1);
+        AggBwdArgs a;
+        memset(&a, 0, sizeof(a));
+        a.ent = at<int32_t>(ws, L.ent[lv]); a.adj = h->adj; a.s = at<float>(ws, L.s) + (long)i * nr;
+        a.WaT = wT + (long)i * D * D;
+        a.V = at<float>(ws, L.V[i + 1][lv]);
+        a.gout = at<float>(ws, L.dV[i + 1][lv]);
+        a.dself = at<float>(ws, L.dV[i][lv]);
+        a.ds = at<float>(ws, L.ds) + (long)i * nr;
+        a.rows = L.rows[lv]; a.rpp = (int)(L.rows[lv] / B); a.K = K; a.n_rel = nr;
+        a.self_accumulate = 1;   // dV[i][0] was initialised by the mix, dV[i][h>0] by hop h-1's child gradients
+        if (leaf) {
+          a.E = P.entity_emb; a.WtT = wT + (long)(H + H) * D * D;
+          a.GROW = at<float>(ws, L.GROW); a.dE = G.entity_emb; a.du = du;
+          agg_bwd_kernel<D, true><<<tile_grid(h, a.rows, ctas_per_sm(sm_leaf, C::NT)), C::NT, sm_leaf, st>>>(a);
+        } else {
+          a.child = at<float>(ws, L.V[i][lv + 1]);
+          a.dchild = at<float>(ws, L.dV[i][lv + 1]);
+          agg_bwd_kernel<D, false><<<tile_grid(h, a.rows, ctas_per_sm(sm_in, C::NT)), C::NT, sm_in, st>>>(a);
+        }
+        LAUNCH_CHECK(h, "agg_bwd");
+        if ((rc = launch_dw<D>(h, st, at<float>(ws, L.Y[i][lv]), D, a.gout, a.rows, G.agg_w + (long)i * D * D,
+                               G.agg_b + (long)i * D)))
+          return rc;
+        if (leaf &&
+            (rc = launch_dw<D>(h, st, at<float>(ws, L.SU), D, a.GROW, a.rows, G.transfer_w + (long)H * D * D,
+                               G.transfer_b + (long)H * D)))
+          return rc;
+      }
+    }
+  }
+  rel_scores_bwd_kernel<<<H, 128, 0, st>>>(P.relation_emb, P.agg_urh_w, at<float>(ws, L.ds), nr, D, G.relation_emb,
+                                           G.agg_urh_w);
+  LAUNCH_CHECK(h, "rel_scores_bwd");
+  // user-oriented transform backward, levels 0..L-1
+  {
+    const size_t sm = sizeof(float) * (D * D + C::R * C::LD);
+    if ((rc = set_smem(transform_bwd_kernel<D>, sm))) return rc;
+    for (int lv = 0; lv < H; ++lv) {
+      TransformBwdArgs a;
+      a.ent = at<int32_t>(ws, L.ent[lv]); a.dT = at<float>(ws, L.dV[0][lv]);
+      a.WT = wT + (long)(H + lv) * D * D; a.dE = G.entity_emb; a.du = du;
+      a.rows = L.rows[lv]; a.rpp = (int)(L.rows[lv] / B);
+      transform_bwd_kernel<D><<<tile_grid(h, a.rows, ctas_per_sm(sm, C::NT)), C::NT, sm, st>>>(a);
+      LAUNCH_CHECK(h, "transform_bwd");
+      if ((rc = launch_dw<D>(h, st, at<float>(ws, L.XU[lv]), D, a.dT, a.rows, G.transfer_w + (long)lv * D * D,
+                             G.transfer_b + (long)lv * D)))
+        return rc;
+    }
+  }
+  // user_o = O . W_user + b  backward
+  for (int s = 0; s <= p; ++s) {
+    if ((rc = launch_dw<D>(h, st, at<float>(ws, L.O) + (long)s * D, (long)(p + 1) * D, du, B,
+                           G.user_mlp_w + (long)s * D * D, s == 0 ? G.user_mlp_b : nullptr)))
+      return rc;
+  }
+  {
+    GemmArgs g = gemm_args();
+    g.A = du; g.sa_m = D; g.sa_k = 1;
+    g.B = P.user_mlp_w; g.sb_k = 1; g.sb_n = D;
+    g.C = at<float>(ws, L.dO); g.ldc = (long)(p + 1) * D;
+    g.M = B; g.N = (p + 1) * D; g.K = D;
+    if ((rc = run_gemm(h, st, g))) return rc;
+  }
+  // ripple backward
+  {
+    RippleBwdArgs a;
+    a.E = P.entity_emb; a.Q = at<float>(ws, L.Q); a.w_hi = P.h_item_w;
+    a.mem_h = h->mem_h; a.mem_r = h->mem_r; a.mem_t = h->mem_t;
+    a.probs = at<float>(ws, L.probs); a.dO = at<float>(ws, L.dO);
+    a.dE = G.entity_emb; a.dQ = at<float>(ws, L.dQ); a.dw_hi = G.h_item_w; a.l2_acc = acc + 1;
+    a.l2_weight = l2w; a.B = B; a.m = m; a.p = p; a.n_rel = nr;
+    const size_t sm = ripple_smem(m, D);
+    if ((rc = set_smem(ripple_bwd_kernel<D>, sm))) return rc;
+    const long warps = (long)B * (p + 1);
+    ripple_bwd_kernel<D><<<(unsigned)((warps + RIPPLE_NW - 1) / RIPPLE_NW), RIPPLE_NT, sm, st>>>(a);
+    LAUNCH_CHECK(h, "ripple_bwd");
+  }
+  if (p > 0) {
+    const long n = (long)p * B * m;
+    hist_r_kernel<<<h->sm_count, 256, sizeof(float) * nr, st>>>(h->mem_r, n, nr, at<float>(ws, L.cnt));
+    LAUNCH_CHECK(h, "hist_r");
+    rk_l2_kernel<<<nr, 256, 0, st>>>(P.relation_kge, at<float>(ws, L.cnt), D * D, 2.f * l2w, G.relation_kge, acc + 1);
+    LAUNCH_CHECK(h, "rk_l2");
+    // dRK[r][i][j] += sum_b v[b][i] dQ[b][r][j]
+    GemmArgs g = gemm_args();
+    g.A = at<float>(ws, L.Vbuf); g.sa_m = 1; g.sa_k = D; g.bsA = 0;
+    g.B = at<float>(ws, L.dQ); g.sb_k = (long)nr * D; g.sb_n = 1; g.bsB = D;
+    g.C = G.relation_kge; g.ldc = D; g.bsC = (long)D * D;
+    g.M = D; g.N = D; g.K = B; g.nbatch = nr; g.ksplit = pick_ksplit(B); g.accumulate = 1;
+    if ((rc = run_gemm(h, st, g))) return rc;
+    // dE[item_b][i] += sum_r sum_j dQ[b][r][j] RK[r][i][j]
+    GemmArgs g2 = gemm_args();
+    g2.A = at<float>(ws, L.dQ); g2.sa_m = (long)nr * D; g2.sa_k = 1; g2.bsA = D;
+    g2.B = P.relation_kge; g2.sb_k = 1; g2.sb_n = D; g2.bsB = (long)D * D;
+    g2.C = G.entity_emb; g2.ldc = D; g2.bsC = 0; g2.c_rows = at<int32_t>(ws, L.ent[0]);
+    g2.M = B; g2.N = D; g2.K = D; g2.nbatch = nr; g2.accumulate = 1;
+    if ((rc = run_gemm(h, st, g2))) return rc;
+  }
+  finalize_loss_kernel<<<1, 32, 0, st>>>(acc, l2w, l2a, losses_out);
+  LAUNCH_CHECK(h, "finalize_loss");
+  return MVIN_OK;
+}
+
+int check_supported(const mvin_config_t* c) {
+  if (c->flags != MVIN_FLAGS_ALL)
+    return fail(MVIN_ERR_UNSUPPORTED, "only --ablation all (flags 0x1f) is supported, got 0x%x", c->flags);
+  if (c->n_mix_hop != 1) return fail(MVIN_ERR_UNSUPPORTED, "n_mix_hop must be 1, got %d", c->n_mix_hop);
+  if (c->h_hop < 1 || c->h_hop > MAX_L) return fail(MVIN_ERR_UNSUPPORTED, "h_hop must be in 1..3, got %d", c->h_hop);
+  const int d = c->dim;
+  if (!(d == 8 || d == 16 || d == 32 || d == 64 || d == 128))
+    return fail(MVIN_ERR_UNSUPPORTED, "dim must be one of 8,16,32,64,128, got %d", d);
+  if (c->neighbor_sample_size < 1 || c->neighbor_sample_size > MAX_K)
+    return fail(MVIN_ERR_UNSUPPORTED, "neighbor_sample_size must be in 1..64, got %d", c->neighbor_sample_size);
+  if (c->p_hop < 0 || c->p_hop > 8) return fail(MVIN_ERR_UNSUPPORTED, "p_hop must be in 0..8, got %d", c->p_hop);
+  if (c->n_memory < 1 || c->n_memory > 4096)
+    return fail(MVIN_ERR_UNSUPPORTED, "n_memory must be in 1..4096, got %d", c->n_memory);
+  if (c->n_user < 1 || c->n_entity < 1 || c->n_relation < 1 || c->n_relation > 4096)
+    return fail(MVIN_ERR_INVALID, "bad table sizes (n_user %d, n_entity %d, n_relation %d)", c->n_user, c->n_entity,
+                c->n_relation);
+  if (c->max_batch < 1) return fail(MVIN_ERR_INVALID, "max_batch must be >= 1");
+  return MVIN_OK;
+}
+
+#define DISPATCH_D(d, CALL)                                           \
+  switch (d) {                                                        \
+    case 8: { constexpr int DD = 8; return CALL; }                    \
+    case 16: { constexpr int DD = 16; return CALL; }                  \
+    case 32: { constexpr int DD = 32; return CALL; }                  \
+    case 64: { constexpr int DD = 64; return CALL; }                  \
+    case 128: { constexpr int DD = 128; return CALL; }                \
+    default: return fail(MVIN_ERR_UNSUPPORTED, "dim %d", d);          \
+  }
+
+int dispatch_forward(mvin_handle_t h, const int64_t* item, const int32_t* mh, const int32_t* mr, const int32_t* mt,
+                     int B, float* scores, float* sn, void* ws, cudaStream_t st) {
+  DISPATCH_D(h->cfg.dim, (forward_impl<DD>(h, item, mh, mr, mt, B, scores, sn, ws, st)));
+}
+int dispatch_backward(mvin_handle_t h, const float* labels, int B, float* losses, void* ws, cudaStream_t st) {
+  DISPATCH_D(h->cfg.dim, (backward_impl<DD>(h, labels, B, losses, ws, st)));
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int mvin_abi_version(void) { return MVIN_ABI_VERSION; }
+const char* mvin_last_error(void) { return g_err; }
+
+int mvin_create(const mvin_config_t* cfg, mvin_handle_t* out) {
+  if (!cfg || !out) return fail(MVIN_ERR_INVALID, "null argument");
+  int rc = check_supported(cfg);
+  if (rc) return rc;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major < 10)
+    return fail(MVIN_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major,
+                prop.minor);
+  mvin_handle_t h = new mvin_handle_s();
+  h->cfg = *cfg;
+  h->device = dev;
+  h->sm_count = prop.multiProcessorCount;
+  *out = h;
+  return MVIN_OK;
+}
+
+int mvin_destroy(mvin_handle_t h) {
+  delete h;
+  return MVIN_OK;
+}
+
+int mvin_bind_params(mvin_handle_t h, const mvin_params_t* params) {
+  if (!h || !params) return fail(MVIN_ERR_INVALID, "null argument");
+  h->P = *params;
+  h->has_params = true;
+  return MVIN_OK;
+}
+int mvin_bind_grads(mvin_handle_t h, const mvin_params_t* grads) {
+  if (!h || !grads) return fail(MVIN_ERR_INVALID, "null argument");
+  h->G = *grads;
+  h->has_grads = true;
+  return MVIN_OK;
+}
+int mvin_bind_adjacency(mvin_handle_t h, const int32_t* adj_packed) {
+  if (!h || !adj_packed) return fail(MVIN_ERR_INVALID, "null argument");
+  h->adj = adj_packed;
+  return MVIN_OK;
+}
+
+int mvin_pack_adjacency(const int64_t* adj_entity, const int64_t* adj_relation, int32_t n_entity, int32_t K,
+                        int32_t* adj_packed, void* stream) {
+  if (!adj_entity || !adj_relation || !adj_packed || n_entity < 1 || K < 1) return fail(MVIN_ERR_INVALID, "bad argument");
+  const long n = (long)n_entity * K;
+  pack_adj_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(adj_entity, adj_relation, n_entity, K,
+                                                                                adj_packed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MVIN_ERR_CUDA, "launch pack_adj: %s", cudaGetErrorString(e));
+  return MVIN_OK;
+}
+
+size_t mvin_workspace_bytes(mvin_handle_t h, int32_t B) {
+  if (!h || B < 1) return 0;
+  return make_layout(h->cfg, B).total;
+}
+
+int mvin_get_neighbors(mvin_handle_t h, const int64_t* item_indices, int32_t B, int32_t n_levels,
+                       int64_t* const* entities, int64_t* const* relations, void* stream) {
+  if (!h || !item_indices || !entities || (n_levels > 0 && !relations) || B < 1 || n_levels < 0)
+    return fail(MVIN_ERR_INVALID, "bad argument");
+  if (!h->adj) return fail(MVIN_ERR_STATE, "adjacency not bound");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int K = h->cfg.neighbor_sample_size;
+  copy_i64_kernel<<<(B + 255) / 256, 256, 0, st>>>(item_indices, B, entities[0]);
+  LAUNCH_CHECK(h, "copy_i64");
+  long rows = B;
+  for (int i = 0; i < n_levels; ++i) {
+    const long n = rows * K;
+    expand_i64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(entities[i], h->adj, rows, K, entities[i + 1],
+                                                                   relations[i]);
+    LAUNCH_CHECK(h, "expand_i64");
+    rows = n;
+  }
+  return MVIN_OK;
+}
+
+int mvin_forward(mvin_handle_t h, const int64_t* user_indices, const int64_t* item_indices, const int32_t* mem_h,
+                 const int32_t* mem_r, const int32_t* mem_t, int32_t B, float* scores, float* scores_normalized,
+                 void* workspace, void* stream) {
+  if (!h || !item_indices || !mem_h || !mem_r || !mem_t || !workspace) return fail(MVIN_ERR_INVALID, "null argument");
+  if (B < 1 || B > h->cfg.max_batch) return fail(MVIN_ERR_INVALID, "B = %d outside 1..max_batch (%d)", B, h->cfg.max_batch);
+  if (!h->has_params || !h->adj) return fail(MVIN_ERR_STATE, "parameters / adjacency not bound");
+  h->user = user_indices;   // inert under --ablation all; kept for the feed contract
+  h->item = item_indices;
+  h->mem_h = mem_h; h->mem_r = mem_r; h->mem_t = mem_t;
+  h->B = B;
+  h->fwd_workspace = workspace;
+  return dispatch_forward(h, item_indices, mem_h, mem_r, mem_t, B, scores, scores_normalized, workspace,
+                          (cudaStream_t)stream);
+}
+
+int mvin_importance(mvin_handle_t h, float* imp0, float* imp1, void* workspace, void* stream) {
+  if (!h || !imp0 || !workspace) return fail(MVIN_ERR_INVALID, "null argument");
+  if (h->fwd_workspace != workspace || h->B < 1) return fail(MVIN_ERR_STATE, "no forward pass on this workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Layout L = make_layout(h->cfg, h->B);
+  const int K = h->cfg.neighbor_sample_size;
+  float* outs[2] = {imp0, imp1};
+  for (int lv = 0; lv < 2 && lv < h->cfg.h_hop; ++lv) {
+    if (!outs[lv]) continue;
+    const long rows = L.rows[lv];
+    importance_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(at<int32_t>(workspace, L.ent[lv]), h->adj,
+                                                                           at<float>(workspace, L.s), rows, K, outs[lv]);
+    LAUNCH_CHECK(h, "importance");
+  }
+  return MVIN_OK;
+}
+
+int mvin_backward(mvin_handle_t h, const float* labels, int32_t B, float* losses_out, void* workspace, void* stream) {
+  if (!h || !labels || !losses_out || !workspace) return fail(MVIN_ERR_INVALID, "null argument");
+  if (!h->has_grads) return fail(MVIN_ERR_STATE, "gradient buffers not bound");
+  if (h->fwd_workspace != workspace || h->B != B)
+    return fail(MVIN_ERR_STATE, "mvin_backward must follow mvin_forward on the same workspace and batch size");
+  return dispatch_backward(h, labels, B, losses_out, workspace, (cudaStream_t)stream);
+}
+
+int mvin_adam_step(mvin_handle_t h, const mvin_params_t* m, const mvin_params_t* v, float lr, float beta1, float beta2,
+                   float eps, int32_t step, void* stream) {
+  if (!h || !m || !v || step < 1) return fail(MVIN_ERR_INVALID, "bad argument");
+  if (!h->has_params || !h->has_grads) return fail(MVIN_ERR_STATE, "parameters / gradients not bound");
+  const mvin_config_t& c = h->cfg;
+  const long D = c.dim, H = c.h_hop, p = c.p_hop, nr = c.n_relation;
+  AdamSegments sg;
+  memset(&sg, 0, sizeof(sg));
+  int n = 0;
+  auto add = [&](float* prm, const float* grd, float* mm, float* vv, long cnt) {
+    sg.param[n] = prm; sg.grad[n] = grd; sg.m[n] = mm; sg.v[n] = vv; sg.n[n] = cnt;
+    ++n;
+  };
+#define SEG(field, cnt) add(h->P.field, h->G.field, m->field, v->field, (cnt))
+  SEG(user_emb, (long)c.n_user * D);
+  SEG(entity_emb, (long)c.n_entity * D);
+  SEG(relation_emb, nr * D);
+  SEG(relation_kge, nr * D * D);
+  SEG(mix_w, (H + 1) * D * D);
+  SEG(mix_b, D);
+  SEG(user_mlp_w, (p + 1) * D * D);
+  SEG(user_mlp_b, D);
+  SEG(transfer_w, (H + 1) * D * D);
+  SEG(transfer_b, (H + 1) * D);
+  SEG(h_item_w, 2 * D);
+  SEG(h_item_b, 1);
+  SEG(agg_w, H * D * D);
+  SEG(agg_b, H * D);
+  SEG(agg_urh_w, H * 3 * D);
+  SEG(agg_urh_b, H);
+#undef SEG
+  sg.count = n;
+  const float lr_t = (float)((double)lr * std::sqrt(1.0 - std::pow((double)beta2, step)) /
+                             (1.0 - std::pow((double)beta1, step)));
+  adam_kernel<<<h->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(sg, lr_t, beta1, beta2, eps);
+  LAUNCH_CHECK(h, "adam");
+  return MVIN_OK;
+}
+
+size_t mvin_feed_bytes(mvin_handle_t h, int32_t B) {
+  if (!h || B < 1) return 0;
+  const size_t pm = (size_t)(h->cfg.p_hop > 0 ? h->cfg.p_hop : 1) * B * h->cfg.n_memory;
+  return align_up(sizeof(int64_t) * B) * 2 + align_up(sizeof(float) * B) + 3 * align_up(sizeof(int32_t) * pm) +
+         align_up(sizeof(float) * 4);
+}
+
+int mvin_train_step_host(mvin_handle_t h, const int64_t* user_indices, const int64_t* item_indices, const float* labels,
+                         const int32_t* mem_h, const int32_t* mem_r, const int32_t* mem_t, int32_t B, void* staging,
+                         void* workspace, const mvin_params_t* adam_m, const mvin_params_t* adam_v, float lr, int32_t step,
+                         float* losses_host, void* stream) {
+  if (!h || !user_indices || !item_indices || !labels || !mem_h || !mem_r || !mem_t || !staging || !workspace ||
+      !losses_host)
+    return fail(MVIN_ERR_INVALID, "null argument");
+  if (B < 1 || B > h->cfg.max_batch) return fail(MVIN_ERR_INVALID, "B = %d outside 1..max_batch (%d)", B, h->cfg.max_batch);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t pm = (size_t)(h->cfg.p_hop > 0 ? h->cfg.p_hop : 1) * B * h->cfg.n_memory;
+  char* base = static_cast<char*>(staging);
+  size_t off = 0;
+  auto stage = [&](const void* src, size_t bytes) -> void* {
+    void* dst = base + off;
+    off += align_up(bytes);
+    cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+    return dst;
+  };
+  const int64_t* d_user = (const int64_t*)stage(user_indices, sizeof(int64_t) * B);
+  const int64_t* d_item = (const int64_t*)stage(item_indices, sizeof(int64_t) * B);
+  const float* d_lab = (const float*)stage(labels, sizeof(float) * B);
+  const int32_t* d_mh = (const int32_t*)stage(mem_h, sizeof(int32_t) * pm);
+  const int32_t* d_mr = (const int32_t*)stage(mem_r, sizeof(int32_t) * pm);
+  const int32_t* d_mt = (const int32_t*)stage(mem_t, sizeof(int32_t) * pm);
+  float* d_loss = (float*)(base + off);
+  CUDA_TRY(cudaGetLastError());
+  int rc = mvin_forward(h, d_user, d_item, d_mh, d_mr, d_mt, B, nullptr, nullptr, workspace, stream);
+  if (rc) return rc;
+  rc = mvin_backward(h, d_lab, B, d_loss, workspace, stream);
+  if (rc) return rc;
+  if (adam_m && adam_v) {
+    rc = mvin_adam_step(h, adam_m, adam_v, lr, 0.9f, 0.999f, 1e-8f, step, stream);
+    if (rc) return rc;
+  }
+  CUDA_TRY(cudaMemcpyAsync(losses_host, d_loss, sizeof(float) * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return MVIN_OK;
+}
+
+int64_t mvin_launch_count(mvin_handle_t h) { return h ? h->launches : 0; }
+
+}  // extern "C"

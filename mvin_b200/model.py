@@ -1,0 +1,408 @@
+"""Python face of the drop-in: the reference's `MVIN` class API on top of libmvin_b200.so.
+
+Mirrors src/model/MVIN/model.py of the reference:
+  ctor            MVIN(args, n_user, n_entity, n_relation, adj_entity, adj_relation)      model.py:7
+  feed keys       model.user_indices / item_indices / labels, model.memories_{h,r,t}[hop]  model.py:49-64
+  train           -> (None, loss), one Adam step                                           model.py:416-417
+  eval            -> (auc, acc, f1)                                                        model.py:419-426
+  eval_case_study -> 7-tuple                                                               model.py:428-441
+  get_scores      -> (item_indices, scores_normalized)                                     model.py:443-444
+  save_pretrain_emb_fuc                                                                    model.py:66-67
+
+`sess` arguments are accepted and ignored (there is no TF session).  torch tensors are used only as device
+buffers whose `.data_ptr()` goes through the C ABI.  There is no CPU fallback: without a CUDA device or the
+built library every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Config, Params, PARAM_FIELDS, check
+
+
+class _Placeholder:
+    """Stand-in for tf.placeholder: only used as a feed-dict key (train.py:113-120)."""
+
+    def __init__(self, name, dtype, shape):
+        self.name, self.dtype, self.shape = name, dtype, shape
+
+    def __repr__(self):
+        return f"<placeholder {self.name} {self.dtype} {self.shape}>"
+
+
+def _flag(args, name, default):
+    return bool(getattr(args, name, default))
+
+
+def flags_from_args(args) -> int:
+    bits = [("User_orient", 1), ("User_orient_rela", 1), ("User_orient_kg_eh", 1), ("PS_O_ft", 1), ("wide_deep", 1),
+            ("PS_only", 0), ("HO_only", 0)]
+    f = 0
+    for i, (name, dflt) in enumerate(bits):
+        if _flag(args, name, dflt):
+            f |= 1 << i
+    return f
+
+
+class MVIN(object):
+    def __init__(self, args, n_user, n_entity, n_relation, adj_entity, adj_relation, device=None, seed: int = 1):
+        if not torch.cuda.is_available():
+            raise RuntimeError("mvin_b200.MVIN needs a CUDA device (sm_100a); there is no CPU path")
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self._parse_args(args, adj_entity, adj_relation)
+        self.n_user, self.n_entity, self.n_relation = int(n_user), int(n_entity), int(n_relation)
+        self._build_inputs()
+        with torch.cuda.device(self.device):
+            self._create_handle()
+            self._build_model(seed)
+            self._build_train()
+        if getattr(args, "load_pretrain_emb", False):
+            self.load_pretrain_emb_fuc()
+
+    # ------------------------------------------------------------------ model.py:17-47
+    def _parse_args(self, args, adj_entity, adj_relation):
+        self.args = args
+        self.dataset = getattr(args, "dataset", None)
+        self.load_pretrain_emb = getattr(args, "load_pretrain_emb", False)
+        self.h_hop = int(args.h_hop)
+        self.batch_size = int(args.batch_size)
+        self.n_neighbor = int(args.neighbor_sample_size)
+        self.p_hop = int(args.p_hop)
+        self.dim = int(args.dim)
+        self.l2_weight = float(args.l2_weight)
+        self.l2_agg_weight = float(args.l2_agg_weight)
+        self.kge_weight = getattr(args, "kge_weight", None)
+        self.lr = float(args.lr)
+        self.save_model_name = getattr(args, "save_model_name", "mvin")
+        self.n_mix_hop = int(getattr(args, "n_mix_hop", 1))
+        self.n_memory = int(args.n_memory)
+        self.path = getattr(args, "path", None)
+        self.flags = flags_from_args(args)
+        adj_entity = np.ascontiguousarray(adj_entity, dtype=np.int64)
+        adj_relation = np.ascontiguousarray(adj_relation, dtype=np.int64)
+        if adj_entity.shape != adj_relation.shape or adj_entity.ndim != 2 or adj_entity.shape[1] != self.n_neighbor:
+            raise ValueError(f"adj_entity / adj_relation must be int64 [n_entity, {self.n_neighbor}]")
+        self.adj_entity, self.adj_relation = adj_entity, adj_relation
+
+    # ------------------------------------------------------------------ model.py:49-64
+    def _build_inputs(self):
+        self.user_indices = _Placeholder("user_indices", np.int64, [None])
+        self.item_indices = _Placeholder("item_indices", np.int64, [None])
+        self.labels = _Placeholder("labels", np.float32, [None])
+        self.memories_h, self.memories_r, self.memories_t = [], [], []
+        for hop in range(max(1, self.p_hop)):
+            self.memories_h.append(_Placeholder(f"memories_h_{hop}", np.int32, [None, self.n_memory]))
+            self.memories_r.append(_Placeholder(f"memories_r_{hop}", np.int32, [None, self.n_memory]))
+            self.memories_t.append(_Placeholder(f"memories_t_{hop}", np.int32, [None, self.n_memory]))
+
+    def _create_handle(self):
+        cfg = Config(dim=self.dim, neighbor_sample_size=self.n_neighbor, h_hop=self.h_hop, n_mix_hop=self.n_mix_hop,
+                     p_hop=self.p_hop, n_memory=self.n_memory, n_user=self.n_user, n_entity=self.n_entity,
+                     n_relation=self.n_relation, max_batch=self.batch_size, l2_weight=self.l2_weight,
+                     l2_agg_weight=self.l2_agg_weight, flags=self.flags)
+        self._handle = C.c_void_p()
+        check(self.lib.mvin_create(C.byref(cfg), C.byref(self._handle)), "mvin_create")
+
+    # ------------------------------------------------------------------ model.py:69-122, aggregators.py:83-93
+    def param_shapes(self) -> Dict[str, tuple]:
+        d, H, p = self.dim, self.h_hop, self.p_hop
+        return {"user_emb": (self.n_user, d), "entity_emb": (self.n_entity, d), "relation_emb": (self.n_relation, d),
+                "relation_kge": (self.n_relation, d, d), "mix_w": ((H + 1) * d, d), "mix_b": (d,),
+                "user_mlp_w": ((p + 1) * d, d), "user_mlp_b": (d,), "transfer_w": (H + 1, d, d),
+                "transfer_b": (H + 1, d), "h_item_w": (2 * d,), "h_item_b": (1,), "agg_w": (H, d, d),
+                "agg_b": (H, d), "agg_urh_w": (H, 3 * d), "agg_urh_b": (H,)}
+
+    @staticmethod
+    def _xavier(shape, gen, fan=None):
+        """tf.contrib.layers.xavier_initializer (model.py:14-15): uniform(+-sqrt(6 / (fan_in + fan_out)))."""
+        if fan is None:
+            if len(shape) == 1:
+                fan = (shape[0], shape[0])
+            elif len(shape) == 2:
+                fan = (shape[0], shape[1])
+            else:
+                rec = int(np.prod(shape[:-2]))
+                fan = (shape[-2] * rec, shape[-1] * rec)
+        limit = math.sqrt(6.0 / (fan[0] + fan[1]))
+        return (torch.rand(shape, generator=gen, dtype=torch.float32) * 2 - 1) * limit
+
+    def _build_model(self, seed):
+        d, H, p = self.dim, self.h_hop, self.p_hop
+        gen = torch.Generator().manual_seed(seed)
+        shapes = self.param_shapes()
+        host = {}
+        for name, shape in shapes.items():
+            if name in ("agg_b", "agg_urh_b"):                     # aggregators.py:87,93 zero-init
+                host[name] = torch.zeros(shape)
+            elif name in ("transfer_w", "agg_w"):                  # stacks of [d, d] matrices
+                host[name] = torch.stack([self._xavier((d, d), gen) for _ in range(shape[0])])
+            elif name in ("transfer_b",):
+                host[name] = torch.stack([self._xavier((d,), gen) for _ in range(shape[0])])
+            elif name == "agg_urh_w":                              # [3d, 1] each
+                host[name] = torch.stack([self._xavier((3 * d,), gen, fan=(3 * d, 1)) for _ in range(shape[0])])
+            elif name == "h_item_w":                               # [2d, 1]
+                host[name] = self._xavier((2 * d,), gen, fan=(2 * d, 1))
+            else:
+                host[name] = self._xavier(shape, gen)
+        self.params = {k: v.to(self.device).contiguous() for k, v in host.items()}
+        self.grads = {k: torch.zeros_like(v) for k, v in self.params.items()}
+        self.adam_m = {k: torch.zeros_like(v) for k, v in self.params.items()}
+        self.adam_v = {k: torch.zeros_like(v) for k, v in self.params.items()}
+        self._p_struct = self._make_struct(self.params)
+        self._g_struct = self._make_struct(self.grads)
+        self._m_struct = self._make_struct(self.adam_m)
+        self._v_struct = self._make_struct(self.adam_v)
+        check(self.lib.mvin_bind_params(self._handle, C.byref(self._p_struct)), "mvin_bind_params")
+        check(self.lib.mvin_bind_grads(self._handle, C.byref(self._g_struct)), "mvin_bind_grads")
+        # packed adjacency
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        adj_e = torch.from_numpy(self.adj_entity).to(self.device)
+        adj_r = torch.from_numpy(self.adj_relation).to(self.device)
+        self.adj_packed = torch.empty((self.n_entity, 2, self.n_neighbor), dtype=torch.int32, device=self.device)
+        check(self.lib.mvin_pack_adjacency(adj_e.data_ptr(), adj_r.data_ptr(), self.n_entity, self.n_neighbor,
+                                           self.adj_packed.data_ptr(), stream), "mvin_pack_adjacency")
+        check(self.lib.mvin_bind_adjacency(self._handle, self.adj_packed.data_ptr()), "mvin_bind_adjacency")
+        torch.cuda.synchronize(self.device)
+        del adj_e, adj_r
+        self._workspace: Optional[torch.Tensor] = None
+        self._workspace_B = 0
+        self._staging: Optional[torch.Tensor] = None
+        self._dev_feed = None
+
+    @staticmethod
+    def _make_struct(tensors) -> Params:
+        s = Params()
+        for f in PARAM_FIELDS:
+            setattr(s, f, tensors[f].data_ptr())
+        return s
+
+    def _build_train(self):
+        self.step = 0
+        self._losses_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self._losses_dev = torch.zeros(4, dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------ buffers
+    def _ensure_workspace(self, B):
+        if self._workspace is None or self._workspace_B != B:
+            nbytes = self.lib.mvin_workspace_bytes(self._handle, B)
+            if nbytes == 0:
+                raise _lib.MvinError("mvin_workspace_bytes returned 0")
+            self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._staging = torch.empty(self.lib.mvin_feed_bytes(self._handle, B), dtype=torch.uint8, device=self.device)
+            self._workspace_B = B
+        return self._workspace
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ------------------------------------------------------------------ feed handling (train.py:112-122)
+    def _host_feed(self, feed_dict):
+        users = np.ascontiguousarray(np.asarray(feed_dict[self.user_indices]), dtype=np.int64)
+        items = np.ascontiguousarray(np.asarray(feed_dict[self.item_indices]), dtype=np.int64)
+        B = items.shape[0]
+        labels = feed_dict.get(self.labels)
+        labels = (np.zeros(B, dtype=np.float32) if labels is None
+                  else np.ascontiguousarray(np.asarray(labels), dtype=np.float32))
+        n_mem = max(1, self.p_hop)
+        stack = lambda keys: np.ascontiguousarray(
+            np.stack([np.asarray(feed_dict[k], dtype=np.int32).reshape(B, self.n_memory) for k in keys]))
+        mem_h, mem_r, mem_t = stack(self.memories_h[:n_mem]), stack(self.memories_r[:n_mem]), stack(self.memories_t[:n_mem])
+        if B > self.batch_size:
+            raise ValueError(f"batch of {B} exceeds args.batch_size = {self.batch_size} (static in the reference graph)")
+        return users, items, labels, mem_h, mem_r, mem_t
+
+    def _device_feed(self, feed_dict):
+        users, items, labels, mem_h, mem_r, mem_t = self._host_feed(feed_dict)
+        to = lambda a: torch.from_numpy(a).to(self.device, non_blocking=False)
+        self._dev_feed = tuple(to(a) for a in (users, items, labels, mem_h, mem_r, mem_t))   # keep alive for backward
+        return (users, items, labels) + self._dev_feed
+
+    # ------------------------------------------------------------------ device-resident entry points
+    def forward_device(self, users, items, mem_h, mem_r, mem_t, scores=None, scores_normalized=None):
+        """users/items int64 [B], mem_* int32 [max(1,p), B, m] -- torch CUDA tensors.  Enqueues the forward pass."""
+        B = items.shape[0]
+        ws = self._ensure_workspace(B)
+        self._keepalive = (users, items, mem_h, mem_r, mem_t)     # the library reads them again in backward
+        check(self.lib.mvin_forward(self._handle, users.data_ptr(), items.data_ptr(), mem_h.data_ptr(), mem_r.data_ptr(),
+                                    mem_t.data_ptr(), B, scores.data_ptr() if scores is not None else None,
+                                    scores_normalized.data_ptr() if scores_normalized is not None else None,
+                                    ws.data_ptr(), self._stream()), "mvin_forward")
+
+    def backward_device(self, labels, losses=None):
+        """labels float32 [B] CUDA tensor; fills self.grads and `losses` (4 floats: loss, base, l2, l2_agg)."""
+        losses = self._losses_dev if losses is None else losses
+        check(self.lib.mvin_backward(self._handle, labels.data_ptr(), labels.shape[0], losses.data_ptr(),
+                                     self._workspace.data_ptr(), self._stream()), "mvin_backward")
+        return losses
+
+    def adam_step_device(self):
+        self.step += 1
+        check(self.lib.mvin_adam_step(self._handle, C.byref(self._m_struct), C.byref(self._v_struct), self.lr, 0.9,
+                                      0.999, 1e-8, self.step, self._stream()), "mvin_adam_step")
+
+    def train_step_host(self, users, items, labels, mem_h, mem_r, mem_t, apply_adam=True):
+        """One fwd+bwd(+Adam) step from HOST numpy / pinned buffers through mvin_train_step_host (feed H2D copy and
+        loss D2H inside).  Returns the 4 losses as a numpy array."""
+        B = items.shape[0]
+        ws = self._ensure_workspace(B)
+        ptr = lambda a: a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr()
+        if apply_adam:
+            self.step += 1
+        check(self.lib.mvin_train_step_host(
+            self._handle, ptr(users), ptr(items), ptr(labels), ptr(mem_h), ptr(mem_r), ptr(mem_t), B,
+            self._staging.data_ptr(), ws.data_ptr(), C.byref(self._m_struct) if apply_adam else None,
+            C.byref(self._v_struct) if apply_adam else None, self.lr, max(self.step, 1), self._losses_host.data_ptr(),
+            self._stream()), "mvin_train_step_host")
+        return self._losses_host.numpy().copy()
+
+    # ------------------------------------------------------------------ reference API (model.py:416-444)
+    def train(self, sess, feed_dict):
+        users, items, labels, mem_h, mem_r, mem_t = self._host_feed(feed_dict)
+        losses = self.train_step_host(users, items, labels, mem_h, mem_r, mem_t, apply_adam=True)
+        return None, float(losses[0])
+
+    def loss_and_grads(self, feed_dict):
+        """Forward + backward without the optimiser step: returns (losses[4], scores) and leaves self.grads filled."""
+        users, items, labels, mem_h, mem_r, mem_t = self._host_feed(feed_dict)
+        losses = self.train_step_host(users, items, labels, mem_h, mem_r, mem_t, apply_adam=False)
+        return losses
+
+    def _scores(self, feed_dict):
+        _, items, labels, d_users, d_items, d_labels, d_mh, d_mr, d_mt = self._device_feed(feed_dict)
+        B = items.shape[0]
+        scores = torch.empty(B, dtype=torch.float32, device=self.device)
+        scores_n = torch.empty(B, dtype=torch.float32, device=self.device)
+        self.forward_device(d_users, d_items, d_mh, d_mr, d_mt, scores, scores_n)
+        torch.cuda.synchronize(self.device)
+        return items, labels, scores.cpu().numpy(), scores_n.cpu().numpy()
+
+    def eval(self, sess, feed_dict):
+        from sklearn.metrics import f1_score, roc_auc_score
+        _, labels, _, scores = self._scores(feed_dict)
+        auc = roc_auc_score(y_true=labels, y_score=scores)
+        scores[scores >= 0.5] = 1
+        scores[scores < 0.5] = 0
+        f1 = f1_score(y_true=labels, y_pred=scores)
+        acc = np.mean(np.equal(scores, labels))
+        return auc, acc, f1
+
+    def get_scores(self, sess, feed_dict):
+        items, _, _, scores_n = self._scores(feed_dict)
+        return [items, scores_n]
+
+    def get_raw_scores(self, feed_dict):
+        _, _, scores, _ = self._scores(feed_dict)
+        return scores
+
+    def get_neighbors(self, items) -> (List[np.ndarray], List[np.ndarray]):
+        """model.py:243-256 on the device; returns (entities[0..L], relations[0..L-1]) as int64 numpy arrays."""
+        items = np.ascontiguousarray(items, dtype=np.int64)
+        B, K, L = items.shape[0], self.n_neighbor, self.h_hop * self.n_mix_hop
+        d_items = torch.from_numpy(items).to(self.device)
+        ents = [torch.empty((B, K ** i), dtype=torch.int64, device=self.device) for i in range(L + 1)]
+        rels = [torch.empty((B, K ** (i + 1)), dtype=torch.int64, device=self.device) for i in range(L)]
+        e_ptrs = (C.c_void_p * (L + 1))(*[t.data_ptr() for t in ents])
+        r_ptrs = (C.c_void_p * max(L, 1))(*[t.data_ptr() for t in rels])
+        check(self.lib.mvin_get_neighbors(self._handle, d_items.data_ptr(), B, L, e_ptrs, r_ptrs, self._stream()),
+              "mvin_get_neighbors")
+        torch.cuda.synchronize(self.device)
+        return [t.cpu().numpy() for t in ents], [t.cpu().numpy() for t in rels]
+
+    def eval_case_study(self, sess, feed_dict):
+        users = np.asarray(feed_dict[self.user_indices])
+        items, labels, _, _ = self._scores(feed_dict)
+        B, K = items.shape[0], self.n_neighbor
+        imp0 = torch.empty((B, 1, K), dtype=torch.float32, device=self.device)
+        imp1 = torch.empty((B, K, K), dtype=torch.float32, device=self.device) if self.h_hop > 1 else None
+        check(self.lib.mvin_importance(self._handle, imp0.data_ptr(), imp1.data_ptr() if imp1 is not None else None,
+                                       self._workspace.data_ptr(), self._stream()), "mvin_importance")
+        entities_data, relations_data = self.get_neighbors(items)
+        torch.cuda.synchronize(self.device)
+        return (users, labels, items, entities_data, relations_data, imp0.cpu().numpy(),
+                imp1.cpu().numpy() if imp1 is not None else None)
+
+    # ------------------------------------------------------------------ checkpoint of the four STWS tables
+    def _emb_path(self):
+        base = getattr(getattr(self.args, "path", None), "emb", None)
+        if base is None:
+            raise ValueError("args.path.emb is not set")
+        return f"{base}_sw_para_{self.save_model_name}_parameter.npz"
+
+    def save_pretrain_emb_fuc(self, sess=None, saver=None):
+        """model.py:66-67 / train.py:43-54: persists the user, entity, relation and relation-KGE tables."""
+        path = self._emb_path()
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        np.savez(path, **{k: self.params[k].cpu().numpy() for k in ("user_emb", "entity_emb", "relation_emb",
+                                                                    "relation_kge")})
+
+    def load_pretrain_emb_fuc(self):
+        z = np.load(self._emb_path())
+        for k in ("user_emb", "entity_emb", "relation_emb", "relation_kge"):
+            self.params[k].copy_(torch.from_numpy(z[k]))
+
+    # ------------------------------------------------------------------ test / interop helpers
+    # oracle (reference attribute) name -> (field, index or None)
+    def _name_map(self):
+        H = self.h_hop
+        mp = {"user_emb_matrix": ("user_emb", None), "entity_emb_matrix": ("entity_emb", None),
+              "relation_emb_matrix": ("relation_emb", None), "relation_emb_KGE_matrix": ("relation_kge", None),
+              "enti_transfer_matrix_0": ("mix_w", None), "enti_transfer_bias_0": ("mix_b", None),
+              "user_mlp_matrix": ("user_mlp_w", None), "user_mlp_bias": ("user_mlp_b", None),
+              "h_emb_item_mlp_matrix": ("h_item_w", None), "h_emb_item_mlp_bias": ("h_item_b", None)}
+        for e in range(H + 1):
+            mp[f"transfer_agg_matrix_{e}"] = ("transfer_w", e)
+            mp[f"transfer_agg_bias_{e}"] = ("transfer_b", e)
+        for i in range(H):
+            mp[f"agg_{i}_0_weights"] = ("agg_w", i)
+            mp[f"agg_{i}_0_bias"] = ("agg_b", i)
+            mp[f"agg_{i}_0_urh_weights"] = ("agg_urh_w", i)
+            mp[f"agg_{i}_0_urh_bias"] = ("agg_urh_b", i)
+        return mp
+
+    def load_named_parameters(self, named: Dict[str, np.ndarray]):
+        """Set parameters from a dict keyed by the reference's variable names (see oracle.param_shapes)."""
+        for name, (field, idx) in self._name_map().items():
+            src = torch.as_tensor(np.asarray(named[name]), dtype=torch.float32)
+            dst = self.params[field] if idx is None else self.params[field][idx]
+            dst.copy_(src.reshape(dst.shape))
+        torch.cuda.synchronize(self.device)
+
+    def _export(self, tensors) -> Dict[str, np.ndarray]:
+        from_shapes = {"h_emb_item_mlp_matrix": (2 * self.dim, 1), "h_emb_item_mlp_bias": (1,)}
+        out = {}
+        for name, (field, idx) in self._name_map().items():
+            t = tensors[field] if idx is None else tensors[field][idx]
+            a = t.detach().cpu().numpy().copy()
+            if name.endswith("urh_weights"):
+                a = a.reshape(3 * self.dim, 1)
+            elif name.endswith("urh_bias"):
+                a = a.reshape(1)
+            elif name in from_shapes:
+                a = a.reshape(from_shapes[name])
+            out[name] = a
+        return out
+
+    def named_parameters(self):
+        return self._export(self.params)
+
+    def named_gradients(self):
+        return self._export(self.grads)
+
+    def launch_count(self) -> int:
+        return int(self.lib.mvin_launch_count(self._handle))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                self.lib.mvin_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass

@@ -1,0 +1,77 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds for sm_100a, loads without a GPU and exports
+every symbol include/mvin_b200.h declares; the ctypes structs match the header; unsupported configurations are
+refused loudly (no compute call is made here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from mvin_b200 import build
+    return build.build()
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "mvin_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mvin_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    names = _declared_functions()
+    assert len(names) >= 17
+    for n in names:
+        assert hasattr(lib, n), n
+    from mvin_b200 import _lib
+    assert sorted(_lib.EXPORTS) == names
+
+
+def test_abi_version_and_struct_layout(lib_path):
+    from mvin_b200 import _lib
+    lib = ctypes.CDLL(lib_path)
+    assert lib.mvin_abi_version() == _lib.ABI_VERSION
+    assert ctypes.sizeof(_lib.Config) == 13 * 4
+    assert ctypes.sizeof(_lib.Params) == 16 * ctypes.sizeof(ctypes.c_void_p)
+    hdr = open(os.path.join(ROOT, "include", "mvin_b200.h")).read()
+    fields = re.findall(r"float\*\s+(\w+);", hdr.split("typedef struct mvin_params")[1].split("} mvin_params_t")[0])
+    assert fields == _lib.PARAM_FIELDS
+
+
+def test_unsupported_config_is_refused_without_gpu(lib_path):
+    from mvin_b200 import _lib
+    lib = ctypes.CDLL(lib_path)
+    lib.mvin_last_error.restype = ctypes.c_char_p
+    h = ctypes.c_void_p()
+    base = dict(dim=16, neighbor_sample_size=8, h_hop=2, n_mix_hop=1, p_hop=2, n_memory=16, n_user=4, n_entity=9,
+                n_relation=3, max_batch=8, l2_weight=1e-4, l2_agg_weight=1e-6, flags=_lib.FLAGS_ALL)
+    for over in (dict(n_mix_hop=2), dict(dim=24), dict(h_hop=4), dict(neighbor_sample_size=65), dict(flags=0x0F)):
+        cfg = _lib.Config(**{**base, **over})
+        rc = lib.mvin_create(ctypes.byref(cfg), ctypes.byref(h))
+        assert rc == -2, over
+        assert lib.mvin_last_error()
+
+
+def test_product_has_no_oracle_import():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "mvin_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+                assert "oracle/" not in src and "mvin_oracle" not in src, f
+
+
+def test_model_needs_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mvin_b200 import MVIN
+    from tests.synth import make_args
+    import numpy as np
+    with pytest.raises(RuntimeError):
+        MVIN(make_args(), 4, 9, 3, np.zeros((9, 8), np.int64), np.zeros((9, 8), np.int64))
