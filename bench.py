@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- user-item pairs/s, forward+backward, of the MVIN hot path on B200 (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one forward + backward pass (loss and every parameter gradient; Adam excluded) over one
+batch of B user-item pairs of the workload.  Prints ONE JSON line (rank 0).
+
+  value        whole-job pairs/s with the batch already resident in HBM (device-timed, CUDA events per step, max over
+               ranks).  L2 is flushed (256 MiB write) between timed steps, outside the event pairs.
+  e2e          same metric through the C-ABI host entry point mvin_train_step_host: the feed is copied H2D from pinned
+               host memory and the loss scalars are read back D2H inside the timed region of every step.
+  roofline     dominant kernel (by device time, measured live with CUDA events recorded by the library on its launch
+               stream in a third pass over the same steps): algorithmic bytes per launch / mean launch duration vs the
+               measured HBM copy peak (MEASURED_PEAKS.json).
+  cpu_baseline the oracle (op-for-op CPU restatement of the reference's TF1 graph, oracle/mvin_oracle.py) timed on the
+               host cores on a bounded sample of the same workload.  The oracle is used ONLY here and in --impl
+               reference; the product path never touches it.
+N > 1: data-parallel replicas (tables <= 30 MB are replicated); every rank processes its own batches
+(weak scaling, no data-path collective).  --allreduce adds the DP gradient all-reduce (NCCL) to every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# BASELINE.json configs: dataset shape, d, L (= h_hop, n_mix_hop 1), K, B, p, m
+WORKLOADS = {
+    "C1": dict(dataset="MovieLens-1M", dim=16, h_hop=1, K=8, B=1024, p=2, m=64),
+    "C2": dict(dataset="MovieLens-1M", dim=32, h_hop=2, K=16, B=4096, p=2, m=64),
+    "C3": dict(dataset="last-fm_50core", dim=64, h_hop=2, K=32, B=8192, p=2, m=64),
+    "C4": dict(dataset="amazon-book_20core", dim=64, h_hop=3, K=32, B=16384, p=1, m=16),
+}
+METRIC = "user-item pairs/sec fwd+bwd"
+UNIT = "pairs/s"
+FLUSH_BYTES = 256 << 20
+
+
+def workload_name(key, w):
+    return (f"{key}: {w['dataset']}-shaped synthetic KG, dim={w['dim']}, n_hop={w['h_hop']}, neighbor_size={w['K']}, "
+            f"batch={w['B']}, p_hop={w['p']}, n_memory={w['m']}")
+
+
+def make_args(w, batch=None):
+    return types.SimpleNamespace(
+        dataset=w["dataset"], load_pretrain_emb=False, h_hop=w["h_hop"], batch_size=batch or w["B"],
+        neighbor_sample_size=w["K"], p_hop=w["p"], dim=w["dim"], l2_weight=1e-7, l2_agg_weight=1e-7, kge_weight=1e-2,
+        lr=5e-3, save_model_name="bench", n_mix_hop=1, n_memory=w["m"], update_item_emb="transform_matrix",
+        h0_att="st_att_h_set", path=None, User_orient=1, User_orient_rela=1, User_orient_kg_eh=1, PS_O_ft=1,
+        wide_deep=1, PS_only=0, HO_only=0)
+
+
+def bytes_per_pair(w):
+    """algorithmic HBM bytes per user-item pair (fp32 rows, int32 ids)."""
+    d, L, K, p, m = w["dim"], w["h_hop"], w["K"], w["p"], w["m"]
+    r_kg = sum(K ** i for i in range(L + 1))
+    i_kg = sum(K ** i for i in range(1, L + 1))
+    r_mem = 2 * p * m
+    fwd = 4 * d * (r_kg + r_mem + 1) + 4 * (2 * i_kg + 3 * p * m) + 24
+    bwd = 2 * 4 * d * (r_kg + r_mem + 1)
+    return fwd, bwd
+
+
+def kernel_bytes_per_step(w):
+    """Algorithmic bytes per STEP of each kernel family = its share of the 8(d) per-pair figure x B."""
+    d, L, K, B, p, m = w["dim"], w["h_hop"], w["K"], w["B"], w["p"], w["m"]
+    rows = [B * K ** h for h in range(L + 1)]
+    row, ids = 4 * d, 8
+    out = {
+        "agg_fwd_leaf": rows[L] * (row + ids),
+        "agg_bwd_leaf": rows[L] * (2 * row + ids),
+        "transform_fwd": sum(rows[h] * (row + 4) for h in range(L)),
+        "transform_bwd": sum(rows[h] * (2 * row + 4) for h in range(L)),
+        "ripple_fwd": B * (2 * p * m * row + 3 * p * m * 4),
+        "ripple_bwd": B * (2 * 2 * p * m * row + 3 * p * m * 4),
+    }
+    inner_f = inner_b = 0
+    for i in range(L):
+        for h in range(L - i):
+            if not (i == 0 and h == L - 1):
+                inner_f += rows[h + 1] * (row + ids)
+                inner_b += rows[h + 1] * (2 * row + ids)
+    out["agg_fwd_inner"], out["agg_bwd_inner"] = inner_f, inner_b
+    return out
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self.power = index, [], set(), None, []
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "power_w_max": round(max(self.power), 1) if self.power else None}
+
+
+# --------------------------------------------------------------------------------------------------------------
+def oracle_problem(w, ds, n_pairs, seed=0):
+    """A bounded sample of the workload for the CPU arm: first n_pairs pairs of the (seeded) interaction list."""
+    from oracle import mvin_oracle as orc            # checker / CPU baseline only
+    from mvin_b200 import data as D
+    args = make_args(w, batch=n_pairs)
+    cfg = orc.OracleConfig.from_args(args)
+    shp = ds["shape"]
+    P = orc.init_params(cfg, shp["n_user"], shp["n_entity"], shp["n_relation"], seed=seed, regime="xavier")
+    batch = ds["data"][:n_pairs]
+    mh, mr, mt = D.stacked_memories(ds["user_triplet_set"], batch[:, 0])
+    return orc, cfg, P, batch, list(mh), list(mr), list(mt)
+
+
+def time_oracle(w, ds, n_pairs, steps, warmup):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    orc, cfg, P, batch, mh, mr, mt = oracle_problem(w, ds, n_pairs)
+    run = lambda: orc.loss_and_grads(P, cfg, ds["adj_entity"], ds["adj_relation"], batch[:, 0], batch[:, 1], mh, mr, mt,
+                                     batch[:, 2].astype(np.float32))
+    for _ in range(warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+    dt = time.perf_counter() - t0
+    return n_pairs * steps / dt, dt / steps, cores
+
+
+def run_reference(a, w, wl_key):
+    """--impl reference: the reference's own CPU implementation of the path.  TensorFlow 1.13 is not installable in
+    this image, so this is the oracle port, timed on all host cores on a bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from mvin_b200 import data as D
+    ds = D.make_synthetic_dataset(w["dataset"], w["K"], w["p"], w["m"], seed=2020, n_interactions=50_000)
+    # size the per-step sample so that (steps + warmup) steps take about two minutes
+    probe = 64
+    _, t_probe, cores = time_oracle(w, ds, probe, 1, 1)
+    budget = 120.0 / max(1, a.steps + a.warmup)
+    n_pairs = int(max(8, min(w["B"], probe * budget / max(t_probe, 1e-6))))
+    value, t_step, cores = time_oracle(w, ds, n_pairs, a.steps, a.warmup)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": workload_name(wl_key, w), "pairs_per_step": n_pairs},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{n_pairs} pairs/step of {wl_key} x {a.steps} steps, torch-CPU fp32 oracle, "
+                                       f"fwd + autograd bwd"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------
+def run_ours(a, w, wl_key):
+    import torch
+    import torch.distributed as dist
+    from mvin_b200 import MVIN
+    from mvin_b200 import data as D
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU path for the product arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = w["B"]
+    ds = D.make_synthetic_dataset(w["dataset"], w["K"], w["p"], w["m"], seed=2020)
+    shp = ds["shape"]
+    model = MVIN(make_args(w), shp["n_user"], shp["n_entity"], shp["n_relation"], ds["adj_entity"], ds["adj_relation"],
+                 device=dev, seed=1)
+    # NB pre-staged batches per rank (disjoint slices of the shuffled interaction list)
+    NB = 8
+    rng = np.random.RandomState(1234)
+    perm = rng.permutation(ds["data"].shape[0])
+    host, devb = [], []
+    for i in range(NB):
+        sel = perm[((rank * NB + i) * B) % (perm.size - B):][:B]
+        batch = ds["data"][sel]
+        mh, mr, mt = D.stacked_memories(ds["user_triplet_set"], batch[:, 0])
+        arrs = [np.ascontiguousarray(batch[:, 0]), np.ascontiguousarray(batch[:, 1]),
+                np.ascontiguousarray(batch[:, 2].astype(np.float32)), mh, mr, mt]
+        pinned = [torch.from_numpy(x).pin_memory() for x in arrs]
+        host.append(pinned)
+        devb.append([t.to(dev) for t in pinned])
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    d2h = 16
+    flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    losses = torch.zeros(4, dtype=torch.float32, device=dev)
+    flat_grads = None
+    if a.allreduce and world > 1:
+        flat_grads = list(model.grads.values())
+
+    def step_device(i):
+        u, it, lab, mh, mr, mt = devb[i % NB]
+        model.forward_device(u, it, mh, mr, mt)
+        model.backward_device(lab, losses)
+        if flat_grads is not None:
+            for g in flat_grads:
+                dist.all_reduce(g)
+
+    def step_host(i):
+        u, it, lab, mh, mr, mt = host[i % NB]
+        return model.train_step_host(u, it, lab, mh, mr, mt, apply_adam=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for i in range(steps):
+            flush.zero_()                                    # L2 flush, outside the event pair
+            evs[i][0].record()
+            fn(i)
+            evs[i][1].record()
+        barrier()
+        ms = sum(s.elapsed_time(e) for s, e in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for i in range(max(3, a.warmup)):
+        step_device(i)
+    step_host(0)
+    sampler = ClockSampler(local)
+    launches0 = model.launch_count()
+    sampler.start()
+    ms_total = timed(step_device, a.steps)
+    clocks = sampler.stop()
+    launches = model.launch_count() - launches0
+    ms_e2e = timed(step_host, a.steps)
+
+    # per-kernel device times, same steps, events recorded by the library on its launch stream
+    prof = {}
+    if rank == 0:
+        import ctypes
+        model.lib.mvin_profile_enable(model._handle, 1)
+        barrier_local = lambda: torch.cuda.synchronize(dev)
+        barrier_local()
+        n_prof = min(a.steps, 50)
+        buf = ctypes.create_string_buffer(8192)
+        for i in range(n_prof):
+            flush.zero_()
+            u, it, lab, mh, mr, mt = devb[i % NB]
+            model.forward_device(u, it, mh, mr, mt)
+            model.backward_device(lab, losses)
+            model.lib.mvin_profile_read(model._handle, buf, len(buf))
+            for rec in buf.value.decode().split(";"):
+                if rec:
+                    name, ms, n = rec.split(":")
+                    p = prof.setdefault(name, [0.0, 0])
+                    p[0] += float(ms)
+                    p[1] += int(n)
+        model.lib.mvin_profile_enable(model._handle, 0)
+        prof = {k: {"ms_per_step": v[0] / n_prof, "launches_per_step": v[1] / n_prof} for k, v in prof.items()}
+    if world > 1:
+        dist.barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pairs_per_s = world * B * a.steps / (ms_total * 1e-3)
+    e2e_pairs_per_s = world * B * a.steps / (ms_e2e * 1e-3)
+    peak, peak_src = load_peaks()
+    fwd_b, bwd_b = bytes_per_pair(w)
+    kb = kernel_bytes_per_step(w)
+    gather_kernels = {k: v for k, v in prof.items() if k in kb and kb[k] > 0}
+    top = max(gather_kernels, key=lambda k: gather_kernels[k]["ms_per_step"]) if gather_kernels else None
+    roofline = None
+    if top:
+        per_launch_bytes = kb[top] / prof[top]["launches_per_step"]
+        per_launch_ms = prof[top]["ms_per_step"] / prof[top]["launches_per_step"]
+        achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(wl_key, {}).get(top)
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": per_launch_bytes, "launch_ms": per_launch_ms,
+                    "share_of_step": prof[top]["ms_per_step"] / max(1e-9, sum(v["ms_per_step"] for v in prof.values())),
+                    "step_logical_gbs": (fwd_b + bwd_b) * pairs_per_s / world / 1e9,
+                    "step_frac": (fwd_b + bwd_b) * pairs_per_s / world / 1e9 / peak,
+                    "note": "tables (<=30 MB) are L2-resident at this workload: logical gather bytes, not DRAM traffic"}
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        n_pairs = a.cpu_sample_pairs
+        v, t_step, cores = time_oracle(w, ds, n_pairs, 1, 1)
+        reps = int(max(2, min(20, 15.0 / max(t_step, 1e-3))))
+        v, t_step, cores = time_oracle(w, ds, n_pairs, reps, 0)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n_pairs} pairs/step of {wl_key} x {reps} steps, torch-CPU fp32 oracle (op-for-op restatement "
+                         f"of the TF1 graph), fwd + autograd bwd"}
+    line = {"metric": METRIC, "value": pairs_per_s, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(wl_key, w), "pairs_per_step_per_gpu": B,
+                       "parallelism": f"dp{world} replicas" + (" + grad all-reduce" if flat_grads is not None else ""),
+                       "l2": "flushed between timed steps (256 MiB write outside the event pairs)",
+                       "init": "reference Xavier init, seed 1"},
+            "e2e": {"value": e2e_pairs_per_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / a.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "kernels_ms_per_step": {k: round(v["ms_per_step"], 5) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms_per_step"])}}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=30)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--allreduce", action="store_true", help="add the DP gradient all-reduce to every step (N > 1)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-pairs", type=int, default=256)
+    a = ap.parse_args()
+    w = WORKLOADS[a.workload]
+    if a.impl == "reference":
+        run_reference(a, w, a.workload)
+    else:
+        run_ours(a, w, a.workload)
+
+
+if __name__ == "__main__":
+    main()

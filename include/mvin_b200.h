@@ -146,6 +146,12 @@ int mvin_train_step_host(mvin_handle_t h, const int64_t* user_indices, const int
 /* Number of kernels the library has launched on behalf of this handle since creation (bench evidence). */
 int64_t mvin_launch_count(mvin_handle_t h);
 
+/* Per-kernel device timing for bench.py's roofline figure.  While enabled the library records one CUDA event on
+ * the launch stream after each of its kernel launches; mvin_profile_read synchronises on the last one and writes
+ * "name:total_ms:launches;..." (accumulated since the previous read) into buf, then clears the records. */
+int mvin_profile_enable(mvin_handle_t h, int32_t on);
+int mvin_profile_read(mvin_handle_t h, char* buf, size_t buflen);
+
 #ifdef __cplusplus
 }
 #endif

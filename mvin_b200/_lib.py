@@ -14,7 +14,8 @@ ABI_VERSION = 1
 EXPORTS = ["mvin_abi_version", "mvin_last_error", "mvin_create", "mvin_destroy", "mvin_bind_params",
            "mvin_bind_grads", "mvin_bind_adjacency", "mvin_pack_adjacency", "mvin_workspace_bytes",
            "mvin_get_neighbors", "mvin_forward", "mvin_importance", "mvin_backward", "mvin_adam_step",
-           "mvin_feed_bytes", "mvin_train_step_host", "mvin_launch_count"]
+           "mvin_feed_bytes", "mvin_train_step_host", "mvin_launch_count", "mvin_profile_enable",
+           "mvin_profile_read"]
 
 
 class Config(C.Structure):
@@ -72,6 +73,8 @@ def load():
                                          C.POINTER(Params), C.c_float, i32, vp, vp]
     lib.mvin_launch_count.argtypes = [vp]
     lib.mvin_launch_count.restype = C.c_int64
+    lib.mvin_profile_enable.argtypes = [vp, i32]
+    lib.mvin_profile_read.argtypes = [vp, C.c_char_p, C.c_size_t]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is None or (name not in ("mvin_last_error", "mvin_workspace_bytes", "mvin_feed_bytes",

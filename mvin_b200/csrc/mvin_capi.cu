@@ -31,6 +31,8 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+void prof_mark(mvin_handle_t h, cudaStream_t st, const char* name);
+
 #define CUDA_TRY(expr)                                                                              \
   do {                                                                                              \
     cudaError_t _e = (expr);                                                                        \
@@ -41,6 +43,7 @@ int fail(int code, const char* fmt, ...) {
 #define LAUNCH_CHECK(h, name)                                                                       \
   do {                                                                                              \
     (h)->launches++;                                                                                \
+    prof_mark((h), st, name);                                                                       \
     cudaError_t _e = cudaGetLastError();                                                            \
     if (_e != cudaSuccess) return fail(MVIN_ERR_CUDA, "launch %s: %s", name, cudaGetErrorString(_e)); \
   } while (0)
@@ -80,9 +83,23 @@ struct mvin_handle_s {
   const int32_t *mem_h = nullptr, *mem_r = nullptr, *mem_t = nullptr;
   int B = 0;
   void* fwd_workspace = nullptr;
+  // optional per-category kernel timing (mvin_profile_enable / mvin_profile_read)
+  bool prof_on = false;
+  struct ProfRec { const char* name; cudaEvent_t ev; };
+  std::vector<ProfRec> prof;
 };
 
 namespace {
+
+// Kernel timing: when enabled, one CUDA event is recorded on the launch stream after every kernel launch (and one
+// marker at each API entry); the stream is in-order, so consecutive events bracket one kernel.
+void prof_mark(mvin_handle_t h, cudaStream_t st, const char* name) {
+  if (!h->prof_on) return;
+  cudaEvent_t ev;
+  if (cudaEventCreate(&ev) != cudaSuccess) return;
+  cudaEventRecord(ev, st);
+  h->prof.push_back({name, ev});
+}
 
 Layout make_layout(const mvin_config_t& c, long B) {
   Layout L;
@@ -192,6 +209,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
   const Layout L = make_layout(c, B);
   const mvin_params_t& P = h->P;
   int rc;
+  prof_mark(h, st, nullptr);
 
   // seeds + integer expansion (model.py:243-256); level L ids are never materialised
   {
@@ -283,7 +301,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
           a.child = at<float>(ws, L.V[i][lv + 1]);
           agg_fwd_kernel<D, false><<<tile_grid(h, a.rows, ctas_per_sm(sm_in, C::NT)), C::NT, sm_in, st>>>(a);
         }
-        LAUNCH_CHECK(h, "agg_fwd");
+        LAUNCH_CHECK(h, leaf ? "agg_fwd_leaf" : "agg_fwd_inner");
       }
     }
   }
@@ -337,9 +355,11 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
   const float l2w = c.l2_weight, l2a = c.l2_agg_weight;
   int rc;
   float* acc = at<float>(ws, L.acc);
+  prof_mark(h, st, nullptr);
 
   CUDA_TRY(cudaMemsetAsync(at<char>(ws, L.zero_begin), 0, L.zero_end - L.zero_begin, st));
   CUDA_TRY(cudaMemsetAsync(G.entity_emb, 0, sizeof(float) * (size_t)c.n_entity * D, st));
+  prof_mark(h, st, "memset");
   // dense L2 terms: initialise every other gradient buffer with coef * param (model.py:388-410)
   {
     L2Segments sg;
@@ -427,7 +447,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
           a.dchild = at<float>(ws, L.dV[i][lv + 1]);
           agg_bwd_kernel<D, false><<<tile_grid(h, a.rows, ctas_per_sm(sm_in, C::NT)), C::NT, sm_in, st>>>(a);
         }
-        LAUNCH_CHECK(h, "agg_bwd");
+        LAUNCH_CHECK(h, leaf ? "agg_bwd_leaf" : "agg_bwd_inner");
         if ((rc = launch_dw<D>(h, st, at<float>(ws, L.Y[i][lv]), D, a.gout, a.rows, G.agg_w + (long)i * D * D,
                                G.agg_b + (long)i * D)))
           return rc;
@@ -711,7 +731,9 @@ int mvin_adam_step(mvin_handle_t h, const mvin_params_t* m, const mvin_params_t*
   sg.count = n;
   const float lr_t = (float)((double)lr * std::sqrt(1.0 - std::pow((double)beta2, step)) /
                              (1.0 - std::pow((double)beta1, step)));
-  adam_kernel<<<h->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(sg, lr_t, beta1, beta2, eps);
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_mark(h, st, nullptr);
+  adam_kernel<<<h->sm_count * 4, 256, 0, st>>>(sg, lr_t, beta1, beta2, eps);
   LAUNCH_CHECK(h, "adam");
   return MVIN_OK;
 }
@@ -763,5 +785,40 @@ int mvin_train_step_host(mvin_handle_t h, const int64_t* user_indices, const int
 }
 
 int64_t mvin_launch_count(mvin_handle_t h) { return h ? h->launches : 0; }
+
+int mvin_profile_enable(mvin_handle_t h, int32_t on) {
+  if (!h) return fail(MVIN_ERR_INVALID, "null handle");
+  h->prof_on = on != 0;
+  return MVIN_OK;
+}
+
+int mvin_profile_read(mvin_handle_t h, char* buf, size_t buflen) {
+  if (!h || !buf || buflen < 2) return fail(MVIN_ERR_INVALID, "bad argument");
+  struct Row { const char* name; double ms; long n; };
+  std::vector<Row> rows;
+  if (!h->prof.empty()) CUDA_TRY(cudaEventSynchronize(h->prof.back().ev));
+  for (size_t i = 1; i < h->prof.size(); ++i) {
+    const char* name = h->prof[i].name;
+    if (!name) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->prof[i - 1].ev, h->prof[i].ev) != cudaSuccess) continue;
+    Row* r = nullptr;
+    for (auto& x : rows)
+      if (strcmp(x.name, name) == 0) r = &x;
+    if (!r) { rows.push_back({name, 0.0, 0}); r = &rows.back(); }
+    r->ms += ms;
+    r->n += 1;
+  }
+  for (auto& e : h->prof) cudaEventDestroy(e.ev);
+  h->prof.clear();
+  size_t off = 0;
+  buf[0] = 0;
+  for (auto& r : rows) {
+    int w = snprintf(buf + off, buflen - off, "%s:%.6f:%ld;", r.name, r.ms, r.n);
+    if (w < 0 || (size_t)w >= buflen - off) break;
+    off += (size_t)w;
+  }
+  return MVIN_OK;
+}
 
 }  // extern "C"

@@ -1,0 +1,171 @@
+"""Host-side producers of the hot path's inputs, in the reference's layouts (vectorised NumPy).
+
+Mirrors src/model/MVIN/data_loader_user_set.py of the reference:
+  build_undirected_csr   <- construct_kg            :324-343  (undirected KG; CSR instead of a dict of lists)
+  sample_adjacency       <- contruct_random_adj     :375-388  (K neighbours per entity, without replacement when
+                                                               degree >= K, else with; isolated entities keep zeros)
+  build_ripple_sets      <- get_user_triplet_set    :392-441  (per user and hop: <= 16 edges per head, then m
+                                                               sampled, with replacement only when fewer than m)
+  get_feed_dict          <- train.py:112-122                  (same keys / shapes; one fancy-index instead of
+                                                               3 p B Python row picks)
+and a seeded synthetic generator of KGs / interaction data with a given dataset's shape (there are no datasets on
+the GPU box).  Sampling is distribution-equivalent to the reference, not stream-equivalent (the reference itself is
+unseeded).
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import numpy as np
+
+# dataset shapes (verified by loading the shipped .npy / .csv files)
+DATASET_SHAPES = {
+    "MovieLens-1M": dict(n_entity=182_011, n_relation=12, n_triples=1_241_995, n_user=6_036, n_item=2_445,
+                         n_interactions=753_772),
+    "last-fm_50core": dict(n_entity=106_389, n_relation=9, n_triples=464_567, n_user=23_554, n_item=48_092,
+                           n_interactions=1_000_000),
+    "amazon-book_20core": dict(n_entity=113_487, n_relation=39, n_triples=2_557_746, n_user=70_585, n_item=24_915,
+                               n_interactions=600_000),
+}
+
+
+def synthetic_kg(n_entity: int, n_relation: int, n_triples: int, seed: int = 2020, skew: float = 0.8) -> np.ndarray:
+    """int64 [n_triples, 3] (head, relation, tail).  Tails follow a power law P(rank) ~ rank^-skew; skew = 0.8
+    reproduces the hub structure of the shipped MovieLens-1M KG (max degree ~3e4, the top entity holding ~1.5 % and
+    the top 100 ~10 % of all sampled-adjacency slots; calibrated against data/MovieLens-1M/kg_final.npy).  Every
+    entity appears at least once as a head so no adjacency row is empty (true of the three shipped KGs)."""
+    rng = np.random.RandomState(seed)
+    n_triples = max(n_triples, n_entity)
+    heads = np.concatenate([np.arange(n_entity), rng.randint(0, n_entity, size=n_triples - n_entity)])
+    cdf = np.cumsum((np.arange(n_entity) + 1.0) ** -skew)
+    cdf /= cdf[-1]
+    tails = np.minimum(np.searchsorted(cdf, rng.rand(n_triples)), n_entity - 1)
+    perm = rng.permutation(n_entity)                # hubs are spread over the id space
+    tails = perm[tails]
+    rels = rng.randint(0, n_relation, size=n_triples)
+    return np.stack([heads, rels, tails], axis=1).astype(np.int64)
+
+
+def build_undirected_csr(kg_np: np.ndarray, n_entity: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """(indptr [n_entity+1], nbr [2T], rel [2T]): for every triple (h, r, t) both h->(t, r) and t->(h, r)."""
+    h, r, t = kg_np[:, 0], kg_np[:, 1], kg_np[:, 2]
+    src = np.concatenate([h, t])
+    dst = np.concatenate([t, h])
+    rr = np.concatenate([r, r])
+    order = np.argsort(src, kind="stable")
+    counts = np.bincount(src, minlength=n_entity)
+    indptr = np.zeros(n_entity + 1, dtype=np.int64)
+    np.cumsum(counts, out=indptr[1:])
+    return indptr, dst[order].astype(np.int64), rr[order].astype(np.int64)
+
+
+def sample_adjacency(indptr, nbr, rel, K: int, seed: int = 2020) -> Tuple[np.ndarray, np.ndarray]:
+    """adj_entity, adj_relation int64 [n_entity, K]."""
+    rng = np.random.RandomState(seed)
+    n_entity = indptr.shape[0] - 1
+    deg = np.diff(indptr)
+    adj_e = np.zeros((n_entity, K), dtype=np.int64)
+    adj_r = np.zeros((n_entity, K), dtype=np.int64)
+    # degree < K: with replacement
+    small = np.nonzero((deg > 0) & (deg < K))[0]
+    if small.size:
+        pick = (rng.rand(small.size, K) * deg[small, None]).astype(np.int64) + indptr[small, None]
+        adj_e[small], adj_r[small] = nbr[pick], rel[pick]
+    # degree >= K: without replacement = first K of a random permutation of the row
+    big = np.nonzero(deg >= K)[0]
+    if big.size:
+        keys = rng.rand(nbr.shape[0])
+        row_of = np.repeat(np.arange(n_entity), deg)
+        order = np.lexsort((keys, row_of))          # within each row, a uniformly random order
+        pick = indptr[big, None] + np.arange(K)[None, :]
+        sel = order[pick]
+        adj_e[big], adj_r[big] = nbr[sel], rel[sel]
+    return adj_e, adj_r
+
+
+def synthetic_interactions(n_user: int, n_item: int, n_interactions: int, seed: int = 2020) -> np.ndarray:
+    """int64 [N, 3] (user, item, label in {0,1}), half positive (the reference's negative sampling ratio)."""
+    rng = np.random.RandomState(seed)
+    users = rng.randint(0, n_user, size=n_interactions)
+    items = (rng.zipf(1.3, size=n_interactions) - 1) % n_item
+    labels = rng.randint(0, 2, size=n_interactions)
+    return np.stack([users, items, labels], axis=1).astype(np.int64)
+
+
+def user_history(data: np.ndarray, n_user: int, n_item: int, seed: int = 2020) -> Dict[int, np.ndarray]:
+    """user -> positive items (data_loader_user_set.py:get_user_record); users without one get a random item so
+    every user has a ripple set (the reference drops such users instead, :77-97)."""
+    pos = data[data[:, 2] == 1]
+    order = np.argsort(pos[:, 0], kind="stable")
+    pos = pos[order]
+    bounds = np.searchsorted(pos[:, 0], np.arange(n_user + 1))
+    rng = np.random.RandomState(seed)
+    hist = {}
+    for u in range(n_user):
+        items = np.unique(pos[bounds[u]:bounds[u + 1], 1])
+        hist[u] = items if items.size else rng.randint(0, n_item, size=1)
+    return hist
+
+
+def build_ripple_sets(indptr, nbr, rel, history: Dict[int, np.ndarray], n_user: int, p_hop: int, n_memory: int,
+                      n_neighbor: int = 16, seed: int = 2020) -> np.ndarray:
+    """user_triplet_set as one dense int32 array [n_user, max(1,p), 3, m] (rows h, r, t), the packed form of the
+    reference's dict user -> int32 [p, 3, m] (data_loader_user_set.py:402)."""
+    rng = np.random.RandomState(seed)
+    P = max(1, p_hop)
+    out = np.zeros((n_user, P, 3, n_memory), dtype=np.int32)
+    for u in range(n_user):
+        tails = history[u]
+        prev = None
+        for hop in range(P):
+            heads = np.asarray(tails, dtype=np.int64)
+            deg = indptr[heads + 1] - indptr[heads]
+            take = np.minimum(deg, n_neighbor)
+            tot = int(take.sum())
+            if tot == 0:
+                out[u, hop] = prev                  # copy the previous hop (:425-426)
+                continue
+            rep_head = np.repeat(heads, take)
+            start = np.repeat(indptr[heads], take)
+            rep_deg = np.repeat(deg, take)
+            # <= n_neighbor edges per head: random offsets (with replacement inside a head when deg > n_neighbor)
+            within = np.arange(tot) - np.repeat(np.cumsum(take) - take, take)
+            off = np.where(rep_deg > n_neighbor, (rng.rand(tot) * rep_deg).astype(np.int64), within)
+            eidx = start + off
+            idx = rng.choice(tot, size=n_memory, replace=tot < n_memory)
+            trip = np.stack([rep_head[idx], rel[eidx[idx]], nbr[eidx[idx]]]).astype(np.int32)
+            out[u, hop] = trip
+            prev = trip
+            tails = trip[2]
+    return out
+
+
+def get_feed_dict(model, data: np.ndarray, user_triplet_set: np.ndarray, start: int, end: int):
+    """train.py:112-122 with the packed ripple sets: same keys, values int32 [B, m] arrays."""
+    users = data[start:end, 0]
+    feed = {model.user_indices: users, model.item_indices: data[start:end, 1], model.labels: data[start:end, 2]}
+    trip = user_triplet_set[users]                  # [B, P, 3, m]
+    for i in range(trip.shape[1]):
+        feed[model.memories_h[i]] = trip[:, i, 0]
+        feed[model.memories_r[i]] = trip[:, i, 1]
+        feed[model.memories_t[i]] = trip[:, i, 2]
+    return feed
+
+
+def stacked_memories(user_triplet_set: np.ndarray, users: np.ndarray):
+    """The C-ABI feed form: mem_h, mem_r, mem_t int32 [P, B, m] (contiguous)."""
+    trip = user_triplet_set[users]                  # [B, P, 3, m]
+    t = np.ascontiguousarray(trip.transpose(2, 1, 0, 3))   # [3, P, B, m]
+    return t[0], t[1], t[2]
+
+
+def make_synthetic_dataset(name: str, K: int, p_hop: int, n_memory: int, seed: int = 2020, n_interactions=None):
+    shp = DATASET_SHAPES[name]
+    kg = synthetic_kg(shp["n_entity"], shp["n_relation"], shp["n_triples"], seed)
+    indptr, nbr, rel = build_undirected_csr(kg, shp["n_entity"])
+    adj_e, adj_r = sample_adjacency(indptr, nbr, rel, K, seed)
+    n_int = n_interactions or min(shp["n_interactions"], 400_000)
+    data = synthetic_interactions(shp["n_user"], shp["n_item"], n_int, seed)
+    hist = user_history(data, shp["n_user"], shp["n_item"], seed)
+    uts = build_ripple_sets(indptr, nbr, rel, hist, shp["n_user"], p_hop, n_memory, seed=seed)
+    return dict(shape=shp, adj_entity=adj_e, adj_relation=adj_r, data=data, user_triplet_set=uts)
