@@ -75,25 +75,22 @@ def bytes_per_pair(w):
 
 
 def kernel_bytes_per_step(w):
-    """Algorithmic bytes per STEP of each kernel family = its share of the 8(d) per-pair figure x B."""
+    """Algorithmic bytes per STEP of each kernel family = its share of the 8(d) per-pair figure x B.
+    agg_{fwd,bwd}_i is the single launch of aggregator iteration i over all its levels (iteration 0 holds the leaf
+    gather): every child / leaf row is read once (fwd) or read + gradient-written (bwd), plus its 8 id bytes."""
     d, L, K, B, p, m = w["dim"], w["h_hop"], w["K"], w["B"], w["p"], w["m"]
     rows = [B * K ** h for h in range(L + 1)]
     row, ids = 4 * d, 8
     out = {
-        "agg_fwd_leaf": rows[L] * (row + ids),
-        "agg_bwd_leaf": rows[L] * (2 * row + ids),
         "transform_fwd": sum(rows[h] * (row + 4) for h in range(L)),
         "transform_bwd": sum(rows[h] * (2 * row + 4) for h in range(L)),
         "ripple_fwd": B * (2 * p * m * row + 3 * p * m * 4),
         "ripple_bwd": B * (2 * 2 * p * m * row + 3 * p * m * 4),
     }
-    inner_f = inner_b = 0
     for i in range(L):
-        for h in range(L - i):
-            if not (i == 0 and h == L - 1):
-                inner_f += rows[h + 1] * (row + ids)
-                inner_b += rows[h + 1] * (2 * row + ids)
-    out["agg_fwd_inner"], out["agg_bwd_inner"] = inner_f, inner_b
+        child_rows = sum(rows[h + 1] for h in range(L - i))
+        out[f"agg_fwd_{i}"] = child_rows * (row + ids)
+        out[f"agg_bwd_{i}"] = child_rows * (2 * row + ids)
     return out
 
 

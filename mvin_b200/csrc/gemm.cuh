@@ -20,6 +20,7 @@ struct GemmArgs {
   const float* bias;      // [N] or nullptr; added once (k-split 0)
   int M, N, K;
   int nbatch, ksplit;
+  int reduce;             // 1: sum over the nbatch batches inside the CTA (C has no batch dimension)
   int accumulate;         // 1: atomicAdd into C (required when ksplit > 1 or c_rows has duplicates)
   float alpha;
 };
@@ -31,14 +32,15 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(GemmArgs g) {
   __shared__ float Bs[GEMM_BK][GEMM_BN + 4];
   const int tid = threadIdx.x;
   const int tx = tid % 16, ty = tid / 16;
-  const int batch = blockIdx.z / g.ksplit, split = blockIdx.z % g.ksplit;
+  const int batch = g.reduce ? 0 : blockIdx.z / g.ksplit, split = blockIdx.z % g.ksplit;
+  const int nred = g.reduce ? g.nbatch : 1;
   const int m0 = blockIdx.y * GEMM_BM, n0 = blockIdx.x * GEMM_BN;
   int kchunk = (g.K + g.ksplit - 1) / g.ksplit;
   kchunk = (kchunk + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
   const int k_begin = split * kchunk;
   const int k_end = min(g.K, k_begin + kchunk);
-  const float* A = g.A + (long)batch * g.bsA;
-  const float* B = g.B + (long)batch * g.bsB;
+  const float* A0 = g.A + (long)batch * g.bsA;
+  const float* B0 = g.B + (long)batch * g.bsB;
   const bool a_kfast = (g.sa_k == 1), b_nfast = (g.sb_n == 1);
 
   float acc[4][4];
@@ -47,6 +49,9 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(GemmArgs g) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
+  for (int red = 0; red < nred; ++red) {
+  const float* A = A0 + (long)red * g.bsA;
+  const float* B = B0 + (long)red * g.bsB;
   for (int kt = k_begin; kt < k_end; kt += GEMM_BK) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -80,6 +85,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(GemmArgs g) {
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
+  }
   }
 
   float* C = g.C + (long)batch * g.bsC;

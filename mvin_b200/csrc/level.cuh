@@ -1,17 +1,20 @@
-// level.cuh -- the KG side of the MVIN hot path: per-level fused gather-attend-aggregate kernels.
+// level.cuh -- the KG side of the MVIN hot path: fused gather-attend-aggregate kernels, one launch per
+// aggregator iteration covering EVERY level of that iteration.
 //
 // Replaces (reference, src/model/MVIN/): model.py:267-283 (entity gather + user-oriented transform),
 // aggregators.py:98-146 (attention over K, mean of weighted neighbours, (self+agg).W+b, ReLU) as driven by the
-// loop at model.py:286-307, and the TF autodiff of the same ops.
+// loop at model.py:286-307, and the TF autodiff of the same ops (weight gradients included: dW is accumulated in
+// registers by the CTA that already holds the tile, never by a second pass over the activations).
 //
 // Layout: every activation buffer is row-major [rows, D] fp32 with rows = B * K^h (pair-major, child k of node
-// j at row j*K+k, model.py:251).  One CTA owns a tile of R = 64 consecutive rows and walks tiles persistently;
-// the d x d weights live in shared memory for the CTA's lifetime.  Two thread mappings are used on the tile:
+// j at row j*K+k, model.py:251).  A launch carries up to MAX_LV level descriptors; the grid is partitioned
+// between the levels (cta_end[]), each CTA owns tiles of R = 64 consecutive rows of ONE level and walks them
+// persistently; the d x d weights live in shared memory for the CTA's lifetime.  Two thread mappings per tile:
 //   * "warp per row" for the neighbour phase: a warp reads the node's packed adjacency record (K ids + K
 //     relation ids, contiguous), does the K-softmax with shuffles, then streams the K child rows with G = 32/LPR
 //     rows in flight per load instruction (LPR = D/4 lanes x 16 B cover one row).
 //   * "register tile" for the dense maps: thread (ty, tx) owns TM rows x 4 columns, FP32 FFMA (see gemm.cuh for
-//     why not TF32).
+//     why not TF32), and TMW x 4 entries of each weight gradient.
 #pragma once
 #include "common.cuh"
 
@@ -19,18 +22,31 @@ namespace mvin {
 
 template <int D>
 struct TC {
-  static constexpr int LPR = D / 4;                  // float4 lanes per row
-  static constexpr int NT = (D >= 16) ? 256 : 128;   // threads per CTA
-  static constexpr int NTY = NT / LPR;               // thread rows of the register tile
-  static constexpr int R = 64;                       // rows per tile
-  static constexpr int TM = R / NTY;                 // rows per thread
-  static constexpr int LD = D + 4;                   // padded leading dimension of a row tile in smem
-  static constexpr int NW = NT / 32;                 // warps per CTA
-  static constexpr int G = 32 / LPR;                 // rows one warp load instruction covers
-  static constexpr int TMW = (D / NTY) > 0 ? (D / NTY) : 1;   // dW rows per thread in dw_kernel
+  static constexpr int LPR = D / 4;                                   // float4 lanes per row
+  static constexpr int NT = (D >= 128) ? 512 : (D >= 16) ? 256 : 128; // threads per CTA
+  static constexpr int NTY = NT / LPR;                                // thread rows of the register tile
+  static constexpr int R = 64;                                        // rows per tile
+  static constexpr int TM = R / NTY;                                  // rows per thread
+  static constexpr int LD = D + 4;                                    // padded leading dimension of a smem row tile
+  static constexpr int NW = NT / 32;                                  // warps per CTA
+  static constexpr int G = 32 / LPR;                                  // rows one warp load instruction covers
+  static constexpr int TMW = (D / NTY) > 0 ? (D / NTY) : 1;           // dW rows per thread
 };
 
 constexpr int MAX_K = 64;
+constexpr int MAX_LV = 3;
+
+// which level does this CTA work on?  CTAs [cta_end[l-1], cta_end[l]) own level l.
+struct CtaSlice { int level, local, count; };
+MVIN_DEV CtaSlice cta_slice(const int* cta_end, int nlev) {
+  int l = 0, begin = 0;
+  while (l + 1 < nlev && (int)blockIdx.x >= cta_end[l]) { begin = cta_end[l]; ++l; }
+  CtaSlice s;
+  s.level = l;
+  s.local = (int)blockIdx.x - begin;
+  s.count = cta_end[l] - begin;
+  return s;
+}
 
 // acc[i][0..3] += sum_k As[(ty*TM+i)][k] * Ws[k][tx*4 .. tx*4+3]
 template <int D>
@@ -55,6 +71,57 @@ MVIN_DEV void mm_tile(const float* __restrict__ As, const float* __restrict__ Ws
       }
     }
   }
+}
+
+// dw[i][0..3] += sum_r As[r][ty*TMW+i] * Gs[r][tx*4 .. tx*4+3]      (dW = A^T G over the R rows of a tile)
+template <int D>
+MVIN_DEV void dw_tile(const float* __restrict__ As, const float* __restrict__ Gs, int ty, int tx,
+                      float (&dw)[TC<D>::TMW][4]) {
+  constexpr int TMW = TC<D>::TMW, LD = TC<D>::LD, R = TC<D>::R;
+  if (ty * TMW >= D) return;
+#pragma unroll 4
+  for (int r = 0; r < R; ++r) {
+    const float4 gv = ld4(&Gs[r * LD + tx * 4]);
+    float av[TMW];
+    if constexpr (TMW % 4 == 0) {
+#pragma unroll
+      for (int q = 0; q < TMW / 4; ++q) {
+        const float4 a4 = ld4(&As[r * LD + ty * TMW + q * 4]);
+        av[q * 4 + 0] = a4.x; av[q * 4 + 1] = a4.y; av[q * 4 + 2] = a4.z; av[q * 4 + 3] = a4.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < TMW; ++i) av[i] = As[r * LD + ty * TMW + i];
+    }
+#pragma unroll
+    for (int i = 0; i < TMW; ++i) {
+      dw[i][0] = fmaf(av[i], gv.x, dw[i][0]);
+      dw[i][1] = fmaf(av[i], gv.y, dw[i][1]);
+      dw[i][2] = fmaf(av[i], gv.z, dw[i][2]);
+      dw[i][3] = fmaf(av[i], gv.w, dw[i][3]);
+    }
+  }
+}
+
+// CTA-level flush of the register-resident weight gradient (and of the per-thread bias partial) to global memory
+template <int D>
+MVIN_DEV void dw_flush(float (&dw)[TC<D>::TMW][4], float* __restrict__ dW, int ty, int tx) {
+  constexpr int TMW = TC<D>::TMW;
+  if (ty * TMW >= D) return;
+#pragma unroll
+  for (int i = 0; i < TMW; ++i)
+    red_add4(dW + (long)(ty * TMW + i) * D + tx * 4, make_float4(dw[i][0], dw[i][1], dw[i][2], dw[i][3]));
+}
+// red[D] (shared, zeroed) += per-thread column partials, then one global atomic per column
+template <int D>
+MVIN_DEV void bias_flush(float4 part, float* __restrict__ red, float* __restrict__ db, int tid, int tx) {
+  atomicAdd(&red[tx * 4 + 0], part.x);
+  atomicAdd(&red[tx * 4 + 1], part.y);
+  atomicAdd(&red[tx * 4 + 2], part.z);
+  atomicAdd(&red[tx * 4 + 3], part.w);
+  __syncthreads();
+  if (tid < D) atomicAdd(db + tid, red[tid]);
+  __syncthreads();
 }
 
 template <int D>
@@ -92,19 +159,56 @@ MVIN_DEV Att attend(const int32_t* __restrict__ arow, int K, const float* __rest
   return a;
 }
 
+// accumulate per-pair sums of the rows of a smem tile into du[B, D]; rows of one pair are contiguous, so each
+// thread walks a strip of the tile and flushes one atomic per (pair, column) run.
+template <int D>
+MVIN_DEV void tile_rows_to_pairs(const float* __restrict__ As, float* __restrict__ du, long row0, long rows,
+                                 int rpp, int tid) {
+  using C = TC<D>;
+  constexpr int PARTS = (C::NT / D) < C::R ? (C::NT / D) : C::R;
+  constexpr int RPS = C::R / PARTS;                   // rows per strip
+  const int col = tid % D, part = tid / D;
+  if (part >= PARTS) return;
+  long cur = -1;
+  float acc = 0.f;
+#pragma unroll 4
+  for (int r = part * RPS; r < (part + 1) * RPS; ++r) {
+    const long row = row0 + r;
+    if (row >= rows) break;
+    const long b = row / rpp;
+    if (b != cur) {
+      if (cur >= 0) atomicAdd(du + cur * D + col, acc);
+      cur = b;
+      acc = 0.f;
+    }
+    acc += As[r * C::LD + col];
+  }
+  if (cur >= 0) atomicAdd(du + cur * D + col, acc);
+}
+
 // ---------------------------------------------------------------------------------------------------------
-// user-oriented transform  T = (E[ent] + u) . W_t[h] + b_t[h]      (model.py:270-283), levels h < L
+// user-oriented transform  T = (E[ent] + u) . W_t[h] + b_t[h]      (model.py:270-283), levels h < L, one launch
 // ---------------------------------------------------------------------------------------------------------
-struct TransformArgs {
+struct TransformLevel {
   const int32_t* ent;   // [rows]
-  const float* E;       // entity table
-  const float* u;       // [B, D]  user_o
-  const float* W;       // [D, D]
+  const float* W;       // [D, D]   W_t[h]   (backward: W_t[h] transposed)
   const float* b;       // [D]
-  float* XU;            // [rows, D]  E[ent] + u   (kept for dW_t)
-  float* T;             // [rows, D]
+  float* T;             // fwd out [rows, D]
+  const float* g1;      // bwd in  [rows, D]  dT = g1 (+ g2)
+  const float* g2;      // bwd in, optional
+  float* dW;            // bwd out [D, D]  (accumulated)
+  float* db;            // bwd out [D]
   long rows;
   int rpp;              // rows per pair = K^h
+};
+struct TransformArgs {
+  TransformLevel lv[MAX_LV];
+  int nlev;
+  int cta_end[MAX_LV];
+  const float* E;       // entity table
+  const float* u;       // [B, D]  user_o
+  float* dE;            // bwd: entity-table gradient (scatter-add)
+  float* du;            // bwd: [B, D] (accumulated)
 };
 
 template <int D>
@@ -114,20 +218,21 @@ __global__ void __launch_bounds__(TC<D>::NT) transform_fwd_kernel(TransformArgs 
   float* Ws = smem;
   float* As = Ws + D * D;
   const int tid = threadIdx.x, tx = tid % C::LPR, ty = tid / C::LPR;
-  load_weight<D>(Ws, a.W, tid);
-  const float4 bias = ldg4(a.b + tx * 4);
-  const long ntiles = (a.rows + C::R - 1) / C::R;
-  for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  const CtaSlice cs = cta_slice(a.cta_end, a.nlev);
+  const TransformLevel& L = a.lv[cs.level];
+  load_weight<D>(Ws, L.W, tid);
+  const float4 bias = ldg4(L.b + tx * 4);
+  const long ntiles = (L.rows + C::R - 1) / C::R;
+  for (long t = cs.local; t < ntiles; t += cs.count) {
     const long row0 = t * C::R;
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) {
       const int r = ty * C::TM + i;
       const long row = row0 + r;
       float4 x = f4zero();
-      if (row < a.rows) {
-        const long e = a.ent[row];
-        x = f4add(ldg4(a.E + e * D + tx * 4), ldg4(a.u + (row / a.rpp) * D + tx * 4));
-        st4(a.XU + row * D + tx * 4, x);
+      if (row < L.rows) {
+        const long e = L.ent[row];
+        x = f4add(ldg4(a.E + e * D + tx * 4), ldg4(a.u + (row / L.rpp) * D + tx * 4));
       }
       st4(&As[r * C::LD + tx * 4], x);
     }
@@ -139,64 +244,52 @@ __global__ void __launch_bounds__(TC<D>::NT) transform_fwd_kernel(TransformArgs 
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) {
       const long row = row0 + ty * C::TM + i;
-      if (row < a.rows) st4(a.T + row * D + tx * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+      if (row < L.rows) st4(L.T + row * D + tx * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
     }
     __syncthreads();
   }
 }
 
-// accumulate per-pair sums of the rows of a smem tile into du[B, D]; rows of one pair are contiguous, so each
-// of D threads walks the tile and flushes one atomic per (pair, column) run.
+// backward: dT = g1 (+ g2);  dW_t[h] += XU^T dT with XU = E[ent] + u recomputed;  db += sum dT;
+//           gx = dT . W_t[h]^T ;  dE[ent] += gx ;  du[b] += sum_rows gx
 template <int D>
-MVIN_DEV void tile_rows_to_pairs(const float* __restrict__ As, float* __restrict__ du, long row0, long rows,
-                                 int rpp, int tid) {
-  using C = TC<D>;
-  if (tid < D) {
-    long cur = -1;
-    float acc = 0.f;
-    for (int r = 0; r < C::R; ++r) {
-      const long row = row0 + r;
-      if (row >= rows) break;
-      const long b = row / rpp;
-      if (b != cur) {
-        if (cur >= 0) atomicAdd(du + cur * D + tid, acc);
-        cur = b;
-        acc = 0.f;
-      }
-      acc += As[r * C::LD + tid];
-    }
-    if (cur >= 0) atomicAdd(du + cur * D + tid, acc);
-  }
-}
-
-struct TransformBwdArgs {
-  const int32_t* ent;   // [rows]
-  const float* dT;      // [rows, D]
-  const float* WT;      // [D, D]  W_t[h] transposed
-  float* dE;            // entity-table gradient (scatter-add)
-  float* du;            // [B, D]  (accumulated)
-  long rows;
-  int rpp;
-};
-
-template <int D>
-__global__ void __launch_bounds__(TC<D>::NT) transform_bwd_kernel(TransformBwdArgs a) {
+__global__ void __launch_bounds__(TC<D>::NT) transform_bwd_kernel(TransformArgs a) {
   using C = TC<D>;
   extern __shared__ __align__(16) float smem[];
   float* Ws = smem;
-  float* As = Ws + D * D;
+  float* As = Ws + D * D;                 // dT tile, later gx tile
+  float* Xs = As + C::R * C::LD;          // XU tile
+  float* red = Xs + C::R * C::LD;         // [D]
   const int tid = threadIdx.x, tx = tid % C::LPR, ty = tid / C::LPR;
-  load_weight<D>(Ws, a.WT, tid);
-  const long ntiles = (a.rows + C::R - 1) / C::R;
-  for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  const CtaSlice cs = cta_slice(a.cta_end, a.nlev);
+  const TransformLevel& L = a.lv[cs.level];
+  load_weight<D>(Ws, L.W, tid);
+  if (tid < D) red[tid] = 0.f;
+  float dw[C::TMW][4];
+#pragma unroll
+  for (int i = 0; i < C::TMW; ++i) dw[i][0] = dw[i][1] = dw[i][2] = dw[i][3] = 0.f;
+  float4 bpart = f4zero();
+  __syncthreads();
+  const long ntiles = (L.rows + C::R - 1) / C::R;
+  for (long t = cs.local; t < ntiles; t += cs.count) {
     const long row0 = t * C::R;
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) {
       const int r = ty * C::TM + i;
       const long row = row0 + r;
-      st4(&As[r * C::LD + tx * 4], row < a.rows ? ld4(a.dT + row * D + tx * 4) : f4zero());
+      float4 g = f4zero(), x = f4zero();
+      if (row < L.rows) {
+        g = ld4(L.g1 + row * D + tx * 4);
+        if (L.g2) g = f4add(g, ld4(L.g2 + row * D + tx * 4));
+        const long e = L.ent[row];
+        x = f4add(ldg4(a.E + e * D + tx * 4), ldg4(a.u + (row / L.rpp) * D + tx * 4));
+      }
+      bpart = f4add(bpart, g);
+      st4(&As[r * C::LD + tx * 4], g);
+      st4(&Xs[r * C::LD + tx * 4], x);
     }
     __syncthreads();
+    dw_tile<D>(Xs, As, ty, tx, dw);
     float acc[C::TM][4];
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
@@ -207,97 +300,112 @@ __global__ void __launch_bounds__(TC<D>::NT) transform_bwd_kernel(TransformBwdAr
       const int r = ty * C::TM + i;
       const long row = row0 + r;
       const float4 gx = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-      if (row < a.rows) red_add4(a.dE + (long)a.ent[row] * D + tx * 4, gx);
+      if (row < L.rows) red_add4(a.dE + (long)L.ent[row] * D + tx * 4, gx);
       st4(&As[r * C::LD + tx * 4], gx);
     }
     __syncthreads();
-    tile_rows_to_pairs<D>(As, a.du, row0, a.rows, a.rpp, tid);
+    tile_rows_to_pairs<D>(As, a.du, row0, L.rows, L.rpp, tid);
     __syncthreads();
   }
+  dw_flush<D>(dw, L.dW, ty, tx);
+  bias_flush<D>(bpart, red, L.db, tid, tx);
 }
 
+template <int D>
+constexpr size_t transform_fwd_smem() { return sizeof(float) * (D * D + TC<D>::R * TC<D>::LD); }
+template <int D>
+constexpr size_t transform_bwd_smem() { return sizeof(float) * (D * D + 2 * TC<D>::R * TC<D>::LD + D); }
+
 // ---------------------------------------------------------------------------------------------------------
-// one aggregation step, forward  (aggregators.py:98-146; model.py:295-306)
-//   LEAF = false:  agg = (1/K) sum_k p_k child[row*K+k]          (children are the rows of the next level)
-//   LEAF = true :  S = sum_k p_k E[adj[e][k]];  agg = ((S + u) . W_t[L] + b_t[L]) / K     (hoisted transform)
+// one aggregator iteration, forward, all levels  (aggregators.py:98-146; model.py:295-306)
+//   inner level:  agg = (1/K) sum_k p_k child[row*K+k]          (children are the rows of the next level)
+//   leaf level :  S = sum_k p_k E[adj[e][k]];  agg = ((S + u) . W_t[L] + b_t[L]) / K     (hoisted transform)
 //   Y = self + agg;   V = relu(Y . W_a + b_a)
 // ---------------------------------------------------------------------------------------------------------
-struct AggArgs {
+struct AggLevel {
   const int32_t* ent;   // [rows] entity id of each node of this level
-  const int32_t* adj;   // packed adjacency [n_entity][2][K]
-  const float* s;       // [n_rel] relation scores of this aggregator
-  const float* child;   // !LEAF: [rows*K, D]
-  const float* E;       //  LEAF: entity table
-  const float* u;       //  LEAF: [B, D]
-  const float* Wt;      //  LEAF: W_t[L] [D, D]
-  const float* bt;      //  LEAF: b_t[L]
+  const float* child;   // inner: [rows*K, D]
   const float* self;    // [rows, D]
-  const float* Wa;      // [D, D]
-  const float* ba;      // [D]
-  float* SU;            //  LEAF: [rows, D]  S + u
+  float* SU;            // leaf: [rows, D]  S + u
   float* Y;             // [rows, D]
   float* V;             // [rows, D]
-  float* probs;         // optional [rows, K]
   long rows;
-  int rpp, K, n_rel;
+  int rpp;
+  int leaf;
+};
+struct AggArgs {
+  AggLevel lv[MAX_LV];
+  int nlev;
+  int cta_end[MAX_LV];
+  const int32_t* adj;   // packed adjacency [n_entity][2][K]
+  const float* s;       // [n_rel] relation scores of this aggregator
+  const float* E;       // leaf: entity table
+  const float* u;       // leaf: [B, D]
+  const float* Wt;      // leaf: W_t[L] [D, D]
+  const float* bt;      // leaf: b_t[L]
+  const float* Wa;      // [D, D]
+  const float* ba;      // [D]
+  int K, n_rel;
 };
 
-template <int D, bool LEAF>
+template <int D, bool HAS_LEAF>
 __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
   using C = TC<D>;
   extern __shared__ __align__(16) float smem[];
   float* Wa_s = smem;
   float* Wt_s = Wa_s + D * D;
-  float* As = Wt_s + (LEAF ? D * D : 0);
-  float* pw = As + C::R * C::LD;                      // [NW][MAX_K]
+  float* As = Wt_s + (HAS_LEAF ? D * D : 0);
+  float* pw = As + C::R * C::LD;                           // [NW][MAX_K]
   int* idw = reinterpret_cast<int*>(pw + C::NW * MAX_K);   // [NW][MAX_K]
   float* s_s = reinterpret_cast<float*>(idw + C::NW * MAX_K);
   const int tid = threadIdx.x, tx = tid % C::LPR, ty = tid / C::LPR;
   const int warp = tid / 32, lane = tid % 32, g = lane / C::LPR, c = lane % C::LPR;
+  const CtaSlice cs = cta_slice(a.cta_end, a.nlev);
+  const AggLevel& L = a.lv[cs.level];
+  const bool leaf = HAS_LEAF && L.leaf;
   load_weight<D>(Wa_s, a.Wa, tid);
-  if (LEAF) load_weight<D>(Wt_s, a.Wt, tid);
+  if (leaf) load_weight<D>(Wt_s, a.Wt, tid);
   for (int i = tid; i < a.n_rel; i += C::NT) s_s[i] = a.s[i];
   const float4 ba = ldg4(a.ba + tx * 4);
   float4 bt = f4zero();
-  if (LEAF) bt = ldg4(a.bt + tx * 4);
+  if (leaf) bt = ldg4(a.bt + tx * 4);
   const int K = a.K;
   const float invK = 1.f / (float)K;
   float* pw_w = pw + warp * MAX_K;
   int* idw_w = idw + warp * MAX_K;
   __syncthreads();
 
-  const long ntiles = (a.rows + C::R - 1) / C::R;
-  for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  const long ntiles = (L.rows + C::R - 1) / C::R;
+  for (long t = cs.local; t < ntiles; t += cs.count) {
     const long row0 = t * C::R;
     // ---- neighbour phase: warp per row ----
     for (int r = warp; r < C::R; r += C::NW) {
       const long row = row0 + r;
-      if (row < a.rows) {
-        const long e = a.ent[row];
+      if (row < L.rows) {
+        const long e = L.ent[row];
         const Att at = attend(a.adj + e * 2 * K, K, s_s, lane);
         pw_w[lane] = at.p0;
         pw_w[lane + 32] = at.p1;
-        if (LEAF) { idw_w[lane] = at.id0; idw_w[lane + 32] = at.id1; }
-        if (a.probs) {
-          if (lane < K) a.probs[row * K + lane] = at.p0;
-          if (lane + 32 < K) a.probs[row * K + lane + 32] = at.p1;
-        }
+        if (leaf) { idw_w[lane] = at.id0; idw_w[lane + 32] = at.id1; }
         __syncwarp();
         float4 acc = f4zero();
+        if (leaf) {
 #pragma unroll 4
-        for (int k = g; k < K; k += C::G) {
-          const float* src = LEAF ? a.E + (long)idw_w[k] * D : a.child + (row * K + k) * D;
-          acc = f4fma(pw_w[k], ldg4(src + c * 4), acc);
+          for (int k = g; k < K; k += C::G) acc = f4fma(pw_w[k], ldg4(a.E + (long)idw_w[k] * D + c * 4), acc);
+        } else {
+          const float* base = L.child + row * K * D + c * 4;
+#pragma unroll 4
+          for (int k = g; k < K; k += C::G) acc = f4fma(pw_w[k], ldg4(base + (long)k * D), acc);
         }
         acc = cross_group_sum4<C::LPR>(acc);
         if (g == 0) {
           float4 o;
-          if (LEAF) {
-            o = f4add(acc, ldg4(a.u + (row / a.rpp) * D + c * 4));
-            st4(a.SU + row * D + c * 4, o);
+          if (leaf) {
+            o = f4add(acc, ldg4(a.u + (row / L.rpp) * D + c * 4));
+            st4(L.SU + row * D + c * 4, o);
           } else {
-            o = f4fma(invK, acc, ld4(a.self + row * D + c * 4));
-            st4(a.Y + row * D + c * 4, o);
+            o = f4fma(invK, acc, ld4(L.self + row * D + c * 4));
+            st4(L.Y + row * D + c * 4, o);
           }
           st4(&As[r * C::LD + c * 4], o);
         }
@@ -309,7 +417,7 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
     __syncthreads();
     // ---- dense phase: register tile ----
     float acc[C::TM][4];
-    if (LEAF) {
+    if (leaf) {
 #pragma unroll
       for (int i = 0; i < C::TM; ++i) { acc[i][0] = bt.x; acc[i][1] = bt.y; acc[i][2] = bt.z; acc[i][3] = bt.w; }
       mm_tile<D>(As, Wt_s, ty, tx, acc);
@@ -319,9 +427,9 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
         const int r = ty * C::TM + i;
         const long row = row0 + r;
         float4 y = f4zero();
-        if (row < a.rows) {
-          y = f4fma(invK, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]), ld4(a.self + row * D + tx * 4));
-          st4(a.Y + row * D + tx * 4, y);
+        if (row < L.rows) {
+          y = f4fma(invK, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]), ld4(L.self + row * D + tx * 4));
+          st4(L.Y + row * D + tx * 4, y);
         }
         st4(&As[r * C::LD + tx * 4], y);
       }
@@ -333,91 +441,122 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) {
       const long row = row0 + ty * C::TM + i;
-      if (row < a.rows)
-        st4(a.V + row * D + tx * 4, make_float4(fmaxf(acc[i][0], 0.f), fmaxf(acc[i][1], 0.f), fmaxf(acc[i][2], 0.f),
+      if (row < L.rows)
+        st4(L.V + row * D + tx * 4, make_float4(fmaxf(acc[i][0], 0.f), fmaxf(acc[i][1], 0.f), fmaxf(acc[i][2], 0.f),
                                                 fmaxf(acc[i][3], 0.f)));
     }
     __syncthreads();
   }
 }
 
-template <int D, bool LEAF>
+template <int D, bool HAS_LEAF>
 constexpr size_t agg_fwd_smem(int n_rel) {
-  return sizeof(float) * ((LEAF ? 2 : 1) * D * D + TC<D>::R * TC<D>::LD + 2 * TC<D>::NW * MAX_K + n_rel);
+  return sizeof(float) * ((HAS_LEAF ? 2 : 1) * D * D + TC<D>::R * TC<D>::LD + 2 * TC<D>::NW * MAX_K + n_rel);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// one aggregation step, backward (Appendix B of SURVEY.md; tests/fused_model.py is the CPU twin)
-//   gz = gout * [V > 0]            (written in place over gout: it is the G operand of dW_a = Y^T gz)
-//   gs = gz . W_a^T ;  dself (+)= gs ;  grow = gs / K
-//   !LEAF: dchild[row*K+k] = p_k * grow ; dp_k = grow . child_k
-//    LEAF: GROW[row] = grow (G operand of dW_t[L] = SU^T grow);  gsu = grow . W_t[L]^T ;  du[b] += gsu ;
+// one aggregator iteration, backward, all levels (Appendix B of SURVEY.md; tests/fused_model.py is the CPU twin)
+//   gout = g1 (+ g2) ;  gz = gout * [V > 0] ;  dW_a += Y^T gz ;  db_a += sum gz
+//   gs = gz . W_a^T ;  dself = gs ;  grow = gs / K
+//   inner: dchild[row*K+k] = p_k * grow ; dp_k = grow . child_k
+//   leaf : dW_t[L] += SU^T grow ; db_t[L] += sum grow ;  gsu = grow . W_t[L]^T ;  du[b] += gsu ;
 //          dE[n_k] += p_k * gsu ;  dp_k = gsu . E[n_k]
 //   dlogit_k = p_k (dp_k - sum_j p_j dp_j) ;  ds[rel_k] += dlogit_k
+// The gradient of a node's output arrives from up to two producers (its own aggregator step one iteration later
+// and its parent's dchild); they are summed on load (g1 + g2) instead of read-modify-written, so every level of an
+// iteration is independent and shares one launch.
 // ---------------------------------------------------------------------------------------------------------
-struct AggBwdArgs {
+struct AggBwdLevel {
   const int32_t* ent;
+  const float* child;   // inner
+  const float* V;       // [rows, D] forward output (ReLU mask)
+  const float* Y;       // [rows, D] forward GEMM input
+  const float* SU;      // leaf
+  const float* g1;      // [rows, D]
+  const float* g2;      // optional
+  float* dself;         // [rows, D]
+  float* dchild;        // inner: [rows*K, D]
+  long rows;
+  int rpp;
+  int leaf;
+};
+struct AggBwdArgs {
+  AggBwdLevel lv[MAX_LV];
+  int nlev;
+  int cta_end[MAX_LV];
   const int32_t* adj;
   const float* s;
-  const float* child;   // !LEAF
-  const float* E;       //  LEAF
+  const float* E;       // leaf
   const float* WaT;     // W_a transposed
-  const float* WtT;     //  LEAF: W_t[L] transposed
-  const float* V;       // [rows, D] forward output (ReLU mask)
-  float* gout;          // [rows, D] in: dL/dV; out: gz
-  float* dself;         // [rows, D]
-  float* dchild;        // !LEAF: [rows*K, D]
-  float* GROW;          //  LEAF: [rows, D]
-  float* dE;            //  LEAF
-  float* du;            //  LEAF: [B, D]
+  const float* WtT;     // leaf: W_t[L] transposed
+  float* dWa;           // [D, D]
+  float* dba;           // [D]
+  float* dWt;           // leaf: [D, D]
+  float* dbt;           // leaf: [D]
+  float* dE;            // leaf
+  float* du;            // leaf: [B, D]
   float* ds;            // [n_rel]
-  long rows;
-  int rpp, K, n_rel;
-  int self_accumulate;  // 1: dself += gs, 0: dself = gs
+  int K, n_rel;
 };
 
-template <int D, bool LEAF>
+template <int D, bool HAS_LEAF>
 __global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
   using C = TC<D>;
   extern __shared__ __align__(16) float smem[];
   float* Wa_s = smem;
   float* Wt_s = Wa_s + D * D;
-  float* Gs = Wt_s + (LEAF ? D * D : 0);
-  float* pw = Gs + C::R * C::LD;                       // [NW][MAX_K]
+  float* Gs = Wt_s + (HAS_LEAF ? D * D : 0);
+  float* Ys = Gs + C::R * C::LD;
+  float* pw = Ys + C::R * C::LD;                       // [NW][MAX_K]
   float* dpw = pw + C::NW * MAX_K;                     // [NW][MAX_K]
   int* idw = reinterpret_cast<int*>(dpw + C::NW * MAX_K);
   float* s_s = reinterpret_cast<float*>(idw + C::NW * MAX_K);
   float* ds_s = s_s + a.n_rel;
+  float* red = ds_s + a.n_rel;                         // [2][D]
   const int tid = threadIdx.x, tx = tid % C::LPR, ty = tid / C::LPR;
   const int warp = tid / 32, lane = tid % 32, g = lane / C::LPR, c = lane % C::LPR;
+  const CtaSlice cs = cta_slice(a.cta_end, a.nlev);
+  const AggBwdLevel& L = a.lv[cs.level];
+  const bool leaf = HAS_LEAF && L.leaf;
   load_weight<D>(Wa_s, a.WaT, tid);
-  if (LEAF) load_weight<D>(Wt_s, a.WtT, tid);
+  if (leaf) load_weight<D>(Wt_s, a.WtT, tid);
   for (int i = tid; i < a.n_rel; i += C::NT) { s_s[i] = a.s[i]; ds_s[i] = 0.f; }
+  for (int i = tid; i < 2 * D; i += C::NT) red[i] = 0.f;
   const int K = a.K;
   const float invK = 1.f / (float)K;
   float* pw_w = pw + warp * MAX_K;
   float* dpw_w = dpw + warp * MAX_K;
   int* idw_w = idw + warp * MAX_K;
+  float dwa[C::TMW][4], dwt[HAS_LEAF ? C::TMW : 1][4];
+#pragma unroll
+  for (int i = 0; i < C::TMW; ++i) dwa[i][0] = dwa[i][1] = dwa[i][2] = dwa[i][3] = 0.f;
+#pragma unroll
+  for (int i = 0; i < (HAS_LEAF ? C::TMW : 1); ++i) dwt[i][0] = dwt[i][1] = dwt[i][2] = dwt[i][3] = 0.f;
+  float4 bpa = f4zero(), bpt = f4zero();
   __syncthreads();
 
-  const long ntiles = (a.rows + C::R - 1) / C::R;
-  for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  const long ntiles = (L.rows + C::R - 1) / C::R;
+  for (long t = cs.local; t < ntiles; t += cs.count) {
     const long row0 = t * C::R;
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) {
       const int r = ty * C::TM + i;
       const long row = row0 + r;
-      float4 gz = f4zero();
-      if (row < a.rows) {
-        const float4 go = ld4(a.gout + row * D + tx * 4);
-        const float4 v = ld4(a.V + row * D + tx * 4);
+      float4 gz = f4zero(), y = f4zero();
+      if (row < L.rows) {
+        float4 go = ld4(L.g1 + row * D + tx * 4);
+        if (L.g2) go = f4add(go, ld4(L.g2 + row * D + tx * 4));
+        const float4 v = ld4(L.V + row * D + tx * 4);
         gz = make_float4(v.x > 0.f ? go.x : 0.f, v.y > 0.f ? go.y : 0.f, v.z > 0.f ? go.z : 0.f,
                          v.w > 0.f ? go.w : 0.f);
-        st4(a.gout + row * D + tx * 4, gz);
+        y = ld4(L.Y + row * D + tx * 4);
       }
+      bpa = f4add(bpa, gz);
       st4(&Gs[r * C::LD + tx * 4], gz);
+      st4(&Ys[r * C::LD + tx * 4], y);
     }
     __syncthreads();
+    dw_tile<D>(Ys, Gs, ty, tx, dwa);
     float acc[C::TM][4];
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
@@ -429,15 +568,20 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
       const long row = row0 + r;
       const float4 gs = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
       const float4 grow = f4scale(gs, invK);
-      if (row < a.rows) {
-        float* dst = a.dself + row * D + tx * 4;
-        st4(dst, a.self_accumulate ? f4add(ld4(dst), gs) : gs);
-        if (LEAF) st4(a.GROW + row * D + tx * 4, grow);
+      float4 su = f4zero();
+      if (row < L.rows) {
+        st4(L.dself + row * D + tx * 4, gs);
+        if (leaf) su = ld4(L.SU + row * D + tx * 4);
       }
       st4(&Gs[r * C::LD + tx * 4], grow);
+      if (leaf) {
+        bpt = f4add(bpt, grow);
+        st4(&Ys[r * C::LD + tx * 4], su);
+      }
     }
     __syncthreads();
-    if (LEAF) {
+    if (leaf) {
+      if constexpr (HAS_LEAF) dw_tile<D>(Ys, Gs, ty, tx, dwt);
 #pragma unroll
       for (int i = 0; i < C::TM; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
       mm_tile<D>(Gs, Wt_s, ty, tx, acc);
@@ -446,17 +590,17 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
       for (int i = 0; i < C::TM; ++i)
         st4(&Gs[(ty * C::TM + i) * C::LD + tx * 4], make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
       __syncthreads();
-      tile_rows_to_pairs<D>(Gs, a.du, row0, a.rows, a.rpp, tid);
+      tile_rows_to_pairs<D>(Gs, a.du, row0, L.rows, L.rpp, tid);
     }
     // ---- neighbour phase: warp per row ----
     for (int r = warp; r < C::R; r += C::NW) {
       const long row = row0 + r;
-      if (row >= a.rows) break;
-      const long e = a.ent[row];
+      if (row >= L.rows) break;
+      const long e = L.ent[row];
       const Att at = attend(a.adj + e * 2 * K, K, s_s, lane);
       pw_w[lane] = at.p0;
       pw_w[lane + 32] = at.p1;
-      if (LEAF) { idw_w[lane] = at.id0; idw_w[lane + 32] = at.id1; }
+      if (leaf) { idw_w[lane] = at.id0; idw_w[lane + 32] = at.id1; }
       __syncwarp();
       const float4 gr = ld4(&Gs[r * C::LD + c * 4]);
       // uniform trip count: the shuffles inside need every lane of the warp
@@ -467,14 +611,14 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
         float part = 0.f;
         if (valid) {
           const float pk = pw_w[k];
-          if (LEAF) {
+          if (leaf) {
             const long n = idw_w[k];
             part = f4dot(gr, ldg4(a.E + n * D + c * 4));
             red_add4(a.dE + n * D + c * 4, f4scale(gr, pk));
           } else {
             const long cr = (row * K + k) * D + c * 4;
-            part = f4dot(gr, ld4(a.child + cr));
-            st4(a.dchild + cr, f4scale(gr, pk));
+            part = f4dot(gr, ld4(L.child + cr));
+            st4(L.dchild + cr, f4scale(gr, pk));
           }
         }
         part = group_sum<C::LPR>(part);
@@ -491,75 +635,74 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
     __syncthreads();
   }
   for (int i = tid; i < a.n_rel; i += C::NT) atomicAdd(a.ds + i, ds_s[i]);
+  dw_flush<D>(dwa, a.dWa, ty, tx);
+  bias_flush<D>(bpa, red, a.dba, tid, tx);
+  if (leaf) {
+    if constexpr (HAS_LEAF) dw_flush<D>(dwt, a.dWt, ty, tx);
+    bias_flush<D>(bpt, red + D, a.dbt, tid, tx);
+  }
 }
 
-template <int D, bool LEAF>
+template <int D, bool HAS_LEAF>
 constexpr size_t agg_bwd_smem(int n_rel) {
-  return sizeof(float) * ((LEAF ? 2 : 1) * D * D + TC<D>::R * TC<D>::LD + 3 * TC<D>::NW * MAX_K + 2 * n_rel);
+  return sizeof(float) *
+         ((HAS_LEAF ? 2 : 1) * D * D + 2 * TC<D>::R * TC<D>::LD + 3 * TC<D>::NW * MAX_K + 2 * n_rel + 2 * D);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// dW[i][j] += sum_r A[r][i] G[r][j];  db[j] += sum_r G[r][j]   over rows of A [rows, D] (row stride lda) and
-// G [rows, D]
-// (the weight gradients of every d x d map on the path)
+// grouped weight gradient for the B-row maps (mix layer, user MLP):
+//   dW_g[i][j] += sum_r A_g[r][i] G[r][j];  db[j] += sum_r G[r][j] (group 0 only)    blockIdx.y = group g
 // ---------------------------------------------------------------------------------------------------------
+constexpr int MAX_DW_GROUPS = 8;
+struct DwArgs {
+  const float* A[MAX_DW_GROUPS];
+  long lda[MAX_DW_GROUPS];
+  float* dW[MAX_DW_GROUPS];
+  const float* G;       // [rows, D]
+  float* db;            // [D] or nullptr
+  long rows;
+};
+
 template <int D>
-__global__ void __launch_bounds__(TC<D>::NT) dw_kernel(const float* __restrict__ A, long lda,
-                                                       const float* __restrict__ Gm, long rows,
-                                                       float* __restrict__ dW, float* __restrict__ db) {
+__global__ void __launch_bounds__(TC<D>::NT) dw_kernel(DwArgs a) {
   using C = TC<D>;
   extern __shared__ __align__(16) float smem[];
   float* As = smem;
   float* Gs = As + C::R * C::LD;
+  float* red = Gs + C::R * C::LD;
   const int tid = threadIdx.x, tx = tid % C::LPR, ty = tid / C::LPR;
-  const bool active = ty * C::TMW < D;
-  float acc[C::TMW][4];
+  const int grp = blockIdx.y;
+  const float* A = a.A[grp];
+  const long lda = a.lda[grp];
+  const bool do_bias = (grp == 0 && a.db != nullptr);
+  if (tid < D) red[tid] = 0.f;
+  float dw[C::TMW][4];
 #pragma unroll
-  for (int i = 0; i < C::TMW; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-  float bsum = 0.f;
-  const long ntiles = (rows + C::R - 1) / C::R;
+  for (int i = 0; i < C::TMW; ++i) dw[i][0] = dw[i][1] = dw[i][2] = dw[i][3] = 0.f;
+  float4 bpart = f4zero();
+  __syncthreads();
+  const long ntiles = (a.rows + C::R - 1) / C::R;
   for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const long row0 = t * C::R;
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) {
       const int r = ty * C::TM + i;
       const long row = row0 + r;
-      const bool ok = row < rows;
+      const bool ok = row < a.rows;
+      const float4 gv = ok ? ld4(a.G + row * D + tx * 4) : f4zero();
+      bpart = f4add(bpart, gv);
       st4(&As[r * C::LD + tx * 4], ok ? ld4(A + row * lda + tx * 4) : f4zero());
-      st4(&Gs[r * C::LD + tx * 4], ok ? ld4(Gm + row * D + tx * 4) : f4zero());
+      st4(&Gs[r * C::LD + tx * 4], gv);
     }
     __syncthreads();
-    if (active) {
-#pragma unroll 4
-      for (int r = 0; r < C::R; ++r) {
-        const float4 gv = ld4(&Gs[r * C::LD + tx * 4]);
-#pragma unroll
-        for (int i = 0; i < C::TMW; ++i) {
-          const float av = As[r * C::LD + ty * C::TMW + i];
-          acc[i][0] = fmaf(av, gv.x, acc[i][0]);
-          acc[i][1] = fmaf(av, gv.y, acc[i][1]);
-          acc[i][2] = fmaf(av, gv.z, acc[i][2]);
-          acc[i][3] = fmaf(av, gv.w, acc[i][3]);
-        }
-      }
-    }
-    if (tid < D) {
-#pragma unroll 8
-      for (int r = 0; r < C::R; ++r) bsum += Gs[r * C::LD + tid];
-    }
+    dw_tile<D>(As, Gs, ty, tx, dw);
     __syncthreads();
   }
-  if (active) {
-#pragma unroll
-    for (int i = 0; i < C::TMW; ++i) {
-      float* dst = dW + (long)(ty * C::TMW + i) * D + tx * 4;
-      atomicAdd(dst + 0, acc[i][0]);
-      atomicAdd(dst + 1, acc[i][1]);
-      atomicAdd(dst + 2, acc[i][2]);
-      atomicAdd(dst + 3, acc[i][3]);
-    }
-  }
-  if (db != nullptr && tid < D) atomicAdd(db + tid, bsum);
+  dw_flush<D>(dw, a.dW[grp], ty, tx);
+  if (do_bias) bias_flush<D>(bpart, red, a.db, tid, tx);
 }
+
+template <int D>
+constexpr size_t dw_smem() { return sizeof(float) * (2 * TC<D>::R * TC<D>::LD + D); }
 
 }  // namespace mvin

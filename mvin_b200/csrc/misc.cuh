@@ -200,10 +200,12 @@ __global__ void finalize_loss_kernel(const float* __restrict__ acc, float l2w, f
   }
 }
 
-// ---- [nmat, D, D] -> transposed copies -------------------------------------------------------------------
-__global__ void transpose_kernel(const float* __restrict__ src, int D, float* __restrict__ dst) {
-  const float* s = src + (long)blockIdx.x * D * D;
-  float* d = dst + (long)blockIdx.x * D * D;
+// ---- transposed copies of the d x d weights: dst[i] = W_a[i]^T (i < H), dst[H + e] = W_t[e]^T (e <= H) ------
+__global__ void transpose_kernel(const float* __restrict__ agg_w, const float* __restrict__ transfer_w, int H, int D,
+                                 float* __restrict__ dst) {
+  const int b = blockIdx.x;
+  const float* s = b < H ? agg_w + (long)b * D * D : transfer_w + (long)(b - H) * D * D;
+  float* d = dst + (long)b * D * D;
   for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
     const int r = i / D, c = i % D;
     d[c * D + r] = s[i];

@@ -53,16 +53,21 @@ constexpr int MAX_L = 3;
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 // Workspace layout for batch size B (all offsets in bytes from the workspace base).
+//   V[j][h]   output of aggregator iteration j-1 at level h (V[0][h] = T[h], the user-oriented transform); the
+//             level-0 slices V[0..H][0] are contiguous (Vtop) so the mix layer is one batch-reduce GEMM
+//   Y[i][h]   GEMM input (self + agg) of aggregator iteration i at level h
+//   DC[j][h]  gradient of V[j][h] arriving from its parent's dchild (h >= 1) or from the mix layer (h = 0)
+//   DS[j][h]  gradient of V[j][h] arriving from its own aggregator step (iteration j, level h)
 struct Layout {
   size_t ent[MAX_L];                      // int32 [B K^h], h < L
   size_t Vbuf, Q, probs, O, u, s;         // ripple side + relation scores
-  size_t XU[MAX_L], T[MAX_L], SU;         // user-oriented transform
-  size_t Y[MAX_L][MAX_L];                 // Y[i][h], i < H, h < L - i
-  size_t V[MAX_L + 1][MAX_L];             // V[j][h], 1 <= j <= H, h < L - j + 1   (V[0] aliases T)
+  size_t SU;                              // leaf: S + u
+  size_t Y[MAX_L][MAX_L];                 // Y[i][h], i < H, h < H - i
+  size_t V[MAX_L + 1][MAX_L];             // V[j][h]
   size_t item, scores;
   // backward
-  size_t dV[MAX_L + 1][MAX_L];            // dV[0][h] = dT[h]
-  size_t GROW, du, ditem, dO, wT;         // wT: [H + L + 1][D][D] transposed weights
+  size_t DC[MAX_L + 1][MAX_L], DS[MAX_L][MAX_L];
+  size_t du, ditem, dO, wT;               // wT: [H + H + 1][D][D] transposed weights
   size_t zero_begin, dQ, ds, cnt, acc, zero_end;   // region cleared at the start of every backward
   size_t total;
   long rows[MAX_L + 1];
@@ -101,6 +106,9 @@ void prof_mark(mvin_handle_t h, cudaStream_t st, const char* name) {
   h->prof.push_back({name, ev});
 }
 
+inline bool has_agg(int H, int i, int h) { return i < H && h < H - i; }          // aggregator step (i, h) exists
+inline bool has_V(int H, int j, int h) { return j == 0 ? h < H : h <= H - j; }   // buffer V[j][h] exists
+
 Layout make_layout(const mvin_config_t& c, long B) {
   Layout L;
   memset(&L, 0, sizeof(L));
@@ -121,18 +129,21 @@ Layout make_layout(const mvin_config_t& c, long B) {
   L.O = take(f * B * (p + 1) * D);
   L.u = take(f * B * D);
   L.s = take(f * H * nr);
-  for (int h = 0; h < H; ++h) { L.XU[h] = take(f * L.rows[h] * D); L.T[h] = take(f * L.rows[h] * D); }
   L.SU = take(f * L.rows[H - 1] * D);
+  const size_t vtop = take(f * (H + 1) * B * D);
+  for (int j = 0; j <= H; ++j)
+    for (int h = 0; h < MAX_L; ++h)
+      if (has_V(H, j, h)) L.V[j][h] = h == 0 ? vtop + f * j * B * D : take(f * L.rows[h] * D);
   for (int i = 0; i < H; ++i)
     for (int h = 0; h < H - i; ++h) L.Y[i][h] = take(f * L.rows[h] * D);
-  for (int h = 0; h < H; ++h) L.V[0][h] = L.T[h];
-  for (int j = 1; j <= H; ++j)
-    for (int h = 0; h < H - j + 1; ++h) L.V[j][h] = take(f * L.rows[h] * D);
   L.item = take(f * B * D);
   L.scores = take(f * B);
+  const size_t dtop = take(f * (H + 1) * B * D);
   for (int j = 0; j <= H; ++j)
-    for (int h = 0; h < (j == 0 ? H : H - j + 1); ++h) L.dV[j][h] = take(f * L.rows[h] * D);
-  L.GROW = take(f * L.rows[H - 1] * D);
+    for (int h = 0; h < MAX_L; ++h)
+      if (has_V(H, j, h)) L.DC[j][h] = h == 0 ? dtop + f * j * B * D : take(f * L.rows[h] * D);
+  for (int i = 0; i < H; ++i)
+    for (int h = 0; h < H - i; ++h) L.DS[i][h] = take(f * L.rows[h] * D);
   L.du = take(f * B * D);
   L.ditem = take(f * B * D);
   L.dO = take(f * B * (p + 1) * D);
@@ -150,11 +161,11 @@ Layout make_layout(const mvin_config_t& c, long B) {
 template <typename T>
 T* at(void* ws, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(ws) + off); }
 
-int run_gemm(mvin_handle_t h, cudaStream_t st, const GemmArgs& g) {
+int run_gemm(mvin_handle_t h, cudaStream_t st, const GemmArgs& g, const char* name = "gemm") {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return MVIN_OK;
-  dim3 grid((g.N + GEMM_BN - 1) / GEMM_BN, (g.M + GEMM_BM - 1) / GEMM_BM, g.nbatch * g.ksplit);
+  dim3 grid((g.N + GEMM_BN - 1) / GEMM_BN, (g.M + GEMM_BM - 1) / GEMM_BM, (g.reduce ? 1 : g.nbatch) * g.ksplit);
   gemm_kernel<<<grid, GEMM_THREADS, 0, st>>>(g);
-  LAUNCH_CHECK(h, "gemm");
+  LAUNCH_CHECK(h, name);
   return MVIN_OK;
 }
 
@@ -168,7 +179,7 @@ GemmArgs gemm_args() {
 }
 
 int pick_ksplit(long K) {
-  long s = K / 512;
+  long s = K / 128;
   if (s < 1) s = 1;
   if (s > 64) s = 64;
   return (int)s;
@@ -183,18 +194,28 @@ int set_smem(KernelT k, size_t bytes) {
   return MVIN_OK;
 }
 
-int tile_grid(mvin_handle_t h, long rows, int per_sm) {
-  long tiles = (rows + 63) / 64;
-  long cap = (long)h->sm_count * per_sm;
-  return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
-}
-
 // CTAs per SM to aim for, from the kernel's shared-memory footprint
 int ctas_per_sm(size_t smem_bytes, int threads) {
   int by_smem = (int)((220 * 1024) / (smem_bytes + 1024));
   int by_thr = 2048 / threads;
   int n = by_smem < by_thr ? by_smem : by_thr;
   return n < 1 ? 1 : (n > 8 ? 8 : n);
+}
+
+// Split a grid of at most `cap` CTAs between levels in proportion to their tile counts (>= 1 CTA per level); a
+// level never gets more CTAs than tiles.  Returns the grid size and fills cta_end[].
+int partition_grid(const long* rows, int nlev, int cap, int* cta_end) {
+  long tiles[MAX_LV], tot = 0;
+  for (int l = 0; l < nlev; ++l) { tiles[l] = (rows[l] + 63) / 64; if (tiles[l] < 1) tiles[l] = 1; tot += tiles[l]; }
+  int end = 0;
+  for (int l = 0; l < nlev; ++l) {
+    long n = tot <= cap ? tiles[l] : (long)((double)cap * (double)tiles[l] / (double)tot);
+    if (n < 1) n = 1;
+    if (n > tiles[l]) n = tiles[l];
+    end += (int)n;
+    cta_end[l] = end;
+  }
+  return end;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -231,7 +252,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
     g.B = P.relation_kge; g.sb_k = D; g.sb_n = 1; g.bsB = (long)D * D;
     g.C = at<float>(ws, L.Q); g.ldc = (long)nr * D; g.bsC = D;
     g.M = B; g.N = D; g.K = D; g.nbatch = nr;
-    if ((rc = run_gemm(h, st, g))) return rc;
+    if ((rc = run_gemm(h, st, g, "gemm_q"))) return rc;
   }
   // ripple attention (model.py:162-229)
   {
@@ -240,7 +261,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
     a.mem_h = mem_h; a.mem_r = mem_r; a.mem_t = mem_t;
     a.probs = at<float>(ws, L.probs); a.O = at<float>(ws, L.O);
     a.B = B; a.m = m; a.p = p; a.n_rel = nr;
-    const size_t sm = ripple_smem(m, D);
+    const size_t sm = ripple_fwd_smem(m);
     if ((rc = set_smem(ripple_fwd_kernel<D>, sm))) return rc;
     const long warps = (long)B * (p + 1);
     ripple_fwd_kernel<D><<<(unsigned)((warps + RIPPLE_NW - 1) / RIPPLE_NW), RIPPLE_NT, sm, st>>>(a);
@@ -253,7 +274,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
     g.B = P.user_mlp_w; g.sb_k = D; g.sb_n = 1;
     g.C = at<float>(ws, L.u); g.ldc = D; g.bias = P.user_mlp_b;
     g.M = B; g.N = D; g.K = (p + 1) * D;
-    if ((rc = run_gemm(h, st, g))) return rc;
+    if ((rc = run_gemm(h, st, g, "gemm_user"))) return rc;
   }
   // relation scores of every aggregator
   {
@@ -262,59 +283,71 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
                                                                at<float>(ws, L.s));
     LAUNCH_CHECK(h, "rel_scores");
   }
-  // user-oriented transform of levels 0..L-1   (model.py:270-283)
+  // user-oriented transform of levels 0..L-1, one launch   (model.py:270-283)
   {
-    const size_t sm = sizeof(float) * (D * D + C::R * C::LD);
+    const size_t sm = transform_fwd_smem<D>();
     if ((rc = set_smem(transform_fwd_kernel<D>, sm))) return rc;
+    TransformArgs a;
+    memset(&a, 0, sizeof(a));
+    long rows[MAX_LV];
     for (int lv = 0; lv < H; ++lv) {
-      TransformArgs a;
-      a.ent = at<int32_t>(ws, L.ent[lv]); a.E = P.entity_emb; a.u = at<float>(ws, L.u);
-      a.W = P.transfer_w + (long)lv * D * D; a.b = P.transfer_b + (long)lv * D;
-      a.XU = at<float>(ws, L.XU[lv]); a.T = at<float>(ws, L.T[lv]);
-      a.rows = L.rows[lv]; a.rpp = (int)(L.rows[lv] / B);
-      transform_fwd_kernel<D><<<tile_grid(h, a.rows, ctas_per_sm(sm, C::NT)), C::NT, sm, st>>>(a);
-      LAUNCH_CHECK(h, "transform_fwd");
+      TransformLevel& t = a.lv[lv];
+      t.ent = at<int32_t>(ws, L.ent[lv]);
+      t.W = P.transfer_w + (long)lv * D * D; t.b = P.transfer_b + (long)lv * D;
+      t.T = at<float>(ws, L.V[0][lv]);
+      t.rows = rows[lv] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B);
     }
+    a.nlev = H; a.E = P.entity_emb; a.u = at<float>(ws, L.u);
+    const int grid = partition_grid(rows, H, h->sm_count * ctas_per_sm(sm, C::NT), a.cta_end);
+    transform_fwd_kernel<D><<<grid, C::NT, sm, st>>>(a);
+    LAUNCH_CHECK(h, "transform_fwd");
   }
-  // aggregation iterations (model.py:286-307)
+  // aggregation iterations (model.py:286-307): one launch per iteration, every level of it
   {
     const size_t sm_leaf = agg_fwd_smem<D, true>(nr), sm_in = agg_fwd_smem<D, false>(nr);
     if ((rc = set_smem(agg_fwd_kernel<D, true>, sm_leaf))) return rc;
     if ((rc = set_smem(agg_fwd_kernel<D, false>, sm_in))) return rc;
+    static const char* names[MAX_L] = {"agg_fwd_0", "agg_fwd_1", "agg_fwd_2"};
     for (int i = 0; i < H; ++i) {
-      for (int lv = 0; lv < H - i; ++lv) {
-        const bool leaf = (i == 0 && lv == H - 1);
-        AggArgs a;
-        memset(&a, 0, sizeof(a));
-        a.ent = at<int32_t>(ws, L.ent[lv]); a.adj = h->adj; a.s = at<float>(ws, L.s) + (long)i * nr;
-        a.self = at<float>(ws, L.V[i][lv]);
-        a.Wa = P.agg_w + (long)i * D * D; a.ba = P.agg_b + (long)i * D;
-        a.Y = at<float>(ws, L.Y[i][lv]); a.V = at<float>(ws, L.V[i + 1][lv]);
-        a.probs = nullptr;
-        a.rows = L.rows[lv]; a.rpp = (int)(L.rows[lv] / B); a.K = K; a.n_rel = nr;
-        if (leaf) {
-          a.E = P.entity_emb; a.u = at<float>(ws, L.u);
-          a.Wt = P.transfer_w + (long)H * D * D; a.bt = P.transfer_b + (long)H * D;
-          a.SU = at<float>(ws, L.SU);
-          agg_fwd_kernel<D, true><<<tile_grid(h, a.rows, ctas_per_sm(sm_leaf, C::NT)), C::NT, sm_leaf, st>>>(a);
-        } else {
-          a.child = at<float>(ws, L.V[i][lv + 1]);
-          agg_fwd_kernel<D, false><<<tile_grid(h, a.rows, ctas_per_sm(sm_in, C::NT)), C::NT, sm_in, st>>>(a);
-        }
-        LAUNCH_CHECK(h, leaf ? "agg_fwd_leaf" : "agg_fwd_inner");
+      AggArgs a;
+      memset(&a, 0, sizeof(a));
+      long rows[MAX_LV];
+      const int nlev = H - i;
+      // biggest level first: its CTAs are scheduled first
+      for (int q = 0; q < nlev; ++q) {
+        const int lv = nlev - 1 - q;
+        AggLevel& t = a.lv[q];
+        t.ent = at<int32_t>(ws, L.ent[lv]);
+        t.self = at<float>(ws, L.V[i][lv]);
+        t.Y = at<float>(ws, L.Y[i][lv]); t.V = at<float>(ws, L.V[i + 1][lv]);
+        t.rows = rows[q] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B);
+        t.leaf = (i == 0 && lv == H - 1);
+        if (t.leaf) t.SU = at<float>(ws, L.SU); else t.child = at<float>(ws, L.V[i][lv + 1]);
       }
+      a.nlev = nlev; a.adj = h->adj; a.s = at<float>(ws, L.s) + (long)i * nr;
+      a.Wa = P.agg_w + (long)i * D * D; a.ba = P.agg_b + (long)i * D;
+      a.K = K; a.n_rel = nr;
+      if (i == 0) {
+        a.E = P.entity_emb; a.u = at<float>(ws, L.u);
+        a.Wt = P.transfer_w + (long)H * D * D; a.bt = P.transfer_b + (long)H * D;
+        const int grid = partition_grid(rows, nlev, h->sm_count * ctas_per_sm(sm_leaf, C::NT), a.cta_end);
+        agg_fwd_kernel<D, true><<<grid, C::NT, sm_leaf, st>>>(a);
+      } else {
+        const int grid = partition_grid(rows, nlev, h->sm_count * ctas_per_sm(sm_in, C::NT), a.cta_end);
+        agg_fwd_kernel<D, false><<<grid, C::NT, sm_in, st>>>(a);
+      }
+      LAUNCH_CHECK(h, names[i]);
     }
   }
-  // wide&deep mix (model.py:309-315): item = concat(V[0][0] .. V[H][0]) . W_mix + b_mix
-  for (int j = 0; j <= H; ++j) {
+  // wide&deep mix (model.py:309-315): item = concat(V[0][0] .. V[H][0]) . W_mix + b_mix, one batch-reduce GEMM
+  {
     GemmArgs g = gemm_args();
-    g.A = at<float>(ws, L.V[j][0]); g.sa_m = D; g.sa_k = 1;
-    g.B = P.mix_w + (long)j * D * D; g.sb_k = D; g.sb_n = 1;
+    g.A = at<float>(ws, L.V[0][0]); g.sa_m = D; g.sa_k = 1; g.bsA = (long)B * D;
+    g.B = P.mix_w; g.sb_k = D; g.sb_n = 1; g.bsB = (long)D * D;
     g.C = at<float>(ws, L.item); g.ldc = D;
-    g.bias = j == 0 ? P.mix_b : nullptr;
-    g.accumulate = j > 0;
-    g.M = B; g.N = D; g.K = D;
-    if ((rc = run_gemm(h, st, g))) return rc;
+    g.bias = P.mix_b;
+    g.M = B; g.N = D; g.K = D; g.nbatch = H + 1; g.reduce = 1;
+    if ((rc = run_gemm(h, st, g, "gemm_mix"))) return rc;
   }
   // score (model.py:158-159)
   {
@@ -331,16 +364,15 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
 // backward
 // ------------------------------------------------------------------------------------------------------
 template <int D>
-int launch_dw(mvin_handle_t h, cudaStream_t st, const float* A, long lda, const float* G, long rows, float* dW,
-              float* db) {
+int launch_dw(mvin_handle_t h, cudaStream_t st, const DwArgs& a, int groups, const char* name) {
   using C = TC<D>;
-  const size_t sm = sizeof(float) * 2 * C::R * C::LD;
+  const size_t sm = dw_smem<D>();
   int rc;
   if ((rc = set_smem(dw_kernel<D>, sm))) return rc;
-  long tiles = (rows + C::R - 1) / C::R;
-  int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
-  dw_kernel<D><<<grid, C::NT, sm, st>>>(A, lda, G, rows, dW, db);
-  LAUNCH_CHECK(h, "dw");
+  long tiles = (a.rows + C::R - 1) / C::R;
+  int gx = (int)(tiles < h->sm_count ? tiles : h->sm_count);
+  dw_kernel<D><<<dim3(gx, groups), C::NT, sm, st>>>(a);
+  LAUNCH_CHECK(h, name);
   return MVIN_OK;
 }
 
@@ -395,10 +427,14 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
   }
   // transposed weights: wT[i] = W_a[i]^T (i < H), wT[H + e] = W_t[e]^T (e <= H)
   float* wT = at<float>(ws, L.wT);
-  transpose_kernel<<<H, 256, 0, st>>>(P.agg_w, D, wT);
+  transpose_kernel<<<dim3(2 * H + 1), 256, 0, st>>>(P.agg_w, P.transfer_w, H, D, wT);
   LAUNCH_CHECK(h, "transpose");
-  transpose_kernel<<<H + 1, 256, 0, st>>>(P.transfer_w, D, wT + (long)H * D * D);
-  LAUNCH_CHECK(h, "transpose");
+  // ripple-memory relation histogram (feeds the un-normalised L2 over gathered RK matrices, model.py:386)
+  if (p > 0) {
+    const long n = (long)p * B * m;
+    hist_r_kernel<<<h->sm_count * 4, 256, sizeof(float) * nr, st>>>(h->mem_r, n, nr, at<float>(ws, L.cnt));
+    LAUNCH_CHECK(h, "hist_r");
+  }
 
   float* du = at<float>(ws, L.du);
   float* ditem = at<float>(ws, L.ditem);
@@ -408,88 +444,105 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
                                                                     at<float>(ws, L.item), B, ditem, du, acc);
     LAUNCH_CHECK(h, "loss_bwd");
   }
-  // mix backward
-  for (int j = 0; j <= H; ++j) {
-    if ((rc = launch_dw<D>(h, st, at<float>(ws, L.V[j][0]), D, ditem, B, G.mix_w + (long)j * D * D,
-                           j == 0 ? G.mix_b : nullptr)))
-      return rc;
+  // mix backward: dW_mix[j] = V[j][0]^T ditem (grouped), DC[j][0] = ditem . W_mix[j]^T (batched)
+  {
+    DwArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int j = 0; j <= H; ++j) { a.A[j] = at<float>(ws, L.V[j][0]); a.lda[j] = D; a.dW[j] = G.mix_w + (long)j * D * D; }
+    a.G = ditem; a.db = G.mix_b; a.rows = B;
+    if ((rc = launch_dw<D>(h, st, a, H + 1, "dw_mix"))) return rc;
     GemmArgs g = gemm_args();
-    g.A = ditem; g.sa_m = D; g.sa_k = 1;
-    g.B = P.mix_w + (long)j * D * D; g.sb_k = 1; g.sb_n = D;      // W_mix[jD + n][k] -> transposed use
-    g.C = at<float>(ws, L.dV[j][0]); g.ldc = D;
-    g.M = B; g.N = D; g.K = D;
-    if ((rc = run_gemm(h, st, g))) return rc;
+    g.A = ditem; g.sa_m = D; g.sa_k = 1; g.bsA = 0;
+    g.B = P.mix_w; g.sb_k = 1; g.sb_n = D; g.bsB = (long)D * D;   // W_mix[jD + n][k] -> transposed use
+    g.C = at<float>(ws, L.DC[0][0]); g.ldc = D; g.bsC = (long)B * D;
+    g.M = B; g.N = D; g.K = D; g.nbatch = H + 1;
+    if ((rc = run_gemm(h, st, g, "gemm_mix_bwd"))) return rc;
   }
-  // aggregation iterations, reversed
+  // aggregation iterations, reversed; one launch per iteration
   {
     const size_t sm_leaf = agg_bwd_smem<D, true>(nr), sm_in = agg_bwd_smem<D, false>(nr);
     if ((rc = set_smem(agg_bwd_kernel<D, true>, sm_leaf))) return rc;
     if ((rc = set_smem(agg_bwd_kernel<D, false>, sm_in))) return rc;
+    static const char* names[MAX_L] = {"agg_bwd_0", "agg_bwd_1", "agg_bwd_2"};
     for (int i = H - 1; i >= 0; --i) {
-      for (int lv = 0; lv < H - i; ++lv) {
-        const bool leaf = (i == 0 && lv == H - 1);
-        AggBwdArgs a;
-        memset(&a, 0, sizeof(a));
-        a.ent = at<int32_t>(ws, L.ent[lv]); a.adj = h->adj; a.s = at<float>(ws, L.s) + (long)i * nr;
-        a.WaT = wT + (long)i * D * D;
-        a.V = at<float>(ws, L.V[i + 1][lv]);
-        a.gout = at<float>(ws, L.dV[i + 1][lv]);
-        a.dself = at<float>(ws, L.dV[i][lv]);
-        a.ds = at<float>(ws, L.ds) + (long)i * nr;
-        a.rows = L.rows[lv]; a.rpp = (int)(L.rows[lv] / B); a.K = K; a.n_rel = nr;
-        a.self_accumulate = 1;   // dV[i][0] was initialised by the mix, dV[i][h>0] by hop h-1's child gradients
-        if (leaf) {
-          a.E = P.entity_emb; a.WtT = wT + (long)(H + H) * D * D;
-          a.GROW = at<float>(ws, L.GROW); a.dE = G.entity_emb; a.du = du;
-          agg_bwd_kernel<D, true><<<tile_grid(h, a.rows, ctas_per_sm(sm_leaf, C::NT)), C::NT, sm_leaf, st>>>(a);
+      AggBwdArgs a;
+      memset(&a, 0, sizeof(a));
+      long rows[MAX_LV];
+      const int nlev = H - i;
+      for (int q = 0; q < nlev; ++q) {
+        const int lv = nlev - 1 - q;
+        AggBwdLevel& t = a.lv[q];
+        t.ent = at<int32_t>(ws, L.ent[lv]);
+        t.V = at<float>(ws, L.V[i + 1][lv]); t.Y = at<float>(ws, L.Y[i][lv]);
+        t.g1 = at<float>(ws, L.DC[i + 1][lv]);
+        t.g2 = has_agg(H, i + 1, lv) ? at<float>(ws, L.DS[i + 1][lv]) : nullptr;
+        t.dself = at<float>(ws, L.DS[i][lv]);
+        t.rows = rows[q] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B);
+        t.leaf = (i == 0 && lv == H - 1);
+        if (t.leaf) {
+          t.SU = at<float>(ws, L.SU);
         } else {
-          a.child = at<float>(ws, L.V[i][lv + 1]);
-          a.dchild = at<float>(ws, L.dV[i][lv + 1]);
-          agg_bwd_kernel<D, false><<<tile_grid(h, a.rows, ctas_per_sm(sm_in, C::NT)), C::NT, sm_in, st>>>(a);
+          t.child = at<float>(ws, L.V[i][lv + 1]);
+          t.dchild = at<float>(ws, L.DC[i][lv + 1]);
         }
-        LAUNCH_CHECK(h, leaf ? "agg_bwd_leaf" : "agg_bwd_inner");
-        if ((rc = launch_dw<D>(h, st, at<float>(ws, L.Y[i][lv]), D, a.gout, a.rows, G.agg_w + (long)i * D * D,
-                               G.agg_b + (long)i * D)))
-          return rc;
-        if (leaf &&
-            (rc = launch_dw<D>(h, st, at<float>(ws, L.SU), D, a.GROW, a.rows, G.transfer_w + (long)H * D * D,
-                               G.transfer_b + (long)H * D)))
-          return rc;
       }
+      a.nlev = nlev; a.adj = h->adj; a.s = at<float>(ws, L.s) + (long)i * nr;
+      a.WaT = wT + (long)i * D * D;
+      a.dWa = G.agg_w + (long)i * D * D; a.dba = G.agg_b + (long)i * D;
+      a.ds = at<float>(ws, L.ds) + (long)i * nr;
+      a.K = K; a.n_rel = nr;
+      if (i == 0) {
+        a.E = P.entity_emb; a.WtT = wT + (long)(H + H) * D * D;
+        a.dWt = G.transfer_w + (long)H * D * D; a.dbt = G.transfer_b + (long)H * D;
+        a.dE = G.entity_emb; a.du = du;
+        const int grid = partition_grid(rows, nlev, h->sm_count * ctas_per_sm(sm_leaf, C::NT), a.cta_end);
+        agg_bwd_kernel<D, true><<<grid, C::NT, sm_leaf, st>>>(a);
+      } else {
+        const int grid = partition_grid(rows, nlev, h->sm_count * ctas_per_sm(sm_in, C::NT), a.cta_end);
+        agg_bwd_kernel<D, false><<<grid, C::NT, sm_in, st>>>(a);
+      }
+      LAUNCH_CHECK(h, names[i]);
     }
   }
   rel_scores_bwd_kernel<<<H, 128, 0, st>>>(P.relation_emb, P.agg_urh_w, at<float>(ws, L.ds), nr, D, G.relation_emb,
                                            G.agg_urh_w);
   LAUNCH_CHECK(h, "rel_scores_bwd");
-  // user-oriented transform backward, levels 0..L-1
+  // user-oriented transform backward, levels 0..L-1, one launch
   {
-    const size_t sm = sizeof(float) * (D * D + C::R * C::LD);
+    const size_t sm = transform_bwd_smem<D>();
     if ((rc = set_smem(transform_bwd_kernel<D>, sm))) return rc;
-    for (int lv = 0; lv < H; ++lv) {
-      TransformBwdArgs a;
-      a.ent = at<int32_t>(ws, L.ent[lv]); a.dT = at<float>(ws, L.dV[0][lv]);
-      a.WT = wT + (long)(H + lv) * D * D; a.dE = G.entity_emb; a.du = du;
-      a.rows = L.rows[lv]; a.rpp = (int)(L.rows[lv] / B);
-      transform_bwd_kernel<D><<<tile_grid(h, a.rows, ctas_per_sm(sm, C::NT)), C::NT, sm, st>>>(a);
-      LAUNCH_CHECK(h, "transform_bwd");
-      if ((rc = launch_dw<D>(h, st, at<float>(ws, L.XU[lv]), D, a.dT, a.rows, G.transfer_w + (long)lv * D * D,
-                             G.transfer_b + (long)lv * D)))
-        return rc;
+    TransformArgs a;
+    memset(&a, 0, sizeof(a));
+    long rows[MAX_LV];
+    for (int q = 0; q < H; ++q) {
+      const int lv = H - 1 - q;
+      TransformLevel& t = a.lv[q];
+      t.ent = at<int32_t>(ws, L.ent[lv]);
+      t.W = wT + (long)(H + lv) * D * D;
+      t.g1 = at<float>(ws, L.DC[0][lv]); t.g2 = at<float>(ws, L.DS[0][lv]);
+      t.dW = G.transfer_w + (long)lv * D * D; t.db = G.transfer_b + (long)lv * D;
+      t.rows = rows[q] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B);
     }
+    a.nlev = H; a.E = P.entity_emb; a.u = at<float>(ws, L.u); a.dE = G.entity_emb; a.du = du;
+    const int grid = partition_grid(rows, H, h->sm_count * ctas_per_sm(sm, C::NT), a.cta_end);
+    transform_bwd_kernel<D><<<grid, C::NT, sm, st>>>(a);
+    LAUNCH_CHECK(h, "transform_bwd");
   }
   // user_o = O . W_user + b  backward
-  for (int s = 0; s <= p; ++s) {
-    if ((rc = launch_dw<D>(h, st, at<float>(ws, L.O) + (long)s * D, (long)(p + 1) * D, du, B,
-                           G.user_mlp_w + (long)s * D * D, s == 0 ? G.user_mlp_b : nullptr)))
-      return rc;
-  }
   {
+    DwArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int s = 0; s <= p; ++s) {
+      a.A[s] = at<float>(ws, L.O) + (long)s * D; a.lda[s] = (long)(p + 1) * D; a.dW[s] = G.user_mlp_w + (long)s * D * D;
+    }
+    a.G = du; a.db = G.user_mlp_b; a.rows = B;
+    if ((rc = launch_dw<D>(h, st, a, p + 1, "dw_user"))) return rc;
     GemmArgs g = gemm_args();
     g.A = du; g.sa_m = D; g.sa_k = 1;
     g.B = P.user_mlp_w; g.sb_k = 1; g.sb_n = D;
     g.C = at<float>(ws, L.dO); g.ldc = (long)(p + 1) * D;
     g.M = B; g.N = (p + 1) * D; g.K = D;
-    if ((rc = run_gemm(h, st, g))) return rc;
+    if ((rc = run_gemm(h, st, g, "gemm_user_bwd"))) return rc;
   }
   // ripple backward
   {
@@ -499,16 +552,13 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     a.probs = at<float>(ws, L.probs); a.dO = at<float>(ws, L.dO);
     a.dE = G.entity_emb; a.dQ = at<float>(ws, L.dQ); a.dw_hi = G.h_item_w; a.l2_acc = acc + 1;
     a.l2_weight = l2w; a.B = B; a.m = m; a.p = p; a.n_rel = nr;
-    const size_t sm = ripple_smem(m, D);
+    const size_t sm = ripple_bwd_smem(m, D);
     if ((rc = set_smem(ripple_bwd_kernel<D>, sm))) return rc;
     const long warps = (long)B * (p + 1);
     ripple_bwd_kernel<D><<<(unsigned)((warps + RIPPLE_NW - 1) / RIPPLE_NW), RIPPLE_NT, sm, st>>>(a);
     LAUNCH_CHECK(h, "ripple_bwd");
   }
   if (p > 0) {
-    const long n = (long)p * B * m;
-    hist_r_kernel<<<h->sm_count, 256, sizeof(float) * nr, st>>>(h->mem_r, n, nr, at<float>(ws, L.cnt));
-    LAUNCH_CHECK(h, "hist_r");
     rk_l2_kernel<<<nr, 256, 0, st>>>(P.relation_kge, at<float>(ws, L.cnt), D * D, 2.f * l2w, G.relation_kge, acc + 1);
     LAUNCH_CHECK(h, "rk_l2");
     // dRK[r][i][j] += sum_b v[b][i] dQ[b][r][j]
@@ -517,14 +567,14 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     g.B = at<float>(ws, L.dQ); g.sb_k = (long)nr * D; g.sb_n = 1; g.bsB = D;
     g.C = G.relation_kge; g.ldc = D; g.bsC = (long)D * D;
     g.M = D; g.N = D; g.K = B; g.nbatch = nr; g.ksplit = pick_ksplit(B); g.accumulate = 1;
-    if ((rc = run_gemm(h, st, g))) return rc;
-    // dE[item_b][i] += sum_r sum_j dQ[b][r][j] RK[r][i][j]
+    if ((rc = run_gemm(h, st, g, "gemm_drk"))) return rc;
+    // dE[item_b][i] += sum_r sum_j dQ[b][r][j] RK[r][i][j]   (reduced over r inside the CTA, one atomic per element)
     GemmArgs g2 = gemm_args();
     g2.A = at<float>(ws, L.dQ); g2.sa_m = (long)nr * D; g2.sa_k = 1; g2.bsA = D;
     g2.B = P.relation_kge; g2.sb_k = 1; g2.sb_n = D; g2.bsB = (long)D * D;
     g2.C = G.entity_emb; g2.ldc = D; g2.bsC = 0; g2.c_rows = at<int32_t>(ws, L.ent[0]);
-    g2.M = B; g2.N = D; g2.K = D; g2.nbatch = nr; g2.accumulate = 1;
-    if ((rc = run_gemm(h, st, g2))) return rc;
+    g2.M = B; g2.N = D; g2.K = D; g2.nbatch = nr; g2.reduce = 1; g2.accumulate = 1;
+    if ((rc = run_gemm(h, st, g2, "gemm_dv"))) return rc;
   }
   finalize_loss_kernel<<<1, 32, 0, st>>>(acc, l2w, l2a, losses_out);
   LAUNCH_CHECK(h, "finalize_loss");
