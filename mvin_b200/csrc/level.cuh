@@ -23,7 +23,7 @@ namespace mvin {
 template <int D>
 struct TC {
   static constexpr int LPR = D / 4;                                   // float4 lanes per row
-  static constexpr int NT = (D >= 128) ? 512 : (D >= 16) ? 256 : 128; // threads per CTA
+  static constexpr int NT = (D >= 64) ? 512 : (D >= 16) ? 256 : 128;  // threads per CTA
   static constexpr int NTY = NT / LPR;                                // thread rows of the register tile
   static constexpr int R = 64;                                        // rows per tile
   static constexpr int TM = R / NTY;                                  // rows per thread
