@@ -43,13 +43,22 @@ WORKLOADS = {
     "C2": dict(dataset="MovieLens-1M", dim=32, h_hop=2, K=16, B=4096, p=2, m=64),
     "C3": dict(dataset="last-fm_50core", dim=64, h_hop=2, K=32, B=8192, p=2, m=64),
     "C4": dict(dataset="amazon-book_20core", dim=64, h_hop=3, K=32, B=16384, p=1, m=16),
+    # C5 = BASELINE.json configs[4]: 100 M entities / 1 B edges, batch 65536, entity table row-sharded over 8 GPUs.
+    # Per GPU: B = 8192 pairs and a 12.5 M-row shard; with N < 8 GPUs the graph shrinks with N (weak scaling), so
+    # N = 8 is exactly C5 and N = 1 is one GPU's share of it (6.4 GB table, HBM-bound random gather).
+    "C5": dict(dataset="synthetic-100M", dim=128, h_hop=2, K=64, B=8192, p=2, m=64, sharded=True,
+               n_entity_per_gpu=12_500_000, n_relation=64, n_user_per_gpu=125_000, n_item_per_gpu=1_250_000),
 }
 METRIC = "user-item pairs/sec fwd+bwd"
 UNIT = "pairs/s"
 FLUSH_BYTES = 256 << 20
 
 
-def workload_name(key, w):
+def workload_name(key, w, world=1):
+    if w.get("sharded"):
+        return (f"{key}: synthetic KG {w['n_entity_per_gpu'] * world / 1e6:.1f} M entities (x{w['K']} sampled edges), "
+                f"dim={w['dim']}, n_hop={w['h_hop']}, neighbor_size={w['K']}, batch={w['B'] * world} "
+                f"({w['B']}/GPU), p_hop={w['p']}, n_memory={w['m']}, entity table row-sharded over {world} GPU(s)")
     return (f"{key}: {w['dataset']}-shaped synthetic KG, dim={w['dim']}, n_hop={w['h_hop']}, neighbor_size={w['K']}, "
             f"batch={w['B']}, p_hop={w['p']}, n_memory={w['m']}")
 
@@ -227,36 +236,62 @@ def run_ours(a, w, wl_key):
         dist.init_process_group("nccl", device_id=dev)
 
     B = w["B"]
-    ds = D.make_synthetic_dataset(w["dataset"], w["K"], w["p"], w["m"], seed=2020)
-    shp = ds["shape"]
-    model = MVIN(make_args(w), shp["n_user"], shp["n_entity"], shp["n_relation"], ds["adj_entity"], ds["adj_relation"],
-                 device=dev, seed=1)
-    # NB pre-staged batches per rank (disjoint slices of the shuffled interaction list)
     NB = 8
-    rng = np.random.RandomState(1234)
-    perm = rng.permutation(ds["data"].shape[0])
     host, devb = [], []
-    for i in range(NB):
-        sel = perm[((rank * NB + i) * B) % (perm.size - B):][:B]
-        batch = ds["data"][sel]
-        mh, mr, mt = D.stacked_memories(ds["user_triplet_set"], batch[:, 0])
-        arrs = [np.ascontiguousarray(batch[:, 0]), np.ascontiguousarray(batch[:, 1]),
-                np.ascontiguousarray(batch[:, 2].astype(np.float32)), mh, mr, mt]
-        pinned = [torch.from_numpy(x).pin_memory() for x in arrs]
-        host.append(pinned)
-        devb.append([t.to(dev) for t in pinned])
+    sharded = bool(w.get("sharded"))
+    ds = None
+    if sharded:
+        # C5: graph, ripple sets and batches are generated on the device (same seed on every rank)
+        n_entity, n_user = w["n_entity_per_gpu"] * world, w["n_user_per_gpu"] * world
+        n_item = w["n_item_per_gpu"] * world
+        adj = D.synthetic_packed_adjacency_device(n_entity, w["n_relation"], w["K"], dev, seed=1234)
+        uts = D.synthetic_ripple_sets_device(adj, n_user, n_item, w["p"], w["m"], seed=1234)
+        model = MVIN(make_args(w), n_user, n_entity, w["n_relation"], adj, None, device=dev, seed=1,
+                     entity_shards=world, process_group=dist.group.WORLD if world > 1 else None)
+        gen = torch.Generator(device=dev).manual_seed(99 + rank)
+        for i in range(NB):
+            users = torch.randint(0, n_user, (B,), device=dev, generator=gen)
+            items = torch.randint(0, n_item, (B,), device=dev, generator=gen)
+            labels = torch.randint(0, 2, (B,), device=dev, generator=gen).float()
+            mh, mr, mt = D.stacked_memories_device(uts, users)
+            devb.append([users, items, labels, mh, mr, mt])
+            host.append([t.cpu().pin_memory() for t in devb[-1]])
+        del uts
+    else:
+        ds = D.make_synthetic_dataset(w["dataset"], w["K"], w["p"], w["m"], seed=2020)
+        shp = ds["shape"]
+        model = MVIN(make_args(w), shp["n_user"], shp["n_entity"], shp["n_relation"], ds["adj_entity"],
+                     ds["adj_relation"], device=dev, seed=1)
+        # NB pre-staged batches per rank (disjoint slices of the shuffled interaction list)
+        rng = np.random.RandomState(1234)
+        perm = rng.permutation(ds["data"].shape[0])
+        for i in range(NB):
+            sel = perm[((rank * NB + i) * B) % (perm.size - B):][:B]
+            batch = ds["data"][sel]
+            mh, mr, mt = D.stacked_memories(ds["user_triplet_set"], batch[:, 0])
+            arrs = [np.ascontiguousarray(batch[:, 0]), np.ascontiguousarray(batch[:, 1]),
+                    np.ascontiguousarray(batch[:, 2].astype(np.float32)), mh, mr, mt]
+            pinned = [torch.from_numpy(x).pin_memory() for x in arrs]
+            host.append(pinned)
+            devb.append([t.to(dev) for t in pinned])
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     d2h = 16
     flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
     losses = torch.zeros(4, dtype=torch.float32, device=dev)
     flat_grads = None
-    if a.allreduce and world > 1:
+    if a.allreduce and world > 1 and not sharded:
         flat_grads = list(model.grads.values())
+    group_mode = sharded and world > 1
 
     def step_device(i):
         u, it, lab, mh, mr, mt = devb[i % NB]
+        if group_mode:
+            model.begin_step()              # zero this rank's gradient shard + fence (peers scatter into it)
         model.forward_device(u, it, mh, mr, mt)
         model.backward_device(lab, losses)
+        if group_mode:
+            model.allreduce_replicated()    # NCCL: dense-weight / relation-table gradients
+            model.end_step()
         if flat_grads is not None:
             for g in flat_grads:
                 dist.all_reduce(g)
@@ -352,9 +387,10 @@ def run_ours(a, w, wl_key):
                     "share_of_step": prof[top]["ms_per_step"] / max(1e-9, sum(v["ms_per_step"] for v in prof.values())),
                     "step_logical_gbs": (fwd_b + bwd_b) * pairs_per_s / world / 1e9,
                     "step_frac": (fwd_b + bwd_b) * pairs_per_s / world / 1e9 / peak,
-                    "note": "tables (<=30 MB) are L2-resident at this workload: logical gather bytes, not DRAM traffic"}
+                    "note": ("entity table >> L2: gathers are served by HBM / NVLink peers" if sharded else
+                             "tables (<=30 MB) are L2-resident at this workload: logical gather bytes, not DRAM traffic")}
     cpu = None
-    if world == 1 and not a.no_cpu_baseline:
+    if world == 1 and not a.no_cpu_baseline and not sharded:
         n_pairs = a.cpu_sample_pairs
         v, t_step, cores = time_oracle(w, ds, n_pairs, 1, 1)
         reps = int(max(2, min(20, 15.0 / max(t_step, 1e-3))))
@@ -365,8 +401,10 @@ def run_ours(a, w, wl_key):
     line = {"metric": METRIC, "value": pairs_per_s, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(wl_key, w), "pairs_per_step_per_gpu": B,
-                       "parallelism": f"dp{world} replicas" + (" + grad all-reduce" if flat_grads is not None else ""),
+            "config": {"workload": workload_name(wl_key, w, world), "pairs_per_step_per_gpu": B,
+                       "parallelism": (f"dp{world}, entity table row-sharded over {world} GPUs (NVLink peer gathers / "
+                                       f"peer reductions), replicated-gradient all-reduce" if group_mode else
+                                       f"dp{world} replicas" + (" + grad all-reduce" if flat_grads is not None else "")),
                        "l2": "flushed between timed steps (256 MiB write outside the event pairs)",
                        "init": "reference Xavier init, seed 1"},
             "e2e": {"value": e2e_pairs_per_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

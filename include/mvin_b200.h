@@ -34,7 +34,7 @@ extern "C" {
 #define MVIN_ERR_CUDA -3
 #define MVIN_ERR_STATE -4
 
-#define MVIN_ABI_VERSION 1
+#define MVIN_ABI_VERSION 2
 
 typedef struct mvin_handle_s* mvin_handle_t;
 
@@ -97,6 +97,33 @@ int mvin_bind_adjacency(mvin_handle_t h, const int32_t* adj_packed /* [n_entity,
  * ids, one contiguous 8K-byte record per entity.  Device pointers. */
 int mvin_pack_adjacency(const int64_t* adj_entity, const int64_t* adj_relation, int32_t n_entity, int32_t K,
                         int32_t* adj_packed, void* stream);
+
+/* Row-sharded entity table (BASELINE.json C5: the 51 GB entity table of the 100 M-entity KG does not share one
+ * GPU's HBM with its gradient and Adam state).  Replaces the single `entity_emb_matrix` variable of model.py:76-78
+ * and every tf.nn.embedding_lookup on it (model.py:130,134,144,199,267) by a lookup through a shard table:
+ * entity e lives in shard (e mod n_shards) at local row (e div n_shards); n_shards is a power of two <= 16.
+ * entity_shards[g] / grad_shards[g] are DEVICE pointers valid in this process -- the local shard, and the peers'
+ * shards mapped with CUDA IPC, so gathers are NVLink peer loads and gradient scatter-adds are NVLink peer
+ * reductions issued by the same kernels (no separate exchange step).  Each shard is fp32
+ * [ceil(n_entity / n_shards), d].  After this call params.entity_emb / grads.entity_emb (mvin_bind_params /
+ * mvin_bind_grads) must point at THIS rank's shard: mvin_adam_step updates only that shard, and mvin_backward no
+ * longer zero-fills the entity gradient -- the caller zeroes its shard and synchronises the ranks before the
+ * step (peers scatter into it) and again before reading it.  Both arrays are host arrays of device pointers. */
+int mvin_bind_entity_shards(mvin_handle_t h, int32_t n_shards, const float* const* entity_shards,
+                            float* const* grad_shards);
+
+/* CUDA IPC helpers for the shard exchange between the one-process-per-GPU ranks of a box: export gives the 64-byte
+ * cudaIpcMemHandle_t of the allocation containing dev_ptr and dev_ptr's offset in it; open maps a peer's
+ * allocation into this process (once per allocation, peer access enabled lazily) and returns the pointer. */
+#define MVIN_IPC_HANDLE_BYTES 64
+int mvin_ipc_export(const void* dev_ptr, void* handle_out, int64_t* offset_out);
+int mvin_ipc_open(const void* handle, int64_t offset, void** ptr_out);
+
+/* Data-parallel ranks: the base loss and its gradient are divided by `global_batch` (0 = the batch of the call,
+ * model.py:379-380 semantics) and the dense L2 terms (model.py:388-410) are multiplied by dense_l2_scale
+ * (1 / world size), so that a SUM all-reduce of losses and gradients over the ranks equals the single-device
+ * result on the concatenated batch. */
+int mvin_set_batch_scale(mvin_handle_t h, int32_t global_batch, float dense_l2_scale);
 
 /* Workspace (activations kept for backward + scratch), in bytes, for batch size B. */
 size_t mvin_workspace_bytes(mvin_handle_t h, int32_t B);

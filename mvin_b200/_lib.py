@@ -9,10 +9,10 @@ from . import build as _build
 
 MVIN_OK = 0
 FLAGS_ALL = 0x1F
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTS = ["mvin_abi_version", "mvin_last_error", "mvin_create", "mvin_destroy", "mvin_bind_params",
-           "mvin_bind_grads", "mvin_bind_adjacency", "mvin_pack_adjacency", "mvin_workspace_bytes",
+           "mvin_bind_grads", "mvin_bind_adjacency", "mvin_bind_entity_shards", "mvin_set_batch_scale", "mvin_ipc_export", "mvin_ipc_open", "mvin_pack_adjacency", "mvin_workspace_bytes",
            "mvin_get_neighbors", "mvin_forward", "mvin_importance", "mvin_backward", "mvin_adam_step",
            "mvin_feed_bytes", "mvin_train_step_host", "mvin_launch_count", "mvin_profile_enable",
            "mvin_profile_read"]
@@ -58,6 +58,10 @@ def load():
     lib.mvin_bind_params.argtypes = [vp, C.POINTER(Params)]
     lib.mvin_bind_grads.argtypes = [vp, C.POINTER(Params)]
     lib.mvin_bind_adjacency.argtypes = [vp, vp]
+    lib.mvin_bind_entity_shards.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp)]
+    lib.mvin_set_batch_scale.argtypes = [vp, i32, C.c_float]
+    lib.mvin_ipc_export.argtypes = [vp, vp, C.POINTER(C.c_int64)]
+    lib.mvin_ipc_open.argtypes = [vp, C.c_int64, C.POINTER(vp)]
     lib.mvin_pack_adjacency.argtypes = [vp, vp, i32, i32, vp, vp]
     lib.mvin_workspace_bytes.argtypes = [vp, i32]
     lib.mvin_workspace_bytes.restype = C.c_size_t

@@ -58,4 +58,22 @@ MVIN_DEV void red_add4(float* p, float4 v) {
                : "memory");
 }
 
+
+// Entity table / entity-gradient table, optionally row-sharded over 2^shift shards: entity e lives in shard
+// (e & mask) at local row (e >> shift).  `shards` is a device array of base pointers -- the local shard and, on a
+// multi-GPU box, the peers' shards mapped through CUDA IPC (NVLink peer loads / peer reductions).  shards == nullptr
+// means one contiguous table at `base`.
+struct ETab { const float* base; const float* const* shards; int shift, mask; };
+struct GTab { float* base; float* const* shards; int shift, mask; };
+MVIN_DEV const float* erow(const ETab& t, long e, int D) {
+  if (t.shards == nullptr) return t.base + e * D;
+  const unsigned long long p = __ldg(reinterpret_cast<const unsigned long long*>(t.shards) + (e & t.mask));
+  return reinterpret_cast<const float*>(p) + (e >> t.shift) * D;
+}
+MVIN_DEV float* grow_of(const GTab& t, long e, int D) {
+  if (t.shards == nullptr) return t.base + e * D;
+  const unsigned long long p = __ldg(reinterpret_cast<const unsigned long long*>(t.shards) + (e & t.mask));
+  return reinterpret_cast<float*>(p) + (e >> t.shift) * D;
+}
+
 }  // namespace mvin

@@ -205,9 +205,9 @@ struct TransformArgs {
   TransformLevel lv[MAX_LV];
   int nlev;
   int cta_end[MAX_LV];
-  const float* E;       // entity table
+  ETab E;               // entity table
   const float* u;       // [B, D]  user_o
-  float* dE;            // bwd: entity-table gradient (scatter-add)
+  GTab dE;              // bwd: entity-table gradient (scatter-add)
   float* du;            // bwd: [B, D] (accumulated)
 };
 
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(TC<D>::NT) transform_fwd_kernel(TransformArgs 
       float4 x = f4zero();
       if (row < L.rows) {
         const long e = L.ent[row];
-        x = f4add(ldg4(a.E + e * D + tx * 4), ldg4(a.u + (row / L.rpp) * D + tx * 4));
+        x = f4add(ldg4(erow(a.E, e, D) + tx * 4), ldg4(a.u + (row / L.rpp) * D + tx * 4));
       }
       st4(&As[r * C::LD + tx * 4], x);
     }
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(TC<D>::NT) transform_bwd_kernel(TransformArgs 
         g = ld4(L.g1 + row * D + tx * 4);
         if (L.g2) g = f4add(g, ld4(L.g2 + row * D + tx * 4));
         const long e = L.ent[row];
-        x = f4add(ldg4(a.E + e * D + tx * 4), ldg4(a.u + (row / L.rpp) * D + tx * 4));
+        x = f4add(ldg4(erow(a.E, e, D) + tx * 4), ldg4(a.u + (row / L.rpp) * D + tx * 4));
       }
       bpart = f4add(bpart, g);
       st4(&As[r * C::LD + tx * 4], g);
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(TC<D>::NT) transform_bwd_kernel(TransformArgs 
       const int r = ty * C::TM + i;
       const long row = row0 + r;
       const float4 gx = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-      if (row < L.rows) red_add4(a.dE + (long)L.ent[row] * D + tx * 4, gx);
+      if (row < L.rows) red_add4(grow_of(a.dE, L.ent[row], D) + tx * 4, gx);
       st4(&As[r * C::LD + tx * 4], gx);
     }
     __syncthreads();
@@ -339,7 +339,7 @@ struct AggArgs {
   int cta_end[MAX_LV];
   const int32_t* adj;   // packed adjacency [n_entity][2][K]
   const float* s;       // [n_rel] relation scores of this aggregator
-  const float* E;       // leaf: entity table
+  ETab E;               // leaf: entity table
   const float* u;       // leaf: [B, D]
   const float* Wt;      // leaf: W_t[L] [D, D]
   const float* bt;      // leaf: b_t[L]
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
         float4 acc = f4zero();
         if (leaf) {
 #pragma unroll 4
-          for (int k = g; k < K; k += C::G) acc = f4fma(pw_w[k], ldg4(a.E + (long)idw_w[k] * D + c * 4), acc);
+          for (int k = g; k < K; k += C::G) acc = f4fma(pw_w[k], ldg4(erow(a.E, idw_w[k], D) + c * 4), acc);
         } else {
           const float* base = L.child + row * K * D + c * 4;
 #pragma unroll 4
@@ -486,14 +486,14 @@ struct AggBwdArgs {
   int cta_end[MAX_LV];
   const int32_t* adj;
   const float* s;
-  const float* E;       // leaf
+  ETab E;               // leaf
   const float* WaT;     // W_a transposed
   const float* WtT;     // leaf: W_t[L] transposed
   float* dWa;           // [D, D]
   float* dba;           // [D]
   float* dWt;           // leaf: [D, D]
   float* dbt;           // leaf: [D]
-  float* dE;            // leaf
+  GTab dE;              // leaf
   float* du;            // leaf: [B, D]
   float* ds;            // [n_rel]
   int K, n_rel;
@@ -613,8 +613,8 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
           const float pk = pw_w[k];
           if (leaf) {
             const long n = idw_w[k];
-            part = f4dot(gr, ldg4(a.E + n * D + c * 4));
-            red_add4(a.dE + n * D + c * 4, f4scale(gr, pk));
+            part = f4dot(gr, ldg4(erow(a.E, n, D) + c * 4));
+            red_add4(grow_of(a.dE, n, D) + c * 4, f4scale(gr, pk));
           } else {
             const long cr = (row * K + k) * D + c * 4;
             part = f4dot(gr, ld4(L.child + cr));

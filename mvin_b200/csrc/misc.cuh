@@ -44,7 +44,7 @@ __global__ void copy_i64_kernel(const int64_t* __restrict__ src, long n, int64_t
 
 // ---- seeds: ent[0] = item (int32) and Vbuf = E[item]  (model.py:199) -----------------------------------
 template <int D>
-__global__ void prep_items_kernel(const int64_t* __restrict__ item, const float* __restrict__ E, int B,
+__global__ void prep_items_kernel(const int64_t* __restrict__ item, ETab E, int B,
                                   int32_t* __restrict__ ent0, float* __restrict__ Vbuf) {
   constexpr int LPR = D / 4;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -53,7 +53,18 @@ __global__ void prep_items_kernel(const int64_t* __restrict__ item, const float*
   const int c = (int)(i % LPR);
   const long e = item[b];
   if (c == 0) ent0[b] = (int32_t)e;
-  st4(Vbuf + b * D + c * 4, ldg4(E + e * D + c * 4));
+  st4(Vbuf + b * D + c * 4, ldg4(erow(E, e, D) + c * 4));
+}
+
+// ---- dE[ent[b]] += rows[b]   (row scatter-add of a dense [B, D] buffer) ---------------------------------
+template <int D>
+__global__ void scatter_rows_kernel(const float* __restrict__ rows, const int32_t* __restrict__ ent, int B, GTab dE) {
+  constexpr int LPR = D / 4;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)B * LPR) return;
+  const long b = i / LPR;
+  const int c = (int)(i % LPR);
+  red_add4(grow_of(dE, ent[b], D) + c * 4, ld4(rows + b * D + c * 4));
 }
 
 // ---- relation scores s[i][r] = Rel[r] . urh_weights_i[D:2D]  (aggregators.py:130-133, relation third) --
@@ -102,10 +113,10 @@ __global__ void score_kernel(const float* __restrict__ u, const float* __restric
   }
 }
 
-// base loss (model.py:379-380) and its gradient: g = (sigmoid(x) - z) / B ; ditem = g u ; du = g item
+// base loss (model.py:379-380) and its gradient (invB = 1 / batch size of the whole job): g = (sigmoid(x) - z) / B ; ditem = g u ; du = g item
 template <int D>
 __global__ void loss_bwd_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
-                                const float* __restrict__ u, const float* __restrict__ item, int B,
+                                const float* __restrict__ u, const float* __restrict__ item, int B, float invB,
                                 float* __restrict__ ditem, float* __restrict__ du, float* __restrict__ bce_acc) {
   constexpr int LPR = D / 4;
   __shared__ float red;
@@ -117,7 +128,7 @@ __global__ void loss_bwd_kernel(const float* __restrict__ scores, const float* _
   float bce = 0.f;
   if (b < B) {
     const float x = scores[b], z = labels[b];
-    const float gsc = (1.f / (1.f + expf(-x)) - z) / (float)B;
+    const float gsc = (1.f / (1.f + expf(-x)) - z) * invB;
     st4(ditem + b * D + c * 4, f4scale(ld4(u + b * D + c * 4), gsc));
     st4(du + b * D + c * 4, f4scale(ld4(item + b * D + c * 4), gsc));
     if (c == 0) bce = fmaxf(x, 0.f) - x * z + log1pf(expf(-fabsf(x)));
@@ -125,7 +136,7 @@ __global__ void loss_bwd_kernel(const float* __restrict__ scores, const float* _
   bce = warp_sum(bce);
   if (threadIdx.x % 32 == 0 && bce != 0.f) atomicAdd(&red, bce);
   __syncthreads();
-  if (threadIdx.x == 0) atomicAdd(bce_acc, red / (float)B);
+  if (threadIdx.x == 0) atomicAdd(bce_acc, red * invB);
 }
 
 // ---- dense L2 terms (model.py:388-410): grad = coef * mult * param (store: this also zero-fills buffers

@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "../../include/mvin_b200.h"
@@ -49,6 +50,7 @@ void prof_mark(mvin_handle_t h, cudaStream_t st, const char* name);
   } while (0)
 
 constexpr int MAX_L = 3;
+constexpr int MAX_SHARDS = 16;
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
@@ -67,7 +69,7 @@ struct Layout {
   size_t item, scores;
   // backward
   size_t DC[MAX_L + 1][MAX_L], DS[MAX_L][MAX_L];
-  size_t du, ditem, dO, wT;               // wT: [H + H + 1][D][D] transposed weights
+  size_t du, ditem, dO, dv, wT;           // wT: [H + H + 1][D][D] transposed weights
   size_t zero_begin, dQ, ds, cnt, acc, zero_end;   // region cleared at the start of every backward
   size_t total;
   long rows[MAX_L + 1];
@@ -89,6 +91,14 @@ struct mvin_handle_s {
   int B = 0;
   void* fwd_workspace = nullptr;
   // optional per-category kernel timing (mvin_profile_enable / mvin_profile_read)
+  // entity table / gradient accessors (single table, or row-sharded over n_shards peers)
+  ETab etab{};
+  GTab gtab{};
+  int n_shards = 1;
+  long n_local_rows = 0;           // rows of the local entity shard
+  void** d_shard_tab = nullptr;    // device array [2][MAX_SHARDS] of shard base pointers (allocated in mvin_create)
+  int global_batch = 0;            // 0: the batch of the call
+  float dense_l2_scale = 1.f;
   bool prof_on = false;
   struct ProfRec { const char* name; cudaEvent_t ev; };
   std::vector<ProfRec> prof;
@@ -147,6 +157,7 @@ Layout make_layout(const mvin_config_t& c, long B) {
   L.du = take(f * B * D);
   L.ditem = take(f * B * D);
   L.dO = take(f * B * (p + 1) * D);
+  L.dv = take(f * B * D);
   L.wT = take(f * (2 * H + 1) * D * D);
   L.zero_begin = off;
   L.dQ = take(f * B * nr * D);
@@ -161,10 +172,23 @@ Layout make_layout(const mvin_config_t& c, long B) {
 template <typename T>
 T* at(void* ws, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(ws) + off); }
 
+template <int BM, int BN, int BK>
+void launch_gemm_tile(const GemmArgs& g, cudaStream_t st) {
+  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, (g.reduce ? 1 : g.nbatch) * g.ksplit);
+  gemm_kernel<BM, BN, BK><<<grid, GEMM_THREADS, 0, st>>>(g);
+}
+
+// Tile choice: these GEMMs are tall and skinny and tiny next to the gather kernels, so pick the tile that yields
+// enough CTAs to cover the SMs rather than the one with the best reuse.
 int run_gemm(mvin_handle_t h, cudaStream_t st, const GemmArgs& g, const char* name = "gemm") {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return MVIN_OK;
-  dim3 grid((g.N + GEMM_BN - 1) / GEMM_BN, (g.M + GEMM_BM - 1) / GEMM_BM, (g.reduce ? 1 : g.nbatch) * g.ksplit);
-  gemm_kernel<<<grid, GEMM_THREADS, 0, st>>>(g);
+  const long z = (long)(g.reduce ? 1 : g.nbatch) * g.ksplit;
+  if (g.N <= 32) {
+    launch_gemm_tile<32, 32, 32>(g, st);
+  } else {
+    const long ctas64 = (long)((g.M + 63) / 64) * ((g.N + 63) / 64) * z;
+    if (ctas64 < 2L * h->sm_count) launch_gemm_tile<16, 64, 32>(g, st); else launch_gemm_tile<64, 64, 16>(g, st);
+  }
   LAUNCH_CHECK(h, name);
   return MVIN_OK;
 }
@@ -235,7 +259,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
   // seeds + integer expansion (model.py:243-256); level L ids are never materialised
   {
     const long n = (long)B * C::LPR;
-    prep_items_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(item, P.entity_emb, B, at<int32_t>(ws, L.ent[0]),
+    prep_items_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(item, h->etab, B, at<int32_t>(ws, L.ent[0]),
                                                                       at<float>(ws, L.Vbuf));
     LAUNCH_CHECK(h, "prep_items");
   }
@@ -257,7 +281,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
   // ripple attention (model.py:162-229)
   {
     RippleArgs a;
-    a.E = P.entity_emb; a.Q = at<float>(ws, L.Q); a.w_hi = P.h_item_w;
+    a.E = h->etab; a.Q = at<float>(ws, L.Q); a.w_hi = P.h_item_w;
     a.mem_h = mem_h; a.mem_r = mem_r; a.mem_t = mem_t;
     a.probs = at<float>(ws, L.probs); a.O = at<float>(ws, L.O);
     a.B = B; a.m = m; a.p = p; a.n_rel = nr;
@@ -297,7 +321,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
       t.T = at<float>(ws, L.V[0][lv]);
       t.rows = rows[lv] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B);
     }
-    a.nlev = H; a.E = P.entity_emb; a.u = at<float>(ws, L.u);
+    a.nlev = H; a.E = h->etab; a.u = at<float>(ws, L.u);
     const int grid = partition_grid(rows, H, h->sm_count * ctas_per_sm(sm, C::NT), a.cta_end);
     transform_fwd_kernel<D><<<grid, C::NT, sm, st>>>(a);
     LAUNCH_CHECK(h, "transform_fwd");
@@ -328,7 +352,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
       a.Wa = P.agg_w + (long)i * D * D; a.ba = P.agg_b + (long)i * D;
       a.K = K; a.n_rel = nr;
       if (i == 0) {
-        a.E = P.entity_emb; a.u = at<float>(ws, L.u);
+        a.E = h->etab; a.u = at<float>(ws, L.u);
         a.Wt = P.transfer_w + (long)H * D * D; a.bt = P.transfer_b + (long)H * D;
         const int grid = partition_grid(rows, nlev, h->sm_count * ctas_per_sm(sm_leaf, C::NT), a.cta_end);
         agg_fwd_kernel<D, true><<<grid, C::NT, sm_leaf, st>>>(a);
@@ -390,7 +414,8 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
   prof_mark(h, st, nullptr);
 
   CUDA_TRY(cudaMemsetAsync(at<char>(ws, L.zero_begin), 0, L.zero_end - L.zero_begin, st));
-  CUDA_TRY(cudaMemsetAsync(G.entity_emb, 0, sizeof(float) * (size_t)c.n_entity * D, st));
+  // sharded mode: peers scatter into this rank's shard, so the CALLER zeroes it (and synchronises the ranks)
+  if (h->n_shards == 1) CUDA_TRY(cudaMemsetAsync(G.entity_emb, 0, sizeof(float) * (size_t)c.n_entity * D, st));
   prof_mark(h, st, "memset");
   // dense L2 terms: initialise every other gradient buffer with coef * param (model.py:388-410)
   {
@@ -398,7 +423,8 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     memset(&sg, 0, sizeof(sg));
     int n = 0;
     auto add = [&](const float* prm, float* grd, long cnt, float coef, float mult, int which) {
-      sg.param[n] = prm; sg.grad[n] = grd; sg.n[n] = cnt; sg.coef[n] = coef * mult; sg.mult[n] = mult; sg.which[n] = which;
+      sg.param[n] = prm; sg.grad[n] = grd; sg.n[n] = cnt; sg.coef[n] = coef * mult * h->dense_l2_scale;
+      sg.mult[n] = mult * h->dense_l2_scale; sg.which[n] = which;
       ++n;
     };
     const float pm = p > 0 ? 1.f : 0.f;
@@ -441,7 +467,8 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
   {
     const long n = (long)B * C::LPR;
     loss_bwd_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(at<float>(ws, L.scores), labels, at<float>(ws, L.u),
-                                                                    at<float>(ws, L.item), B, ditem, du, acc);
+                                                                    at<float>(ws, L.item), B,
+                                                                    1.f / (float)(h->global_batch > 0 ? h->global_batch : B), ditem, du, acc);
     LAUNCH_CHECK(h, "loss_bwd");
   }
   // mix backward: dW_mix[j] = V[j][0]^T ditem (grouped), DC[j][0] = ditem . W_mix[j]^T (batched)
@@ -492,9 +519,9 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
       a.ds = at<float>(ws, L.ds) + (long)i * nr;
       a.K = K; a.n_rel = nr;
       if (i == 0) {
-        a.E = P.entity_emb; a.WtT = wT + (long)(H + H) * D * D;
+        a.E = h->etab; a.WtT = wT + (long)(H + H) * D * D;
         a.dWt = G.transfer_w + (long)H * D * D; a.dbt = G.transfer_b + (long)H * D;
-        a.dE = G.entity_emb; a.du = du;
+        a.dE = h->gtab; a.du = du;
         const int grid = partition_grid(rows, nlev, h->sm_count * ctas_per_sm(sm_leaf, C::NT), a.cta_end);
         agg_bwd_kernel<D, true><<<grid, C::NT, sm_leaf, st>>>(a);
       } else {
@@ -523,7 +550,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
       t.dW = G.transfer_w + (long)lv * D * D; t.db = G.transfer_b + (long)lv * D;
       t.rows = rows[q] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B);
     }
-    a.nlev = H; a.E = P.entity_emb; a.u = at<float>(ws, L.u); a.dE = G.entity_emb; a.du = du;
+    a.nlev = H; a.E = h->etab; a.u = at<float>(ws, L.u); a.dE = h->gtab; a.du = du;
     const int grid = partition_grid(rows, H, h->sm_count * ctas_per_sm(sm, C::NT), a.cta_end);
     transform_bwd_kernel<D><<<grid, C::NT, sm, st>>>(a);
     LAUNCH_CHECK(h, "transform_bwd");
@@ -547,10 +574,10 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
   // ripple backward
   {
     RippleBwdArgs a;
-    a.E = P.entity_emb; a.Q = at<float>(ws, L.Q); a.w_hi = P.h_item_w;
+    a.E = h->etab; a.Q = at<float>(ws, L.Q); a.w_hi = P.h_item_w;
     a.mem_h = h->mem_h; a.mem_r = h->mem_r; a.mem_t = h->mem_t;
     a.probs = at<float>(ws, L.probs); a.dO = at<float>(ws, L.dO);
-    a.dE = G.entity_emb; a.dQ = at<float>(ws, L.dQ); a.dw_hi = G.h_item_w; a.l2_acc = acc + 1;
+    a.dE = h->gtab; a.dQ = at<float>(ws, L.dQ); a.dw_hi = G.h_item_w; a.l2_acc = acc + 1;
     a.l2_weight = l2w; a.B = B; a.m = m; a.p = p; a.n_rel = nr;
     const size_t sm = ripple_bwd_smem(m, D);
     if ((rc = set_smem(ripple_bwd_kernel<D>, sm))) return rc;
@@ -568,13 +595,17 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     g.C = G.relation_kge; g.ldc = D; g.bsC = (long)D * D;
     g.M = D; g.N = D; g.K = B; g.nbatch = nr; g.ksplit = pick_ksplit(B); g.accumulate = 1;
     if ((rc = run_gemm(h, st, g, "gemm_drk"))) return rc;
-    // dE[item_b][i] += sum_r sum_j dQ[b][r][j] RK[r][i][j]   (reduced over r inside the CTA, one atomic per element)
+    // dv[b][i] = sum_r sum_j dQ[b][r][j] RK[r][i][j]  (reduced over r inside the CTA);  dE[item_b] += dv[b]
     GemmArgs g2 = gemm_args();
     g2.A = at<float>(ws, L.dQ); g2.sa_m = (long)nr * D; g2.sa_k = 1; g2.bsA = D;
     g2.B = P.relation_kge; g2.sb_k = 1; g2.sb_n = D; g2.bsB = (long)D * D;
-    g2.C = G.entity_emb; g2.ldc = D; g2.bsC = 0; g2.c_rows = at<int32_t>(ws, L.ent[0]);
-    g2.M = B; g2.N = D; g2.K = D; g2.nbatch = nr; g2.reduce = 1; g2.accumulate = 1;
+    g2.C = at<float>(ws, L.dv); g2.ldc = D; g2.bsC = 0;
+    g2.M = B; g2.N = D; g2.K = D; g2.nbatch = nr; g2.reduce = 1;
     if ((rc = run_gemm(h, st, g2, "gemm_dv"))) return rc;
+    const long n = (long)B * C::LPR;
+    scatter_rows_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(at<float>(ws, L.dv), at<int32_t>(ws, L.ent[0]), B,
+                                                                        h->gtab);
+    LAUNCH_CHECK(h, "scatter_dv");
   }
   finalize_loss_kernel<<<1, 32, 0, st>>>(acc, l2w, l2a, losses_out);
   LAUNCH_CHECK(h, "finalize_loss");
@@ -644,11 +675,17 @@ int mvin_create(const mvin_config_t* cfg, mvin_handle_t* out) {
   h->cfg = *cfg;
   h->device = dev;
   h->sm_count = prop.multiProcessorCount;
+  h->n_local_rows = cfg->n_entity;
+  if (cudaMalloc(&h->d_shard_tab, sizeof(void*) * 2 * MAX_SHARDS) != cudaSuccess) {
+    delete h;
+    return fail(MVIN_ERR_CUDA, "cudaMalloc(shard table): %s", cudaGetErrorString(cudaGetLastError()));
+  }
   *out = h;
   return MVIN_OK;
 }
 
 int mvin_destroy(mvin_handle_t h) {
+  if (h && h->d_shard_tab) cudaFree(h->d_shard_tab);
   delete h;
   return MVIN_OK;
 }
@@ -657,12 +694,14 @@ int mvin_bind_params(mvin_handle_t h, const mvin_params_t* params) {
   if (!h || !params) return fail(MVIN_ERR_INVALID, "null argument");
   h->P = *params;
   h->has_params = true;
+  if (h->n_shards == 1) h->etab = ETab{params->entity_emb, nullptr, 0, 0};
   return MVIN_OK;
 }
 int mvin_bind_grads(mvin_handle_t h, const mvin_params_t* grads) {
   if (!h || !grads) return fail(MVIN_ERR_INVALID, "null argument");
   h->G = *grads;
   h->has_grads = true;
+  if (h->n_shards == 1) h->gtab = GTab{grads->entity_emb, nullptr, 0, 0};
   return MVIN_OK;
 }
 int mvin_bind_adjacency(mvin_handle_t h, const int32_t* adj_packed) {
@@ -679,6 +718,75 @@ int mvin_pack_adjacency(const int64_t* adj_entity, const int64_t* adj_relation, 
                                                                                 adj_packed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(MVIN_ERR_CUDA, "launch pack_adj: %s", cudaGetErrorString(e));
+  return MVIN_OK;
+}
+
+int mvin_bind_entity_shards(mvin_handle_t h, int32_t n_shards, const float* const* entity_shards,
+                            float* const* grad_shards) {
+  if (!h || !entity_shards || !grad_shards) return fail(MVIN_ERR_INVALID, "null argument");
+  if (n_shards < 1 || n_shards > MAX_SHARDS || (n_shards & (n_shards - 1)))
+    return fail(MVIN_ERR_INVALID, "n_shards must be a power of two in 1..%d, got %d", MAX_SHARDS, n_shards);
+  int shift = 0;
+  while ((1 << shift) < n_shards) ++shift;
+  void* host[2 * MAX_SHARDS] = {nullptr};
+  for (int i = 0; i < n_shards; ++i) {
+    if (!entity_shards[i] || !grad_shards[i]) return fail(MVIN_ERR_INVALID, "null shard pointer %d", i);
+    host[i] = const_cast<float*>(entity_shards[i]);
+    host[MAX_SHARDS + i] = grad_shards[i];
+  }
+  CUDA_TRY(cudaMemcpy(h->d_shard_tab, host, sizeof(host), cudaMemcpyHostToDevice));
+  h->n_shards = n_shards;
+  h->n_local_rows = ((long)h->cfg.n_entity + n_shards - 1) / n_shards;
+  h->etab = ETab{nullptr, reinterpret_cast<const float* const*>(h->d_shard_tab), shift, n_shards - 1};
+  h->gtab = GTab{nullptr, reinterpret_cast<float* const*>(h->d_shard_tab + MAX_SHARDS), shift, n_shards - 1};
+  return MVIN_OK;
+}
+
+// ---- CUDA IPC plumbing for the peers' shards ---------------------------------------------------------------
+namespace {
+struct IpcOpened { cudaIpcMemHandle_t handle; void* base; };
+std::vector<IpcOpened> g_ipc_opened;
+std::mutex g_ipc_mutex;
+}  // namespace
+
+int mvin_ipc_export(const void* dev_ptr, void* handle_out, int64_t* offset_out) {
+  if (!dev_ptr || !handle_out || !offset_out) return fail(MVIN_ERR_INVALID, "null argument");
+  // base of the containing allocation (the caching allocator of the caller may sub-allocate): driver entry point
+  // resolved at run time so that the library carries no link-time dependency on libcuda
+  typedef int (*GetRangeFn)(unsigned long long*, size_t*, unsigned long long);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CUDA_TRY(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) return fail(MVIN_ERR_CUDA, "cuMemGetAddressRange not available");
+  unsigned long long base = 0;
+  size_t size = 0;
+  const int drc = reinterpret_cast<GetRangeFn>(fn)(&base, &size, (unsigned long long)(uintptr_t)dev_ptr);
+  if (drc != 0) return fail(MVIN_ERR_CUDA, "cuMemGetAddressRange failed (%d)", drc);
+  cudaIpcMemHandle_t hd;
+  CUDA_TRY(cudaIpcGetMemHandle(&hd, reinterpret_cast<void*>((uintptr_t)base)));
+  memcpy(handle_out, &hd, sizeof(hd));
+  *offset_out = (int64_t)((unsigned long long)(uintptr_t)dev_ptr - base);
+  return MVIN_OK;
+}
+
+int mvin_ipc_open(const void* handle, int64_t offset, void** ptr_out) {
+  if (!handle || !ptr_out || offset < 0) return fail(MVIN_ERR_INVALID, "bad argument");
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle, sizeof(hd));
+  std::lock_guard<std::mutex> lock(g_ipc_mutex);
+  for (auto& o : g_ipc_opened)
+    if (memcmp(&o.handle, &hd, sizeof(hd)) == 0) { *ptr_out = static_cast<char*>(o.base) + offset; return MVIN_OK; }
+  void* base = nullptr;
+  CUDA_TRY(cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
+  g_ipc_opened.push_back({hd, base});
+  *ptr_out = static_cast<char*>(base) + offset;
+  return MVIN_OK;
+}
+
+int mvin_set_batch_scale(mvin_handle_t h, int32_t global_batch, float dense_l2_scale) {
+  if (!h || global_batch < 0) return fail(MVIN_ERR_INVALID, "bad argument");
+  h->global_batch = global_batch;
+  h->dense_l2_scale = dense_l2_scale;
   return MVIN_OK;
 }
 
@@ -762,7 +870,7 @@ int mvin_adam_step(mvin_handle_t h, const mvin_params_t* m, const mvin_params_t*
   };
 #define SEG(field, cnt) add(h->P.field, h->G.field, m->field, v->field, (cnt))
   SEG(user_emb, (long)c.n_user * D);
-  SEG(entity_emb, (long)c.n_entity * D);
+  SEG(entity_emb, h->n_local_rows * D);
   SEG(relation_emb, nr * D);
   SEG(relation_kge, nr * D * D);
   SEG(mix_w, (H + 1) * D * D);

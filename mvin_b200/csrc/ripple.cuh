@@ -18,7 +18,7 @@ namespace mvin {
 constexpr int RIPPLE_NT = 256, RIPPLE_NW = RIPPLE_NT / 32, RIPPLE_UNR = 4;
 
 struct RippleArgs {
-  const float* E;          // entity table
+  ETab E;                  // entity table
   const float* Q;          // [B, n_rel, D]
   const float* w_hi;       // h_emb_item_mlp_matrix [2D] (first D used)
   const int32_t* mem_h;    // [max(1,p), B, m]
@@ -53,7 +53,6 @@ __global__ void __launch_bounds__(RIPPLE_NT) ripple_fwd_kernel(RippleArgs a) {
   __syncwarp();
   const float4 wk = ldg4(a.w_hi + c * 4);
   const float* Qb = a.Q + b * a.n_rel * D + c * 4;
-  const float* Ec = a.E + c * 4;
 
 #pragma unroll RIPPLE_UNR
   for (int m0 = 0; m0 < m; m0 += G) {
@@ -61,7 +60,7 @@ __global__ void __launch_bounds__(RIPPLE_NT) ripple_fwd_kernel(RippleArgs a) {
     const bool valid = mm < m;
     float part = 0.f;
     if (valid) {
-      const float4 hrow = ldg4(Ec + (long)sh[mm] * D);
+      const float4 hrow = ldg4(erow(a.E, sh[mm], D) + c * 4);
       const float4 key = s == 0 ? wk : ldg4(Qb + (long)sr[mm] * D);
       part = f4dot(hrow, key);
     }
@@ -89,13 +88,13 @@ __global__ void __launch_bounds__(RIPPLE_NT) ripple_fwd_kernel(RippleArgs a) {
   const int32_t* val = s == 0 ? sh : stt;
   float4 acc = f4zero();
 #pragma unroll RIPPLE_UNR
-  for (int mm = g; mm < m; mm += G) acc = f4fma(lg[mm], ldg4(Ec + (long)val[mm] * D), acc);
+  for (int mm = g; mm < m; mm += G) acc = f4fma(lg[mm], ldg4(erow(a.E, val[mm], D) + c * 4), acc);
   acc = cross_group_sum4<LPR>(acc);
   if (g == 0) st4(a.O + b * S * D + s * D + c * 4, acc);
 }
 
 struct RippleBwdArgs {
-  const float* E;
+  ETab E;
   const float* Q;
   const float* w_hi;
   const int32_t* mem_h;
@@ -103,7 +102,7 @@ struct RippleBwdArgs {
   const int32_t* mem_t;
   const float* probs;      // [p+1, B, m]
   const float* dO;         // [B, (p+1) D]
-  float* dE;               // entity-table gradient (scatter-add)
+  GTab dE;                 // entity-table gradient (scatter-add)
   float* dQ;               // [B, n_rel, D] (zeroed by the caller)
   float* dw_hi;            // gradient of h_emb_item_mlp_matrix [2D] (first D touched)
   float* l2_acc;           // += sum over gathered h / t rows of |row|^2   (model.py:383-385)
@@ -145,8 +144,6 @@ __global__ void __launch_bounds__(RIPPLE_NT) ripple_bwd_kernel(RippleBwdArgs a) 
     const float4 wk = ldg4(a.w_hi + c * 4);
     const float* Qb = a.Q + b * a.n_rel * D + c * 4;
     float* dQb = a.dQ + b * a.n_rel * D + c * 4;
-    const float* Ec = a.E + c * 4;
-    float* dEc = a.dE + c * 4;
     const float4 go = ldg4(a.dO + b * S * D + s * D + c * 4);
     const float two_l2 = 2.f * a.l2_weight;
     const int32_t* val = s == 0 ? sh : stt;
@@ -160,10 +157,10 @@ __global__ void __launch_bounds__(RIPPLE_NT) ripple_bwd_kernel(RippleBwdArgs a) 
       float part = 0.f;
       if (valid) {
         const long id = val[mm];
-        const float4 row = ldg4(Ec + id * D);
+        const float4 row = ldg4(erow(a.E, id, D) + c * 4);
         part = f4dot(go, row);
         if (s > 0) {
-          red_add4(dEc + id * D, f4fma(pr[mm], go, f4scale(row, two_l2)));
+          red_add4(grow_of(a.dE, id, D) + c * 4, f4fma(pr[mm], go, f4scale(row, two_l2)));
           l2 += f4dot(row, row);
         }
       }
@@ -182,9 +179,9 @@ __global__ void __launch_bounds__(RIPPLE_NT) ripple_bwd_kernel(RippleBwdArgs a) 
 #pragma unroll RIPPLE_UNR
       for (int mm = g; mm < m; mm += G) {
         const long hid = sh[mm];
-        const float4 hrow = ldg4(Ec + hid * D);
+        const float4 hrow = ldg4(erow(a.E, hid, D) + c * 4);
         const float dlm = dl[mm];
-        red_add4(dEc + hid * D, f4fma(pr[mm], go, f4scale(wk, dlm)));
+        red_add4(grow_of(a.dE, hid, D) + c * 4, f4fma(pr[mm], go, f4scale(wk, dlm)));
         dw = f4fma(dlm, hrow, dw);
       }
       dw = cross_group_sum4<LPR>(dw);
@@ -199,10 +196,10 @@ __global__ void __launch_bounds__(RIPPLE_NT) ripple_bwd_kernel(RippleBwdArgs a) 
       for (int mm = g; mm < m; mm += G) {
         const long hid = sh[mm];
         const long r = sr[mm];
-        const float4 hrow = ldg4(Ec + hid * D);
+        const float4 hrow = ldg4(erow(a.E, hid, D) + c * 4);
         const float4 key = ldg4(Qb + r * D);
         const float dlm = dl[mm];
-        red_add4(dEc + hid * D, f4fma(dlm, key, f4scale(hrow, two_l2)));
+        red_add4(grow_of(a.dE, hid, D) + c * 4, f4fma(dlm, key, f4scale(hrow, two_l2)));
         red_add4(dQb + r * D, f4scale(hrow, dlm));
         l2 += f4dot(hrow, hrow);
       }

@@ -180,3 +180,63 @@ def make_synthetic_dataset(name: str, K: int, p_hop: int, n_memory: int, seed: i
     hist = user_history(data, shp["n_user"], shp["n_item"], seed)
     uts = build_ripple_sets(indptr, nbr, rel, hist, shp["n_user"], p_hop, n_memory, seed=seed)
     return dict(shape=shp, adj_entity=adj_e, adj_relation=adj_r, data=data, user_triplet_set=uts)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# BASELINE.json config C5 (synthetic KG, 100 M entities / 1 B edges, K = 64): far too large for the reference's
+# host-side Python loops and int64 NumPy adjacency, so it is generated on the device, directly in the packed
+# layout the kernels read: degree ~ clamp(Poisson(20), 1, 48) undirected neighbours drawn
+# uniformly over the entities, relation uniform, then K slots sampled WITH replacement from the entity's own
+# neighbour list (the reference's deg < K rule, data_loader_user_set.py:383-386).  Same seed -> same graph on
+# every rank.
+# ----------------------------------------------------------------------------------------------------------------
+def synthetic_packed_adjacency_device(n_entity: int, n_relation: int, K: int, device, seed: int = 1234,
+                                      mean_degree: float = 20.0, max_degree: int = 48, chunk: int = 1 << 21):
+    import torch
+    gen = torch.Generator(device=device).manual_seed(seed)
+    adj = torch.empty((n_entity, 2, K), dtype=torch.int32, device=device)
+    for start in range(0, n_entity, chunk):
+        n = min(chunk, n_entity - start)
+        deg = torch.poisson(torch.full((n,), mean_degree, device=device), generator=gen).clamp_(1, max_degree)
+        pool_e = torch.randint(0, n_entity, (n, max_degree), dtype=torch.int32, device=device, generator=gen)
+        pool_r = torch.randint(0, n_relation, (n, max_degree), dtype=torch.int32, device=device, generator=gen)
+        sel = (torch.rand((n, K), device=device, generator=gen) * deg[:, None]).long().clamp_(max=max_degree - 1)
+        adj[start:start + n, 0] = torch.gather(pool_e, 1, sel)
+        adj[start:start + n, 1] = torch.gather(pool_r, 1, sel)
+        del deg, pool_e, pool_r, sel
+    return adj
+
+
+def synthetic_ripple_sets_device(adj_packed, n_user: int, n_item: int, p_hop: int, n_memory: int, seed: int = 1234,
+                                 chunk: int = 1 << 17):
+    """user_triplet_set int32 [n_user, max(1,p), 3, m] on the device: hop-0 heads uniform over the items, relations
+    and tails read from the sampled adjacency, hop h+1 heads = hop h tails (data_loader_user_set.py:407-441)."""
+    import torch
+    device = adj_packed.device
+    K = adj_packed.shape[2]
+    P = max(1, p_hop)
+    gen = torch.Generator(device=device).manual_seed(seed + 1)
+    out = torch.empty((n_user, P, 3, n_memory), dtype=torch.int32, device=device)
+    for start in range(0, n_user, chunk):
+        n = min(chunk, n_user - start)
+        heads = torch.randint(0, n_item, (n, n_memory), device=device, generator=gen)
+        for hop in range(P):
+            slot = torch.randint(0, K, (n, n_memory), device=device, generator=gen)
+            rec = adj_packed[heads.reshape(-1)]                                     # [n*m, 2, K]
+            pick = slot.reshape(-1, 1)
+            tails = torch.gather(rec[:, 0], 1, pick).reshape(n, n_memory)
+            rels = torch.gather(rec[:, 1], 1, pick).reshape(n, n_memory)
+            out[start:start + n, hop, 0] = heads.to(torch.int32)
+            out[start:start + n, hop, 1] = rels
+            out[start:start + n, hop, 2] = tails
+            heads = tails.long()
+            del rec
+    return out
+
+
+def stacked_memories_device(user_triplet_set, users):
+    """Device version of stacked_memories: the feed of one batch gathered from the device-resident ripple sets
+    (the host loop of train.py:112-122 replaced by one gather): mem_h, mem_r, mem_t int32 [P, B, m]."""
+    trip = user_triplet_set[users]                       # [B, P, 3, m]
+    t = trip.permute(2, 1, 0, 3).contiguous()            # [3, P, B, m]
+    return t[0], t[1], t[2]

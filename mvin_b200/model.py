@@ -23,7 +23,7 @@ from typing import Dict, List, Optional
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, sharding
 from ._lib import Config, Params, PARAM_FIELDS, check
 
 
@@ -52,11 +52,32 @@ def flags_from_args(args) -> int:
 
 
 class MVIN(object):
-    def __init__(self, args, n_user, n_entity, n_relation, adj_entity, adj_relation, device=None, seed: int = 1):
+    def __init__(self, args, n_user, n_entity, n_relation, adj_entity, adj_relation, device=None, seed: int = 1,
+                 entity_shards: int = 1, process_group=None):
+        """Reference signature (model.py:7) plus keyword-only extensions:
+        device / seed      where the tables live, seed of the Xavier init;
+        entity_shards = G  row-shard the entity table (and its gradient / Adam state) over G shards, entity e in
+                           shard e % G at row e // G (include/mvin_b200.h: mvin_bind_entity_shards);
+        process_group      a torch.distributed group of G one-GPU ranks of one box: every rank owns shard `rank`
+                           and maps the peers' shards through CUDA IPC (NVLink peer loads / reductions).  Without a
+                           group all G shards live on this device ("virtual shards", used by the tests).
+        `adj_entity` may also be a packed device tensor int32 [n_entity, 2, K] (ids then relation ids) with
+        adj_relation=None, for graphs too large for the reference's host-side int64 arrays."""
         if not torch.cuda.is_available():
             raise RuntimeError("mvin_b200.MVIN needs a CUDA device (sm_100a); there is no CPU path")
         self.lib = _lib.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.n_shards = int(entity_shards)
+        self.group = process_group
+        if self.n_shards < 1 or (self.n_shards & (self.n_shards - 1)) or self.n_shards > 16:
+            raise ValueError("entity_shards must be a power of two in 1..16")
+        if self.group is not None:
+            import torch.distributed as dist
+            if dist.get_world_size(self.group) != self.n_shards:
+                raise ValueError("entity_shards must equal the size of process_group")
+            self.rank = dist.get_rank(self.group)
+        else:
+            self.rank = 0
         self._parse_args(args, adj_entity, adj_relation)
         self.n_user, self.n_entity, self.n_relation = int(n_user), int(n_entity), int(n_relation)
         self._build_inputs()
@@ -86,6 +107,14 @@ class MVIN(object):
         self.n_memory = int(args.n_memory)
         self.path = getattr(args, "path", None)
         self.flags = flags_from_args(args)
+        if isinstance(adj_entity, torch.Tensor) and adj_relation is None:
+            if (adj_entity.dtype != torch.int32 or adj_entity.ndim != 3 or adj_entity.shape[1] != 2
+                    or adj_entity.shape[2] != self.n_neighbor or not adj_entity.is_cuda or not adj_entity.is_contiguous()):
+                raise ValueError(f"packed adjacency must be a contiguous CUDA int32 [n_entity, 2, {self.n_neighbor}] tensor")
+            self.adj_entity = self.adj_relation = None
+            self._adj_packed_in = adj_entity
+            return
+        self._adj_packed_in = None
         adj_entity = np.ascontiguousarray(adj_entity, dtype=np.int64)
         adj_relation = np.ascontiguousarray(adj_relation, dtype=np.int64)
         if adj_entity.shape != adj_relation.shape or adj_entity.ndim != 2 or adj_entity.shape[1] != self.n_neighbor:
@@ -114,7 +143,8 @@ class MVIN(object):
     # ------------------------------------------------------------------ model.py:69-122, aggregators.py:83-93
     def param_shapes(self) -> Dict[str, tuple]:
         d, H, p = self.dim, self.h_hop, self.p_hop
-        return {"user_emb": (self.n_user, d), "entity_emb": (self.n_entity, d), "relation_emb": (self.n_relation, d),
+        n_ent_rows = self.n_entity if self.n_shards == 1 else self.n_local_rows
+        return {"user_emb": (self.n_user, d), "entity_emb": (n_ent_rows, d), "relation_emb": (self.n_relation, d),
                 "relation_kge": (self.n_relation, d, d), "mix_w": ((H + 1) * d, d), "mix_b": (d,),
                 "user_mlp_w": ((p + 1) * d, d), "user_mlp_b": (d,), "transfer_w": (H + 1, d, d),
                 "transfer_b": (H + 1, d), "h_item_w": (2 * d,), "h_item_b": (1,), "agg_w": (H, d, d),
@@ -137,9 +167,22 @@ class MVIN(object):
     def _build_model(self, seed):
         d, H, p = self.dim, self.h_hop, self.p_hop
         gen = torch.Generator().manual_seed(seed)
+        G = self.n_shards
+        self.n_local_rows = (self.n_entity + G - 1) // G
         shapes = self.param_shapes()
         host = {}
+        big = {}
         for name, shape in shapes.items():
+            if name in ("entity_emb", "user_emb") and (G > 1 or int(np.prod(shape)) > (1 << 26)):
+                # large or sharded tables are drawn on the device; fan-in/out are those of the FULL table
+                rows_full = self.n_entity if name == "entity_emb" else self.n_user
+                limit = math.sqrt(6.0 / (rows_full + d))
+                dgen = torch.Generator(device=self.device).manual_seed(seed * 1000003 + 17 * self.rank + len(big))
+                n_copies = G if (name == "entity_emb" and self.group is None) else 1
+                t = torch.empty((n_copies,) + tuple(shape), dtype=torch.float32, device=self.device)
+                t.uniform_(-limit, limit, generator=dgen)
+                big[name] = t
+                continue
             if name in ("agg_b", "agg_urh_b"):                     # aggregators.py:87,93 zero-init
                 host[name] = torch.zeros(shape)
             elif name in ("transfer_w", "agg_w"):                  # stacks of [d, d] matrices
@@ -153,7 +196,19 @@ class MVIN(object):
             else:
                 host[name] = self._xavier(shape, gen)
         self.params = {k: v.to(self.device).contiguous() for k, v in host.items()}
-        self.grads = {k: torch.zeros_like(v) for k, v in self.params.items()}
+        self._entity_all = self._entity_grad_all = None
+        for name, t in big.items():
+            if name == "entity_emb" and G > 1:
+                self._entity_all = t                               # [G or 1, n_local_rows, d]; [0] is the local shard
+                self.params[name] = t[0]
+            else:
+                self.params[name] = t[0]
+        self.params = {k: self.params[k] for k in shapes}          # header field order
+        self.grads = {k: torch.zeros_like(v) for k, v in self.params.items() if not (G > 1 and k == "entity_emb")}
+        if G > 1:
+            self._entity_grad_all = torch.zeros_like(self._entity_all)
+            self.grads["entity_emb"] = self._entity_grad_all[0]
+            self.grads = {k: self.grads[k] for k in shapes}
         self.adam_m = {k: torch.zeros_like(v) for k, v in self.params.items()}
         self.adam_v = {k: torch.zeros_like(v) for k, v in self.params.items()}
         self._p_struct = self._make_struct(self.params)
@@ -162,20 +217,81 @@ class MVIN(object):
         self._v_struct = self._make_struct(self.adam_v)
         check(self.lib.mvin_bind_params(self._handle, C.byref(self._p_struct)), "mvin_bind_params")
         check(self.lib.mvin_bind_grads(self._handle, C.byref(self._g_struct)), "mvin_bind_grads")
+        if G > 1:
+            self._bind_shards()
         # packed adjacency
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        adj_e = torch.from_numpy(self.adj_entity).to(self.device)
-        adj_r = torch.from_numpy(self.adj_relation).to(self.device)
-        self.adj_packed = torch.empty((self.n_entity, 2, self.n_neighbor), dtype=torch.int32, device=self.device)
-        check(self.lib.mvin_pack_adjacency(adj_e.data_ptr(), adj_r.data_ptr(), self.n_entity, self.n_neighbor,
-                                           self.adj_packed.data_ptr(), stream), "mvin_pack_adjacency")
+        if self._adj_packed_in is not None:
+            if self._adj_packed_in.shape[0] != self.n_entity:
+                raise ValueError("packed adjacency has the wrong number of rows")
+            self.adj_packed = self._adj_packed_in
+        else:
+            adj_e = torch.from_numpy(self.adj_entity).to(self.device)
+            adj_r = torch.from_numpy(self.adj_relation).to(self.device)
+            self.adj_packed = torch.empty((self.n_entity, 2, self.n_neighbor), dtype=torch.int32, device=self.device)
+            check(self.lib.mvin_pack_adjacency(adj_e.data_ptr(), adj_r.data_ptr(), self.n_entity, self.n_neighbor,
+                                               self.adj_packed.data_ptr(), stream), "mvin_pack_adjacency")
+            torch.cuda.synchronize(self.device)
+            del adj_e, adj_r
         check(self.lib.mvin_bind_adjacency(self._handle, self.adj_packed.data_ptr()), "mvin_bind_adjacency")
         torch.cuda.synchronize(self.device)
-        del adj_e, adj_r
         self._workspace: Optional[torch.Tensor] = None
         self._workspace_B = 0
         self._staging: Optional[torch.Tensor] = None
         self._dev_feed = None
+
+    def _bind_shards(self):
+        """Shard table for mvin_bind_entity_shards: local pointers (virtual shards) or the peers' shards opened through
+        CUDA IPC after an all-gather of the 64-byte handles (one process per GPU)."""
+        G, rows, d = self.n_shards, self.n_local_rows, self.dim
+        stride = rows * d * 4
+        if self.group is None:
+            e_ptrs = [self._entity_all.data_ptr() + g * stride for g in range(G)]
+            g_ptrs = [self._entity_grad_all.data_ptr() + g * stride for g in range(G)]
+        else:
+            import torch.distributed as dist
+            mine = []
+            for t in (self._entity_all, self._entity_grad_all):
+                hbuf = C.create_string_buffer(64)
+                off = C.c_int64()
+                check(self.lib.mvin_ipc_export(t.data_ptr(), hbuf, C.byref(off)), "mvin_ipc_export")
+                mine.append((hbuf.raw, int(off.value)))
+            everyone = [None] * G
+            dist.all_gather_object(everyone, mine, group=self.group)
+            e_ptrs, g_ptrs = [], []
+            for r, (he, hg) in enumerate(everyone):
+                if r == self.rank:
+                    e_ptrs.append(self._entity_all.data_ptr())
+                    g_ptrs.append(self._entity_grad_all.data_ptr())
+                    continue
+                for (raw, off), out in ((he, e_ptrs), (hg, g_ptrs)):
+                    ptr = C.c_void_p()
+                    check(self.lib.mvin_ipc_open(raw, off, C.byref(ptr)), "mvin_ipc_open")
+                    out.append(ptr.value)
+            dist.barrier(group=self.group)
+        arr_e = (C.c_void_p * G)(*e_ptrs)
+        arr_g = (C.c_void_p * G)(*g_ptrs)
+        check(self.lib.mvin_bind_entity_shards(self._handle, G, arr_e, arr_g), "mvin_bind_entity_shards")
+        self._shard_ptrs = (e_ptrs, g_ptrs)
+        if self.group is not None:
+            check(self.lib.mvin_set_batch_scale(self._handle, self.batch_size * G, 1.0 / G), "mvin_set_batch_scale")
+
+    def begin_step(self):
+        """Sharded mode: zero this rank's entity-gradient shard(s) and fence the ranks (peers scatter into it during
+        the backward pass and read the entity shard during the forward pass).  No-op otherwise."""
+        if self.n_shards == 1:
+            return
+        self._entity_grad_all.zero_()
+        if self.group is not None:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)
+
+    def end_step(self):
+        """Sharded mode: fence the ranks after the backward pass (every peer's contribution has landed)."""
+        if self.group is not None:
+            import torch.distributed as dist
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
 
     @staticmethod
     def _make_struct(tensors) -> Params:
@@ -254,14 +370,36 @@ class MVIN(object):
         B = items.shape[0]
         ws = self._ensure_workspace(B)
         ptr = lambda a: a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr()
-        if apply_adam:
+        if self.n_shards > 1:
+            if apply_adam and self.group is None:
+                raise NotImplementedError("virtual shards (entity_shards > 1 without a process group) are fwd/bwd only")
+            self.begin_step()
+        fused_adam = apply_adam and self.group is None
+        if fused_adam:
             self.step += 1
         check(self.lib.mvin_train_step_host(
             self._handle, ptr(users), ptr(items), ptr(labels), ptr(mem_h), ptr(mem_r), ptr(mem_t), B,
-            self._staging.data_ptr(), ws.data_ptr(), C.byref(self._m_struct) if apply_adam else None,
-            C.byref(self._v_struct) if apply_adam else None, self.lr, max(self.step, 1), self._losses_host.data_ptr(),
+            self._staging.data_ptr(), ws.data_ptr(), C.byref(self._m_struct) if fused_adam else None,
+            C.byref(self._v_struct) if fused_adam else None, self.lr, max(self.step, 1), self._losses_host.data_ptr(),
             self._stream()), "mvin_train_step_host")
-        return self._losses_host.numpy().copy()
+        losses = self._losses_host.numpy().copy()
+        if self.group is not None:
+            losses = self.allreduce_replicated(losses)
+            self.end_step()
+            if apply_adam:
+                self.adam_step_device()
+        return losses
+
+    def allreduce_replicated(self, losses=None):
+        """One-process-per-GPU ranks: SUM all-reduce (NCCL) of the gradients of every replicated parameter (all but
+        the sharded entity table, whose contributions already landed in the owners' shards through peer
+        reductions, and the user table, which only carries its dense L2 term under --ablation all) and of the
+        4 loss scalars."""
+        small = [self.grads[k] for k in self.grads if k not in ("entity_emb", "user_emb")]
+        extra = torch.as_tensor(losses if losses is not None else np.zeros(4, np.float32), dtype=torch.float32)
+        out = sharding.allreduce_flat(small, self.group, extra=extra)
+        self.grads["user_emb"].mul_(float(self.n_shards))
+        return out.cpu().numpy()
 
     # ------------------------------------------------------------------ reference API (model.py:416-444)
     def train(self, sess, feed_dict):
@@ -371,14 +509,38 @@ class MVIN(object):
         """Set parameters from a dict keyed by the reference's variable names (see oracle.param_shapes)."""
         for name, (field, idx) in self._name_map().items():
             src = torch.as_tensor(np.asarray(named[name]), dtype=torch.float32)
+            if field == "entity_emb" and self.n_shards > 1:
+                self._scatter_entity_table(src, self._entity_all)
+                continue
             dst = self.params[field] if idx is None else self.params[field][idx]
             dst.copy_(src.reshape(dst.shape))
         torch.cuda.synchronize(self.device)
+
+    def _scatter_entity_table(self, full, shards):
+        """full [n_entity, d] (host) -> shards[g or 0][e // G] for e % G == g (all shards, or this rank's one)."""
+        G = self.n_shards
+        for g in (range(G) if self.group is None else [self.rank]):
+            shards[g if self.group is None else 0].copy_(sharding.scatter_table(full, G, g))
+
+    def _gather_entity_table(self, shards) -> np.ndarray:
+        """Inverse of _scatter_entity_table; with a process group every rank receives the full table."""
+        G = self.n_shards
+        if self.group is None:
+            parts = [shards[g] for g in range(G)]
+        else:
+            import torch.distributed as dist
+            parts = [torch.empty_like(shards[0]) for _ in range(G)]
+            dist.all_gather(parts, shards[0].contiguous(), group=self.group)
+        return sharding.gather_table(parts, self.n_entity).numpy().copy()
 
     def _export(self, tensors) -> Dict[str, np.ndarray]:
         from_shapes = {"h_emb_item_mlp_matrix": (2 * self.dim, 1), "h_emb_item_mlp_bias": (1,)}
         out = {}
         for name, (field, idx) in self._name_map().items():
+            if field == "entity_emb" and self.n_shards > 1:
+                out[name] = self._gather_entity_table(self._entity_all if tensors is self.params
+                                                      else self._entity_grad_all)
+                continue
             t = tensors[field] if idx is None else tensors[field][idx]
             a = t.detach().cpu().numpy().copy()
             if name.endswith("urh_weights"):

@@ -147,3 +147,91 @@ def test_native_library_is_what_ran():
     model.loss_and_grads(feed_dict(model, prob))
     assert model.launch_count() - before >= 20
     assert any("libmvin_b200.so" in line for line in open("/proc/self/maps"))
+
+
+@pytest.mark.parametrize("G,n_entity", [(4, 301), (2, 300), (8, 500)])
+def test_virtual_entity_shards_match_oracle(G, n_entity):
+    """Row-sharded entity table (mvin_bind_entity_shards) with all shards on one device: same scores / loss /
+    gradients as the oracle's single table, including n_entity not divisible by the shard count."""
+    from mvin_b200 import MVIN
+    args = make_args(dim=32, neighbor_sample_size=8, h_hop=2, p_hop=2, n_memory=16, batch_size=48)
+    prob = make_problem(args, n_entity=n_entity, seed=11 + G)
+    model = MVIN(args, prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"], prob["adj_relation"],
+                 entity_shards=G)
+    model.load_named_parameters({k: v.numpy() for k, v in prob["P"].items()})
+    assert np.array_equal(model.named_parameters()["entity_emb_matrix"], prob["P"]["entity_emb_matrix"].numpy())
+    fd = feed_dict(model, prob)
+    out, grads = orc.loss_and_grads(prob["P"], prob["cfg"], prob["adj_entity"], prob["adj_relation"], prob["users"],
+                                    prob["items"], prob["mem_h"], prob["mem_r"], prob["mem_t"], prob["labels"])
+    assert rel_err(model.get_raw_scores(fd), out.scores.detach().numpy()) < SCORE_TOL
+    losses = model.loss_and_grads(fd)
+    assert abs(float(losses[0]) - float(out.loss.detach())) <= 1e-4 * max(1.0, abs(float(out.loss.detach())))
+    _assert_grads(model.named_gradients(), lambda k: grads[k].numpy())
+    with pytest.raises(NotImplementedError):
+        model.train(None, fd)
+
+
+def _two_rank_worker(rank, port, ret):
+    import os
+    import torch.distributed as dist
+    from mvin_b200 import MVIN, sharding
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=2, device_id=torch.device("cuda", rank))
+    try:
+        Bg = 64
+        args_g = make_args(dim=32, neighbor_sample_size=8, h_hop=2, p_hop=2, n_memory=16, batch_size=Bg)
+        prob = make_problem(args_g, n_entity=301, seed=5)
+        args_l = make_args(dim=32, neighbor_sample_size=8, h_hop=2, p_hop=2, n_memory=16, batch_size=Bg // 2)
+        model = MVIN(args_l, prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"],
+                     prob["adj_relation"], entity_shards=2, process_group=dist.group.WORLD)
+        model.load_named_parameters({k: v.numpy() for k, v in prob["P"].items()})
+        sl = sharding.split_batch(Bg, rank, 2)
+        local = dict(prob, users=prob["users"][sl], items=prob["items"][sl], labels=prob["labels"][sl],
+                     mem_h=[m[sl] for m in prob["mem_h"]], mem_r=[m[sl] for m in prob["mem_r"]],
+                     mem_t=[m[sl] for m in prob["mem_t"]])
+        fd = feed_dict(model, local)
+        losses = model.loss_and_grads(fd)                    # summed over the ranks inside
+        out, grads = orc.loss_and_grads(prob["P"], prob["cfg"], prob["adj_entity"], prob["adj_relation"],
+                                        prob["users"], prob["items"], prob["mem_h"], prob["mem_r"], prob["mem_t"],
+                                        prob["labels"])
+        ok = abs(float(losses[0]) - float(out.loss.detach())) <= 1e-4 * max(1.0, abs(float(out.loss.detach())))
+        got = model.named_gradients()
+        bad = []
+        for k, g in got.items():
+            ref = grads[k].numpy().reshape(g.shape)
+            if not np.abs(g - ref).max() <= GRAD_TOL * max(np.abs(ref).max(), 1e-8) + 1e-8:
+                bad.append(k)
+        # one Adam step on every rank keeps the replicated parameters identical and updates each shard
+        model.train(None, fd)
+        w = torch.from_numpy(model.named_parameters()["user_mlp_matrix"]).cuda()
+        both = [torch.empty_like(w) for _ in range(2)]
+        dist.all_gather(both, w)
+        ok = ok and torch.equal(both[0], both[1])
+        ret[rank] = (bool(ok), bad)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_rank_sharded_entity_table_matches_oracle():
+    """One process per GPU, entity table row-sharded over the 2 ranks, peers' shards mapped through CUDA IPC:
+    NVLink peer loads in the forward pass and peer reductions in the backward pass give the oracle's gradients on
+    the concatenated batch."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_two_rank_worker, args=(r, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+        assert p.exitcode == 0
+    for r in range(2):
+        ok, bad = ret[r]
+        assert ok and not bad, (r, ok, bad)
