@@ -58,6 +58,9 @@ MVIN_DEV void red_add4(float* p, float4 v) {
                : "memory");
 }
 
+MVIN_DEV void red_add2(float* p, float x, float y) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(x), "f"(y) : "memory");
+}
 
 // Entity table / entity-gradient table, optionally row-sharded over 2^shift shards: entity e lives in shard
 // (e & mask) at local row (e >> shift).  `shards` is a device array of base pointers -- the local shard and, on a

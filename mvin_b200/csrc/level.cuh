@@ -30,11 +30,27 @@ struct TC {
   static constexpr int LD = D + 4;                                    // padded leading dimension of a smem row tile
   static constexpr int NW = NT / 32;                                  // warps per CTA
   static constexpr int G = 32 / LPR;                                  // rows one warp load instruction covers
-  static constexpr int TMW = (D / NTY) > 0 ? (D / NTY) : 1;           // dW rows per thread
+  static constexpr int TMW = (D / NTY) > 0 ? (D / NTY) : 1;           // dW rows per thread (SIMT path)
+  static constexpr int LDW = D + 8;                                   // padded leading dimension of a smem weight
+  static constexpr int WSZ = D * LDW;                                 // floats of one smem weight
+  // tensor-core path (3xTF32 mma.sync, d >= 32): the 64 x D output tile is split into 4 row blocks of 16 rows and
+  // NW/4 column groups, one (row block, column group) per warp
+  static constexpr bool TCORE = D >= 32;
+  static constexpr int CGRP = NW / 4 > 0 ? NW / 4 : 1;                // column groups
+  static constexpr int NTW = D / CGRP / 8 > 0 ? D / CGRP / 8 : 1;     // n8 tiles per warp
+  static constexpr int MT = D / 16 > 0 ? D / 16 : 1;                  // m16 tiles of a D x D weight gradient
+  static constexpr int TPW = (MT * (D / 8)) / NW > 0 ? (MT * (D / 8)) / NW : 1;   // dW n8 tiles per warp
+  static constexpr int DWN = TCORE ? TPW : TMW;                       // per-thread dW accumulator rows of 4 floats
 };
 
 constexpr int MAX_K = 64;
 constexpr int MAX_LV = 3;
+
+// rows per pair are a runtime K^h: q = n / d through a 64-bit multiply-high with M = floor(2^64 / d) + 1 (exact for
+// n, d < 2^32; d = 1 is flagged by M = 0) instead of the ~100-instruction 64-bit software division
+MVIN_DEV long fastdiv(long n, unsigned long long M) {
+  return M == 0 ? n : (long)__umul64hi((unsigned long long)n, M);
+}
 
 // which level does this CTA work on?  CTAs [cta_end[l-1], cta_end[l]) own level l.
 struct CtaSlice { int level, local, count; };
@@ -60,7 +76,7 @@ MVIN_DEV void mm_tile(const float* __restrict__ As, const float* __restrict__ Ws
     for (int i = 0; i < TM; ++i) a[i] = ld4(&As[(ty * TM + i) * LD + k]);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      const float4 w = ld4(&Ws[(k + kk) * D + tx * 4]);
+      const float4 w = ld4(&Ws[(k + kk) * TC<D>::LDW + tx * 4]);
 #pragma unroll
       for (int i = 0; i < TM; ++i) {
         const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
@@ -73,44 +89,148 @@ MVIN_DEV void mm_tile(const float* __restrict__ As, const float* __restrict__ Ws
   }
 }
 
-// dw[i][0..3] += sum_r As[r][ty*TMW+i] * Gs[r][tx*4 .. tx*4+3]      (dW = A^T G over the R rows of a tile)
+// ---- 3xTF32 tensor-core tile GEMMs (mma.sync.m16n8k8): fp32 operands are split x = hi + lo with hi, lo in
+// TF32, and  a.b ~= hi_a.hi_b + hi_a.lo_b + lo_a.hi_b  is accumulated in fp32 -- fp32-level accuracy (the dropped
+// lo.lo term is ~2^-22 relative), which plain TF32 does not give (parity is 1e-4 on the final scores).
+// hi = x truncated to TF32 (one LOP3; the residual x - hi is then exact in fp32), lo = x - hi handed to the tensor
+// core as is: the MMA reads the TF32 bits of its operands only, i.e. truncates lo to 10 mantissa bits, leaving a
+// ~2^-20 relative error per product.  (cvt.rna.tf32.f32 costs ~8 SASS instructions on sm_100 and made the split,
+// not the MMA, the bottleneck.)
+MVIN_DEV void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+MVIN_DEV void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+MVIN_DEV void mma3(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], const uint32_t (&bh)[2],
+                   const uint32_t (&bl)[2]) {
+  mma_tf32(c, al, bh);
+  mma_tf32(c, ah, bl);
+  mma_tf32(c, ah, bh);
+}
+
+// acc[i][0..3] (thread-mapped, rows ty*TM+i, cols tx*4..) += (As . Ws)[row][col];  As [64][LD] is CLOBBERED (it
+// receives the product), Ws is [D][LDW].  Every thread of the CTA must call it; As must be complete and
+// synchronised on entry; the caller synchronises before overwriting As again.
 template <int D>
-MVIN_DEV void dw_tile(const float* __restrict__ As, const float* __restrict__ Gs, int ty, int tx,
-                      float (&dw)[TC<D>::TMW][4]) {
-  constexpr int TMW = TC<D>::TMW, LD = TC<D>::LD, R = TC<D>::R;
-  if (ty * TMW >= D) return;
-#pragma unroll 4
-  for (int r = 0; r < R; ++r) {
-    const float4 gv = ld4(&Gs[r * LD + tx * 4]);
-    float av[TMW];
-    if constexpr (TMW % 4 == 0) {
+MVIN_DEV void tile_mm(float* __restrict__ As, const float* __restrict__ Ws, int ty, int tx,
+                      float (&acc)[TC<D>::TM][4]) {
+  using C = TC<D>;
+  if constexpr (!C::TCORE) {
+    mm_tile<D>(As, Ws, ty, tx, acc);
+  } else {
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, g = lane / 4, t = lane % 4;
+    const int r0 = (warp % 4) * 16, n0 = (warp / 4) * (C::NTW * 8);
+    float c[C::NTW][4];
 #pragma unroll
-      for (int q = 0; q < TMW / 4; ++q) {
-        const float4 a4 = ld4(&As[r * LD + ty * TMW + q * 4]);
-        av[q * 4 + 0] = a4.x; av[q * 4 + 1] = a4.y; av[q * 4 + 2] = a4.z; av[q * 4 + 3] = a4.w;
+    for (int j = 0; j < C::NTW; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
+#pragma unroll 2
+    for (int k0 = 0; k0 < D; k0 += 8) {
+      uint32_t ah[4], al[4];
+      split_tf32(As[(r0 + g) * C::LD + k0 + t], ah[0], al[0]);
+      split_tf32(As[(r0 + g + 8) * C::LD + k0 + t], ah[1], al[1]);
+      split_tf32(As[(r0 + g) * C::LD + k0 + t + 4], ah[2], al[2]);
+      split_tf32(As[(r0 + g + 8) * C::LD + k0 + t + 4], ah[3], al[3]);
+#pragma unroll
+      for (int j = 0; j < C::NTW; ++j) {
+        uint32_t bh[2], bl[2];
+        split_tf32(Ws[(k0 + t) * C::LDW + n0 + j * 8 + g], bh[0], bl[0]);
+        split_tf32(Ws[(k0 + t + 4) * C::LDW + n0 + j * 8 + g], bh[1], bl[1]);
+        mma3(c[j], ah, al, bh, bl);
       }
-    } else {
-#pragma unroll
-      for (int i = 0; i < TMW; ++i) av[i] = As[r * LD + ty * TMW + i];
     }
+    __syncthreads();
 #pragma unroll
-    for (int i = 0; i < TMW; ++i) {
-      dw[i][0] = fmaf(av[i], gv.x, dw[i][0]);
-      dw[i][1] = fmaf(av[i], gv.y, dw[i][1]);
-      dw[i][2] = fmaf(av[i], gv.z, dw[i][2]);
-      dw[i][3] = fmaf(av[i], gv.w, dw[i][3]);
+    for (int j = 0; j < C::NTW; ++j) {
+      *reinterpret_cast<float2*>(&As[(r0 + g) * C::LD + n0 + j * 8 + 2 * t]) = make_float2(c[j][0], c[j][1]);
+      *reinterpret_cast<float2*>(&As[(r0 + g + 8) * C::LD + n0 + j * 8 + 2 * t]) = make_float2(c[j][2], c[j][3]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < C::TM; ++i) {
+      const float4 v = ld4(&As[(ty * C::TM + i) * C::LD + tx * 4]);
+      acc[i][0] += v.x; acc[i][1] += v.y; acc[i][2] += v.z; acc[i][3] += v.w;
     }
   }
 }
 
-// CTA-level flush of the register-resident weight gradient (and of the per-thread bias partial) to global memory
+// dW += A^T G over the 64 rows of a tile (A = As [64][LD], G = Gs [64][LD]); register-resident accumulator.
+//   SIMT path:  dw[i] = dW[ty*TMW+i][tx*4 .. +3]
+//   tensor-core path: warp owns m16 tile (warp % MT) and TPW consecutive n8 tiles; dw[j] is the mma C fragment
 template <int D>
-MVIN_DEV void dw_flush(float (&dw)[TC<D>::TMW][4], float* __restrict__ dW, int ty, int tx) {
-  constexpr int TMW = TC<D>::TMW;
-  if (ty * TMW >= D) return;
+MVIN_DEV void dw_tile(const float* __restrict__ As, const float* __restrict__ Gs, int ty, int tx,
+                      float (&dw)[TC<D>::DWN][4]) {
+  using C = TC<D>;
+  constexpr int LD = C::LD, R = C::R;
+  if constexpr (!C::TCORE) {
+    constexpr int TMW = C::TMW;
+    if (ty * TMW >= D) return;
+#pragma unroll 4
+    for (int r = 0; r < R; ++r) {
+      const float4 gv = ld4(&Gs[r * LD + tx * 4]);
+      float av[TMW];
+      if constexpr (TMW % 4 == 0) {
 #pragma unroll
-  for (int i = 0; i < TMW; ++i)
-    red_add4(dW + (long)(ty * TMW + i) * D + tx * 4, make_float4(dw[i][0], dw[i][1], dw[i][2], dw[i][3]));
+        for (int q = 0; q < TMW / 4; ++q) {
+          const float4 a4 = ld4(&As[r * LD + ty * TMW + q * 4]);
+          av[q * 4 + 0] = a4.x; av[q * 4 + 1] = a4.y; av[q * 4 + 2] = a4.z; av[q * 4 + 3] = a4.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < TMW; ++i) av[i] = As[r * LD + ty * TMW + i];
+      }
+#pragma unroll
+      for (int i = 0; i < TMW; ++i) {
+        dw[i][0] = fmaf(av[i], gv.x, dw[i][0]);
+        dw[i][1] = fmaf(av[i], gv.y, dw[i][1]);
+        dw[i][2] = fmaf(av[i], gv.z, dw[i][2]);
+        dw[i][3] = fmaf(av[i], gv.w, dw[i][3]);
+      }
+    }
+  } else {
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, g = lane / 4, t = lane % 4;
+    const int i0 = (warp % C::MT) * 16, j0 = (warp / C::MT) * (C::TPW * 8);
+#pragma unroll 2
+    for (int k0 = 0; k0 < R; k0 += 8) {
+      uint32_t ah[4], al[4];
+      split_tf32(As[(k0 + t) * LD + i0 + g], ah[0], al[0]);
+      split_tf32(As[(k0 + t) * LD + i0 + g + 8], ah[1], al[1]);
+      split_tf32(As[(k0 + t + 4) * LD + i0 + g], ah[2], al[2]);
+      split_tf32(As[(k0 + t + 4) * LD + i0 + g + 8], ah[3], al[3]);
+#pragma unroll
+      for (int j = 0; j < C::TPW; ++j) {
+        uint32_t bh[2], bl[2];
+        split_tf32(Gs[(k0 + t) * LD + j0 + j * 8 + g], bh[0], bl[0]);
+        split_tf32(Gs[(k0 + t + 4) * LD + j0 + j * 8 + g], bh[1], bl[1]);
+        mma3(dw[j], ah, al, bh, bl);
+      }
+    }
+  }
+}
+
+// CTA-level flush of the register-resident weight gradient to global memory
+template <int D>
+MVIN_DEV void dw_flush(float (&dw)[TC<D>::DWN][4], float* __restrict__ dW, int ty, int tx) {
+  using C = TC<D>;
+  if constexpr (!C::TCORE) {
+    constexpr int TMW = C::TMW;
+    if (ty * TMW >= D) return;
+#pragma unroll
+    for (int i = 0; i < TMW; ++i)
+      red_add4(dW + (long)(ty * TMW + i) * D + tx * 4, make_float4(dw[i][0], dw[i][1], dw[i][2], dw[i][3]));
+  } else {
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, g = lane / 4, t = lane % 4;
+    const int i0 = (warp % C::MT) * 16, j0 = (warp / C::MT) * (C::TPW * 8);
+#pragma unroll
+    for (int j = 0; j < C::TPW; ++j) {
+      red_add2(dW + (long)(i0 + g) * D + j0 + j * 8 + 2 * t, dw[j][0], dw[j][1]);
+      red_add2(dW + (long)(i0 + g + 8) * D + j0 + j * 8 + 2 * t, dw[j][2], dw[j][3]);
+    }
+  }
 }
 // red[D] (shared, zeroed) += per-thread column partials, then one global atomic per column
 template <int D>
@@ -126,7 +246,7 @@ MVIN_DEV void bias_flush(float4 part, float* __restrict__ red, float* __restrict
 
 template <int D>
 MVIN_DEV void load_weight(float* __restrict__ Ws, const float* __restrict__ Wg, int tid) {
-  for (int i = tid * 4; i < D * D; i += TC<D>::NT * 4) st4(&Ws[i], ldg4(&Wg[i]));
+  for (int i = tid * 4; i < D * D; i += TC<D>::NT * 4) st4(&Ws[(i / D) * TC<D>::LDW + i % D], ldg4(&Wg[i]));
 }
 
 // attention of one node over its K sampled neighbours: p_k = softmax_k(s[rel_k])  (aggregators.py:121-139 with
@@ -163,7 +283,7 @@ MVIN_DEV Att attend(const int32_t* __restrict__ arow, int K, const float* __rest
 // thread walks a strip of the tile and flushes one atomic per (pair, column) run.
 template <int D>
 MVIN_DEV void tile_rows_to_pairs(const float* __restrict__ As, float* __restrict__ du, long row0, long rows,
-                                 int rpp, int tid) {
+                                 unsigned long long rpp_magic, int tid) {
   using C = TC<D>;
   constexpr int PARTS = (C::NT / D) < C::R ? (C::NT / D) : C::R;
   constexpr int RPS = C::R / PARTS;                   // rows per strip
@@ -175,7 +295,7 @@ MVIN_DEV void tile_rows_to_pairs(const float* __restrict__ As, float* __restrict
   for (int r = part * RPS; r < (part + 1) * RPS; ++r) {
     const long row = row0 + r;
     if (row >= rows) break;
-    const long b = row / rpp;
+    const long b = fastdiv(row, rpp_magic);
     if (b != cur) {
       if (cur >= 0) atomicAdd(du + cur * D + col, acc);
       cur = b;
@@ -200,6 +320,7 @@ struct TransformLevel {
   float* db;            // bwd out [D]
   long rows;
   int rpp;              // rows per pair = K^h
+  unsigned long long rpp_magic;
 };
 struct TransformArgs {
   TransformLevel lv[MAX_LV];
@@ -216,7 +337,7 @@ __global__ void __launch_bounds__(TC<D>::NT) transform_fwd_kernel(TransformArgs 
   using C = TC<D>;
   extern __shared__ __align__(16) float smem[];
   float* Ws = smem;
-  float* As = Ws + D * D;
+  float* As = Ws + C::WSZ;
   const int tid = threadIdx.x, tx = tid % C::LPR, ty = tid / C::LPR;
   const CtaSlice cs = cta_slice(a.cta_end, a.nlev);
   const TransformLevel& L = a.lv[cs.level];
@@ -232,7 +353,7 @@ __global__ void __launch_bounds__(TC<D>::NT) transform_fwd_kernel(TransformArgs 
       float4 x = f4zero();
       if (row < L.rows) {
         const long e = L.ent[row];
-        x = f4add(ldg4(erow(a.E, e, D) + tx * 4), ldg4(a.u + (row / L.rpp) * D + tx * 4));
+        x = f4add(ldg4(erow(a.E, e, D) + tx * 4), ldg4(a.u + fastdiv(row, L.rpp_magic) * D + tx * 4));
       }
       st4(&As[r * C::LD + tx * 4], x);
     }
@@ -240,7 +361,7 @@ __global__ void __launch_bounds__(TC<D>::NT) transform_fwd_kernel(TransformArgs 
     float acc[C::TM][4];
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) { acc[i][0] = bias.x; acc[i][1] = bias.y; acc[i][2] = bias.z; acc[i][3] = bias.w; }
-    mm_tile<D>(As, Ws, ty, tx, acc);
+    tile_mm<D>(As, Ws, ty, tx, acc);
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) {
       const long row = row0 + ty * C::TM + i;
@@ -257,7 +378,7 @@ __global__ void __launch_bounds__(TC<D>::NT) transform_bwd_kernel(TransformArgs 
   using C = TC<D>;
   extern __shared__ __align__(16) float smem[];
   float* Ws = smem;
-  float* As = Ws + D * D;                 // dT tile, later gx tile
+  float* As = Ws + C::WSZ;                 // dT tile, later gx tile
   float* Xs = As + C::R * C::LD;          // XU tile
   float* red = Xs + C::R * C::LD;         // [D]
   const int tid = threadIdx.x, tx = tid % C::LPR, ty = tid / C::LPR;
@@ -265,9 +386,9 @@ __global__ void __launch_bounds__(TC<D>::NT) transform_bwd_kernel(TransformArgs 
   const TransformLevel& L = a.lv[cs.level];
   load_weight<D>(Ws, L.W, tid);
   if (tid < D) red[tid] = 0.f;
-  float dw[C::TMW][4];
+  float dw[C::DWN][4];
 #pragma unroll
-  for (int i = 0; i < C::TMW; ++i) dw[i][0] = dw[i][1] = dw[i][2] = dw[i][3] = 0.f;
+  for (int i = 0; i < C::DWN; ++i) dw[i][0] = dw[i][1] = dw[i][2] = dw[i][3] = 0.f;
   float4 bpart = f4zero();
   __syncthreads();
   const long ntiles = (L.rows + C::R - 1) / C::R;
@@ -282,7 +403,7 @@ __global__ void __launch_bounds__(TC<D>::NT) transform_bwd_kernel(TransformArgs 
         g = ld4(L.g1 + row * D + tx * 4);
         if (L.g2) g = f4add(g, ld4(L.g2 + row * D + tx * 4));
         const long e = L.ent[row];
-        x = f4add(ldg4(erow(a.E, e, D) + tx * 4), ldg4(a.u + (row / L.rpp) * D + tx * 4));
+        x = f4add(ldg4(erow(a.E, e, D) + tx * 4), ldg4(a.u + fastdiv(row, L.rpp_magic) * D + tx * 4));
       }
       bpart = f4add(bpart, g);
       st4(&As[r * C::LD + tx * 4], g);
@@ -293,7 +414,7 @@ __global__ void __launch_bounds__(TC<D>::NT) transform_bwd_kernel(TransformArgs 
     float acc[C::TM][4];
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-    mm_tile<D>(As, Ws, ty, tx, acc);
+    tile_mm<D>(As, Ws, ty, tx, acc);
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) {
@@ -304,7 +425,7 @@ __global__ void __launch_bounds__(TC<D>::NT) transform_bwd_kernel(TransformArgs 
       st4(&As[r * C::LD + tx * 4], gx);
     }
     __syncthreads();
-    tile_rows_to_pairs<D>(As, a.du, row0, L.rows, L.rpp, tid);
+    tile_rows_to_pairs<D>(As, a.du, row0, L.rows, L.rpp_magic, tid);
     __syncthreads();
   }
   dw_flush<D>(dw, L.dW, ty, tx);
@@ -312,9 +433,9 @@ __global__ void __launch_bounds__(TC<D>::NT) transform_bwd_kernel(TransformArgs 
 }
 
 template <int D>
-constexpr size_t transform_fwd_smem() { return sizeof(float) * (D * D + TC<D>::R * TC<D>::LD); }
+constexpr size_t transform_fwd_smem() { return sizeof(float) * (TC<D>::WSZ + TC<D>::R * TC<D>::LD); }
 template <int D>
-constexpr size_t transform_bwd_smem() { return sizeof(float) * (D * D + 2 * TC<D>::R * TC<D>::LD + D); }
+constexpr size_t transform_bwd_smem() { return sizeof(float) * (TC<D>::WSZ + 2 * TC<D>::R * TC<D>::LD + D); }
 
 // ---------------------------------------------------------------------------------------------------------
 // one aggregator iteration, forward, all levels  (aggregators.py:98-146; model.py:295-306)
@@ -331,6 +452,7 @@ struct AggLevel {
   float* V;             // [rows, D]
   long rows;
   int rpp;
+  unsigned long long rpp_magic;
   int leaf;
 };
 struct AggArgs {
@@ -345,6 +467,7 @@ struct AggArgs {
   const float* bt;      // leaf: b_t[L]
   const float* Wa;      // [D, D]
   const float* ba;      // [D]
+  const float* Se;      // leaf, entity mode: [n_entity, D] per-entity S = sum_k p_k E[n_k] (leaf_entity_fwd_kernel)
   int K, n_rel;
 };
 
@@ -353,8 +476,8 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
   using C = TC<D>;
   extern __shared__ __align__(16) float smem[];
   float* Wa_s = smem;
-  float* Wt_s = Wa_s + D * D;
-  float* As = Wt_s + (HAS_LEAF ? D * D : 0);
+  float* Wt_s = Wa_s + C::WSZ;
+  float* As = Wt_s + (HAS_LEAF ? C::WSZ : 0);
   float* pw = As + C::R * C::LD;                           // [NW][MAX_K]
   int* idw = reinterpret_cast<int*>(pw + C::NW * MAX_K);   // [NW][MAX_K]
   float* s_s = reinterpret_cast<float*>(idw + C::NW * MAX_K);
@@ -381,7 +504,15 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
     // ---- neighbour phase: warp per row ----
     for (int r = warp; r < C::R; r += C::NW) {
       const long row = row0 + r;
-      if (row < L.rows) {
+      if (row < L.rows && leaf && a.Se != nullptr) {
+        // entity mode: S depends on the node's entity only and was computed once per distinct entity
+        if (g == 0) {
+          const long e = L.ent[row];
+          const float4 o = f4add(ldg4(a.Se + e * D + c * 4), ldg4(a.u + fastdiv(row, L.rpp_magic) * D + c * 4));
+          st4(L.SU + row * D + c * 4, o);
+          st4(&As[r * C::LD + c * 4], o);
+        }
+      } else if (row < L.rows) {
         const long e = L.ent[row];
         const Att at = attend(a.adj + e * 2 * K, K, s_s, lane);
         pw_w[lane] = at.p0;
@@ -401,7 +532,7 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
         if (g == 0) {
           float4 o;
           if (leaf) {
-            o = f4add(acc, ldg4(a.u + (row / L.rpp) * D + c * 4));
+            o = f4add(acc, ldg4(a.u + fastdiv(row, L.rpp_magic) * D + c * 4));
             st4(L.SU + row * D + c * 4, o);
           } else {
             o = f4fma(invK, acc, ld4(L.self + row * D + c * 4));
@@ -420,7 +551,7 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
     if (leaf) {
 #pragma unroll
       for (int i = 0; i < C::TM; ++i) { acc[i][0] = bt.x; acc[i][1] = bt.y; acc[i][2] = bt.z; acc[i][3] = bt.w; }
-      mm_tile<D>(As, Wt_s, ty, tx, acc);
+      tile_mm<D>(As, Wt_s, ty, tx, acc);
       __syncthreads();
 #pragma unroll
       for (int i = 0; i < C::TM; ++i) {
@@ -437,7 +568,7 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
     }
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) { acc[i][0] = ba.x; acc[i][1] = ba.y; acc[i][2] = ba.z; acc[i][3] = ba.w; }
-    mm_tile<D>(As, Wa_s, ty, tx, acc);
+    tile_mm<D>(As, Wa_s, ty, tx, acc);
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) {
       const long row = row0 + ty * C::TM + i;
@@ -451,7 +582,7 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
 
 template <int D, bool HAS_LEAF>
 constexpr size_t agg_fwd_smem(int n_rel) {
-  return sizeof(float) * ((HAS_LEAF ? 2 : 1) * D * D + TC<D>::R * TC<D>::LD + 2 * TC<D>::NW * MAX_K + n_rel);
+  return sizeof(float) * ((HAS_LEAF ? 2 : 1) * TC<D>::WSZ + TC<D>::R * TC<D>::LD + 2 * TC<D>::NW * MAX_K + n_rel);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -478,6 +609,7 @@ struct AggBwdLevel {
   float* dchild;        // inner: [rows*K, D]
   long rows;
   int rpp;
+  unsigned long long rpp_magic;
   int leaf;
 };
 struct AggBwdArgs {
@@ -496,6 +628,7 @@ struct AggBwdArgs {
   GTab dE;              // leaf
   float* du;            // leaf: [B, D]
   float* ds;            // [n_rel]
+  float* GSe;           // leaf, entity mode: [n_entity, D] per-entity sum of gsu (consumed by leaf_entity_bwd_kernel)
   int K, n_rel;
 };
 
@@ -504,8 +637,8 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
   using C = TC<D>;
   extern __shared__ __align__(16) float smem[];
   float* Wa_s = smem;
-  float* Wt_s = Wa_s + D * D;
-  float* Gs = Wt_s + (HAS_LEAF ? D * D : 0);
+  float* Wt_s = Wa_s + C::WSZ;
+  float* Gs = Wt_s + (HAS_LEAF ? C::WSZ : 0);
   float* Ys = Gs + C::R * C::LD;
   float* pw = Ys + C::R * C::LD;                       // [NW][MAX_K]
   float* dpw = pw + C::NW * MAX_K;                     // [NW][MAX_K]
@@ -527,11 +660,11 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
   float* pw_w = pw + warp * MAX_K;
   float* dpw_w = dpw + warp * MAX_K;
   int* idw_w = idw + warp * MAX_K;
-  float dwa[C::TMW][4], dwt[HAS_LEAF ? C::TMW : 1][4];
+  float dwa[C::DWN][4], dwt[HAS_LEAF ? C::DWN : 1][4];
 #pragma unroll
-  for (int i = 0; i < C::TMW; ++i) dwa[i][0] = dwa[i][1] = dwa[i][2] = dwa[i][3] = 0.f;
+  for (int i = 0; i < C::DWN; ++i) dwa[i][0] = dwa[i][1] = dwa[i][2] = dwa[i][3] = 0.f;
 #pragma unroll
-  for (int i = 0; i < (HAS_LEAF ? C::TMW : 1); ++i) dwt[i][0] = dwt[i][1] = dwt[i][2] = dwt[i][3] = 0.f;
+  for (int i = 0; i < (HAS_LEAF ? C::DWN : 1); ++i) dwt[i][0] = dwt[i][1] = dwt[i][2] = dwt[i][3] = 0.f;
   float4 bpa = f4zero(), bpt = f4zero();
   __syncthreads();
 
@@ -560,7 +693,7 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
     float acc[C::TM][4];
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-    mm_tile<D>(Gs, Wa_s, ty, tx, acc);
+    tile_mm<D>(Gs, Wa_s, ty, tx, acc);
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) {
@@ -584,19 +717,24 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
       if constexpr (HAS_LEAF) dw_tile<D>(Ys, Gs, ty, tx, dwt);
 #pragma unroll
       for (int i = 0; i < C::TM; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-      mm_tile<D>(Gs, Wt_s, ty, tx, acc);
+      tile_mm<D>(Gs, Wt_s, ty, tx, acc);
       __syncthreads();
 #pragma unroll
       for (int i = 0; i < C::TM; ++i)
         st4(&Gs[(ty * C::TM + i) * C::LD + tx * 4], make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
       __syncthreads();
-      tile_rows_to_pairs<D>(Gs, a.du, row0, L.rows, L.rpp, tid);
+      tile_rows_to_pairs<D>(Gs, a.du, row0, L.rows, L.rpp_magic, tid);
     }
     // ---- neighbour phase: warp per row ----
     for (int r = warp; r < C::R; r += C::NW) {
       const long row = row0 + r;
       if (row >= L.rows) break;
       const long e = L.ent[row];
+      if (leaf && a.GSe != nullptr) {
+        // entity mode: the leaf scatter and the softmax gradient are linear in gsu and depend on the entity only
+        if (g == 0) red_add4(a.GSe + e * D + c * 4, ld4(&Gs[r * C::LD + c * 4]));
+        continue;
+      }
       const Att at = attend(a.adj + e * 2 * K, K, s_s, lane);
       pw_w[lane] = at.p0;
       pw_w[lane + 32] = at.p1;
@@ -646,7 +784,92 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
 template <int D, bool HAS_LEAF>
 constexpr size_t agg_bwd_smem(int n_rel) {
   return sizeof(float) *
-         ((HAS_LEAF ? 2 : 1) * D * D + 2 * TC<D>::R * TC<D>::LD + 3 * TC<D>::NW * MAX_K + 2 * n_rel + 2 * D);
+         ((HAS_LEAF ? 2 : 1) * TC<D>::WSZ + 2 * TC<D>::R * TC<D>::LD + 3 * TC<D>::NW * MAX_K + 2 * n_rel + 2 * D);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// entity mode of the leaf level.  S_e = sum_k p_k(e) E[adj[e][k]] depends on the depth-(L-1) node's ENTITY only
+// (attention is relation-only), and a batch re-uses the same depth-(L-1) entities many times
+// (2-150x at C2..C4), so the K-row gather, its scatter-add and the softmax gradient run once per DISTINCT entity
+// marked in `stamp` (set by the expansion kernel) instead of once per (pair, node):
+//   fwd:  Se[e] = sum_k p_k E[n_k]
+//   bwd:  g = GSe[e] (sum of gsu over the nodes holding e);  dE[n_k] += p_k g;  dp_k = g . E[n_k];
+//         dlogit_k = p_k (dp_k - sum_j p_j dp_j);  ds[rel_k] += dlogit_k
+// One warp per entity, grid-stride.
+// ---------------------------------------------------------------------------------------------------------
+struct LeafEntArgs {
+  const int32_t* stamp; // [n_entity] != 0: entity occurs at depth L-1 in this batch
+  const int32_t* adj;
+  const float* s;       // [n_rel] relation scores of aggregator 0
+  ETab E;
+  float* Se;            // [n_entity, D]
+  float* GSe;           // [n_entity, D]
+  GTab dE;
+  float* ds;            // [n_rel]
+  int n_entity, K, n_rel;
+};
+constexpr int LEAF_NT = 256, LEAF_NW = LEAF_NT / 32;
+inline size_t leaf_entity_smem(int n_rel) { return sizeof(float) * (3 * LEAF_NW * MAX_K + 2 * n_rel); }
+
+template <int D, bool BWD>
+__global__ void __launch_bounds__(LEAF_NT) leaf_entity_kernel(LeafEntArgs a) {
+  constexpr int LPR = D / 4, G = 32 / LPR;
+  extern __shared__ __align__(16) float smem[];
+  float* pw = smem;                                        // [NW][MAX_K]
+  float* dpw = pw + LEAF_NW * MAX_K;                       // [NW][MAX_K]
+  int* idw = reinterpret_cast<int*>(dpw + LEAF_NW * MAX_K);
+  float* s_s = reinterpret_cast<float*>(idw + LEAF_NW * MAX_K);
+  float* ds_s = s_s + a.n_rel;
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32, g = lane / LPR, c = lane % LPR;
+  for (int i = tid; i < a.n_rel; i += LEAF_NT) { s_s[i] = a.s[i]; ds_s[i] = 0.f; }
+  __syncthreads();
+  float* pw_w = pw + warp * MAX_K;
+  float* dpw_w = dpw + warp * MAX_K;
+  int* idw_w = idw + warp * MAX_K;
+  const int K = a.K;
+  for (long e = (long)blockIdx.x * LEAF_NW + warp; e < a.n_entity; e += (long)gridDim.x * LEAF_NW) {
+    if (a.stamp[e] == 0) continue;
+    const Att at = attend(a.adj + e * 2 * K, K, s_s, lane);
+    pw_w[lane] = at.p0;
+    pw_w[lane + 32] = at.p1;
+    idw_w[lane] = at.id0;
+    idw_w[lane + 32] = at.id1;
+    __syncwarp();
+    if (!BWD) {
+      float4 acc = f4zero();
+#pragma unroll 4
+      for (int k = g; k < K; k += G) acc = f4fma(pw_w[k], ldg4(erow(a.E, idw_w[k], D) + c * 4), acc);
+      acc = cross_group_sum4<LPR>(acc);
+      if (g == 0) st4(a.Se + e * D + c * 4, acc);
+    } else {
+      const float4 gr = ld4(a.GSe + e * D + c * 4);
+#pragma unroll 4
+      for (int k0 = 0; k0 < K; k0 += G) {
+        const int k = k0 + g;
+        const bool valid = k < K;
+        float part = 0.f;
+        if (valid) {
+          const long n = idw_w[k];
+          part = f4dot(gr, ldg4(erow(a.E, n, D) + c * 4));
+          red_add4(grow_of(a.dE, n, D) + c * 4, f4scale(gr, pw_w[k]));
+        }
+        part = group_sum<LPR>(part);
+        if (valid && c == 0) dpw_w[k] = part;
+      }
+      __syncwarp();
+      const float dp0 = lane < K ? dpw_w[lane] : 0.f;
+      const float dp1 = lane + 32 < K ? dpw_w[lane + 32] : 0.f;
+      const float dot = warp_sum(at.p0 * dp0 + at.p1 * dp1);
+      if (lane < K) atomicAdd(&ds_s[at.rel0], at.p0 * (dp0 - dot));
+      if (lane + 32 < K) atomicAdd(&ds_s[at.rel1], at.p1 * (dp1 - dot));
+    }
+    __syncwarp();
+  }
+  if (BWD) {
+    __syncthreads();
+    for (int i = tid; i < a.n_rel; i += LEAF_NT)
+      if (ds_s[i] != 0.f) atomicAdd(a.ds + i, ds_s[i]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -676,9 +899,9 @@ __global__ void __launch_bounds__(TC<D>::NT) dw_kernel(DwArgs a) {
   const long lda = a.lda[grp];
   const bool do_bias = (grp == 0 && a.db != nullptr);
   if (tid < D) red[tid] = 0.f;
-  float dw[C::TMW][4];
+  float dw[C::DWN][4];
 #pragma unroll
-  for (int i = 0; i < C::TMW; ++i) dw[i][0] = dw[i][1] = dw[i][2] = dw[i][3] = 0.f;
+  for (int i = 0; i < C::DWN; ++i) dw[i][0] = dw[i][1] = dw[i][2] = dw[i][3] = 0.f;
   float4 bpart = f4zero();
   __syncthreads();
   const long ntiles = (a.rows + C::R - 1) / C::R;

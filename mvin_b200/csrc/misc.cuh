@@ -17,13 +17,16 @@ __global__ void pack_adj_kernel(const int64_t* __restrict__ adjE, const int64_t*
 }
 
 // ---- get_neighbors (model.py:243-256): one level of expansion, child k of node j at j*K+k -------------
+// `stamp` (optional): mark the produced ids (entity mode of the leaf level, level.cuh)
 __global__ void expand_kernel(const int32_t* __restrict__ ent, const int32_t* __restrict__ adj, long rows, int K,
-                              int32_t* __restrict__ out) {
+                              int32_t* __restrict__ out, int32_t* __restrict__ stamp) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * K) return;
   const long j = i / K;
   const int k = (int)(i % K);
-  out[i] = __ldg(adj + (long)ent[j] * 2 * K + k);
+  const int32_t id = __ldg(adj + (long)ent[j] * 2 * K + k);
+  out[i] = id;
+  if (stamp) stamp[id] = 1;
 }
 
 __global__ void expand_i64_kernel(const int64_t* __restrict__ ent, const int32_t* __restrict__ adj, long rows,
@@ -45,14 +48,14 @@ __global__ void copy_i64_kernel(const int64_t* __restrict__ src, long n, int64_t
 // ---- seeds: ent[0] = item (int32) and Vbuf = E[item]  (model.py:199) -----------------------------------
 template <int D>
 __global__ void prep_items_kernel(const int64_t* __restrict__ item, ETab E, int B,
-                                  int32_t* __restrict__ ent0, float* __restrict__ Vbuf) {
+                                  int32_t* __restrict__ ent0, float* __restrict__ Vbuf, int32_t* __restrict__ stamp) {
   constexpr int LPR = D / 4;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long)B * LPR) return;
   const long b = i / LPR;
   const int c = (int)(i % LPR);
   const long e = item[b];
-  if (c == 0) ent0[b] = (int32_t)e;
+  if (c == 0) { ent0[b] = (int32_t)e; if (stamp) stamp[e] = 1; }
   st4(Vbuf + b * D + c * 4, ldg4(erow(E, e, D) + c * 4));
 }
 

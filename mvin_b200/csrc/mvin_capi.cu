@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -70,7 +71,9 @@ struct Layout {
   // backward
   size_t DC[MAX_L + 1][MAX_L], DS[MAX_L][MAX_L];
   size_t du, ditem, dO, dv, wT;           // wT: [H + H + 1][D][D] transposed weights
-  size_t zero_begin, dQ, ds, cnt, acc, zero_end;   // region cleared at the start of every backward
+  size_t zero_begin, dQ, ds, cnt, acc, GSe, zero_end;   // region cleared at the start of every backward
+  size_t stamp, Se;                       // entity mode of the leaf level (stamp is cleared by every forward)
+  bool entity_leaf;
   size_t total;
   long rows[MAX_L + 1];
 };
@@ -99,6 +102,7 @@ struct mvin_handle_s {
   void** d_shard_tab = nullptr;    // device array [2][MAX_SHARDS] of shard base pointers (allocated in mvin_create)
   int global_batch = 0;            // 0: the batch of the call
   float dense_l2_scale = 1.f;
+  int entity_leaf_mode = -1;       // -1 auto, 0 off, 1 on (env MVIN_B200_ENTITY_LEAF, read in mvin_create)
   bool prof_on = false;
   struct ProfRec { const char* name; cudaEvent_t ev; };
   std::vector<ProfRec> prof;
@@ -116,12 +120,26 @@ void prof_mark(mvin_handle_t h, cudaStream_t st, const char* name) {
   h->prof.push_back({name, ev});
 }
 
+// M of fastdiv (level.cuh): floor(2^64 / d) + 1, 0 for d = 1
+inline unsigned long long div_magic(long d) { return d <= 1 ? 0ull : ~0ull / (unsigned long long)d + 1ull; }
+
 inline bool has_agg(int H, int i, int h) { return i < H && h < H - i; }          // aggregator step (i, h) exists
 inline bool has_V(int H, int j, int h) { return j == 0 ? h < H : h <= H - j; }   // buffer V[j][h] exists
 
-Layout make_layout(const mvin_config_t& c, long B) {
+// Entity mode of the leaf level (level.cuh, leaf_entity_kernel) pays off when the depth-(L-1) nodes of a batch
+// re-use entities: enabled when there are at least n_entity / 4 of them and the two per-entity buffers are small.
+bool use_entity_leaf(const mvin_config_t& c, long B, int n_shards, int mode) {
+  if (n_shards != 1 || mode == 0) return false;
+  if (mode == 1) return true;
+  long rows = B;
+  for (int h = 1; h < c.h_hop; ++h) rows *= c.neighbor_sample_size;
+  return n_shards == 1 && rows * 4 >= (long)c.n_entity && (long)c.n_entity * c.dim * 8 <= (2L << 30);
+}
+
+Layout make_layout(const mvin_config_t& c, long B, bool entity_leaf) {
   Layout L;
   memset(&L, 0, sizeof(L));
+  L.entity_leaf = entity_leaf;
   const long D = c.dim, K = c.neighbor_sample_size, H = c.h_hop, p = c.p_hop, m = c.n_memory, nr = c.n_relation;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -164,7 +182,12 @@ Layout make_layout(const mvin_config_t& c, long B) {
   L.ds = take(f * H * nr);
   L.cnt = take(f * nr);
   L.acc = take(f * 8);
+  if (entity_leaf) L.GSe = take(f * (size_t)c.n_entity * D);
   L.zero_end = off;
+  if (entity_leaf) {
+    L.stamp = take(sizeof(int32_t) * (size_t)c.n_entity);
+    L.Se = take(f * (size_t)c.n_entity * D);
+  }
   L.total = off;
   return L;
 }
@@ -251,22 +274,25 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
   using C = TC<D>;
   const mvin_config_t& c = h->cfg;
   const int K = c.neighbor_sample_size, H = c.h_hop, p = c.p_hop, m = c.n_memory, nr = c.n_relation;
-  const Layout L = make_layout(c, B);
+  const Layout L = make_layout(c, B, use_entity_leaf(c, B, h->n_shards, h->entity_leaf_mode));
   const mvin_params_t& P = h->P;
   int rc;
   prof_mark(h, st, nullptr);
 
   // seeds + integer expansion (model.py:243-256); level L ids are never materialised
+  int32_t* stamp = L.entity_leaf ? at<int32_t>(ws, L.stamp) : nullptr;
+  if (stamp) CUDA_TRY(cudaMemsetAsync(stamp, 0, sizeof(int32_t) * (size_t)c.n_entity, st));
   {
     const long n = (long)B * C::LPR;
     prep_items_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(item, h->etab, B, at<int32_t>(ws, L.ent[0]),
-                                                                      at<float>(ws, L.Vbuf));
+                                                                      at<float>(ws, L.Vbuf), H == 1 ? stamp : nullptr);
     LAUNCH_CHECK(h, "prep_items");
   }
   for (int lv = 0; lv + 1 < H; ++lv) {
     const long n = L.rows[lv] * K;
     expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(at<int32_t>(ws, L.ent[lv]), h->adj, L.rows[lv], K,
-                                                               at<int32_t>(ws, L.ent[lv + 1]));
+                                                               at<int32_t>(ws, L.ent[lv + 1]),
+                                                               lv + 1 == H - 1 ? stamp : nullptr);
     LAUNCH_CHECK(h, "expand");
   }
   // Q[b, r, :] = RK[r]^T v_b      (model.py:211-220 refactored)
@@ -307,6 +333,19 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
                                                                at<float>(ws, L.s));
     LAUNCH_CHECK(h, "rel_scores");
   }
+  // entity mode: S_e for every distinct depth-(L-1) entity of the batch
+  if (L.entity_leaf) {
+    LeafEntArgs a;
+    memset(&a, 0, sizeof(a));
+    a.stamp = stamp; a.adj = h->adj; a.s = at<float>(ws, L.s); a.E = h->etab; a.Se = at<float>(ws, L.Se);
+    a.n_entity = c.n_entity; a.K = K; a.n_rel = nr;
+    const size_t sm = leaf_entity_smem(nr);
+    if ((rc = set_smem(leaf_entity_kernel<D, false>, sm))) return rc;
+    const long want = ((long)c.n_entity + LEAF_NW - 1) / LEAF_NW;
+    const long cap = (long)h->sm_count * 8;
+    leaf_entity_kernel<D, false><<<(unsigned)(want < cap ? want : cap), LEAF_NT, sm, st>>>(a);
+    LAUNCH_CHECK(h, "leaf_entity_fwd");
+  }
   // user-oriented transform of levels 0..L-1, one launch   (model.py:270-283)
   {
     const size_t sm = transform_fwd_smem<D>();
@@ -319,7 +358,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
       t.ent = at<int32_t>(ws, L.ent[lv]);
       t.W = P.transfer_w + (long)lv * D * D; t.b = P.transfer_b + (long)lv * D;
       t.T = at<float>(ws, L.V[0][lv]);
-      t.rows = rows[lv] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B);
+      t.rows = rows[lv] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
     }
     a.nlev = H; a.E = h->etab; a.u = at<float>(ws, L.u);
     const int grid = partition_grid(rows, H, h->sm_count * ctas_per_sm(sm, C::NT), a.cta_end);
@@ -344,7 +383,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
         t.ent = at<int32_t>(ws, L.ent[lv]);
         t.self = at<float>(ws, L.V[i][lv]);
         t.Y = at<float>(ws, L.Y[i][lv]); t.V = at<float>(ws, L.V[i + 1][lv]);
-        t.rows = rows[q] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B);
+        t.rows = rows[q] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
         t.leaf = (i == 0 && lv == H - 1);
         if (t.leaf) t.SU = at<float>(ws, L.SU); else t.child = at<float>(ws, L.V[i][lv + 1]);
       }
@@ -353,6 +392,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
       a.K = K; a.n_rel = nr;
       if (i == 0) {
         a.E = h->etab; a.u = at<float>(ws, L.u);
+        a.Se = L.entity_leaf ? at<float>(ws, L.Se) : nullptr;
         a.Wt = P.transfer_w + (long)H * D * D; a.bt = P.transfer_b + (long)H * D;
         const int grid = partition_grid(rows, nlev, h->sm_count * ctas_per_sm(sm_leaf, C::NT), a.cta_end);
         agg_fwd_kernel<D, true><<<grid, C::NT, sm_leaf, st>>>(a);
@@ -405,7 +445,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
   using C = TC<D>;
   const mvin_config_t& c = h->cfg;
   const int K = c.neighbor_sample_size, H = c.h_hop, p = c.p_hop, m = c.n_memory, nr = c.n_relation;
-  const Layout L = make_layout(c, B);
+  const Layout L = make_layout(c, B, use_entity_leaf(c, B, h->n_shards, h->entity_leaf_mode));
   const mvin_params_t& P = h->P;
   const mvin_params_t& G = h->G;
   const float l2w = c.l2_weight, l2a = c.l2_agg_weight;
@@ -504,7 +544,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
         t.g1 = at<float>(ws, L.DC[i + 1][lv]);
         t.g2 = has_agg(H, i + 1, lv) ? at<float>(ws, L.DS[i + 1][lv]) : nullptr;
         t.dself = at<float>(ws, L.DS[i][lv]);
-        t.rows = rows[q] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B);
+        t.rows = rows[q] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
         t.leaf = (i == 0 && lv == H - 1);
         if (t.leaf) {
           t.SU = at<float>(ws, L.SU);
@@ -522,6 +562,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
         a.E = h->etab; a.WtT = wT + (long)(H + H) * D * D;
         a.dWt = G.transfer_w + (long)H * D * D; a.dbt = G.transfer_b + (long)H * D;
         a.dE = h->gtab; a.du = du;
+        a.GSe = L.entity_leaf ? at<float>(ws, L.GSe) : nullptr;
         const int grid = partition_grid(rows, nlev, h->sm_count * ctas_per_sm(sm_leaf, C::NT), a.cta_end);
         agg_bwd_kernel<D, true><<<grid, C::NT, sm_leaf, st>>>(a);
       } else {
@@ -530,6 +571,19 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
       }
       LAUNCH_CHECK(h, names[i]);
     }
+  }
+  if (L.entity_leaf) {
+    LeafEntArgs a;
+    memset(&a, 0, sizeof(a));
+    a.stamp = at<int32_t>(ws, L.stamp); a.adj = h->adj; a.s = at<float>(ws, L.s); a.E = h->etab;
+    a.GSe = at<float>(ws, L.GSe); a.dE = h->gtab; a.ds = at<float>(ws, L.ds);
+    a.n_entity = c.n_entity; a.K = K; a.n_rel = nr;
+    const size_t sm = leaf_entity_smem(nr);
+    if ((rc = set_smem(leaf_entity_kernel<D, true>, sm))) return rc;
+    const long want = ((long)c.n_entity + LEAF_NW - 1) / LEAF_NW;
+    const long cap = (long)h->sm_count * 8;
+    leaf_entity_kernel<D, true><<<(unsigned)(want < cap ? want : cap), LEAF_NT, sm, st>>>(a);
+    LAUNCH_CHECK(h, "leaf_entity_bwd");
   }
   rel_scores_bwd_kernel<<<H, 128, 0, st>>>(P.relation_emb, P.agg_urh_w, at<float>(ws, L.ds), nr, D, G.relation_emb,
                                            G.agg_urh_w);
@@ -548,7 +602,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
       t.W = wT + (long)(H + lv) * D * D;
       t.g1 = at<float>(ws, L.DC[0][lv]); t.g2 = at<float>(ws, L.DS[0][lv]);
       t.dW = G.transfer_w + (long)lv * D * D; t.db = G.transfer_b + (long)lv * D;
-      t.rows = rows[q] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B);
+      t.rows = rows[q] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
     }
     a.nlev = H; a.E = h->etab; a.u = at<float>(ws, L.u); a.dE = h->gtab; a.du = du;
     const int grid = partition_grid(rows, H, h->sm_count * ctas_per_sm(sm, C::NT), a.cta_end);
@@ -676,6 +730,7 @@ int mvin_create(const mvin_config_t* cfg, mvin_handle_t* out) {
   h->device = dev;
   h->sm_count = prop.multiProcessorCount;
   h->n_local_rows = cfg->n_entity;
+  if (const char* ev = getenv("MVIN_B200_ENTITY_LEAF")) h->entity_leaf_mode = atoi(ev) != 0 ? 1 : 0;
   if (cudaMalloc(&h->d_shard_tab, sizeof(void*) * 2 * MAX_SHARDS) != cudaSuccess) {
     delete h;
     return fail(MVIN_ERR_CUDA, "cudaMalloc(shard table): %s", cudaGetErrorString(cudaGetLastError()));
@@ -792,7 +847,7 @@ int mvin_set_batch_scale(mvin_handle_t h, int32_t global_batch, float dense_l2_s
 
 size_t mvin_workspace_bytes(mvin_handle_t h, int32_t B) {
   if (!h || B < 1) return 0;
-  return make_layout(h->cfg, B).total;
+  return make_layout(h->cfg, B, use_entity_leaf(h->cfg, B, h->n_shards, h->entity_leaf_mode)).total;
 }
 
 int mvin_get_neighbors(mvin_handle_t h, const int64_t* item_indices, int32_t B, int32_t n_levels,
@@ -834,7 +889,7 @@ int mvin_importance(mvin_handle_t h, float* imp0, float* imp1, void* workspace, 
   if (!h || !imp0 || !workspace) return fail(MVIN_ERR_INVALID, "null argument");
   if (h->fwd_workspace != workspace || h->B < 1) return fail(MVIN_ERR_STATE, "no forward pass on this workspace");
   cudaStream_t st = (cudaStream_t)stream;
-  const Layout L = make_layout(h->cfg, h->B);
+  const Layout L = make_layout(h->cfg, h->B, use_entity_leaf(h->cfg, h->B, h->n_shards, h->entity_leaf_mode));
   const int K = h->cfg.neighbor_sample_size;
   float* outs[2] = {imp0, imp1};
   for (int lv = 0; lv < 2 && lv < h->cfg.h_hop; ++lv) {

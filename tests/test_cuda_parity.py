@@ -235,3 +235,27 @@ def test_two_rank_sharded_entity_table_matches_oracle():
     for r in range(2):
         ok, bad = ret[r]
         assert ok and not bad, (r, ok, bad)
+
+
+@pytest.mark.parametrize("mode", ["0", "1"])
+@pytest.mark.parametrize("dim,K,H,p,m,B", [(32, 16, 2, 2, 32, 80), (16, 8, 1, 2, 16, 96), (64, 8, 3, 1, 16, 6)])
+def test_leaf_modes_match_oracle(monkeypatch, mode, dim, K, H, p, m, B):
+    """The leaf level has two implementations: per (pair, node) gather (mode 0, used for sharded / huge tables) and
+    per distinct entity (mode 1, leaf_entity_kernel).  Both must give the oracle's numbers; hub_frac makes the same
+    entity appear many times at depth L-1."""
+    from mvin_b200 import MVIN
+    monkeypatch.setenv("MVIN_B200_ENTITY_LEAF", mode)
+    args = make_args(dim=dim, neighbor_sample_size=K, h_hop=H, p_hop=p, n_memory=m, batch_size=B)
+    prob = make_problem(args, n_entity=350, seed=3 * dim + K, hub_frac=0.25)
+    model = MVIN(args, prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"], prob["adj_relation"])
+    model.load_named_parameters({k: v.numpy() for k, v in prob["P"].items()})
+    fd = feed_dict(model, prob)
+    out, grads = orc.loss_and_grads(prob["P"], prob["cfg"], prob["adj_entity"], prob["adj_relation"], prob["users"],
+                                    prob["items"], prob["mem_h"], prob["mem_r"], prob["mem_t"], prob["labels"])
+    assert rel_err(model.get_raw_scores(fd), out.scores.detach().numpy()) < SCORE_TOL
+    losses = model.loss_and_grads(fd)
+    assert abs(float(losses[0]) - float(out.loss.detach())) <= 1e-4 * max(1.0, abs(float(out.loss.detach())))
+    _assert_grads(model.named_gradients(), lambda k: grads[k].numpy())
+    losses2 = model.loss_and_grads(fd)                           # second step on the same workspace: buffers re-zeroed
+    assert np.allclose(losses, losses2, rtol=1e-5)
+    _assert_grads(model.named_gradients(), lambda k: grads[k].numpy())
