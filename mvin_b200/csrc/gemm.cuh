@@ -21,7 +21,8 @@ struct GemmArgs {
   const float* bias;      // [N] or nullptr; added once (k-split 0)
   int M, N, K;
   int nbatch, ksplit;
-  int reduce;             // 1: sum over the nbatch batches inside the CTA (C has no batch dimension)
+  int reduce;             // 1: sum over the nbatch batches inside the CTA (C has no batch dimension); ksplit then
+                          //    splits the BATCH range over CTAs instead of K
   int accumulate;         // 1: atomicAdd into C (required when ksplit > 1 or c_rows has duplicates)
   float alpha;
 };
@@ -38,12 +39,19 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(GemmArgs g) {
   const int tid = threadIdx.x;
   const int tx = tid % TX, ty = tid / TX;
   const int batch = g.reduce ? 0 : blockIdx.z / g.ksplit, split = blockIdx.z % g.ksplit;
-  const int nred = g.reduce ? g.nbatch : 1;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   int kchunk = (g.K + g.ksplit - 1) / g.ksplit;
   kchunk = (kchunk + BK - 1) / BK * BK;
-  const int k_begin = split * kchunk;
-  const int k_end = min(g.K, k_begin + kchunk);
+  int k_begin = split * kchunk;
+  int k_end = min(g.K, k_begin + kchunk);
+  int red_begin = 0, red_end = 1;
+  if (g.reduce) {
+    const int per = (g.nbatch + g.ksplit - 1) / g.ksplit;
+    red_begin = split * per;
+    red_end = min(g.nbatch, red_begin + per);
+    k_begin = 0;
+    k_end = g.K;
+  }
   const float* A0 = g.A + (long)batch * g.bsA;
   const float* B0 = g.B + (long)batch * g.bsB;
   const bool a_kfast = (g.sa_k == 1), b_nfast = (g.sb_n == 1);
@@ -52,7 +60,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(GemmArgs g) {
 #pragma unroll
   for (int i = 0; i < TMR; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
 
-  for (int red = 0; red < nred; ++red) {
+  for (int red = red_begin; red < red_end; ++red) {
     const float* A = A0 + (long)red * g.bsA;
     const float* B = B0 + (long)red * g.bsB;
     for (int kt = k_begin; kt < k_end; kt += BK) {

@@ -501,18 +501,27 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
   const long ntiles = (L.rows + C::R - 1) / C::R;
   for (long t = cs.local; t < ntiles; t += cs.count) {
     const long row0 = t * C::R;
-    // ---- neighbour phase: warp per row ----
-    for (int r = warp; r < C::R; r += C::NW) {
-      const long row = row0 + r;
-      if (row < L.rows && leaf && a.Se != nullptr) {
-        // entity mode: S depends on the node's entity only and was computed once per distinct entity
-        if (g == 0) {
+    const bool ent_mode = leaf && a.Se != nullptr;
+    if (ent_mode) {
+      // entity mode: S depends on the node's entity only and was computed once per distinct entity
+      // (leaf_entity_kernel); thread-mapped row loads, all TM of them in flight at once
+#pragma unroll
+      for (int i = 0; i < C::TM; ++i) {
+        const int r = ty * C::TM + i;
+        const long row = row0 + r;
+        float4 o = f4zero();
+        if (row < L.rows) {
           const long e = L.ent[row];
-          const float4 o = f4add(ldg4(a.Se + e * D + c * 4), ldg4(a.u + fastdiv(row, L.rpp_magic) * D + c * 4));
-          st4(L.SU + row * D + c * 4, o);
-          st4(&As[r * C::LD + c * 4], o);
+          o = f4add(ldg4(a.Se + e * D + tx * 4), ldg4(a.u + fastdiv(row, L.rpp_magic) * D + tx * 4));
+          st4(L.SU + row * D + tx * 4, o);
         }
-      } else if (row < L.rows) {
+        st4(&As[r * C::LD + tx * 4], o);
+      }
+    }
+    // ---- neighbour phase: warp per row ----
+    for (int r = warp; r < C::R && !ent_mode; r += C::NW) {
+      const long row = row0 + r;
+      if (row < L.rows) {
         const long e = L.ent[row];
         const Att at = attend(a.adj + e * 2 * K, K, s_s, lane);
         pw_w[lane] = at.p0;
@@ -720,21 +729,23 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
       tile_mm<D>(Gs, Wt_s, ty, tx, acc);
       __syncthreads();
 #pragma unroll
-      for (int i = 0; i < C::TM; ++i)
-        st4(&Gs[(ty * C::TM + i) * C::LD + tx * 4], make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+      for (int i = 0; i < C::TM; ++i) {
+        const float4 gsu = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        st4(&Gs[(ty * C::TM + i) * C::LD + tx * 4], gsu);
+        if (a.GSe != nullptr) {
+          // entity mode: the leaf scatter and the softmax gradient are linear in gsu and depend on the entity only
+          const long row = row0 + ty * C::TM + i;
+          if (row < L.rows) red_add4(a.GSe + (long)L.ent[row] * D + tx * 4, gsu);
+        }
+      }
       __syncthreads();
       tile_rows_to_pairs<D>(Gs, a.du, row0, L.rows, L.rpp_magic, tid);
     }
     // ---- neighbour phase: warp per row ----
-    for (int r = warp; r < C::R; r += C::NW) {
+    for (int r = warp; r < C::R && !(leaf && a.GSe != nullptr); r += C::NW) {
       const long row = row0 + r;
       if (row >= L.rows) break;
       const long e = L.ent[row];
-      if (leaf && a.GSe != nullptr) {
-        // entity mode: the leaf scatter and the softmax gradient are linear in gsu and depend on the entity only
-        if (g == 0) red_add4(a.GSe + e * D + c * 4, ld4(&Gs[r * C::LD + c * 4]));
-        continue;
-      }
       const Att at = attend(a.adj + e * 2 * K, K, s_s, lane);
       pw_w[lane] = at.p0;
       pw_w[lane + 32] = at.p1;

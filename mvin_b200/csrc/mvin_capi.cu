@@ -102,6 +102,10 @@ struct mvin_handle_s {
   void** d_shard_tab = nullptr;    // device array [2][MAX_SHARDS] of shard base pointers (allocated in mvin_create)
   int global_batch = 0;            // 0: the batch of the call
   float dense_l2_scale = 1.f;
+  // fork/join helpers: independent kernels of a step run on two internal side streams (disabled while profiling)
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
+  bool use_streams = true;
   int entity_leaf_mode = -1;       // -1 auto, 0 off, 1 on (env MVIN_B200_ENTITY_LEAF, read in mvin_create)
   bool prof_on = false;
   struct ProfRec { const char* name; cudaEvent_t ev; };
@@ -122,6 +126,25 @@ void prof_mark(mvin_handle_t h, cudaStream_t st, const char* name) {
 
 // M of fastdiv (level.cuh): floor(2^64 / d) + 1, 0 for d = 1
 inline unsigned long long div_magic(long d) { return d <= 1 ? 0ull : ~0ull / (unsigned long long)d + 1ull; }
+
+// Fork/join of the launch stream onto the handle's side streams.  Plain stream/event calls, so a step can also be
+// stream-captured into a CUDA graph with the side work as parallel branches.
+struct Par {
+  mvin_handle_t h;
+  cudaStream_t main;
+  bool on;
+  cudaStream_t s(int i) const { return on ? h->side[i] : main; }
+  void fork(int i) const {
+    if (!on) return;
+    cudaEventRecord(h->ev_fork[i], main);
+    cudaStreamWaitEvent(h->side[i], h->ev_fork[i], 0);
+  }
+  void join(int i) const {
+    if (!on) return;
+    cudaEventRecord(h->ev_join[i], h->side[i]);
+    cudaStreamWaitEvent(main, h->ev_join[i], 0);
+  }
+};
 
 inline bool has_agg(int H, int i, int h) { return i < H && h < H - i; }          // aggregator step (i, h) exists
 inline bool has_V(int H, int j, int h) { return j == 0 ? h < H : h <= H - j; }   // buffer V[j][h] exists
@@ -175,10 +198,10 @@ Layout make_layout(const mvin_config_t& c, long B, bool entity_leaf) {
   L.du = take(f * B * D);
   L.ditem = take(f * B * D);
   L.dO = take(f * B * (p + 1) * D);
-  L.dv = take(f * B * D);
   L.wT = take(f * (2 * H + 1) * D * D);
   L.zero_begin = off;
   L.dQ = take(f * B * nr * D);
+  L.dv = take(f * B * D);
   L.ds = take(f * H * nr);
   L.cnt = take(f * nr);
   L.acc = take(f * 8);
@@ -288,12 +311,39 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
                                                                       at<float>(ws, L.Vbuf), H == 1 ? stamp : nullptr);
     LAUNCH_CHECK(h, "prep_items");
   }
-  for (int lv = 0; lv + 1 < H; ++lv) {
-    const long n = L.rows[lv] * K;
-    expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(at<int32_t>(ws, L.ent[lv]), h->adj, L.rows[lv], K,
-                                                               at<int32_t>(ws, L.ent[lv + 1]),
-                                                               lv + 1 == H - 1 ? stamp : nullptr);
-    LAUNCH_CHECK(h, "expand");
+  // side stream: integer expansion, relation scores and the per-entity leaf aggregate are independent of the
+  // ripple chain (Q -> ripple attention -> user_o) that runs on the launch stream meanwhile
+  const Par par{h, st, h->use_streams && !h->prof_on};
+  par.fork(0);
+  {
+    cudaStream_t st = par.s(0);
+    for (int lv = 0; lv + 1 < H; ++lv) {
+      const long n = L.rows[lv] * K;
+      expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(at<int32_t>(ws, L.ent[lv]), h->adj, L.rows[lv], K,
+                                                                 at<int32_t>(ws, L.ent[lv + 1]),
+                                                                 lv + 1 == H - 1 ? stamp : nullptr);
+      LAUNCH_CHECK(h, "expand");
+    }
+    // relation scores of every aggregator
+    {
+      const int warps = H * nr;
+      rel_scores_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(P.relation_emb, P.agg_urh_w, nr, D, H,
+                                                                 at<float>(ws, L.s));
+      LAUNCH_CHECK(h, "rel_scores");
+    }
+    // entity mode: S_e for every distinct depth-(L-1) entity of the batch
+    if (L.entity_leaf) {
+      LeafEntArgs a;
+      memset(&a, 0, sizeof(a));
+      a.stamp = stamp; a.adj = h->adj; a.s = at<float>(ws, L.s); a.E = h->etab; a.Se = at<float>(ws, L.Se);
+      a.n_entity = c.n_entity; a.K = K; a.n_rel = nr;
+      const size_t sm = leaf_entity_smem(nr);
+      if ((rc = set_smem(leaf_entity_kernel<D, false>, sm))) return rc;
+      const long want = ((long)c.n_entity + LEAF_NW - 1) / LEAF_NW;
+      const long cap = (long)h->sm_count * 8;
+      leaf_entity_kernel<D, false><<<(unsigned)(want < cap ? want : cap), LEAF_NT, sm, st>>>(a);
+      LAUNCH_CHECK(h, "leaf_entity_fwd");
+    }
   }
   // Q[b, r, :] = RK[r]^T v_b      (model.py:211-220 refactored)
   if (p > 0) {
@@ -326,26 +376,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
     g.M = B; g.N = D; g.K = (p + 1) * D;
     if ((rc = run_gemm(h, st, g, "gemm_user"))) return rc;
   }
-  // relation scores of every aggregator
-  {
-    const int warps = H * nr;
-    rel_scores_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(P.relation_emb, P.agg_urh_w, nr, D, H,
-                                                               at<float>(ws, L.s));
-    LAUNCH_CHECK(h, "rel_scores");
-  }
-  // entity mode: S_e for every distinct depth-(L-1) entity of the batch
-  if (L.entity_leaf) {
-    LeafEntArgs a;
-    memset(&a, 0, sizeof(a));
-    a.stamp = stamp; a.adj = h->adj; a.s = at<float>(ws, L.s); a.E = h->etab; a.Se = at<float>(ws, L.Se);
-    a.n_entity = c.n_entity; a.K = K; a.n_rel = nr;
-    const size_t sm = leaf_entity_smem(nr);
-    if ((rc = set_smem(leaf_entity_kernel<D, false>, sm))) return rc;
-    const long want = ((long)c.n_entity + LEAF_NW - 1) / LEAF_NW;
-    const long cap = (long)h->sm_count * 8;
-    leaf_entity_kernel<D, false><<<(unsigned)(want < cap ? want : cap), LEAF_NT, sm, st>>>(a);
-    LAUNCH_CHECK(h, "leaf_entity_fwd");
-  }
+  par.join(0);
   // user-oriented transform of levels 0..L-1, one launch   (model.py:270-283)
   {
     const size_t sm = transform_fwd_smem<D>();
@@ -451,9 +482,15 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
   const float l2w = c.l2_weight, l2a = c.l2_agg_weight;
   int rc;
   float* acc = at<float>(ws, L.acc);
+  float* wT = at<float>(ws, L.wT);
   prof_mark(h, st, nullptr);
 
   CUDA_TRY(cudaMemsetAsync(at<char>(ws, L.zero_begin), 0, L.zero_end - L.zero_begin, st));
+  // side stream 0: gradient-buffer initialisation that does not depend on the batch's activations
+  const Par par{h, st, h->use_streams && !h->prof_on};
+  par.fork(0);
+  {
+  cudaStream_t st = par.s(0);
   // sharded mode: peers scatter into this rank's shard, so the CALLER zeroes it (and synchronises the ranks)
   if (h->n_shards == 1) CUDA_TRY(cudaMemsetAsync(G.entity_emb, 0, sizeof(float) * (size_t)c.n_entity * D, st));
   prof_mark(h, st, "memset");
@@ -492,7 +529,6 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     LAUNCH_CHECK(h, "l2_dense");
   }
   // transposed weights: wT[i] = W_a[i]^T (i < H), wT[H + e] = W_t[e]^T (e <= H)
-  float* wT = at<float>(ws, L.wT);
   transpose_kernel<<<dim3(2 * H + 1), 256, 0, st>>>(P.agg_w, P.transfer_w, H, D, wT);
   LAUNCH_CHECK(h, "transpose");
   // ripple-memory relation histogram (feeds the un-normalised L2 over gathered RK matrices, model.py:386)
@@ -500,6 +536,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     const long n = (long)p * B * m;
     hist_r_kernel<<<h->sm_count * 4, 256, sizeof(float) * nr, st>>>(h->mem_r, n, nr, at<float>(ws, L.cnt));
     LAUNCH_CHECK(h, "hist_r");
+  }
   }
 
   float* du = at<float>(ws, L.du);
@@ -511,13 +548,15 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
                                                                     1.f / (float)(h->global_batch > 0 ? h->global_batch : B), ditem, du, acc);
     LAUNCH_CHECK(h, "loss_bwd");
   }
+  par.join(0);
   // mix backward: dW_mix[j] = V[j][0]^T ditem (grouped), DC[j][0] = ditem . W_mix[j]^T (batched)
   {
     DwArgs a;
     memset(&a, 0, sizeof(a));
     for (int j = 0; j <= H; ++j) { a.A[j] = at<float>(ws, L.V[j][0]); a.lda[j] = D; a.dW[j] = G.mix_w + (long)j * D * D; }
     a.G = ditem; a.db = G.mix_b; a.rows = B;
-    if ((rc = launch_dw<D>(h, st, a, H + 1, "dw_mix"))) return rc;
+    par.fork(1);                                   // side stream 1: weight gradient of the mix layer
+    if ((rc = launch_dw<D>(h, par.s(1), a, H + 1, "dw_mix"))) return rc;
     GemmArgs g = gemm_args();
     g.A = ditem; g.sa_m = D; g.sa_k = 1; g.bsA = 0;
     g.B = P.mix_w; g.sb_k = 1; g.sb_n = D; g.bsB = (long)D * D;   // W_mix[jD + n][k] -> transposed use
@@ -572,6 +611,11 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
       LAUNCH_CHECK(h, names[i]);
     }
   }
+  // side stream 0: per-entity leaf backward + relation-score gradients, while the user-oriented transform backward
+  // runs on the launch stream (both only add into dE)
+  par.fork(0);
+  {
+  cudaStream_t st = par.s(0);
   if (L.entity_leaf) {
     LeafEntArgs a;
     memset(&a, 0, sizeof(a));
@@ -588,6 +632,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
   rel_scores_bwd_kernel<<<H, 128, 0, st>>>(P.relation_emb, P.agg_urh_w, at<float>(ws, L.ds), nr, D, G.relation_emb,
                                            G.agg_urh_w);
   LAUNCH_CHECK(h, "rel_scores_bwd");
+  }
   // user-oriented transform backward, levels 0..L-1, one launch
   {
     const size_t sm = transform_bwd_smem<D>();
@@ -617,7 +662,8 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
       a.A[s] = at<float>(ws, L.O) + (long)s * D; a.lda[s] = (long)(p + 1) * D; a.dW[s] = G.user_mlp_w + (long)s * D * D;
     }
     a.G = du; a.db = G.user_mlp_b; a.rows = B;
-    if ((rc = launch_dw<D>(h, st, a, p + 1, "dw_user"))) return rc;
+    par.fork(1);                                   // side stream 1: weight gradient of the user MLP
+    if ((rc = launch_dw<D>(h, par.s(1), a, p + 1, "dw_user"))) return rc;
     GemmArgs g = gemm_args();
     g.A = du; g.sa_m = D; g.sa_k = 1;
     g.B = P.user_mlp_w; g.sb_k = 1; g.sb_n = D;
@@ -640,7 +686,10 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     LAUNCH_CHECK(h, "ripple_bwd");
   }
   if (p > 0) {
-    rk_l2_kernel<<<nr, 256, 0, st>>>(P.relation_kge, at<float>(ws, L.cnt), D * D, 2.f * l2w, G.relation_kge, acc + 1);
+    // three independent consumers of dQ / cnt: RK L2 term (side 1), dRK (side 0), dE[item] (launch stream)
+    par.fork(0);
+    par.fork(1);
+    rk_l2_kernel<<<nr, 256, 0, par.s(1)>>>(P.relation_kge, at<float>(ws, L.cnt), D * D, 2.f * l2w, G.relation_kge, acc + 1);
     LAUNCH_CHECK(h, "rk_l2");
     // dRK[r][i][j] += sum_b v[b][i] dQ[b][r][j]
     GemmArgs g = gemm_args();
@@ -648,19 +697,22 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     g.B = at<float>(ws, L.dQ); g.sb_k = (long)nr * D; g.sb_n = 1; g.bsB = D;
     g.C = G.relation_kge; g.ldc = D; g.bsC = (long)D * D;
     g.M = D; g.N = D; g.K = B; g.nbatch = nr; g.ksplit = pick_ksplit(B); g.accumulate = 1;
-    if ((rc = run_gemm(h, st, g, "gemm_drk"))) return rc;
+    if ((rc = run_gemm(h, par.s(0), g, "gemm_drk"))) return rc;
     // dv[b][i] = sum_r sum_j dQ[b][r][j] RK[r][i][j]  (reduced over r inside the CTA);  dE[item_b] += dv[b]
     GemmArgs g2 = gemm_args();
     g2.A = at<float>(ws, L.dQ); g2.sa_m = (long)nr * D; g2.sa_k = 1; g2.bsA = D;
     g2.B = P.relation_kge; g2.sb_k = 1; g2.sb_n = D; g2.bsB = (long)D * D;
     g2.C = at<float>(ws, L.dv); g2.ldc = D; g2.bsC = 0;
     g2.M = B; g2.N = D; g2.K = D; g2.nbatch = nr; g2.reduce = 1;
+    g2.ksplit = nr >= 8 ? 4 : 1; g2.accumulate = g2.ksplit > 1;      // dv lives in the zeroed region
     if ((rc = run_gemm(h, st, g2, "gemm_dv"))) return rc;
     const long n = (long)B * C::LPR;
     scatter_rows_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(at<float>(ws, L.dv), at<int32_t>(ws, L.ent[0]), B,
                                                                         h->gtab);
     LAUNCH_CHECK(h, "scatter_dv");
   }
+  par.join(0);
+  par.join(1);
   finalize_loss_kernel<<<1, 32, 0, st>>>(acc, l2w, l2a, losses_out);
   LAUNCH_CHECK(h, "finalize_loss");
   return MVIN_OK;
@@ -730,6 +782,14 @@ int mvin_create(const mvin_config_t* cfg, mvin_handle_t* out) {
   h->device = dev;
   h->sm_count = prop.multiProcessorCount;
   h->n_local_rows = cfg->n_entity;
+  if (const char* ev = getenv("MVIN_B200_STREAMS")) h->use_streams = atoi(ev) != 0;
+  for (int i = 0; i < 2; ++i) {
+    if (cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming) != cudaSuccess) {
+      return fail(MVIN_ERR_CUDA, "stream / event creation: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+  }
   if (const char* ev = getenv("MVIN_B200_ENTITY_LEAF")) h->entity_leaf_mode = atoi(ev) != 0 ? 1 : 0;
   if (cudaMalloc(&h->d_shard_tab, sizeof(void*) * 2 * MAX_SHARDS) != cudaSuccess) {
     delete h;
@@ -741,6 +801,11 @@ int mvin_create(const mvin_config_t* cfg, mvin_handle_t* out) {
 
 int mvin_destroy(mvin_handle_t h) {
   if (h && h->d_shard_tab) cudaFree(h->d_shard_tab);
+  for (int i = 0; h && i < 2; ++i) {
+    if (h->side[i]) cudaStreamDestroy(h->side[i]);
+    if (h->ev_fork[i]) cudaEventDestroy(h->ev_fork[i]);
+    if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  }
   delete h;
   return MVIN_OK;
 }
