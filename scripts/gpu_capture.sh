@@ -1,0 +1,25 @@
+#!/bin/bash
+# One gpurun call: parity tests, bench lines, ncu launch list and --set full captures (B200_PROFILING.md recipe).
+# usage: scripts/gpu_capture.sh <tag> [workloads...]
+set -u
+TAG=${1:-r01}
+shift || true
+WLS=${@:-C2}
+OUT=gpurun_out
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_smi.csv 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1
+echo "pytest exit $?" >> $OUT/${TAG}_pytest.log
+tail -3 $OUT/${TAG}_pytest.log
+for WL in $WLS; do
+  timeout 600 python bench.py --workload $WL > $OUT/${TAG}_bench_${WL}.json 2> $OUT/${TAG}_bench_${WL}.err
+  tail -c 600 $OUT/${TAG}_bench_${WL}.json
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
+      --log-file $OUT/${TAG}_launches_${WL}.csv python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu-baseline \
+      > $OUT/${TAG}_ncu_launch_${WL}.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'agg_(fwd|bwd)_kernel|leaf_entity|ripple_(fwd|bwd)' \
+      -s 30 -c 8 -f -o $OUT/${TAG}_full_${WL} python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu-baseline \
+      > $OUT/${TAG}_ncu_full_${WL}.log 2>&1
+done
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err
+tail -c 400 $OUT/${TAG}_bench_reference.json
