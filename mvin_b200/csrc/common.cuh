@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #define MVIN_DEV __device__ __forceinline__
+#define MVIN_HD __host__ __device__ __forceinline__
 #define FULL_MASK 0xffffffffu
 
 namespace mvin {

@@ -8,43 +8,52 @@
 //
 // Layout: every activation buffer is row-major [rows, D] fp32 with rows = B * K^h (pair-major, child k of node
 // j at row j*K+k, model.py:251).  A launch carries up to MAX_LV level descriptors; the grid is partitioned
-// between the levels (cta_end[]), each CTA owns tiles of R = 64 consecutive rows of ONE level and walks them
-// persistently; the d x d weights live in shared memory for the CTA's lifetime.  Two thread mappings per tile:
-//   * "warp per row" for the neighbour phase: a warp reads the node's packed adjacency record (K ids + K
-//     relation ids, contiguous), does the K-softmax with shuffles, then streams the K child rows with G = 32/LPR
-//     rows in flight per load instruction (LPR = D/4 lanes x 16 B cover one row).
-//   * "register tile" for the dense maps: thread (ty, tx) owns TM rows x 4 columns, FP32 FFMA (see gemm.cuh for
-//     why not TF32), and TMW x 4 entries of each weight gradient.
+// between the levels (cta_end[]), each CTA owns tiles of R consecutive rows of ONE level and walks them
+// persistently; the d x d weights live in shared memory for the CTA's lifetime.  Three phases per tile:
+//   * "stage" (warp per row, all rows of the warp in flight): read the node's packed adjacency record (K ids + K
+//     relation ids, contiguous), K-softmax with shuffles, park (p_k, id_k[, rel_k]) in shared memory.
+//   * "neighbour" (thread-mapped: LPR = D/4 lanes x 16 B cover one row, thread (ty, tx) owns row ty*TM+i and
+//     columns 4tx..4tx+3): stream the K child / entity rows of the thread's row with every 16-byte load
+//     independent of the others (ids and weights come from shared memory), 8 in flight per thread.  The backward
+//     needs one dot product per (row, k) across the LPR lanes: W of them are reduced together by a butterfly
+//     reduce-scatter (W-1 shuffles for W sums).
+//   * "dense" (register tile / tensor cores): the d x d maps and the weight gradients, FP32 FFMA for d < 32 and
+//     3xTF32 mma.sync for d >= 32 (see gemm.cuh for why not plain TF32).
 #pragma once
 #include "common.cuh"
 
 namespace mvin {
+
+constexpr int MAX_K = 64;
+constexpr int MAX_LV = 3;
 
 template <int D>
 struct TC {
   static constexpr int LPR = D / 4;                                   // float4 lanes per row
   static constexpr int NT = (D >= 64) ? 512 : (D >= 16) ? 256 : 128;  // threads per CTA
   static constexpr int NTY = NT / LPR;                                // thread rows of the register tile
-  static constexpr int R = 64;                                        // rows per tile
+  static constexpr int R = (D >= 32) ? 32 : 64;                       // rows per tile
   static constexpr int TM = R / NTY;                                  // rows per thread
   static constexpr int LD = D + 4;                                    // padded leading dimension of a smem row tile
   static constexpr int NW = NT / 32;                                  // warps per CTA
   static constexpr int G = 32 / LPR;                                  // rows one warp load instruction covers
+  static constexpr int RPW = R / NW;                                  // rows per warp in the stage phase
   static constexpr int TMW = (D / NTY) > 0 ? (D / NTY) : 1;           // dW rows per thread (SIMT path)
   static constexpr int LDW = D + 8;                                   // padded leading dimension of a smem weight
   static constexpr int WSZ = D * LDW;                                 // floats of one smem weight
-  // tensor-core path (3xTF32 mma.sync, d >= 32): the 64 x D output tile is split into 4 row blocks of 16 rows and
-  // NW/4 column groups, one (row block, column group) per warp
+  static constexpr int W = LPR < 8 ? LPR : 8;                         // dot products reduced together (backward)
+  static constexpr int NKW = MAX_K / W;                               // chunks of W neighbours
+  // tensor-core path (3xTF32 mma.sync, d >= 32): the R x D output tile is split into RB row blocks of 16 rows and
+  // CGRP column groups, one (row block, column group) per warp
   static constexpr bool TCORE = D >= 32;
-  static constexpr int CGRP = NW / 4 > 0 ? NW / 4 : 1;                // column groups
+  static constexpr int RB = R / 16;                                   // row blocks
+  static constexpr int CGRP = NW / RB > 0 ? NW / RB : 1;              // column groups
   static constexpr int NTW = D / CGRP / 8 > 0 ? D / CGRP / 8 : 1;     // n8 tiles per warp
   static constexpr int MT = D / 16 > 0 ? D / 16 : 1;                  // m16 tiles of a D x D weight gradient
   static constexpr int TPW = (MT * (D / 8)) / NW > 0 ? (MT * (D / 8)) / NW : 1;   // dW n8 tiles per warp
   static constexpr int DWN = TCORE ? TPW : TMW;                       // per-thread dW accumulator rows of 4 floats
+  static_assert(TM >= 1 && TM * NTY == R && RPW >= 1 && RPW * NW == R, "bad tile");
 };
-
-constexpr int MAX_K = 64;
-constexpr int MAX_LV = 3;
 
 // rows per pair are a runtime K^h: q = n / d through a 64-bit multiply-high with M = floor(2^64 / d) + 1 (exact for
 // n, d < 2^32; d = 1 is flagged by M = 0) instead of the ~100-instruction 64-bit software division
@@ -113,7 +122,7 @@ MVIN_DEV void mma3(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[
   mma_tf32(c, ah, bh);
 }
 
-// acc[i][0..3] (thread-mapped, rows ty*TM+i, cols tx*4..) += (As . Ws)[row][col];  As [64][LD] is CLOBBERED (it
+// acc[i][0..3] (thread-mapped, rows ty*TM+i, cols tx*4..) += (As . Ws)[row][col];  As [R][LD] is CLOBBERED (it
 // receives the product), Ws is [D][LDW].  Every thread of the CTA must call it; As must be complete and
 // synchronised on entry; the caller synchronises before overwriting As again.
 template <int D>
@@ -124,7 +133,7 @@ MVIN_DEV void tile_mm(float* __restrict__ As, const float* __restrict__ Ws, int 
     mm_tile<D>(As, Ws, ty, tx, acc);
   } else {
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, g = lane / 4, t = lane % 4;
-    const int r0 = (warp % 4) * 16, n0 = (warp / 4) * (C::NTW * 8);
+    const int r0 = (warp % C::RB) * 16, n0 = (warp / C::RB) * (C::NTW * 8);
     float c[C::NTW][4];
 #pragma unroll
     for (int j = 0; j < C::NTW; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
@@ -158,7 +167,7 @@ MVIN_DEV void tile_mm(float* __restrict__ As, const float* __restrict__ Ws, int 
   }
 }
 
-// dW += A^T G over the 64 rows of a tile (A = As [64][LD], G = Gs [64][LD]); register-resident accumulator.
+// dW += A^T G over the R rows of a tile (A = As [R][LD], G = Gs [R][LD]); register-resident accumulator.
 //   SIMT path:  dw[i] = dW[ty*TMW+i][tx*4 .. +3]
 //   tensor-core path: warp owns m16 tile (warp % MT) and TPW consecutive n8 tiles; dw[j] is the mma C fragment
 template <int D>
@@ -232,15 +241,23 @@ MVIN_DEV void dw_flush(float (&dw)[TC<D>::DWN][4], float* __restrict__ dW, int t
     }
   }
 }
-// red[D] (shared, zeroed) += per-thread column partials, then one global atomic per column
+// db[D] += column sums of the per-thread partials: warp shuffle over the rows of a warp, one smem slot per warp,
+// then one global atomic per column.  `scratch` is >= NW * D floats of shared memory nobody else is using; ends
+// with a __syncthreads().
 template <int D>
-MVIN_DEV void bias_flush(float4 part, float* __restrict__ red, float* __restrict__ db, int tid, int tx) {
-  atomicAdd(&red[tx * 4 + 0], part.x);
-  atomicAdd(&red[tx * 4 + 1], part.y);
-  atomicAdd(&red[tx * 4 + 2], part.z);
-  atomicAdd(&red[tx * 4 + 3], part.w);
+MVIN_DEV void bias_flush(float4 part, float* __restrict__ scratch, float* __restrict__ db, int tid) {
+  using C = TC<D>;
+  const int warp = tid / 32, lane = tid % 32, g = lane / C::LPR, c = lane % C::LPR;
+  part = cross_group_sum4<C::LPR>(part);
   __syncthreads();
-  if (tid < D) atomicAdd(db + tid, red[tid]);
+  if (g == 0) st4(&scratch[warp * D + c * 4], part);
+  __syncthreads();
+  if (tid < D) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < C::NW; ++w) s += scratch[w * D + tid];
+    atomicAdd(db + tid, s);
+  }
   __syncthreads();
 }
 
@@ -249,61 +266,96 @@ MVIN_DEV void load_weight(float* __restrict__ Ws, const float* __restrict__ Wg, 
   for (int i = tid * 4; i < D * D; i += TC<D>::NT * 4) st4(&Ws[(i / D) * TC<D>::LDW + i % D], ldg4(&Wg[i]));
 }
 
-// attention of one node over its K sampled neighbours: p_k = softmax_k(s[rel_k])  (aggregators.py:121-139 with
-// the user / self thirds of the logit cancelled).  Lane l handles k = l and k = l + 32.
-struct Att {
-  float p0, p1;
-  int rel0, rel1, id0, id1;
-};
-MVIN_DEV Att attend(const int32_t* __restrict__ arow, int K, const float* __restrict__ s_s, int lane) {
-  Att a;
-  a.rel0 = a.rel1 = 0;
-  a.id0 = a.id1 = 0;
-  float l0 = -INFINITY, l1 = -INFINITY;
-  if (lane < K) {
-    a.id0 = __ldg(arow + lane);
-    a.rel0 = __ldg(arow + K + lane);
-    l0 = s_s[a.rel0];
+// ---- stage phase ------------------------------------------------------------------------------------------
+// attention of a node over its K sampled neighbours: p_k = softmax_k(s[rel_k])  (aggregators.py:121-139 with the
+// user / self thirds of the logit cancelled).  Each warp handles its RPW rows of the tile, CH
+// of them at a time with all their adjacency loads issued before the first softmax; lane l handles k = l and
+// k = l + 32.  Output: nb_s[r][k] = (p_k, id_k) and, for the backward, rel_s[r][k].
+template <int D, bool WITH_REL>
+MVIN_DEV void stage_tile(const int32_t* __restrict__ ent, const int32_t* __restrict__ adj,
+                         const float* __restrict__ s_s, long row0, long rows, int K, int KP, int2* __restrict__ nb_s,
+                         uint16_t* __restrict__ rel_s, int warp, int lane) {
+  using C = TC<D>;
+  constexpr int CH = C::RPW < 4 ? C::RPW : 4;
+#pragma unroll 1
+  for (int j0 = 0; j0 < C::RPW; j0 += CH) {
+    int id0[CH], id1[CH], rl0[CH], rl1[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const long row = row0 + warp * C::RPW + j0 + j;
+      id0[j] = id1[j] = rl0[j] = rl1[j] = 0;
+      if (row < rows) {
+        const int32_t* arow = adj + (long)__ldg(ent + row) * 2 * K;
+        if (lane < K) { id0[j] = __ldg(arow + lane); rl0[j] = __ldg(arow + K + lane); }
+        if (lane + 32 < K) { id1[j] = __ldg(arow + lane + 32); rl1[j] = __ldg(arow + K + lane + 32); }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const int r = warp * C::RPW + j0 + j;
+      if (row0 + r >= rows) continue;                       // warp-uniform
+      const float l0 = lane < K ? s_s[rl0[j]] : -INFINITY;
+      const float l1 = lane + 32 < K ? s_s[rl1[j]] : -INFINITY;
+      const float mx = warp_max(fmaxf(l0, l1));
+      const float e0 = lane < K ? expf(l0 - mx) : 0.f;
+      const float e1 = lane + 32 < K ? expf(l1 - mx) : 0.f;
+      const float inv = 1.f / warp_sum(e0 + e1);
+      if (lane < K) {
+        nb_s[r * KP + lane] = make_int2(__float_as_int(e0 * inv), id0[j]);
+        if (WITH_REL) rel_s[r * KP + lane] = (uint16_t)rl0[j];
+      }
+      if (lane + 32 < K) {
+        nb_s[r * KP + lane + 32] = make_int2(__float_as_int(e1 * inv), id1[j]);
+        if (WITH_REL) rel_s[r * KP + lane + 32] = (uint16_t)rl1[j];
+      }
+    }
   }
-  if (lane + 32 < K) {
-    a.id1 = __ldg(arow + lane + 32);
-    a.rel1 = __ldg(arow + K + lane + 32);
-    l1 = s_s[a.rel1];
+}
+MVIN_DEV int padded_k(int K) { return K | 1; }   // odd row pitch of the staged neighbour records (bank spread)
+
+// W partial sums per lane -> complete sums across the LPR lanes of a row: butterfly reduce-scatter over the low
+// log2(W) lane bits (W - 1 shuffles), then an all-reduce over the remaining bits.  Returns the total of
+// v[lane % W]; lanes that agree on lane % W (within a row group) hold the same value.
+template <int W, int LPR>
+MVIN_DEV float reduce_scatter(float (&v)[W], int lane) {
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < o; ++j) {
+      const float send = up ? v[j] : v[j + o];
+      const float keep = up ? v[j + o] : v[j];
+      v[j] = keep + __shfl_xor_sync(FULL_MASK, send, o);
+    }
   }
-  const float mx = warp_max(fmaxf(l0, l1));
-  const float e0 = lane < K ? expf(l0 - mx) : 0.f;
-  const float e1 = lane + 32 < K ? expf(l1 - mx) : 0.f;
-  const float inv = 1.f / warp_sum(e0 + e1);
-  a.p0 = e0 * inv;
-  a.p1 = e1 * inv;
-  return a;
+  float t = v[0];
+#pragma unroll
+  for (int o = W; o < LPR; o <<= 1) t += __shfl_xor_sync(FULL_MASK, t, o);
+  return t;
 }
 
-// accumulate per-pair sums of the rows of a smem tile into du[B, D]; rows of one pair are contiguous, so each
-// thread walks a strip of the tile and flushes one atomic per (pair, column) run.
+// du[pair] += sum over the rows of the pair of v (thread-mapped rows ty*TM+i; rows past the end of the level must
+// hold zeros).  Rows of one pair are contiguous (rpp = K^h per pair): when a warp's G*TM consecutive rows cannot
+// straddle two pairs they are summed with shuffles first, one 16-byte red per warp and column chunk.
 template <int D>
-MVIN_DEV void tile_rows_to_pairs(const float* __restrict__ As, float* __restrict__ du, long row0, long rows,
-                                 unsigned long long rpp_magic, int tid) {
+MVIN_DEV void pair_accumulate(const float4 (&v)[TC<D>::TM], float* __restrict__ du, long row0, long rows, int rpp,
+                              unsigned long long rpp_magic, int ty, int tx, int lane) {
   using C = TC<D>;
-  constexpr int PARTS = (C::NT / D) < C::R ? (C::NT / D) : C::R;
-  constexpr int RPS = C::R / PARTS;                   // rows per strip
-  const int col = tid % D, part = tid / D;
-  if (part >= PARTS) return;
-  long cur = -1;
-  float acc = 0.f;
-#pragma unroll 4
-  for (int r = part * RPS; r < (part + 1) * RPS; ++r) {
-    const long row = row0 + r;
-    if (row >= rows) break;
-    const long b = fastdiv(row, rpp_magic);
-    if (b != cur) {
-      if (cur >= 0) atomicAdd(du + cur * D + col, acc);
-      cur = b;
-      acc = 0.f;
+  constexpr int RW = C::G * C::TM;
+  if (rpp % RW == 0) {
+    float4 s = v[0];
+#pragma unroll
+    for (int i = 1; i < C::TM; ++i) s = f4add(s, v[i]);
+    s = cross_group_sum4<C::LPR>(s);
+    const long first = row0 + (long)(ty - lane / C::LPR) * C::TM;
+    if (lane / C::LPR == 0 && first < rows) red_add4(du + fastdiv(first, rpp_magic) * D + tx * 4, s);
+  } else {
+#pragma unroll
+    for (int i = 0; i < C::TM; ++i) {
+      const long row = row0 + ty * C::TM + i;
+      if (row < rows) red_add4(du + fastdiv(row, rpp_magic) * D + tx * 4, v[i]);
     }
-    acc += As[r * C::LD + col];
   }
-  if (cur >= 0) atomicAdd(du + cur * D + col, acc);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -380,12 +432,10 @@ __global__ void __launch_bounds__(TC<D>::NT) transform_bwd_kernel(TransformArgs 
   float* Ws = smem;
   float* As = Ws + C::WSZ;                 // dT tile, later gx tile
   float* Xs = As + C::R * C::LD;          // XU tile
-  float* red = Xs + C::R * C::LD;         // [D]
   const int tid = threadIdx.x, tx = tid % C::LPR, ty = tid / C::LPR;
   const CtaSlice cs = cta_slice(a.cta_end, a.nlev);
   const TransformLevel& L = a.lv[cs.level];
   load_weight<D>(Ws, L.W, tid);
-  if (tid < D) red[tid] = 0.f;
   float dw[C::DWN][4];
 #pragma unroll
   for (int i = 0; i < C::DWN; ++i) dw[i][0] = dw[i][1] = dw[i][2] = dw[i][3] = 0.f;
@@ -415,27 +465,24 @@ __global__ void __launch_bounds__(TC<D>::NT) transform_bwd_kernel(TransformArgs 
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
     tile_mm<D>(As, Ws, ty, tx, acc);
-    __syncthreads();
+    float4 gx[C::TM];
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) {
-      const int r = ty * C::TM + i;
-      const long row = row0 + r;
-      const float4 gx = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-      if (row < L.rows) red_add4(grow_of(a.dE, L.ent[row], D) + tx * 4, gx);
-      st4(&As[r * C::LD + tx * 4], gx);
+      const long row = row0 + ty * C::TM + i;
+      gx[i] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);   // zero for rows past the end (dT = 0)
+      if (row < L.rows) red_add4(grow_of(a.dE, L.ent[row], D) + tx * 4, gx[i]);
     }
-    __syncthreads();
-    tile_rows_to_pairs<D>(As, a.du, row0, L.rows, L.rpp_magic, tid);
+    pair_accumulate<D>(gx, a.du, row0, L.rows, L.rpp, L.rpp_magic, ty, tx, tid % 32);
     __syncthreads();
   }
   dw_flush<D>(dw, L.dW, ty, tx);
-  bias_flush<D>(bpart, red, L.db, tid, tx);
+  bias_flush<D>(bpart, As, L.db, tid);
 }
 
 template <int D>
 constexpr size_t transform_fwd_smem() { return sizeof(float) * (TC<D>::WSZ + TC<D>::R * TC<D>::LD); }
 template <int D>
-constexpr size_t transform_bwd_smem() { return sizeof(float) * (TC<D>::WSZ + 2 * TC<D>::R * TC<D>::LD + D); }
+constexpr size_t transform_bwd_smem() { return sizeof(float) * (TC<D>::WSZ + 2 * TC<D>::R * TC<D>::LD); }
 
 // ---------------------------------------------------------------------------------------------------------
 // one aggregator iteration, forward, all levels  (aggregators.py:98-146; model.py:295-306)
@@ -471,91 +518,97 @@ struct AggArgs {
   int K, n_rel;
 };
 
+// shared-memory carve-up shared by the host-side size functions and the kernels (byte offsets, 16-byte aligned)
+template <int D>
+struct AggSmem {
+  using C = TC<D>;
+  static MVIN_HD size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+  // forward: Wa | [Wt] | As | nb[R][KP] int2 | s[n_rel]
+  static MVIN_HD size_t fwd(bool has_leaf, int K, int n_rel) {
+    return sizeof(float) * ((has_leaf ? 2 : 1) * C::WSZ + C::R * C::LD) + align16(sizeof(int2) * C::R * (K | 1)) +
+           sizeof(float) * n_rel;
+  }
+  // backward: WaT | [WtT] | Gs | Ys | nb[R][KP] int2 | rel[R][KP] u16 | s[n_rel] | ds[NWH][n_rel]
+  static MVIN_HD int ds_copies(int n_rel) { return n_rel <= 128 ? C::NW : 1; }
+  static MVIN_HD size_t bwd(bool has_leaf, int K, int n_rel) {
+    return sizeof(float) * ((has_leaf ? 2 : 1) * C::WSZ + 2 * C::R * C::LD) + align16(sizeof(int2) * C::R * (K | 1)) +
+           align16(sizeof(uint16_t) * C::R * (K | 1)) + sizeof(float) * n_rel * (1 + ds_copies(n_rel));
+  }
+};
+
 template <int D, bool HAS_LEAF>
 __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
   using C = TC<D>;
-  extern __shared__ __align__(16) float smem[];
-  float* Wa_s = smem;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int K = a.K, KP = padded_k(K);
+  float* Wa_s = reinterpret_cast<float*>(smem_raw);
   float* Wt_s = Wa_s + C::WSZ;
   float* As = Wt_s + (HAS_LEAF ? C::WSZ : 0);
-  float* pw = As + C::R * C::LD;                           // [NW][MAX_K]
-  int* idw = reinterpret_cast<int*>(pw + C::NW * MAX_K);   // [NW][MAX_K]
-  float* s_s = reinterpret_cast<float*>(idw + C::NW * MAX_K);
+  int2* nb_s = reinterpret_cast<int2*>(As + C::R * C::LD);
+  float* s_s = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(nb_s) +
+                                        AggSmem<D>::align16(sizeof(int2) * C::R * KP));
   const int tid = threadIdx.x, tx = tid % C::LPR, ty = tid / C::LPR;
-  const int warp = tid / 32, lane = tid % 32, g = lane / C::LPR, c = lane % C::LPR;
+  const int warp = tid / 32, lane = tid % 32;
   const CtaSlice cs = cta_slice(a.cta_end, a.nlev);
   const AggLevel& L = a.lv[cs.level];
   const bool leaf = HAS_LEAF && L.leaf;
+  const bool ent_mode = leaf && a.Se != nullptr;
   load_weight<D>(Wa_s, a.Wa, tid);
   if (leaf) load_weight<D>(Wt_s, a.Wt, tid);
   for (int i = tid; i < a.n_rel; i += C::NT) s_s[i] = a.s[i];
   const float4 ba = ldg4(a.ba + tx * 4);
   float4 bt = f4zero();
   if (leaf) bt = ldg4(a.bt + tx * 4);
-  const int K = a.K;
   const float invK = 1.f / (float)K;
-  float* pw_w = pw + warp * MAX_K;
-  int* idw_w = idw + warp * MAX_K;
   __syncthreads();
 
   const long ntiles = (L.rows + C::R - 1) / C::R;
   for (long t = cs.local; t < ntiles; t += cs.count) {
     const long row0 = t * C::R;
-    const bool ent_mode = leaf && a.Se != nullptr;
-    if (ent_mode) {
-      // entity mode: S depends on the node's entity only and was computed once per distinct entity
-      // (leaf_entity_kernel); thread-mapped row loads, all TM of them in flight at once
+    // ---- stage phase: (p_k, id_k) of every row of the tile ----
+    if (!ent_mode) {
+      stage_tile<D, false>(L.ent, a.adj, s_s, row0, L.rows, K, KP, nb_s, nullptr, warp, lane);
+      __syncthreads();
+    }
+    // ---- neighbour phase: thread-mapped ----
 #pragma unroll
-      for (int i = 0; i < C::TM; ++i) {
-        const int r = ty * C::TM + i;
-        const long row = row0 + r;
-        float4 o = f4zero();
-        if (row < L.rows) {
-          const long e = L.ent[row];
+    for (int i = 0; i < C::TM; ++i) {
+      const int r = ty * C::TM + i;
+      const long row = row0 + r;
+      float4 o = f4zero();
+      if (row < L.rows) {
+        if (ent_mode) {
+          // entity mode: S depends on the node's entity only and was computed once per distinct entity
+          // (leaf_entity_kernel)
+          const long e = __ldg(L.ent + row);
           o = f4add(ldg4(a.Se + e * D + tx * 4), ldg4(a.u + fastdiv(row, L.rpp_magic) * D + tx * 4));
           st4(L.SU + row * D + tx * 4, o);
-        }
-        st4(&As[r * C::LD + tx * 4], o);
-      }
-    }
-    // ---- neighbour phase: warp per row ----
-    for (int r = warp; r < C::R && !ent_mode; r += C::NW) {
-      const long row = row0 + r;
-      if (row < L.rows) {
-        const long e = L.ent[row];
-        const Att at = attend(a.adj + e * 2 * K, K, s_s, lane);
-        pw_w[lane] = at.p0;
-        pw_w[lane + 32] = at.p1;
-        if (leaf) { idw_w[lane] = at.id0; idw_w[lane + 32] = at.id1; }
-        __syncwarp();
-        float4 acc = f4zero();
-        if (leaf) {
-#pragma unroll 4
-          for (int k = g; k < K; k += C::G) acc = f4fma(pw_w[k], ldg4(erow(a.E, idw_w[k], D) + c * 4), acc);
-        } else {
-          const float* base = L.child + row * K * D + c * 4;
-#pragma unroll 4
-          for (int k = g; k < K; k += C::G) acc = f4fma(pw_w[k], ldg4(base + (long)k * D), acc);
-        }
-        acc = cross_group_sum4<C::LPR>(acc);
-        if (g == 0) {
-          float4 o;
-          if (leaf) {
-            o = f4add(acc, ldg4(a.u + fastdiv(row, L.rpp_magic) * D + c * 4));
-            st4(L.SU + row * D + c * 4, o);
-          } else {
-            o = f4fma(invK, acc, ld4(L.self + row * D + c * 4));
-            st4(L.Y + row * D + c * 4, o);
+        } else if (leaf) {
+          const float4 uv = ldg4(a.u + fastdiv(row, L.rpp_magic) * D + tx * 4);
+          const int2* nb = nb_s + r * KP;
+          float4 acc = f4zero();
+#pragma unroll 8
+          for (int k = 0; k < K; ++k) {
+            const int2 v = nb[k];
+            acc = f4fma(__int_as_float(v.x), ldg4(erow(a.E, v.y, D) + tx * 4), acc);
           }
-          st4(&As[r * C::LD + c * 4], o);
+          o = f4add(acc, uv);
+          st4(L.SU + row * D + tx * 4, o);
+        } else {
+          const float4 sv = ldg4(L.self + row * D + tx * 4);
+          const int2* nb = nb_s + r * KP;
+          const float* base = L.child + row * K * D + tx * 4;
+          float4 acc = f4zero();
+#pragma unroll 8
+          for (int k = 0; k < K; ++k) acc = f4fma(__int_as_float(nb[k].x), ldg4(base + (long)k * D), acc);
+          o = f4fma(invK, acc, sv);
+          st4(L.Y + row * D + tx * 4, o);
         }
-        __syncwarp();
-      } else if (g == 0) {
-        st4(&As[r * C::LD + c * 4], f4zero());
       }
+      st4(&As[r * C::LD + tx * 4], o);
     }
     __syncthreads();
-    // ---- dense phase: register tile ----
+    // ---- dense phase: register tile / tensor cores ----
     float acc[C::TM][4];
     if (leaf) {
 #pragma unroll
@@ -568,7 +621,7 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
         const long row = row0 + r;
         float4 y = f4zero();
         if (row < L.rows) {
-          y = f4fma(invK, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]), ld4(L.self + row * D + tx * 4));
+          y = f4fma(invK, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]), ldg4(L.self + row * D + tx * 4));
           st4(L.Y + row * D + tx * 4, y);
         }
         st4(&As[r * C::LD + tx * 4], y);
@@ -590,9 +643,7 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
 }
 
 template <int D, bool HAS_LEAF>
-constexpr size_t agg_fwd_smem(int n_rel) {
-  return sizeof(float) * ((HAS_LEAF ? 2 : 1) * TC<D>::WSZ + TC<D>::R * TC<D>::LD + 2 * TC<D>::NW * MAX_K + n_rel);
-}
+inline size_t agg_fwd_smem(int K, int n_rel) { return AggSmem<D>::fwd(HAS_LEAF, K, n_rel); }
 
 // ---------------------------------------------------------------------------------------------------------
 // one aggregator iteration, backward, all levels (Appendix B of SURVEY.md; tests/fused_model.py is the CPU twin)
@@ -644,31 +695,31 @@ struct AggBwdArgs {
 template <int D, bool HAS_LEAF>
 __global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
   using C = TC<D>;
-  extern __shared__ __align__(16) float smem[];
-  float* Wa_s = smem;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int K = a.K, KP = padded_k(K);
+  float* Wa_s = reinterpret_cast<float*>(smem_raw);
   float* Wt_s = Wa_s + C::WSZ;
   float* Gs = Wt_s + (HAS_LEAF ? C::WSZ : 0);
   float* Ys = Gs + C::R * C::LD;
-  float* pw = Ys + C::R * C::LD;                       // [NW][MAX_K]
-  float* dpw = pw + C::NW * MAX_K;                     // [NW][MAX_K]
-  int* idw = reinterpret_cast<int*>(dpw + C::NW * MAX_K);
-  float* s_s = reinterpret_cast<float*>(idw + C::NW * MAX_K);
-  float* ds_s = s_s + a.n_rel;
-  float* red = ds_s + a.n_rel;                         // [2][D]
+  int2* nb_s = reinterpret_cast<int2*>(Ys + C::R * C::LD);
+  uint16_t* rel_s = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(nb_s) +
+                                                AggSmem<D>::align16(sizeof(int2) * C::R * KP));
+  float* s_s = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(rel_s) +
+                                        AggSmem<D>::align16(sizeof(uint16_t) * C::R * KP));
+  float* ds_s = s_s + a.n_rel;                         // [NWH][n_rel]: one private copy per warp when n_rel is small
+  const int NWH = AggSmem<D>::ds_copies(a.n_rel);
   const int tid = threadIdx.x, tx = tid % C::LPR, ty = tid / C::LPR;
-  const int warp = tid / 32, lane = tid % 32, g = lane / C::LPR, c = lane % C::LPR;
+  const int warp = tid / 32, lane = tid % 32;
   const CtaSlice cs = cta_slice(a.cta_end, a.nlev);
   const AggBwdLevel& L = a.lv[cs.level];
   const bool leaf = HAS_LEAF && L.leaf;
+  const bool ent_mode = leaf && a.GSe != nullptr;
   load_weight<D>(Wa_s, a.WaT, tid);
   if (leaf) load_weight<D>(Wt_s, a.WtT, tid);
-  for (int i = tid; i < a.n_rel; i += C::NT) { s_s[i] = a.s[i]; ds_s[i] = 0.f; }
-  for (int i = tid; i < 2 * D; i += C::NT) red[i] = 0.f;
-  const int K = a.K;
+  for (int i = tid; i < a.n_rel; i += C::NT) s_s[i] = a.s[i];
+  for (int i = tid; i < NWH * a.n_rel; i += C::NT) ds_s[i] = 0.f;
   const float invK = 1.f / (float)K;
-  float* pw_w = pw + warp * MAX_K;
-  float* dpw_w = dpw + warp * MAX_K;
-  int* idw_w = idw + warp * MAX_K;
+  float* ds_w = ds_s + (NWH > 1 ? warp : 0) * a.n_rel;
   float dwa[C::DWN][4], dwt[HAS_LEAF ? C::DWN : 1][4];
 #pragma unroll
   for (int i = 0; i < C::DWN; ++i) dwa[i][0] = dwa[i][1] = dwa[i][2] = dwa[i][3] = 0.f;
@@ -680,18 +731,20 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
   const long ntiles = (L.rows + C::R - 1) / C::R;
   for (long t = cs.local; t < ntiles; t += cs.count) {
     const long row0 = t * C::R;
+    // ---- stage phase (its loads overlap the tile loads below) ----
+    if (!ent_mode) stage_tile<D, true>(L.ent, a.adj, s_s, row0, L.rows, K, KP, nb_s, rel_s, warp, lane);
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) {
       const int r = ty * C::TM + i;
       const long row = row0 + r;
       float4 gz = f4zero(), y = f4zero();
       if (row < L.rows) {
-        float4 go = ld4(L.g1 + row * D + tx * 4);
-        if (L.g2) go = f4add(go, ld4(L.g2 + row * D + tx * 4));
-        const float4 v = ld4(L.V + row * D + tx * 4);
+        float4 go = ldg4(L.g1 + row * D + tx * 4);
+        if (L.g2) go = f4add(go, ldg4(L.g2 + row * D + tx * 4));
+        const float4 v = ldg4(L.V + row * D + tx * 4);
         gz = make_float4(v.x > 0.f ? go.x : 0.f, v.y > 0.f ? go.y : 0.f, v.z > 0.f ? go.z : 0.f,
                          v.w > 0.f ? go.w : 0.f);
-        y = ld4(L.Y + row * D + tx * 4);
+        y = ldg4(L.Y + row * D + tx * 4);
       }
       bpa = f4add(bpa, gz);
       st4(&Gs[r * C::LD + tx * 4], gz);
@@ -713,7 +766,7 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
       float4 su = f4zero();
       if (row < L.rows) {
         st4(L.dself + row * D + tx * 4, gs);
-        if (leaf) su = ld4(L.SU + row * D + tx * 4);
+        if (leaf) su = ldg4(L.SU + row * D + tx * 4);
       }
       st4(&Gs[r * C::LD + tx * 4], grow);
       if (leaf) {
@@ -728,75 +781,99 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
       for (int i = 0; i < C::TM; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
       tile_mm<D>(Gs, Wt_s, ty, tx, acc);
       __syncthreads();
+      float4 gsu[C::TM];
 #pragma unroll
       for (int i = 0; i < C::TM; ++i) {
-        const float4 gsu = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-        st4(&Gs[(ty * C::TM + i) * C::LD + tx * 4], gsu);
-        if (a.GSe != nullptr) {
+        const int r = ty * C::TM + i;
+        const long row = row0 + r;
+        gsu[i] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);   // zero for rows past the end
+        if (ent_mode) {
           // entity mode: the leaf scatter and the softmax gradient are linear in gsu and depend on the entity only
-          const long row = row0 + ty * C::TM + i;
-          if (row < L.rows) red_add4(a.GSe + (long)L.ent[row] * D + tx * 4, gsu);
+          if (row < L.rows) red_add4(a.GSe + (long)__ldg(L.ent + row) * D + tx * 4, gsu[i]);
+        } else {
+          st4(&Gs[r * C::LD + tx * 4], gsu[i]);                            // same thread reads it back below
         }
       }
-      __syncthreads();
-      tile_rows_to_pairs<D>(Gs, a.du, row0, L.rows, L.rpp_magic, tid);
+      pair_accumulate<D>(gsu, a.du, row0, L.rows, L.rpp, L.rpp_magic, ty, tx, lane);
     }
-    // ---- neighbour phase: warp per row ----
-    for (int r = warp; r < C::R && !(leaf && a.GSe != nullptr); r += C::NW) {
-      const long row = row0 + r;
-      if (row >= L.rows) break;
-      const long e = L.ent[row];
-      const Att at = attend(a.adj + e * 2 * K, K, s_s, lane);
-      pw_w[lane] = at.p0;
-      pw_w[lane + 32] = at.p1;
-      if (leaf) { idw_w[lane] = at.id0; idw_w[lane + 32] = at.id1; }
-      __syncwarp();
-      const float4 gr = ld4(&Gs[r * C::LD + c * 4]);
-      // uniform trip count: the shuffles inside need every lane of the warp
-#pragma unroll 4
-      for (int k0 = 0; k0 < K; k0 += C::G) {
-        const int k = k0 + g;
-        const bool valid = k < K;
-        float part = 0.f;
-        if (valid) {
-          const float pk = pw_w[k];
-          if (leaf) {
-            const long n = idw_w[k];
-            part = f4dot(gr, ldg4(erow(a.E, n, D) + c * 4));
-            red_add4(grow_of(a.dE, n, D) + c * 4, f4scale(gr, pk));
-          } else {
-            const long cr = (row * K + k) * D + c * 4;
-            part = f4dot(gr, ld4(L.child + cr));
-            st4(L.dchild + cr, f4scale(gr, pk));
+    // ---- neighbour phase: thread-mapped.  gr = dL/d(sum_k p_k x_k) of the thread's row; per neighbour k:
+    //      dx_k = p_k gr (stored / scattered), dp_k = gr . x_k (W dot products reduced together) ----
+    if (!ent_mode) {
+      const int kl = lane & (C::W - 1);
+#pragma unroll
+      for (int i = 0; i < C::TM; ++i) {
+        const int r = ty * C::TM + i;
+        const long row = row0 + r;
+        const bool valid = row < L.rows;
+        const float4 gr = ld4(&Gs[r * C::LD + tx * 4]);
+        const int2* nb = nb_s + r * KP;
+        float dp[C::NKW];
+#pragma unroll
+        for (int c = 0; c < C::NKW; ++c) {
+          dp[c] = 0.f;
+          if (c * C::W < K) {                                   // CTA-uniform
+            float4 x[C::W];
+            int2 v[C::W];
+#pragma unroll
+            for (int j = 0; j < C::W; ++j) {
+              const int k = c * C::W + j;
+              x[j] = f4zero();
+              v[j] = make_int2(0, 0);
+              if (valid && k < K) {
+                v[j] = nb[k];
+                if (leaf) x[j] = ldg4(erow(a.E, v[j].y, D) + tx * 4);
+                else x[j] = ldg4(L.child + (row * K + k) * D + tx * 4);
+              }
+            }
+            float part[C::W];
+#pragma unroll
+            for (int j = 0; j < C::W; ++j) {
+              const int k = c * C::W + j;
+              part[j] = f4dot(gr, x[j]);
+              if (valid && k < K) {
+                const float4 dx = f4scale(gr, __int_as_float(v[j].x));
+                if (leaf) red_add4(grow_of(a.dE, v[j].y, D) + tx * 4, dx);
+                else st4(L.dchild + (row * K + k) * D + tx * 4, dx);
+              }
+            }
+            dp[c] = reduce_scatter<C::W, C::LPR>(part, lane);   // dp of k = c*W + kl
           }
         }
-        part = group_sum<C::LPR>(part);
-        if (valid && c == 0) dpw_w[k] = part;
+        // softmax backward: dlogit_k = p_k (dp_k - sum_j p_j dp_j);  ds[rel_k] += dlogit_k
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < C::NKW; ++c) {
+          const int k = c * C::W + kl;
+          if (valid && k < K) dot = fmaf(__int_as_float(nb[k].x), dp[c], dot);
+        }
+#pragma unroll
+        for (int o = C::W / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL_MASK, dot, o);
+        if (valid && tx < C::W) {
+#pragma unroll
+          for (int c = 0; c < C::NKW; ++c) {
+            const int k = c * C::W + tx;
+            if (k < K) atomicAdd(&ds_w[rel_s[r * KP + k]], __int_as_float(nb[k].x) * (dp[c] - dot));
+          }
+        }
       }
-      __syncwarp();
-      const float dp0 = lane < K ? dpw_w[lane] : 0.f;
-      const float dp1 = lane + 32 < K ? dpw_w[lane + 32] : 0.f;
-      const float dot = warp_sum(at.p0 * dp0 + at.p1 * dp1);
-      if (lane < K) atomicAdd(&ds_s[at.rel0], at.p0 * (dp0 - dot));
-      if (lane + 32 < K) atomicAdd(&ds_s[at.rel1], at.p1 * (dp1 - dot));
-      __syncwarp();
     }
     __syncthreads();
   }
-  for (int i = tid; i < a.n_rel; i += C::NT) atomicAdd(a.ds + i, ds_s[i]);
+  for (int i = tid; i < a.n_rel; i += C::NT) {
+    float s = 0.f;
+    for (int w = 0; w < NWH; ++w) s += ds_s[w * a.n_rel + i];
+    if (s != 0.f) atomicAdd(a.ds + i, s);
+  }
   dw_flush<D>(dwa, a.dWa, ty, tx);
-  bias_flush<D>(bpa, red, a.dba, tid, tx);
+  bias_flush<D>(bpa, Gs, a.dba, tid);
   if (leaf) {
     if constexpr (HAS_LEAF) dw_flush<D>(dwt, a.dWt, ty, tx);
-    bias_flush<D>(bpt, red + D, a.dbt, tid, tx);
+    bias_flush<D>(bpt, Gs, a.dbt, tid);
   }
 }
 
 template <int D, bool HAS_LEAF>
-constexpr size_t agg_bwd_smem(int n_rel) {
-  return sizeof(float) *
-         ((HAS_LEAF ? 2 : 1) * TC<D>::WSZ + 2 * TC<D>::R * TC<D>::LD + 3 * TC<D>::NW * MAX_K + 2 * n_rel + 2 * D);
-}
+inline size_t agg_bwd_smem(int K, int n_rel) { return AggSmem<D>::bwd(HAS_LEAF, K, n_rel); }
 
 // ---------------------------------------------------------------------------------------------------------
 // entity mode of the leaf level.  S_e = sum_k p_k(e) E[adj[e][k]] depends on the depth-(L-1) node's ENTITY only
@@ -820,8 +897,23 @@ struct LeafEntArgs {
   int n_entity, K, n_rel;
 };
 constexpr int LEAF_NT = 256, LEAF_NW = LEAF_NT / 32;
-inline size_t leaf_entity_smem(int n_rel) { return sizeof(float) * (3 * LEAF_NW * MAX_K + 2 * n_rel); }
+MVIN_HD int leaf_ds_copies(int n_rel) { return n_rel <= 128 ? LEAF_NW : 1; }
+inline size_t leaf_entity_smem(int n_rel) {
+  return sizeof(float) * (3 * LEAF_NW * MAX_K + (1 + leaf_ds_copies(n_rel)) * n_rel);
+}
 
+// adjacency record of one entity spread over a warp: lane l holds k = l and k = l + 32
+struct AdjRec { int id0, id1, rel0, rel1; };
+MVIN_DEV AdjRec load_adj(const int32_t* __restrict__ adj, long e, int K, int lane) {
+  AdjRec r{0, 0, 0, 0};
+  const int32_t* arow = adj + e * 2 * K;
+  if (lane < K) { r.id0 = __ldg(arow + lane); r.rel0 = __ldg(arow + K + lane); }
+  if (lane + 32 < K) { r.id1 = __ldg(arow + lane + 32); r.rel1 = __ldg(arow + K + lane + 32); }
+  return r;
+}
+
+// One warp per chunk of 32 consecutive entities: one coalesced read of their stamps, then the marked ones in turn
+// (the adjacency record of the next marked entity is fetched while the current one is processed).
 template <int D, bool BWD>
 __global__ void __launch_bounds__(LEAF_NT) leaf_entity_kernel(LeafEntArgs a) {
   constexpr int LPR = D / 4, G = 32 / LPR;
@@ -830,56 +922,77 @@ __global__ void __launch_bounds__(LEAF_NT) leaf_entity_kernel(LeafEntArgs a) {
   float* dpw = pw + LEAF_NW * MAX_K;                       // [NW][MAX_K]
   int* idw = reinterpret_cast<int*>(dpw + LEAF_NW * MAX_K);
   float* s_s = reinterpret_cast<float*>(idw + LEAF_NW * MAX_K);
-  float* ds_s = s_s + a.n_rel;
+  float* ds_s = s_s + a.n_rel;                             // [NWH][n_rel]
+  const int NWH = leaf_ds_copies(a.n_rel);
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32, g = lane / LPR, c = lane % LPR;
-  for (int i = tid; i < a.n_rel; i += LEAF_NT) { s_s[i] = a.s[i]; ds_s[i] = 0.f; }
+  for (int i = tid; i < a.n_rel; i += LEAF_NT) s_s[i] = a.s[i];
+  for (int i = tid; i < NWH * a.n_rel; i += LEAF_NT) ds_s[i] = 0.f;
   __syncthreads();
   float* pw_w = pw + warp * MAX_K;
   float* dpw_w = dpw + warp * MAX_K;
   int* idw_w = idw + warp * MAX_K;
+  float* ds_w = ds_s + (NWH > 1 ? warp : 0) * a.n_rel;
   const int K = a.K;
-  for (long e = (long)blockIdx.x * LEAF_NW + warp; e < a.n_entity; e += (long)gridDim.x * LEAF_NW) {
-    if (a.stamp[e] == 0) continue;
-    const Att at = attend(a.adj + e * 2 * K, K, s_s, lane);
-    pw_w[lane] = at.p0;
-    pw_w[lane + 32] = at.p1;
-    idw_w[lane] = at.id0;
-    idw_w[lane + 32] = at.id1;
-    __syncwarp();
-    if (!BWD) {
-      float4 acc = f4zero();
+  for (long c0 = ((long)blockIdx.x * LEAF_NW + warp) * 32; c0 < a.n_entity; c0 += (long)gridDim.x * LEAF_NW * 32) {
+    const long me = c0 + lane;
+    unsigned mask = __ballot_sync(FULL_MASK, me < a.n_entity && __ldg(a.stamp + me) != 0);
+    AdjRec nxt{0, 0, 0, 0};
+    if (mask) nxt = load_adj(a.adj, c0 + (__ffs(mask) - 1), K, lane);
+    while (mask) {
+      const long e = c0 + (__ffs(mask) - 1);
+      mask &= mask - 1;
+      const AdjRec rec = nxt;
+      if (mask) nxt = load_adj(a.adj, c0 + (__ffs(mask) - 1), K, lane);
+      const float l0 = lane < K ? s_s[rec.rel0] : -INFINITY;
+      const float l1 = lane + 32 < K ? s_s[rec.rel1] : -INFINITY;
+      const float mx = warp_max(fmaxf(l0, l1));
+      const float e0 = lane < K ? expf(l0 - mx) : 0.f;
+      const float e1 = lane + 32 < K ? expf(l1 - mx) : 0.f;
+      const float inv = 1.f / warp_sum(e0 + e1);
+      const float p0 = e0 * inv, p1 = e1 * inv;
+      pw_w[lane] = p0;
+      pw_w[lane + 32] = p1;
+      idw_w[lane] = rec.id0;
+      idw_w[lane + 32] = rec.id1;
+      __syncwarp();
+      if (!BWD) {
+        float4 acc = f4zero();
 #pragma unroll 4
-      for (int k = g; k < K; k += G) acc = f4fma(pw_w[k], ldg4(erow(a.E, idw_w[k], D) + c * 4), acc);
-      acc = cross_group_sum4<LPR>(acc);
-      if (g == 0) st4(a.Se + e * D + c * 4, acc);
-    } else {
-      const float4 gr = ld4(a.GSe + e * D + c * 4);
+        for (int k = g; k < K; k += G) acc = f4fma(pw_w[k], ldg4(erow(a.E, idw_w[k], D) + c * 4), acc);
+        acc = cross_group_sum4<LPR>(acc);
+        if (g == 0) st4(a.Se + e * D + c * 4, acc);
+      } else {
+        const float4 gr = ld4(a.GSe + e * D + c * 4);
 #pragma unroll 4
-      for (int k0 = 0; k0 < K; k0 += G) {
-        const int k = k0 + g;
-        const bool valid = k < K;
-        float part = 0.f;
-        if (valid) {
-          const long n = idw_w[k];
-          part = f4dot(gr, ldg4(erow(a.E, n, D) + c * 4));
-          red_add4(grow_of(a.dE, n, D) + c * 4, f4scale(gr, pw_w[k]));
+        for (int k0 = 0; k0 < K; k0 += G) {
+          const int k = k0 + g;
+          const bool valid = k < K;
+          float part = 0.f;
+          if (valid) {
+            const long n = idw_w[k];
+            part = f4dot(gr, ldg4(erow(a.E, n, D) + c * 4));
+            red_add4(grow_of(a.dE, n, D) + c * 4, f4scale(gr, pw_w[k]));
+          }
+          part = group_sum<LPR>(part);
+          if (valid && c == 0) dpw_w[k] = part;
         }
-        part = group_sum<LPR>(part);
-        if (valid && c == 0) dpw_w[k] = part;
+        __syncwarp();
+        const float dp0 = lane < K ? dpw_w[lane] : 0.f;
+        const float dp1 = lane + 32 < K ? dpw_w[lane + 32] : 0.f;
+        const float dot = warp_sum(p0 * dp0 + p1 * dp1);
+        if (lane < K) atomicAdd(&ds_w[rec.rel0], p0 * (dp0 - dot));
+        if (lane + 32 < K) atomicAdd(&ds_w[rec.rel1], p1 * (dp1 - dot));
       }
       __syncwarp();
-      const float dp0 = lane < K ? dpw_w[lane] : 0.f;
-      const float dp1 = lane + 32 < K ? dpw_w[lane + 32] : 0.f;
-      const float dot = warp_sum(at.p0 * dp0 + at.p1 * dp1);
-      if (lane < K) atomicAdd(&ds_s[at.rel0], at.p0 * (dp0 - dot));
-      if (lane + 32 < K) atomicAdd(&ds_s[at.rel1], at.p1 * (dp1 - dot));
     }
-    __syncwarp();
   }
   if (BWD) {
     __syncthreads();
-    for (int i = tid; i < a.n_rel; i += LEAF_NT)
-      if (ds_s[i] != 0.f) atomicAdd(a.ds + i, ds_s[i]);
+    for (int i = tid; i < a.n_rel; i += LEAF_NT) {
+      float s = 0.f;
+      for (int w = 0; w < NWH; ++w) s += ds_s[w * a.n_rel + i];
+      if (s != 0.f) atomicAdd(a.ds + i, s);
+    }
   }
 }
 
@@ -903,13 +1016,11 @@ __global__ void __launch_bounds__(TC<D>::NT) dw_kernel(DwArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* As = smem;
   float* Gs = As + C::R * C::LD;
-  float* red = Gs + C::R * C::LD;
   const int tid = threadIdx.x, tx = tid % C::LPR, ty = tid / C::LPR;
   const int grp = blockIdx.y;
   const float* A = a.A[grp];
   const long lda = a.lda[grp];
   const bool do_bias = (grp == 0 && a.db != nullptr);
-  if (tid < D) red[tid] = 0.f;
   float dw[C::DWN][4];
 #pragma unroll
   for (int i = 0; i < C::DWN; ++i) dw[i][0] = dw[i][1] = dw[i][2] = dw[i][3] = 0.f;
@@ -933,10 +1044,10 @@ __global__ void __launch_bounds__(TC<D>::NT) dw_kernel(DwArgs a) {
     __syncthreads();
   }
   dw_flush<D>(dw, a.dW[grp], ty, tx);
-  if (do_bias) bias_flush<D>(bpart, red, a.db, tid, tx);
+  if (do_bias) bias_flush<D>(bpart, As, a.db, tid);
 }
 
 template <int D>
-constexpr size_t dw_smem() { return sizeof(float) * (2 * TC<D>::R * TC<D>::LD + D); }
+constexpr size_t dw_smem() { return sizeof(float) * (2 * TC<D>::R * TC<D>::LD); }
 
 }  // namespace mvin

@@ -107,6 +107,7 @@ struct mvin_handle_s {
   cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
   bool use_streams = true;
   int entity_leaf_mode = -1;       // -1 auto, 0 off, 1 on (env MVIN_B200_ENTITY_LEAF, read in mvin_create)
+  int max_ctas_per_sm = 4;         // cap on resident CTAs per SM of the persistent row kernels (env MVIN_B200_CTAS_PER_SM)
   bool prof_on = false;
   struct ProfRec { const char* name; cudaEvent_t ev; };
   std::vector<ProfRec> prof;
@@ -264,24 +265,41 @@ int set_smem(KernelT k, size_t bytes) {
   return MVIN_OK;
 }
 
-// CTAs per SM to aim for, from the kernel's shared-memory footprint
-int ctas_per_sm(size_t smem_bytes, int threads) {
-  int by_smem = (int)((220 * 1024) / (smem_bytes + 1024));
-  int by_thr = 2048 / threads;
-  int n = by_smem < by_thr ? by_smem : by_thr;
-  return n < 1 ? 1 : (n > 8 ? 8 : n);
+// Resident CTAs per SM of a kernel at a given dynamic shared-memory size (registers, threads and shared memory all
+// taken into account by the occupancy calculator), capped by the handle's limit: the row kernels are persistent, so
+// CTAs beyond the resident set only add prologue / epilogue work (weight loads, dW flushes).
+template <typename KernelT>
+int resident_ctas(mvin_handle_t h, KernelT k, int threads, size_t smem_bytes) {
+  struct Key { const void* f; size_t s; int n; };
+  static thread_local std::vector<Key> cache;
+  for (const Key& e : cache)
+    if (e.f == (const void*)k && e.s == smem_bytes) return e.n < h->max_ctas_per_sm ? e.n : h->max_ctas_per_sm;
+  int n = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, threads, smem_bytes) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    n = 1;
+  }
+  cache.push_back({(const void*)k, smem_bytes, n});
+  return n < h->max_ctas_per_sm ? n : h->max_ctas_per_sm;
 }
 
-// Split a grid of at most `cap` CTAs between levels in proportion to their tile counts (>= 1 CTA per level); a
-// level never gets more CTAs than tiles.  Returns the grid size and fills cta_end[].
-int partition_grid(const long* rows, int nlev, int cap, int* cta_end) {
+// Split a grid of at most `cap` CTAs between levels in proportion to their tile counts (>= 1 CTA per level), then
+// shrink each level's share so that all its CTAs walk the same number of tiles (+-1).  Returns the grid size and
+// fills cta_end[].
+int partition_grid(const long* rows, int nlev, int tile_rows, int cap, int* cta_end) {
   long tiles[MAX_LV], tot = 0;
-  for (int l = 0; l < nlev; ++l) { tiles[l] = (rows[l] + 63) / 64; if (tiles[l] < 1) tiles[l] = 1; tot += tiles[l]; }
+  for (int l = 0; l < nlev; ++l) {
+    tiles[l] = (rows[l] + tile_rows - 1) / tile_rows;
+    if (tiles[l] < 1) tiles[l] = 1;
+    tot += tiles[l];
+  }
   int end = 0;
   for (int l = 0; l < nlev; ++l) {
     long n = tot <= cap ? tiles[l] : (long)((double)cap * (double)tiles[l] / (double)tot);
     if (n < 1) n = 1;
     if (n > tiles[l]) n = tiles[l];
+    const long rounds = (tiles[l] + n - 1) / n;
+    n = (tiles[l] + rounds - 1) / rounds;
     end += (int)n;
     cta_end[l] = end;
   }
@@ -339,7 +357,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
       a.n_entity = c.n_entity; a.K = K; a.n_rel = nr;
       const size_t sm = leaf_entity_smem(nr);
       if ((rc = set_smem(leaf_entity_kernel<D, false>, sm))) return rc;
-      const long want = ((long)c.n_entity + LEAF_NW - 1) / LEAF_NW;
+      const long want = ((long)c.n_entity + LEAF_NW * 32 - 1) / (LEAF_NW * 32);
       const long cap = (long)h->sm_count * 8;
       leaf_entity_kernel<D, false><<<(unsigned)(want < cap ? want : cap), LEAF_NT, sm, st>>>(a);
       LAUNCH_CHECK(h, "leaf_entity_fwd");
@@ -392,13 +410,13 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
       t.rows = rows[lv] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
     }
     a.nlev = H; a.E = h->etab; a.u = at<float>(ws, L.u);
-    const int grid = partition_grid(rows, H, h->sm_count * ctas_per_sm(sm, C::NT), a.cta_end);
+    const int grid = partition_grid(rows, H, C::R, h->sm_count * resident_ctas(h, transform_fwd_kernel<D>, C::NT, sm), a.cta_end);
     transform_fwd_kernel<D><<<grid, C::NT, sm, st>>>(a);
     LAUNCH_CHECK(h, "transform_fwd");
   }
   // aggregation iterations (model.py:286-307): one launch per iteration, every level of it
   {
-    const size_t sm_leaf = agg_fwd_smem<D, true>(nr), sm_in = agg_fwd_smem<D, false>(nr);
+    const size_t sm_leaf = agg_fwd_smem<D, true>(K, nr), sm_in = agg_fwd_smem<D, false>(K, nr);
     if ((rc = set_smem(agg_fwd_kernel<D, true>, sm_leaf))) return rc;
     if ((rc = set_smem(agg_fwd_kernel<D, false>, sm_in))) return rc;
     static const char* names[MAX_L] = {"agg_fwd_0", "agg_fwd_1", "agg_fwd_2"};
@@ -425,10 +443,10 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
         a.E = h->etab; a.u = at<float>(ws, L.u);
         a.Se = L.entity_leaf ? at<float>(ws, L.Se) : nullptr;
         a.Wt = P.transfer_w + (long)H * D * D; a.bt = P.transfer_b + (long)H * D;
-        const int grid = partition_grid(rows, nlev, h->sm_count * ctas_per_sm(sm_leaf, C::NT), a.cta_end);
+        const int grid = partition_grid(rows, nlev, C::R, h->sm_count * resident_ctas(h, agg_fwd_kernel<D, true>, C::NT, sm_leaf), a.cta_end);
         agg_fwd_kernel<D, true><<<grid, C::NT, sm_leaf, st>>>(a);
       } else {
-        const int grid = partition_grid(rows, nlev, h->sm_count * ctas_per_sm(sm_in, C::NT), a.cta_end);
+        const int grid = partition_grid(rows, nlev, C::R, h->sm_count * resident_ctas(h, agg_fwd_kernel<D, false>, C::NT, sm_in), a.cta_end);
         agg_fwd_kernel<D, false><<<grid, C::NT, sm_in, st>>>(a);
       }
       LAUNCH_CHECK(h, names[i]);
@@ -566,7 +584,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
   }
   // aggregation iterations, reversed; one launch per iteration
   {
-    const size_t sm_leaf = agg_bwd_smem<D, true>(nr), sm_in = agg_bwd_smem<D, false>(nr);
+    const size_t sm_leaf = agg_bwd_smem<D, true>(K, nr), sm_in = agg_bwd_smem<D, false>(K, nr);
     if ((rc = set_smem(agg_bwd_kernel<D, true>, sm_leaf))) return rc;
     if ((rc = set_smem(agg_bwd_kernel<D, false>, sm_in))) return rc;
     static const char* names[MAX_L] = {"agg_bwd_0", "agg_bwd_1", "agg_bwd_2"};
@@ -602,10 +620,10 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
         a.dWt = G.transfer_w + (long)H * D * D; a.dbt = G.transfer_b + (long)H * D;
         a.dE = h->gtab; a.du = du;
         a.GSe = L.entity_leaf ? at<float>(ws, L.GSe) : nullptr;
-        const int grid = partition_grid(rows, nlev, h->sm_count * ctas_per_sm(sm_leaf, C::NT), a.cta_end);
+        const int grid = partition_grid(rows, nlev, C::R, h->sm_count * resident_ctas(h, agg_bwd_kernel<D, true>, C::NT, sm_leaf), a.cta_end);
         agg_bwd_kernel<D, true><<<grid, C::NT, sm_leaf, st>>>(a);
       } else {
-        const int grid = partition_grid(rows, nlev, h->sm_count * ctas_per_sm(sm_in, C::NT), a.cta_end);
+        const int grid = partition_grid(rows, nlev, C::R, h->sm_count * resident_ctas(h, agg_bwd_kernel<D, false>, C::NT, sm_in), a.cta_end);
         agg_bwd_kernel<D, false><<<grid, C::NT, sm_in, st>>>(a);
       }
       LAUNCH_CHECK(h, names[i]);
@@ -624,7 +642,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     a.n_entity = c.n_entity; a.K = K; a.n_rel = nr;
     const size_t sm = leaf_entity_smem(nr);
     if ((rc = set_smem(leaf_entity_kernel<D, true>, sm))) return rc;
-    const long want = ((long)c.n_entity + LEAF_NW - 1) / LEAF_NW;
+    const long want = ((long)c.n_entity + LEAF_NW * 32 - 1) / (LEAF_NW * 32);
     const long cap = (long)h->sm_count * 8;
     leaf_entity_kernel<D, true><<<(unsigned)(want < cap ? want : cap), LEAF_NT, sm, st>>>(a);
     LAUNCH_CHECK(h, "leaf_entity_bwd");
@@ -650,7 +668,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
       t.rows = rows[q] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
     }
     a.nlev = H; a.E = h->etab; a.u = at<float>(ws, L.u); a.dE = h->gtab; a.du = du;
-    const int grid = partition_grid(rows, H, h->sm_count * ctas_per_sm(sm, C::NT), a.cta_end);
+    const int grid = partition_grid(rows, H, C::R, h->sm_count * resident_ctas(h, transform_bwd_kernel<D>, C::NT, sm), a.cta_end);
     transform_bwd_kernel<D><<<grid, C::NT, sm, st>>>(a);
     LAUNCH_CHECK(h, "transform_bwd");
   }
@@ -791,6 +809,7 @@ int mvin_create(const mvin_config_t* cfg, mvin_handle_t* out) {
     }
   }
   if (const char* ev = getenv("MVIN_B200_ENTITY_LEAF")) h->entity_leaf_mode = atoi(ev) != 0 ? 1 : 0;
+  if (const char* ev = getenv("MVIN_B200_CTAS_PER_SM")) { const int n = atoi(ev); if (n >= 1 && n <= 32) h->max_ctas_per_sm = n; }
   if (cudaMalloc(&h->d_shard_tab, sizeof(void*) * 2 * MAX_SHARDS) != cudaSuccess) {
     delete h;
     return fail(MVIN_ERR_CUDA, "cudaMalloc(shard table): %s", cudaGetErrorString(cudaGetLastError()));
