@@ -8,8 +8,8 @@
 //
 // Layout: every activation buffer is row-major [rows, D] fp32 with rows = B * K^h (pair-major, child k of node
 // j at row j*K+k, model.py:251).  A launch carries up to MAX_LV level descriptors; the grid is partitioned
-// between the levels (cta_end[]), each CTA owns tiles of R consecutive rows of ONE level and walks them
-// persistently; the d x d weights live in shared memory for the CTA's lifetime.  Three phases per tile:
+// between the levels (transform kernels) or pulls tiles of R consecutive rows from a shared list (aggregator
+// kernels) and walks them persistently; the d x d weights live in shared memory for the CTA's lifetime.  Three phases per tile:
 //   * "stage" (warp per row, all rows of the warp in flight): read the node's packed adjacency record (K ids + K
 //     relation ids, contiguous), K-softmax with shuffles, park (p_k, id_k[, rel_k]) in shared memory.
 //   * "neighbour" (thread-mapped: LPR = D/4 lanes x 16 B cover one row, thread (ty, tx) owns row ty*TM+i and
@@ -30,7 +30,7 @@ constexpr int MAX_LV = 3;
 template <int D>
 struct TC {
   static constexpr int LPR = D / 4;                                   // float4 lanes per row
-  static constexpr int NT = (D >= 64) ? 512 : (D >= 16) ? 256 : 128;  // threads per CTA
+  static constexpr int NT = (D >= 128) ? 512 : (D >= 16) ? 256 : 128; // threads per CTA
   static constexpr int NTY = NT / LPR;                                // thread rows of the register tile
   static constexpr int R = (D >= 32) ? 32 : 64;                       // rows per tile
   static constexpr int TM = R / NTY;                                  // rows per thread
@@ -71,6 +71,28 @@ MVIN_DEV CtaSlice cta_slice(const int* cta_end, int nlev) {
   s.local = (int)blockIdx.x - begin;
   s.count = cta_end[l] - begin;
   return s;
+}
+
+// Dynamic tile scheduler of the aggregator kernels.  The levels of one launch have very different costs per tile
+// (an inner level streams K child rows per row, the per-entity leaf mode streams none), so tiles are not assigned
+// statically: the launch's tiles form one list (levels in the order given, heaviest first) and every CTA pulls the
+// next index from a global counter.  The counter pair lives in the handle, starts at {0, 0} and is reset by the
+// last CTA to leave, so no memset is needed between launches.
+struct TileList {
+  long tile_end[MAX_LV];   // cumulative tile counts of the levels
+  int nlev;
+  int* ctr;                // [2] {next tile, CTAs finished}
+};
+MVIN_DEV int sched_next(const TileList& tl) { return atomicAdd(tl.ctr, 1); }
+MVIN_DEV void sched_exit(const TileList& tl) {
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(tl.ctr + 1, 1) == (int)gridDim.x - 1) {
+      tl.ctr[0] = 0;
+      tl.ctr[1] = 0;
+      __threadfence();
+    }
+  }
 }
 
 // acc[i][0..3] += sum_k As[(ty*TM+i)][k] * Ws[k][tx*4 .. tx*4+3]
@@ -504,8 +526,7 @@ struct AggLevel {
 };
 struct AggArgs {
   AggLevel lv[MAX_LV];
-  int nlev;
-  int cta_end[MAX_LV];
+  TileList tl;
   const int32_t* adj;   // packed adjacency [n_entity][2][K]
   const float* s;       // [n_rel] relation scores of this aggregator
   ETab E;               // leaf: entity table
@@ -549,22 +570,28 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
                                         AggSmem<D>::align16(sizeof(int2) * C::R * KP));
   const int tid = threadIdx.x, tx = tid % C::LPR, ty = tid / C::LPR;
   const int warp = tid / 32, lane = tid % 32;
-  const CtaSlice cs = cta_slice(a.cta_end, a.nlev);
-  const AggLevel& L = a.lv[cs.level];
-  const bool leaf = HAS_LEAF && L.leaf;
-  const bool ent_mode = leaf && a.Se != nullptr;
+  __shared__ int sched[2];
+  if (tid == 0) sched[0] = sched_next(a.tl);
   load_weight<D>(Wa_s, a.Wa, tid);
-  if (leaf) load_weight<D>(Wt_s, a.Wt, tid);
+  if (HAS_LEAF) load_weight<D>(Wt_s, a.Wt, tid);
   for (int i = tid; i < a.n_rel; i += C::NT) s_s[i] = a.s[i];
   const float4 ba = ldg4(a.ba + tx * 4);
   float4 bt = f4zero();
-  if (leaf) bt = ldg4(a.bt + tx * 4);
+  if (HAS_LEAF) bt = ldg4(a.bt + tx * 4);
   const float invK = 1.f / (float)K;
   __syncthreads();
 
-  const long ntiles = (L.rows + C::R - 1) / C::R;
-  for (long t = cs.local; t < ntiles; t += cs.count) {
-    const long row0 = t * C::R;
+  for (int it = 0;; ++it) {
+    const long t = sched[it & 1];
+    if (t >= a.tl.tile_end[a.tl.nlev - 1]) break;
+    int nxt = 0;
+    if (tid == 0) nxt = sched_next(a.tl);                    // consumed at the end of this tile
+    int lvl = 0;
+    while (t >= a.tl.tile_end[lvl]) ++lvl;
+    const AggLevel& L = a.lv[lvl];
+    const bool leaf = HAS_LEAF && L.leaf;
+    const bool ent_mode = leaf && a.Se != nullptr;
+    const long row0 = (t - (lvl ? a.tl.tile_end[lvl - 1] : 0)) * C::R;
     // ---- stage phase: (p_k, id_k) of every row of the tile ----
     if (!ent_mode) {
       stage_tile<D, false>(L.ent, a.adj, s_s, row0, L.rows, K, KP, nb_s, nullptr, warp, lane);
@@ -638,8 +665,10 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
         st4(L.V + row * D + tx * 4, make_float4(fmaxf(acc[i][0], 0.f), fmaxf(acc[i][1], 0.f), fmaxf(acc[i][2], 0.f),
                                                 fmaxf(acc[i][3], 0.f)));
     }
+    if (tid == 0) sched[(it + 1) & 1] = nxt;
     __syncthreads();
   }
+  sched_exit(a.tl);
 }
 
 template <int D, bool HAS_LEAF>
@@ -674,8 +703,7 @@ struct AggBwdLevel {
 };
 struct AggBwdArgs {
   AggBwdLevel lv[MAX_LV];
-  int nlev;
-  int cta_end[MAX_LV];
+  TileList tl;
   const int32_t* adj;
   const float* s;
   ETab E;               // leaf
@@ -710,12 +738,10 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
   const int NWH = AggSmem<D>::ds_copies(a.n_rel);
   const int tid = threadIdx.x, tx = tid % C::LPR, ty = tid / C::LPR;
   const int warp = tid / 32, lane = tid % 32;
-  const CtaSlice cs = cta_slice(a.cta_end, a.nlev);
-  const AggBwdLevel& L = a.lv[cs.level];
-  const bool leaf = HAS_LEAF && L.leaf;
-  const bool ent_mode = leaf && a.GSe != nullptr;
+  __shared__ int sched[2];
+  if (tid == 0) sched[0] = sched_next(a.tl);
   load_weight<D>(Wa_s, a.WaT, tid);
-  if (leaf) load_weight<D>(Wt_s, a.WtT, tid);
+  if (HAS_LEAF) load_weight<D>(Wt_s, a.WtT, tid);
   for (int i = tid; i < a.n_rel; i += C::NT) s_s[i] = a.s[i];
   for (int i = tid; i < NWH * a.n_rel; i += C::NT) ds_s[i] = 0.f;
   const float invK = 1.f / (float)K;
@@ -726,11 +752,21 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
 #pragma unroll
   for (int i = 0; i < (HAS_LEAF ? C::DWN : 1); ++i) dwt[i][0] = dwt[i][1] = dwt[i][2] = dwt[i][3] = 0.f;
   float4 bpa = f4zero(), bpt = f4zero();
+  bool had_leaf = false;
   __syncthreads();
 
-  const long ntiles = (L.rows + C::R - 1) / C::R;
-  for (long t = cs.local; t < ntiles; t += cs.count) {
-    const long row0 = t * C::R;
+  for (int it = 0;; ++it) {
+    const long t = sched[it & 1];
+    if (t >= a.tl.tile_end[a.tl.nlev - 1]) break;
+    int nxt = 0;
+    if (tid == 0) nxt = sched_next(a.tl);                    // consumed at the end of this tile
+    int lvl = 0;
+    while (t >= a.tl.tile_end[lvl]) ++lvl;
+    const AggBwdLevel& L = a.lv[lvl];
+    const bool leaf = HAS_LEAF && L.leaf;
+    const bool ent_mode = leaf && a.GSe != nullptr;
+    had_leaf |= leaf;
+    const long row0 = (t - (lvl ? a.tl.tile_end[lvl - 1] : 0)) * C::R;
     // ---- stage phase (its loads overlap the tile loads below) ----
     if (!ent_mode) stage_tile<D, true>(L.ent, a.adj, s_s, row0, L.rows, K, KP, nb_s, rel_s, warp, lane);
 #pragma unroll
@@ -857,6 +893,7 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
         }
       }
     }
+    if (tid == 0) sched[(it + 1) & 1] = nxt;
     __syncthreads();
   }
   for (int i = tid; i < a.n_rel; i += C::NT) {
@@ -866,10 +903,13 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
   }
   dw_flush<D>(dwa, a.dWa, ty, tx);
   bias_flush<D>(bpa, Gs, a.dba, tid);
-  if (leaf) {
-    if constexpr (HAS_LEAF) dw_flush<D>(dwt, a.dWt, ty, tx);
-    bias_flush<D>(bpt, Gs, a.dbt, tid);
+  if constexpr (HAS_LEAF) {
+    if (had_leaf) {                                          // CTA-uniform
+      dw_flush<D>(dwt, a.dWt, ty, tx);
+      bias_flush<D>(bpt, Gs, a.dbt, tid);
+    }
   }
+  sched_exit(a.tl);
 }
 
 template <int D, bool HAS_LEAF>

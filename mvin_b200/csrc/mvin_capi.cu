@@ -100,6 +100,7 @@ struct mvin_handle_s {
   int n_shards = 1;
   long n_local_rows = 0;           // rows of the local entity shard
   void** d_shard_tab = nullptr;    // device array [2][MAX_SHARDS] of shard base pointers (allocated in mvin_create)
+  int* d_sched = nullptr;          // tile-scheduler counter pairs of the aggregator kernels (level.cuh), zero between launches
   int global_batch = 0;            // 0: the batch of the call
   float dense_l2_scale = 1.f;
   // fork/join helpers: independent kernels of a step run on two internal side streams (disabled while profiling)
@@ -306,6 +307,18 @@ int partition_grid(const long* rows, int nlev, int tile_rows, int cap, int* cta_
   return end;
 }
 
+// Tile list of one aggregator launch (level.cuh, TileList): returns the grid size (every CTA is resident).
+int make_tile_list(TileList& tl, const long* rows, int nlev, int tile_rows, int cap, int* ctr) {
+  long end = 0;
+  for (int l = 0; l < nlev; ++l) {
+    end += (rows[l] + tile_rows - 1) / tile_rows;
+    tl.tile_end[l] = end;
+  }
+  tl.nlev = nlev;
+  tl.ctr = ctr;
+  return (int)(end < cap ? end : cap);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------
@@ -425,9 +438,10 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
       memset(&a, 0, sizeof(a));
       long rows[MAX_LV];
       const int nlev = H - i;
-      // biggest level first: its CTAs are scheduled first
+      // tile order: the levels with the most expensive tiles first (the per-entity leaf mode has the cheapest)
+      const bool leaf_last = (i == 0 && L.entity_leaf);
       for (int q = 0; q < nlev; ++q) {
-        const int lv = nlev - 1 - q;
+        const int lv = leaf_last ? q : nlev - 1 - q;
         AggLevel& t = a.lv[q];
         t.ent = at<int32_t>(ws, L.ent[lv]);
         t.self = at<float>(ws, L.V[i][lv]);
@@ -436,17 +450,19 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
         t.leaf = (i == 0 && lv == H - 1);
         if (t.leaf) t.SU = at<float>(ws, L.SU); else t.child = at<float>(ws, L.V[i][lv + 1]);
       }
-      a.nlev = nlev; a.adj = h->adj; a.s = at<float>(ws, L.s) + (long)i * nr;
+      a.adj = h->adj; a.s = at<float>(ws, L.s) + (long)i * nr;
       a.Wa = P.agg_w + (long)i * D * D; a.ba = P.agg_b + (long)i * D;
       a.K = K; a.n_rel = nr;
       if (i == 0) {
         a.E = h->etab; a.u = at<float>(ws, L.u);
         a.Se = L.entity_leaf ? at<float>(ws, L.Se) : nullptr;
         a.Wt = P.transfer_w + (long)H * D * D; a.bt = P.transfer_b + (long)H * D;
-        const int grid = partition_grid(rows, nlev, C::R, h->sm_count * resident_ctas(h, agg_fwd_kernel<D, true>, C::NT, sm_leaf), a.cta_end);
+        const int grid = make_tile_list(a.tl, rows, nlev, C::R,
+                                        h->sm_count * resident_ctas(h, agg_fwd_kernel<D, true>, C::NT, sm_leaf), h->d_sched);
         agg_fwd_kernel<D, true><<<grid, C::NT, sm_leaf, st>>>(a);
       } else {
-        const int grid = partition_grid(rows, nlev, C::R, h->sm_count * resident_ctas(h, agg_fwd_kernel<D, false>, C::NT, sm_in), a.cta_end);
+        const int grid = make_tile_list(a.tl, rows, nlev, C::R,
+                                        h->sm_count * resident_ctas(h, agg_fwd_kernel<D, false>, C::NT, sm_in), h->d_sched);
         agg_fwd_kernel<D, false><<<grid, C::NT, sm_in, st>>>(a);
       }
       LAUNCH_CHECK(h, names[i]);
@@ -593,8 +609,9 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
       memset(&a, 0, sizeof(a));
       long rows[MAX_LV];
       const int nlev = H - i;
+      const bool leaf_last = (i == 0 && L.entity_leaf);
       for (int q = 0; q < nlev; ++q) {
-        const int lv = nlev - 1 - q;
+        const int lv = leaf_last ? q : nlev - 1 - q;
         AggBwdLevel& t = a.lv[q];
         t.ent = at<int32_t>(ws, L.ent[lv]);
         t.V = at<float>(ws, L.V[i + 1][lv]); t.Y = at<float>(ws, L.Y[i][lv]);
@@ -610,7 +627,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
           t.dchild = at<float>(ws, L.DC[i][lv + 1]);
         }
       }
-      a.nlev = nlev; a.adj = h->adj; a.s = at<float>(ws, L.s) + (long)i * nr;
+      a.adj = h->adj; a.s = at<float>(ws, L.s) + (long)i * nr;
       a.WaT = wT + (long)i * D * D;
       a.dWa = G.agg_w + (long)i * D * D; a.dba = G.agg_b + (long)i * D;
       a.ds = at<float>(ws, L.ds) + (long)i * nr;
@@ -620,10 +637,12 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
         a.dWt = G.transfer_w + (long)H * D * D; a.dbt = G.transfer_b + (long)H * D;
         a.dE = h->gtab; a.du = du;
         a.GSe = L.entity_leaf ? at<float>(ws, L.GSe) : nullptr;
-        const int grid = partition_grid(rows, nlev, C::R, h->sm_count * resident_ctas(h, agg_bwd_kernel<D, true>, C::NT, sm_leaf), a.cta_end);
+        const int grid = make_tile_list(a.tl, rows, nlev, C::R,
+                                        h->sm_count * resident_ctas(h, agg_bwd_kernel<D, true>, C::NT, sm_leaf), h->d_sched + 2);
         agg_bwd_kernel<D, true><<<grid, C::NT, sm_leaf, st>>>(a);
       } else {
-        const int grid = partition_grid(rows, nlev, C::R, h->sm_count * resident_ctas(h, agg_bwd_kernel<D, false>, C::NT, sm_in), a.cta_end);
+        const int grid = make_tile_list(a.tl, rows, nlev, C::R,
+                                        h->sm_count * resident_ctas(h, agg_bwd_kernel<D, false>, C::NT, sm_in), h->d_sched + 2);
         agg_bwd_kernel<D, false><<<grid, C::NT, sm_in, st>>>(a);
       }
       LAUNCH_CHECK(h, names[i]);
@@ -810,9 +829,11 @@ int mvin_create(const mvin_config_t* cfg, mvin_handle_t* out) {
   }
   if (const char* ev = getenv("MVIN_B200_ENTITY_LEAF")) h->entity_leaf_mode = atoi(ev) != 0 ? 1 : 0;
   if (const char* ev = getenv("MVIN_B200_CTAS_PER_SM")) { const int n = atoi(ev); if (n >= 1 && n <= 32) h->max_ctas_per_sm = n; }
-  if (cudaMalloc(&h->d_shard_tab, sizeof(void*) * 2 * MAX_SHARDS) != cudaSuccess) {
+  if (cudaMalloc(&h->d_shard_tab, sizeof(void*) * 2 * MAX_SHARDS) != cudaSuccess ||
+      cudaMalloc(&h->d_sched, sizeof(int) * 16) != cudaSuccess ||
+      cudaMemset(h->d_sched, 0, sizeof(int) * 16) != cudaSuccess) {
     delete h;
-    return fail(MVIN_ERR_CUDA, "cudaMalloc(shard table): %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(MVIN_ERR_CUDA, "cudaMalloc(shard table / scheduler counters): %s", cudaGetErrorString(cudaGetLastError()));
   }
   *out = h;
   return MVIN_OK;
@@ -820,6 +841,7 @@ int mvin_create(const mvin_config_t* cfg, mvin_handle_t* out) {
 
 int mvin_destroy(mvin_handle_t h) {
   if (h && h->d_shard_tab) cudaFree(h->d_shard_tab);
+  if (h && h->d_sched) cudaFree(h->d_sched);
   for (int i = 0; h && i < 2; ++i) {
     if (h->side[i]) cudaStreamDestroy(h->side[i]);
     if (h->ev_fork[i]) cudaEventDestroy(h->ev_fork[i]);
