@@ -45,6 +45,16 @@ __global__ void copy_i64_kernel(const int64_t* __restrict__ src, long n, int64_t
   if (i < n) dst[i] = src[i];
 }
 
+// ---- seeds: ent[0] = item as int32 (model.py:243-256 starts from item_indices); optional stamps -------------
+__global__ void seed_kernel(const int64_t* __restrict__ item, int B, int32_t* __restrict__ ent0,
+                            int32_t* __restrict__ stamp) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const long e = item[b];
+  ent0[b] = (int32_t)e;
+  if (stamp) stamp[e] = 1;
+}
+
 // ---- seeds: ent[0] = item (int32) and Vbuf = E[item]  (model.py:199) -----------------------------------
 template <int D>
 __global__ void prep_items_kernel(const int64_t* __restrict__ item, ETab E, int B,

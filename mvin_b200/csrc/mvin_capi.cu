@@ -17,7 +17,7 @@
 #include "gemm.cuh"
 #include "level.cuh"
 #include "misc.cuh"
-#include "ripple.cuh"
+#include "user.cuh"
 
 using namespace mvin;
 
@@ -63,15 +63,16 @@ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 //   DS[j][h]  gradient of V[j][h] arriving from its own aggregator step (iteration j, level h)
 struct Layout {
   size_t ent[MAX_L];                      // int32 [B K^h], h < L
-  size_t Vbuf, Q, probs, O, u, s;         // ripple side + relation scores
+  size_t Vbuf, Q, probs, O, u, s;         // user side + relation scores
   size_t SU;                              // leaf: S + u
   size_t Y[MAX_L][MAX_L];                 // Y[i][h], i < H, h < H - i
   size_t V[MAX_L + 1][MAX_L];             // V[j][h]
   size_t item, scores;
   // backward
   size_t DC[MAX_L + 1][MAX_L], DS[MAX_L][MAX_L];
-  size_t du, ditem, dO, dv, wT;           // wT: [H + H + 1][D][D] transposed weights
-  size_t zero_begin, dQ, ds, cnt, acc, GSe, zero_end;   // region cleared at the start of every backward
+  size_t du, ditem, dO, wT;               // wT: [H + H + 1][D][D] transposed weights
+  size_t zero_begin, ds, cnt, acc, zero_mid, dQ, dv, GSe, zero_end;   // cleared at the start of every backward:
+                                          // [begin, mid) on the launch stream, [mid, end) on a side stream
   size_t stamp, Se;                       // entity mode of the leaf level (stamp is cleared by every forward)
   bool entity_leaf;
   size_t total;
@@ -108,6 +109,7 @@ struct mvin_handle_s {
   cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
   bool use_streams = true;
   int entity_leaf_mode = -1;       // -1 auto, 0 off, 1 on (env MVIN_B200_ENTITY_LEAF, read in mvin_create)
+  int user_pb_fwd = 4;             // max pairs per CTA of the user-side forward kernel (env MVIN_B200_USER_PB_FWD)
   int max_ctas_per_sm = 4;         // cap on resident CTAs per SM of the persistent row kernels (env MVIN_B200_CTAS_PER_SM)
   bool prof_on = false;
   struct ProfRec { const char* name; cudaEvent_t ev; };
@@ -202,11 +204,12 @@ Layout make_layout(const mvin_config_t& c, long B, bool entity_leaf) {
   L.dO = take(f * B * (p + 1) * D);
   L.wT = take(f * (2 * H + 1) * D * D);
   L.zero_begin = off;
-  L.dQ = take(f * B * nr * D);
-  L.dv = take(f * B * D);
   L.ds = take(f * H * nr);
   L.cnt = take(f * nr);
   L.acc = take(f * 8);
+  L.zero_mid = off;
+  L.dQ = take(f * B * nr * D);
+  L.dv = take(f * B * D);
   if (entity_leaf) L.GSe = take(f * (size_t)c.n_entity * D);
   L.zero_end = off;
   if (entity_leaf) {
@@ -333,21 +336,16 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
   int rc;
   prof_mark(h, st, nullptr);
 
-  // seeds + integer expansion (model.py:243-256); level L ids are never materialised
-  int32_t* stamp = L.entity_leaf ? at<int32_t>(ws, L.stamp) : nullptr;
-  if (stamp) CUDA_TRY(cudaMemsetAsync(stamp, 0, sizeof(int32_t) * (size_t)c.n_entity, st));
-  {
-    const long n = (long)B * C::LPR;
-    prep_items_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(item, h->etab, B, at<int32_t>(ws, L.ent[0]),
-                                                                      at<float>(ws, L.Vbuf), H == 1 ? stamp : nullptr);
-    LAUNCH_CHECK(h, "prep_items");
-  }
-  // side stream: integer expansion, relation scores and the per-entity leaf aggregate are independent of the
-  // ripple chain (Q -> ripple attention -> user_o) that runs on the launch stream meanwhile
+  // side stream: integer expansion (model.py:243-256; level L ids are never materialised), relation scores and the
+  // per-entity leaf aggregate are independent of the user side that runs on the launch stream meanwhile
   const Par par{h, st, h->use_streams && !h->prof_on};
+  int32_t* stamp = L.entity_leaf ? at<int32_t>(ws, L.stamp) : nullptr;
   par.fork(0);
   {
     cudaStream_t st = par.s(0);
+    if (stamp) CUDA_TRY(cudaMemsetAsync(stamp, 0, sizeof(int32_t) * (size_t)c.n_entity, st));
+    seed_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(item, B, at<int32_t>(ws, L.ent[0]), H == 1 ? stamp : nullptr);
+    LAUNCH_CHECK(h, "seed");
     for (int lv = 0; lv + 1 < H; ++lv) {
       const long n = L.rows[lv] * K;
       expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(at<int32_t>(ws, L.ent[lv]), h->adj, L.rows[lv], K,
@@ -376,36 +374,35 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
       LAUNCH_CHECK(h, "leaf_entity_fwd");
     }
   }
-  // Q[b, r, :] = RK[r]^T v_b      (model.py:211-220 refactored)
-  if (p > 0) {
-    GemmArgs g = gemm_args();
-    g.A = at<float>(ws, L.Vbuf); g.sa_m = D; g.sa_k = 1; g.bsA = 0;
-    g.B = P.relation_kge; g.sb_k = D; g.sb_n = 1; g.bsB = (long)D * D;
-    g.C = at<float>(ws, L.Q); g.ldc = (long)nr * D; g.bsC = D;
-    g.M = B; g.N = D; g.K = D; g.nbatch = nr;
-    if ((rc = run_gemm(h, st, g, "gemm_q"))) return rc;
-  }
-  // ripple attention (model.py:162-229)
+  // the user side in one launch: seeds v = E[item], Q = RK^T v, ripple attention, user MLP -> user_o
+  // (model.py:125-134, :161-240)
   {
-    RippleArgs a;
-    a.E = h->etab; a.Q = at<float>(ws, L.Q); a.w_hi = P.h_item_w;
+    UserArgs a;
+    memset(&a, 0, sizeof(a));
+    a.E = h->etab; a.item = item; a.RK = P.relation_kge; a.w_hi = P.h_item_w;
+    a.W_user = P.user_mlp_w; a.b_user = P.user_mlp_b;
     a.mem_h = mem_h; a.mem_r = mem_r; a.mem_t = mem_t;
-    a.probs = at<float>(ws, L.probs); a.O = at<float>(ws, L.O);
+    a.Vbuf = at<float>(ws, L.Vbuf); a.Q = at<float>(ws, L.Q); a.probs = at<float>(ws, L.probs);
+    a.O = at<float>(ws, L.O); a.u = at<float>(ws, L.u);
     a.B = B; a.m = m; a.p = p; a.n_rel = nr;
-    const size_t sm = ripple_fwd_smem(m);
-    if ((rc = set_smem(ripple_fwd_kernel<D>, sm))) return rc;
-    const long warps = (long)B * (p + 1);
-    ripple_fwd_kernel<D><<<(unsigned)((warps + RIPPLE_NW - 1) / RIPPLE_NW), RIPPLE_NT, sm, st>>>(a);
-    LAUNCH_CHECK(h, "ripple_fwd");
-  }
-  // user_o = O . W_user + b      (model.py:232-234)
-  {
-    GemmArgs g = gemm_args();
-    g.A = at<float>(ws, L.O); g.sa_m = (long)(p + 1) * D; g.sa_k = 1;
-    g.B = P.user_mlp_w; g.sb_k = D; g.sb_n = 1;
-    g.C = at<float>(ws, L.u); g.ldc = D; g.bias = P.user_mlp_b;
-    g.M = B; g.N = D; g.K = (p + 1) * D;
-    if ((rc = run_gemm(h, st, g, "gemm_user"))) return rc;
+    const int PB = user_pairs_per_cta(D, nr, p, m, h->user_pb_fwd);
+    const size_t sm = user_fwd_smem(D, PB, nr, p, m);
+    const int nt = 32 * user_warps(PB, p);
+    const unsigned grid = (unsigned)((B + PB - 1) / PB);
+    switch (PB) {
+      case 4:
+        if ((rc = set_smem(user_fwd_kernel<D, 4>, sm))) return rc;
+        user_fwd_kernel<D, 4><<<grid, nt, sm, st>>>(a);
+        break;
+      case 2:
+        if ((rc = set_smem(user_fwd_kernel<D, 2>, sm))) return rc;
+        user_fwd_kernel<D, 2><<<grid, nt, sm, st>>>(a);
+        break;
+      default:
+        if ((rc = set_smem(user_fwd_kernel<D, 1>, sm))) return rc;
+        user_fwd_kernel<D, 1><<<grid, nt, sm, st>>>(a);
+    }
+    LAUNCH_CHECK(h, "user_fwd");
   }
   par.join(0);
   // user-oriented transform of levels 0..L-1, one launch   (model.py:270-283)
@@ -519,12 +516,13 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
   float* wT = at<float>(ws, L.wT);
   prof_mark(h, st, nullptr);
 
-  CUDA_TRY(cudaMemsetAsync(at<char>(ws, L.zero_begin), 0, L.zero_end - L.zero_begin, st));
+  CUDA_TRY(cudaMemsetAsync(at<char>(ws, L.zero_begin), 0, L.zero_mid - L.zero_begin, st));
   // side stream 0: gradient-buffer initialisation that does not depend on the batch's activations
   const Par par{h, st, h->use_streams && !h->prof_on};
   par.fork(0);
   {
   cudaStream_t st = par.s(0);
+  CUDA_TRY(cudaMemsetAsync(at<char>(ws, L.zero_mid), 0, L.zero_end - L.zero_mid, st));
   // sharded mode: peers scatter into this rank's shard, so the CALLER zeroes it (and synchronises the ranks)
   if (h->n_shards == 1) CUDA_TRY(cudaMemsetAsync(G.entity_emb, 0, sizeof(float) * (size_t)c.n_entity * D, st));
   prof_mark(h, st, "memset");
@@ -772,6 +770,10 @@ int check_supported(const mvin_config_t* c) {
     return fail(MVIN_ERR_INVALID, "bad table sizes (n_user %d, n_entity %d, n_relation %d)", c->n_user, c->n_entity,
                 c->n_relation);
   if (c->max_batch < 1) return fail(MVIN_ERR_INVALID, "max_batch must be >= 1");
+  if (user_pairs_per_cta(d, c->n_relation, c->p_hop, c->n_memory) == 0)
+    return fail(MVIN_ERR_UNSUPPORTED,
+                "n_relation x dim (%d x %d) with n_memory %d does not fit the user-side kernel's shared memory",
+                c->n_relation, d, c->n_memory);
   return MVIN_OK;
 }
 
@@ -828,6 +830,7 @@ int mvin_create(const mvin_config_t* cfg, mvin_handle_t* out) {
     }
   }
   if (const char* ev = getenv("MVIN_B200_ENTITY_LEAF")) h->entity_leaf_mode = atoi(ev) != 0 ? 1 : 0;
+  if (const char* ev = getenv("MVIN_B200_USER_PB_FWD")) { const int n = atoi(ev); if (n == 1 || n == 2 || n == 4) h->user_pb_fwd = n; }
   if (const char* ev = getenv("MVIN_B200_CTAS_PER_SM")) { const int n = atoi(ev); if (n >= 1 && n <= 32) h->max_ctas_per_sm = n; }
   if (cudaMalloc(&h->d_shard_tab, sizeof(void*) * 2 * MAX_SHARDS) != cudaSuccess ||
       cudaMalloc(&h->d_sched, sizeof(int) * 16) != cudaSuccess ||
