@@ -93,7 +93,7 @@ def kernel_bytes_per_step(w):
     out = {
         "transform_fwd": sum(rows[h] * (row + 4) for h in range(L)),
         "transform_bwd": sum(rows[h] * (2 * row + 4) for h in range(L)),
-        "ripple_fwd": B * (2 * p * m * row + 3 * p * m * 4),
+        "user_fwd": B * ((2 * p * m + 1) * row + 3 * p * m * 4 + 8),
         "ripple_bwd": B * (2 * 2 * p * m * row + 3 * p * m * 4),
     }
     for i in range(L):

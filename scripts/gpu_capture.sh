@@ -17,8 +17,8 @@ for WL in $WLS; do
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
       --log-file $OUT/${TAG}_launches_${WL}.csv python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu-baseline \
       > $OUT/${TAG}_ncu_launch_${WL}.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'agg_(fwd|bwd)_kernel|leaf_entity|ripple_(fwd|bwd)' \
-      -s 30 -c 8 -f -o $OUT/${TAG}_full_${WL} python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu-baseline \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'agg_(fwd|bwd)_kernel|leaf_entity|ripple_bwd|user_fwd|transform_(fwd|bwd)' \
+      -s 40 -c 12 -f -o $OUT/${TAG}_full_${WL} python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu-baseline \
       > $OUT/${TAG}_ncu_full_${WL}.log 2>&1
 done
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err
