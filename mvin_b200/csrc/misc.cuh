@@ -65,7 +65,7 @@ __global__ void prep_items_kernel(const int64_t* __restrict__ item, ETab E, int 
   const long b = i / LPR;
   const int c = (int)(i % LPR);
   const long e = item[b];
-  if (c == 0) { ent0[b] = (int32_t)e; if (stamp) stamp[e] = 1; }
+  if (c == 0 && ent0) { ent0[b] = (int32_t)e; if (stamp) stamp[e] = 1; }
   st4(Vbuf + b * D + c * 4, ldg4(erow(E, e, D) + c * 4));
 }
 

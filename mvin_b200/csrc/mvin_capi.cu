@@ -375,7 +375,23 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
     }
   }
   // the user side in one launch: seeds v = E[item], Q = RK^T v, ripple attention, user MLP -> user_o
-  // (model.py:125-134, :161-240)
+  // (model.py:125-134, :161-240).  With a large relation-KGE table Q comes from a batched GEMM instead.
+  const bool q_fused = user_q_fused(D, nr);
+  if (!q_fused && p > 0) {
+    const long n = (long)B * C::LPR;
+    prep_items_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(item, h->etab, B, nullptr,
+                                                                      at<float>(ws, L.Vbuf), nullptr);
+    LAUNCH_CHECK(h, "prep_items");
+  }
+  // Q[b, r, :] = RK[r]^T v_b      (model.py:211-220 refactored)
+  if (!q_fused && p > 0) {
+    GemmArgs g = gemm_args();
+    g.A = at<float>(ws, L.Vbuf); g.sa_m = D; g.sa_k = 1; g.bsA = 0;
+    g.B = P.relation_kge; g.sb_k = D; g.sb_n = 1; g.bsB = (long)D * D;
+    g.C = at<float>(ws, L.Q); g.ldc = (long)nr * D; g.bsC = D;
+    g.M = B; g.N = D; g.K = D; g.nbatch = nr;
+    if ((rc = run_gemm(h, st, g, "gemm_q"))) return rc;
+  }
   {
     UserArgs a;
     memset(&a, 0, sizeof(a));
@@ -384,7 +400,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
     a.mem_h = mem_h; a.mem_r = mem_r; a.mem_t = mem_t;
     a.Vbuf = at<float>(ws, L.Vbuf); a.Q = at<float>(ws, L.Q); a.probs = at<float>(ws, L.probs);
     a.O = at<float>(ws, L.O); a.u = at<float>(ws, L.u);
-    a.B = B; a.m = m; a.p = p; a.n_rel = nr;
+    a.B = B; a.m = m; a.p = p; a.n_rel = nr; a.q_ready = q_fused ? 0 : 1;
     const int PB = user_pairs_per_cta(D, nr, p, m, h->user_pb_fwd);
     const size_t sm = user_fwd_smem(D, PB, nr, p, m);
     const int nt = 32 * user_warps(PB, p);

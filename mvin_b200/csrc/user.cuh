@@ -32,6 +32,7 @@ struct UserArgs {
   const int32_t* mem_t;
   float* Vbuf;             // [B, D]  v_b
   float* Q;                // [B, n_rel, D]  Q[b, r] = RK[r]^T v_b (re-used by the backward)
+  int q_ready;             // 1: Q was produced by a batched GEMM (large RK: n_rel d^2 floats do not stay in L1)
   float* probs;            // [p+1, B, m]
   float* O;                // [B, (p+1) D]   concat(user_h_set, o_0 .. o_{p-1})  (model.py:232)
   float* u;                // [B, D]  user_o
@@ -43,9 +44,11 @@ inline int user_warps(int PB, int p) {
   const int w = PB * (p + 1);
   return w < 4 ? 4 : (w > USER_MAX_NT / 32 ? USER_MAX_NT / 32 : w);
 }
+// RK is re-streamed by every CTA of the fused kernel: only worth it while it stays L1 / L2-cheap
+inline bool user_q_fused(int D, int n_rel) { return (size_t)n_rel * D * D * sizeof(float) <= 256u * 1024; }
 inline size_t user_fwd_smem(int D, int PB, int n_rel, int p, int m) {
-  return sizeof(float) * ((size_t)PB * D + (size_t)PB * n_rel * D + (size_t)PB * (p + 1) * D +
-                          (size_t)user_warps(PB, p) * 4 * m);
+  const size_t q = user_q_fused(D, n_rel) ? (size_t)PB * n_rel * D : 0;
+  return sizeof(float) * ((size_t)PB * D + q + (size_t)PB * (p + 1) * D + (size_t)user_warps(PB, p) * 4 * m);
 }
 // pairs per CTA: as many as keep the shared memory under ~64 KB (three CTAs per SM); 0 = does not fit at all
 inline int user_pairs_per_cta(int D, int n_rel, int p, int m, int pb_max = 4) {
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(USER_MAX_NT) user_fwd_kernel(UserArgs a) {
   const int m = a.m, S = a.p + 1, n_rel = a.n_rel;
   float* v_s = smem;                                   // [PB][D]
   float* Q_s = v_s + PB * D;                           // [PB][n_rel][D]
-  float* O_s = Q_s + PB * n_rel * D;                   // [PB][S*D]
+  float* O_s = Q_s + (a.q_ready ? 0 : PB * n_rel * D); // [PB][S*D]
   float* lg = O_s + PB * S * D + warp * m;             // [NW][m]
   int32_t* ids = reinterpret_cast<int32_t*>(O_s + PB * S * D + NW * m) + warp * 3 * m;
   int32_t *sh = ids, *sr = ids + m, *stt = ids + 2 * m;
@@ -104,9 +107,9 @@ __global__ void __launch_bounds__(USER_MAX_NT) user_fwd_kernel(UserArgs a) {
   }
   __syncthreads();
   // (2) Q
-  if (a.p > 0) build_q<D, PB>(a.RK, v_s, Q_s, n_rel, tid, NT);
+  if (a.p > 0 && !a.q_ready) build_q<D, PB>(a.RK, v_s, Q_s, n_rel, tid, NT);
   __syncthreads();
-  if (a.p > 0) {
+  if (a.p > 0 && !a.q_ready) {
     for (int i = tid * 4; i < PB * n_rel * D; i += NT * 4) {
       const int q = i / (n_rel * D);
       if (b0 + q < a.B) st4(a.Q + (b0 + q) * n_rel * D + (i - q * n_rel * D), ld4(&Q_s[i]));
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(USER_MAX_NT) user_fwd_kernel(UserArgs a) {
       if (s) { sr[i] = __ldg(a.mem_r + off + i); stt[i] = __ldg(a.mem_t + off + i); }
     }
     __syncwarp();
-    const float* Qb = Q_s + (long)q * n_rel * D + c * 4;
+    const float* Qb = (a.q_ready ? a.Q + b * n_rel * D : Q_s + (long)q * n_rel * D) + c * 4;   // generic pointer
 #pragma unroll USER_UNR
     for (int m0 = 0; m0 < m; m0 += G) {
       const int mm = m0 + g;

@@ -114,6 +114,24 @@ def test_synthetic_vs_oracle(dim, K, H, p, m, B, regime, hub):
     _assert_grads(model.named_gradients(), lambda k: grads[k].numpy())
 
 
+@pytest.mark.parametrize("dim,n_rel", [(64, 150), (16, 150)])
+def test_many_relations(dim, n_rel):
+    """n_relation > 128: one shared ds histogram per CTA instead of one per warp; with dim 64 the relation-KGE table
+    (n_rel d^2 floats) is too large for the fused Q build and Q comes from the batched GEMM."""
+    from mvin_b200 import MVIN
+    args = make_args(dim=dim, neighbor_sample_size=8, h_hop=2, p_hop=2, n_memory=16, batch_size=24)
+    prob = make_problem(args, n_relation=n_rel, seed=11)
+    model = MVIN(args, prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"], prob["adj_relation"])
+    model.load_named_parameters({k: v.numpy() for k, v in prob["P"].items()})
+    fd = feed_dict(model, prob)
+    out, grads = orc.loss_and_grads(prob["P"], prob["cfg"], prob["adj_entity"], prob["adj_relation"], prob["users"],
+                                    prob["items"], prob["mem_h"], prob["mem_r"], prob["mem_t"], prob["labels"])
+    assert rel_err(model.get_raw_scores(fd), out.scores.detach().numpy()) < SCORE_TOL
+    losses = model.loss_and_grads(fd)
+    assert abs(float(losses[0]) - float(out.loss)) <= 1e-4 * max(1.0, abs(float(out.loss)))
+    _assert_grads(model.named_gradients(), lambda k: grads[k].numpy())
+
+
 def test_partial_batch_and_errors():
     from mvin_b200 import MVIN
     from mvin_b200._lib import MvinError
