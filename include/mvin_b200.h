@@ -179,6 +179,11 @@ int64_t mvin_launch_count(mvin_handle_t h);
 int mvin_profile_enable(mvin_handle_t h, int32_t on);
 int mvin_profile_read(mvin_handle_t h, char* buf, size_t buflen);
 
+/* Self-test of the tcgen05 (5th-generation tensor core) building block the row kernels use for their d x d maps:
+ * C[M, D] = A[M, D] . W[D, D]^T in 3xTF32 (fp32-level accuracy), device pointers, D in {32, 64}.  Not part of the
+ * model path; tests/test_umma.py checks it against an fp64 product. */
+int mvin_test_umma_gemm(const float* A, const float* W, float* C, int64_t M, int32_t D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

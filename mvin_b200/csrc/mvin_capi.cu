@@ -17,6 +17,7 @@
 #include "gemm.cuh"
 #include "level.cuh"
 #include "misc.cuh"
+#include "umma.cuh"
 #include "user.cuh"
 
 using namespace mvin;
@@ -1119,6 +1120,25 @@ int mvin_train_step_host(mvin_handle_t h, const int64_t* user_indices, const int
   }
   CUDA_TRY(cudaMemcpyAsync(losses_host, d_loss, sizeof(float) * 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  return MVIN_OK;
+}
+
+int mvin_test_umma_gemm(const float* A, const float* W, float* C, int64_t M, int32_t D, void* stream) {
+  if (!A || !W || !C || M < 1) return fail(MVIN_ERR_INVALID, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((M + 127) / 128);
+  int rc;
+  if (D == 32) {
+    if ((rc = set_smem(umma_gemm_test_kernel<32>, umma_gemm_test_smem<32>()))) return rc;
+    umma_gemm_test_kernel<32><<<grid, 256, umma_gemm_test_smem<32>(), st>>>(A, W, C, M);
+  } else if (D == 64) {
+    if ((rc = set_smem(umma_gemm_test_kernel<64>, umma_gemm_test_smem<64>()))) return rc;
+    umma_gemm_test_kernel<64><<<grid, 256, umma_gemm_test_smem<64>(), st>>>(A, W, C, M);
+  } else {
+    return fail(MVIN_ERR_UNSUPPORTED, "tcgen05 path: dim must be 32 or 64, got %d", D);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MVIN_ERR_CUDA, "launch umma_gemm_test: %s", cudaGetErrorString(e));
   return MVIN_OK;
 }
 
