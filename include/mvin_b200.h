@@ -183,6 +183,10 @@ int mvin_profile_read(mvin_handle_t h, char* buf, size_t buflen);
  * C[M, D] = A[M, D] . W[D, D]^T in 3xTF32 (fp32-level accuracy), device pointers, D in {32, 64}.  Not part of the
  * model path; tests/test_umma.py checks it against an fp64 product. */
 int mvin_test_umma_gemm(const float* A, const float* W, float* C, int64_t M, int32_t D, void* stream);
+/* Same for the transposed product used by the weight gradients: dump[128, D] receives the raw accumulator lanes of
+ * dW = A^T . G (A, G [M, D]), accumulated over all 128-row tiles by one CTA. */
+int mvin_test_umma_dw(const float* A, const float* G, float* dump, int64_t M, int32_t D, int32_t variant,
+                      void* stream);
 
 #ifdef __cplusplus
 }

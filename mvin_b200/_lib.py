@@ -15,7 +15,7 @@ EXPORTS = ["mvin_abi_version", "mvin_last_error", "mvin_create", "mvin_destroy",
            "mvin_bind_grads", "mvin_bind_adjacency", "mvin_bind_entity_shards", "mvin_set_batch_scale", "mvin_ipc_export", "mvin_ipc_open", "mvin_pack_adjacency", "mvin_workspace_bytes",
            "mvin_get_neighbors", "mvin_forward", "mvin_importance", "mvin_backward", "mvin_adam_step",
            "mvin_feed_bytes", "mvin_train_step_host", "mvin_launch_count", "mvin_profile_enable",
-           "mvin_profile_read", "mvin_test_umma_gemm"]
+           "mvin_profile_read", "mvin_test_umma_gemm", "mvin_test_umma_dw"]
 
 
 class Config(C.Structure):
@@ -76,6 +76,7 @@ def load():
     lib.mvin_train_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, C.POINTER(Params),
                                          C.POINTER(Params), C.c_float, i32, vp, vp]
     lib.mvin_test_umma_gemm.argtypes = [vp, vp, vp, C.c_int64, i32, vp]
+    lib.mvin_test_umma_dw.argtypes = [vp, vp, vp, C.c_int64, i32, i32, vp]
     lib.mvin_launch_count.argtypes = [vp]
     lib.mvin_launch_count.restype = C.c_int64
     lib.mvin_profile_enable.argtypes = [vp, i32]

@@ -1142,6 +1142,24 @@ int mvin_test_umma_gemm(const float* A, const float* W, float* C, int64_t M, int
   return MVIN_OK;
 }
 
+int mvin_test_umma_dw(const float* A, const float* G, float* dump, int64_t M, int32_t D, int32_t variant, void* stream) {
+  if (!A || !G || !dump || M < 1) return fail(MVIN_ERR_INVALID, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (D == 32) {
+    if ((rc = set_smem(umma_dw_test_kernel<32>, umma_dw_test_smem<32>()))) return rc;
+    umma_dw_test_kernel<32><<<1, 256, umma_dw_test_smem<32>(), st>>>(A, G, dump, M, variant);
+  } else if (D == 64) {
+    if ((rc = set_smem(umma_dw_test_kernel<64>, umma_dw_test_smem<64>()))) return rc;
+    umma_dw_test_kernel<64><<<1, 256, umma_dw_test_smem<64>(), st>>>(A, G, dump, M, variant);
+  } else {
+    return fail(MVIN_ERR_UNSUPPORTED, "tcgen05 path: dim must be 32 or 64, got %d", D);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MVIN_ERR_CUDA, "launch umma_dw_test: %s", cudaGetErrorString(e));
+  return MVIN_OK;
+}
+
 int64_t mvin_launch_count(mvin_handle_t h) { return h ? h->launches : 0; }
 
 int mvin_profile_enable(mvin_handle_t h, int32_t on) {

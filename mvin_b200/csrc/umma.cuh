@@ -214,6 +214,102 @@ __global__ void __launch_bounds__(256) umma_gemm_test_kernel(const float* __rest
   if (warp == 0) umma::tmem_dealloc(tmem, D < 32 ? 32 : D);
 }
 
+// self-test / probe of the transposed product (weight gradients): dump[128][D] = raw accumulator lanes of
+// dW = A^T . G accumulated over all 128-row tiles of A, G [M, D] by ONE CTA.
+//   variant bit 0: A operand = MN-major view of the K-major tile (else a transposed, K-major staged copy)
+//   variant bit 1: B operand likewise;   bit 2: MMA M = 128 instead of 64
+template <int D>
+__global__ void __launch_bounds__(256) umma_dw_test_kernel(const float* __restrict__ A, const float* __restrict__ G,
+                                                           float* __restrict__ dump, long M, int variant) {
+  using L = umma::OpLayout<D>;
+  using LT = umma::OpLayout<128>;                        // transposed copies: K = 128 rows of the tile
+  constexpr int LPR = D / 4;
+  const int MM = (variant & 4) ? 128 : 64;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* a_hi = smem_raw;                        // probe: single-product TF32 (hi parts only)
+  unsigned char* g_hi = a_hi + L::bytes(128);
+  unsigned char* at_hi = g_hi + L::bytes(128) + 1024;    // [64 (m, zero beyond D)][128 (k = row)]
+  unsigned char* gt_hi = at_hi + LT::bytes(64);          // [D (n)][128]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(gt_hi + LT::bytes(D));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  if (warp == 0) umma::tmem_alloc(tmem_slot, D < 32 ? 32 : D);
+  if (tid == 32) {
+    umma::mbar_init(bar, 1);
+    umma::fence_barrier_init();
+  }
+  for (int i = tid; i < LT::bytes(64) / 4; i += 256) reinterpret_cast<float*>(at_hi)[i] = 0.f;
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  uint32_t idesc = umma::idesc_tf32(MM, D);
+  if (variant & 1) idesc |= umma::IDESC_A_MN;
+  if (variant & 2) idesc |= umma::IDESC_B_MN;
+  uint32_t phase = 0;
+  const long ntiles = (M + 127) / 128;
+  for (long t = 0; t < ntiles; ++t) {
+    const long row0 = t * 128;
+    for (int i = tid; i < 128 * LPR; i += 256) {
+      const int r = i / LPR, k4 = i % LPR;
+      float4 x = f4zero(), g = f4zero();
+      if (row0 + r < M) {
+        x = ldg4(A + (row0 + r) * D + k4 * 4);
+        g = ldg4(G + (row0 + r) * D + k4 * 4);
+      }
+      float4 hi, lo;
+      umma::split4(x, hi, lo);
+      *reinterpret_cast<float4*>(a_hi + L::off(r, k4)) = hi;
+      umma::split4(g, hi, lo);
+      *reinterpret_cast<float4*>(g_hi + L::off(r, k4)) = hi;
+      const float xs[4] = {x.x, x.y, x.z, x.w}, gs[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int mcol = k4 * 4 + j;
+        const int o = LT::off(mcol, r / 4) + (r % 4) * 4;
+        *reinterpret_cast<float*>(at_hi + o) = xs[j];
+        *reinterpret_cast<float*>(gt_hi + o) = gs[j];
+      }
+    }
+    umma::fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      umma::fence_after_sync();
+      uint32_t acc = t == 0 ? 0u : 1u;
+      for (int k = 0; k < 128 / 8; ++k) {                  // K = rows of the tile, 8 per instruction
+        // MN-major view: leading (K-group) offset = SBO of the K-major tile, stride (MN chunk) offset = its LBO
+        const uint32_t kmn = k * L::SBO, kk = k * 2 * LT::LBO;
+        const uint64_t da = (variant & 1) ? umma::make_desc(umma::smem_u32(a_hi) + kmn, L::SBO, L::LBO)
+                                          : umma::make_desc(umma::smem_u32(at_hi) + kk, LT::LBO, LT::SBO);
+        const uint64_t dg = (variant & 2) ? umma::make_desc(umma::smem_u32(g_hi) + kmn, L::SBO, L::LBO)
+                                          : umma::make_desc(umma::smem_u32(gt_hi) + kk, LT::LBO, LT::SBO);
+        umma::mma_tf32(tmem, da, dg, idesc, acc);
+        acc = 1u;
+      }
+      umma::commit(bar);
+    }
+    umma::mbar_wait(bar, phase);
+    phase ^= 1;
+    umma::fence_after_sync();
+  }
+  const int r = 32 * (warp % 4) + lane;
+  const int c0 = (warp / 4) * (D / 2);
+#pragma unroll
+  for (int cc = 0; cc < D / 2; cc += 16) {
+    float v[16];
+    umma::tmem_ld16(tmem + ((uint32_t)(32 * (warp % 4)) << 16) + (uint32_t)(c0 + cc), v);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dump[(long)r * D + c0 + cc + j] = v[j];
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, D < 32 ? 32 : D);
+}
+template <int D>
+inline size_t umma_dw_test_smem() {
+  return 2 * umma::OpLayout<D>::bytes(128) + 1024 + umma::OpLayout<128>::bytes(64) + umma::OpLayout<128>::bytes(D) + 16;
+}
+
 template <int D>
 inline size_t umma_gemm_test_smem() {
   return 2 * umma::OpLayout<D>::bytes(128) + 2 * umma::OpLayout<D>::bytes(D) + 16;

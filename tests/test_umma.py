@@ -26,3 +26,28 @@ def test_umma_gemm_matches_fp64(D, M):
     got = dC.cpu().numpy()
     err = np.abs(got - ref).max() / np.abs(ref).max()
     assert err < 2e-6, err
+
+
+@pytest.mark.parametrize("D,M", [(64, 128), (64, 700), (32, 128), (32, 300)])
+def test_umma_dw_probe(D, M):
+    """Transposed product dW = A^T G (single-product TF32 probe, M = 64): K-major transposed staging works and row i
+    of the 64-row accumulator sits in lane 32 (i / 16) + i % 16; the MN-major view of the K-major tiles (variant 3)
+    is NOT usable for kind::tf32 without swizzle -- the tensor core returns zeros -- which is why the weight
+    gradients stay on the mma.sync path (level.cuh)."""
+    from mvin_b200 import _lib
+    from mvin_b200.umma_layout import dw_lane
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(7 * D + M)
+    A = torch.randn(M, D, generator=g)
+    G = torch.randn(M, D, generator=g)
+    dA, dG = A.cuda(), G.cuda()
+    ref = (A.double().t() @ G.double()).numpy()
+    scale = np.abs(ref).max()
+    dump = torch.full((128, D), float("nan"), device="cuda")
+    rc = lib.mvin_test_umma_dw(ctypes.c_void_p(dA.data_ptr()), ctypes.c_void_p(dG.data_ptr()),
+                               ctypes.c_void_p(dump.data_ptr()), ctypes.c_int64(M), ctypes.c_int32(D), 0, None)
+    assert rc == 0, lib.mvin_last_error()
+    torch.cuda.synchronize()
+    got = dump.cpu().numpy()
+    for i in range(D):
+        assert np.abs(got[dw_lane(i, D)] - ref[i]).max() / scale < 5e-3, i      # one TF32 product: ~1e-3
