@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libmvin_b200.so")
 SOURCES = ["mvin_capi.cu"]
-HEADERS = ["common.cuh", "gemm.cuh", "level.cuh", "misc.cuh", "user.cuh", "umma.cuh", os.path.join("..", "..", "include", "mvin_b200.h")]
+HEADERS = ["common.cuh", "gemm.cuh", "level.cuh", "level_tc.cuh", "misc.cuh", "user.cuh", "umma.cuh", os.path.join("..", "..", "include", "mvin_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -45,6 +45,14 @@ MVIN_DEV float4 cross_group_sum4(float4 v) {
 MVIN_DEV float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 MVIN_DEV float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 MVIN_DEV void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// activation rows of a level much larger than L2 are touched once per kernel: streaming (evict-first) accesses keep
+// them from flushing the entity table and the weights out of L2
+MVIN_DEV float4 ld4a(const float* p, bool cs) {
+  return cs ? __ldcs(reinterpret_cast<const float4*>(p)) : __ldg(reinterpret_cast<const float4*>(p));
+}
+MVIN_DEV void st4a(float* p, float4 v, bool cs) {
+  if (cs) __stcs(reinterpret_cast<float4*>(p), v); else *reinterpret_cast<float4*>(p) = v;
+}
 MVIN_DEV float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 MVIN_DEV float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 MVIN_DEV float4 f4scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }

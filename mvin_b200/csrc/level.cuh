@@ -395,6 +395,7 @@ struct TransformLevel {
   long rows;
   int rpp;              // rows per pair = K^h
   unsigned long long rpp_magic;
+  int stream;           // level buffers >> L2: streaming (evict-first) activation accesses
 };
 struct TransformArgs {
   TransformLevel lv[MAX_LV];
@@ -404,6 +405,7 @@ struct TransformArgs {
   const float* u;       // [B, D]  user_o
   GTab dE;              // bwd: entity-table gradient (scatter-add)
   float* du;            // bwd: [B, D] (accumulated)
+  int dbg;              // experiments only (env MVIN_B200_DBG): skip phases of the tcgen05 kernels
 };
 
 template <int D>
@@ -439,7 +441,7 @@ __global__ void __launch_bounds__(TC<D>::NT) transform_fwd_kernel(TransformArgs 
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) {
       const long row = row0 + ty * C::TM + i;
-      if (row < L.rows) st4(L.T + row * D + tx * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+      if (row < L.rows) st4a(L.T + row * D + tx * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]), L.stream);
     }
     __syncthreads();
   }
@@ -472,8 +474,8 @@ __global__ void __launch_bounds__(TC<D>::NT) transform_bwd_kernel(TransformArgs 
       const long row = row0 + r;
       float4 g = f4zero(), x = f4zero();
       if (row < L.rows) {
-        g = ld4(L.g1 + row * D + tx * 4);
-        if (L.g2) g = f4add(g, ld4(L.g2 + row * D + tx * 4));
+        g = ld4a(L.g1 + row * D + tx * 4, L.stream);
+        if (L.g2) g = f4add(g, ld4a(L.g2 + row * D + tx * 4, L.stream));
         const long e = L.ent[row];
         x = f4add(ldg4(erow(a.E, e, D) + tx * 4), ldg4(a.u + fastdiv(row, L.rpp_magic) * D + tx * 4));
       }
@@ -523,6 +525,7 @@ struct AggLevel {
   int rpp;
   unsigned long long rpp_magic;
   int leaf;
+  int stream;           // level buffers >> L2: streaming (evict-first) activation accesses
 };
 struct AggArgs {
   AggLevel lv[MAX_LV];
@@ -609,7 +612,7 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
           // (leaf_entity_kernel)
           const long e = __ldg(L.ent + row);
           o = f4add(ldg4(a.Se + e * D + tx * 4), ldg4(a.u + fastdiv(row, L.rpp_magic) * D + tx * 4));
-          st4(L.SU + row * D + tx * 4, o);
+          st4a(L.SU + row * D + tx * 4, o, L.stream);
         } else if (leaf) {
           const float4 uv = ldg4(a.u + fastdiv(row, L.rpp_magic) * D + tx * 4);
           const int2* nb = nb_s + r * KP;
@@ -620,16 +623,16 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
             acc = f4fma(__int_as_float(v.x), ldg4(erow(a.E, v.y, D) + tx * 4), acc);
           }
           o = f4add(acc, uv);
-          st4(L.SU + row * D + tx * 4, o);
+          st4a(L.SU + row * D + tx * 4, o, L.stream);
         } else {
-          const float4 sv = ldg4(L.self + row * D + tx * 4);
+          const float4 sv = ld4a(L.self + row * D + tx * 4, L.stream);
           const int2* nb = nb_s + r * KP;
           const float* base = L.child + row * K * D + tx * 4;
           float4 acc = f4zero();
 #pragma unroll 8
-          for (int k = 0; k < K; ++k) acc = f4fma(__int_as_float(nb[k].x), ldg4(base + (long)k * D), acc);
+          for (int k = 0; k < K; ++k) acc = f4fma(__int_as_float(nb[k].x), ld4a(base + (long)k * D, L.stream), acc);
           o = f4fma(invK, acc, sv);
-          st4(L.Y + row * D + tx * 4, o);
+          st4a(L.Y + row * D + tx * 4, o, L.stream);
         }
       }
       st4(&As[r * C::LD + tx * 4], o);
@@ -648,8 +651,8 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
         const long row = row0 + r;
         float4 y = f4zero();
         if (row < L.rows) {
-          y = f4fma(invK, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]), ldg4(L.self + row * D + tx * 4));
-          st4(L.Y + row * D + tx * 4, y);
+          y = f4fma(invK, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]), ld4a(L.self + row * D + tx * 4, L.stream));
+          st4a(L.Y + row * D + tx * 4, y, L.stream);
         }
         st4(&As[r * C::LD + tx * 4], y);
       }
@@ -662,8 +665,8 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
     for (int i = 0; i < C::TM; ++i) {
       const long row = row0 + ty * C::TM + i;
       if (row < L.rows)
-        st4(L.V + row * D + tx * 4, make_float4(fmaxf(acc[i][0], 0.f), fmaxf(acc[i][1], 0.f), fmaxf(acc[i][2], 0.f),
-                                                fmaxf(acc[i][3], 0.f)));
+        st4a(L.V + row * D + tx * 4, make_float4(fmaxf(acc[i][0], 0.f), fmaxf(acc[i][1], 0.f), fmaxf(acc[i][2], 0.f),
+                                                fmaxf(acc[i][3], 0.f)), L.stream);
     }
     if (tid == 0) sched[(it + 1) & 1] = nxt;
     __syncthreads();
@@ -700,6 +703,7 @@ struct AggBwdLevel {
   int rpp;
   unsigned long long rpp_magic;
   int leaf;
+  int stream;           // level buffers >> L2: streaming (evict-first) activation accesses
 };
 struct AggBwdArgs {
   AggBwdLevel lv[MAX_LV];
@@ -775,12 +779,12 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
       const long row = row0 + r;
       float4 gz = f4zero(), y = f4zero();
       if (row < L.rows) {
-        float4 go = ldg4(L.g1 + row * D + tx * 4);
-        if (L.g2) go = f4add(go, ldg4(L.g2 + row * D + tx * 4));
-        const float4 v = ldg4(L.V + row * D + tx * 4);
+        float4 go = ld4a(L.g1 + row * D + tx * 4, L.stream);
+        if (L.g2) go = f4add(go, ld4a(L.g2 + row * D + tx * 4, L.stream));
+        const float4 v = ld4a(L.V + row * D + tx * 4, L.stream);
         gz = make_float4(v.x > 0.f ? go.x : 0.f, v.y > 0.f ? go.y : 0.f, v.z > 0.f ? go.z : 0.f,
                          v.w > 0.f ? go.w : 0.f);
-        y = ldg4(L.Y + row * D + tx * 4);
+        y = ld4a(L.Y + row * D + tx * 4, L.stream);
       }
       bpa = f4add(bpa, gz);
       st4(&Gs[r * C::LD + tx * 4], gz);
@@ -801,8 +805,8 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
       const float4 grow = f4scale(gs, invK);
       float4 su = f4zero();
       if (row < L.rows) {
-        st4(L.dself + row * D + tx * 4, gs);
-        if (leaf) su = ldg4(L.SU + row * D + tx * 4);
+        st4a(L.dself + row * D + tx * 4, gs, L.stream);
+        if (leaf) su = ld4a(L.SU + row * D + tx * 4, L.stream);
       }
       st4(&Gs[r * C::LD + tx * 4], grow);
       if (leaf) {
@@ -858,7 +862,7 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
               if (valid && k < K) {
                 v[j] = nb[k];
                 if (leaf) x[j] = ldg4(erow(a.E, v[j].y, D) + tx * 4);
-                else x[j] = ldg4(L.child + (row * K + k) * D + tx * 4);
+                else x[j] = ld4a(L.child + (row * K + k) * D + tx * 4, L.stream);
               }
             }
             float part[C::W];
@@ -869,7 +873,7 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
               if (valid && k < K) {
                 const float4 dx = f4scale(gr, __int_as_float(v[j].x));
                 if (leaf) red_add4(grow_of(a.dE, v[j].y, D) + tx * 4, dx);
-                else st4(L.dchild + (row * K + k) * D + tx * 4, dx);
+                else st4a(L.dchild + (row * K + k) * D + tx * 4, dx, L.stream);
               }
             }
             dp[c] = reduce_scatter<C::W, C::LPR>(part, lane);   // dp of k = c*W + kl

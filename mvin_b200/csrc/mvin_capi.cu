@@ -16,6 +16,7 @@
 #include "../../include/mvin_b200.h"
 #include "gemm.cuh"
 #include "level.cuh"
+#include "level_tc.cuh"
 #include "misc.cuh"
 #include "umma.cuh"
 #include "user.cuh"
@@ -111,6 +112,8 @@ struct mvin_handle_s {
   bool use_streams = true;
   int entity_leaf_mode = -1;       // -1 auto, 0 off, 1 on (env MVIN_B200_ENTITY_LEAF, read in mvin_create)
   int user_pb_fwd = 4;             // max pairs per CTA of the user-side forward kernel (env MVIN_B200_USER_PB_FWD)
+  int stream_mode = -1;            // -1 auto, 0 never, 1 always (env MVIN_B200_STREAM)
+  int tc_mode = 1;                 // tcgen05 forward row kernels for d in {32, 64}: 0 never, 1 auto, 2 always (env MVIN_B200_TC)
   int max_ctas_per_sm = 4;         // cap on resident CTAs per SM of the persistent row kernels (env MVIN_B200_CTAS_PER_SM)
   bool prof_on = false;
   struct ProfRec { const char* name; cudaEvent_t ev; };
@@ -267,6 +270,10 @@ int set_smem(KernelT k, size_t bytes) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return fail(MVIN_ERR_CUDA, "cudaFuncSetAttribute(%zu B): %s", bytes, cudaGetErrorString(e));
   }
+  // the persistent row kernels want as many co-resident CTAs as shared memory allows: without this hint the driver
+  // sizes the L1 / shared split for ONE block of a large-footprint kernel
+  if (bytes > 16 * 1024)
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   return MVIN_OK;
 }
 
@@ -309,6 +316,20 @@ int partition_grid(const long* rows, int nlev, int tile_rows, int cap, int* cta_
     cta_end[l] = end;
   }
   return end;
+}
+
+// tcgen05 versions of the forward row kernels (level_tc.cuh): 128-row tiles and a heavier prologue pay off only on
+// large levels (measured: +8 % on transform_fwd at C3, parity at C4, slower at C2); env MVIN_B200_TC=0 / 2 = never / always
+inline bool use_tc_path(mvin_handle_t h, long leaf_rows) {
+  if (h->tc_mode == 0) return false;
+  if (h->tc_mode == 2) return true;
+  return leaf_rows >= 131072;
+}
+
+// activation buffers of a level that dwarf L2 (126 MB) are accessed with streaming hints (common.cuh, ld4a / st4a)
+inline int stream_level(mvin_handle_t h, long rows, int D) {
+  if (h->stream_mode >= 0) return h->stream_mode;
+  return (size_t)rows * D * sizeof(float) >= ((size_t)48 << 20) ? 1 : 0;
 }
 
 // Tile list of one aggregator launch (level.cuh, TileList): returns the grid size (every CTA is resident).
@@ -435,10 +456,25 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
       t.W = P.transfer_w + (long)lv * D * D; t.b = P.transfer_b + (long)lv * D;
       t.T = at<float>(ws, L.V[0][lv]);
       t.rows = rows[lv] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
+        t.stream = stream_level(h, L.rows[lv], D);
     }
     a.nlev = H; a.E = h->etab; a.u = at<float>(ws, L.u);
-    const int grid = partition_grid(rows, H, C::R, h->sm_count * resident_ctas(h, transform_fwd_kernel<D>, C::NT, sm), a.cta_end);
-    transform_fwd_kernel<D><<<grid, C::NT, sm, st>>>(a);
+    if (const char* ev = getenv("MVIN_B200_DBG")) a.dbg = atoi(ev);
+    bool done = false;
+    if constexpr (D == 32 || D == 64) {
+      if (use_tc_path(h, L.rows[H - 1])) {
+        const size_t smt = transform_fwd_tc_smem<D>();
+        if ((rc = set_smem(transform_fwd_tc_kernel<D>, smt))) return rc;
+        const int grid = partition_grid(rows, H, TT<D>::R,
+                                        h->sm_count * resident_ctas(h, transform_fwd_tc_kernel<D>, TT<D>::NT, smt), a.cta_end);
+        transform_fwd_tc_kernel<D><<<grid, TT<D>::NT, smt, st>>>(a);
+        done = true;
+      }
+    }
+    if (!done) {
+      const int grid = partition_grid(rows, H, C::R, h->sm_count * resident_ctas(h, transform_fwd_kernel<D>, C::NT, sm), a.cta_end);
+      transform_fwd_kernel<D><<<grid, C::NT, sm, st>>>(a);
+    }
     LAUNCH_CHECK(h, "transform_fwd");
   }
   // aggregation iterations (model.py:286-307): one launch per iteration, every level of it
@@ -461,6 +497,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
         t.self = at<float>(ws, L.V[i][lv]);
         t.Y = at<float>(ws, L.Y[i][lv]); t.V = at<float>(ws, L.V[i + 1][lv]);
         t.rows = rows[q] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
+        t.stream = stream_level(h, L.rows[lv], D);
         t.leaf = (i == 0 && lv == H - 1);
         if (t.leaf) t.SU = at<float>(ws, L.SU); else t.child = at<float>(ws, L.V[i][lv + 1]);
       }
@@ -471,6 +508,27 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
         a.E = h->etab; a.u = at<float>(ws, L.u);
         a.Se = L.entity_leaf ? at<float>(ws, L.Se) : nullptr;
         a.Wt = P.transfer_w + (long)H * D * D; a.bt = P.transfer_b + (long)H * D;
+      }
+      bool done = false;
+      if constexpr (D == 32 || D == 64) {
+        if (i == 0 && use_tc_path(h, L.rows[H - 1])) {     // leaf iteration; inner-only iterations are faster on mma.sync
+          const size_t smt = agg_fwd_tc_smem<D>(i == 0, K, nr);
+          if (i == 0) {
+            if ((rc = set_smem(agg_fwd_tc_kernel<D, true>, smt))) return rc;
+            const int grid = make_tile_list(a.tl, rows, nlev, TT<D>::R,
+                                            h->sm_count * resident_ctas(h, agg_fwd_tc_kernel<D, true>, TT<D>::NT, smt), h->d_sched);
+            agg_fwd_tc_kernel<D, true><<<grid, TT<D>::NT, smt, st>>>(a);
+          } else {
+            if ((rc = set_smem(agg_fwd_tc_kernel<D, false>, smt))) return rc;
+            const int grid = make_tile_list(a.tl, rows, nlev, TT<D>::R,
+                                            h->sm_count * resident_ctas(h, agg_fwd_tc_kernel<D, false>, TT<D>::NT, smt), h->d_sched);
+            agg_fwd_tc_kernel<D, false><<<grid, TT<D>::NT, smt, st>>>(a);
+          }
+          done = true;
+        }
+      }
+      if (done) {
+      } else if (i == 0) {
         const int grid = make_tile_list(a.tl, rows, nlev, C::R,
                                         h->sm_count * resident_ctas(h, agg_fwd_kernel<D, true>, C::NT, sm_leaf), h->d_sched);
         agg_fwd_kernel<D, true><<<grid, C::NT, sm_leaf, st>>>(a);
@@ -634,6 +692,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
         t.g2 = has_agg(H, i + 1, lv) ? at<float>(ws, L.DS[i + 1][lv]) : nullptr;
         t.dself = at<float>(ws, L.DS[i][lv]);
         t.rows = rows[q] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
+        t.stream = stream_level(h, L.rows[lv], D);
         t.leaf = (i == 0 && lv == H - 1);
         if (t.leaf) {
           t.SU = at<float>(ws, L.SU);
@@ -700,6 +759,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
       t.g1 = at<float>(ws, L.DC[0][lv]); t.g2 = at<float>(ws, L.DS[0][lv]);
       t.dW = G.transfer_w + (long)lv * D * D; t.db = G.transfer_b + (long)lv * D;
       t.rows = rows[q] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
+        t.stream = stream_level(h, L.rows[lv], D);
     }
     a.nlev = H; a.E = h->etab; a.u = at<float>(ws, L.u); a.dE = h->gtab; a.du = du;
     const int grid = partition_grid(rows, H, C::R, h->sm_count * resident_ctas(h, transform_bwd_kernel<D>, C::NT, sm), a.cta_end);
@@ -848,6 +908,8 @@ int mvin_create(const mvin_config_t* cfg, mvin_handle_t* out) {
   }
   if (const char* ev = getenv("MVIN_B200_ENTITY_LEAF")) h->entity_leaf_mode = atoi(ev) != 0 ? 1 : 0;
   if (const char* ev = getenv("MVIN_B200_USER_PB_FWD")) { const int n = atoi(ev); if (n == 1 || n == 2 || n == 4) h->user_pb_fwd = n; }
+  if (const char* ev = getenv("MVIN_B200_TC")) { const int n = atoi(ev); if (n >= 0 && n <= 2) h->tc_mode = n; }
+  if (const char* ev = getenv("MVIN_B200_STREAM")) h->stream_mode = atoi(ev) != 0 ? 1 : 0;
   if (const char* ev = getenv("MVIN_B200_CTAS_PER_SM")) { const int n = atoi(ev); if (n >= 1 && n <= 32) h->max_ctas_per_sm = n; }
   if (cudaMalloc(&h->d_shard_tab, sizeof(void*) * 2 * MAX_SHARDS) != cudaSuccess ||
       cudaMalloc(&h->d_sched, sizeof(int) * 16) != cudaSuccess ||

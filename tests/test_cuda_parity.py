@@ -114,6 +114,27 @@ def test_synthetic_vs_oracle(dim, K, H, p, m, B, regime, hub):
     _assert_grads(model.named_gradients(), lambda k: grads[k].numpy())
 
 
+@pytest.mark.parametrize("dim,K,H,B", [(64, 32, 2, 40), (32, 16, 2, 80), (64, 8, 3, 5), (32, 5, 1, 300)])
+@pytest.mark.parametrize("entity_leaf", ["0", "1"])
+def test_tcgen05_forward_kernels(dim, K, H, B, entity_leaf, monkeypatch):
+    """MVIN_B200_TC=2 forces the tcgen05 (umma.cuh / level_tc.cuh) versions of the forward row kernels, which the
+    library otherwise selects for large levels only; both leaf modes."""
+    from mvin_b200 import MVIN
+    monkeypatch.setenv("MVIN_B200_TC", "2")
+    monkeypatch.setenv("MVIN_B200_ENTITY_LEAF", entity_leaf)
+    args = make_args(dim=dim, neighbor_sample_size=K, h_hop=H, p_hop=2, n_memory=16, batch_size=B)
+    prob = make_problem(args, seed=3 * dim + K)
+    model = MVIN(args, prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"], prob["adj_relation"])
+    model.load_named_parameters({k: v.numpy() for k, v in prob["P"].items()})
+    fd = feed_dict(model, prob)
+    out, grads = orc.loss_and_grads(prob["P"], prob["cfg"], prob["adj_entity"], prob["adj_relation"], prob["users"],
+                                    prob["items"], prob["mem_h"], prob["mem_r"], prob["mem_t"], prob["labels"])
+    assert rel_err(model.get_raw_scores(fd), out.scores.detach().numpy()) < SCORE_TOL
+    losses = model.loss_and_grads(fd)
+    assert abs(float(losses[0]) - float(out.loss)) <= 1e-4 * max(1.0, abs(float(out.loss)))
+    _assert_grads(model.named_gradients(), lambda k: grads[k].numpy())
+
+
 @pytest.mark.parametrize("dim,n_rel", [(64, 150), (16, 150)])
 def test_many_relations(dim, n_rel):
     """n_relation > 128: one shared ds histogram per CTA instead of one per warp; with dim 64 the relation-KGE table
