@@ -170,6 +170,19 @@ int mvin_train_step_host(mvin_handle_t h, const int64_t* user_indices, const int
                          int32_t B, void* staging, void* workspace, const mvin_params_t* adam_m,
                          const mvin_params_t* adam_v, float lr, int32_t step, float* losses_host, void* stream);
 
+/* Device-resident feed path -- replaces the host feed assembly get_feed_dict (train.py:112-122, util.py:208-218):
+ * the packed ripple sets  user_triplet_set int32 [n_user, max(1,p), 3, n_memory]  (data_loader_user_set.py:402; one
+ * [p, 3, m] block per user) are uploaded once and bound; mvin_gather_feed builds memories_{h,r,t} [max(1,p), B, m] of a
+ * batch from user_indices on the device; mvin_train_step_users_host is mvin_train_step_host with only
+ * user / item / label crossing the bus (20 bytes per pair instead of 20 + 12 p m). */
+int mvin_bind_user_triplets(mvin_handle_t h, const int32_t* user_triplet_set);
+int mvin_gather_feed(mvin_handle_t h, const int64_t* user_indices, int32_t B, int32_t* mem_h, int32_t* mem_r,
+                     int32_t* mem_t, void* stream);
+int mvin_train_step_users_host(mvin_handle_t h, const int64_t* user_indices, const int64_t* item_indices,
+                               const float* labels, int32_t B, void* staging, void* workspace,
+                               const mvin_params_t* adam_m, const mvin_params_t* adam_v, float lr, int32_t step,
+                               float* losses_host, void* stream);
+
 /* Number of kernels the library has launched on behalf of this handle since creation (bench evidence). */
 int64_t mvin_launch_count(mvin_handle_t h);
 

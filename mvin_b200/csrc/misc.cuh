@@ -55,6 +55,22 @@ __global__ void seed_kernel(const int64_t* __restrict__ item, int B, int32_t* __
   if (stamp) stamp[e] = 1;
 }
 
+// ---- feed assembly on the device (train.py:112-122, util.py:208-218): the ripple memories of a batch gathered from
+// the packed per-user sets  uts int32 [n_user, P, 3, m]  (data_loader_user_set.py:402)  into  mem_x int32 [P, B, m]
+__global__ void gather_feed_kernel(const int32_t* __restrict__ uts, const int64_t* __restrict__ user, int B, int P, int m,
+                                   int32_t* __restrict__ mem_h, int32_t* __restrict__ mem_r, int32_t* __restrict__ mem_t) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;        // over [P][B][m]
+  const long n = (long)P * B * m;
+  if (i >= n) return;
+  const int j = (int)(i % m);
+  const long b = (i / m) % B;
+  const int hop = (int)(i / ((long)m * B));
+  const int32_t* src = uts + (((long)user[b] * P + hop) * 3) * m + j;
+  mem_h[i] = __ldg(src);
+  mem_r[i] = __ldg(src + m);
+  mem_t[i] = __ldg(src + 2 * m);
+}
+
 // ---- seeds: ent[0] = item (int32) and Vbuf = E[item]  (model.py:199) -----------------------------------
 template <int D>
 __global__ void prep_items_kernel(const int64_t* __restrict__ item, ETab E, int B,

@@ -88,6 +88,7 @@ struct mvin_handle_s {
   mvin_params_t P, G;
   bool has_params = false, has_grads = false;
   const int32_t* adj = nullptr;
+  const int32_t* uts = nullptr;    // device-resident ripple sets [n_user, max(1,p), 3, m] (mvin_bind_user_triplets)
   int device = 0, sm_count = 148;
   int64_t launches = 0;
   // batch of the last forward (pointers owned by the caller, must stay valid until backward)
@@ -1219,6 +1220,62 @@ int mvin_test_umma_dw(const float* A, const float* G, float* dump, int64_t M, in
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(MVIN_ERR_CUDA, "launch umma_dw_test: %s", cudaGetErrorString(e));
+  return MVIN_OK;
+}
+
+int mvin_bind_user_triplets(mvin_handle_t h, const int32_t* user_triplet_set) {
+  if (!h || !user_triplet_set) return fail(MVIN_ERR_INVALID, "null argument");
+  h->uts = user_triplet_set;
+  return MVIN_OK;
+}
+
+int mvin_gather_feed(mvin_handle_t h, const int64_t* user_indices, int32_t B, int32_t* mem_h, int32_t* mem_r,
+                     int32_t* mem_t, void* stream) {
+  if (!h || !user_indices || !mem_h || !mem_r || !mem_t || B < 1) return fail(MVIN_ERR_INVALID, "bad argument");
+  if (!h->uts) return fail(MVIN_ERR_STATE, "user triplet sets not bound (mvin_bind_user_triplets)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = h->cfg.p_hop > 0 ? h->cfg.p_hop : 1, m = h->cfg.n_memory;
+  const long n = (long)P * B * m;
+  gather_feed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->uts, user_indices, B, P, m, mem_h, mem_r, mem_t);
+  LAUNCH_CHECK(h, "gather_feed");
+  return MVIN_OK;
+}
+
+int mvin_train_step_users_host(mvin_handle_t h, const int64_t* user_indices, const int64_t* item_indices,
+                               const float* labels, int32_t B, void* staging, void* workspace,
+                               const mvin_params_t* adam_m, const mvin_params_t* adam_v, float lr, int32_t step,
+                               float* losses_host, void* stream) {
+  if (!h || !user_indices || !item_indices || !labels || !staging || !workspace || !losses_host)
+    return fail(MVIN_ERR_INVALID, "null argument");
+  if (B < 1 || B > h->cfg.max_batch) return fail(MVIN_ERR_INVALID, "B = %d outside 1..max_batch (%d)", B, h->cfg.max_batch);
+  if (!h->uts) return fail(MVIN_ERR_STATE, "user triplet sets not bound (mvin_bind_user_triplets)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t pm = (size_t)(h->cfg.p_hop > 0 ? h->cfg.p_hop : 1) * B * h->cfg.n_memory;
+  char* base = static_cast<char*>(staging);
+  size_t off = 0;
+  auto carve = [&](size_t bytes) -> void* { void* p = base + off; off += align_up(bytes); return p; };
+  int64_t* d_user = (int64_t*)carve(sizeof(int64_t) * B);
+  int64_t* d_item = (int64_t*)carve(sizeof(int64_t) * B);
+  float* d_lab = (float*)carve(sizeof(float) * B);
+  int32_t* d_mh = (int32_t*)carve(sizeof(int32_t) * pm);
+  int32_t* d_mr = (int32_t*)carve(sizeof(int32_t) * pm);
+  int32_t* d_mt = (int32_t*)carve(sizeof(int32_t) * pm);
+  float* d_loss = (float*)(base + off);
+  CUDA_TRY(cudaMemcpyAsync(d_user, user_indices, sizeof(int64_t) * B, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_item, item_indices, sizeof(int64_t) * B, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_lab, labels, sizeof(float) * B, cudaMemcpyHostToDevice, st));
+  int rc = mvin_gather_feed(h, d_user, B, d_mh, d_mr, d_mt, stream);
+  if (rc) return rc;
+  rc = mvin_forward(h, d_user, d_item, d_mh, d_mr, d_mt, B, nullptr, nullptr, workspace, stream);
+  if (rc) return rc;
+  rc = mvin_backward(h, d_lab, B, d_loss, workspace, stream);
+  if (rc) return rc;
+  if (adam_m && adam_v) {
+    rc = mvin_adam_step(h, adam_m, adam_v, lr, 0.9f, 0.999f, 1e-8f, step, stream);
+    if (rc) return rc;
+  }
+  CUDA_TRY(cudaMemcpyAsync(losses_host, d_loss, sizeof(float) * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
   return MVIN_OK;
 }
 

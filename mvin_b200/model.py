@@ -390,6 +390,42 @@ class MVIN(object):
                 self.adam_step_device()
         return losses
 
+    # ------------------------------------------------------------------ device-resident feed
+    def bind_user_triplet_set(self, user_triplet_set):
+        """Upload the packed ripple sets once: int32 [n_user, max(1,p), 3, n_memory] (data_loader_user_set.py:402 stacks
+        one [p, 3, m] block per user).  After this, train_users / gather_feed replace get_feed_dict (train.py:112-122)."""
+        uts = np.ascontiguousarray(np.asarray(user_triplet_set), dtype=np.int32)
+        want = (max(1, self.p_hop), 3, self.n_memory)
+        if uts.ndim != 4 or tuple(uts.shape[1:]) != want:
+            raise ValueError(f"user_triplet_set must be [n_user, {want[0]}, 3, {want[2]}], got {uts.shape}")
+        self._uts = torch.from_numpy(uts).to(self.device)
+        check(self.lib.mvin_bind_user_triplets(self._handle, self._uts.data_ptr()), "mvin_bind_user_triplets")
+
+    def gather_feed(self, users):
+        """users: int64 CUDA tensor [B] -> (mem_h, mem_r, mem_t) int32 CUDA tensors [max(1,p), B, m]."""
+        B = users.shape[0]
+        shape = (max(1, self.p_hop), B, self.n_memory)
+        out = [torch.empty(shape, dtype=torch.int32, device=self.device) for _ in range(3)]
+        check(self.lib.mvin_gather_feed(self._handle, users.data_ptr(), B, out[0].data_ptr(), out[1].data_ptr(),
+                                        out[2].data_ptr(), self._stream()), "mvin_gather_feed")
+        return tuple(out)
+
+    def train_users(self, users, items, labels, apply_adam=True):
+        """train(sess, get_feed_dict(...)) of the reference loop (train.py:62-64) with the feed assembled on the
+        device: only user / item / label cross the bus.  HOST numpy or pinned torch buffers; returns the 4 losses."""
+        if self.n_shards > 1:
+            raise NotImplementedError("device-resident feed path: single-table configurations only")
+        B = items.shape[0]
+        ws = self._ensure_workspace(B)
+        ptr = lambda a: a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr()
+        if apply_adam:
+            self.step += 1
+        check(self.lib.mvin_train_step_users_host(
+            self._handle, ptr(users), ptr(items), ptr(labels), B, self._staging.data_ptr(), ws.data_ptr(),
+            C.byref(self._m_struct) if apply_adam else None, C.byref(self._v_struct) if apply_adam else None, self.lr,
+            max(self.step, 1), self._losses_host.data_ptr(), self._stream()), "mvin_train_step_users_host")
+        return self._losses_host.numpy().copy()
+
     def allreduce_replicated(self, losses=None):
         """One-process-per-GPU ranks: SUM all-reduce (NCCL) of the gradients of every replicated parameter (all but
         the sharded entity table, whose contributions already landed in the owners' shards through peer
