@@ -109,7 +109,7 @@ struct mvin_handle_s {
   float dense_l2_scale = 1.f;
   // fork/join helpers: independent kernels of a step run on two internal side streams (disabled while profiling)
   cudaStream_t side[2] = {nullptr, nullptr};
-  cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr}, ev_mid = nullptr;
   bool use_streams = true;
   int entity_leaf_mode = -1;       // -1 auto, 0 off, 1 on (env MVIN_B200_ENTITY_LEAF, read in mvin_create)
   int user_pb_fwd = 4;             // max pairs per CTA of the user-side forward kernel (env MVIN_B200_USER_PB_FWD)
@@ -153,6 +153,9 @@ struct Par {
     cudaEventRecord(h->ev_join[i], h->side[i]);
     cudaStreamWaitEvent(main, h->ev_join[i], 0);
   }
+  // partial join: the launch stream waits for what side stream 0 has been given so far, the side stream carries on
+  void mark_mid() const { if (on) cudaEventRecord(h->ev_mid, h->side[0]); }
+  void wait_mid() const { if (on) cudaStreamWaitEvent(main, h->ev_mid, 0); }
 };
 
 inline bool has_agg(int H, int i, int h) { return i < H && h < H - i; }          // aggregator step (i, h) exists
@@ -598,10 +601,6 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
   par.fork(0);
   {
   cudaStream_t st = par.s(0);
-  CUDA_TRY(cudaMemsetAsync(at<char>(ws, L.zero_mid), 0, L.zero_end - L.zero_mid, st));
-  // sharded mode: peers scatter into this rank's shard, so the CALLER zeroes it (and synchronises the ranks)
-  if (h->n_shards == 1) CUDA_TRY(cudaMemsetAsync(G.entity_emb, 0, sizeof(float) * (size_t)c.n_entity * D, st));
-  prof_mark(h, st, "memset");
   // dense L2 terms: initialise every other gradient buffer with coef * param (model.py:388-410)
   {
     L2Segments sg;
@@ -639,6 +638,11 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
   // transposed weights: wT[i] = W_a[i]^T (i < H), wT[H + e] = W_t[e]^T (e <= H)
   transpose_kernel<<<dim3(2 * H + 1), 256, 0, st>>>(P.agg_w, P.transfer_w, H, D, wT);
   LAUNCH_CHECK(h, "transpose");
+  par.mark_mid();          // the first backward kernels need only the two launches above
+  CUDA_TRY(cudaMemsetAsync(at<char>(ws, L.zero_mid), 0, L.zero_end - L.zero_mid, st));
+  // sharded mode: peers scatter into this rank's shard, so the CALLER zeroes it (and synchronises the ranks)
+  if (h->n_shards == 1) CUDA_TRY(cudaMemsetAsync(G.entity_emb, 0, sizeof(float) * (size_t)c.n_entity * D, st));
+  prof_mark(h, st, "memset");
   // ripple-memory relation histogram (feeds the un-normalised L2 over gathered RK matrices, model.py:386)
   if (p > 0) {
     const long n = (long)p * B * m;
@@ -656,7 +660,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
                                                                     1.f / (float)(h->global_batch > 0 ? h->global_batch : B), ditem, du, acc);
     LAUNCH_CHECK(h, "loss_bwd");
   }
-  par.join(0);
+  par.wait_mid();
   // mix backward: dW_mix[j] = V[j][0]^T ditem (grouped), DC[j][0] = ditem . W_mix[j]^T (batched)
   {
     DwArgs a;
@@ -708,6 +712,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
       a.ds = at<float>(ws, L.ds) + (long)i * nr;
       a.K = K; a.n_rel = nr;
       if (i == 0) {
+        par.join(0);       // zeroed dE / GSe / dQ / cnt are first needed here
         a.E = h->etab; a.WtT = wT + (long)(H + H) * D * D;
         a.dWt = G.transfer_w + (long)H * D * D; a.dbt = G.transfer_b + (long)H * D;
         a.dE = h->gtab; a.du = du;
@@ -903,7 +908,8 @@ int mvin_create(const mvin_config_t* cfg, mvin_handle_t* out) {
   for (int i = 0; i < 2; ++i) {
     if (cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork[i], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming) != cudaSuccess ||
+        (i == 0 && cudaEventCreateWithFlags(&h->ev_mid, cudaEventDisableTiming) != cudaSuccess)) {
       return fail(MVIN_ERR_CUDA, "stream / event creation: %s", cudaGetErrorString(cudaGetLastError()));
     }
   }
@@ -929,6 +935,7 @@ int mvin_destroy(mvin_handle_t h) {
     if (h->side[i]) cudaStreamDestroy(h->side[i]);
     if (h->ev_fork[i]) cudaEventDestroy(h->ev_fork[i]);
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    if (i == 0 && h->ev_mid) cudaEventDestroy(h->ev_mid);
   }
   delete h;
   return MVIN_OK;
