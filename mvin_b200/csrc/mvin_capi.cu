@@ -111,6 +111,9 @@ struct mvin_handle_s {
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr}, ev_mid = nullptr;
   bool use_streams = true;
+  bool early_init = false;         // backward part 0 of this step was already enqueued (host-step entry points)
+  cudaEvent_t ev_early = nullptr, ev_item = nullptr;   // its completion; 'item ids are on the device'
+  bool pre_fork = false;           // forward: the side stream starts from ev_item instead of the launch stream's tail
   int entity_leaf_mode = -1;       // -1 auto, 0 off, 1 on (env MVIN_B200_ENTITY_LEAF, read in mvin_create)
   int user_pb_fwd = 4;             // max pairs per CTA of the user-side forward kernel (env MVIN_B200_USER_PB_FWD)
   int stream_mode = -1;            // -1 auto, 0 never, 1 always (env MVIN_B200_STREAM)
@@ -366,7 +369,12 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
   // per-entity leaf aggregate are independent of the user side that runs on the launch stream meanwhile
   const Par par{h, st, h->use_streams && !h->prof_on};
   int32_t* stamp = L.entity_leaf ? at<int32_t>(ws, L.stamp) : nullptr;
-  par.fork(0);
+  if (par.on && h->pre_fork) {
+    CUDA_TRY(cudaStreamWaitEvent(h->side[0], h->ev_item, 0));   // only the item ids are needed on this branch
+    h->pre_fork = false;
+  } else {
+    par.fork(0);
+  }
   {
     cudaStream_t st = par.s(0);
     if (stamp) CUDA_TRY(cudaMemsetAsync(stamp, 0, sizeof(int32_t) * (size_t)c.n_entity, st));
@@ -566,41 +574,22 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
 }
 
 // ------------------------------------------------------------------------------------------------------
-// backward
+// backward, part 0: everything that depends on the parameters only -- zeroed accumulators, gradient buffers
+// initialised with their dense L2 terms, transposed weights.  `mid` (optional) is recorded once the part the first
+// backward kernels need is enqueued.  The host-step entry points run it on a side stream while the feed is still
+// crossing the bus.
 // ------------------------------------------------------------------------------------------------------
 template <int D>
-int launch_dw(mvin_handle_t h, cudaStream_t st, const DwArgs& a, int groups, const char* name) {
-  using C = TC<D>;
-  const size_t sm = dw_smem<D>();
-  int rc;
-  if ((rc = set_smem(dw_kernel<D>, sm))) return rc;
-  long tiles = (a.rows + C::R - 1) / C::R;
-  int gx = (int)(tiles < h->sm_count ? tiles : h->sm_count);
-  dw_kernel<D><<<dim3(gx, groups), C::NT, sm, st>>>(a);
-  LAUNCH_CHECK(h, name);
-  return MVIN_OK;
-}
-
-template <int D>
-int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out, void* ws, cudaStream_t st) {
-  using C = TC<D>;
+int backward_init(mvin_handle_t h, int B, void* ws, cudaStream_t st, cudaEvent_t mid, bool zero_small) {
   const mvin_config_t& c = h->cfg;
-  const int K = c.neighbor_sample_size, H = c.h_hop, p = c.p_hop, m = c.n_memory, nr = c.n_relation;
+  const int H = c.h_hop, p = c.p_hop, nr = c.n_relation;
   const Layout L = make_layout(c, B, use_entity_leaf(c, B, h->n_shards, h->entity_leaf_mode));
   const mvin_params_t& P = h->P;
   const mvin_params_t& G = h->G;
   const float l2w = c.l2_weight, l2a = c.l2_agg_weight;
-  int rc;
   float* acc = at<float>(ws, L.acc);
   float* wT = at<float>(ws, L.wT);
-  prof_mark(h, st, nullptr);
-
-  CUDA_TRY(cudaMemsetAsync(at<char>(ws, L.zero_begin), 0, L.zero_mid - L.zero_begin, st));
-  // side stream 0: gradient-buffer initialisation that does not depend on the batch's activations
-  const Par par{h, st, h->use_streams && !h->prof_on};
-  par.fork(0);
-  {
-  cudaStream_t st = par.s(0);
+  if (zero_small) CUDA_TRY(cudaMemsetAsync(at<char>(ws, L.zero_begin), 0, L.zero_mid - L.zero_begin, st));
   // dense L2 terms: initialise every other gradient buffer with coef * param (model.py:388-410)
   {
     L2Segments sg;
@@ -638,11 +627,58 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
   // transposed weights: wT[i] = W_a[i]^T (i < H), wT[H + e] = W_t[e]^T (e <= H)
   transpose_kernel<<<dim3(2 * H + 1), 256, 0, st>>>(P.agg_w, P.transfer_w, H, D, wT);
   LAUNCH_CHECK(h, "transpose");
-  par.mark_mid();          // the first backward kernels need only the two launches above
+  if (mid) cudaEventRecord(mid, st);
   CUDA_TRY(cudaMemsetAsync(at<char>(ws, L.zero_mid), 0, L.zero_end - L.zero_mid, st));
   // sharded mode: peers scatter into this rank's shard, so the CALLER zeroes it (and synchronises the ranks)
   if (h->n_shards == 1) CUDA_TRY(cudaMemsetAsync(G.entity_emb, 0, sizeof(float) * (size_t)c.n_entity * D, st));
   prof_mark(h, st, "memset");
+  return MVIN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------------
+template <int D>
+int launch_dw(mvin_handle_t h, cudaStream_t st, const DwArgs& a, int groups, const char* name) {
+  using C = TC<D>;
+  const size_t sm = dw_smem<D>();
+  int rc;
+  if ((rc = set_smem(dw_kernel<D>, sm))) return rc;
+  long tiles = (a.rows + C::R - 1) / C::R;
+  int gx = (int)(tiles < h->sm_count ? tiles : h->sm_count);
+  dw_kernel<D><<<dim3(gx, groups), C::NT, sm, st>>>(a);
+  LAUNCH_CHECK(h, name);
+  return MVIN_OK;
+}
+
+template <int D>
+int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out, void* ws, cudaStream_t st) {
+  using C = TC<D>;
+  const mvin_config_t& c = h->cfg;
+  const int K = c.neighbor_sample_size, H = c.h_hop, p = c.p_hop, m = c.n_memory, nr = c.n_relation;
+  const Layout L = make_layout(c, B, use_entity_leaf(c, B, h->n_shards, h->entity_leaf_mode));
+  const mvin_params_t& P = h->P;
+  const mvin_params_t& G = h->G;
+  const float l2w = c.l2_weight, l2a = c.l2_agg_weight;
+  int rc;
+  float* acc = at<float>(ws, L.acc);
+  float* wT = at<float>(ws, L.wT);
+  prof_mark(h, st, nullptr);
+
+  // part 0 (parameters only) on side stream 0 -- unless a host-step entry point already ran it during the feed copy
+  const Par par{h, st, h->use_streams && !h->prof_on};
+  if (h->early_init) {
+    CUDA_TRY(cudaStreamWaitEvent(st, h->ev_early, 0));
+    h->early_init = false;
+    par.fork(0);
+    par.mark_mid();
+  } else {
+    CUDA_TRY(cudaMemsetAsync(at<char>(ws, L.zero_begin), 0, L.zero_mid - L.zero_begin, st));   // loss accumulators
+    par.fork(0);
+    if ((rc = backward_init<D>(h, B, ws, par.s(0), par.on ? h->ev_mid : nullptr, false))) return rc;
+  }
+  {
+  cudaStream_t st = par.s(0);
   // ripple-memory relation histogram (feeds the un-normalised L2 over gathered RK matrices, model.py:386)
   if (p > 0) {
     const long n = (long)p * B * m;
@@ -874,6 +910,24 @@ int dispatch_forward(mvin_handle_t h, const int64_t* item, const int32_t* mh, co
                      int B, float* scores, float* sn, void* ws, cudaStream_t st) {
   DISPATCH_D(h->cfg.dim, (forward_impl<DD>(h, item, mh, mr, mt, B, scores, sn, ws, st)));
 }
+int dispatch_backward_init(mvin_handle_t h, int B, void* ws, cudaStream_t st) {
+  DISPATCH_D(h->cfg.dim, (backward_init<DD>(h, B, ws, st, nullptr, true)));
+}
+// Host-step entry points: once the item ids are on the device the KG side of the forward can start, and the
+// parameter-only part of the backward can run right away -- both overlap the H2D copy of the ripple memories.
+int host_step_overlap(mvin_handle_t h, int B, void* ws, cudaStream_t st) {
+  h->early_init = false;
+  h->pre_fork = false;
+  if (!h->use_streams || h->prof_on || !h->has_grads) return MVIN_OK;
+  CUDA_TRY(cudaEventRecord(h->ev_item, st));
+  h->pre_fork = true;
+  CUDA_TRY(cudaStreamWaitEvent(h->side[1], h->ev_item, 0));
+  int rc = dispatch_backward_init(h, B, ws, h->side[1]);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(h->ev_early, h->side[1]));
+  h->early_init = true;
+  return MVIN_OK;
+}
 int dispatch_backward(mvin_handle_t h, const float* labels, int B, float* losses, void* ws, cudaStream_t st) {
   DISPATCH_D(h->cfg.dim, (backward_impl<DD>(h, labels, B, losses, ws, st)));
 }
@@ -909,7 +963,9 @@ int mvin_create(const mvin_config_t* cfg, mvin_handle_t* out) {
     if (cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork[i], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming) != cudaSuccess ||
-        (i == 0 && cudaEventCreateWithFlags(&h->ev_mid, cudaEventDisableTiming) != cudaSuccess)) {
+        (i == 0 && (cudaEventCreateWithFlags(&h->ev_mid, cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&h->ev_early, cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&h->ev_item, cudaEventDisableTiming) != cudaSuccess))) {
       return fail(MVIN_ERR_CUDA, "stream / event creation: %s", cudaGetErrorString(cudaGetLastError()));
     }
   }
@@ -936,6 +992,8 @@ int mvin_destroy(mvin_handle_t h) {
     if (h->ev_fork[i]) cudaEventDestroy(h->ev_fork[i]);
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
     if (i == 0 && h->ev_mid) cudaEventDestroy(h->ev_mid);
+    if (i == 0 && h->ev_early) cudaEventDestroy(h->ev_early);
+    if (i == 0 && h->ev_item) cudaEventDestroy(h->ev_item);
   }
   delete h;
   return MVIN_OK;
@@ -1175,12 +1233,14 @@ int mvin_train_step_host(mvin_handle_t h, const int64_t* user_indices, const int
   const int64_t* d_user = (const int64_t*)stage(user_indices, sizeof(int64_t) * B);
   const int64_t* d_item = (const int64_t*)stage(item_indices, sizeof(int64_t) * B);
   const float* d_lab = (const float*)stage(labels, sizeof(float) * B);
+  int rc = host_step_overlap(h, B, workspace, st);
+  if (rc) return rc;
   const int32_t* d_mh = (const int32_t*)stage(mem_h, sizeof(int32_t) * pm);
   const int32_t* d_mr = (const int32_t*)stage(mem_r, sizeof(int32_t) * pm);
   const int32_t* d_mt = (const int32_t*)stage(mem_t, sizeof(int32_t) * pm);
   float* d_loss = (float*)(base + off);
   CUDA_TRY(cudaGetLastError());
-  int rc = mvin_forward(h, d_user, d_item, d_mh, d_mr, d_mt, B, nullptr, nullptr, workspace, stream);
+  rc = mvin_forward(h, d_user, d_item, d_mh, d_mr, d_mt, B, nullptr, nullptr, workspace, stream);
   if (rc) return rc;
   rc = mvin_backward(h, d_lab, B, d_loss, workspace, stream);
   if (rc) return rc;
@@ -1271,7 +1331,9 @@ int mvin_train_step_users_host(mvin_handle_t h, const int64_t* user_indices, con
   CUDA_TRY(cudaMemcpyAsync(d_user, user_indices, sizeof(int64_t) * B, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(d_item, item_indices, sizeof(int64_t) * B, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(d_lab, labels, sizeof(float) * B, cudaMemcpyHostToDevice, st));
-  int rc = mvin_gather_feed(h, d_user, B, d_mh, d_mr, d_mt, stream);
+  int rc = host_step_overlap(h, B, workspace, st);
+  if (rc) return rc;
+  rc = mvin_gather_feed(h, d_user, B, d_mh, d_mr, d_mt, stream);
   if (rc) return rc;
   rc = mvin_forward(h, d_user, d_item, d_mh, d_mr, d_mt, B, nullptr, nullptr, workspace, stream);
   if (rc) return rc;

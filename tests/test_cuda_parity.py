@@ -331,10 +331,16 @@ def test_device_resident_feed_matches_feed_dict():
         fd[a.memories_h[i]] = trip[:, i, 0]
         fd[a.memories_r[i]] = trip[:, i, 1]
         fd[a.memories_t[i]] = trip[:, i, 2]
+    # gradients of one step without Adam (atomic accumulation order differs run to run: 1e-5 of the largest entry)
+    la = a.loss_and_grads(fd)
+    lb = b.train_users(users, items, labels, apply_adam=False)
+    assert abs(float(la[0]) - float(lb[0])) <= 1e-6 * max(1.0, abs(float(la[0])))
+    ga, gb = a.named_gradients(), b.named_gradients()
+    for k in ga:
+        assert np.abs(ga[k] - gb[k]).max() <= 1e-5 * max(np.abs(ga[k]).max(), 1e-8), k
+    # two Adam steps: same loss trajectory (Adam amplifies round-off on near-zero gradients, so parameters are not
+    # compared entry by entry)
     for _ in range(2):
-        _, la = a.train(None, fd)
-        lb = b.train_users(users, items, labels)
-        assert abs(la - float(lb[0])) <= 1e-6 * max(1.0, abs(la))
-    pa, pb = a.named_parameters(), b.named_parameters()
-    for k in pa:
-        assert np.allclose(pa[k], pb[k], rtol=1e-5, atol=1e-7), k
+        _, l1 = a.train(None, fd)
+        l2 = b.train_users(users, items, labels)
+        assert abs(l1 - float(l2[0])) <= 1e-5 * max(1.0, abs(l1))
