@@ -142,6 +142,106 @@ __global__ void score_kernel(const float* __restrict__ u, const float* __restric
   }
 }
 
+// ---- wide&deep mix + score in one launch (model.py:309-315, :158-159):
+//   item[b] = concat_j V[j][0][b] . W_mix + b_mix ;  score[b] = u[b] . item[b]
+// RT rows per CTA; thread (r, tx) owns 4 output columns of row r; the concatenated inputs sit in shared memory, the
+// weights are read through L1 (every CTA reads the same (H+1) d^2 floats).
+template <int D>
+__global__ void __launch_bounds__(256) mix_score_kernel(const float* __restrict__ Vtop /* [H+1][B][D] */,
+                                                        const float* __restrict__ W, const float* __restrict__ bias,
+                                                        const float* __restrict__ u, int B, int H1,
+                                                        float* __restrict__ item, float* __restrict__ scores,
+                                                        float* __restrict__ scores_norm) {
+  constexpr int LPR = D / 4, RT = 256 / LPR;
+  extern __shared__ __align__(16) float a_s[];            // [RT][H1 * D]
+  const int tid = threadIdx.x, tx = tid % LPR, r = tid / LPR;
+  const long row0 = (long)blockIdx.x * RT;
+  const int KD = H1 * D;
+  for (int i = tid; i < RT * H1 * LPR; i += 256) {
+    const int rr = i / (H1 * LPR), rem = i % (H1 * LPR), j = rem / LPR, c4 = rem % LPR;
+    float4 v = f4zero();
+    if (row0 + rr < B) v = ldg4(Vtop + ((long)j * B + row0 + rr) * D + c4 * 4);
+    st4(&a_s[rr * KD + j * D + c4 * 4], v);
+  }
+  __syncthreads();
+  const long b = row0 + r;
+  float4 acc = ldg4(bias + tx * 4);
+  const float* ar = a_s + r * KD;
+  const float* Wc = W + tx * 4;
+#pragma unroll 8
+  for (int k = 0; k < KD; ++k) acc = f4fma(ar[k], ldg4(Wc + (long)k * D), acc);
+  float part = 0.f;
+  if (b < B) {
+    st4(item + b * D + tx * 4, acc);
+    part = f4dot(acc, ldg4(u + b * D + tx * 4));
+  }
+  part = group_sum<LPR>(part);
+  if (b < B && tx == 0) {
+    scores[b] = part;
+    if (scores_norm) scores_norm[b] = 1.f / (1.f + expf(-part));
+  }
+}
+
+// ---- loss gradient + mix-layer backward in one launch (model.py:379-380, :309-315 backward), d <= 64:
+//   g = (sigmoid(score) - label) / B ;  ditem = g u ;  du = g item ;  DC[j][b] = ditem[b] . W_mix[j]^T
+// W_mix^T is staged in shared memory once per CTA; RT rows per tile.
+template <int D>
+__global__ void __launch_bounds__(256) loss_mix_bwd_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
+                                                           const float* __restrict__ u, const float* __restrict__ item,
+                                                           const float* __restrict__ W, int B, int H1, float invB,
+                                                           float* __restrict__ ditem, float* __restrict__ du,
+                                                           float* __restrict__ DC /* [H1][B][D] */,
+                                                           float* __restrict__ bce_acc) {
+  constexpr int LPR = D / 4, RT = 16;
+  extern __shared__ __align__(16) float sm[];
+  const int KO = H1 * D;                                   // outputs per row
+  float* wt_s = sm;                                        // [D (k)][KO]   wt_s[k][j D + n] = W[(j D + n) D + k]... see below
+  float* d_s = wt_s + D * KO;                              // [RT][D] ditem tile
+  __shared__ float red;
+  const int tid = threadIdx.x;
+  if (tid == 0) red = 0.f;
+  // DC[j][b][n] = sum_k ditem[b][k] W[(j D + n)][k]  with W [(H+1) D, D] row-major  ->  stage transposed: [k][j D + n]
+  for (int i = tid; i < KO * D; i += 256) {
+    const int o = i / D, k = i % D;                        // coalesced read of W rows
+    wt_s[k * KO + o] = __ldg(W + i);
+  }
+  __syncthreads();
+  float bce = 0.f;
+  for (long row0 = (long)blockIdx.x * RT; row0 < B; row0 += (long)gridDim.x * RT) {
+    for (int i = tid; i < RT * LPR; i += 256) {
+      const int rr = i / LPR, c4 = i % LPR;
+      const long b = row0 + rr;
+      float4 di = f4zero();
+      if (b < B) {
+        const float x = scores[b], z = labels[b];
+        const float gsc = (1.f / (1.f + expf(-x)) - z) * invB;
+        di = f4scale(ldg4(u + b * D + c4 * 4), gsc);
+        st4(ditem + b * D + c4 * 4, di);
+        st4(du + b * D + c4 * 4, f4scale(ldg4(item + b * D + c4 * 4), gsc));
+        if (c4 == 0) bce += fmaxf(x, 0.f) - x * z + log1pf(expf(-fabsf(x)));
+      }
+      st4(&d_s[rr * D + c4 * 4], di);
+    }
+    __syncthreads();
+    for (int i = tid; i < RT * (KO / 4); i += 256) {
+      const int rr = i / (KO / 4), oc = i % (KO / 4);
+      const long b = row0 + rr;
+      if (b >= B) continue;
+      float4 acc = f4zero();
+      const float* dr = d_s + rr * D;
+#pragma unroll 8
+      for (int k = 0; k < D; ++k) acc = f4fma(dr[k], ld4(&wt_s[k * KO + oc * 4]), acc);
+      const int j = (oc * 4) / D, n = (oc * 4) % D;
+      st4(DC + ((long)j * B + b) * D + n, acc);
+    }
+    __syncthreads();
+  }
+  bce = warp_sum(bce);
+  if (tid % 32 == 0 && bce != 0.f) atomicAdd(&red, bce);
+  __syncthreads();
+  if (tid == 0 && red != 0.f) atomicAdd(bce_acc, red * invB);
+}
+
 // base loss (model.py:379-380) and its gradient (invB = 1 / batch size of the whole job): g = (sigmoid(x) - z) / B ; ditem = g u ; du = g item
 template <int D>
 __global__ void loss_bwd_kernel(const float* __restrict__ scores, const float* __restrict__ labels,

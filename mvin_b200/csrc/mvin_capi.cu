@@ -552,22 +552,16 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
       LAUNCH_CHECK(h, names[i]);
     }
   }
-  // wide&deep mix (model.py:309-315): item = concat(V[0][0] .. V[H][0]) . W_mix + b_mix, one batch-reduce GEMM
+  // wide&deep mix + score (model.py:309-315, :158-159) in one launch: item = concat(V[0][0] .. V[H][0]) . W_mix + b_mix,
+  // score = u . item   (the level-0 slices V[0..H][0] are contiguous)
   {
-    GemmArgs g = gemm_args();
-    g.A = at<float>(ws, L.V[0][0]); g.sa_m = D; g.sa_k = 1; g.bsA = (long)B * D;
-    g.B = P.mix_w; g.sb_k = D; g.sb_n = 1; g.bsB = (long)D * D;
-    g.C = at<float>(ws, L.item); g.ldc = D;
-    g.bias = P.mix_b;
-    g.M = B; g.N = D; g.K = D; g.nbatch = H + 1; g.reduce = 1;
-    if ((rc = run_gemm(h, st, g, "gemm_mix"))) return rc;
-  }
-  // score (model.py:158-159)
-  {
-    const long n = (long)B * C::LPR;
-    score_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(at<float>(ws, L.u), at<float>(ws, L.item), B,
-                                                                 at<float>(ws, L.scores), scores_norm);
-    LAUNCH_CHECK(h, "score");
+    constexpr int RT = 256 / C::LPR;
+    const size_t sm = sizeof(float) * RT * (H + 1) * D;
+    if ((rc = set_smem(mix_score_kernel<D>, sm))) return rc;
+    mix_score_kernel<D><<<(unsigned)((B + RT - 1) / RT), 256, sm, st>>>(at<float>(ws, L.V[0][0]), P.mix_w, P.mix_b,
+                                                                        at<float>(ws, L.u), B, H + 1, at<float>(ws, L.item),
+                                                                        at<float>(ws, L.scores), scores_norm);
+    LAUNCH_CHECK(h, "mix_score");
     if (scores) CUDA_TRY(cudaMemcpyAsync(scores, at<float>(ws, L.scores), sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
   }
   return MVIN_OK;
@@ -689,11 +683,20 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
 
   float* du = at<float>(ws, L.du);
   float* ditem = at<float>(ws, L.ditem);
-  {
+  const float invB = 1.f / (float)(h->global_batch > 0 ? h->global_batch : B);
+  const bool fused_mix_bwd = D <= 64;          // W_mix^T ((H+1) d^2 floats) is staged in shared memory
+  if (fused_mix_bwd) {
+    // loss gradient + mix backward in one launch: ditem, du, DC[j][0] = ditem . W_mix[j]^T
+    const size_t sm = sizeof(float) * ((size_t)D * (H + 1) * D + 16 * D);
+    if ((rc = set_smem(loss_mix_bwd_kernel<D>, sm))) return rc;
+    const int grid = (B + 15) / 16 < 2 * h->sm_count ? (B + 15) / 16 : 2 * h->sm_count;
+    loss_mix_bwd_kernel<D><<<grid, 256, sm, st>>>(at<float>(ws, L.scores), labels, at<float>(ws, L.u), at<float>(ws, L.item),
+                                                  P.mix_w, B, H + 1, invB, ditem, du, at<float>(ws, L.DC[0][0]), acc);
+    LAUNCH_CHECK(h, "loss_mix_bwd");
+  } else {
     const long n = (long)B * C::LPR;
     loss_bwd_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(at<float>(ws, L.scores), labels, at<float>(ws, L.u),
-                                                                    at<float>(ws, L.item), B,
-                                                                    1.f / (float)(h->global_batch > 0 ? h->global_batch : B), ditem, du, acc);
+                                                                    at<float>(ws, L.item), B, invB, ditem, du, acc);
     LAUNCH_CHECK(h, "loss_bwd");
   }
   par.wait_mid();
@@ -705,12 +708,14 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     a.G = ditem; a.db = G.mix_b; a.rows = B;
     par.fork(1);                                   // side stream 1: weight gradient of the mix layer
     if ((rc = launch_dw<D>(h, par.s(1), a, H + 1, "dw_mix"))) return rc;
-    GemmArgs g = gemm_args();
-    g.A = ditem; g.sa_m = D; g.sa_k = 1; g.bsA = 0;
-    g.B = P.mix_w; g.sb_k = 1; g.sb_n = D; g.bsB = (long)D * D;   // W_mix[jD + n][k] -> transposed use
-    g.C = at<float>(ws, L.DC[0][0]); g.ldc = D; g.bsC = (long)B * D;
-    g.M = B; g.N = D; g.K = D; g.nbatch = H + 1;
-    if ((rc = run_gemm(h, st, g, "gemm_mix_bwd"))) return rc;
+    if (!fused_mix_bwd) {
+      GemmArgs g = gemm_args();
+      g.A = ditem; g.sa_m = D; g.sa_k = 1; g.bsA = 0;
+      g.B = P.mix_w; g.sb_k = 1; g.sb_n = D; g.bsB = (long)D * D;   // W_mix[jD + n][k] -> transposed use
+      g.C = at<float>(ws, L.DC[0][0]); g.ldc = D; g.bsC = (long)B * D;
+      g.M = B; g.N = D; g.K = D; g.nbatch = H + 1;
+      if ((rc = run_gemm(h, st, g, "gemm_mix_bwd"))) return rc;
+    }
   }
   // aggregation iterations, reversed; one launch per iteration
   {
@@ -818,6 +823,8 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     a.G = du; a.db = G.user_mlp_b; a.rows = B;
     par.fork(1);                                   // side stream 1: weight gradient of the user MLP
     if ((rc = launch_dw<D>(h, par.s(1), a, p + 1, "dw_user"))) return rc;
+    // dO = du . W_user^T as a batched GEMM (a per-warp matvec inside the ripple kernel re-reads W_user per warp and
+    // measured slower: +9 us at C2, +78 us at C3)
     GemmArgs g = gemm_args();
     g.A = du; g.sa_m = D; g.sa_k = 1;
     g.B = P.user_mlp_w; g.sb_k = 1; g.sb_n = D;
@@ -856,14 +863,20 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     GemmArgs g2 = gemm_args();
     g2.A = at<float>(ws, L.dQ); g2.sa_m = (long)nr * D; g2.sa_k = 1; g2.bsA = D;
     g2.B = P.relation_kge; g2.sb_k = 1; g2.sb_n = D; g2.bsB = (long)D * D;
-    g2.C = at<float>(ws, L.dv); g2.ldc = D; g2.bsC = 0;
     g2.M = B; g2.N = D; g2.K = D; g2.nbatch = nr; g2.reduce = 1;
-    g2.ksplit = nr >= 8 ? 4 : 1; g2.accumulate = g2.ksplit > 1;      // dv lives in the zeroed region
-    if ((rc = run_gemm(h, st, g2, "gemm_dv"))) return rc;
-    const long n = (long)B * C::LPR;
-    scatter_rows_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(at<float>(ws, L.dv), at<int32_t>(ws, L.ent[0]), B,
-                                                                        h->gtab);
-    LAUNCH_CHECK(h, "scatter_dv");
+    g2.ksplit = nr >= 8 ? 4 : 1;
+    if (h->n_shards == 1) {
+      // accumulate straight into the entity-table gradient rows of the items
+      g2.C = G.entity_emb; g2.ldc = D; g2.bsC = 0; g2.c_rows = at<int32_t>(ws, L.ent[0]); g2.accumulate = 1;
+      if ((rc = run_gemm(h, st, g2, "gemm_dv"))) return rc;
+    } else {
+      g2.C = at<float>(ws, L.dv); g2.ldc = D; g2.bsC = 0; g2.accumulate = g2.ksplit > 1;   // dv lives in the zeroed region
+      if ((rc = run_gemm(h, st, g2, "gemm_dv"))) return rc;
+      const long n = (long)B * C::LPR;
+      scatter_rows_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(at<float>(ws, L.dv), at<int32_t>(ws, L.ent[0]), B,
+                                                                          h->gtab);
+      LAUNCH_CHECK(h, "scatter_dv");
+    }
   }
   par.join(0);
   par.join(1);
