@@ -153,10 +153,14 @@ __global__ void __launch_bounds__(256) mix_score_kernel(const float* __restrict_
                                                         float* __restrict__ item, float* __restrict__ scores,
                                                         float* __restrict__ scores_norm) {
   constexpr int LPR = D / 4, RT = 256 / LPR;
-  extern __shared__ __align__(16) float a_s[];            // [RT][H1 * D]
+  extern __shared__ __align__(16) float a_s[];            // [RT][H1 * D] (+ [H1 * D][D] weights when d <= 64)
   const int tid = threadIdx.x, tx = tid % LPR, r = tid / LPR;
   const long row0 = (long)blockIdx.x * RT;
   const int KD = H1 * D;
+  constexpr bool STAGE_W = D <= 64;                        // one coalesced pass instead of KD dependent L2 round trips
+  float* w_s = a_s + RT * KD;
+  if (STAGE_W)
+    for (int i = tid * 4; i < KD * D; i += 256 * 4) st4(&w_s[i], ldg4(W + i));
   for (int i = tid; i < RT * H1 * LPR; i += 256) {
     const int rr = i / (H1 * LPR), rem = i % (H1 * LPR), j = rem / LPR, c4 = rem % LPR;
     float4 v = f4zero();
@@ -167,9 +171,15 @@ __global__ void __launch_bounds__(256) mix_score_kernel(const float* __restrict_
   const long b = row0 + r;
   float4 acc = ldg4(bias + tx * 4);
   const float* ar = a_s + r * KD;
-  const float* Wc = W + tx * 4;
+  if (STAGE_W) {
+    const float* Wc = w_s + tx * 4;
 #pragma unroll 8
-  for (int k = 0; k < KD; ++k) acc = f4fma(ar[k], ldg4(Wc + (long)k * D), acc);
+    for (int k = 0; k < KD; ++k) acc = f4fma(ar[k], ld4(Wc + k * D), acc);
+  } else {
+    const float* Wc = W + tx * 4;
+#pragma unroll 8
+    for (int k = 0; k < KD; ++k) acc = f4fma(ar[k], ldg4(Wc + (long)k * D), acc);
+  }
   float part = 0.f;
   if (b < B) {
     st4(item + b * D + tx * 4, acc);

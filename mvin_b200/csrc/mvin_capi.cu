@@ -556,7 +556,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
   // score = u . item   (the level-0 slices V[0..H][0] are contiguous)
   {
     constexpr int RT = 256 / C::LPR;
-    const size_t sm = sizeof(float) * RT * (H + 1) * D;
+    const size_t sm = sizeof(float) * ((size_t)RT * (H + 1) * D + (D <= 64 ? (size_t)(H + 1) * D * D : 0));
     if ((rc = set_smem(mix_score_kernel<D>, sm))) return rc;
     mix_score_kernel<D><<<(unsigned)((B + RT - 1) / RT), 256, sm, st>>>(at<float>(ws, L.V[0][0]), P.mix_w, P.mix_b,
                                                                         at<float>(ws, L.u), B, H + 1, at<float>(ws, L.item),
@@ -842,8 +842,12 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     a.l2_weight = l2w; a.B = B; a.m = m; a.p = p; a.n_rel = nr;
     const size_t sm = ripple_bwd_smem(m, D);
     if ((rc = set_smem(ripple_bwd_kernel<D>, sm))) return rc;
+    a.ctr = h->d_sched + 4;
     const long warps = (long)B * (p + 1);
-    ripple_bwd_kernel<D><<<(unsigned)((warps + RIPPLE_NW - 1) / RIPPLE_NW), RIPPLE_NT, sm, st>>>(a);
+    long grid = (warps + RIPPLE_NW - 1) / RIPPLE_NW;
+    const long resident = (long)h->sm_count * resident_ctas(h, ripple_bwd_kernel<D>, RIPPLE_NT, sm) * 2;   // cap 4 -> 8
+    if (grid > resident) grid = resident;
+    ripple_bwd_kernel<D><<<(unsigned)grid, RIPPLE_NT, sm, st>>>(a);
     LAUNCH_CHECK(h, "ripple_bwd");
   }
   if (p > 0) {

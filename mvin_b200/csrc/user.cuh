@@ -208,6 +208,7 @@ struct RippleBwdArgs {
   float* l2_acc;           // += sum over gathered h / t rows of |row|^2   (model.py:383-385)
   float l2_weight;
   int B, m, p, n_rel;
+  int* ctr;                // [2] work counter pair (zero between launches, see sched_exit in level.cuh)
 };
 
 // per-warp: dl[m], pr[m] floats and ids h[m], r[m], t[m]; per CTA: dwh[D] + l2[1]
@@ -229,10 +230,16 @@ __global__ void __launch_bounds__(RIPPLE_NT) ripple_bwd_kernel(RippleBwdArgs a) 
   float* l2_s = dwh_s + D;                   // [1]
   for (int i = threadIdx.x; i < D + 1; i += RIPPLE_NT) dwh_s[i] = 0.f;
   __syncthreads();
-  const long w = (long)blockIdx.x * RIPPLE_NW + warp;
-  if (w < (long)a.B * S) {
-    const long b = w / S;
-    const int s = (int)(w % S), hop = s ? s - 1 : 0;
+  // persistent CTAs; every warp pulls (pair, slot) items from a global counter.  Items of the hop slots (three row
+  // passes each) come first, the cheaper h-set items last, so the tail of the launch is made of short items.
+  const long n_items = (long)a.B * S, n_heavy = (long)a.B * a.p;
+  for (;;) {
+    long w = 0;
+    if (lane == 0) w = atomicAdd(a.ctr, 1);
+    w = __shfl_sync(FULL_MASK, w, 0);
+    if (w >= n_items) break;
+    const long b = w < n_heavy ? w % a.B : w - n_heavy;
+    const int s = w < n_heavy ? (int)(w / a.B) + 1 : 0, hop = s ? s - 1 : 0;
     const long off = ((long)hop * a.B + b) * m;
     const float* prg = a.probs + ((long)s * a.B + b) * m;
     for (int i = lane; i < m; i += 32) {
@@ -306,6 +313,7 @@ __global__ void __launch_bounds__(RIPPLE_NT) ripple_bwd_kernel(RippleBwdArgs a) 
       l2 = warp_sum(l2);
       if (lane == 0) atomicAdd(l2_s, l2);
     }
+    __syncwarp();
   }
   __syncthreads();
   if (threadIdx.x < D) {
@@ -313,6 +321,14 @@ __global__ void __launch_bounds__(RIPPLE_NT) ripple_bwd_kernel(RippleBwdArgs a) 
     if (v != 0.f) atomicAdd(a.dw_hi + threadIdx.x, v);
   }
   if (threadIdx.x == 0 && l2_s[0] != 0.f) atomicAdd(a.l2_acc, l2_s[0]);
+  if (threadIdx.x == 0) {                                  // last CTA out resets the counter pair
+    __threadfence();
+    if (atomicAdd(a.ctr + 1, 1) == (int)gridDim.x - 1) {
+      a.ctr[0] = 0;
+      a.ctr[1] = 0;
+      __threadfence();
+    }
+  }
 }
 
 }  // namespace mvin
