@@ -183,6 +183,13 @@ int mvin_train_step_users_host(mvin_handle_t h, const int64_t* user_indices, con
                                const mvin_params_t* adam_m, const mvin_params_t* adam_v, float lr, int32_t step,
                                float* losses_host, void* stream);
 
+/* CTR evaluation on the device -- replaces the per-batch sklearn calls of MVIN.eval (model.py:419-426, util.py:44-56):
+ * out3 = {roc_auc_score(labels, scores), mean((scores >= 0.5) == labels), f1_score(labels, scores >= 0.5)} from exact
+ * pair counts (ties count 1/2, as the trapezoidal ROC area does).  scores / labels / out3 device pointers;
+ * scratch40 = 40 bytes of device scratch. */
+int mvin_ctr_metrics(mvin_handle_t h, const float* scores_normalized, const float* labels, int32_t B, float* out3,
+                     void* scratch40, void* stream);
+
 /* Number of kernels the library has launched on behalf of this handle since creation (bench evidence). */
 int64_t mvin_launch_count(mvin_handle_t h);
 

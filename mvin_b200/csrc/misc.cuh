@@ -380,6 +380,57 @@ __global__ void importance_kernel(const int32_t* __restrict__ ent, const int32_t
   if (lane + 32 < K) probs[row * K + lane + 32] = e1 * inv;
 }
 
+// ---- CTR metrics on the device (model.py:419-426, util.py:44-56: per-batch sklearn roc_auc_score / accuracy / f1) ---
+// AUC = (#{(i in pos, j in neg): s_i > s_j} + 0.5 #{s_i == s_j}) / (P N): the Mann-Whitney form of the trapezoidal ROC
+// area, ties included, as exact integer pair counts (B <= 65536: P N < 2^32 pairs, counted in 64 bits).
+// acc / f1 use the reference's threshold (score >= 0.5 -> 1).  out = {auc, acc, f1}; acc64 = 5 zeroed counters.
+__global__ void ctr_count_kernel(const float* __restrict__ scores, const float* __restrict__ labels, int B,
+                                 unsigned long long* __restrict__ acc64 /* [0] 2*gt + eq, [1] P, [2] tp, [3] fp, [4] fn */) {
+  extern __shared__ float sj[];                       // tile of scores / labels of the "j" side
+  float* lj = sj + blockDim.x;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool vi = i < B;
+  const float si = vi ? scores[i] : 0.f;
+  const bool pi = vi && labels[i] > 0.5f;
+  unsigned long long cnt = 0;
+  for (int j0 = blockIdx.y * blockDim.x; j0 < B; j0 += gridDim.y * blockDim.x) {
+    const int j = j0 + threadIdx.x;
+    sj[threadIdx.x] = j < B ? scores[j] : 0.f;
+    lj[threadIdx.x] = j < B ? labels[j] : 1.f;        // padding counts as positive: never a negative partner
+    __syncthreads();
+    if (pi) {
+      const int n = min((int)blockDim.x, B - j0);
+      unsigned int c = 0;
+      for (int t = 0; t < n; ++t)
+        if (lj[t] <= 0.5f) c += si > sj[t] ? 2u : (si == sj[t] ? 1u : 0u);
+      cnt += c;
+    }
+    __syncthreads();
+  }
+  // warp + CTA reduction of the pair count; confusion-matrix counts once (blockIdx.y == 0)
+  unsigned long long v[5] = {cnt, 0, 0, 0, 0};
+  if (blockIdx.y == 0 && vi) {
+    const bool pred = si >= 0.5f;
+    v[1] = pi;
+    v[2] = pi && pred;
+    v[3] = !pi && pred;
+    v[4] = pi && !pred;
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(FULL_MASK, v[k], o);
+    if (threadIdx.x % 32 == 0 && v[k]) atomicAdd(acc64 + k, v[k]);
+  }
+}
+__global__ void ctr_finalize_kernel(const unsigned long long* __restrict__ acc64, int B, float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double P = (double)acc64[1], N = (double)B - P;
+  const double tp = (double)acc64[2], fp = (double)acc64[3], fn = (double)acc64[4];
+  out[0] = (P > 0 && N > 0) ? (float)(0.5 * (double)acc64[0] / (P * N)) : nanf("");
+  out[1] = (float)((tp + (N - fp)) / (double)B);
+  out[2] = (2 * tp + fp + fn) > 0 ? (float)(2 * tp / (2 * tp + fp + fn)) : 0.f;
+}
+
 // ---- Adam, TF1 semantics (model.py:414): dense over every segment ---------------------------------------
 struct AdamSegments {
   float* param[MAX_SEG];

@@ -1365,6 +1365,24 @@ int mvin_train_step_users_host(mvin_handle_t h, const int64_t* user_indices, con
   return MVIN_OK;
 }
 
+int mvin_ctr_metrics(mvin_handle_t h, const float* scores_normalized, const float* labels, int32_t B, float* out3,
+                     void* scratch40, void* stream) {
+  if (!h || !scores_normalized || !labels || !out3 || !scratch40 || B < 1) return fail(MVIN_ERR_INVALID, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* acc64 = static_cast<unsigned long long*>(scratch40);
+  CUDA_TRY(cudaMemsetAsync(acc64, 0, 5 * sizeof(unsigned long long), st));
+  const int nt = 256;
+  const int gx = (B + nt - 1) / nt;
+  int gy = (4 * h->sm_count + gx - 1) / gx;            // split the j range so that ~4 CTAs per SM exist
+  if (gy > gx) gy = gx;
+  if (gy < 1) gy = 1;
+  ctr_count_kernel<<<dim3(gx, gy), nt, 2 * nt * sizeof(float), st>>>(scores_normalized, labels, B, acc64);
+  LAUNCH_CHECK(h, "ctr_count");
+  ctr_finalize_kernel<<<1, 32, 0, st>>>(acc64, B, out3);
+  LAUNCH_CHECK(h, "ctr_finalize");
+  return MVIN_OK;
+}
+
 int64_t mvin_launch_count(mvin_handle_t h) { return h ? h->launches : 0; }
 
 int mvin_profile_enable(mvin_handle_t h, int32_t on) {

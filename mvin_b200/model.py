@@ -459,13 +459,22 @@ class MVIN(object):
         return items, labels, scores.cpu().numpy(), scores_n.cpu().numpy()
 
     def eval(self, sess, feed_dict):
-        from sklearn.metrics import f1_score, roc_auc_score
-        _, labels, _, scores = self._scores(feed_dict)
-        auc = roc_auc_score(y_true=labels, y_score=scores)
-        scores[scores >= 0.5] = 1
-        scores[scores < 0.5] = 0
-        f1 = f1_score(y_true=labels, y_pred=scores)
-        acc = np.mean(np.equal(scores, labels))
+        """(auc, acc, f1) of one batch (model.py:419-426) -- computed on the device (mvin_ctr_metrics: exact pair
+        counts, ties 1/2, threshold 0.5), three floats come back instead of B scores for sklearn."""
+        _, items, labels, d_users, d_items, d_labels, d_mh, d_mr, d_mt = self._device_feed(feed_dict)
+        B = items.shape[0]
+        scores_n = torch.empty(B, dtype=torch.float32, device=self.device)
+        self.forward_device(d_users, d_items, d_mh, d_mr, d_mt, None, scores_n)
+        return self.ctr_metrics_device(scores_n, d_labels)
+
+    def ctr_metrics_device(self, scores_normalized, labels):
+        """scores_normalized, labels: float32 CUDA tensors [B] -> (auc, acc, f1) python floats."""
+        out = torch.empty(3, dtype=torch.float32, device=self.device)
+        scratch = torch.empty(5, dtype=torch.int64, device=self.device)
+        check(self.lib.mvin_ctr_metrics(self._handle, scores_normalized.data_ptr(), labels.data_ptr(),
+                                        scores_normalized.shape[0], out.data_ptr(), scratch.data_ptr(), self._stream()),
+              "mvin_ctr_metrics")
+        auc, acc, f1 = out.cpu().tolist()
         return auc, acc, f1
 
     def get_scores(self, sess, feed_dict):

@@ -344,3 +344,23 @@ def test_device_resident_feed_matches_feed_dict():
         _, l1 = a.train(None, fd)
         l2 = b.train_users(users, items, labels)
         assert abs(l1 - float(l2[0])) <= 1e-5 * max(1.0, abs(l1))
+
+
+@pytest.mark.parametrize("B,ties", [(4096, False), (1000, True), (37, True), (65536, False)])
+def test_ctr_metrics_match_sklearn(B, ties):
+    """mvin_ctr_metrics (on-device AUC / ACC / F1) against the sklearn calls of model.py:419-426."""
+    from sklearn.metrics import f1_score, roc_auc_score
+    from mvin_b200 import MVIN
+    args = make_args(batch_size=8)
+    prob = make_problem(args)
+    model = MVIN(args, prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"], prob["adj_relation"])
+    rng = np.random.RandomState(B)
+    scores = rng.rand(B).astype(np.float32)
+    if ties:
+        scores = np.round(scores * 16) / 16                      # many exact ties, some exactly 0.5
+    labels = (rng.rand(B) < 0.4).astype(np.float32)
+    auc, acc, f1 = model.ctr_metrics_device(torch.from_numpy(scores).cuda(), torch.from_numpy(labels).cuda())
+    pred = (scores >= 0.5).astype(np.float32)
+    assert abs(auc - roc_auc_score(labels, scores)) < 2e-6
+    assert abs(acc - float(np.mean(pred == labels))) < 1e-6
+    assert abs(f1 - f1_score(labels, pred)) < 1e-6
