@@ -183,6 +183,16 @@ int mvin_train_step_users_host(mvin_handle_t h, const int64_t* user_indices, con
                                const mvin_params_t* adam_m, const mvin_params_t* adam_v, float lr, int32_t step,
                                float* losses_host, void* stream);
 
+/* Sampled fixed-fan-out adjacency on the device -- replaces contruct_random_adj (data_loader_user_set.py:375-388) on
+ * the undirected CSR of construct_kg (:324-343): indptr int64 [n_entity + 1], nbr / rel int32 [2 T] (device).  Rows with
+ * degree >= K get K distinct edges (uniform subset, uniform order), rows with 0 < degree < K get K draws with
+ * replacement, isolated entities stay zero.  Outputs (any may be NULL except one of adj_packed / adj_entity): the packed
+ * int32 [n_entity][2][K] record mvin_bind_adjacency takes, the reference's int64 [n_entity, K] pair, and the chosen
+ * edge slots (absolute CSR positions, -1 for isolated rows) for tests.  Reproducible for a given seed. */
+int mvin_sample_adjacency(const int64_t* indptr, const int32_t* nbr, const int32_t* rel, int32_t n_entity, int32_t K,
+                          uint64_t seed, int32_t* adj_packed, int64_t* adj_entity, int64_t* adj_relation,
+                          int64_t* picked_edges, void* stream);
+
 /* CTR evaluation on the device -- replaces the per-batch sklearn calls of MVIN.eval (model.py:419-426, util.py:44-56):
  * out3 = {roc_auc_score(labels, scores), mean((scores >= 0.5) == labels), f1_score(labels, scores >= 0.5)} from exact
  * pair counts (ties count 1/2, as the trapezoidal ROC area does).  scores / labels / out3 device pointers;

@@ -380,6 +380,59 @@ __global__ void importance_kernel(const int32_t* __restrict__ ent, const int32_t
   if (lane + 32 < K) probs[row * K + lane + 32] = e1 * inv;
 }
 
+// ---- sampled fixed-fan-out adjacency on the device (contruct_random_adj, data_loader_user_set.py:375-388) ----------
+// Per entity with degree deg in the undirected CSR (construct_kg, :324-343): deg >= K -> K distinct edges, a uniformly
+// random K-subset in uniformly random order (np.random.choice(replace=False)); 0 < deg < K -> K independent uniform
+// draws (replace=True); deg = 0 -> the row stays zero.  The reference is unseeded; a counter-based generator keyed by
+// (seed, entity, draw) makes the result reproducible and independent of the launch geometry.  One thread per entity:
+// Floyd's subset algorithm needs only the <= K picks made so far, whatever the degree (hubs reach 4e5 edges).
+MVIN_DEV unsigned long long mix64(unsigned long long x) {
+  x += 0x9e3779b97f4a7c15ull;
+  x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+  x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+  return x ^ (x >> 31);
+}
+// uniform integer in [0, n), n < 2^32 ... 2^40: 64-bit multiply-high of a 64-bit hash (bias < 2^-24)
+MVIN_DEV long rand_below(unsigned long long seed, long entity, int draw, long n) {
+  const unsigned long long h = mix64(mix64(seed ^ (unsigned long long)entity * 0xd1342543de82ef95ull) + (unsigned long long)draw);
+  return (long)__umul64hi(h, (unsigned long long)n);
+}
+__global__ void sample_adjacency_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ nbr,
+                                        const int32_t* __restrict__ rel, int n_entity, int K, unsigned long long seed,
+                                        int32_t* __restrict__ adj_packed, int64_t* __restrict__ adj_entity,
+                                        int64_t* __restrict__ adj_relation, int64_t* __restrict__ picked_edges) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_entity) return;
+  const long beg = indptr[e], deg = indptr[e + 1] - beg;
+  long pick[64];                                             // MAX_K
+  if (deg >= K) {
+    // Floyd: for j = deg-K .. deg-1: t = U[0, j]; take t unless already taken, else take j  -> uniform K-subset
+    for (int i = 0; i < K; ++i) {
+      const long j = deg - K + i;
+      long t = rand_below(seed, e, i, j + 1);
+      for (int q = 0; q < i; ++q)
+        if (pick[q] == t) { t = j; break; }
+      pick[i] = t;
+    }
+    // Fisher-Yates over the K picks -> uniformly random order
+    for (int i = K - 1; i > 0; --i) {
+      const int j = (int)rand_below(seed, e, K + i, i + 1);
+      const long tmp = pick[i]; pick[i] = pick[j]; pick[j] = tmp;
+    }
+  } else if (deg > 0) {
+    for (int i = 0; i < K; ++i) pick[i] = rand_below(seed, e, i, deg);
+  }
+  for (int i = 0; i < K; ++i) {
+    int32_t n = 0, r = 0;
+    long edge = -1;
+    if (deg > 0) { edge = beg + pick[i]; n = nbr[edge]; r = rel[edge]; }
+    if (adj_packed) { adj_packed[e * 2 * K + i] = n; adj_packed[e * 2 * K + K + i] = r; }
+    if (adj_entity) adj_entity[e * K + i] = n;
+    if (adj_relation) adj_relation[e * K + i] = r;
+    if (picked_edges) picked_edges[e * K + i] = edge;
+  }
+}
+
 // ---- CTR metrics on the device (model.py:419-426, util.py:44-56: per-batch sklearn roc_auc_score / accuracy / f1) ---
 // AUC = (#{(i in pos, j in neg): s_i > s_j} + 0.5 #{s_i == s_j}) / (P N): the Mann-Whitney form of the trapezoidal ROC
 // area, ties included, as exact integer pair counts (B <= 65536: P N < 2^32 pairs, counted in 64 bits).

@@ -1365,6 +1365,18 @@ int mvin_train_step_users_host(mvin_handle_t h, const int64_t* user_indices, con
   return MVIN_OK;
 }
 
+int mvin_sample_adjacency(const int64_t* indptr, const int32_t* nbr, const int32_t* rel, int32_t n_entity, int32_t K,
+                          uint64_t seed, int32_t* adj_packed, int64_t* adj_entity, int64_t* adj_relation,
+                          int64_t* picked_edges, void* stream) {
+  if (!indptr || !nbr || !rel || n_entity < 1 || K < 1 || K > MAX_K || (!adj_packed && !adj_entity))
+    return fail(MVIN_ERR_INVALID, "bad argument (K must be in 1..%d)", MAX_K);
+  sample_adjacency_kernel<<<(unsigned)((n_entity + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      indptr, nbr, rel, n_entity, K, (unsigned long long)seed, adj_packed, adj_entity, adj_relation, picked_edges);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MVIN_ERR_CUDA, "launch sample_adjacency: %s", cudaGetErrorString(e));
+  return MVIN_OK;
+}
+
 int mvin_ctr_metrics(mvin_handle_t h, const float* scores_normalized, const float* labels, int32_t B, float* out3,
                      void* scratch40, void* stream) {
   if (!h || !scores_normalized || !labels || !out3 || !scratch40 || B < 1) return fail(MVIN_ERR_INVALID, "bad argument");

@@ -240,3 +240,32 @@ def stacked_memories_device(user_triplet_set, users):
     trip = user_triplet_set[users]                       # [B, P, 3, m]
     t = trip.permute(2, 1, 0, 3).contiguous()            # [3, P, B, m]
     return t[0], t[1], t[2]
+
+
+def sample_adjacency_device(kg_np, n_entity: int, K: int, device, seed: int = 2020, want_edges: bool = False):
+    """GPU version of construct_kg + contruct_random_adj (data_loader_user_set.py:324-343, :375-388): the undirected
+    CSR is built with device sorts, the per-entity sampling runs in mvin_sample_adjacency.  Returns
+    (adj_packed int32 [n_entity, 2, K], adj_entity int64 [n_entity, K], adj_relation int64 [n_entity, K]) CUDA tensors
+    (+ the CSR and the chosen edge slots when want_edges)."""
+    import torch
+    from . import _lib
+    lib = _lib.load()
+    kg = torch.as_tensor(np.ascontiguousarray(kg_np), device=device).long()
+    src = torch.cat([kg[:, 0], kg[:, 2]])
+    dst = torch.cat([kg[:, 2], kg[:, 0]])
+    rr = torch.cat([kg[:, 1], kg[:, 1]])
+    order = torch.argsort(src, stable=True)
+    indptr = torch.zeros(n_entity + 1, dtype=torch.int64, device=device)
+    indptr[1:] = torch.cumsum(torch.bincount(src, minlength=n_entity), 0)
+    nbr, rel = dst[order].int().contiguous(), rr[order].int().contiguous()
+    packed = torch.zeros((n_entity, 2, K), dtype=torch.int32, device=device)
+    adj_e = torch.zeros((n_entity, K), dtype=torch.int64, device=device)
+    adj_r = torch.zeros((n_entity, K), dtype=torch.int64, device=device)
+    edges = torch.empty((n_entity, K), dtype=torch.int64, device=device) if want_edges else None
+    _lib.check(lib.mvin_sample_adjacency(indptr.data_ptr(), nbr.data_ptr(), rel.data_ptr(), n_entity, K, seed,
+                                         packed.data_ptr(), adj_e.data_ptr(), adj_r.data_ptr(),
+                                         edges.data_ptr() if want_edges else None,
+                                         torch.cuda.current_stream(device).cuda_stream), "mvin_sample_adjacency")
+    if want_edges:
+        return packed, adj_e, adj_r, (indptr, nbr, rel, edges)
+    return packed, adj_e, adj_r
