@@ -193,6 +193,17 @@ int mvin_sample_adjacency(const int64_t* indptr, const int32_t* nbr, const int32
                           uint64_t seed, int32_t* adj_packed, int64_t* adj_entity, int64_t* adj_relation,
                           int64_t* picked_edges, void* stream);
 
+/* Ripple sets on the device -- replaces get_user_triplet_set (data_loader_user_set.py:392-441) and its 12-process
+ * pool: per user and hop, every source entity (the user's positive items at hop 0: hist_items[hist_ptr[u] ..
+ * hist_ptr[u+1]); the previous hop's tails afterwards) offers a random min(degree, n_neighbor)-subset of its edges
+ * (the reference passes n_neighbor = 16); n_memory of those candidates are drawn, without replacement when there are
+ * enough; an empty candidate list repeats the previous hop.  Output: user_triplet_set int32 [n_user, max(1,p), 3,
+ * n_memory] (rows heads, relations, tails) -- the array mvin_bind_user_triplets takes.  `slots` (optional, [n_user,
+ * max(1,p), n_memory]) receives the candidate slot of each draw for tests.  n_memory <= 64, n_neighbor <= 16. */
+int mvin_build_ripple_sets(const int64_t* indptr, const int32_t* nbr, const int32_t* rel, const int64_t* hist_ptr,
+                           const int32_t* hist_items, int32_t n_user, int32_t p_hop, int32_t n_memory, int32_t n_neighbor,
+                           uint64_t seed, int32_t* user_triplet_set, int64_t* slots, void* stream);
+
 /* CTR evaluation on the device -- replaces the per-batch sklearn calls of MVIN.eval (model.py:419-426, util.py:44-56):
  * out3 = {roc_auc_score(labels, scores), mean((scores >= 0.5) == labels), f1_score(labels, scores >= 0.5)} from exact
  * pair counts (ties count 1/2, as the trapezoidal ROC area does).  scores / labels / out3 device pointers;

@@ -433,6 +433,87 @@ __global__ void sample_adjacency_kernel(const int64_t* __restrict__ indptr, cons
   }
 }
 
+// ---- ripple sets on the device (get_user_triplet_set / _get_user_triplet_set, data_loader_user_set.py:392-441) --------
+// Per user and hop: sources = the user's positive items (hop 0) or the previous hop's tails; every source contributes a
+// random min(deg, n_neighbor)-subset of its edges as candidates (random.sample, :419); n_memory candidates are then
+// drawn, without replacement if there are at least n_memory of them, else with (:431-432); an empty candidate list
+// copies the previous hop (:425-426).  One thread per user; a candidate slot is addressed as (source position, q) and
+// resolved lazily: the q-th element of the source's subset comes from Floyd's algorithm keyed by (seed, user, hop,
+// source position), so the same subset is seen by every draw that lands on that source.
+MVIN_DEV long subset_element(unsigned long long key, long deg, int take, int q) {
+  if (deg <= take) return q;                              // the whole neighbourhood: slot q is edge q
+  long pick[16];
+  for (int i = 0; i <= q; ++i) {                          // Floyd, first q + 1 picks (prefix-stable)
+    const long j = deg - take + i;
+    long t = (long)__umul64hi(mix64(key + (unsigned long long)i), (unsigned long long)(j + 1));
+    for (int z = 0; z < i; ++z)
+      if (pick[z] == t) { t = j; break; }
+    pick[i] = t;
+  }
+  return pick[q];
+}
+__global__ void ripple_sets_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ nbr,
+                                   const int32_t* __restrict__ rel, const int64_t* __restrict__ hist_ptr,
+                                   const int32_t* __restrict__ hist_items, int n_user, int P, int m, int n_neighbor,
+                                   unsigned long long seed, int32_t* __restrict__ uts /* [n_user, P, 3, m] */,
+                                   int64_t* __restrict__ slots /* optional [n_user, P, m]: candidate slot ids */) {
+  const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_user) return;
+  for (int hop = 0; hop < P; ++hop) {
+    int32_t* out = uts + ((u * P + hop) * 3) * m;
+    const int32_t* src = hop == 0 ? hist_items + hist_ptr[u] : uts + ((u * P + hop - 1) * 3 + 2) * m;
+    const long ns = hop == 0 ? hist_ptr[u + 1] - hist_ptr[u] : m;
+    long total = 0;
+    for (long i = 0; i < ns; ++i) {
+      const long d = indptr[src[i] + 1] - indptr[src[i]];
+      total += d < n_neighbor ? d : n_neighbor;
+    }
+    if (total == 0) {
+      for (int i = 0; i < 3 * m; ++i) out[i] = hop ? out[i - 3 * m] : 0;
+      if (slots) for (int i = 0; i < m; ++i) slots[(u * P + hop) * m + i] = -1;
+      continue;
+    }
+    const unsigned long long key = mix64(seed ^ ((unsigned long long)u * 0x9e3779b97f4a7c15ull + (unsigned long long)hop));
+    long pick[64];                                         // n_memory <= 64 on this path
+    if (total >= m) {
+      for (int i = 0; i < m; ++i) {
+        const long j = total - m + i;
+        long t = (long)__umul64hi(mix64(key + 0x100 + (unsigned long long)i), (unsigned long long)(j + 1));
+        for (int z = 0; z < i; ++z)
+          if (pick[z] == t) { t = j; break; }
+        pick[i] = t;
+      }
+      for (int i = m - 1; i > 0; --i) {
+        const int j = (int)__umul64hi(mix64(key + 0x200 + (unsigned long long)i), (unsigned long long)(i + 1));
+        const long tmp = pick[i]; pick[i] = pick[j]; pick[j] = tmp;
+      }
+    } else {
+      for (int i = 0; i < m; ++i)
+        pick[i] = (long)__umul64hi(mix64(key + 0x100 + (unsigned long long)i), (unsigned long long)total);
+    }
+    for (int i = 0; i < m; ++i) {
+      // candidate slot -> (source position, q)
+      long c = pick[i], pos = 0;
+      for (;; ++pos) {
+        const long d = indptr[src[pos] + 1] - indptr[src[pos]];
+        const long take = d < n_neighbor ? d : n_neighbor;
+        if (c < take) break;
+        c -= take;
+      }
+      const long head = src[pos];
+      const long beg = indptr[head], deg = indptr[head + 1] - beg;
+      const int take = (int)(deg < n_neighbor ? deg : n_neighbor);
+      const long edge = beg + subset_element(mix64(key ^ ((unsigned long long)pos * 0xd1342543de82ef95ull + 0x300)), deg, take, (int)c);
+      // the heads / tails of this hop must not overwrite the sources of the SAME hop: hop >= 1 reads the previous
+      // hop's block, hop 0 reads the history -- both distinct from `out`
+      out[i] = (int32_t)head;
+      out[m + i] = rel[edge];
+      out[2 * m + i] = nbr[edge];
+      if (slots) slots[(u * P + hop) * m + i] = pick[i];
+    }
+  }
+}
+
 // ---- CTR metrics on the device (model.py:419-426, util.py:44-56: per-batch sklearn roc_auc_score / accuracy / f1) ---
 // AUC = (#{(i in pos, j in neg): s_i > s_j} + 0.5 #{s_i == s_j}) / (P N): the Mann-Whitney form of the trapezoidal ROC
 // area, ties included, as exact integer pair counts (B <= 65536: P N < 2^32 pairs, counted in 64 bits).

@@ -1377,6 +1377,21 @@ int mvin_sample_adjacency(const int64_t* indptr, const int32_t* nbr, const int32
   return MVIN_OK;
 }
 
+int mvin_build_ripple_sets(const int64_t* indptr, const int32_t* nbr, const int32_t* rel, const int64_t* hist_ptr,
+                           const int32_t* hist_items, int32_t n_user, int32_t p_hop, int32_t n_memory, int32_t n_neighbor,
+                           uint64_t seed, int32_t* user_triplet_set, int64_t* slots, void* stream) {
+  if (!indptr || !nbr || !rel || !hist_ptr || !hist_items || !user_triplet_set || n_user < 1)
+    return fail(MVIN_ERR_INVALID, "null / bad argument");
+  if (n_memory < 1 || n_memory > 64 || n_neighbor < 1 || n_neighbor > 16)
+    return fail(MVIN_ERR_UNSUPPORTED, "device ripple sets: n_memory must be in 1..64 and n_neighbor in 1..16");
+  const int P = p_hop > 0 ? p_hop : 1;
+  ripple_sets_kernel<<<(unsigned)((n_user + 63) / 64), 64, 0, (cudaStream_t)stream>>>(
+      indptr, nbr, rel, hist_ptr, hist_items, n_user, P, n_memory, n_neighbor, (unsigned long long)seed, user_triplet_set, slots);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MVIN_ERR_CUDA, "launch ripple_sets: %s", cudaGetErrorString(e));
+  return MVIN_OK;
+}
+
 int mvin_ctr_metrics(mvin_handle_t h, const float* scores_normalized, const float* labels, int32_t B, float* out3,
                      void* scratch40, void* stream) {
   if (!h || !scores_normalized || !labels || !out3 || !scratch40 || B < 1) return fail(MVIN_ERR_INVALID, "bad argument");

@@ -269,3 +269,25 @@ def sample_adjacency_device(kg_np, n_entity: int, K: int, device, seed: int = 20
     if want_edges:
         return packed, adj_e, adj_r, (indptr, nbr, rel, edges)
     return packed, adj_e, adj_r
+
+
+def build_ripple_sets_device(csr, history: Dict[int, np.ndarray], n_user: int, p_hop: int, n_memory: int, device,
+                             n_neighbor: int = 16, seed: int = 2020, want_slots: bool = False):
+    """GPU version of get_user_triplet_set (data_loader_user_set.py:392-441): csr = (indptr int64, nbr int32, rel int32)
+    CUDA tensors (sample_adjacency_device(..., want_edges=True)[3][:3]); history: user -> positive items.  Returns the
+    packed ripple sets int32 [n_user, max(1,p), 3, m] as a CUDA tensor -- ready for MVIN.bind_user_triplet_set."""
+    import torch
+    from . import _lib
+    lib = _lib.load()
+    indptr, nbr, rel = csr
+    lens = np.array([len(history[u]) for u in range(n_user)], dtype=np.int64)
+    hist_ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)])).to(device)
+    hist_items = torch.from_numpy(np.concatenate([np.asarray(history[u], dtype=np.int32) for u in range(n_user)])).to(device)
+    P = max(1, p_hop)
+    uts = torch.zeros((n_user, P, 3, n_memory), dtype=torch.int32, device=device)
+    slots = torch.empty((n_user, P, n_memory), dtype=torch.int64, device=device) if want_slots else None
+    _lib.check(lib.mvin_build_ripple_sets(indptr.data_ptr(), nbr.data_ptr(), rel.data_ptr(), hist_ptr.data_ptr(),
+                                          hist_items.data_ptr(), n_user, p_hop, n_memory, n_neighbor, seed, uts.data_ptr(),
+                                          slots.data_ptr() if want_slots else None,
+                                          torch.cuda.current_stream(device).cuda_stream), "mvin_build_ripple_sets")
+    return (uts, slots) if want_slots else uts

@@ -70,3 +70,44 @@ def test_sampled_adjacency_is_uniform_on_a_hub():
     chi2 = ((counts - expect) ** 2 / expect).sum()
     assert abs(chi2 - (deg - 1)) < 5 * np.sqrt(2 * (deg - 1)), (chi2, deg)
     assert first.max() <= 6 + 6 * trials / deg
+
+
+@pytest.mark.parametrize("p_hop,m", [(2, 16), (1, 64), (3, 8)])
+def test_ripple_sets_device_properties(p_hop, m):
+    """mvin_build_ripple_sets against the rules of _get_user_triplet_set (data_loader_user_set.py:407-441)."""
+    from mvin_b200 import data as D
+    n_entity, n_user, n_item = 500, 60, 80
+    kg = _kg(n_entity)
+    _, _, _, (indptr, nbr, rel, _) = D.sample_adjacency_device(kg, n_entity, 4, "cuda", want_edges=True)
+    rng = np.random.RandomState(1)
+    history = {u: np.unique(rng.randint(0, n_item, rng.randint(1, 12))) for u in range(n_user)}
+    history[5] = np.array([n_entity - 1])                      # an isolated item: empty candidate list at hop 0
+    uts, slots = D.build_ripple_sets_device((indptr, nbr, rel), history, n_user, p_hop, m, "cuda", want_slots=True)
+    uts, slots = uts.cpu().numpy(), slots.cpu().numpy()
+    ip, nb, rl = indptr.cpu().numpy(), nbr.cpu().numpy(), rel.cpu().numpy()
+    edges = set()
+    for e in range(n_entity):
+        for k in range(ip[e], ip[e + 1]):
+            edges.add((e, int(rl[k]), int(nb[k])))
+    P = max(1, p_hop)
+    assert uts.shape == (n_user, P, 3, m)
+    deg = np.diff(ip)
+    for u in range(n_user):
+        for hop in range(P):
+            h, r, t = uts[u, hop]
+            if u == 5:                                         # the reference never meets this case (:425-427)
+                if hop == 0:
+                    assert not uts[u, hop].any()               # nothing to sample from, nothing to copy at hop 0
+                continue
+            src = history[u] if hop == 0 else uts[u, hop - 1, 2]
+            assert set(h.tolist()) <= set(np.asarray(src).tolist())            # heads come from the sources
+            assert all((int(a), int(b), int(c)) in edges for a, b, c in zip(h, r, t))   # true (undirected) triples
+            total = int(np.minimum(deg[np.asarray(src)], 16).sum())
+            s = slots[u, hop]
+            assert ((s >= 0) & (s < total)).all()
+            if total >= m:
+                assert len(set(s.tolist())) == m                # replace=False when there are enough candidates
+    again = D.build_ripple_sets_device((indptr, nbr, rel), history, n_user, p_hop, m, "cuda").cpu().numpy()
+    assert np.array_equal(again, uts)
+    # the packed result drives the device-resident feed path as is
+    assert uts.dtype == np.int32
