@@ -12,6 +12,8 @@ batch of B user-item pairs of the workload.  Prints ONE JSON line (rank 0).
                ranks).  L2 is flushed (256 MiB write) between timed steps, outside the event pairs.
   e2e          same metric through the C-ABI host entry point mvin_train_step_host: the feed is copied H2D from pinned
                host memory and the loss scalars are read back D2H inside the timed region of every step.
+  e2e_device_feed  same, through mvin_train_step_users_host: the ripple sets are bound on the device once and only
+               user / item / label ids cross the bus per step.
   roofline     dominant kernel (by device time, measured live with CUDA events recorded by the library on its launch
                stream in a third pass over the same steps): algorithmic bytes per launch / mean launch duration vs the
                measured HBM copy peak (MEASURED_PEAKS.json).

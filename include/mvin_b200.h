@@ -34,7 +34,7 @@ extern "C" {
 #define MVIN_ERR_CUDA -3
 #define MVIN_ERR_STATE -4
 
-#define MVIN_ABI_VERSION 2
+#define MVIN_ABI_VERSION 3
 
 typedef struct mvin_handle_s* mvin_handle_t;
 

@@ -9,7 +9,7 @@ from . import build as _build
 
 MVIN_OK = 0
 FLAGS_ALL = 0x1F
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EXPORTS = ["mvin_abi_version", "mvin_last_error", "mvin_create", "mvin_destroy", "mvin_bind_params",
            "mvin_bind_grads", "mvin_bind_adjacency", "mvin_bind_entity_shards", "mvin_set_batch_scale", "mvin_ipc_export", "mvin_ipc_open", "mvin_pack_adjacency", "mvin_workspace_bytes",

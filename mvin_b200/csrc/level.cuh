@@ -405,7 +405,6 @@ struct TransformArgs {
   const float* u;       // [B, D]  user_o
   GTab dE;              // bwd: entity-table gradient (scatter-add)
   float* du;            // bwd: [B, D] (accumulated)
-  int dbg;              // experiments only (env MVIN_B200_DBG): skip phases of the tcgen05 kernels
 };
 
 template <int D>
@@ -725,7 +724,7 @@ struct AggBwdArgs {
 };
 
 template <int D, bool HAS_LEAF>
-__global__ void __launch_bounds__(TC<D>::NT) agg_bwd_kernel(AggBwdArgs a) {
+__global__ void __launch_bounds__(TC<D>::NT, (D <= 64 ? 3 : 1)) agg_bwd_kernel(AggBwdArgs a) {
   using C = TC<D>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int K = a.K, KP = padded_k(K);

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(TT<D>::NT) transform_fwd_tc_kernel(TransformAr
 #pragma unroll
     for (int ps = 0; ps < T::NP; ++ps) {
       const long row = tile * T::R + ps * T::RP + ty;
-      e[ps] = (tile < ntiles && row < L.rows && !(a.dbg & 4)) ? (long)__ldg(L.ent + row) : -1;
+      e[ps] = (tile < ntiles && row < L.rows) ? (long)__ldg(L.ent + row) : -1;
     }
 #pragma unroll
     for (int ps = 0; ps < T::NP; ++ps) {
@@ -153,17 +153,15 @@ __global__ void __launch_bounds__(TT<D>::NT) transform_fwd_tc_kernel(TransformAr
     for (int ps = 0; ps < T::NP; ++ps) umma::store_split<D>(a_hi, a_lo, ps * T::RP + ty, tx, x[ps]);
     umma::fence_async_smem();
     __syncthreads();
-    if (tid == 0 && !(a.dbg & 1)) {
+    if (tid == 0) {
       umma::fence_after_sync();
       umma::issue_3xtf32<D>(tmem, umma::smem_u32(a_hi), umma::smem_u32(a_lo), umma::smem_u32(w_hi), umma::smem_u32(w_lo), D,
                             true);
       umma::commit(bar);
     }
     gather(t + cs.count);
-    if (!(a.dbg & 1)) {
-      umma::mbar_wait(bar, phase);
-      phase ^= 1;
-    }
+    umma::mbar_wait(bar, phase);
+    phase ^= 1;
     umma::fence_after_sync();
     // epilogue: accumulator rows (thread = row) -> row-major staging tile in the A_hi buffer (free once the MMAs have
     // completed) -> coalesced 16-byte stores, LPR lanes per row
@@ -182,7 +180,7 @@ __global__ void __launch_bounds__(TT<D>::NT) transform_fwd_tc_kernel(TransformAr
     for (int ps = 0; ps < T::NP; ++ps) {
       const int r = ps * T::RP + ty;
       const long row = row0 + r;
-      if (row < L.rows && !(a.dbg & 2)) st4a(L.T + row * D + tx * 4, f4add(ld4(&stg[r * T::SLD + tx * 4]), b), L.stream);
+      if (row < L.rows) st4a(L.T + row * D + tx * 4, f4add(ld4(&stg[r * T::SLD + tx * 4]), b), L.stream);
     }
     __syncthreads();                                      // staging tile is the next A operand
   }

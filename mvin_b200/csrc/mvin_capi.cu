@@ -471,7 +471,6 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
         t.stream = stream_level(h, L.rows[lv], D);
     }
     a.nlev = H; a.E = h->etab; a.u = at<float>(ws, L.u);
-    if (const char* ev = getenv("MVIN_B200_DBG")) a.dbg = atoi(ev);
     bool done = false;
     if constexpr (D == 32 || D == 64) {
       if (use_tc_path(h, L.rows[H - 1])) {
