@@ -399,8 +399,13 @@ def run_ours(a, w, wl_key):
                     "share_of_step": prof[top]["ms_per_step"] / max(1e-9, sum(v["ms_per_step"] for v in prof.values())),
                     "step_logical_gbs": (fwd_b + bwd_b) * pairs_per_s / world / 1e9,
                     "step_frac": (fwd_b + bwd_b) * pairs_per_s / world / 1e9 / peak,
+                    "achieved_dram": (traffic / (per_launch_ms * 1e-3) / 1e9 if traffic else None),
                     "note": ("entity table >> L2: gathers are served by HBM / NVLink peers" if sharded else
-                             "tables (<=30 MB) are L2-resident at this workload: logical gather bytes, not DRAM traffic")}
+                             "tables (<=30 MB) are L2-resident at this workload: `achieved` counts the logical (per-pair) "
+                             "gather bytes of SURVEY.md 8(d), `traffic` / `achieved_dram` the DRAM bytes ncu measured; "
+                             "where the per-entity leaf mode is active the K-row leaf gathers run once per distinct "
+                             "entity (leaf_entity kernels), so executed bytes are below the logical ones and frac can "
+                             "exceed 1")}
     cpu = None
     if world == 1 and not a.no_cpu_baseline and not sharded:
         n_pairs = a.cpu_sample_pairs

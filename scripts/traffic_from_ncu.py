@@ -2,7 +2,7 @@
 """profiles/traffic.json[workload][kernel family] = dram__bytes_read.sum + dram__bytes_write.sum per launch, from an
 ncu --set full capture of one step (scripts/gpu_capture.sh).  bench.py reports it as roofline.traffic.
 
-    python scripts/traffic_from_ncu.py gpurun_out/r01v8_full_C2.ncu-rep C2 2
+    python scripts/traffic_from_ncu.py gpurun_out/r01v8_full_C2.ncu-rep C2 2 [out.json]
 """
 import csv
 import io
@@ -30,6 +30,7 @@ def main():
         m = re.match(r"(?:void )?(\w+)<([^>]*)>", name)
         base, targs = (m.group(1), [t.strip() for t in m.group(2).split(",")]) if m else (name, [])
         flag = targs[1] if len(targs) > 1 else ""
+        base = base.replace("_tc_kernel", "_kernel")          # tcgen05 versions share the family of the mma.sync ones
         if base == "agg_fwd_kernel":
             key = "agg_fwd_0" if flag in ("1", "true") else f"agg_fwd_{(n_fwd_in := n_fwd_in + 1)}"
         elif base == "agg_bwd_kernel":
@@ -46,7 +47,7 @@ def main():
             continue                      # first launch of each family (one step)
         byts = float(r[ri]) * UNIT[units[ri]] + float(r[wi]) * UNIT[units[wi]]
         fam[key] = {"dram_bytes": byts, "ncu_us": float(r[ti])}
-    path = os.path.join(ROOT, "profiles", "traffic.json")
+    path = sys.argv[4] if len(sys.argv) > 4 else os.path.join(ROOT, "profiles", "traffic.json")
     data = json.load(open(path)) if os.path.exists(path) else {}
     data[wl] = {k: v["dram_bytes"] for k, v in fam.items()}
     data.setdefault("_ncu_us", {})[wl] = {k: v["ncu_us"] for k, v in fam.items()}
