@@ -12,6 +12,7 @@ batch of B user-item pairs of the workload.  Prints ONE JSON line (rank 0).
                ranks).  L2 is flushed (256 MiB write) between timed steps, outside the event pairs.
   e2e          same metric through the C-ABI host entry point mvin_train_step_host: the feed is copied H2D from pinned
                host memory and the loss scalars are read back D2H inside the timed region of every step.
+  e2e_prefetch same host feed, copied one step ahead (mvin_feed_prefetch + mvin_train_step_prefetched).
   e2e_device_feed  same, through mvin_train_step_users_host: the ripple sets are bound on the device once and only
                user / item / label ids cross the bus per step.
   roofline     dominant kernel (by device time, measured live with CUDA events recorded by the library on its launch
@@ -336,6 +337,19 @@ def run_ours(a, w, wl_key):
     clocks = sampler.stop()
     launches = model.launch_count() - launches0
     ms_e2e = timed(step_host, a.steps)
+    ms_e2e_pre = None
+    if not sharded:
+        # double-buffered input pipeline: the feed of step i + 1 is copied while step i computes (every copy is inside
+        # the timed region: K prefetches and K steps per K timed steps)
+        model.prefetch_feed(*host[0])
+
+        def step_prefetched(i):
+            model.prefetch_feed(*host[(i + 1) % NB])
+            return model.train_step_prefetched(apply_adam=False)
+
+        step_prefetched(0)
+        ms_e2e_pre = timed(step_prefetched, a.steps)
+        model.train_step_prefetched(apply_adam=False)      # drain the last pending batch
     ms_e2e_dev = None
     if not sharded:
         # device-resident feed: ripple sets uploaded once, only user / item / label per step
@@ -426,6 +440,11 @@ def run_ours(a, w, wl_key):
                        "init": "reference Xavier init, seed 1"},
             "e2e": {"value": e2e_pairs_per_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / a.steps},
+            "e2e_prefetch": (None if ms_e2e_pre is None else
+                             {"value": world * B * a.steps / (ms_e2e_pre * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                              "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e_pre / a.steps,
+                              "note": "same host feed as e2e, copied one step ahead on a copy stream "
+                                      "(mvin_feed_prefetch / mvin_train_step_prefetched)"}),
             "e2e_device_feed": (None if ms_e2e_dev is None else
                                 {"value": world * B * a.steps / (ms_e2e_dev * 1e-3), "unit": UNIT,
                                  "h2d_bytes_per_step": B * 20, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e_dev / a.steps,

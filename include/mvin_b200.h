@@ -211,6 +211,19 @@ int mvin_build_ripple_sets(const int64_t* indptr, const int32_t* nbr, const int3
 int mvin_ctr_metrics(mvin_handle_t h, const float* scores_normalized, const float* labels, int32_t B, float* out3,
                      void* scratch40, void* stream);
 
+/* Double-buffered input pipeline for a training loop that knows its next batch (train.py:58-64 iterates a shuffled
+ * array): mvin_feed_prefetch copies the NEXT batch's feed (same arguments as mvin_train_step_host, host buffers,
+ * pinned for a truly asynchronous copy) into `staging` on an internal copy stream, beside whatever runs on `stream`;
+ * mvin_train_step_prefetched then runs forward + backward (+ Adam) from that staging buffer and blocks like
+ * mvin_train_step_host.  Two slots (0 / 1), each with its own staging buffer of mvin_feed_bytes(), are used alternately:
+ * prefetch(batch i+1 -> slot (i+1)%2) is called before step(batch i from slot i%2). */
+int mvin_feed_prefetch(mvin_handle_t h, const int64_t* user_indices, const int64_t* item_indices, const float* labels,
+                       const int32_t* mem_h, const int32_t* mem_r, const int32_t* mem_t, int32_t B, void* staging,
+                       int32_t slot, void* stream);
+int mvin_train_step_prefetched(mvin_handle_t h, int32_t B, void* staging, int32_t slot, void* workspace,
+                               const mvin_params_t* adam_m, const mvin_params_t* adam_v, float lr, int32_t step,
+                               float* losses_host, void* stream);
+
 /* Number of kernels the library has launched on behalf of this handle since creation (bench evidence). */
 int64_t mvin_launch_count(mvin_handle_t h);
 

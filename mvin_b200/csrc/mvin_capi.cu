@@ -113,6 +113,10 @@ struct mvin_handle_s {
   bool use_streams = true;
   bool early_init = false;         // backward part 0 of this step was already enqueued (host-step entry points)
   cudaEvent_t ev_early = nullptr, ev_item = nullptr;   // its completion; 'item ids are on the device'
+  cudaStream_t copy_stream = nullptr;   // mvin_feed_prefetch: H2D copies of the NEXT batch while this one computes
+  cudaEvent_t ev_feed[2] = {nullptr, nullptr}, ev_free = nullptr;   // one 'feed landed' event per staging slot
+  const void* prefetched_staging[2] = {nullptr, nullptr};
+  int prefetched_B[2] = {0, 0};
   bool pre_fork = false;           // forward: the side stream starts from ev_item instead of the launch stream's tail
   int entity_leaf_mode = -1;       // -1 auto, 0 off, 1 on (env MVIN_B200_ENTITY_LEAF, read in mvin_create)
   int user_pb_fwd = 4;             // max pairs per CTA of the user-side forward kernel (env MVIN_B200_USER_PB_FWD)
@@ -1003,6 +1007,9 @@ int mvin_create(const mvin_config_t* cfg, mvin_handle_t* out) {
 int mvin_destroy(mvin_handle_t h) {
   if (h && h->d_shard_tab) cudaFree(h->d_shard_tab);
   if (h && h->d_sched) cudaFree(h->d_sched);
+  if (h && h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (int i = 0; h && i < 2; ++i) if (h->ev_feed[i]) cudaEventDestroy(h->ev_feed[i]);
+  if (h && h->ev_free) cudaEventDestroy(h->ev_free);
   for (int i = 0; h && i < 2; ++i) {
     if (h->side[i]) cudaStreamDestroy(h->side[i]);
     if (h->ev_fork[i]) cudaEventDestroy(h->ev_fork[i]);
@@ -1256,6 +1263,77 @@ int mvin_train_step_host(mvin_handle_t h, const int64_t* user_indices, const int
   const int32_t* d_mt = (const int32_t*)stage(mem_t, sizeof(int32_t) * pm);
   float* d_loss = (float*)(base + off);
   CUDA_TRY(cudaGetLastError());
+  rc = mvin_forward(h, d_user, d_item, d_mh, d_mr, d_mt, B, nullptr, nullptr, workspace, stream);
+  if (rc) return rc;
+  rc = mvin_backward(h, d_lab, B, d_loss, workspace, stream);
+  if (rc) return rc;
+  if (adam_m && adam_v) {
+    rc = mvin_adam_step(h, adam_m, adam_v, lr, 0.9f, 0.999f, 1e-8f, step, stream);
+    if (rc) return rc;
+  }
+  CUDA_TRY(cudaMemcpyAsync(losses_host, d_loss, sizeof(float) * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return MVIN_OK;
+}
+
+int mvin_feed_prefetch(mvin_handle_t h, const int64_t* user_indices, const int64_t* item_indices, const float* labels,
+                       const int32_t* mem_h, const int32_t* mem_r, const int32_t* mem_t, int32_t B, void* staging,
+                       int32_t slot, void* stream) {
+  if (!h || !user_indices || !item_indices || !labels || !mem_h || !mem_r || !mem_t || !staging || slot < 0 || slot > 1)
+    return fail(MVIN_ERR_INVALID, "null argument / slot must be 0 or 1");
+  if (B < 1 || B > h->cfg.max_batch) return fail(MVIN_ERR_INVALID, "B = %d outside 1..max_batch (%d)", B, h->cfg.max_batch);
+  if (!h->copy_stream) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_feed[0], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_feed[1], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_free, cudaEventDisableTiming));
+  }
+  // the copy may start once everything enqueued so far on the caller's stream -- in particular the last step that read
+  // this staging buffer -- has finished; it then runs beside whatever the caller enqueues next
+  CUDA_TRY(cudaEventRecord(h->ev_free, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_free, 0));
+  const size_t pm = (size_t)(h->cfg.p_hop > 0 ? h->cfg.p_hop : 1) * B * h->cfg.n_memory;
+  char* base = static_cast<char*>(staging);
+  size_t off = 0;
+  auto stage = [&](const void* src, size_t bytes) {
+    cudaMemcpyAsync(base + off, src, bytes, cudaMemcpyHostToDevice, h->copy_stream);
+    off += align_up(bytes);
+  };
+  stage(user_indices, sizeof(int64_t) * B);
+  stage(item_indices, sizeof(int64_t) * B);
+  stage(labels, sizeof(float) * B);
+  stage(mem_h, sizeof(int32_t) * pm);
+  stage(mem_r, sizeof(int32_t) * pm);
+  stage(mem_t, sizeof(int32_t) * pm);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(h->ev_feed[slot], h->copy_stream));
+  h->prefetched_staging[slot] = staging;
+  h->prefetched_B[slot] = B;
+  return MVIN_OK;
+}
+
+int mvin_train_step_prefetched(mvin_handle_t h, int32_t B, void* staging, int32_t slot, void* workspace,
+                               const mvin_params_t* adam_m, const mvin_params_t* adam_v, float lr, int32_t step,
+                               float* losses_host, void* stream) {
+  if (!h || !staging || !workspace || !losses_host || slot < 0 || slot > 1) return fail(MVIN_ERR_INVALID, "bad argument");
+  if (h->prefetched_staging[slot] != staging || h->prefetched_B[slot] != B)
+    return fail(MVIN_ERR_STATE, "mvin_train_step_prefetched must follow mvin_feed_prefetch on the same slot, staging buffer and B");
+  h->prefetched_staging[slot] = nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaStreamWaitEvent(st, h->ev_feed[slot], 0));
+  const size_t pm = (size_t)(h->cfg.p_hop > 0 ? h->cfg.p_hop : 1) * B * h->cfg.n_memory;
+  char* base = static_cast<char*>(staging);
+  size_t off = 0;
+  auto carve = [&](size_t bytes) -> void* { void* p = base + off; off += align_up(bytes); return p; };
+  const int64_t* d_user = (const int64_t*)carve(sizeof(int64_t) * B);
+  const int64_t* d_item = (const int64_t*)carve(sizeof(int64_t) * B);
+  const float* d_lab = (const float*)carve(sizeof(float) * B);
+  const int32_t* d_mh = (const int32_t*)carve(sizeof(int32_t) * pm);
+  const int32_t* d_mr = (const int32_t*)carve(sizeof(int32_t) * pm);
+  const int32_t* d_mt = (const int32_t*)carve(sizeof(int32_t) * pm);
+  float* d_loss = (float*)(base + off);
+  int rc = host_step_overlap(h, B, workspace, st);
+  if (rc) return rc;
   rc = mvin_forward(h, d_user, d_item, d_mh, d_mr, d_mt, B, nullptr, nullptr, workspace, stream);
   if (rc) return rc;
   rc = mvin_backward(h, d_lab, B, d_loss, workspace, stream);

@@ -390,6 +390,39 @@ class MVIN(object):
                 self.adam_step_device()
         return losses
 
+    # ------------------------------------------------------------------ double-buffered input pipeline
+    def prefetch_feed(self, users, items, labels, mem_h, mem_r, mem_t):
+        """Start the H2D copy of a coming batch (host numpy / pinned torch buffers, shapes of train_step_host) on the
+        library's copy stream; it overlaps the step that is running.  At most two batches may be pending; each
+        train_step_prefetched() consumes the oldest.  Loop shape: prefetch(0); for i: prefetch(i + 1); step()."""
+        if self.n_shards > 1:
+            raise NotImplementedError("prefetch pipeline: single-table configurations only")
+        B = items.shape[0]
+        self._ensure_workspace(B)
+        if getattr(self, "_staging2", None) is None or self._staging2[0].numel() != self._staging.numel():
+            self._staging2 = [self._staging, torch.empty_like(self._staging)]
+            self._stage_next, self._pending = 0, []
+        if len(self._pending) >= 2:
+            raise RuntimeError("two batches are already pending: call train_step_prefetched() first")
+        ptr = lambda a: a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr()
+        slot = self._stage_next
+        self._stage_next ^= 1
+        buf = self._staging2[slot]
+        self._pending.append((slot, B, (users, items, labels, mem_h, mem_r, mem_t)))   # keeps the host buffers alive
+        check(self.lib.mvin_feed_prefetch(self._handle, ptr(users), ptr(items), ptr(labels), ptr(mem_h), ptr(mem_r),
+                                          ptr(mem_t), B, buf.data_ptr(), slot, self._stream()), "mvin_feed_prefetch")
+
+    def train_step_prefetched(self, apply_adam=True):
+        """forward + backward (+ Adam) on the oldest pending batch of prefetch_feed(); returns the 4 losses."""
+        slot, B, _ = self._pending.pop(0)
+        if apply_adam:
+            self.step += 1
+        check(self.lib.mvin_train_step_prefetched(
+            self._handle, B, self._staging2[slot].data_ptr(), slot, self._workspace.data_ptr(),
+            C.byref(self._m_struct) if apply_adam else None, C.byref(self._v_struct) if apply_adam else None, self.lr,
+            max(self.step, 1), self._losses_host.data_ptr(), self._stream()), "mvin_train_step_prefetched")
+        return self._losses_host.numpy().copy()
+
     # ------------------------------------------------------------------ device-resident feed (SURVEY.md 8(f) rank 2)
     def bind_user_triplet_set(self, user_triplet_set):
         """Upload the packed ripple sets once: int32 [n_user, max(1,p), 3, n_memory] (data_loader_user_set.py:402 stacks

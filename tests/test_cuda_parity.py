@@ -364,3 +364,34 @@ def test_ctr_metrics_match_sklearn(B, ties):
     assert abs(auc - roc_auc_score(labels, scores)) < 2e-6
     assert abs(acc - float(np.mean(pred == labels))) < 1e-6
     assert abs(f1 - f1_score(labels, pred)) < 1e-6
+
+
+def test_prefetch_pipeline_matches_plain_steps():
+    """mvin_feed_prefetch / mvin_train_step_prefetched (next batch copied while the current one computes) against
+    plain train_step_host calls on the same sequence of batches."""
+    from mvin_b200 import MVIN
+    args = make_args(dim=32, neighbor_sample_size=8, h_hop=2, p_hop=2, n_memory=16, batch_size=40)
+    probs = [make_problem(args, seed=s) for s in (1, 2, 3)]
+
+    def fresh():
+        m = MVIN(args, probs[0]["n_user"], probs[0]["n_entity"], probs[0]["n_relation"], probs[0]["adj_entity"],
+                 probs[0]["adj_relation"])
+        m.load_named_parameters({k: v.numpy() for k, v in probs[0]["P"].items()})
+        return m
+
+    def batch(pr):
+        st = lambda xs: np.ascontiguousarray(np.stack(xs))
+        return (pr["users"], pr["items"], pr["labels"], st(pr["mem_h"]), st(pr["mem_r"]), st(pr["mem_t"]))
+
+    a, b = fresh(), fresh()
+    plain = [a.train_step_host(*batch(pr), apply_adam=False) for pr in probs]
+    piped = []
+    b.prefetch_feed(*batch(probs[0]))
+    for i in range(len(probs)):
+        if i + 1 < len(probs):
+            b.prefetch_feed(*batch(probs[i + 1]))          # copy of batch i + 1 runs beside step i
+        piped.append(b.train_step_prefetched(apply_adam=False))
+    for x, y in zip(plain, piped):
+        assert np.allclose(x, y, rtol=1e-5, atol=1e-7), (x, y)
+    with pytest.raises(IndexError):
+        b.train_step_prefetched()                          # nothing pending
