@@ -111,6 +111,7 @@ struct mvin_handle_s {
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr}, ev_mid = nullptr;
   bool use_streams = true;
+  bool in_host_step = false;       // set for the duration of a host-step entry point (guards the two flags below)
   bool early_init = false;         // backward part 0 of this step was already enqueued (host-step entry points)
   cudaEvent_t ev_early = nullptr, ev_item = nullptr;   // its completion; 'item ids are on the device'
   cudaStream_t copy_stream = nullptr;   // mvin_feed_prefetch: H2D copies of the NEXT batch while this one computes
@@ -373,7 +374,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
   // per-entity leaf aggregate are independent of the user side that runs on the launch stream meanwhile
   const Par par{h, st, h->use_streams && !h->prof_on};
   int32_t* stamp = L.entity_leaf ? at<int32_t>(ws, L.stamp) : nullptr;
-  if (par.on && h->pre_fork) {
+  if (par.on && h->pre_fork && h->in_host_step) {
     CUDA_TRY(cudaStreamWaitEvent(h->side[0], h->ev_item, 0));   // only the item ids are needed on this branch
     h->pre_fork = false;
   } else {
@@ -664,7 +665,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
 
   // part 0 (parameters only) on side stream 0 -- unless a host-step entry point already ran it during the feed copy
   const Par par{h, st, h->use_streams && !h->prof_on};
-  if (h->early_init) {
+  if (h->early_init && h->in_host_step) {
     CUDA_TRY(cudaStreamWaitEvent(st, h->ev_early, 0));
     h->early_init = false;
     par.fork(0);
@@ -930,6 +931,12 @@ int dispatch_forward(mvin_handle_t h, const int64_t* item, const int32_t* mh, co
                      int B, float* scores, float* sn, void* ws, cudaStream_t st) {
   DISPATCH_D(h->cfg.dim, (forward_impl<DD>(h, item, mh, mr, mt, B, scores, sn, ws, st)));
 }
+struct HostStepGuard {
+  mvin_handle_t h;
+  explicit HostStepGuard(mvin_handle_t hh) : h(hh) { h->in_host_step = true; h->early_init = false; h->pre_fork = false; }
+  ~HostStepGuard() { h->in_host_step = false; h->early_init = false; h->pre_fork = false; }
+};
+
 int dispatch_backward_init(mvin_handle_t h, int B, void* ws, cudaStream_t st) {
   DISPATCH_D(h->cfg.dim, (backward_init<DD>(h, B, ws, st, nullptr, true)));
 }
@@ -1243,6 +1250,7 @@ int mvin_train_step_host(mvin_handle_t h, const int64_t* user_indices, const int
       !losses_host)
     return fail(MVIN_ERR_INVALID, "null argument");
   if (B < 1 || B > h->cfg.max_batch) return fail(MVIN_ERR_INVALID, "B = %d outside 1..max_batch (%d)", B, h->cfg.max_batch);
+  HostStepGuard guard(h);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t pm = (size_t)(h->cfg.p_hop > 0 ? h->cfg.p_hop : 1) * B * h->cfg.n_memory;
   char* base = static_cast<char*>(staging);
@@ -1319,6 +1327,7 @@ int mvin_train_step_prefetched(mvin_handle_t h, int32_t B, void* staging, int32_
   if (h->prefetched_staging[slot] != staging || h->prefetched_B[slot] != B)
     return fail(MVIN_ERR_STATE, "mvin_train_step_prefetched must follow mvin_feed_prefetch on the same slot, staging buffer and B");
   h->prefetched_staging[slot] = nullptr;
+  HostStepGuard guard(h);
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_TRY(cudaStreamWaitEvent(st, h->ev_feed[slot], 0));
   const size_t pm = (size_t)(h->cfg.p_hop > 0 ? h->cfg.p_hop : 1) * B * h->cfg.n_memory;
@@ -1410,6 +1419,7 @@ int mvin_train_step_users_host(mvin_handle_t h, const int64_t* user_indices, con
     return fail(MVIN_ERR_INVALID, "null argument");
   if (B < 1 || B > h->cfg.max_batch) return fail(MVIN_ERR_INVALID, "B = %d outside 1..max_batch (%d)", B, h->cfg.max_batch);
   if (!h->uts) return fail(MVIN_ERR_STATE, "user triplet sets not bound (mvin_bind_user_triplets)");
+  HostStepGuard guard(h);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t pm = (size_t)(h->cfg.p_hop > 0 ? h->cfg.p_hop : 1) * B * h->cfg.n_memory;
   char* base = static_cast<char*>(staging);
