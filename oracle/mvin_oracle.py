@@ -26,6 +26,10 @@ reference's OWN ``model.py`` / ``aggregators.py`` executed in this container und
 (``tests/golden/tf1_shim.py``; generator ``tests/golden/make_golden.py``; fixtures ``tests/golden/*.npz``),
 so every wiring convention (concat orders, reshapes, which tensors feed which op, the L2 bookkeeping quirks)
 is checked against reference code, while op numerics (matmul/softmax/...) follow the TF documentation.
+The only numerical output of the real TensorFlow model that ships with the reference -- the attention weights of 18
+trained models in ``case_st/amazon-book_20core/*.log`` -- is a second pin (``tests/golden/case_study_att.npz``,
+``tests/test_case_study_logs.py``): ``sum_aggregator_urh`` reproduces them to print precision.  What remains
+unpinned against a TF binary: the ripple side, the dense maps, the loss and Adam ("parity unpinned" for those).
 """
 from __future__ import annotations
 
