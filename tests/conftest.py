@@ -16,7 +16,8 @@ def pytest_configure(config):
 
 def golden_cases():
     # model goldens of make_golden.py; case_study_att.npz (make_case_study_fixture.py) has its own test
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("case_study"))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR)
+                  if f.endswith(".npz") and not f.startswith(("case_study", "loader_")))
 
 
 @pytest.fixture(scope="session")

@@ -111,3 +111,19 @@ def test_ripple_sets_device_properties(p_hop, m):
     assert np.array_equal(again, uts)
     # the packed result drives the device-resident feed path as is
     assert uts.dtype == np.int32
+
+
+def test_device_samplers_obey_the_reference_rules():
+    """The checker of tests/test_data_host.py (validated there on the reference's own draw) applied to the CUDA kernels
+    on the same small KG."""
+    from mvin_b200 import data as D
+    from tests.test_data_host import check_adjacency, check_ripple_sets, load, neighbour_sets
+    z = load()
+    nbrs = neighbour_sets(z)
+    n_entity = int(z["n_entity"])
+    _, adj_e, adj_r, (indptr, nbr, rel, _) = D.sample_adjacency_device(z["kg_np"], n_entity, 8, "cuda", seed=11,
+                                                                       want_edges=True)
+    check_adjacency(adj_e.cpu().numpy(), adj_r.cpu().numpy(), nbrs, 8)
+    hist = {u: z["hist_items"][z["hist_ptr"][u]:z["hist_ptr"][u + 1]] for u in range(30)}
+    uts = D.build_ripple_sets_device((indptr, nbr, rel), hist, 30, 2, 16, "cuda", seed=11).cpu().numpy()
+    check_ripple_sets(uts, [hist[u] for u in range(30)], nbrs, 16)
