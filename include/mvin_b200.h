@@ -224,6 +224,16 @@ int mvin_train_step_prefetched(mvin_handle_t h, int32_t B, void* staging, int32_
                                const mvin_params_t* adam_m, const mvin_params_t* adam_v, float lr, int32_t step,
                                float* losses_host, void* stream);
 
+/* Top-K evaluation metrics on the device -- replaces the per-user Python sort and metric calls of topk_eval
+ * (util.py:183-197; metrics.py:3-31, 34-37, 97-100).  Per user u: scores[u, :n_cand[u]] of its candidate items in
+ * candidate order (get_scores output, util.py:159-181), relevant[u, i] = candidate i is in ref_user[user],
+ * n_answers[u] = len(ref_user[user]); k_list ascending, nk <= 8.  Outputs [n_users, nk]: precision@k, recall@k and
+ * ndcg@k exactly as the reference computes them (stable descending sort; the hit list of ndcg is built over the top
+ * k_list[-1] items).  All pointers device; the caller averages over users (util.py:199-201). */
+int mvin_topk_metrics(const float* scores, const uint8_t* relevant, const int32_t* n_cand, const int32_t* n_answers,
+                      int32_t n_users, int32_t max_cand, const int32_t* k_list, int32_t nk, float* precision, float* recall,
+                      float* ndcg, void* stream);
+
 /* Number of kernels the library has launched on behalf of this handle since creation (bench evidence). */
 int64_t mvin_launch_count(mvin_handle_t h);
 

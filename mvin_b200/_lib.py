@@ -17,7 +17,7 @@ EXPORTS = ["mvin_abi_version", "mvin_last_error", "mvin_create", "mvin_destroy",
            "mvin_feed_bytes", "mvin_train_step_host", "mvin_launch_count", "mvin_profile_enable",
            "mvin_profile_read", "mvin_test_umma_gemm", "mvin_test_umma_dw", "mvin_bind_user_triplets", "mvin_gather_feed",
            "mvin_train_step_users_host", "mvin_ctr_metrics", "mvin_sample_adjacency", "mvin_build_ripple_sets", "mvin_feed_prefetch",
-           "mvin_train_step_prefetched"]
+           "mvin_train_step_prefetched", "mvin_topk_metrics"]
 
 
 class Config(C.Structure):
@@ -89,6 +89,7 @@ def load():
     lib.mvin_feed_prefetch.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, vp]
     lib.mvin_train_step_prefetched.argtypes = [vp, i32, vp, i32, vp, C.POINTER(Params), C.POINTER(Params), C.c_float, i32,
                                                vp, vp]
+    lib.mvin_topk_metrics.argtypes = [vp, vp, vp, vp, i32, i32, vp, i32, vp, vp, vp, vp]
     lib.mvin_launch_count.argtypes = [vp]
     lib.mvin_launch_count.restype = C.c_int64
     lib.mvin_profile_enable.argtypes = [vp, i32]

@@ -565,6 +565,63 @@ __global__ void ctr_finalize_kernel(const unsigned long long* __restrict__ acc64
   out[2] = (2 * tp + fp + fn) > 0 ? (float)(2 * tp / (2 * tp + fp + fn)) : 0.f;
 }
 
+// ---- top-K metrics on the device (util.py:137-205 + metrics.py:3-31,34-37,97-100) -----------------------------------
+// One CTA per user.  Candidates are ranked by score, descending, ties in candidate order (Python's stable sorted() over
+// the insertion-ordered item_score_map, util.py:183-184); rank by counting.  Per k of k_list:
+//   precision@k = |top-k & answers| / k,  recall@k = |top-k & answers| / n_answers,
+//   ndcg@k = dcg(r_hit[:k]) / dcg(sorted(r_hit, reverse)[:k])  with r_hit = the hit flags of the top k_list[-1] items
+//   (the reference builds r_hit once with the loop variable k left over from the precision loop, util.py:190-197) and
+//   dcg(r) = sum_i r_i / log2(i + 2)  (metrics.py:15, method 1).
+constexpr int TOPK_MAX_K = 8, TOPK_MAX_RANK = 1024;
+struct TopkArgs {
+  const float* scores;        // [n_users, max_cand]
+  const unsigned char* rel;   // [n_users, max_cand]  candidate is one of the user's held-out items
+  const int32_t* n_cand;      // [n_users]
+  const int32_t* n_answers;   // [n_users]  len(ref_user[user])
+  int max_cand, nk;
+  int k_list[TOPK_MAX_K];
+  float* precision;           // [n_users, nk]
+  float* recall;
+  float* ndcg;
+};
+__global__ void __launch_bounds__(256) topk_metrics_kernel(TopkArgs a) {
+  extern __shared__ float sc[];                          // [max_cand] scores, then hit flags by rank
+  unsigned char* hit = reinterpret_cast<unsigned char*>(sc + a.max_cand);   // [k_last]
+  __shared__ int cnt[TOPK_MAX_K];
+  const int u = blockIdx.x, n = a.n_cand[u], k_last = a.k_list[a.nk - 1];
+  const float* s = a.scores + (long)u * a.max_cand;
+  const unsigned char* rl = a.rel + (long)u * a.max_cand;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sc[i] = s[i];
+  for (int i = threadIdx.x; i < k_last; i += blockDim.x) hit[i] = 0;
+  if (threadIdx.x < TOPK_MAX_K) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    if (!rl[i]) continue;                                // only hits matter
+    const float si = sc[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += (sc[j] > si) || (sc[j] == si && j < i);
+    for (int q = 0; q < a.nk; ++q)
+      if (rank < a.k_list[q]) atomicAdd(&cnt[q], 1);
+    if (rank < k_last) hit[rank] = 1;
+  }
+  __syncthreads();
+  if (threadIdx.x < a.nk) {
+    const int q = threadIdx.x, k = a.k_list[q];
+    a.precision[(long)u * a.nk + q] = (float)cnt[q] / (float)k;
+    a.recall[(long)u * a.nk + q] = a.n_answers[u] > 0 ? (float)cnt[q] / (float)a.n_answers[u] : 0.f;
+    const int len = n < k_last ? n : k_last;             // r_hit has one entry per ranked item, at most k_last
+    int total_hits = 0;
+    for (int i = 0; i < len; ++i) total_hits += hit[i];
+    double dcg = 0.0, ideal = 0.0;
+    for (int i = 0; i < len && i < k; ++i) {
+      const double disc = 1.0 / log2((double)i + 2.0);
+      if (hit[i]) dcg += disc;
+      if (i < total_hits) ideal += disc;
+    }
+    a.ndcg[(long)u * a.nk + q] = ideal > 0.0 ? (float)(dcg / ideal) : 0.f;
+  }
+}
+
 // ---- Adam, TF1 semantics (model.py:414): dense over every segment ---------------------------------------
 struct AdamSegments {
   float* param[MAX_SEG];

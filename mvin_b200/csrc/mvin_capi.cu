@@ -1479,6 +1479,31 @@ int mvin_build_ripple_sets(const int64_t* indptr, const int32_t* nbr, const int3
   return MVIN_OK;
 }
 
+int mvin_topk_metrics(const float* scores, const uint8_t* relevant, const int32_t* n_cand, const int32_t* n_answers,
+                      int32_t n_users, int32_t max_cand, const int32_t* k_list, int32_t nk, float* precision, float* recall,
+                      float* ndcg, void* stream) {
+  if (!scores || !relevant || !n_cand || !n_answers || !k_list || !precision || !recall || !ndcg || n_users < 1)
+    return fail(MVIN_ERR_INVALID, "null / bad argument");
+  if (nk < 1 || nk > TOPK_MAX_K || max_cand < 1) return fail(MVIN_ERR_INVALID, "nk must be in 1..%d", TOPK_MAX_K);
+  TopkArgs a;
+  memset(&a, 0, sizeof(a));
+  a.scores = scores; a.rel = relevant; a.n_cand = n_cand; a.n_answers = n_answers; a.max_cand = max_cand; a.nk = nk;
+  for (int i = 0; i < nk; ++i) {
+    if (k_list[i] < 1 || k_list[i] > TOPK_MAX_RANK || (i && k_list[i] < k_list[i - 1]))
+      return fail(MVIN_ERR_INVALID, "k_list must be ascending with entries in 1..%d", TOPK_MAX_RANK);
+    a.k_list[i] = k_list[i];
+  }
+  a.precision = precision; a.recall = recall; a.ndcg = ndcg;
+  const size_t sm = sizeof(float) * max_cand + (size_t)k_list[nk - 1] + 16;
+  if (sm > 200 * 1024) return fail(MVIN_ERR_UNSUPPORTED, "too many candidates per user (%d)", max_cand);
+  int rc;
+  if ((rc = set_smem(topk_metrics_kernel, sm))) return rc;
+  topk_metrics_kernel<<<n_users, 256, sm, (cudaStream_t)stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MVIN_ERR_CUDA, "launch topk_metrics: %s", cudaGetErrorString(e));
+  return MVIN_OK;
+}
+
 int mvin_ctr_metrics(mvin_handle_t h, const float* scores_normalized, const float* labels, int32_t B, float* out3,
                      void* scratch40, void* stream) {
   if (!h || !scores_normalized || !labels || !out3 || !scratch40 || B < 1) return fail(MVIN_ERR_INVALID, "bad argument");

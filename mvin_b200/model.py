@@ -500,6 +500,19 @@ class MVIN(object):
         self.forward_device(d_users, d_items, d_mh, d_mr, d_mt, None, scores_n)
         return self.ctr_metrics_device(scores_n, d_labels)
 
+    def topk_metrics_device(self, scores, relevant, n_cand, n_answers, k_list):
+        """Per-user precision@k / recall@k / ndcg@k of topk_eval (util.py:183-197) on the device.  scores float32
+        [n_users, max_cand], relevant uint8 [n_users, max_cand], n_cand / n_answers int32 [n_users] -- CUDA tensors;
+        returns three numpy arrays [n_users, len(k_list)] (the reference then takes np.mean over users)."""
+        n_users, max_cand = scores.shape
+        nk = len(k_list)
+        out = [torch.empty((n_users, nk), dtype=torch.float32, device=self.device) for _ in range(3)]
+        ks = (C.c_int32 * nk)(*[int(k) for k in k_list])
+        check(self.lib.mvin_topk_metrics(scores.data_ptr(), relevant.data_ptr(), n_cand.data_ptr(), n_answers.data_ptr(),
+                                         n_users, max_cand, C.cast(ks, C.c_void_p), nk, out[0].data_ptr(), out[1].data_ptr(),
+                                         out[2].data_ptr(), self._stream()), "mvin_topk_metrics")
+        return tuple(o.cpu().numpy() for o in out)
+
     def ctr_metrics_device(self, scores_normalized, labels):
         """scores_normalized, labels: float32 CUDA tensors [B] -> (auc, acc, f1) python floats."""
         out = torch.empty(3, dtype=torch.float32, device=self.device)

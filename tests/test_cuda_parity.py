@@ -395,3 +395,42 @@ def test_prefetch_pipeline_matches_plain_steps():
         assert np.allclose(x, y, rtol=1e-5, atol=1e-7), (x, y)
     with pytest.raises(IndexError):
         b.train_step_prefetched()                          # nothing pending
+
+
+def test_topk_metrics_match_reference_formulas():
+    """mvin_topk_metrics against a restatement of the metric steps of topk_eval (util.py:183-197) and metrics.py
+    (dcg / ndcg method 1 :3-31, precision :34-37, recall :97-100), ties and short candidate lists included."""
+    from mvin_b200 import MVIN
+    args = make_args(batch_size=8)
+    prob = make_problem(args)
+    model = MVIN(args, prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"], prob["adj_relation"])
+    rng = np.random.RandomState(0)
+    n_users, max_cand, k_list = 37, 500, [1, 2, 5, 10, 25, 50, 100]
+    scores = rng.rand(n_users, max_cand).astype(np.float32)
+    scores[::3] = np.round(scores[::3] * 20) / 20                       # heavy ties for a third of the users
+    n_cand = rng.randint(60, max_cand + 1, n_users).astype(np.int32)
+    n_cand[0] = 30                                                      # fewer candidates than k_list[-1]
+    rel = (rng.rand(n_users, max_cand) < 0.03).astype(np.uint8)
+    rel[5] = 0                                                          # a user without any hit
+    extra = rng.randint(0, 4, n_users)                                  # held-out items outside the candidate list
+    n_answers = np.array([int(rel[u, :n_cand[u]].sum()) + int(extra[u]) for u in range(n_users)], dtype=np.int32)
+    n_answers = np.maximum(n_answers, 1)
+    prec, rec, ndcg = model.topk_metrics_device(torch.from_numpy(scores).cuda(), torch.from_numpy(rel).cuda(),
+                                                torch.from_numpy(n_cand).cuda(), torch.from_numpy(n_answers).cuda(), k_list)
+
+    def dcg(r, k):
+        r = np.asarray(r, dtype=np.float64)[:k]
+        return float(np.sum(r / np.log2(np.arange(2, r.size + 2)))) if r.size else 0.0
+
+    for u in range(n_users):
+        n = int(n_cand[u])
+        order = sorted(range(n), key=lambda i: -scores[u, i])            # stable: ties keep candidate order
+        hits_sorted = [int(rel[u, i]) for i in order]
+        r_hit = hits_sorted[:k_list[-1]]                                # built once, with the last k (util.py:190-195)
+        for q, k in enumerate(k_list):
+            inter = sum(hits_sorted[:k])
+            assert abs(prec[u, q] - inter / k) < 1e-6
+            assert abs(rec[u, q] - inter / n_answers[u]) < 1e-6
+            ideal = dcg(sorted(r_hit, reverse=True), k)
+            want = dcg(r_hit, k) / ideal if ideal else 0.0
+            assert abs(ndcg[u, q] - want) < 1e-6, (u, k)
