@@ -434,3 +434,110 @@ def test_topk_metrics_match_reference_formulas():
             ideal = dcg(sorted(r_hit, reverse=True), k)
             want = dcg(r_hit, k) / ideal if ideal else 0.0
             assert abs(ndcg[u, q] - want) < 1e-6, (u, k)
+
+
+def _random_uts(prob, args, seed=9):
+    rng = np.random.RandomState(seed)
+    p = max(1, args.p_hop)
+    return np.stack([np.stack([np.stack([rng.randint(0, prob["n_entity"], args.n_memory),
+                                         rng.randint(0, prob["n_relation"], args.n_memory),
+                                         rng.randint(0, prob["n_entity"], args.n_memory)]) for _ in range(p)])
+                     for _ in range(prob["n_user"])]).astype(np.int32)             # [n_user, p, 3, m]
+
+
+def _feed_top_k(model, args, users, items, uts):
+    """get_feed_dict_top_k (util.py:220-230) restated."""
+    fd = {model.user_indices: np.asarray(users, dtype=np.int64), model.item_indices: np.asarray(items, dtype=np.int64),
+          model.labels: np.ones(len(users), dtype=np.float32)}
+    for i in range(max(1, args.p_hop)):
+        fd[model.memories_h[i]] = np.stack([uts[u][i][0] for u in users])
+        fd[model.memories_r[i]] = np.stack([uts[u][i][1] for u in users])
+        fd[model.memories_t[i]] = np.stack([uts[u][i][2] for u in users])
+    return fd
+
+
+@pytest.mark.parametrize("bound", [False, True])
+def test_topk_eval_driver_matches_reference_loop(bound):
+    """evaluate.topk_eval (packed scoring + one metrics launch) against the reference's loop (util.py:137-205): one
+    user per batch, last batch padded with the last candidate, dict of scores, sorted(), metrics.py formulas."""
+    from mvin_b200 import MVIN
+    from mvin_b200.evaluate import topk_eval
+    args = make_args(dim=16, neighbor_sample_size=4, h_hop=2, p_hop=2, n_memory=8, batch_size=16)
+    prob = make_problem(args, seed=3)
+    uts = _random_uts(prob, args)
+    model = MVIN(args, prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"], prob["adj_relation"])
+    model.load_named_parameters({k: v.numpy() for k, v in prob["P"].items()})
+    if bound:
+        model.bind_user_triplet_set(uts)
+    rng = np.random.RandomState(4)
+    item_set = set(range(60))
+    train_record = {u: set(rng.choice(60, rng.randint(0, 12), replace=False).tolist()) for u in range(prob["n_user"])}
+    test_record = {u: set(rng.choice(60, rng.randint(1, 9), replace=False).tolist()) for u in range(0, prob["n_user"], 2)}
+    user_list = list(range(3, 33))                     # odd users are not in the test record and are skipped
+    k_list = [1, 2, 5, 10, 20]
+    prec, rec, ndcg, _, _ = topk_eval(None, args, uts, model, user_list, train_record, {}, test_record, item_set, k_list,
+                                      args.batch_size, mode="test")
+
+    def dcg(r, k):
+        r = np.asarray(r, dtype=np.float64)[:k]
+        return float(np.sum(r / np.log2(np.arange(2, r.size + 2)))) if r.size else 0.0
+
+    want = {name: {k: [] for k in k_list} for name in ("p", "r", "n")}
+    bs = args.batch_size
+    for user in user_list:
+        if user not in test_record:
+            continue
+        cand = list(item_set - train_record[user])
+        score_of = {}
+        start = 0
+        while start < len(cand):
+            chunk = cand[start:start + bs]
+            chunk = chunk + [cand[-1]] * (bs - len(chunk))
+            items, scores = model.get_scores(None, _feed_top_k(model, args, [user] * bs, chunk, uts))
+            for it, s in zip(items, scores):
+                score_of[int(it)] = float(s)
+            start += bs
+        ranked = [it for it, _ in sorted(score_of.items(), key=lambda kv: kv[1], reverse=True)]
+        hits = [1 if it in test_record[user] else 0 for it in ranked]
+        r_hit = hits[:k_list[-1]]
+        for k in k_list:
+            want["p"][k].append(sum(hits[:k]) / k)
+            want["r"][k].append(sum(hits[:k]) / len(test_record[user]))
+            ideal = dcg(sorted(r_hit, reverse=True), k)
+            want["n"][k].append(dcg(r_hit, k) / ideal if ideal else 0.0)
+    for q, k in enumerate(k_list):
+        assert abs(prec[q] - np.mean(want["p"][k])) < 1e-6, k
+        assert abs(rec[q] - np.mean(want["r"][k])) < 1e-6, k
+        assert abs(ndcg[q] - np.mean(want["n"][k])) < 1e-6, k
+    assert max(rec) > 0.0
+
+
+def test_ctr_eval_driver_matches_per_batch_eval():
+    """evaluate.ctr_eval against the reference loop (util.py:44-56): model.eval per full batch of the split, means."""
+    from mvin_b200 import MVIN
+    from mvin_b200.evaluate import ctr_eval
+    args = make_args(dim=16, neighbor_sample_size=4, h_hop=2, p_hop=2, n_memory=8, batch_size=32)
+    prob = make_problem(args, seed=6)
+    uts = _random_uts(prob, args)
+    rng = np.random.RandomState(2)
+    data = np.stack([rng.randint(0, prob["n_user"], 150), rng.randint(0, 60, 150), rng.randint(0, 2, 150)], axis=1)
+    results = []
+    for bound in (False, True):
+        model = MVIN(args, prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"], prob["adj_relation"])
+        model.load_named_parameters({k: v.numpy() for k, v in prob["P"].items()})
+        if bound:
+            model.bind_user_triplet_set(uts)
+        results.append(ctr_eval(args, None, None, model, data, uts, args.batch_size))
+    want = []
+    for s in range(0, 150 - 32 + 1, 32):
+        rows = data[s:s + 32]
+        fd = _feed_top_k(model, args, rows[:, 0], rows[:, 1], uts)
+        fd[model.labels] = rows[:, 2].astype(np.float32)
+        want.append(model.eval(None, fd))
+    assert len(want) == 4
+    for res in results:
+        assert len(res[0]) == 4
+        for b in range(4):
+            assert abs(res[0][b] - want[b][0]) < 1e-6 and abs(res[1][b] - want[b][1]) < 1e-6
+            assert abs(res[2][b] - want[b][2]) < 1e-6
+        assert abs(res[3] - np.mean([w[0] for w in want])) < 1e-6
