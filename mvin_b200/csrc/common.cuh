@@ -9,6 +9,16 @@
 
 namespace mvin {
 
+// Programmatic dependent launch (mvin_capi.cu launches every kernel with programmatic stream serialisation): the first
+// statement of every kernel.  griddepcontrol.wait blocks until the preceding kernel of the stream has completed and its
+// writes are visible (a no-op for a normal launch); launch_dependents then lets the NEXT kernel's CTAs become resident
+// and sit at their own wait while this grid runs, so launch latency, CTA rasterisation and block start-up leave the
+// critical path.  The trigger comes after the wait, so at most two kernels of a stream are co-resident.
+MVIN_DEV void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 MVIN_DEV float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o));

@@ -32,6 +32,7 @@ constexpr int GEMM_THREADS = 256;
 // CTA tile BM x BN, k-step BK; thread (ty, tx) owns TMR rows x 4 columns.
 template <int BM, int BN, int BK>
 __global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(GemmArgs g) {
+  pdl_enter();
   constexpr int TX = BN / 4, TY = GEMM_THREADS / TX, TMR = BM / TY;
   static_assert(TMR >= 1 && TMR * TY == BM, "bad tile");
   __shared__ float As[BK][BM + 4];

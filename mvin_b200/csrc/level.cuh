@@ -409,6 +409,7 @@ struct TransformArgs {
 
 template <int D>
 __global__ void __launch_bounds__(TC<D>::NT) transform_fwd_kernel(TransformArgs a) {
+  pdl_enter();
   using C = TC<D>;
   extern __shared__ __align__(16) float smem[];
   float* Ws = smem;
@@ -450,6 +451,7 @@ __global__ void __launch_bounds__(TC<D>::NT) transform_fwd_kernel(TransformArgs 
 //           gx = dT . W_t[h]^T ;  dE[ent] += gx ;  du[b] += sum_rows gx
 template <int D>
 __global__ void __launch_bounds__(TC<D>::NT) transform_bwd_kernel(TransformArgs a) {
+  pdl_enter();
   using C = TC<D>;
   extern __shared__ __align__(16) float smem[];
   float* Ws = smem;
@@ -561,6 +563,7 @@ struct AggSmem {
 
 template <int D, bool HAS_LEAF>
 __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
+  pdl_enter();
   using C = TC<D>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int K = a.K, KP = padded_k(K);
@@ -725,6 +728,7 @@ struct AggBwdArgs {
 
 template <int D, bool HAS_LEAF>
 __global__ void __launch_bounds__(TC<D>::NT, (D <= 64 ? 3 : 1)) agg_bwd_kernel(AggBwdArgs a) {
+  pdl_enter();
   using C = TC<D>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int K = a.K, KP = padded_k(K);
@@ -959,6 +963,7 @@ MVIN_DEV AdjRec load_adj(const int32_t* __restrict__ adj, long e, int K, int lan
 // (the adjacency record of the next marked entity is fetched while the current one is processed).
 template <int D, bool BWD>
 __global__ void __launch_bounds__(LEAF_NT) leaf_entity_kernel(LeafEntArgs a) {
+  pdl_enter();
   constexpr int LPR = D / 4, G = 32 / LPR;
   extern __shared__ __align__(16) float smem[];
   float* pw = smem;                                        // [NW][MAX_K]
@@ -1055,6 +1060,7 @@ struct DwArgs {
 
 template <int D>
 __global__ void __launch_bounds__(TC<D>::NT) dw_kernel(DwArgs a) {
+  pdl_enter();
   using C = TC<D>;
   extern __shared__ __align__(16) float smem[];
   float* As = smem;

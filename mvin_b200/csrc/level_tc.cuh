@@ -96,6 +96,7 @@ inline size_t transform_fwd_tc_smem() { return 2 * TT<D>::TILE + 2 * TT<D>::WTIL
 
 template <int D>
 __global__ void __launch_bounds__(TT<D>::NT) transform_fwd_tc_kernel(TransformArgs a) {
+  pdl_enter();
   using T = TT<D>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* a_hi = smem_raw;
@@ -199,6 +200,7 @@ inline size_t agg_fwd_tc_smem(bool has_leaf, int K, int n_rel) {
 
 template <int D, bool HAS_LEAF>
 __global__ void __launch_bounds__(TT<D>::NT) agg_fwd_tc_kernel(AggArgs a) {
+  pdl_enter();
   using T = TT<D>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int K = a.K, KP = padded_k(K);

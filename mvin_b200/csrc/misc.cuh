@@ -8,6 +8,7 @@ namespace mvin {
 // ---- adjacency packing: int64 [n_entity, K] x 2 (model.py:7,19-20) -> int32 [n_entity][2][K] -----------
 __global__ void pack_adj_kernel(const int64_t* __restrict__ adjE, const int64_t* __restrict__ adjR, long n_entity,
                                 int K, int32_t* __restrict__ out) {
+  pdl_enter();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_entity * K) return;
   const long e = i / K;
@@ -20,6 +21,7 @@ __global__ void pack_adj_kernel(const int64_t* __restrict__ adjE, const int64_t*
 // `stamp` (optional): mark the produced ids (entity mode of the leaf level, level.cuh)
 __global__ void expand_kernel(const int32_t* __restrict__ ent, const int32_t* __restrict__ adj, long rows, int K,
                               int32_t* __restrict__ out, int32_t* __restrict__ stamp) {
+  pdl_enter();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * K) return;
   const long j = i / K;
@@ -31,6 +33,7 @@ __global__ void expand_kernel(const int32_t* __restrict__ ent, const int32_t* __
 
 __global__ void expand_i64_kernel(const int64_t* __restrict__ ent, const int32_t* __restrict__ adj, long rows,
                                   int K, int64_t* __restrict__ out_e, int64_t* __restrict__ out_r) {
+  pdl_enter();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * K) return;
   const long j = i / K;
@@ -41,6 +44,7 @@ __global__ void expand_i64_kernel(const int64_t* __restrict__ ent, const int32_t
 }
 
 __global__ void copy_i64_kernel(const int64_t* __restrict__ src, long n, int64_t* __restrict__ dst) {
+  pdl_enter();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i];
 }
@@ -48,6 +52,7 @@ __global__ void copy_i64_kernel(const int64_t* __restrict__ src, long n, int64_t
 // ---- seeds: ent[0] = item as int32 (model.py:243-256 starts from item_indices); optional stamps -------------
 __global__ void seed_kernel(const int64_t* __restrict__ item, int B, int32_t* __restrict__ ent0,
                             int32_t* __restrict__ stamp) {
+  pdl_enter();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const long e = item[b];
@@ -59,6 +64,7 @@ __global__ void seed_kernel(const int64_t* __restrict__ item, int B, int32_t* __
 // the packed per-user sets  uts int32 [n_user, P, 3, m]  (data_loader_user_set.py:402)  into  mem_x int32 [P, B, m]
 __global__ void gather_feed_kernel(const int32_t* __restrict__ uts, const int64_t* __restrict__ user, int B, int P, int m,
                                    int32_t* __restrict__ mem_h, int32_t* __restrict__ mem_r, int32_t* __restrict__ mem_t) {
+  pdl_enter();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;        // over [P][B][m]
   const long n = (long)P * B * m;
   if (i >= n) return;
@@ -75,6 +81,7 @@ __global__ void gather_feed_kernel(const int32_t* __restrict__ uts, const int64_
 template <int D>
 __global__ void prep_items_kernel(const int64_t* __restrict__ item, ETab E, int B,
                                   int32_t* __restrict__ ent0, float* __restrict__ Vbuf, int32_t* __restrict__ stamp) {
+  pdl_enter();
   constexpr int LPR = D / 4;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long)B * LPR) return;
@@ -88,6 +95,7 @@ __global__ void prep_items_kernel(const int64_t* __restrict__ item, ETab E, int 
 // ---- dE[ent[b]] += rows[b]   (row scatter-add of a dense [B, D] buffer) ---------------------------------
 template <int D>
 __global__ void scatter_rows_kernel(const float* __restrict__ rows, const int32_t* __restrict__ ent, int B, GTab dE) {
+  pdl_enter();
   constexpr int LPR = D / 4;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long)B * LPR) return;
@@ -99,6 +107,7 @@ __global__ void scatter_rows_kernel(const float* __restrict__ rows, const int32_
 // ---- relation scores s[i][r] = Rel[r] . urh_weights_i[D:2D]  (aggregators.py:130-133, relation third) --
 __global__ void rel_scores_kernel(const float* __restrict__ Rel, const float* __restrict__ urh, int n_rel, int D,
                                   int H, float* __restrict__ s) {
+  pdl_enter();
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
   if (w >= H * n_rel) return;
   const int i = w / n_rel, r = w % n_rel;
@@ -112,6 +121,7 @@ __global__ void rel_scores_kernel(const float* __restrict__ Rel, const float* __
 __global__ void rel_scores_bwd_kernel(const float* __restrict__ Rel, const float* __restrict__ urh,
                                       const float* __restrict__ ds, int n_rel, int D, float* __restrict__ dRel,
                                       float* __restrict__ durh) {
+  pdl_enter();
   const int i = blockIdx.x;
   for (int j = threadIdx.x; j < D; j += blockDim.x) {
     const float wj = urh[(long)i * 3 * D + D + j];
@@ -129,6 +139,7 @@ __global__ void rel_scores_bwd_kernel(const float* __restrict__ Rel, const float
 template <int D>
 __global__ void score_kernel(const float* __restrict__ u, const float* __restrict__ item, int B,
                              float* __restrict__ scores, float* __restrict__ scores_norm) {
+  pdl_enter();
   constexpr int LPR = D / 4;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long b = i / LPR;
@@ -152,6 +163,7 @@ __global__ void __launch_bounds__(256) mix_score_kernel(const float* __restrict_
                                                         const float* __restrict__ u, int B, int H1,
                                                         float* __restrict__ item, float* __restrict__ scores,
                                                         float* __restrict__ scores_norm) {
+  pdl_enter();
   constexpr int LPR = D / 4, RT = 256 / LPR;
   extern __shared__ __align__(16) float a_s[];            // [RT][H1 * D] (+ [H1 * D][D] weights when d <= 64)
   const int tid = threadIdx.x, tx = tid % LPR, r = tid / LPR;
@@ -202,6 +214,7 @@ __global__ void __launch_bounds__(256) loss_mix_bwd_kernel(const float* __restri
                                                            float* __restrict__ ditem, float* __restrict__ du,
                                                            float* __restrict__ DC /* [H1][B][D] */,
                                                            float* __restrict__ bce_acc) {
+  pdl_enter();
   constexpr int LPR = D / 4, RT = 16;
   extern __shared__ __align__(16) float sm[];
   const int KO = H1 * D;                                   // outputs per row
@@ -257,6 +270,7 @@ template <int D>
 __global__ void loss_bwd_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
                                 const float* __restrict__ u, const float* __restrict__ item, int B, float invB,
                                 float* __restrict__ ditem, float* __restrict__ du, float* __restrict__ bce_acc) {
+  pdl_enter();
   constexpr int LPR = D / 4;
   __shared__ float red;
   if (threadIdx.x == 0) red = 0.f;
@@ -292,6 +306,7 @@ struct L2Segments {
 };
 
 __global__ void l2_dense_kernel(L2Segments sg, float* __restrict__ acc /* [1]=l2, [2]=l2_agg */) {
+  pdl_enter();
   __shared__ float red[2];
   if (threadIdx.x < 2) red[threadIdx.x] = 0.f;
   __syncthreads();
@@ -316,6 +331,7 @@ __global__ void l2_dense_kernel(L2Segments sg, float* __restrict__ acc /* [1]=l2
 
 // ---- un-normalised L2 over the gathered relation-KGE matrices (model.py:386): sum_r cnt[r] |RK[r]|^2 -----
 __global__ void hist_r_kernel(const int32_t* __restrict__ mem_r, long n, int n_rel, float* __restrict__ cnt) {
+  pdl_enter();
   extern __shared__ float h[];
   for (int i = threadIdx.x; i < n_rel; i += blockDim.x) h[i] = 0.f;
   __syncthreads();
@@ -328,6 +344,7 @@ __global__ void hist_r_kernel(const int32_t* __restrict__ mem_r, long n, int n_r
 
 __global__ void rk_l2_kernel(const float* __restrict__ RK, const float* __restrict__ cnt, int DD, float two_l2,
                              float* __restrict__ dRK, float* __restrict__ l2_acc) {
+  pdl_enter();
   const int r = blockIdx.x;
   const float cr = cnt[r];
   float sq = 0.f;
@@ -342,6 +359,7 @@ __global__ void rk_l2_kernel(const float* __restrict__ RK, const float* __restri
 
 // losses_out = {loss, base_loss, l2_loss, l2_agg_loss}  (model.py:412)
 __global__ void finalize_loss_kernel(const float* __restrict__ acc, float l2w, float l2a, float* __restrict__ out) {
+  pdl_enter();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     out[0] = acc[0] + l2w * acc[1] + l2a * acc[2];
     out[1] = acc[0];
@@ -353,6 +371,7 @@ __global__ void finalize_loss_kernel(const float* __restrict__ acc, float l2w, f
 // ---- transposed copies of the d x d weights: dst[i] = W_a[i]^T (i < H), dst[H + e] = W_t[e]^T (e <= H) ------
 __global__ void transpose_kernel(const float* __restrict__ agg_w, const float* __restrict__ transfer_w, int H, int D,
                                  float* __restrict__ dst) {
+  pdl_enter();
   const int b = blockIdx.x;
   const float* s = b < H ? agg_w + (long)b * D * D : transfer_w + (long)(b - H) * D * D;
   float* d = dst + (long)b * D * D;
@@ -365,6 +384,7 @@ __global__ void transpose_kernel(const float* __restrict__ agg_w, const float* _
 // ---- importance_list (model.py:319-323): p = softmax_k(s_0[rel_k]) for the nodes of one level ------------
 __global__ void importance_kernel(const int32_t* __restrict__ ent, const int32_t* __restrict__ adj,
                                   const float* __restrict__ s, long rows, int K, float* __restrict__ probs) {
+  pdl_enter();
   const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) / 32;
   const int lane = threadIdx.x % 32;
   if (row >= rows) return;
@@ -401,6 +421,7 @@ __global__ void sample_adjacency_kernel(const int64_t* __restrict__ indptr, cons
                                         const int32_t* __restrict__ rel, int n_entity, int K, unsigned long long seed,
                                         int32_t* __restrict__ adj_packed, int64_t* __restrict__ adj_entity,
                                         int64_t* __restrict__ adj_relation, int64_t* __restrict__ picked_edges) {
+  pdl_enter();
   const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_entity) return;
   const long beg = indptr[e], deg = indptr[e + 1] - beg;
@@ -457,6 +478,7 @@ __global__ void ripple_sets_kernel(const int64_t* __restrict__ indptr, const int
                                    const int32_t* __restrict__ hist_items, int n_user, int P, int m, int n_neighbor,
                                    unsigned long long seed, int32_t* __restrict__ uts /* [n_user, P, 3, m] */,
                                    int64_t* __restrict__ slots /* optional [n_user, P, m]: candidate slot ids */) {
+  pdl_enter();
   const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= n_user) return;
   for (int hop = 0; hop < P; ++hop) {
@@ -520,6 +542,7 @@ __global__ void ripple_sets_kernel(const int64_t* __restrict__ indptr, const int
 // acc / f1 use the reference's threshold (score >= 0.5 -> 1).  out = {auc, acc, f1}; acc64 = 5 zeroed counters.
 __global__ void ctr_count_kernel(const float* __restrict__ scores, const float* __restrict__ labels, int B,
                                  unsigned long long* __restrict__ acc64 /* [0] 2*gt + eq, [1] P, [2] tp, [3] fp, [4] fn */) {
+  pdl_enter();
   extern __shared__ float sj[];                       // tile of scores / labels of the "j" side
   float* lj = sj + blockDim.x;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -557,6 +580,7 @@ __global__ void ctr_count_kernel(const float* __restrict__ scores, const float* 
   }
 }
 __global__ void ctr_finalize_kernel(const unsigned long long* __restrict__ acc64, int B, float* __restrict__ out) {
+  pdl_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double P = (double)acc64[1], N = (double)B - P;
   const double tp = (double)acc64[2], fp = (double)acc64[3], fn = (double)acc64[4];
@@ -585,6 +609,7 @@ struct TopkArgs {
   float* ndcg;
 };
 __global__ void __launch_bounds__(256) topk_metrics_kernel(TopkArgs a) {
+  pdl_enter();
   extern __shared__ float sc[];                          // [max_cand] scores, then hit flags by rank
   unsigned char* hit = reinterpret_cast<unsigned char*>(sc + a.max_cand);   // [k_last]
   __shared__ int cnt[TOPK_MAX_K];
@@ -633,6 +658,7 @@ struct AdamSegments {
 };
 
 __global__ void adam_kernel(AdamSegments sg, float lr_t, float beta1, float beta2, float eps) {
+  pdl_enter();
   for (int sidx = 0; sidx < sg.count; ++sidx) {
     float* p = sg.param[sidx];
     const float* g = sg.grad[sidx];

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <utility>
 #include <vector>
 
 #include "../../include/mvin_b200.h"
@@ -36,6 +37,34 @@ int fail(int code, const char* fmt, ...) {
 }
 
 void prof_mark(mvin_handle_t h, cudaStream_t st, const char* name);
+
+// Every kernel goes through here.  With programmatic stream serialisation the kernel may start while its predecessor
+// in the stream is still running; each kernel's first statement is pdl_enter() (common.cuh), which restores the
+// dependency on the device.  MVIN_B200_PDL=0 launches normally.
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MVIN_B200_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);   // error picked up by LAUNCH_CHECK
+}
+#define MVIN_LAUNCH(kernel, grid, block, smem, st, ...) launch_kernel(kernel, grid, block, smem, st, ##__VA_ARGS__)
 
 #define CUDA_TRY(expr)                                                                              \
   do {                                                                                              \
@@ -242,7 +271,7 @@ T* at(void* ws, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(ws)
 template <int BM, int BN, int BK>
 void launch_gemm_tile(const GemmArgs& g, cudaStream_t st) {
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, (g.reduce ? 1 : g.nbatch) * g.ksplit);
-  gemm_kernel<BM, BN, BK><<<grid, GEMM_THREADS, 0, st>>>(g);
+  MVIN_LAUNCH((gemm_kernel<BM, BN, BK>), grid, GEMM_THREADS, 0, st, g);
 }
 
 // Tile choice: these GEMMs are tall and skinny and tiny next to the gather kernels, so pick the tile that yields
@@ -383,11 +412,11 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
   {
     cudaStream_t st = par.s(0);
     if (stamp) CUDA_TRY(cudaMemsetAsync(stamp, 0, sizeof(int32_t) * (size_t)c.n_entity, st));
-    seed_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(item, B, at<int32_t>(ws, L.ent[0]), H == 1 ? stamp : nullptr);
+    MVIN_LAUNCH((seed_kernel), (unsigned)((B + 255) / 256), 256, 0, st, item, B, at<int32_t>(ws, L.ent[0]), H == 1 ? stamp : nullptr);
     LAUNCH_CHECK(h, "seed");
     for (int lv = 0; lv + 1 < H; ++lv) {
       const long n = L.rows[lv] * K;
-      expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(at<int32_t>(ws, L.ent[lv]), h->adj, L.rows[lv], K,
+      MVIN_LAUNCH((expand_kernel), (unsigned)((n + 255) / 256), 256, 0, st, at<int32_t>(ws, L.ent[lv]), h->adj, L.rows[lv], K,
                                                                  at<int32_t>(ws, L.ent[lv + 1]),
                                                                  lv + 1 == H - 1 ? stamp : nullptr);
       LAUNCH_CHECK(h, "expand");
@@ -395,7 +424,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
     // relation scores of every aggregator
     {
       const int warps = H * nr;
-      rel_scores_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(P.relation_emb, P.agg_urh_w, nr, D, H,
+      MVIN_LAUNCH((rel_scores_kernel), (warps * 32 + 255) / 256, 256, 0, st, P.relation_emb, P.agg_urh_w, nr, D, H,
                                                                  at<float>(ws, L.s));
       LAUNCH_CHECK(h, "rel_scores");
     }
@@ -409,7 +438,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
       if ((rc = set_smem(leaf_entity_kernel<D, false>, sm))) return rc;
       const long want = ((long)c.n_entity + LEAF_NW * 32 - 1) / (LEAF_NW * 32);
       const long cap = (long)h->sm_count * 8;
-      leaf_entity_kernel<D, false><<<(unsigned)(want < cap ? want : cap), LEAF_NT, sm, st>>>(a);
+      MVIN_LAUNCH((leaf_entity_kernel<D, false>), (unsigned)(want < cap ? want : cap), LEAF_NT, sm, st, a);
       LAUNCH_CHECK(h, "leaf_entity_fwd");
     }
   }
@@ -418,7 +447,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
   const bool q_fused = user_q_fused(D, nr);
   if (!q_fused && p > 0) {
     const long n = (long)B * C::LPR;
-    prep_items_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(item, h->etab, B, nullptr,
+    MVIN_LAUNCH((prep_items_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, item, h->etab, B, nullptr,
                                                                       at<float>(ws, L.Vbuf), nullptr);
     LAUNCH_CHECK(h, "prep_items");
   }
@@ -447,15 +476,15 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
     switch (PB) {
       case 4:
         if ((rc = set_smem(user_fwd_kernel<D, 4>, sm))) return rc;
-        user_fwd_kernel<D, 4><<<grid, nt, sm, st>>>(a);
+        MVIN_LAUNCH((user_fwd_kernel<D, 4>), grid, nt, sm, st, a);
         break;
       case 2:
         if ((rc = set_smem(user_fwd_kernel<D, 2>, sm))) return rc;
-        user_fwd_kernel<D, 2><<<grid, nt, sm, st>>>(a);
+        MVIN_LAUNCH((user_fwd_kernel<D, 2>), grid, nt, sm, st, a);
         break;
       default:
         if ((rc = set_smem(user_fwd_kernel<D, 1>, sm))) return rc;
-        user_fwd_kernel<D, 1><<<grid, nt, sm, st>>>(a);
+        MVIN_LAUNCH((user_fwd_kernel<D, 1>), grid, nt, sm, st, a);
     }
     LAUNCH_CHECK(h, "user_fwd");
   }
@@ -483,13 +512,13 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
         if ((rc = set_smem(transform_fwd_tc_kernel<D>, smt))) return rc;
         const int grid = partition_grid(rows, H, TT<D>::R,
                                         h->sm_count * resident_ctas(h, transform_fwd_tc_kernel<D>, TT<D>::NT, smt), a.cta_end);
-        transform_fwd_tc_kernel<D><<<grid, TT<D>::NT, smt, st>>>(a);
+        MVIN_LAUNCH((transform_fwd_tc_kernel<D>), grid, TT<D>::NT, smt, st, a);
         done = true;
       }
     }
     if (!done) {
       const int grid = partition_grid(rows, H, C::R, h->sm_count * resident_ctas(h, transform_fwd_kernel<D>, C::NT, sm), a.cta_end);
-      transform_fwd_kernel<D><<<grid, C::NT, sm, st>>>(a);
+      MVIN_LAUNCH((transform_fwd_kernel<D>), grid, C::NT, sm, st, a);
     }
     LAUNCH_CHECK(h, "transform_fwd");
   }
@@ -533,12 +562,12 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
             if ((rc = set_smem(agg_fwd_tc_kernel<D, true>, smt))) return rc;
             const int grid = make_tile_list(a.tl, rows, nlev, TT<D>::R,
                                             h->sm_count * resident_ctas(h, agg_fwd_tc_kernel<D, true>, TT<D>::NT, smt), h->d_sched);
-            agg_fwd_tc_kernel<D, true><<<grid, TT<D>::NT, smt, st>>>(a);
+            MVIN_LAUNCH((agg_fwd_tc_kernel<D, true>), grid, TT<D>::NT, smt, st, a);
           } else {
             if ((rc = set_smem(agg_fwd_tc_kernel<D, false>, smt))) return rc;
             const int grid = make_tile_list(a.tl, rows, nlev, TT<D>::R,
                                             h->sm_count * resident_ctas(h, agg_fwd_tc_kernel<D, false>, TT<D>::NT, smt), h->d_sched);
-            agg_fwd_tc_kernel<D, false><<<grid, TT<D>::NT, smt, st>>>(a);
+            MVIN_LAUNCH((agg_fwd_tc_kernel<D, false>), grid, TT<D>::NT, smt, st, a);
           }
           done = true;
         }
@@ -547,11 +576,11 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
       } else if (i == 0) {
         const int grid = make_tile_list(a.tl, rows, nlev, C::R,
                                         h->sm_count * resident_ctas(h, agg_fwd_kernel<D, true>, C::NT, sm_leaf), h->d_sched);
-        agg_fwd_kernel<D, true><<<grid, C::NT, sm_leaf, st>>>(a);
+        MVIN_LAUNCH((agg_fwd_kernel<D, true>), grid, C::NT, sm_leaf, st, a);
       } else {
         const int grid = make_tile_list(a.tl, rows, nlev, C::R,
                                         h->sm_count * resident_ctas(h, agg_fwd_kernel<D, false>, C::NT, sm_in), h->d_sched);
-        agg_fwd_kernel<D, false><<<grid, C::NT, sm_in, st>>>(a);
+        MVIN_LAUNCH((agg_fwd_kernel<D, false>), grid, C::NT, sm_in, st, a);
       }
       LAUNCH_CHECK(h, names[i]);
     }
@@ -562,7 +591,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
     constexpr int RT = 256 / C::LPR;
     const size_t sm = sizeof(float) * ((size_t)RT * (H + 1) * D + (D <= 64 ? (size_t)(H + 1) * D * D : 0));
     if ((rc = set_smem(mix_score_kernel<D>, sm))) return rc;
-    mix_score_kernel<D><<<(unsigned)((B + RT - 1) / RT), 256, sm, st>>>(at<float>(ws, L.V[0][0]), P.mix_w, P.mix_b,
+    MVIN_LAUNCH((mix_score_kernel<D>), (unsigned)((B + RT - 1) / RT), 256, sm, st, at<float>(ws, L.V[0][0]), P.mix_w, P.mix_b,
                                                                         at<float>(ws, L.u), B, H + 1, at<float>(ws, L.item),
                                                                         at<float>(ws, L.scores), scores_norm);
     LAUNCH_CHECK(h, "mix_score");
@@ -619,11 +648,11 @@ int backward_init(mvin_handle_t h, int B, void* ws, cudaStream_t st, cudaEvent_t
     add(P.agg_urh_w, G.agg_urh_w, (long)H * 3 * D, l2a, 1.f, 1);
     add(P.agg_urh_b, G.agg_urh_b, H, 0.f, 0.f, 1);
     sg.count = n;
-    l2_dense_kernel<<<h->sm_count * 2, 256, 0, st>>>(sg, acc);
+    MVIN_LAUNCH((l2_dense_kernel), h->sm_count * 2, 256, 0, st, sg, acc);
     LAUNCH_CHECK(h, "l2_dense");
   }
   // transposed weights: wT[i] = W_a[i]^T (i < H), wT[H + e] = W_t[e]^T (e <= H)
-  transpose_kernel<<<dim3(2 * H + 1), 256, 0, st>>>(P.agg_w, P.transfer_w, H, D, wT);
+  MVIN_LAUNCH((transpose_kernel), dim3(2 * H + 1), 256, 0, st, P.agg_w, P.transfer_w, H, D, wT);
   LAUNCH_CHECK(h, "transpose");
   if (mid) cudaEventRecord(mid, st);
   CUDA_TRY(cudaMemsetAsync(at<char>(ws, L.zero_mid), 0, L.zero_end - L.zero_mid, st));
@@ -644,7 +673,7 @@ int launch_dw(mvin_handle_t h, cudaStream_t st, const DwArgs& a, int groups, con
   if ((rc = set_smem(dw_kernel<D>, sm))) return rc;
   long tiles = (a.rows + C::R - 1) / C::R;
   int gx = (int)(tiles < h->sm_count ? tiles : h->sm_count);
-  dw_kernel<D><<<dim3(gx, groups), C::NT, sm, st>>>(a);
+  MVIN_LAUNCH((dw_kernel<D>), dim3(gx, groups), C::NT, sm, st, a);
   LAUNCH_CHECK(h, name);
   return MVIN_OK;
 }
@@ -680,7 +709,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
   // ripple-memory relation histogram (feeds the un-normalised L2 over gathered RK matrices, model.py:386)
   if (p > 0) {
     const long n = (long)p * B * m;
-    hist_r_kernel<<<h->sm_count * 4, 256, sizeof(float) * nr, st>>>(h->mem_r, n, nr, at<float>(ws, L.cnt));
+    MVIN_LAUNCH((hist_r_kernel), h->sm_count * 4, 256, sizeof(float) * nr, st, h->mem_r, n, nr, at<float>(ws, L.cnt));
     LAUNCH_CHECK(h, "hist_r");
   }
   }
@@ -694,12 +723,12 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     const size_t sm = sizeof(float) * ((size_t)D * (H + 1) * D + 16 * D);
     if ((rc = set_smem(loss_mix_bwd_kernel<D>, sm))) return rc;
     const int grid = (B + 15) / 16 < 2 * h->sm_count ? (B + 15) / 16 : 2 * h->sm_count;
-    loss_mix_bwd_kernel<D><<<grid, 256, sm, st>>>(at<float>(ws, L.scores), labels, at<float>(ws, L.u), at<float>(ws, L.item),
+    MVIN_LAUNCH((loss_mix_bwd_kernel<D>), grid, 256, sm, st, at<float>(ws, L.scores), labels, at<float>(ws, L.u), at<float>(ws, L.item),
                                                   P.mix_w, B, H + 1, invB, ditem, du, at<float>(ws, L.DC[0][0]), acc);
     LAUNCH_CHECK(h, "loss_mix_bwd");
   } else {
     const long n = (long)B * C::LPR;
-    loss_bwd_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(at<float>(ws, L.scores), labels, at<float>(ws, L.u),
+    MVIN_LAUNCH((loss_bwd_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, at<float>(ws, L.scores), labels, at<float>(ws, L.u),
                                                                     at<float>(ws, L.item), B, invB, ditem, du, acc);
     LAUNCH_CHECK(h, "loss_bwd");
   }
@@ -764,11 +793,11 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
         a.GSe = L.entity_leaf ? at<float>(ws, L.GSe) : nullptr;
         const int grid = make_tile_list(a.tl, rows, nlev, C::R,
                                         h->sm_count * resident_ctas(h, agg_bwd_kernel<D, true>, C::NT, sm_leaf), h->d_sched + 2);
-        agg_bwd_kernel<D, true><<<grid, C::NT, sm_leaf, st>>>(a);
+        MVIN_LAUNCH((agg_bwd_kernel<D, true>), grid, C::NT, sm_leaf, st, a);
       } else {
         const int grid = make_tile_list(a.tl, rows, nlev, C::R,
                                         h->sm_count * resident_ctas(h, agg_bwd_kernel<D, false>, C::NT, sm_in), h->d_sched + 2);
-        agg_bwd_kernel<D, false><<<grid, C::NT, sm_in, st>>>(a);
+        MVIN_LAUNCH((agg_bwd_kernel<D, false>), grid, C::NT, sm_in, st, a);
       }
       LAUNCH_CHECK(h, names[i]);
     }
@@ -788,10 +817,10 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     if ((rc = set_smem(leaf_entity_kernel<D, true>, sm))) return rc;
     const long want = ((long)c.n_entity + LEAF_NW * 32 - 1) / (LEAF_NW * 32);
     const long cap = (long)h->sm_count * 8;
-    leaf_entity_kernel<D, true><<<(unsigned)(want < cap ? want : cap), LEAF_NT, sm, st>>>(a);
+    MVIN_LAUNCH((leaf_entity_kernel<D, true>), (unsigned)(want < cap ? want : cap), LEAF_NT, sm, st, a);
     LAUNCH_CHECK(h, "leaf_entity_bwd");
   }
-  rel_scores_bwd_kernel<<<H, 128, 0, st>>>(P.relation_emb, P.agg_urh_w, at<float>(ws, L.ds), nr, D, G.relation_emb,
+  MVIN_LAUNCH((rel_scores_bwd_kernel), H, 128, 0, st, P.relation_emb, P.agg_urh_w, at<float>(ws, L.ds), nr, D, G.relation_emb,
                                            G.agg_urh_w);
   LAUNCH_CHECK(h, "rel_scores_bwd");
   }
@@ -814,7 +843,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     }
     a.nlev = H; a.E = h->etab; a.u = at<float>(ws, L.u); a.dE = h->gtab; a.du = du;
     const int grid = partition_grid(rows, H, C::R, h->sm_count * resident_ctas(h, transform_bwd_kernel<D>, C::NT, sm), a.cta_end);
-    transform_bwd_kernel<D><<<grid, C::NT, sm, st>>>(a);
+    MVIN_LAUNCH((transform_bwd_kernel<D>), grid, C::NT, sm, st, a);
     LAUNCH_CHECK(h, "transform_bwd");
   }
   // user_o = O . W_user + b  backward
@@ -851,14 +880,14 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     long grid = (warps + RIPPLE_NW - 1) / RIPPLE_NW;
     const long resident = (long)h->sm_count * resident_ctas(h, ripple_bwd_kernel<D>, RIPPLE_NT, sm) * 2;   // cap 4 -> 8
     if (grid > resident) grid = resident;
-    ripple_bwd_kernel<D><<<(unsigned)grid, RIPPLE_NT, sm, st>>>(a);
+    MVIN_LAUNCH((ripple_bwd_kernel<D>), (unsigned)grid, RIPPLE_NT, sm, st, a);
     LAUNCH_CHECK(h, "ripple_bwd");
   }
   if (p > 0) {
     // three independent consumers of dQ / cnt: RK L2 term (side 1), dRK (side 0), dE[item] (launch stream)
     par.fork(0);
     par.fork(1);
-    rk_l2_kernel<<<nr, 256, 0, par.s(1)>>>(P.relation_kge, at<float>(ws, L.cnt), D * D, 2.f * l2w, G.relation_kge, acc + 1);
+    MVIN_LAUNCH((rk_l2_kernel), nr, 256, 0, par.s(1), P.relation_kge, at<float>(ws, L.cnt), D * D, 2.f * l2w, G.relation_kge, acc + 1);
     LAUNCH_CHECK(h, "rk_l2");
     // dRK[r][i][j] += sum_b v[b][i] dQ[b][r][j]
     GemmArgs g = gemm_args();
@@ -881,14 +910,14 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
       g2.C = at<float>(ws, L.dv); g2.ldc = D; g2.bsC = 0; g2.accumulate = g2.ksplit > 1;   // dv lives in the zeroed region
       if ((rc = run_gemm(h, st, g2, "gemm_dv"))) return rc;
       const long n = (long)B * C::LPR;
-      scatter_rows_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(at<float>(ws, L.dv), at<int32_t>(ws, L.ent[0]), B,
+      MVIN_LAUNCH((scatter_rows_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, at<float>(ws, L.dv), at<int32_t>(ws, L.ent[0]), B,
                                                                           h->gtab);
       LAUNCH_CHECK(h, "scatter_dv");
     }
   }
   par.join(0);
   par.join(1);
-  finalize_loss_kernel<<<1, 32, 0, st>>>(acc, l2w, l2a, losses_out);
+  MVIN_LAUNCH((finalize_loss_kernel), 1, 32, 0, st, acc, l2w, l2a, losses_out);
   LAUNCH_CHECK(h, "finalize_loss");
   return MVIN_OK;
 }
@@ -1053,7 +1082,7 @@ int mvin_pack_adjacency(const int64_t* adj_entity, const int64_t* adj_relation, 
                         int32_t* adj_packed, void* stream) {
   if (!adj_entity || !adj_relation || !adj_packed || n_entity < 1 || K < 1) return fail(MVIN_ERR_INVALID, "bad argument");
   const long n = (long)n_entity * K;
-  pack_adj_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(adj_entity, adj_relation, n_entity, K,
+  MVIN_LAUNCH((pack_adj_kernel), (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, adj_entity, adj_relation, n_entity, K,
                                                                                 adj_packed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(MVIN_ERR_CUDA, "launch pack_adj: %s", cudaGetErrorString(e));
@@ -1141,12 +1170,12 @@ int mvin_get_neighbors(mvin_handle_t h, const int64_t* item_indices, int32_t B, 
   if (!h->adj) return fail(MVIN_ERR_STATE, "adjacency not bound");
   cudaStream_t st = (cudaStream_t)stream;
   const int K = h->cfg.neighbor_sample_size;
-  copy_i64_kernel<<<(B + 255) / 256, 256, 0, st>>>(item_indices, B, entities[0]);
+  MVIN_LAUNCH((copy_i64_kernel), (B + 255) / 256, 256, 0, st, item_indices, B, entities[0]);
   LAUNCH_CHECK(h, "copy_i64");
   long rows = B;
   for (int i = 0; i < n_levels; ++i) {
     const long n = rows * K;
-    expand_i64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(entities[i], h->adj, rows, K, entities[i + 1],
+    MVIN_LAUNCH((expand_i64_kernel), (unsigned)((n + 255) / 256), 256, 0, st, entities[i], h->adj, rows, K, entities[i + 1],
                                                                    relations[i]);
     LAUNCH_CHECK(h, "expand_i64");
     rows = n;
@@ -1179,7 +1208,7 @@ int mvin_importance(mvin_handle_t h, float* imp0, float* imp1, void* workspace, 
   for (int lv = 0; lv < 2 && lv < h->cfg.h_hop; ++lv) {
     if (!outs[lv]) continue;
     const long rows = L.rows[lv];
-    importance_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(at<int32_t>(workspace, L.ent[lv]), h->adj,
+    MVIN_LAUNCH((importance_kernel), (unsigned)((rows * 32 + 255) / 256), 256, 0, st, at<int32_t>(workspace, L.ent[lv]), h->adj,
                                                                            at<float>(workspace, L.s), rows, K, outs[lv]);
     LAUNCH_CHECK(h, "importance");
   }
@@ -1230,7 +1259,7 @@ int mvin_adam_step(mvin_handle_t h, const mvin_params_t* m, const mvin_params_t*
                              (1.0 - std::pow((double)beta1, step)));
   cudaStream_t st = (cudaStream_t)stream;
   prof_mark(h, st, nullptr);
-  adam_kernel<<<h->sm_count * 4, 256, 0, st>>>(sg, lr_t, beta1, beta2, eps);
+  MVIN_LAUNCH((adam_kernel), h->sm_count * 4, 256, 0, st, sg, lr_t, beta1, beta2, eps);
   LAUNCH_CHECK(h, "adam");
   return MVIN_OK;
 }
@@ -1363,10 +1392,10 @@ int mvin_test_umma_gemm(const float* A, const float* W, float* C, int64_t M, int
   int rc;
   if (D == 32) {
     if ((rc = set_smem(umma_gemm_test_kernel<32>, umma_gemm_test_smem<32>()))) return rc;
-    umma_gemm_test_kernel<32><<<grid, 256, umma_gemm_test_smem<32>(), st>>>(A, W, C, M);
+    MVIN_LAUNCH((umma_gemm_test_kernel<32>), grid, 256, umma_gemm_test_smem<32>(), st, A, W, C, M);
   } else if (D == 64) {
     if ((rc = set_smem(umma_gemm_test_kernel<64>, umma_gemm_test_smem<64>()))) return rc;
-    umma_gemm_test_kernel<64><<<grid, 256, umma_gemm_test_smem<64>(), st>>>(A, W, C, M);
+    MVIN_LAUNCH((umma_gemm_test_kernel<64>), grid, 256, umma_gemm_test_smem<64>(), st, A, W, C, M);
   } else {
     return fail(MVIN_ERR_UNSUPPORTED, "tcgen05 path: dim must be 32 or 64, got %d", D);
   }
@@ -1381,10 +1410,10 @@ int mvin_test_umma_dw(const float* A, const float* G, float* dump, int64_t M, in
   int rc;
   if (D == 32) {
     if ((rc = set_smem(umma_dw_test_kernel<32>, umma_dw_test_smem<32>()))) return rc;
-    umma_dw_test_kernel<32><<<1, 256, umma_dw_test_smem<32>(), st>>>(A, G, dump, M, variant);
+    MVIN_LAUNCH((umma_dw_test_kernel<32>), 1, 256, umma_dw_test_smem<32>(), st, A, G, dump, M, variant);
   } else if (D == 64) {
     if ((rc = set_smem(umma_dw_test_kernel<64>, umma_dw_test_smem<64>()))) return rc;
-    umma_dw_test_kernel<64><<<1, 256, umma_dw_test_smem<64>(), st>>>(A, G, dump, M, variant);
+    MVIN_LAUNCH((umma_dw_test_kernel<64>), 1, 256, umma_dw_test_smem<64>(), st, A, G, dump, M, variant);
   } else {
     return fail(MVIN_ERR_UNSUPPORTED, "tcgen05 path: dim must be 32 or 64, got %d", D);
   }
@@ -1406,7 +1435,7 @@ int mvin_gather_feed(mvin_handle_t h, const int64_t* user_indices, int32_t B, in
   cudaStream_t st = (cudaStream_t)stream;
   const int P = h->cfg.p_hop > 0 ? h->cfg.p_hop : 1, m = h->cfg.n_memory;
   const long n = (long)P * B * m;
-  gather_feed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->uts, user_indices, B, P, m, mem_h, mem_r, mem_t);
+  MVIN_LAUNCH((gather_feed_kernel), (unsigned)((n + 255) / 256), 256, 0, st, h->uts, user_indices, B, P, m, mem_h, mem_r, mem_t);
   LAUNCH_CHECK(h, "gather_feed");
   return MVIN_OK;
 }
@@ -1457,7 +1486,7 @@ int mvin_sample_adjacency(const int64_t* indptr, const int32_t* nbr, const int32
                           int64_t* picked_edges, void* stream) {
   if (!indptr || !nbr || !rel || n_entity < 1 || K < 1 || K > MAX_K || (!adj_packed && !adj_entity))
     return fail(MVIN_ERR_INVALID, "bad argument (K must be in 1..%d)", MAX_K);
-  sample_adjacency_kernel<<<(unsigned)((n_entity + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+  MVIN_LAUNCH((sample_adjacency_kernel), (unsigned)((n_entity + 127) / 128), 128, 0, (cudaStream_t)stream, 
       indptr, nbr, rel, n_entity, K, (unsigned long long)seed, adj_packed, adj_entity, adj_relation, picked_edges);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(MVIN_ERR_CUDA, "launch sample_adjacency: %s", cudaGetErrorString(e));
@@ -1472,7 +1501,7 @@ int mvin_build_ripple_sets(const int64_t* indptr, const int32_t* nbr, const int3
   if (n_memory < 1 || n_memory > 64 || n_neighbor < 1 || n_neighbor > 16)
     return fail(MVIN_ERR_UNSUPPORTED, "device ripple sets: n_memory must be in 1..64 and n_neighbor in 1..16");
   const int P = p_hop > 0 ? p_hop : 1;
-  ripple_sets_kernel<<<(unsigned)((n_user + 63) / 64), 64, 0, (cudaStream_t)stream>>>(
+  MVIN_LAUNCH((ripple_sets_kernel), (unsigned)((n_user + 63) / 64), 64, 0, (cudaStream_t)stream, 
       indptr, nbr, rel, hist_ptr, hist_items, n_user, P, n_memory, n_neighbor, (unsigned long long)seed, user_triplet_set, slots);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(MVIN_ERR_CUDA, "launch ripple_sets: %s", cudaGetErrorString(e));
@@ -1498,7 +1527,7 @@ int mvin_topk_metrics(const float* scores, const uint8_t* relevant, const int32_
   if (sm > 200 * 1024) return fail(MVIN_ERR_UNSUPPORTED, "too many candidates per user (%d)", max_cand);
   int rc;
   if ((rc = set_smem(topk_metrics_kernel, sm))) return rc;
-  topk_metrics_kernel<<<n_users, 256, sm, (cudaStream_t)stream>>>(a);
+  MVIN_LAUNCH((topk_metrics_kernel), n_users, 256, sm, (cudaStream_t)stream, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(MVIN_ERR_CUDA, "launch topk_metrics: %s", cudaGetErrorString(e));
   return MVIN_OK;
@@ -1515,9 +1544,9 @@ int mvin_ctr_metrics(mvin_handle_t h, const float* scores_normalized, const floa
   int gy = (4 * h->sm_count + gx - 1) / gx;            // split the j range so that ~4 CTAs per SM exist
   if (gy > gx) gy = gx;
   if (gy < 1) gy = 1;
-  ctr_count_kernel<<<dim3(gx, gy), nt, 2 * nt * sizeof(float), st>>>(scores_normalized, labels, B, acc64);
+  MVIN_LAUNCH((ctr_count_kernel), dim3(gx, gy), nt, 2 * nt * sizeof(float), st, scores_normalized, labels, B, acc64);
   LAUNCH_CHECK(h, "ctr_count");
-  ctr_finalize_kernel<<<1, 32, 0, st>>>(acc64, B, out3);
+  MVIN_LAUNCH((ctr_finalize_kernel), 1, 32, 0, st, acc64, B, out3);
   LAUNCH_CHECK(h, "ctr_finalize");
   return MVIN_OK;
 }

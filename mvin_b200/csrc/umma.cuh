@@ -162,6 +162,7 @@ MVIN_DEV void issue_3xtf32(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32
 template <int D>
 __global__ void __launch_bounds__(256) umma_gemm_test_kernel(const float* __restrict__ A, const float* __restrict__ W,
                                                              float* __restrict__ C, long M) {
+  pdl_enter();
   using L = umma::OpLayout<D>;
   constexpr int LPR = D / 4;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -221,6 +222,7 @@ __global__ void __launch_bounds__(256) umma_gemm_test_kernel(const float* __rest
 template <int D>
 __global__ void __launch_bounds__(256) umma_dw_test_kernel(const float* __restrict__ A, const float* __restrict__ G,
                                                            float* __restrict__ dump, long M, int variant) {
+  pdl_enter();
   using L = umma::OpLayout<D>;
   using LT = umma::OpLayout<128>;                        // transposed copies: K = 128 rows of the tile
   constexpr int LPR = D / 4;

@@ -80,6 +80,7 @@ MVIN_DEV void build_q(const float* __restrict__ RK, const float* __restrict__ v_
 
 template <int D, int PB>
 __global__ void __launch_bounds__(USER_MAX_NT) user_fwd_kernel(UserArgs a) {
+  pdl_enter();
   constexpr int LPR = D / 4, G = 32 / LPR;
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32, g = lane / LPR, c = lane % LPR;
@@ -218,6 +219,7 @@ inline size_t ripple_bwd_smem(int m, int D) {
 
 template <int D>
 __global__ void __launch_bounds__(RIPPLE_NT) ripple_bwd_kernel(RippleBwdArgs a) {
+  pdl_enter();
   constexpr int LPR = D / 4, G = 32 / LPR;
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, g = lane / LPR, c = lane % LPR;
