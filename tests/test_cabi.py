@@ -57,6 +57,23 @@ def test_unsupported_config_is_refused_without_gpu(lib_path):
         assert lib.mvin_last_error()
 
 
+def test_header_is_plain_c_and_links_from_a_c_host(lib_path, tmp_path):
+    """include/mvin_b200.h compiles as C99 (-pedantic) and a C program linked against libmvin_b200.so gets the ABI
+    version and a loud refusal for an unsupported configuration -- the boundary does not need Python."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    exe = str(tmp_path / "cabi_host")
+    libdir = os.path.dirname(lib_path)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cabi_host.c"), "-o", exe, "-L", libdir, "-lmvin_b200",
+                    "-Wl,-rpath," + libdir], check=True, capture_output=True, text=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "refused:" in out.stdout
+
+
 def test_product_has_no_oracle_import():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "mvin_b200")):
         for f in files:
