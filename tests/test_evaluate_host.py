@@ -101,3 +101,53 @@ def test_ctr_eval_walks_full_batches_only():
         assert abs(auc - np.mean(auc_l)) < 1e-9 and f1 == 16.0
     out = E.ctr_eval(None, None, None, StubModel(uts, True), data[:5], uts, 16)
     assert out[0] == [] and np.isnan(out[3])
+
+
+def test_train_epoch_walks_full_batches_in_permuted_order():
+    from mvin_b200 import loop
+
+    class LoopStub(StubModel):
+        n_shards = 1
+
+        def __init__(self, uts):
+            super().__init__(uts, True)
+            self.seen, self.adam = [], 0
+
+        def forward_device(self, users, items, mem_h, mem_r, mem_t, scores=None, scores_normalized=None):
+            assert users.is_contiguous() and items.is_contiguous() and users.dtype == torch.int64
+            assert np.array_equal(mem_r.numpy(), self.uts_np[users.numpy()][:, :, 1].transpose(1, 0, 2))
+            self.cur = (users.clone(), items.clone())
+
+        def backward_device(self, labels, losses):
+            assert labels.dtype == torch.float32 and labels.is_contiguous() and losses.shape == (4,)
+            self.seen.append(torch.stack([self.cur[0], self.cur[1], labels.long()], dim=1))
+            losses.fill_(float(len(self.seen)))
+
+        def adam_step_device(self):
+            self.adam += 1
+
+    uts = make_uts()
+    rng = np.random.RandomState(3)
+    data = np.stack([rng.randint(0, 12, 53), rng.randint(0, 23, 53), rng.randint(0, 2, 53)], axis=1)
+    model = LoopStub(uts)
+    d = loop.upload_interactions(model, data)
+    out = loop.train_epoch(model, d, 16, shuffle=False)
+    assert out.shape == (3, 4) and out[:, 0].tolist() == [1.0, 2.0, 3.0] and model.adam == 3
+    assert np.array_equal(torch.cat(model.seen).numpy(), data[:48])               # in order, 5-row tail skipped
+    model = LoopStub(uts)
+    g = torch.Generator().manual_seed(5)
+    loop.train_epoch(model, d, 16, shuffle=True, generator=g, apply_adam=False)
+    got = torch.cat(model.seen).numpy()
+    assert model.adam == 0 and got.shape == (48, 3) and not np.array_equal(got, data[:48])
+    rows = {tuple(r) for r in data.tolist()}
+    assert all(tuple(r) in rows for r in got.tolist())
+    want = data[torch.randperm(53, generator=torch.Generator().manual_seed(5)).numpy()][:48]
+    assert np.array_equal(got, want)
+    assert loop.train_epoch(LoopStub(uts), d[:7], 16).shape == (0, 4)
+    unbound = StubModel(uts, False)
+    unbound.n_shards = 1
+    try:
+        loop.train_epoch(unbound, d, 16)
+        raise AssertionError("expected RuntimeError")
+    except RuntimeError:
+        pass
