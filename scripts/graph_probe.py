@@ -1,6 +1,8 @@
 """Experiment: replay one fwd+bwd step of the device-resident path from a CUDA graph (torch.cuda.CUDAGraph capture of
 the library's launches, side streams included) and compare with eager launches."""
-import sys, time
+import os, sys, time
+# measured before programmatic dependent launch was introduced; capturing PDL launches has not been exercised on the GPU
+os.environ.setdefault("MVIN_B200_PDL", "0")
 import numpy as np, torch
 sys.path.insert(0, ".")
 import bench
