@@ -69,10 +69,13 @@ def score_candidates(model, users: Sequence[int], candidates: List[Sequence[int]
     d_users = torch.from_numpy(np.repeat(np.asarray(users, dtype=np.int64), n_cand)).to(dev)
     d_items = torch.from_numpy(item_mat.ravel()[flat_pos]).to(dev)
     flat_scores = torch.zeros(d_users.shape[0], dtype=torch.float32, device=dev)
+    aligned = lambda t: t if t.data_ptr() % 16 == 0 else t.clone()    # the C ABI asks for 16-byte aligned pointers
+    out = torch.empty(batch_size, dtype=torch.float32, device=dev)
     for s in range(0, d_users.shape[0], batch_size):
-        u, it = d_users[s:s + batch_size], d_items[s:s + batch_size]
+        u, it = aligned(d_users[s:s + batch_size]), aligned(d_items[s:s + batch_size])
         mh, mr, mt = _memories(model, u, user_triplet_set)
-        model.forward_device(u, it, mh, mr, mt, None, flat_scores[s:s + batch_size])
+        model.forward_device(u, it, mh, mr, mt, None, out[:u.shape[0]])
+        flat_scores[s:s + u.shape[0]] = out[:u.shape[0]]
     scores = torch.zeros(n_users * max_cand, dtype=torch.float32, device=dev)
     scores[torch.from_numpy(flat_pos).to(dev)] = flat_scores
     return scores.view(n_users, max_cand), item_mat, n_cand

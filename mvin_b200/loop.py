@@ -34,12 +34,13 @@ def train_epoch(model, d_data, batch_size=None, shuffle=True, generator=None, ap
         d_data = d_data[perm]
     cols = d_data[:n_steps * B].t().contiguous()                       # [3, n_steps * B]: each batch slice contiguous
     labels = cols[2].to(torch.float32)
+    aligned = lambda t: t if t.data_ptr() % 16 == 0 else t.clone()    # the C ABI asks for 16-byte aligned pointers
     for s in range(n_steps):
         lo, hi = s * B, (s + 1) * B
-        users, items = cols[0, lo:hi], cols[1, lo:hi]
+        users, items, lab = aligned(cols[0, lo:hi]), aligned(cols[1, lo:hi]), aligned(labels[lo:hi])
         mem_h, mem_r, mem_t = model.gather_feed(users)
         model.forward_device(users, items, mem_h, mem_r, mem_t)
-        model.backward_device(labels[lo:hi], losses[s])
+        model.backward_device(lab, losses[s])
         if apply_adam:
             model.adam_step_device()
     return losses
