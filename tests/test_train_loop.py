@@ -47,3 +47,25 @@ def test_train_epoch_matches_per_step_train_users():
     g = torch.Generator(device=b.device).manual_seed(3)
     shuffled = loop.train_epoch(b, loop.upload_interactions(b, data), B, shuffle=True, generator=g).cpu().numpy()
     assert shuffled.shape == (3, 4) and np.isfinite(shuffled).all() and b.step == 6
+
+
+def test_stws_tables_save_and_restore(tmp_path):
+    """save_pretrain_emb_fuc / load_pretrain_emb (model.py:66-67, train.py:43-54): the four STWS tables written by one
+    model are what a model constructed with args.load_pretrain_emb starts from; the other parameters are not touched."""
+    import types
+    from mvin_b200 import MVIN
+    args = make_args(dim=16, neighbor_sample_size=4, h_hop=1, p_hop=1, n_memory=8, batch_size=8)
+    args.path = types.SimpleNamespace(emb=str(tmp_path / "emb" / "run"))
+    prob = make_problem(args, seed=2)
+    a = MVIN(args, prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"], prob["adj_relation"])
+    a.load_named_parameters({k: v.numpy() for k, v in prob["P"].items()})
+    a.save_pretrain_emb_fuc(None, None)
+    args_b = types.SimpleNamespace(**{**vars(args), "load_pretrain_emb": True})
+    b = MVIN(args_b, prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"], prob["adj_relation"],
+             seed=7)
+    c = MVIN(args, prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"], prob["adj_relation"],
+             seed=7)
+    for k in ("user_emb", "entity_emb", "relation_emb", "relation_kge"):
+        assert torch.equal(a.params[k], b.params[k]), k
+        assert not torch.equal(a.params[k], c.params[k]), k               # seed-7 init differs from the saved tables
+    assert torch.equal(b.params["mix_w"], c.params["mix_w"])               # dense weights keep their own init
