@@ -205,7 +205,7 @@ class _NN:
 
     @staticmethod
     def softmax(x, dim=-1):
-        return Node(lambda a: torch.softmax(a, dim=-1), [x])
+        return Node(lambda a: torch.softmax(a, dim=dim), [x])
 
     @staticmethod
     def dropout(x, keep_prob=1.0):
