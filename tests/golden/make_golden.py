@@ -2,7 +2,7 @@
 
 Run in the build container only (it needs /root/reference, which does not exist on the GPU box):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [--out DIR] [case ...]
 
 It imports ``/root/reference/src/model/MVIN/model.py`` (and its ``aggregators.py``) with
 ``tests/golden/tf1_shim.py`` registered as ``tensorflow``, overwrites the model's variables with seeded values,
@@ -86,7 +86,7 @@ def oracle_name_to_var(model, args):
     return mp
 
 
-def run_case(name, over, regime, MVIN):
+def run_case(name, over, regime, MVIN, out_dir=HERE):
     args = make_args(over)
     B, K, m = args.batch_size, args.neighbor_sample_size, args.n_memory
     rng = np.random.RandomState(sum(ord(c) for c in name))       # deterministic across interpreter runs
@@ -161,18 +161,25 @@ def run_case(name, over, regime, MVIN):
         save[f"mem_h_{i}"], save[f"mem_r_{i}"], save[f"mem_t_{i}"] = mem_h[i], mem_r[i], mem_t[i]
     for k in P:
         save["param__" + k] = P[k].numpy()
-    np.savez_compressed(os.path.join(HERE, name + ".npz"), **save)
+    np.savez_compressed(os.path.join(out_dir, name + ".npz"), **save)
     print(f"{name:28s} loss={float(out['loss']):.6f} scores[:3]={out['scores'][:3]}")
 
 
-def main():
+def main(argv=None):
+    """python tests/golden/make_golden.py [--out DIR] [case ...]   (default: every case, into tests/golden/)"""
+    argv = list(sys.argv[1:] if argv is None else argv)
+    out_dir = HERE
+    if argv[:1] == ["--out"]:
+        out_dir, argv = argv[1], argv[2:]
+    names = argv or list(CASES)
     tf1_shim.install()
     sys.path.insert(0, REF)
     import importlib
     model_mod = importlib.import_module("model")                 # the reference's model.py, unmodified
     assert os.path.realpath(model_mod.__file__).startswith("/root/reference/"), model_mod.__file__
-    for name, (over, regime) in CASES.items():
-        run_case(name, over, regime, model_mod.MVIN)
+    for name in names:
+        over, regime = CASES[name]
+        run_case(name, over, regime, model_mod.MVIN, out_dir)
 
 
 if __name__ == "__main__":

@@ -1,4 +1,6 @@
 """Pin the oracle against the reference's own model.py run under the TF1 shim (tests/golden/make_golden.py)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -57,3 +59,23 @@ def test_eval_metrics_match_reference():
     pred = (s >= 0.5).astype(np.float32)
     assert np.allclose([auc, np.mean(pred == feed["labels"]), f1_score(feed["labels"], pred)],
                        z["eval_auc_acc_f1"], atol=1e-6)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/model/MVIN"),
+                    reason="the reference checkout exists in the build container only")
+def test_goldens_regenerate_bit_for_bit_from_the_reference(tmp_path):
+    """Live pin: run the reference's unmodified model.py under the TF1 shim again (tests/golden/make_golden.py, in a
+    subprocess so that the fake `tensorflow` module stays out of this process) and compare with the committed
+    fixtures array by array -- the fixtures are what the reference code computes, not something edited by hand."""
+    import subprocess
+    import sys
+    cases = ["h2_m1_p2", "h3_m1_p1", "h2_m2_p2"]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, os.path.join(root, "tests", "golden", "make_golden.py"), "--out", str(tmp_path)] + cases,
+                   check=True, capture_output=True, text=True, cwd=root)
+    for name in cases:
+        new = np.load(os.path.join(str(tmp_path), name + ".npz"), allow_pickle=True)
+        old = np.load(os.path.join(root, "tests", "golden", name + ".npz"), allow_pickle=True)
+        assert sorted(new.files) == sorted(old.files), name
+        for k in old.files:
+            assert np.array_equal(new[k], old[k]), (name, k)
