@@ -6,7 +6,7 @@
 namespace mvin {
 
 // ---- adjacency packing: int64 [n_entity, K] x 2 (model.py:7,19-20) -> int32 [n_entity][2][K] -----------
-__global__ void pack_adj_kernel(const int64_t* __restrict__ adjE, const int64_t* __restrict__ adjR, long n_entity,
+static __global__ void pack_adj_kernel(const int64_t* __restrict__ adjE, const int64_t* __restrict__ adjR, long n_entity,
                                 int K, int32_t* __restrict__ out) {
   pdl_enter();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -19,7 +19,7 @@ __global__ void pack_adj_kernel(const int64_t* __restrict__ adjE, const int64_t*
 
 // ---- get_neighbors (model.py:243-256): one level of expansion, child k of node j at j*K+k -------------
 // `stamp` (optional): mark the produced ids (entity mode of the leaf level, level.cuh)
-__global__ void expand_kernel(const int32_t* __restrict__ ent, const int32_t* __restrict__ adj, long rows, int K,
+static __global__ void expand_kernel(const int32_t* __restrict__ ent, const int32_t* __restrict__ adj, long rows, int K,
                               int32_t* __restrict__ out, int32_t* __restrict__ stamp) {
   pdl_enter();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -31,7 +31,7 @@ __global__ void expand_kernel(const int32_t* __restrict__ ent, const int32_t* __
   if (stamp) stamp[id] = 1;
 }
 
-__global__ void expand_i64_kernel(const int64_t* __restrict__ ent, const int32_t* __restrict__ adj, long rows,
+static __global__ void expand_i64_kernel(const int64_t* __restrict__ ent, const int32_t* __restrict__ adj, long rows,
                                   int K, int64_t* __restrict__ out_e, int64_t* __restrict__ out_r) {
   pdl_enter();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -43,14 +43,14 @@ __global__ void expand_i64_kernel(const int64_t* __restrict__ ent, const int32_t
   out_r[i] = (int64_t)__ldg(rec + K + k);
 }
 
-__global__ void copy_i64_kernel(const int64_t* __restrict__ src, long n, int64_t* __restrict__ dst) {
+static __global__ void copy_i64_kernel(const int64_t* __restrict__ src, long n, int64_t* __restrict__ dst) {
   pdl_enter();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i];
 }
 
 // ---- seeds: ent[0] = item as int32 (model.py:243-256 starts from item_indices); optional stamps -------------
-__global__ void seed_kernel(const int64_t* __restrict__ item, int B, int32_t* __restrict__ ent0,
+static __global__ void seed_kernel(const int64_t* __restrict__ item, int B, int32_t* __restrict__ ent0,
                             int32_t* __restrict__ stamp) {
   pdl_enter();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -62,7 +62,7 @@ __global__ void seed_kernel(const int64_t* __restrict__ item, int B, int32_t* __
 
 // ---- feed assembly on the device (train.py:112-122, util.py:208-218): the ripple memories of a batch gathered from
 // the packed per-user sets  uts int32 [n_user, P, 3, m]  (data_loader_user_set.py:402)  into  mem_x int32 [P, B, m]
-__global__ void gather_feed_kernel(const int32_t* __restrict__ uts, const int64_t* __restrict__ user, int B, int P, int m,
+static __global__ void gather_feed_kernel(const int32_t* __restrict__ uts, const int64_t* __restrict__ user, int B, int P, int m,
                                    int32_t* __restrict__ mem_h, int32_t* __restrict__ mem_r, int32_t* __restrict__ mem_t) {
   pdl_enter();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;        // over [P][B][m]
@@ -105,7 +105,7 @@ __global__ void scatter_rows_kernel(const float* __restrict__ rows, const int32_
 }
 
 // ---- relation scores s[i][r] = Rel[r] . urh_weights_i[D:2D]  (aggregators.py:130-133, relation third) --
-__global__ void rel_scores_kernel(const float* __restrict__ Rel, const float* __restrict__ urh, int n_rel, int D,
+static __global__ void rel_scores_kernel(const float* __restrict__ Rel, const float* __restrict__ urh, int n_rel, int D,
                                   int H, float* __restrict__ s) {
   pdl_enter();
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
@@ -118,7 +118,7 @@ __global__ void rel_scores_kernel(const float* __restrict__ Rel, const float* __
 }
 
 // dRel[r] += sum_i ds[i][r] w_i ;  durh_i[D:2D] += sum_r ds[i][r] Rel[r]     (one CTA per aggregator i)
-__global__ void rel_scores_bwd_kernel(const float* __restrict__ Rel, const float* __restrict__ urh,
+static __global__ void rel_scores_bwd_kernel(const float* __restrict__ Rel, const float* __restrict__ urh,
                                       const float* __restrict__ ds, int n_rel, int D, float* __restrict__ dRel,
                                       float* __restrict__ durh) {
   pdl_enter();
@@ -305,7 +305,7 @@ struct L2Segments {
   int count;
 };
 
-__global__ void l2_dense_kernel(L2Segments sg, float* __restrict__ acc /* [1]=l2, [2]=l2_agg */) {
+static __global__ void l2_dense_kernel(L2Segments sg, float* __restrict__ acc /* [1]=l2, [2]=l2_agg */) {
   pdl_enter();
   __shared__ float red[2];
   if (threadIdx.x < 2) red[threadIdx.x] = 0.f;
@@ -330,7 +330,7 @@ __global__ void l2_dense_kernel(L2Segments sg, float* __restrict__ acc /* [1]=l2
 }
 
 // ---- un-normalised L2 over the gathered relation-KGE matrices (model.py:386): sum_r cnt[r] |RK[r]|^2 -----
-__global__ void hist_r_kernel(const int32_t* __restrict__ mem_r, long n, int n_rel, float* __restrict__ cnt) {
+static __global__ void hist_r_kernel(const int32_t* __restrict__ mem_r, long n, int n_rel, float* __restrict__ cnt) {
   pdl_enter();
   extern __shared__ float h[];
   for (int i = threadIdx.x; i < n_rel; i += blockDim.x) h[i] = 0.f;
@@ -342,7 +342,7 @@ __global__ void hist_r_kernel(const int32_t* __restrict__ mem_r, long n, int n_r
     if (h[i] != 0.f) atomicAdd(cnt + i, h[i]);
 }
 
-__global__ void rk_l2_kernel(const float* __restrict__ RK, const float* __restrict__ cnt, int DD, float two_l2,
+static __global__ void rk_l2_kernel(const float* __restrict__ RK, const float* __restrict__ cnt, int DD, float two_l2,
                              float* __restrict__ dRK, float* __restrict__ l2_acc) {
   pdl_enter();
   const int r = blockIdx.x;
@@ -358,7 +358,7 @@ __global__ void rk_l2_kernel(const float* __restrict__ RK, const float* __restri
 }
 
 // losses_out = {loss, base_loss, l2_loss, l2_agg_loss}  (model.py:412)
-__global__ void finalize_loss_kernel(const float* __restrict__ acc, float l2w, float l2a, float* __restrict__ out) {
+static __global__ void finalize_loss_kernel(const float* __restrict__ acc, float l2w, float l2a, float* __restrict__ out) {
   pdl_enter();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     out[0] = acc[0] + l2w * acc[1] + l2a * acc[2];
@@ -369,7 +369,7 @@ __global__ void finalize_loss_kernel(const float* __restrict__ acc, float l2w, f
 }
 
 // ---- transposed copies of the d x d weights: dst[i] = W_a[i]^T (i < H), dst[H + e] = W_t[e]^T (e <= H) ------
-__global__ void transpose_kernel(const float* __restrict__ agg_w, const float* __restrict__ transfer_w, int H, int D,
+static __global__ void transpose_kernel(const float* __restrict__ agg_w, const float* __restrict__ transfer_w, int H, int D,
                                  float* __restrict__ dst) {
   pdl_enter();
   const int b = blockIdx.x;
@@ -382,7 +382,7 @@ __global__ void transpose_kernel(const float* __restrict__ agg_w, const float* _
 }
 
 // ---- importance_list (model.py:319-323): p = softmax_k(s_0[rel_k]) for the nodes of one level ------------
-__global__ void importance_kernel(const int32_t* __restrict__ ent, const int32_t* __restrict__ adj,
+static __global__ void importance_kernel(const int32_t* __restrict__ ent, const int32_t* __restrict__ adj,
                                   const float* __restrict__ s, long rows, int K, float* __restrict__ probs) {
   pdl_enter();
   const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) / 32;
@@ -417,7 +417,7 @@ MVIN_DEV long rand_below(unsigned long long seed, long entity, int draw, long n)
   const unsigned long long h = mix64(mix64(seed ^ (unsigned long long)entity * 0xd1342543de82ef95ull) + (unsigned long long)draw);
   return (long)__umul64hi(h, (unsigned long long)n);
 }
-__global__ void sample_adjacency_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ nbr,
+static __global__ void sample_adjacency_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ nbr,
                                         const int32_t* __restrict__ rel, int n_entity, int K, unsigned long long seed,
                                         int32_t* __restrict__ adj_packed, int64_t* __restrict__ adj_entity,
                                         int64_t* __restrict__ adj_relation, int64_t* __restrict__ picked_edges) {
@@ -473,7 +473,7 @@ MVIN_DEV long subset_element(unsigned long long key, long deg, int take, int q) 
   }
   return pick[q];
 }
-__global__ void ripple_sets_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ nbr,
+static __global__ void ripple_sets_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ nbr,
                                    const int32_t* __restrict__ rel, const int64_t* __restrict__ hist_ptr,
                                    const int32_t* __restrict__ hist_items, int n_user, int P, int m, int n_neighbor,
                                    unsigned long long seed, int32_t* __restrict__ uts /* [n_user, P, 3, m] */,
@@ -540,7 +540,7 @@ __global__ void ripple_sets_kernel(const int64_t* __restrict__ indptr, const int
 // AUC = (#{(i in pos, j in neg): s_i > s_j} + 0.5 #{s_i == s_j}) / (P N): the Mann-Whitney form of the trapezoidal ROC
 // area, ties included, as exact integer pair counts (B <= 65536: P N < 2^32 pairs, counted in 64 bits).
 // acc / f1 use the reference's threshold (score >= 0.5 -> 1).  out = {auc, acc, f1}; acc64 = 5 zeroed counters.
-__global__ void ctr_count_kernel(const float* __restrict__ scores, const float* __restrict__ labels, int B,
+static __global__ void ctr_count_kernel(const float* __restrict__ scores, const float* __restrict__ labels, int B,
                                  unsigned long long* __restrict__ acc64 /* [0] 2*gt + eq, [1] P, [2] tp, [3] fp, [4] fn */) {
   pdl_enter();
   extern __shared__ float sj[];                       // tile of scores / labels of the "j" side
@@ -579,7 +579,7 @@ __global__ void ctr_count_kernel(const float* __restrict__ scores, const float* 
     if (threadIdx.x % 32 == 0 && v[k]) atomicAdd(acc64 + k, v[k]);
   }
 }
-__global__ void ctr_finalize_kernel(const unsigned long long* __restrict__ acc64, int B, float* __restrict__ out) {
+static __global__ void ctr_finalize_kernel(const unsigned long long* __restrict__ acc64, int B, float* __restrict__ out) {
   pdl_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double P = (double)acc64[1], N = (double)B - P;
@@ -608,7 +608,7 @@ struct TopkArgs {
   float* recall;
   float* ndcg;
 };
-__global__ void __launch_bounds__(256) topk_metrics_kernel(TopkArgs a) {
+static __global__ void __launch_bounds__(256) topk_metrics_kernel(TopkArgs a) {
   pdl_enter();
   extern __shared__ float sc[];                          // [max_cand] scores, then hit flags by rank
   unsigned char* hit = reinterpret_cast<unsigned char*>(sc + a.max_cand);   // [k_last]
@@ -647,30 +647,55 @@ __global__ void __launch_bounds__(256) topk_metrics_kernel(TopkArgs a) {
   }
 }
 
-// ---- Adam, TF1 semantics (model.py:414): dense over every segment ---------------------------------------
+// ---- Adam, TF1 semantics (model.py:414): dense over every segment, ONE pass --------------------------------
+// The segments are laid end to end in units of float4 (vec_end[] = running count of 16-byte chunks, the last chunk of
+// a segment may be partial); a grid-stride loop over that flat chunk index finds its segment with a short scan of
+// the prefix, so small and large segments share one sweep: 16 B read x 4 streams, 16 B written x 3 per chunk, every
+// access a full 16-byte vector (segment bases are 16-byte aligned: separate allocations or multiples of d*d floats).
 struct AdamSegments {
   float* param[MAX_SEG];
   const float* grad[MAX_SEG];
   float* m[MAX_SEG];
   float* v[MAX_SEG];
   long n[MAX_SEG];
+  long vec_end[MAX_SEG];   // cumulative ceil(n / 4)
   int count;
 };
 
-__global__ void adam_kernel(AdamSegments sg, float lr_t, float beta1, float beta2, float eps) {
+MVIN_DEV float adam_one(float& m, float& v, float g, float p, float lr_t, float beta1, float beta2, float eps) {
+  m = beta1 * m + (1.f - beta1) * g;
+  v = beta2 * v + (1.f - beta2) * g * g;
+  return p - lr_t * m / (sqrtf(v) + eps);
+}
+
+static __global__ void __launch_bounds__(256) adam_kernel(AdamSegments sg, float lr_t, float beta1, float beta2, float eps) {
   pdl_enter();
-  for (int sidx = 0; sidx < sg.count; ++sidx) {
-    float* p = sg.param[sidx];
-    const float* g = sg.grad[sidx];
-    float* m = sg.m[sidx];
-    float* v = sg.v[sidx];
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < sg.n[sidx]; i += (long)gridDim.x * blockDim.x) {
-      const float gi = g[i];
-      const float mi = beta1 * m[i] + (1.f - beta1) * gi;
-      const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
-      m[i] = mi;
-      v[i] = vi;
-      p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  const long total = sg.vec_end[sg.count - 1];
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int s = 0;
+    while (i >= sg.vec_end[s]) ++s;
+    const long e = (i - (s ? sg.vec_end[s - 1] : 0)) * 4;
+    float* p = sg.param[s] + e;
+    const float* g = sg.grad[s] + e;
+    float* m = sg.m[s] + e;
+    float* v = sg.v[s] + e;
+    if (e + 4 <= sg.n[s]) {
+      const float4 g4 = __ldcs(reinterpret_cast<const float4*>(g));
+      float4 m4 = ld4(m), v4 = ld4(v), p4 = ld4(p);
+      p4.x = adam_one(m4.x, v4.x, g4.x, p4.x, lr_t, beta1, beta2, eps);
+      p4.y = adam_one(m4.y, v4.y, g4.y, p4.y, lr_t, beta1, beta2, eps);
+      p4.z = adam_one(m4.z, v4.z, g4.z, p4.z, lr_t, beta1, beta2, eps);
+      p4.w = adam_one(m4.w, v4.w, g4.w, p4.w, lr_t, beta1, beta2, eps);
+      st4(m, m4);
+      st4(v, v4);
+      st4(p, p4);
+    } else {
+      for (long j = 0; e + j < sg.n[s]; ++j) {
+        float mj = m[j], vj = v[j];
+        p[j] = adam_one(mj, vj, g[j], p[j], lr_t, beta1, beta2, eps);
+        m[j] = mj;
+        v[j] = vj;
+      }
     }
   }
 }

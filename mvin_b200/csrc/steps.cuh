@@ -1,0 +1,545 @@
+// steps.cuh -- one forward / backward step of the MVIN hot path as a sequence of kernel launches, templated on the
+// embedding dimension.  Forward = model.py:125-159 of the reference (src/model/MVIN/), backward = TF autodiff of
+// model.py:378-412.  The factorisation the kernels implement is spelled out in DESIGN.md section 3 and has a CPU twin
+// in tests/fused_model.py.  Instantiated once per dimension by mvin_steps.cu (-DMVIN_DIM=...), so the five
+// instantiations compile in parallel.
+#pragma once
+#include "host.cuh"
+
+namespace mvin_host {
+
+template <int D>
+int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, const int32_t* mem_r,
+                 const int32_t* mem_t, int B, float* scores, float* scores_norm, void* ws, cudaStream_t st) {
+  using C = TC<D>;
+  const mvin_config_t& c = h->cfg;
+  const int K = c.neighbor_sample_size, H = c.h_hop, p = c.p_hop, m = c.n_memory, nr = c.n_relation;
+  const Layout L = make_layout(c, B, use_entity_leaf(c, B, h->n_shards, h->entity_leaf_mode));
+  const mvin_params_t& P = h->P;
+  int rc;
+  prof_mark(h, st, nullptr);
+
+  // side stream: integer expansion (model.py:243-256; level L ids are never materialised), relation scores and the
+  // per-entity leaf aggregate are independent of the user side that runs on the launch stream meanwhile
+  const Par par{h, st, h->use_streams && !h->prof_on};
+  int32_t* stamp = L.entity_leaf ? at<int32_t>(ws, L.stamp) : nullptr;
+  if (par.on && h->pre_fork && h->in_host_step) {
+    CUDA_TRY(cudaStreamWaitEvent(h->side[0], h->ev_item, 0));   // only the item ids are needed on this branch
+    h->pre_fork = false;
+  } else {
+    par.fork(0);
+  }
+  {
+    cudaStream_t st = par.s(0);
+    if (stamp) CUDA_TRY(cudaMemsetAsync(stamp, 0, sizeof(int32_t) * (size_t)c.n_entity, st));
+    MVIN_LAUNCH((seed_kernel), (unsigned)((B + 255) / 256), 256, 0, st, item, B, at<int32_t>(ws, L.ent[0]), H == 1 ? stamp : nullptr);
+    LAUNCH_CHECK(h, "seed");
+    for (int lv = 0; lv + 1 < H; ++lv) {
+      const long n = L.rows[lv] * K;
+      MVIN_LAUNCH((expand_kernel), (unsigned)((n + 255) / 256), 256, 0, st, at<int32_t>(ws, L.ent[lv]), h->adj, L.rows[lv], K,
+                                                                 at<int32_t>(ws, L.ent[lv + 1]),
+                                                                 lv + 1 == H - 1 ? stamp : nullptr);
+      LAUNCH_CHECK(h, "expand");
+    }
+    // relation scores of every aggregator
+    {
+      const int warps = H * nr;
+      MVIN_LAUNCH((rel_scores_kernel), (warps * 32 + 255) / 256, 256, 0, st, P.relation_emb, P.agg_urh_w, nr, D, H,
+                                                                 at<float>(ws, L.s));
+      LAUNCH_CHECK(h, "rel_scores");
+    }
+    // entity mode: S_e for every distinct depth-(L-1) entity of the batch
+    if (L.entity_leaf) {
+      LeafEntArgs a;
+      memset(&a, 0, sizeof(a));
+      a.stamp = stamp; a.adj = h->adj; a.s = at<float>(ws, L.s); a.E = h->etab; a.Se = at<float>(ws, L.Se);
+      a.n_entity = c.n_entity; a.K = K; a.n_rel = nr;
+      const size_t sm = leaf_entity_smem(nr);
+      if ((rc = set_smem(leaf_entity_kernel<D, false>, sm))) return rc;
+      const long want = ((long)c.n_entity + LEAF_NW * 32 - 1) / (LEAF_NW * 32);
+      const long cap = (long)h->sm_count * 8;
+      MVIN_LAUNCH((leaf_entity_kernel<D, false>), (unsigned)(want < cap ? want : cap), LEAF_NT, sm, st, a);
+      LAUNCH_CHECK(h, "leaf_entity_fwd");
+    }
+  }
+  // the user side in one launch: seeds v = E[item], Q = RK^T v, ripple attention, user MLP -> user_o
+  // (model.py:125-134, :161-240).  With a large relation-KGE table Q comes from a batched GEMM instead.
+  const bool q_fused = user_q_fused(D, nr);
+  if (!q_fused && p > 0) {
+    const long n = (long)B * C::LPR;
+    MVIN_LAUNCH((prep_items_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, item, h->etab, B, nullptr,
+                                                                      at<float>(ws, L.Vbuf), nullptr);
+    LAUNCH_CHECK(h, "prep_items");
+  }
+  // Q[b, r, :] = RK[r]^T v_b      (model.py:211-220 refactored)
+  if (!q_fused && p > 0) {
+    GemmArgs g = gemm_args();
+    g.A = at<float>(ws, L.Vbuf); g.sa_m = D; g.sa_k = 1; g.bsA = 0;
+    g.B = P.relation_kge; g.sb_k = D; g.sb_n = 1; g.bsB = (long)D * D;
+    g.C = at<float>(ws, L.Q); g.ldc = (long)nr * D; g.bsC = D;
+    g.M = B; g.N = D; g.K = D; g.nbatch = nr;
+    if ((rc = run_gemm(h, st, g, "gemm_q"))) return rc;
+  }
+  {
+    UserArgs a;
+    memset(&a, 0, sizeof(a));
+    a.E = h->etab; a.item = item; a.RK = P.relation_kge; a.w_hi = P.h_item_w;
+    a.W_user = P.user_mlp_w; a.b_user = P.user_mlp_b;
+    a.mem_h = mem_h; a.mem_r = mem_r; a.mem_t = mem_t;
+    a.Vbuf = at<float>(ws, L.Vbuf); a.Q = at<float>(ws, L.Q); a.probs = at<float>(ws, L.probs);
+    a.O = at<float>(ws, L.O); a.u = at<float>(ws, L.u);
+    a.B = B; a.m = m; a.p = p; a.n_rel = nr; a.q_ready = q_fused ? 0 : 1;
+    const int PB = user_pairs_per_cta(D, nr, p, m, h->user_pb_fwd);
+    const size_t sm = user_fwd_smem(D, PB, nr, p, m);
+    const int nt = 32 * user_warps(PB, p);
+    const unsigned grid = (unsigned)((B + PB - 1) / PB);
+    switch (PB) {
+      case 4:
+        if ((rc = set_smem(user_fwd_kernel<D, 4>, sm))) return rc;
+        MVIN_LAUNCH((user_fwd_kernel<D, 4>), grid, nt, sm, st, a);
+        break;
+      case 2:
+        if ((rc = set_smem(user_fwd_kernel<D, 2>, sm))) return rc;
+        MVIN_LAUNCH((user_fwd_kernel<D, 2>), grid, nt, sm, st, a);
+        break;
+      default:
+        if ((rc = set_smem(user_fwd_kernel<D, 1>, sm))) return rc;
+        MVIN_LAUNCH((user_fwd_kernel<D, 1>), grid, nt, sm, st, a);
+    }
+    LAUNCH_CHECK(h, "user_fwd");
+  }
+  par.join(0);
+  // user-oriented transform of levels 0..L-1, one launch   (model.py:270-283)
+  {
+    const size_t sm = transform_fwd_smem<D>();
+    if ((rc = set_smem(transform_fwd_kernel<D>, sm))) return rc;
+    TransformArgs a;
+    memset(&a, 0, sizeof(a));
+    long rows[MAX_LV];
+    for (int lv = 0; lv < H; ++lv) {
+      TransformLevel& t = a.lv[lv];
+      t.ent = at<int32_t>(ws, L.ent[lv]);
+      t.W = P.transfer_w + (long)lv * D * D; t.b = P.transfer_b + (long)lv * D;
+      t.T = at<float>(ws, L.V[0][lv]);
+      t.rows = rows[lv] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
+        t.stream = stream_level(h, L.rows[lv], D);
+    }
+    a.nlev = H; a.E = h->etab; a.u = at<float>(ws, L.u);
+    bool done = false;
+    if constexpr (D == 32 || D == 64) {
+      if (use_tc_path(h, L.rows[H - 1])) {
+        const size_t smt = transform_fwd_tc_smem<D>();
+        if ((rc = set_smem(transform_fwd_tc_kernel<D>, smt))) return rc;
+        const int grid = partition_grid(rows, H, TT<D>::R,
+                                        h->sm_count * resident_ctas(h, transform_fwd_tc_kernel<D>, TT<D>::NT, smt), a.cta_end);
+        MVIN_LAUNCH((transform_fwd_tc_kernel<D>), grid, TT<D>::NT, smt, st, a);
+        done = true;
+      }
+    }
+    if (!done) {
+      const int grid = partition_grid(rows, H, C::R, h->sm_count * resident_ctas(h, transform_fwd_kernel<D>, C::NT, sm), a.cta_end);
+      MVIN_LAUNCH((transform_fwd_kernel<D>), grid, C::NT, sm, st, a);
+    }
+    LAUNCH_CHECK(h, "transform_fwd");
+  }
+  // aggregation iterations (model.py:286-307): one launch per iteration, every level of it
+  {
+    const size_t sm_leaf = agg_fwd_smem<D, true>(K, nr), sm_in = agg_fwd_smem<D, false>(K, nr);
+    if ((rc = set_smem(agg_fwd_kernel<D, true>, sm_leaf))) return rc;
+    if ((rc = set_smem(agg_fwd_kernel<D, false>, sm_in))) return rc;
+    static const char* names[MAX_L] = {"agg_fwd_0", "agg_fwd_1", "agg_fwd_2"};
+    for (int i = 0; i < H; ++i) {
+      AggArgs a;
+      memset(&a, 0, sizeof(a));
+      long rows[MAX_LV];
+      const int nlev = H - i;
+      // tile order: the levels with the most expensive tiles first (the per-entity leaf mode has the cheapest)
+      const bool leaf_last = (i == 0 && L.entity_leaf);
+      for (int q = 0; q < nlev; ++q) {
+        const int lv = leaf_last ? q : nlev - 1 - q;
+        AggLevel& t = a.lv[q];
+        t.ent = at<int32_t>(ws, L.ent[lv]);
+        t.self = at<float>(ws, L.V[i][lv]);
+        t.Y = at<float>(ws, L.Y[i][lv]); t.V = at<float>(ws, L.V[i + 1][lv]);
+        t.rows = rows[q] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
+        t.stream = stream_level(h, L.rows[lv], D);
+        t.leaf = (i == 0 && lv == H - 1);
+        if (t.leaf) t.SU = at<float>(ws, L.SU); else t.child = at<float>(ws, L.V[i][lv + 1]);
+      }
+      a.adj = h->adj; a.s = at<float>(ws, L.s) + (long)i * nr;
+      a.Wa = P.agg_w + (long)i * D * D; a.ba = P.agg_b + (long)i * D;
+      a.K = K; a.n_rel = nr;
+      if (i == 0) {
+        a.E = h->etab; a.u = at<float>(ws, L.u);
+        a.Se = L.entity_leaf ? at<float>(ws, L.Se) : nullptr;
+        a.Wt = P.transfer_w + (long)H * D * D; a.bt = P.transfer_b + (long)H * D;
+      }
+      bool done = false;
+      if constexpr (D == 32 || D == 64) {
+        if (i == 0 && use_tc_path(h, L.rows[H - 1])) {     // leaf iteration; inner-only iterations are faster on mma.sync
+          const size_t smt = agg_fwd_tc_smem<D>(i == 0, K, nr);
+          if (i == 0) {
+            if ((rc = set_smem(agg_fwd_tc_kernel<D, true>, smt))) return rc;
+            const int grid = make_tile_list(a.tl, rows, nlev, TT<D>::R,
+                                            h->sm_count * resident_ctas(h, agg_fwd_tc_kernel<D, true>, TT<D>::NT, smt), h->d_sched);
+            MVIN_LAUNCH((agg_fwd_tc_kernel<D, true>), grid, TT<D>::NT, smt, st, a);
+          } else {
+            if ((rc = set_smem(agg_fwd_tc_kernel<D, false>, smt))) return rc;
+            const int grid = make_tile_list(a.tl, rows, nlev, TT<D>::R,
+                                            h->sm_count * resident_ctas(h, agg_fwd_tc_kernel<D, false>, TT<D>::NT, smt), h->d_sched);
+            MVIN_LAUNCH((agg_fwd_tc_kernel<D, false>), grid, TT<D>::NT, smt, st, a);
+          }
+          done = true;
+        }
+      }
+      if (done) {
+      } else if (i == 0) {
+        const int grid = make_tile_list(a.tl, rows, nlev, C::R,
+                                        h->sm_count * resident_ctas(h, agg_fwd_kernel<D, true>, C::NT, sm_leaf), h->d_sched);
+        MVIN_LAUNCH((agg_fwd_kernel<D, true>), grid, C::NT, sm_leaf, st, a);
+      } else {
+        const int grid = make_tile_list(a.tl, rows, nlev, C::R,
+                                        h->sm_count * resident_ctas(h, agg_fwd_kernel<D, false>, C::NT, sm_in), h->d_sched);
+        MVIN_LAUNCH((agg_fwd_kernel<D, false>), grid, C::NT, sm_in, st, a);
+      }
+      LAUNCH_CHECK(h, names[i]);
+    }
+  }
+  // wide&deep mix + score (model.py:309-315, :158-159) in one launch: item = concat(V[0][0] .. V[H][0]) . W_mix + b_mix,
+  // score = u . item   (the level-0 slices V[0..H][0] are contiguous)
+  {
+    constexpr int RT = 256 / C::LPR;
+    const size_t sm = sizeof(float) * ((size_t)RT * (H + 1) * D + (D <= 64 ? (size_t)(H + 1) * D * D : 0));
+    if ((rc = set_smem(mix_score_kernel<D>, sm))) return rc;
+    MVIN_LAUNCH((mix_score_kernel<D>), (unsigned)((B + RT - 1) / RT), 256, sm, st, at<float>(ws, L.V[0][0]), P.mix_w, P.mix_b,
+                                                                        at<float>(ws, L.u), B, H + 1, at<float>(ws, L.item),
+                                                                        at<float>(ws, L.scores), scores_norm);
+    LAUNCH_CHECK(h, "mix_score");
+    if (scores) CUDA_TRY(cudaMemcpyAsync(scores, at<float>(ws, L.scores), sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
+  }
+  return MVIN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// backward, part 0: everything that depends on the parameters only -- zeroed accumulators, gradient buffers
+// initialised with their dense L2 terms, transposed weights.  `mid` (optional) is recorded once the part the first
+// backward kernels need is enqueued.  The host-step entry points run it on a side stream while the feed is still
+// crossing the bus.
+// ------------------------------------------------------------------------------------------------------
+template <int D>
+int backward_init(mvin_handle_t h, int B, void* ws, cudaStream_t st, cudaEvent_t mid, bool zero_small) {
+  const mvin_config_t& c = h->cfg;
+  const int H = c.h_hop, p = c.p_hop, nr = c.n_relation;
+  const Layout L = make_layout(c, B, use_entity_leaf(c, B, h->n_shards, h->entity_leaf_mode));
+  const mvin_params_t& P = h->P;
+  const mvin_params_t& G = h->G;
+  const float l2w = c.l2_weight, l2a = c.l2_agg_weight;
+  float* acc = at<float>(ws, L.acc);
+  float* wT = at<float>(ws, L.wT);
+  if (zero_small) CUDA_TRY(cudaMemsetAsync(at<char>(ws, L.zero_begin), 0, L.zero_mid - L.zero_begin, st));
+  // dense L2 terms: initialise every other gradient buffer with coef * param (model.py:388-410)
+  {
+    L2Segments sg;
+    memset(&sg, 0, sizeof(sg));
+    int n = 0;
+    auto add = [&](const float* prm, float* grd, long cnt, float coef, float mult, int which) {
+      sg.param[n] = prm; sg.grad[n] = grd; sg.n[n] = cnt; sg.coef[n] = coef * mult * h->dense_l2_scale;
+      sg.mult[n] = mult * h->dense_l2_scale; sg.which[n] = which;
+      ++n;
+    };
+    const float pm = p > 0 ? 1.f : 0.f;
+    add(P.user_emb, G.user_emb, (long)c.n_user * D, l2a, 1.f, 1);                 // model.py:392
+    add(P.relation_emb, G.relation_emb, (long)nr * D, l2w, 1.f, 0);               // :388
+    add(P.relation_kge, G.relation_kge, (long)nr * D * D, 0.f, 0.f, 0);
+    add(P.mix_w, G.mix_w, (long)(H + 1) * D * D, l2a, 1.f, 1);                    // :400-401
+    add(P.mix_b, G.mix_b, D, l2a, 1.f, 1);
+    add(P.user_mlp_w, G.user_mlp_w, (long)(p + 1) * D * D, l2w, pm, 0);           // :404
+    add(P.user_mlp_b, G.user_mlp_b, D, l2w, pm, 0);
+    if (H > 0) {
+      add(P.transfer_w, G.transfer_w, (long)H * D * D, l2w, pm, 0);               // :407-408
+      add(P.transfer_b, G.transfer_b, (long)H * D, l2w, pm, 0);
+    }
+    add(P.transfer_w + (long)H * D * D, G.transfer_w + (long)H * D * D, (long)D * D, l2w, 2.f * pm, 0);   // :405 + :408
+    add(P.transfer_b + (long)H * D, G.transfer_b + (long)H * D, D, l2w, 2.f * pm, 0);
+    add(P.h_item_w, G.h_item_w, 2 * D, l2w, 1.f, 0);                              // :410
+    add(P.h_item_b, G.h_item_b, 1, l2w, 1.f, 0);
+    add(P.agg_w, G.agg_w, (long)H * D * D, l2a, 1.f, 1);                          // :394-396
+    add(P.agg_b, G.agg_b, (long)H * D, 0.f, 0.f, 1);
+    add(P.agg_urh_w, G.agg_urh_w, (long)H * 3 * D, l2a, 1.f, 1);
+    add(P.agg_urh_b, G.agg_urh_b, H, 0.f, 0.f, 1);
+    sg.count = n;
+    MVIN_LAUNCH((l2_dense_kernel), h->sm_count * 2, 256, 0, st, sg, acc);
+    LAUNCH_CHECK(h, "l2_dense");
+  }
+  // transposed weights: wT[i] = W_a[i]^T (i < H), wT[H + e] = W_t[e]^T (e <= H)
+  MVIN_LAUNCH((transpose_kernel), dim3(2 * H + 1), 256, 0, st, P.agg_w, P.transfer_w, H, D, wT);
+  LAUNCH_CHECK(h, "transpose");
+  if (mid) cudaEventRecord(mid, st);
+  CUDA_TRY(cudaMemsetAsync(at<char>(ws, L.zero_mid), 0, L.zero_end - L.zero_mid, st));
+  // sharded mode: peers scatter into this rank's shard, so the CALLER zeroes it (and synchronises the ranks)
+  if (h->n_shards == 1) CUDA_TRY(cudaMemsetAsync(G.entity_emb, 0, sizeof(float) * (size_t)c.n_entity * D, st));
+  prof_mark(h, st, "memset");
+  return MVIN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------------
+template <int D>
+int launch_dw(mvin_handle_t h, cudaStream_t st, const DwArgs& a, int groups, const char* name) {
+  using C = TC<D>;
+  const size_t sm = dw_smem<D>();
+  int rc;
+  if ((rc = set_smem(dw_kernel<D>, sm))) return rc;
+  long tiles = (a.rows + C::R - 1) / C::R;
+  int gx = (int)(tiles < h->sm_count ? tiles : h->sm_count);
+  MVIN_LAUNCH((dw_kernel<D>), dim3(gx, groups), C::NT, sm, st, a);
+  LAUNCH_CHECK(h, name);
+  return MVIN_OK;
+}
+
+template <int D>
+int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out, void* ws, cudaStream_t st) {
+  using C = TC<D>;
+  const mvin_config_t& c = h->cfg;
+  const int K = c.neighbor_sample_size, H = c.h_hop, p = c.p_hop, m = c.n_memory, nr = c.n_relation;
+  const Layout L = make_layout(c, B, use_entity_leaf(c, B, h->n_shards, h->entity_leaf_mode));
+  const mvin_params_t& P = h->P;
+  const mvin_params_t& G = h->G;
+  const float l2w = c.l2_weight, l2a = c.l2_agg_weight;
+  int rc;
+  float* acc = at<float>(ws, L.acc);
+  float* wT = at<float>(ws, L.wT);
+  prof_mark(h, st, nullptr);
+
+  // part 0 (parameters only) on side stream 0 -- unless a host-step entry point already ran it during the feed copy
+  const Par par{h, st, h->use_streams && !h->prof_on};
+  if (h->early_init && h->in_host_step) {
+    CUDA_TRY(cudaStreamWaitEvent(st, h->ev_early, 0));
+    h->early_init = false;
+    par.fork(0);
+    par.mark_mid();
+  } else {
+    CUDA_TRY(cudaMemsetAsync(at<char>(ws, L.zero_begin), 0, L.zero_mid - L.zero_begin, st));   // loss accumulators
+    par.fork(0);
+    if ((rc = backward_init<D>(h, B, ws, par.s(0), par.on ? h->ev_mid : nullptr, false))) return rc;
+  }
+  {
+  cudaStream_t st = par.s(0);
+  // ripple-memory relation histogram (feeds the un-normalised L2 over gathered RK matrices, model.py:386)
+  if (p > 0) {
+    const long n = (long)p * B * m;
+    MVIN_LAUNCH((hist_r_kernel), h->sm_count * 4, 256, sizeof(float) * nr, st, h->mem_r, n, nr, at<float>(ws, L.cnt));
+    LAUNCH_CHECK(h, "hist_r");
+  }
+  }
+
+  float* du = at<float>(ws, L.du);
+  float* ditem = at<float>(ws, L.ditem);
+  const float invB = 1.f / (float)(h->global_batch > 0 ? h->global_batch : B);
+  const bool fused_mix_bwd = D <= 64;          // W_mix^T ((H+1) d^2 floats) is staged in shared memory
+  if (fused_mix_bwd) {
+    // loss gradient + mix backward in one launch: ditem, du, DC[j][0] = ditem . W_mix[j]^T
+    const size_t sm = sizeof(float) * ((size_t)D * (H + 1) * D + 16 * D);
+    if ((rc = set_smem(loss_mix_bwd_kernel<D>, sm))) return rc;
+    const int grid = (B + 15) / 16 < 2 * h->sm_count ? (B + 15) / 16 : 2 * h->sm_count;
+    MVIN_LAUNCH((loss_mix_bwd_kernel<D>), grid, 256, sm, st, at<float>(ws, L.scores), labels, at<float>(ws, L.u), at<float>(ws, L.item),
+                                                  P.mix_w, B, H + 1, invB, ditem, du, at<float>(ws, L.DC[0][0]), acc);
+    LAUNCH_CHECK(h, "loss_mix_bwd");
+  } else {
+    const long n = (long)B * C::LPR;
+    MVIN_LAUNCH((loss_bwd_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, at<float>(ws, L.scores), labels, at<float>(ws, L.u),
+                                                                    at<float>(ws, L.item), B, invB, ditem, du, acc);
+    LAUNCH_CHECK(h, "loss_bwd");
+  }
+  par.wait_mid();
+  // mix backward: dW_mix[j] = V[j][0]^T ditem (grouped), DC[j][0] = ditem . W_mix[j]^T (batched)
+  {
+    DwArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int j = 0; j <= H; ++j) { a.A[j] = at<float>(ws, L.V[j][0]); a.lda[j] = D; a.dW[j] = G.mix_w + (long)j * D * D; }
+    a.G = ditem; a.db = G.mix_b; a.rows = B;
+    par.fork(1);                                   // side stream 1: weight gradient of the mix layer
+    if ((rc = launch_dw<D>(h, par.s(1), a, H + 1, "dw_mix"))) return rc;
+    if (!fused_mix_bwd) {
+      GemmArgs g = gemm_args();
+      g.A = ditem; g.sa_m = D; g.sa_k = 1; g.bsA = 0;
+      g.B = P.mix_w; g.sb_k = 1; g.sb_n = D; g.bsB = (long)D * D;   // W_mix[jD + n][k] -> transposed use
+      g.C = at<float>(ws, L.DC[0][0]); g.ldc = D; g.bsC = (long)B * D;
+      g.M = B; g.N = D; g.K = D; g.nbatch = H + 1;
+      if ((rc = run_gemm(h, st, g, "gemm_mix_bwd"))) return rc;
+    }
+  }
+  // aggregation iterations, reversed; one launch per iteration
+  {
+    const size_t sm_leaf = agg_bwd_smem<D, true>(K, nr), sm_in = agg_bwd_smem<D, false>(K, nr);
+    if ((rc = set_smem(agg_bwd_kernel<D, true>, sm_leaf))) return rc;
+    if ((rc = set_smem(agg_bwd_kernel<D, false>, sm_in))) return rc;
+    static const char* names[MAX_L] = {"agg_bwd_0", "agg_bwd_1", "agg_bwd_2"};
+    for (int i = H - 1; i >= 0; --i) {
+      AggBwdArgs a;
+      memset(&a, 0, sizeof(a));
+      long rows[MAX_LV];
+      const int nlev = H - i;
+      const bool leaf_last = (i == 0 && L.entity_leaf);
+      for (int q = 0; q < nlev; ++q) {
+        const int lv = leaf_last ? q : nlev - 1 - q;
+        AggBwdLevel& t = a.lv[q];
+        t.ent = at<int32_t>(ws, L.ent[lv]);
+        t.V = at<float>(ws, L.V[i + 1][lv]); t.Y = at<float>(ws, L.Y[i][lv]);
+        t.g1 = at<float>(ws, L.DC[i + 1][lv]);
+        t.g2 = has_agg(H, i + 1, lv) ? at<float>(ws, L.DS[i + 1][lv]) : nullptr;
+        t.dself = at<float>(ws, L.DS[i][lv]);
+        t.rows = rows[q] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
+        t.stream = stream_level(h, L.rows[lv], D);
+        t.leaf = (i == 0 && lv == H - 1);
+        if (t.leaf) {
+          t.SU = at<float>(ws, L.SU);
+        } else {
+          t.child = at<float>(ws, L.V[i][lv + 1]);
+          t.dchild = at<float>(ws, L.DC[i][lv + 1]);
+        }
+      }
+      a.adj = h->adj; a.s = at<float>(ws, L.s) + (long)i * nr;
+      a.WaT = wT + (long)i * D * D;
+      a.dWa = G.agg_w + (long)i * D * D; a.dba = G.agg_b + (long)i * D;
+      a.ds = at<float>(ws, L.ds) + (long)i * nr;
+      a.K = K; a.n_rel = nr;
+      if (i == 0) {
+        par.join(0);       // zeroed dE / GSe / dQ / cnt are first needed here
+        a.E = h->etab; a.WtT = wT + (long)(H + H) * D * D;
+        a.dWt = G.transfer_w + (long)H * D * D; a.dbt = G.transfer_b + (long)H * D;
+        a.dE = h->gtab; a.du = du;
+        a.GSe = L.entity_leaf ? at<float>(ws, L.GSe) : nullptr;
+        const int grid = make_tile_list(a.tl, rows, nlev, C::R,
+                                        h->sm_count * resident_ctas(h, agg_bwd_kernel<D, true>, C::NT, sm_leaf), h->d_sched + 2);
+        MVIN_LAUNCH((agg_bwd_kernel<D, true>), grid, C::NT, sm_leaf, st, a);
+      } else {
+        const int grid = make_tile_list(a.tl, rows, nlev, C::R,
+                                        h->sm_count * resident_ctas(h, agg_bwd_kernel<D, false>, C::NT, sm_in), h->d_sched + 2);
+        MVIN_LAUNCH((agg_bwd_kernel<D, false>), grid, C::NT, sm_in, st, a);
+      }
+      LAUNCH_CHECK(h, names[i]);
+    }
+  }
+  // side stream 0: per-entity leaf backward + relation-score gradients, while the user-oriented transform backward
+  // runs on the launch stream (both only add into dE)
+  par.fork(0);
+  {
+  cudaStream_t st = par.s(0);
+  if (L.entity_leaf) {
+    LeafEntArgs a;
+    memset(&a, 0, sizeof(a));
+    a.stamp = at<int32_t>(ws, L.stamp); a.adj = h->adj; a.s = at<float>(ws, L.s); a.E = h->etab;
+    a.GSe = at<float>(ws, L.GSe); a.dE = h->gtab; a.ds = at<float>(ws, L.ds);
+    a.n_entity = c.n_entity; a.K = K; a.n_rel = nr;
+    const size_t sm = leaf_entity_smem(nr);
+    if ((rc = set_smem(leaf_entity_kernel<D, true>, sm))) return rc;
+    const long want = ((long)c.n_entity + LEAF_NW * 32 - 1) / (LEAF_NW * 32);
+    const long cap = (long)h->sm_count * 8;
+    MVIN_LAUNCH((leaf_entity_kernel<D, true>), (unsigned)(want < cap ? want : cap), LEAF_NT, sm, st, a);
+    LAUNCH_CHECK(h, "leaf_entity_bwd");
+  }
+  MVIN_LAUNCH((rel_scores_bwd_kernel), H, 128, 0, st, P.relation_emb, P.agg_urh_w, at<float>(ws, L.ds), nr, D, G.relation_emb,
+                                           G.agg_urh_w);
+  LAUNCH_CHECK(h, "rel_scores_bwd");
+  }
+  // user-oriented transform backward, levels 0..L-1, one launch
+  {
+    const size_t sm = transform_bwd_smem<D>();
+    if ((rc = set_smem(transform_bwd_kernel<D>, sm))) return rc;
+    TransformArgs a;
+    memset(&a, 0, sizeof(a));
+    long rows[MAX_LV];
+    for (int q = 0; q < H; ++q) {
+      const int lv = H - 1 - q;
+      TransformLevel& t = a.lv[q];
+      t.ent = at<int32_t>(ws, L.ent[lv]);
+      t.W = wT + (long)(H + lv) * D * D;
+      t.g1 = at<float>(ws, L.DC[0][lv]); t.g2 = at<float>(ws, L.DS[0][lv]);
+      t.dW = G.transfer_w + (long)lv * D * D; t.db = G.transfer_b + (long)lv * D;
+      t.rows = rows[q] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
+        t.stream = stream_level(h, L.rows[lv], D);
+    }
+    a.nlev = H; a.E = h->etab; a.u = at<float>(ws, L.u); a.dE = h->gtab; a.du = du;
+    const int grid = partition_grid(rows, H, C::R, h->sm_count * resident_ctas(h, transform_bwd_kernel<D>, C::NT, sm), a.cta_end);
+    MVIN_LAUNCH((transform_bwd_kernel<D>), grid, C::NT, sm, st, a);
+    LAUNCH_CHECK(h, "transform_bwd");
+  }
+  // user_o = O . W_user + b  backward
+  {
+    DwArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int s = 0; s <= p; ++s) {
+      a.A[s] = at<float>(ws, L.O) + (long)s * D; a.lda[s] = (long)(p + 1) * D; a.dW[s] = G.user_mlp_w + (long)s * D * D;
+    }
+    a.G = du; a.db = G.user_mlp_b; a.rows = B;
+    par.fork(1);                                   // side stream 1: weight gradient of the user MLP
+    if ((rc = launch_dw<D>(h, par.s(1), a, p + 1, "dw_user"))) return rc;
+    // dO = du . W_user^T as a batched GEMM (a per-warp matvec inside the ripple kernel re-reads W_user per warp and
+    // measured slower: +9 us at C2, +78 us at C3)
+    GemmArgs g = gemm_args();
+    g.A = du; g.sa_m = D; g.sa_k = 1;
+    g.B = P.user_mlp_w; g.sb_k = 1; g.sb_n = D;
+    g.C = at<float>(ws, L.dO); g.ldc = (long)(p + 1) * D;
+    g.M = B; g.N = (p + 1) * D; g.K = D;
+    if ((rc = run_gemm(h, st, g, "gemm_user_bwd"))) return rc;
+  }
+  // ripple backward
+  {
+    RippleBwdArgs a;
+    a.E = h->etab; a.Q = at<float>(ws, L.Q); a.w_hi = P.h_item_w;
+    a.mem_h = h->mem_h; a.mem_r = h->mem_r; a.mem_t = h->mem_t;
+    a.probs = at<float>(ws, L.probs); a.dO = at<float>(ws, L.dO);
+    a.dE = h->gtab; a.dQ = at<float>(ws, L.dQ); a.dw_hi = G.h_item_w; a.l2_acc = acc + 1;
+    a.l2_weight = l2w; a.B = B; a.m = m; a.p = p; a.n_rel = nr;
+    const size_t sm = ripple_bwd_smem(m, D);
+    if ((rc = set_smem(ripple_bwd_kernel<D>, sm))) return rc;
+    a.ctr = h->d_sched + 4;
+    const long warps = (long)B * (p + 1);
+    long grid = (warps + RIPPLE_NW - 1) / RIPPLE_NW;
+    const long resident = (long)h->sm_count * resident_ctas(h, ripple_bwd_kernel<D>, RIPPLE_NT, sm) * 2;   // cap 4 -> 8
+    if (grid > resident) grid = resident;
+    MVIN_LAUNCH((ripple_bwd_kernel<D>), (unsigned)grid, RIPPLE_NT, sm, st, a);
+    LAUNCH_CHECK(h, "ripple_bwd");
+  }
+  if (p > 0) {
+    // three independent consumers of dQ / cnt: RK L2 term (side 1), dRK (side 0), dE[item] (launch stream)
+    par.fork(0);
+    par.fork(1);
+    MVIN_LAUNCH((rk_l2_kernel), nr, 256, 0, par.s(1), P.relation_kge, at<float>(ws, L.cnt), D * D, 2.f * l2w, G.relation_kge, acc + 1);
+    LAUNCH_CHECK(h, "rk_l2");
+    // dRK[r][i][j] += sum_b v[b][i] dQ[b][r][j]
+    GemmArgs g = gemm_args();
+    g.A = at<float>(ws, L.Vbuf); g.sa_m = 1; g.sa_k = D; g.bsA = 0;
+    g.B = at<float>(ws, L.dQ); g.sb_k = (long)nr * D; g.sb_n = 1; g.bsB = D;
+    g.C = G.relation_kge; g.ldc = D; g.bsC = (long)D * D;
+    g.M = D; g.N = D; g.K = B; g.nbatch = nr; g.ksplit = pick_ksplit(B); g.accumulate = 1;
+    if ((rc = run_gemm(h, par.s(0), g, "gemm_drk"))) return rc;
+    // dv[b][i] = sum_r sum_j dQ[b][r][j] RK[r][i][j]  (reduced over r inside the CTA);  dE[item_b] += dv[b]
+    GemmArgs g2 = gemm_args();
+    g2.A = at<float>(ws, L.dQ); g2.sa_m = (long)nr * D; g2.sa_k = 1; g2.bsA = D;
+    g2.B = P.relation_kge; g2.sb_k = 1; g2.sb_n = D; g2.bsB = (long)D * D;
+    g2.M = B; g2.N = D; g2.K = D; g2.nbatch = nr; g2.reduce = 1;
+    g2.ksplit = nr >= 8 ? 4 : 1;
+    if (h->n_shards == 1) {
+      // accumulate straight into the entity-table gradient rows of the items
+      g2.C = G.entity_emb; g2.ldc = D; g2.bsC = 0; g2.c_rows = at<int32_t>(ws, L.ent[0]); g2.accumulate = 1;
+      if ((rc = run_gemm(h, st, g2, "gemm_dv"))) return rc;
+    } else {
+      g2.C = at<float>(ws, L.dv); g2.ldc = D; g2.bsC = 0; g2.accumulate = g2.ksplit > 1;   // dv lives in the zeroed region
+      if ((rc = run_gemm(h, st, g2, "gemm_dv"))) return rc;
+      const long n = (long)B * C::LPR;
+      MVIN_LAUNCH((scatter_rows_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, at<float>(ws, L.dv), at<int32_t>(ws, L.ent[0]), B,
+                                                                          h->gtab);
+      LAUNCH_CHECK(h, "scatter_dv");
+    }
+  }
+  par.join(0);
+  par.join(1);
+  MVIN_LAUNCH((finalize_loss_kernel), 1, 32, 0, st, acc, l2w, l2a, losses_out);
+  LAUNCH_CHECK(h, "finalize_loss");
+  return MVIN_OK;
+}
+
+}  // namespace mvin_host
