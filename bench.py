@@ -5,24 +5,36 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-One "step" = one forward + backward pass (loss and every parameter gradient; Adam excluded) over one
-batch of B user-item pairs of the workload.  Prints ONE JSON line (rank 0).
+One "step" = one forward + backward pass (loss and every parameter gradient; Adam excluded and reported separately,
+SURVEY.md 8(d)) over one batch of B user-item pairs of the workload.  Default workload: C4, the largest single-GPU
+entry of BASELINE.json's configs.  Prints ONE JSON line (rank 0).
 
   value        whole-job pairs/s with the batch already resident in HBM (device-timed, CUDA events per step, max over
                ranks).  L2 is flushed (256 MiB write) between timed steps, outside the event pairs.
   e2e          same metric through the C-ABI host entry point mvin_train_step_host: the feed is copied H2D from pinned
                host memory and the loss scalars are read back D2H inside the timed region of every step.
-  e2e_prefetch same host feed, copied one step ahead (mvin_feed_prefetch + mvin_train_step_prefetched).
+  e2e_api      the drop-in call itself: model.train(None, feed_dict) with the feed dict the reference's get_feed_dict
+               builds (train.py:112-122: NumPy slices + 3 p Python lists of B int32 rows), Adam step included (that is
+               what train() does); the Python feed assembly is timed separately (`feed_assembly_ms`).
+  e2e_prefetch same host feed as e2e, copied one step ahead (mvin_feed_prefetch + mvin_train_step_prefetched).
   e2e_device_feed  same, through mvin_train_step_users_host: the ripple sets are bound on the device once and only
                user / item / label ids cross the bus per step.
-  roofline     dominant kernel (by device time, measured live with CUDA events recorded by the library on its launch
-               stream in a third pass over the same steps): algorithmic bytes per launch / mean launch duration vs the
-               measured HBM copy peak (MEASURED_PEAKS.json).
+  roofline     dominant kernel by device time over ALL kernel families (timed live with CUDA events the library records
+               on its launch stream in a separate pass over the same steps).  `frac` = EXECUTED bytes per launch
+               (`traffic`: ncu dram__bytes_read + dram__bytes_write of that kernel at this workload, profiles/traffic.json)
+               / live launch duration / measured HBM copy peak (MEASURED_PEAKS.json).  `logical_*` = the contract figure
+               of SURVEY.md 8(d) (per-pair gather bytes, served mostly by L2 at C1-C4), kept beside it.
+  adam         the TF1-semantics Adam step (mvin_adam_step) timed alone: ms, GB/s over its 28 bytes per element, fraction
+               of the HBM peak.
+  parity_check a few pairs of the last timed batch re-computed by the oracle on the extracted sub-problem
+               (oracle/subproblem.py): max relative score error (tolerance 1e-4) and bit-exactness of the integer
+               neighbour ids.  A failing check makes the run exit non-zero.
   cpu_baseline the oracle (op-for-op CPU restatement of the reference's TF1 graph, oracle/mvin_oracle.py) timed on the
-               host cores on a bounded sample of the same workload.  The oracle is used ONLY here and in --impl
-               reference; the product path never touches it.
-N > 1: data-parallel replicas (tables <= 30 MB are replicated); every rank processes its own batches
-(weak scaling, no data-path collective).  --allreduce adds the DP gradient all-reduce (NCCL) to every step.
+               host cores on a bounded sample of the same workload (sized by memory and time).  The oracle is used ONLY
+               here, in parity_check and in --impl reference; the product path never touches it.
+N > 1, C1-C4: data-parallel replicas (tables <= 30 MB are replicated): every rank processes its own
+batch and ONE flat NCCL all-reduce of all gradients (+ the loss scalars) runs inside every timed step; `collective`
+reports its bytes and exposed time.  C5: entity table row-sharded over the ranks.
 """
 from __future__ import annotations
 
@@ -167,6 +179,18 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------------------------------------------
+def oracle_pair_bytes(w):
+    """Rough host memory the oracle holds per pair: the unfused TF graph materialises a [K^L, 3d] concat per aggregator
+    call (25 MB per pair at C4) and autograd keeps a few tensors of the leaf level's size -- measured ~50 MB per pair
+    at C4, budgeted at 12 leaf-level tensors -- plus the [p m, d, d] relation matrices."""
+    d, L, K, p, m = w["dim"], w["h_hop"], w["K"], w["p"], w["m"]
+    return 12 * (K ** L) * d * 4 + 6 * p * m * d * d * 4
+
+
+def cpu_sample_pairs(w, want, mem_budget=12 << 30):
+    return int(max(2, min(want, w["B"], mem_budget // oracle_pair_bytes(w))))
+
+
 def oracle_problem(w, ds, n_pairs, seed=0):
     """A bounded sample of the workload for the CPU arm: first n_pairs pairs of the (seeded) interaction list."""
     from oracle import mvin_oracle as orc            # checker / CPU baseline only
@@ -198,17 +222,22 @@ def time_oracle(w, ds, n_pairs, steps, warmup):
 
 def run_reference(a, w, wl_key):
     """--impl reference: the reference's own CPU implementation of the path.  TensorFlow 1.13 is not installable in
-    this image, so this is the oracle port, timed on all host cores on a bounded sample per step."""
+    this image, so this is the oracle port, timed on all host cores on a bounded sample per step (sized by
+    host memory first -- the unfused graph holds ~50-100 MB per pair at C4 -- then by time)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if w.get("sharded"):
+        print(json.dumps({"impl": "reference", "unavailable": "C5 (51 GB entity table, 137 GB of unfused intermediates per "
+                          "batch) does not fit the reference's TF1 graph (2 GB GraphDef limit on the adjacency constant) "
+                          "nor the CPU port; the CPU baseline is quoted at C1-C4"}), flush=True)
+        return
     from mvin_b200 import data as D
     ds = D.make_synthetic_dataset(w["dataset"], w["K"], w["p"], w["m"], seed=2020, n_interactions=50_000)
-    # size the per-step sample so that (steps + warmup) steps take about two minutes
-    probe = 64
+    probe = cpu_sample_pairs(w, 64, mem_budget=4 << 30)
     _, t_probe, cores = time_oracle(w, ds, probe, 1, 1)
-    budget = 120.0 / max(1, a.steps + a.warmup)
-    n_pairs = int(max(8, min(w["B"], probe * budget / max(t_probe, 1e-6))))
+    budget = 120.0 / max(1, a.steps + a.warmup)       # (steps + warmup) steps in about two minutes
+    n_pairs = cpu_sample_pairs(w, int(max(2, probe * budget / max(t_probe, 1e-6))))
     value, t_step, cores = time_oracle(w, ds, n_pairs, a.steps, a.warmup)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -216,9 +245,21 @@ def run_reference(a, w, wl_key):
             "config": {"workload": workload_name(wl_key, w), "pairs_per_step": n_pairs},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{n_pairs} pairs/step of {wl_key} x {a.steps} steps, torch-CPU fp32 oracle, "
-                                       f"fwd + autograd bwd"},
+                                       f"fwd + autograd bwd (sample bounded by host memory, ~"
+                                       f"{oracle_pair_bytes(w) / 2**20:.0f} MiB per pair, and by time)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def reference_feed_dict(model, data_rows, user_triplet_set):
+    """get_feed_dict of the reference (train.py:112-122) verbatim in shape: NumPy slices for user / item / label and,
+    per hop, Python LISTS of B int32 [m] rows picked from user_triplet_set[user] ([p, 3, m] per user)."""
+    feed = {model.user_indices: data_rows[:, 0], model.item_indices: data_rows[:, 1], model.labels: data_rows[:, 2]}
+    for i in range(max(1, model.p_hop)):
+        feed[model.memories_h[i]] = [user_triplet_set[user][i][0] for user in data_rows[:, 0]]
+        feed[model.memories_r[i]] = [user_triplet_set[user][i][1] for user in data_rows[:, 0]]
+        feed[model.memories_t[i]] = [user_triplet_set[user][i][2] for user in data_rows[:, 0]]
+    return feed
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -239,8 +280,8 @@ def run_ours(a, w, wl_key):
         dist.init_process_group("nccl", device_id=dev)
 
     B = w["B"]
-    NB = 8
-    host, devb = [], []
+    NB = 4 if w["dataset"].startswith("amazon") else 8
+    host, devb, rows_np = [], [], []
     sharded = bool(w.get("sharded"))
     ds = None
     if sharded:
@@ -271,6 +312,7 @@ def run_ours(a, w, wl_key):
         for i in range(NB):
             sel = perm[((rank * NB + i) * B) % (perm.size - B):][:B]
             batch = ds["data"][sel]
+            rows_np.append(batch)
             mh, mr, mt = D.stacked_memories(ds["user_triplet_set"], batch[:, 0])
             arrs = [np.ascontiguousarray(batch[:, 0]), np.ascontiguousarray(batch[:, 1]),
                     np.ascontiguousarray(batch[:, 2].astype(np.float32)), mh, mr, mt]
@@ -280,11 +322,14 @@ def run_ours(a, w, wl_key):
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     d2h = 16
     flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    losses = torch.zeros(4, dtype=torch.float32, device=dev)
-    flat_grads = None
-    if a.allreduce and world > 1 and not sharded:
-        flat_grads = list(model.grads.values())
+    losses = model.loss_slot                     # the 4 loss scalars live at the tail of the flat gradient bucket
     group_mode = sharded and world > 1
+    dp_mode = world > 1 and not sharded
+    if dp_mode:
+        # replicas: base loss / global batch, dense L2 terms / world, so that the SUM all-reduce of the flat gradient
+        # bucket equals the single-device gradient on the concatenated batch
+        model.set_batch_scale(B * world, 1.0 / world)
+    collective_on = [dp_mode and not a.no_allreduce]
 
     def step_device(i):
         u, it, lab, mh, mr, mt = devb[i % NB]
@@ -295,9 +340,8 @@ def run_ours(a, w, wl_key):
         if group_mode:
             model.allreduce_replicated()    # NCCL: dense-weight / relation-table gradients
             model.end_step()
-        if flat_grads is not None:
-            for g in flat_grads:
-                dist.all_reduce(g)
+        if collective_on[0]:
+            model.allreduce_grads()         # ONE NCCL all-reduce: every gradient + the loss scalars, in place
 
     def step_host(i):
         u, it, lab, mh, mr, mt = host[i % NB]
@@ -327,7 +371,8 @@ def run_ours(a, w, wl_key):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for i in range(max(3, a.warmup)):
+    warmup = max(3, a.warmup)
+    for i in range(warmup):
         step_device(i)
     step_host(0)
     sampler = ClockSampler(local)
@@ -336,9 +381,21 @@ def run_ours(a, w, wl_key):
     ms_total = timed(step_device, a.steps)
     clocks = sampler.stop()
     launches = model.launch_count() - launches0
+    collective = None
+    if dp_mode and collective_on[0]:
+        # exposed time of the collective: the same steps without it
+        collective_on[0] = False
+        ms_nocoll = timed(step_device, a.steps)
+        collective_on[0] = True
+        collective = {"kind": "all_reduce", "backend": "nccl", "calls_per_step": 1,
+                      "bytes": int(model.grad_flat.numel() * 4),
+                      "ms_exposed": max(0.0, (ms_total - ms_nocoll) / a.steps),
+                      "ms_per_step_without": ms_nocoll / a.steps}
     ms_e2e = timed(step_host, a.steps)
-    ms_e2e_pre = None
-    if not sharded:
+    full = not a.quick
+    ms_e2e_pre = ms_e2e_dev = None
+    e2e_api = None
+    if not sharded and full:
         # double-buffered input pipeline: the feed of step i + 1 is copied while step i computes (every copy is inside
         # the timed region: K prefetches and K steps per K timed steps)
         model.prefetch_feed(*host[0])
@@ -350,25 +407,53 @@ def run_ours(a, w, wl_key):
         step_prefetched(0)
         ms_e2e_pre = timed(step_prefetched, a.steps)
         model.train_step_prefetched(apply_adam=False)      # drain the last pending batch
-    ms_e2e_dev = None
-    if not sharded:
         # device-resident feed: ripple sets uploaded once, only user / item / label per step
         model.bind_user_triplet_set(ds["user_triplet_set"])
         step_users(0)
         ms_e2e_dev = timed(step_users, a.steps)
+        if world == 1:
+            # the drop-in call with the reference-shaped feed dict; the feed assembly (pure Python, train.py:112-122)
+            # is timed on the wall clock beside the call
+            uts_ref = {u: blk for u, blk in enumerate(ds["user_triplet_set"])}   # user -> int32 [p, 3, m]
+            n_api = max(2, min(a.steps, 10))
+            snap = {k: v.clone() for k, v in model.params.items()}               # train() applies Adam: restore after
+            t_feed = t_call = 0.0
+            model.train(None, reference_feed_dict(model, rows_np[0], uts_ref))
+            torch.cuda.synchronize(dev)
+            for i in range(n_api):
+                t0 = time.perf_counter()
+                fd = reference_feed_dict(model, rows_np[i % NB], uts_ref)
+                t1 = time.perf_counter()
+                model.train(None, fd)                                            # blocks until the loss is back
+                t2 = time.perf_counter()
+                t_feed += t1 - t0
+                t_call += t2 - t1
+            for k, v in snap.items():
+                model.params[k].copy_(v)
+            for st_ in (model.adam_m, model.adam_v):
+                for v in st_.values():
+                    v.zero_()
+            model.step = 0
+            e2e_api = {"value": B * n_api / t_call, "unit": UNIT, "ms_per_step": t_call / n_api * 1e3,
+                       "feed_assembly_ms": t_feed / n_api * 1e3, "steps": n_api,
+                       "value_with_feed_assembly": B * n_api / (t_call + t_feed),
+                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "note": "model.train(None, feed_dict) with lists of rows as train.py:112-122 builds them, wall "
+                               "clock, Adam step included; feed_assembly_ms = the reference's own get_feed_dict"}
 
     # per-kernel device times, same steps, events recorded by the library on its launch stream
     prof = {}
     if rank == 0:
         import ctypes
         model.lib.mvin_profile_enable(model._handle, 1)
-        barrier_local = lambda: torch.cuda.synchronize(dev)
-        barrier_local()
+        torch.cuda.synchronize(dev)
         n_prof = min(a.steps, 50)
-        buf = ctypes.create_string_buffer(8192)
+        buf = ctypes.create_string_buffer(16384)
         for i in range(n_prof):
             flush.zero_()
             u, it, lab, mh, mr, mt = devb[i % NB]
+            if group_mode:
+                model._entity_grad_all.zero_()
             model.forward_device(u, it, mh, mr, mt)
             model.backward_device(lab, losses)
             model.lib.mvin_profile_read(model._handle, buf, len(buf))
@@ -383,6 +468,58 @@ def run_ours(a, w, wl_key):
     if world > 1:
         dist.barrier()
 
+    # Adam alone (excluded from the metric, reported separately): 16 B read + 12 B written per element
+    adam = None
+    if True:
+        n_adam = max(3, min(a.steps, 20))
+        snap = {k: v.clone() for k, v in model.params.items()} if not sharded else None
+        model.adam_step_device()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_adam)]
+        torch.cuda.synchronize(dev)
+        for i in range(n_adam):
+            flush.zero_()
+            evs[i][0].record()
+            model.adam_step_device()
+            evs[i][1].record()
+        torch.cuda.synchronize(dev)
+        ms_adam = sum(s.elapsed_time(e) for s, e in evs) / n_adam
+        n_elem = sum(v.numel() for v in model.params.values())
+        adam = {"ms_per_step": ms_adam, "elements": int(n_elem), "bytes": int(n_elem * 28),
+                "gbs": n_elem * 28 / (ms_adam * 1e-3) / 1e9}
+        if snap is not None:
+            for k, v in snap.items():
+                model.params[k].copy_(v)
+            for st_ in (model.adam_m, model.adam_v):
+                for v in st_.values():
+                    v.zero_()
+            model.step = 0
+
+    # parity check: a few pairs of one timed batch against the oracle on the extracted sub-problem.  Pairs are taken
+    # from both ends of the batch (the last rows sit at the largest buffer offsets).
+    parity = None
+    if not a.no_parity_check:
+        from oracle import mvin_oracle as orc              # the checker, outside every timed region
+        from oracle import subproblem
+        u, it, lab, mh, mr, mt = devb[0]
+        scores = torch.empty(B, dtype=torch.float32, device=dev)
+        if group_mode:
+            model.begin_step()
+        model.forward_device(u, it, mh, mr, mt, scores=scores)
+        torch.cuda.synchronize(dev)
+        if group_mode:
+            model.end_step()
+        n_chk = 8
+        idx = np.r_[0:n_chk // 2, B - n_chk // 2:B]
+        hu, hi = host[0][0].numpy(), host[0][1].numpy()
+        hm = [host[0][j].numpy() for j in (3, 4, 5)]
+        cfg = orc.OracleConfig.from_args(make_args(w))
+        if group_mode and rank != 0:
+            model.entity_rows(np.zeros(0, dtype=np.int64))     # serve rank 0's row lookup (a collective)
+        else:
+            parity = subproblem.check_model_pairs(model, cfg, hu, hi, list(hm[0]), list(hm[1]), list(hm[2]),
+                                                  scores.cpu().numpy(), idx)
+            parity["ok"] = bool(parity["max_rel_err"] <= parity["tolerance"] and parity["ids_bit_exact"])
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -393,53 +530,72 @@ def run_ours(a, w, wl_key):
     peak, peak_src = load_peaks()
     fwd_b, bwd_b = bytes_per_pair(w)
     kb = kernel_bytes_per_step(w)
-    gather_kernels = {k: v for k, v in prof.items() if k in kb and kb[k] > 0}
-    top = max(gather_kernels, key=lambda k: gather_kernels[k]["ms_per_step"]) if gather_kernels else None
+    traffic_all = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic_all = json.load(open(tpath)).get(wl_key, {})
+        except Exception:
+            traffic_all = {}
     roofline = None
-    if top:
-        per_launch_bytes = kb[top] / prof[top]["launches_per_step"]
-        per_launch_ms = prof[top]["ms_per_step"] / prof[top]["launches_per_step"]
-        achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get(wl_key, {}).get(top)
-            except Exception:
-                traffic = None
+    timed_kernels = {k: v for k, v in prof.items() if v["launches_per_step"] > 0 and k != "memset"}
+    if timed_kernels:
+        top = max(timed_kernels, key=lambda k: timed_kernels[k]["ms_per_step"])       # over ALL kernel families
+        n_l = prof[top]["launches_per_step"]
+        per_launch_ms = prof[top]["ms_per_step"] / n_l
+        traffic = traffic_all.get(top)
+        logical = kb[top] / n_l if top in kb else None
+        achieved = traffic / (per_launch_ms * 1e-3) / 1e9 if traffic else None
+        step_ms = sum(v["ms_per_step"] for v in prof.values())
+        step_traffic = sum(traffic_all.get(k, 0.0) * v["launches_per_step"] for k, v in prof.items())
         roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": per_launch_bytes, "launch_ms": per_launch_ms,
-                    "share_of_step": prof[top]["ms_per_step"] / max(1e-9, sum(v["ms_per_step"] for v in prof.values())),
+                    "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                    "launch_ms": per_launch_ms, "share_of_step": prof[top]["ms_per_step"] / max(1e-9, step_ms),
+                    "bytes_basis": ("executed: ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel "
+                                    "at this workload (profiles/traffic.json) / live launch time" if traffic else
+                                    "no ncu traffic entry for this kernel / workload in profiles/traffic.json: frac unset"),
+                    "logical_bytes_per_launch": logical,
+                    "logical_gbs": logical / (per_launch_ms * 1e-3) / 1e9 if logical else None,
+                    "logical_frac": logical / (per_launch_ms * 1e-3) / 1e9 / peak if logical else None,
+                    "step_traffic": step_traffic or None,
+                    "step_dram_gbs": step_traffic / (ms_total / a.steps * 1e-3) / 1e9 if step_traffic else None,
+                    "step_frac": step_traffic / (ms_total / a.steps * 1e-3) / 1e9 / peak if step_traffic else None,
                     "step_logical_gbs": (fwd_b + bwd_b) * pairs_per_s / world / 1e9,
-                    "step_frac": (fwd_b + bwd_b) * pairs_per_s / world / 1e9 / peak,
-                    "achieved_dram": (traffic / (per_launch_ms * 1e-3) / 1e9 if traffic else None),
+                    "step_logical_frac": (fwd_b + bwd_b) * pairs_per_s / world / 1e9 / peak,
                     "note": ("entity table >> L2: gathers are served by HBM / NVLink peers" if sharded else
-                             "tables (<=30 MB) are L2-resident at this workload: `achieved` counts the logical (per-pair) "
-                             "gather bytes of SURVEY.md 8(d), `traffic` / `achieved_dram` the DRAM bytes ncu measured; "
-                             "where the per-entity leaf mode is active the K-row leaf gathers run once per distinct "
-                             "entity (leaf_entity kernels), so executed bytes are below the logical ones and frac can "
-                             "exceed 1")}
+                             "tables (<= 30 MB) are L2-resident at this workload and the per-entity leaf mode gathers each "
+                             "distinct leaf neighbourhood once, so the logical per-pair gather bytes of SURVEY.md 8(d) "
+                             "(logical_*) exceed what the kernels move; frac / step_frac are on executed DRAM bytes")}
+    if adam:
+        adam["frac"] = adam["gbs"] / peak
     cpu = None
     if world == 1 and not a.no_cpu_baseline and not sharded:
-        n_pairs = a.cpu_sample_pairs
+        n_pairs = cpu_sample_pairs(w, a.cpu_sample_pairs)
         v, t_step, cores = time_oracle(w, ds, n_pairs, 1, 1)
         reps = int(max(2, min(20, 15.0 / max(t_step, 1e-3))))
         v, t_step, cores = time_oracle(w, ds, n_pairs, reps, 0)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{n_pairs} pairs/step of {wl_key} x {reps} steps, torch-CPU fp32 oracle (op-for-op restatement "
-                         f"of the TF1 graph), fwd + autograd bwd"}
-    line = {"metric": METRIC, "value": pairs_per_s, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+                         f"of the TF1 graph), fwd + autograd bwd; sample bounded by host memory (~"
+                         f"{oracle_pair_bytes(w) / 2**20:.0f} MiB per pair) -- --impl reference times the same port with "
+                         f"its own time-sized sample"}
+    if dp_mode:
+        par = f"dp{world} replicas + grad all-reduce" if collective else f"dp{world} replicas (no collective: --no-allreduce)"
+    elif group_mode:
+        par = (f"dp{world}, entity table row-sharded over {world} GPUs (NVLink peer gathers / peer reductions), "
+               f"replicated-gradient all-reduce")
+    else:
+        par = "dp1"
+    line = {"metric": METRIC, "value": pairs_per_s, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": warmup,
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(wl_key, w, world), "pairs_per_step_per_gpu": B,
-                       "parallelism": (f"dp{world}, entity table row-sharded over {world} GPUs (NVLink peer gathers / "
-                                       f"peer reductions), replicated-gradient all-reduce" if group_mode else
-                                       f"dp{world} replicas" + (" + grad all-reduce" if flat_grads is not None else "")),
+            "config": {"workload": workload_name(wl_key, w, world), "pairs_per_step_per_gpu": B, "parallelism": par,
                        "l2": "flushed between timed steps (256 MiB write outside the event pairs)",
                        "init": "reference Xavier init, seed 1"},
             "e2e": {"value": e2e_pairs_per_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / a.steps},
+                    "ms_per_step": ms_e2e / a.steps,
+                    "path": "mvin_train_step_host (C ABI): pinned host feed -> H2D -> fwd + bwd -> 4 loss floats D2H"},
+            "e2e_api": e2e_api,
             "e2e_prefetch": (None if ms_e2e_pre is None else
                              {"value": world * B * a.steps / (ms_e2e_pre * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e_pre / a.steps,
@@ -451,21 +607,28 @@ def run_ours(a, w, wl_key):
                                  "note": "feed assembled on the GPU from bound ripple sets (mvin_train_step_users_host): "
                                          "only user / item / label cross the bus"}),
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "collective": collective, "adam": adam, "parity_check": parity,
             "kernels_ms_per_step": {k: round(v["ms_per_step"], 5) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms_per_step"])}}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        raise SystemExit(f"parity check failed: {parity}")
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--warmup", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
-    ap.add_argument("--allreduce", action="store_true", help="add the DP gradient all-reduce to every step (N > 1)")
+    ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-allreduce", action="store_true",
+                    help="N > 1 replicas: leave the DP gradient all-reduce out of the step (for A/B only)")
+    ap.add_argument("--allreduce", action="store_true", help=argparse.SUPPRESS)     # kept: now the default
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="device loop, e2e and kernel profile only")
     ap.add_argument("--cpu-sample-pairs", type=int, default=256)
     a = ap.parse_args()
     w = WORKLOADS[a.workload]

@@ -44,8 +44,13 @@ def _memories(model, d_users, user_triplet_set):
     bound, else stacked on the host the way get_feed_dict does (util.py:207-218) and uploaded."""
     if getattr(model, "_uts", None) is not None:
         return model.gather_feed(d_users)
-    uts = np.asarray(user_triplet_set)
-    blk = uts[d_users.cpu().numpy()]                                   # [B, p, 3, m]
+    from collections.abc import Mapping
+    users = d_users.cpu().numpy()
+    if isinstance(user_triplet_set, Mapping):
+        # the reference's defaultdict(user -> int32 [p, 3, m]) (data_loader_user_set.py:396-402), util.py:210-217
+        blk = np.stack([np.asarray(user_triplet_set[int(u)], dtype=np.int32) for u in users])
+    else:
+        blk = np.asarray(user_triplet_set)[users]                      # [B, p, 3, m]
     stack = lambda c: torch.from_numpy(np.ascontiguousarray(blk[:, :, c, :].transpose(1, 0, 2), dtype=np.int32)).to(
         model.device)
     return stack(0), stack(1), stack(2)

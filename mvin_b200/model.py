@@ -51,6 +51,25 @@ def flags_from_args(args) -> int:
     return f
 
 
+def pack_user_triplet_set(user_triplet_set, n_user, n_hops, n_memory) -> np.ndarray:
+    """The reference's ripple sets are a defaultdict(user -> int32 [p, 3, m]) (data_loader_user_set.py:396-402; users
+    without history are simply absent and the defaultdict would hand back []).  Returns the packed int32
+    [n_user, p, 3, m] array the device path binds; absent users get an all-zero block (they never occur in a batch:
+    every user of the rating file has history).  Arrays pass through."""
+    from collections.abc import Mapping
+    if isinstance(user_triplet_set, Mapping):
+        out = np.zeros((n_user, n_hops, 3, n_memory), dtype=np.int32)
+        for u in list(user_triplet_set.keys()):
+            blk = np.asarray(user_triplet_set[u], dtype=np.int32)
+            if blk.size == 0:
+                continue
+            if not 0 <= int(u) < n_user:
+                raise ValueError(f"user id {u} outside 0..{n_user - 1}")
+            out[int(u)] = blk.reshape(n_hops, 3, n_memory)
+        return out
+    return np.ascontiguousarray(np.asarray(user_triplet_set), dtype=np.int32)
+
+
 class MVIN(object):
     def __init__(self, args, n_user, n_entity, n_relation, adj_entity, adj_relation, device=None, seed: int = 1,
                  entity_shards: int = 1, process_group=None):
@@ -204,11 +223,25 @@ class MVIN(object):
             else:
                 self.params[name] = t[0]
         self.params = {k: self.params[k] for k in shapes}          # header field order
-        self.grads = {k: torch.zeros_like(v) for k, v in self.params.items() if not (G > 1 and k == "entity_emb")}
+        # Every gradient tensor is a view into ONE flat buffer (segments padded to 64 floats, so each view keeps the
+        # 16-byte alignment the C ABI asks for): the data-parallel gradient exchange is then a single in-place
+        # all-reduce of `grad_flat`, no gather / scatter copies.  The row-sharded entity gradient stays outside (peers
+        # reduce into it directly).
+        names = [k for k in shapes if not (G > 1 and k == "entity_emb")]
+        pad = lambda n: (n + 63) // 64 * 64
+        self.grad_flat = torch.zeros(sum(pad(self.params[k].numel()) for k in names) + 64, dtype=torch.float32,
+                                     device=self.device)
+        self.grads, off = {}, 0
+        for k in names:
+            n = self.params[k].numel()
+            self.grads[k] = self.grad_flat[off:off + n].view(self.params[k].shape)
+            off += pad(n)
+        self._user_grad_end = pad(self.params["user_emb"].numel())   # user_emb is the first segment
+        self.loss_slot = self.grad_flat[off:off + 4]                 # 4 loss scalars ride in the same bucket
         if G > 1:
             self._entity_grad_all = torch.zeros_like(self._entity_all)
             self.grads["entity_emb"] = self._entity_grad_all[0]
-            self.grads = {k: self.grads[k] for k in shapes}
+        self.grads = {k: self.grads[k] for k in shapes}
         self.adam_m = {k: torch.zeros_like(v) for k, v in self.params.items()}
         self.adam_v = {k: torch.zeros_like(v) for k, v in self.params.items()}
         self._p_struct = self._make_struct(self.params)
@@ -284,6 +317,7 @@ class MVIN(object):
         self._entity_grad_all.zero_()
         if self.group is not None:
             import torch.distributed as dist
+            torch.cuda.synchronize(self.device)      # the zero fill has landed before any peer may scatter into it
             dist.barrier(group=self.group)
 
     def end_step(self):
@@ -320,26 +354,50 @@ class MVIN(object):
         return torch.cuda.current_stream(self.device).cuda_stream
 
     # ------------------------------------------------------------------ feed handling (train.py:112-122)
-    def _host_feed(self, feed_dict):
-        users = np.ascontiguousarray(np.asarray(feed_dict[self.user_indices]), dtype=np.int64)
-        items = np.ascontiguousarray(np.asarray(feed_dict[self.item_indices]), dtype=np.int64)
-        B = items.shape[0]
-        labels = feed_dict.get(self.labels)
-        labels = (np.zeros(B, dtype=np.float32) if labels is None
-                  else np.ascontiguousarray(np.asarray(labels), dtype=np.float32))
-        n_mem = max(1, self.p_hop)
-        stack = lambda keys: np.ascontiguousarray(
-            np.stack([np.asarray(feed_dict[k], dtype=np.int32).reshape(B, self.n_memory) for k in keys]))
-        mem_h, mem_r, mem_t = stack(self.memories_h[:n_mem]), stack(self.memories_r[:n_mem]), stack(self.memories_t[:n_mem])
+    def _pinned_feed(self, B, slot):
+        """Page-locked host staging for the feed of one batch (two slots, used alternately by the prefetching train()):
+        the feed-dict values are converted straight into these buffers, so the H2D copy of the C ABI is a true
+        asynchronous DMA instead of a pageable copy."""
+        if getattr(self, "_pin", None) is None or self._pin_B != B:
+            n_mem = max(1, self.p_hop)
+            mk = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+            self._pin = [(mk((B,), torch.int64), mk((B,), torch.int64), mk((B,), torch.float32),
+                          mk((n_mem, B, self.n_memory), torch.int32), mk((n_mem, B, self.n_memory), torch.int32),
+                          mk((n_mem, B, self.n_memory), torch.int32)) for _ in range(2)]
+            self._pin_np = [tuple(t.numpy() for t in slot_t) for slot_t in self._pin]
+            self._pin_B = B
+        return self._pin_np[slot]
+
+    def _host_feed(self, feed_dict, slot=0):
+        """train.py:112-122 hands over NumPy slices for user / item / label and, per hop, either a Python list of B
+        int32 [m] rows or a [B, m] array; everything is written into pinned staging buffers (views returned)."""
+        items_in = np.asarray(feed_dict[self.item_indices])
+        B = items_in.shape[0]
         if B > self.batch_size:
             raise ValueError(f"batch of {B} exceeds args.batch_size = {self.batch_size} (static in the reference graph)")
+        users, items, labels, mem_h, mem_r, mem_t = self._pinned_feed(B, slot)
+        items[...] = items_in
+        users[...] = np.asarray(feed_dict[self.user_indices])
+        lab = feed_dict.get(self.labels)
+        if lab is None:
+            labels[...] = 0
+        else:
+            labels[...] = np.asarray(lab)
+        n_mem = max(1, self.p_hop)
+        for keys, dst in ((self.memories_h, mem_h), (self.memories_r, mem_r), (self.memories_t, mem_t)):
+            for hop in range(n_mem):
+                v = feed_dict[keys[hop]]
+                if isinstance(v, np.ndarray):
+                    dst[hop] = v.reshape(B, self.n_memory)
+                else:
+                    np.stack(v, out=dst[hop])             # list of B rows (train.py:118-120)
         return users, items, labels, mem_h, mem_r, mem_t
 
     def _device_feed(self, feed_dict):
         users, items, labels, mem_h, mem_r, mem_t = self._host_feed(feed_dict)
         to = lambda a: torch.from_numpy(a).to(self.device, non_blocking=False)
         self._dev_feed = tuple(to(a) for a in (users, items, labels, mem_h, mem_r, mem_t))   # keep alive for backward
-        return (users, items, labels) + self._dev_feed
+        return (users.copy(), items.copy(), labels.copy()) + self._dev_feed   # copies: the staging is re-used
 
     # ------------------------------------------------------------------ device-resident entry points
     def forward_device(self, users, items, mem_h, mem_r, mem_t, scores=None, scores_normalized=None):
@@ -427,7 +485,7 @@ class MVIN(object):
     def bind_user_triplet_set(self, user_triplet_set):
         """Upload the packed ripple sets once: int32 [n_user, max(1,p), 3, n_memory] (data_loader_user_set.py:402 stacks
         one [p, 3, m] block per user).  After this, train_users / gather_feed replace get_feed_dict (train.py:112-122)."""
-        uts = np.ascontiguousarray(np.asarray(user_triplet_set), dtype=np.int32)
+        uts = pack_user_triplet_set(user_triplet_set, self.n_user, max(1, self.p_hop), self.n_memory)
         want = (max(1, self.p_hop), 3, self.n_memory)
         if uts.ndim != 4 or tuple(uts.shape[1:]) != want:
             raise ValueError(f"user_triplet_set must be [n_user, {want[0]}, 3, {want[2]}], got {uts.shape}")
@@ -464,11 +522,23 @@ class MVIN(object):
         the sharded entity table, whose contributions already landed in the owners' shards through peer
         reductions, and the user table, which only carries its dense L2 term under --ablation all) and of the
         4 loss scalars."""
-        small = [self.grads[k] for k in self.grads if k not in ("entity_emb", "user_emb")]
-        extra = torch.as_tensor(losses if losses is not None else np.zeros(4, np.float32), dtype=torch.float32)
-        out = sharding.allreduce_flat(small, self.group, extra=extra)
+        import torch.distributed as dist
+        if losses is not None:
+            self.loss_slot.copy_(torch.as_tensor(losses, dtype=torch.float32))
+        dist.all_reduce(self.grad_flat[self._user_grad_end:], group=self.group)   # one bucket, in place
         self.grads["user_emb"].mul_(float(self.n_shards))
-        return out.cpu().numpy()
+        return self.loss_slot.cpu().numpy()
+
+    def allreduce_grads(self, group=None):
+        """Data-parallel replicas (tables replicated): ONE in-place SUM all-reduce of every gradient and
+        of the 4 loss scalars (`loss_slot`, where backward_device(labels, model.loss_slot) put them).  With
+        set_batch_scale(global batch, 1 / world) the result equals the single-device gradient on the concatenated
+        batch (tests/test_sharding_gloo.py checks the protocol)."""
+        import torch.distributed as dist
+        dist.all_reduce(self.grad_flat, group=group)
+
+    def set_batch_scale(self, global_batch: int, dense_l2_scale: float):
+        check(self.lib.mvin_set_batch_scale(self._handle, int(global_batch), float(dense_l2_scale)), "mvin_set_batch_scale")
 
     # ------------------------------------------------------------------ reference API (model.py:416-444)
     def train(self, sess, feed_dict):
@@ -568,14 +638,28 @@ class MVIN(object):
     def save_pretrain_emb_fuc(self, sess=None, saver=None):
         """model.py:66-67 / train.py:43-54: persists the user, entity, relation and relation-KGE tables."""
         path = self._emb_path()
-        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-        np.savez(path, **{k: self.params[k].cpu().numpy() for k in ("user_emb", "entity_emb", "relation_emb",
-                                                                    "relation_kge")})
+        tables = {k: self.params[k].cpu().numpy() for k in ("user_emb", "relation_emb", "relation_kge")}
+        # row-sharded entity table: the checkpoint holds the FULL table (train.py:43-54 saves entity_emb_matrix whole);
+        # every rank takes part in the gather, rank 0 alone writes
+        tables["entity_emb"] = (self._gather_entity_table(self._entity_all) if self.n_shards > 1
+                                else self.params["entity_emb"].cpu().numpy())
+        if self.rank == 0:
+            os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+            np.savez(path, **tables)
+        if self.group is not None:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)
 
     def load_pretrain_emb_fuc(self):
         z = np.load(self._emb_path())
-        for k in ("user_emb", "entity_emb", "relation_emb", "relation_kge"):
+        for k in ("user_emb", "relation_emb", "relation_kge"):
             self.params[k].copy_(torch.from_numpy(z[k]))
+        full = torch.from_numpy(z["entity_emb"])
+        if self.n_shards > 1:
+            self._scatter_entity_table(full, self._entity_all)
+        else:
+            self.params["entity_emb"].copy_(full)
+        torch.cuda.synchronize(self.device)
 
     # ------------------------------------------------------------------ test / interop helpers
     # oracle (reference attribute) name -> (field, index or None)
@@ -624,10 +708,35 @@ class MVIN(object):
             dist.all_gather(parts, shards[0].contiguous(), group=self.group)
         return sharding.gather_table(parts, self.n_entity).numpy().copy()
 
-    def _export(self, tensors) -> Dict[str, np.ndarray]:
+    def entity_rows(self, ids) -> np.ndarray:
+        """Rows `ids` (int64 NumPy) of the entity table as float32 [len, d] on the host, whatever its layout: one table,
+        virtual shards, or shards spread over the ranks of the process group -- then a COLLECTIVE: every rank calls it,
+        rank 0's ids are used and every rank gets the rows."""
+        G, dev = self.n_shards, self.device
+        ids_t = torch.from_numpy(np.ascontiguousarray(ids, dtype=np.int64)).to(dev)
+        if G == 1:
+            return self.params["entity_emb"][ids_t].cpu().numpy()
+        if self.group is None:
+            return self._entity_all[ids_t % G, ids_t // G].cpu().numpy()
+        import torch.distributed as dist
+        src = dist.get_global_rank(self.group, 0)
+        n = torch.tensor([ids_t.numel()], dtype=torch.int64, device=dev)
+        dist.broadcast(n, src=src, group=self.group)
+        if self.rank != 0:
+            ids_t = torch.empty(int(n.item()), dtype=torch.int64, device=dev)
+        dist.broadcast(ids_t, src=src, group=self.group)
+        out = torch.zeros((ids_t.numel(), self.dim), dtype=torch.float32, device=dev)
+        mine = (ids_t % G) == self.rank
+        out[mine] = self._entity_all[0][ids_t[mine] // G]
+        dist.all_reduce(out, group=self.group)
+        return out.cpu().numpy()
+
+    def _export(self, tensors, tables=True) -> Dict[str, np.ndarray]:
         from_shapes = {"h_emb_item_mlp_matrix": (2 * self.dim, 1), "h_emb_item_mlp_bias": (1,)}
         out = {}
         for name, (field, idx) in self._name_map().items():
+            if not tables and field in ("entity_emb", "user_emb"):
+                continue
             if field == "entity_emb" and self.n_shards > 1:
                 out[name] = self._gather_entity_table(self._entity_all if tensors is self.params
                                                       else self._entity_grad_all)
@@ -643,8 +752,9 @@ class MVIN(object):
             out[name] = a
         return out
 
-    def named_parameters(self):
-        return self._export(self.params)
+    def named_parameters(self, tables=True):
+        """Parameters under the reference's variable names; tables=False leaves out the entity and user tables."""
+        return self._export(self.params, tables)
 
     def named_gradients(self):
         return self._export(self.grads)

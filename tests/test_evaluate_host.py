@@ -151,3 +151,35 @@ def test_train_epoch_walks_full_batches_in_permuted_order():
         raise AssertionError("expected RuntimeError")
     except RuntimeError:
         pass
+
+
+def test_drivers_accept_the_reference_dict_of_ripple_sets():
+    """The reference's user_triplet_set is a defaultdict(user -> int32 [p, 3, m]) in which users without history are
+    absent (data_loader_user_set.py:396-402): the drivers index it per user (util.py:210-217) and the packer used by
+    MVIN.bind_user_triplet_set zero-fills absent users instead of tripping over the defaultdict's []."""
+    import collections
+    from mvin_b200.model import pack_user_triplet_set
+    uts = make_uts()
+    as_dict = collections.defaultdict(list)
+    for u in range(uts.shape[0]):
+        if u != 3:                                                   # user 3 has no history: absent from the mapping
+            as_dict[u] = uts[u]
+    packed = pack_user_triplet_set(as_dict, uts.shape[0], 2, 4)
+    assert packed.shape == uts.shape and packed.dtype == np.int32
+    assert np.array_equal(np.delete(packed, 3, axis=0), np.delete(uts, 3, axis=0)) and not packed[3].any()
+    assert 3 not in as_dict                                          # packing did not insert keys into the defaultdict
+    assert np.array_equal(pack_user_triplet_set(uts, uts.shape[0], 2, 4), uts)
+    # unbound model: the drivers stack the dict rows per batch, same scores as with the packed array
+    rng = np.random.RandomState(1)
+    users = rng.choice([u for u in range(12) if u != 3], 40)
+    data = np.stack([users, rng.randint(0, 23, 40), rng.randint(0, 2, 40)], axis=1)
+    res_arr = E.ctr_eval(None, None, None, StubModel(uts, False), data, uts, 16)
+    res_map = E.ctr_eval(None, None, None, StubModel(uts, False), data, as_dict, 16)
+    assert res_arr[0] == res_map[0] and res_arr[3] == res_map[3]
+    item_set = set(range(23))
+    train_record = {u: {u % 5, 7} for u in range(12)}
+    test_record = {1: {2, 3}, 4: {22}}
+    m1, m2 = StubModel(uts, False), StubModel(uts, False)
+    E.topk_eval(None, None, uts, m1, [1, 4], train_record, {}, test_record, item_set, [1, 5], 16)
+    E.topk_eval(None, None, as_dict, m2, [1, 4], train_record, {}, test_record, item_set, [1, 5], 16)
+    assert torch.equal(m1.captured[0], m2.captured[0])
