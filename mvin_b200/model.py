@@ -345,8 +345,14 @@ class MVIN(object):
             nbytes = self.lib.mvin_workspace_bytes(self._handle, B)
             if nbytes == 0:
                 raise _lib.MvinError("mvin_workspace_bytes returned 0")
-            self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            self._staging = torch.empty(self.lib.mvin_feed_bytes(self._handle, B), dtype=torch.uint8, device=self.device)
+            # the layout is recomputed from B by every call of the library, so a buffer that is large enough is kept
+            # (a smaller batch after a full one must not allocate a second multi-GB workspace)
+            if self._workspace is None or self._workspace.numel() < nbytes:
+                self._workspace = None
+                self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            fbytes = self.lib.mvin_feed_bytes(self._handle, B)
+            if self._staging is None or self._staging.numel() < fbytes:
+                self._staging = torch.empty(fbytes, dtype=torch.uint8, device=self.device)
             self._workspace_B = B
         return self._workspace
 

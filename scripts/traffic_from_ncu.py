@@ -23,9 +23,18 @@ def main():
     hdr, units = rows[0], rows[1]
     ki, ri, wi, ti = (hdr.index(k) for k in ("Kernel Name", "dram__bytes_read.sum", "dram__bytes_write.sum",
                                               "gpu__time_duration.sum"))
+    # a capture may hold several steps: keep the last complete one (seed_kernel opens a forward pass,
+    # finalize_loss_kernel closes the backward pass)
+    body = rows[2:]
+    starts = [i for i, r in enumerate(body) if "seed_kernel" in r[ki]]
+    ends = [i for i, r in enumerate(body) if "finalize_loss_kernel" in r[ki]]
+    if starts and ends:
+        e = ends[-1]
+        b = max(i for i in starts if i < e)
+        body = body[b:e + 1]
     fam = {}
     n_fwd_in = n_bwd_in = 0
-    for r in rows[2:]:
+    for r in body:
         name = r[ki]
         m = re.match(r"(?:void )?(\w+)<([^>]*)>", name)
         base, targs = (m.group(1), [t.strip() for t in m.group(2).split(",")]) if m else (name, [])

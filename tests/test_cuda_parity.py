@@ -210,31 +210,35 @@ def test_virtual_entity_shards_match_oracle(G, n_entity):
         model.train(None, fd)
 
 
-def _two_rank_worker(rank, port, ret):
+def _rank_worker(rank, world, port, ret):
     import os
     import torch.distributed as dist
     from mvin_b200 import MVIN, sharding
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=2, device_id=torch.device("cuda", rank))
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         Bg = 64
         args_g = make_args(dim=32, neighbor_sample_size=8, h_hop=2, p_hop=2, n_memory=16, batch_size=Bg)
         prob = make_problem(args_g, n_entity=301, seed=5)
-        args_l = make_args(dim=32, neighbor_sample_size=8, h_hop=2, p_hop=2, n_memory=16, batch_size=Bg // 2)
+        args_l = make_args(dim=32, neighbor_sample_size=8, h_hop=2, p_hop=2, n_memory=16, batch_size=Bg // world)
         model = MVIN(args_l, prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"],
-                     prob["adj_relation"], entity_shards=2, process_group=dist.group.WORLD)
+                     prob["adj_relation"], entity_shards=world, process_group=dist.group.WORLD)
         model.load_named_parameters({k: v.numpy() for k, v in prob["P"].items()})
-        sl = sharding.split_batch(Bg, rank, 2)
+        dist.barrier()                                       # every shard is loaded before any peer reads it
+        sl = sharding.split_batch(Bg, rank, world)
         local = dict(prob, users=prob["users"][sl], items=prob["items"][sl], labels=prob["labels"][sl],
                      mem_h=[m[sl] for m in prob["mem_h"]], mem_r=[m[sl] for m in prob["mem_r"]],
                      mem_t=[m[sl] for m in prob["mem_t"]])
         fd = feed_dict(model, local)
-        losses = model.loss_and_grads(fd)                    # summed over the ranks inside
         out, grads = orc.loss_and_grads(prob["P"], prob["cfg"], prob["adj_entity"], prob["adj_relation"],
                                         prob["users"], prob["items"], prob["mem_h"], prob["mem_r"], prob["mem_t"],
                                         prob["labels"])
-        ok = abs(float(losses[0]) - float(out.loss.detach())) <= 1e-4 * max(1.0, abs(float(out.loss.detach())))
+        # forward: this rank's scores come from rows gathered out of every peer's shard
+        score_err = rel_err(model.get_raw_scores(fd), out.scores.detach().numpy()[sl])
+        losses = model.loss_and_grads(fd)                    # summed over the ranks inside
+        ok = score_err < SCORE_TOL
+        ok = ok and abs(float(losses[0]) - float(out.loss.detach())) <= 1e-4 * max(1.0, abs(float(out.loss.detach())))
         got = model.named_gradients()
         bad = []
         for k, g in got.items():
@@ -244,19 +248,22 @@ def _two_rank_worker(rank, port, ret):
         # one Adam step on every rank keeps the replicated parameters identical and updates each shard
         model.train(None, fd)
         w = torch.from_numpy(model.named_parameters()["user_mlp_matrix"]).cuda()
-        both = [torch.empty_like(w) for _ in range(2)]
-        dist.all_gather(both, w)
-        ok = ok and torch.equal(both[0], both[1])
-        ret[rank] = (bool(ok), bad)
+        every = [torch.empty_like(w) for _ in range(world)]
+        dist.all_gather(every, w)
+        ok = ok and all(torch.equal(every[0], e) for e in every[1:])
+        ret[rank] = (bool(ok), bad, float(score_err))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_two_rank_sharded_entity_table_matches_oracle():
-    """One process per GPU, entity table row-sharded over the 2 ranks, peers' shards mapped through CUDA IPC:
-    NVLink peer loads in the forward pass and peer reductions in the backward pass give the oracle's gradients on
-    the concatenated batch."""
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_rank_sharded_entity_table_matches_oracle(world):
+    """One process per GPU, entity table row-sharded over the ranks, peers' shards reached over NVLink: the forward
+    scores, the summed loss and every gradient (each rank's entity-gradient shard included) equal the oracle's on the
+    concatenated batch; replicated parameters stay identical after an Adam step.  Needs `world` GPUs (gpurun --gpus N;
+    scripts/gpu_multi.sh runs it and commits the log under profiles/)."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (gpurun --gpus {world})")
     import socket
     import torch.multiprocessing as mp
     s = socket.socket()
@@ -265,15 +272,15 @@ def test_two_rank_sharded_entity_table_matches_oracle():
     s.close()
     ctx = mp.get_context("spawn")
     ret = ctx.Manager().dict()
-    procs = [ctx.Process(target=_two_rank_worker, args=(r, port, ret)) for r in range(2)]
+    procs = [ctx.Process(target=_rank_worker, args=(r, world, port, ret)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
         p.join(600)
         assert p.exitcode == 0
-    for r in range(2):
-        ok, bad = ret[r]
-        assert ok and not bad, (r, ok, bad)
+    for r in range(world):
+        ok, bad, score_err = ret[r]
+        assert ok and not bad, (r, ok, bad, score_err)
 
 
 @pytest.mark.parametrize("mode", ["0", "1"])

@@ -1,0 +1,210 @@
+"""GPU parity at the sizes the library switches code paths on (the small cases of test_cuda_parity.py never reach
+them): the tcgen05 forward row kernels (leaf level >= 131 072 rows), streaming access hints (level buffers >= 48 MB),
+the automatic per-entity leaf mode (>= n_entity / 4 depth-(L-1) nodes), byte offsets past 2^32 and element offsets past
+2^31 -- on synthetic graphs with the shipped datasets' shapes (mvin_b200/data.py).
+
+What is checked:
+  * C2 at full size (B = 4096, 182 011 entities): scores, loss and every gradient against the oracle directly.
+  * larger configurations, where the oracle cannot run the batch: (i) the scores of pairs from both ends of the batch
+    against the oracle on the extracted sub-problem (oracle/subproblem.py; the forward has no cross-pair term,
+    model.py:158) and the integer neighbour ids bit for bit; (ii) LINEARITY of the backward: with the base loss divided
+    by the full batch size and the dense L2 terms halved (mvin_set_batch_scale), the gradients of the two half batches
+    add up to the gradient of the full batch -- a half batch sits at half the buffer offsets, so a truncated offset or
+    a dropped tile shows as a mismatch; (iii) the two leaf-level implementations (per pair / per distinct entity)
+    against each other.
+Tolerances: scores 1e-4 relative (north_star); gradients 1e-4 of the largest entry of each tensor.
+"""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mvin_oracle as orc
+from oracle import subproblem
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _args(dataset, dim, H, K, B, p, m):
+    return types.SimpleNamespace(
+        dataset=dataset, load_pretrain_emb=False, h_hop=H, batch_size=B, neighbor_sample_size=K, p_hop=p, dim=dim,
+        l2_weight=1e-6, l2_agg_weight=1e-7, kge_weight=1e-2, lr=5e-3, save_model_name="t", n_mix_hop=1, n_memory=m,
+        update_item_emb="transform_matrix", h0_att="st_att_h_set", path=None, User_orient=1, User_orient_rela=1,
+        User_orient_kg_eh=1, PS_O_ft=1, wide_deep=1, PS_only=0, HO_only=0)
+
+
+_DS = {}
+
+
+def _dataset(name, K, p, m):
+    from mvin_b200 import data as D
+    key = (name, K, p, m)
+    if key not in _DS:
+        _DS[key] = D.make_synthetic_dataset(name, K, p, m, seed=2020, n_interactions=80_000)
+    return _DS[key]
+
+
+def _trained_scale(model, seed=3):
+    """N(0, 1/sqrt(d)) tables and N(0, 1/sqrt(fan_in)) weights (SURVEY.md 8(d) regime ii): scores of order 1, softmaxes
+    far from uniform, ReLUs half open -- a wrong row or weight shows up in the scores."""
+    gen = torch.Generator(device=model.device).manual_seed(seed)
+    d, H, p = model.dim, model.h_hop, model.p_hop
+    fan_in = {"user_emb": d, "entity_emb": d, "relation_emb": d, "relation_kge": d, "mix_w": (H + 1) * d,
+              "user_mlp_w": (p + 1) * d, "transfer_w": d, "agg_w": d, "agg_urh_w": 3 * d, "h_item_w": 2 * d}
+    for k, t in model.params.items():
+        if k in ("agg_b", "agg_urh_b"):
+            t.fill_(0.01)
+        elif k in fan_in:
+            t.normal_(0.0, 1.0 / float(np.sqrt(fan_in[k])), generator=gen)
+        else:
+            t.normal_(0.0, 0.1, generator=gen)                            # biases
+    torch.cuda.synchronize(model.device)
+
+
+def _batch(ds, B, offset=0):
+    from mvin_b200 import data as D
+    rows = ds["data"][offset:offset + B]
+    assert rows.shape[0] == B
+    mh, mr, mt = D.stacked_memories(ds["user_triplet_set"], rows[:, 0])
+    return (np.ascontiguousarray(rows[:, 0]), np.ascontiguousarray(rows[:, 1]),
+            np.ascontiguousarray(rows[:, 2].astype(np.float32)), mh, mr, mt)
+
+
+def _build(dataset, dim, H, K, B, p, m):
+    from mvin_b200 import MVIN
+    ds = _dataset(dataset, K, p, m)
+    shp = ds["shape"]
+    args = _args(dataset, dim, H, K, B, p, m)
+    model = MVIN(args, shp["n_user"], shp["n_entity"], shp["n_relation"], ds["adj_entity"], ds["adj_relation"])
+    _trained_scale(model)
+    return model, ds, args
+
+
+def _grads(model):
+    return {k: v.detach().clone() for k, v in model.grads.items()}
+
+
+def _spot_check(model, args, batch, n=8):
+    users, items, labels, mh, mr, mt = batch
+    B = items.shape[0]
+    dev = model.device
+    scores = torch.empty(B, dtype=torch.float32, device=dev)
+    d = [torch.from_numpy(x).to(dev) for x in (users, items, mh, mr, mt)]
+    model.forward_device(d[0], d[1], d[2], d[3], d[4], scores=scores)
+    torch.cuda.synchronize(dev)
+    idx = np.r_[0:n // 2, B - n // 2:B]                                  # both ends: smallest and largest offsets
+    res = subproblem.check_model_pairs(model, orc.OracleConfig.from_args(args), users, items, list(mh), list(mr), list(mt),
+                                       scores.cpu().numpy(), idx)
+    assert res["ids_bit_exact"], res
+    assert res["max_rel_err"] < 1e-4, res
+    return scores.cpu().numpy()
+
+
+def _assert_close(a, b, tol=1e-4):
+    bad = []
+    for k in a:
+        scale = max(float(b[k].abs().max()), 1e-12)
+        err = float((a[k] - b[k]).abs().max())
+        if not err <= tol * scale + 1e-9:
+            bad.append((k, err, scale))
+    assert not bad, bad
+
+
+def _linearity(model, batch):
+    """grad(full batch) == grad(first half) + grad(second half) under the data-parallel loss scaling."""
+    users, items, labels, mh, mr, mt = batch
+    B = items.shape[0]
+    h = B // 2
+    model.set_batch_scale(0, 1.0)
+    full_losses = model.train_step_host(users, items, labels, mh, mr, mt, apply_adam=False)
+    full = _grads(model)
+    model.set_batch_scale(B, 0.5)
+    parts, loss_sum = None, 0.0
+    for sl in (slice(0, h), slice(h, B)):
+        cut = lambda x: np.ascontiguousarray(x[:, sl]) if x.ndim == 3 else np.ascontiguousarray(x[sl])
+        losses = model.train_step_host(cut(users), cut(items), cut(labels), cut(mh), cut(mr), cut(mt), apply_adam=False)
+        loss_sum += float(losses[0])
+        g = _grads(model)
+        parts = g if parts is None else {k: parts[k] + g[k] for k in g}
+    model.set_batch_scale(0, 1.0)
+    assert abs(loss_sum - float(full_losses[0])) <= 1e-4 * max(1.0, abs(float(full_losses[0])))
+    _assert_close(parts, full)
+    return full
+
+
+def test_c2_full_size_matches_oracle():
+    """BASELINE.json configs[1] as it is benchmarked: B = 4096, 182 011 entities, d = 32, L = 2, K = 16."""
+    model, ds, args = _build("MovieLens-1M", 32, 2, 16, 4096, 2, 64)
+    batch = _batch(ds, 4096)
+    users, items, labels, mh, mr, mt = batch
+    P = {k: torch.as_tensor(v) for k, v in model.named_parameters().items()}
+    out, grads = orc.loss_and_grads(P, orc.OracleConfig.from_args(args), ds["adj_entity"], ds["adj_relation"], users, items,
+                                    list(mh), list(mr), list(mt), labels)
+    scores = _spot_check(model, args, batch)
+    assert rel_err(scores, out.scores.detach().numpy()) < 1e-4
+    losses = model.train_step_host(users, items, labels, mh, mr, mt, apply_adam=False)
+    assert abs(float(losses[0]) - float(out.loss.detach())) <= 1e-4 * max(1.0, abs(float(out.loss.detach())))
+    got = model.named_gradients()
+    bad = []
+    for k, g in got.items():
+        ref = grads[k].numpy().reshape(g.shape)
+        if not np.abs(g - ref).max() <= 1e-4 * max(np.abs(ref).max(), 1e-8) + 1e-8:
+            bad.append((k, float(np.abs(g - ref).max()), float(np.abs(ref).max())))
+    assert not bad, bad
+    ents, rels = model.get_neighbors(items)
+    for a, b in zip(ents + rels, out.entities + out.relations):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("B", [256, 8192])
+def test_c3_shape_size_triggered_branches(B, monkeypatch):
+    """last-fm shape, d = 64, L = 2, K = 32.  B = 256: 262 144 leaf-level rows -> tcgen05 forward kernels selected by
+    size, per-pair leaf gather (too few nodes for the entity mode).  B = 8192 (the BASELINE batch): 67 MB level buffers
+    -> streaming hints, automatic per-entity leaf mode; then the per-pair leaf mode forced on the same batch."""
+    for var in ("MVIN_B200_TC", "MVIN_B200_STREAM", "MVIN_B200_ENTITY_LEAF"):
+        monkeypatch.delenv(var, raising=False)
+    model, ds, args = _build("last-fm_50core", 64, 2, 32, B, 2, 64)
+    batch = _batch(ds, B)
+    _spot_check(model, args, batch)
+    auto = _linearity(model, batch)
+    if B == 8192:
+        monkeypatch.setenv("MVIN_B200_ENTITY_LEAF", "0")
+        other, _, _ = _build("last-fm_50core", 64, 2, 32, B, 2, 64)
+        _spot_check(other, args, batch)
+        other.train_step_host(*batch, apply_adam=False)
+        _assert_close(_grads(other), auto)
+
+
+def test_c4_shape_three_hops():
+    """amazon-book shape, d = 64, L = 3, K = 32 at B = 2048: 2.1 M level-2 rows (537 MB buffers, streaming, tcgen05
+    forward, per-entity leaf mode), every level of the three aggregator iterations in play."""
+    model, ds, args = _build("amazon-book_20core", 64, 3, 32, 2048, 1, 16)
+    batch = _batch(ds, 2048)
+    _spot_check(model, args, batch)
+    _linearity(model, batch)
+
+
+def test_offsets_beyond_2_to_31_elements():
+    """One level buffer of more than 2^31 floats (8.6 GB): d = 128, K = 32, L = 3, B = 16 400 -> 16.8 M level-2 rows x
+    128.  The checked pairs sit at both ends of the batch; the backward is checked through linearity."""
+    from mvin_b200 import MVIN
+    B, d, K = 16400, 128, 32
+    assert B * K * K * d > 2 ** 31
+    ds = _dataset("amazon-book_20core", K, 1, 16)
+    shp = ds["shape"]
+    args = _args("amazon-book_20core", d, 3, K, B, 1, 16)
+    model = MVIN(args, shp["n_user"], shp["n_entity"], shp["n_relation"], ds["adj_entity"], ds["adj_relation"])
+    need = model.lib.mvin_workspace_bytes(model._handle, B)
+    free, _ = torch.cuda.mem_get_info(model.device)
+    if need > 0.85 * free:
+        pytest.skip(f"workspace of {need / 2**30:.0f} GiB does not fit the free {free / 2**30:.0f} GiB")
+    _trained_scale(model)
+    rows = np.resize(ds["data"], (B, 3))
+    from mvin_b200 import data as D
+    mh, mr, mt = D.stacked_memories(ds["user_triplet_set"], rows[:, 0])
+    batch = (np.ascontiguousarray(rows[:, 0]), np.ascontiguousarray(rows[:, 1]),
+             np.ascontiguousarray(rows[:, 2].astype(np.float32)), mh, mr, mt)
+    _spot_check(model, args, batch)
+    _linearity(model, batch)

@@ -9,6 +9,12 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+def dw_lane(i: int, D: int) -> int:
+    """Accumulator lane of output row i of a tcgen05 MMA with M = 64 (cta_group::1): 16 rows per 32-lane quadrant
+    (measured by test_umma_dw_probe; see csrc/umma.cuh)."""
+    return 32 * (i // 16) + i % 16
+
+
 @pytest.mark.parametrize("D,M", [(32, 128), (64, 128), (64, 1000), (32, 333)])
 def test_umma_gemm_matches_fp64(D, M):
     from mvin_b200 import _lib
@@ -35,7 +41,6 @@ def test_umma_dw_probe(D, M):
     is NOT usable for kind::tf32 without swizzle -- the tensor core returns zeros -- which is why the weight
     gradients stay on the mma.sync path (level.cuh)."""
     from mvin_b200 import _lib
-    from mvin_b200.umma_layout import dw_lane
     lib = _lib.load()
     g = torch.Generator().manual_seed(7 * D + M)
     A = torch.randn(M, D, generator=g)
