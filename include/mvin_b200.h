@@ -252,6 +252,12 @@ int mvin_test_umma_gemm(const float* A, const float* W, float* C, int64_t M, int
 int mvin_test_umma_dw(const float* A, const float* G, float* dump, int64_t M, int32_t D, int32_t variant,
                       void* stream);
 
+/* Self-test of the split-bf16 tcgen05 block of the backward kernels (csrc/umma_bf.cuh): one tile buffer per operand serves
+ * both  C[M, D] = G . W^T  (contraction over features)  and  dW = A^T . G  (contraction over rows, accumulated over all
+ * 128-row tiles in tensor memory).  n_planes in {2, 3}; dump[128, D] receives the raw accumulator lanes of dW. */
+int mvin_test_umma_bf16(const float* A, const float* G, const float* W, float* C, float* dump, int64_t M, int32_t D,
+                        int32_t n_planes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

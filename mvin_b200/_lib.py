@@ -17,7 +17,7 @@ EXPORTS = ["mvin_abi_version", "mvin_last_error", "mvin_create", "mvin_destroy",
            "mvin_feed_bytes", "mvin_train_step_host", "mvin_launch_count", "mvin_profile_enable",
            "mvin_profile_read", "mvin_test_umma_gemm", "mvin_test_umma_dw", "mvin_bind_user_triplets", "mvin_gather_feed",
            "mvin_train_step_users_host", "mvin_ctr_metrics", "mvin_sample_adjacency", "mvin_build_ripple_sets", "mvin_feed_prefetch",
-           "mvin_train_step_prefetched", "mvin_topk_metrics"]
+           "mvin_train_step_prefetched", "mvin_topk_metrics", "mvin_test_umma_bf16"]
 
 
 class Config(C.Structure):
@@ -79,6 +79,7 @@ def load():
                                          C.POINTER(Params), C.c_float, i32, vp, vp]
     lib.mvin_test_umma_gemm.argtypes = [vp, vp, vp, C.c_int64, i32, vp]
     lib.mvin_test_umma_dw.argtypes = [vp, vp, vp, C.c_int64, i32, i32, vp]
+    lib.mvin_test_umma_bf16.argtypes = [vp, vp, vp, vp, vp, C.c_int64, i32, i32, vp]
     lib.mvin_bind_user_triplets.argtypes = [vp, vp]
     lib.mvin_gather_feed.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     lib.mvin_train_step_users_host.argtypes = [vp, vp, vp, vp, i32, vp, vp, C.POINTER(Params), C.POINTER(Params),

@@ -17,8 +17,10 @@
 #include "gemm.cuh"
 #include "level.cuh"
 #include "level_tc.cuh"
+#include "level_tcb.cuh"
 #include "misc.cuh"
 #include "umma.cuh"
+#include "umma_bf.cuh"
 #include "user.cuh"
 
 using namespace mvin;
@@ -151,6 +153,8 @@ struct mvin_handle_s {
   int user_pb_fwd = 4;             // max pairs per CTA of the user-side forward kernel (env MVIN_B200_USER_PB_FWD)
   int stream_mode = -1;            // -1 auto, 0 never, 1 always (env MVIN_B200_STREAM)
   int tc_mode = 1;                 // tcgen05 forward row kernels for d in {32, 64}: 0 never, 1 auto, 2 always (env MVIN_B200_TC)
+  int tcb_mode = 1;                // tcgen05 backward kernels of the deepest level (level_tcb.cuh): 0 never, 1 auto, 2 always
+                                   // (env MVIN_B200_TCBWD)
   int max_ctas_per_sm = 4;         // cap on resident CTAs per SM of the persistent row kernels (env MVIN_B200_CTAS_PER_SM)
   bool prof_on = false;
   struct ProfRec { const char* name; cudaEvent_t ev; };
@@ -373,6 +377,16 @@ inline bool use_tc_path(mvin_handle_t h, long leaf_rows) {
   if (h->tc_mode == 0) return false;
   if (h->tc_mode == 2) return true;
   return leaf_rows >= 131072;
+}
+
+// tcgen05 backward of the deepest materialised level (level_tcb.cuh): per-entity leaf mode, d in {32, 64}, at least two
+// levels, families of K = 2^j <= 64 rows (128-row tiles hold whole families); auto: from 131 072 rows at that level
+inline bool use_tc_bwd(mvin_handle_t h, const Layout& L, int D) {
+  const mvin_config_t& c = h->cfg;
+  const int K = c.neighbor_sample_size, H = c.h_hop;
+  if (h->tcb_mode == 0 || !L.entity_leaf || H < 2 || !(D == 32 || D == 64)) return false;
+  if (K > 64 || (K & (K - 1)) != 0 || h->n_shards != 1) return false;
+  return h->tcb_mode == 2 || L.rows[H - 1] >= 131072;
 }
 
 // activation buffers of a level that dwarf L2 (126 MB) are accessed with streaming hints (common.cuh, ld4a / st4a)

@@ -613,8 +613,8 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
           // entity mode: S depends on the node's entity only and was computed once per distinct entity
           // (leaf_entity_kernel)
           const long e = __ldg(L.ent + row);
-          o = f4add(ldg4(a.Se + e * D + tx * 4), ldg4(a.u + fastdiv(row, L.rpp_magic) * D + tx * 4));
-          st4a(L.SU + row * D + tx * 4, o, L.stream);
+          o = f4add(ldg4(a.Se + e * D + tx * 4), ldg4(a.u + fastdiv(row, L.rpp_magic) * D + tx * 4));   // not stored:
+                                                               // the backward recomputes S + u from the same table
         } else if (leaf) {
           const float4 uv = ldg4(a.u + fastdiv(row, L.rpp_magic) * D + tx * 4);
           const int2* nb = nb_s + r * KP;
@@ -701,10 +701,13 @@ struct AggBwdLevel {
   const float* g2;      // optional
   float* dself;         // [rows, D]
   float* dchild;        // inner: [rows*K, D]
+  float* gp;            // inner, defer: [rows, D] grow = gs / K of this level's rows (consumed by agg_bwd_leaf_tc_kernel)
   long rows;
   int rpp;
   unsigned long long rpp_magic;
   int leaf;
+  int defer;            // inner: the children's share (dchild, dp_k, ds) is evaluated by the tcgen05 leaf kernel of the
+                        // child level (level_tcb.cuh); this level only leaves `gp`
   int stream;           // level buffers >> L2: streaming (evict-first) activation accesses
 };
 struct AggBwdArgs {
@@ -723,6 +726,8 @@ struct AggBwdArgs {
   float* du;            // leaf: [B, D]
   float* ds;            // [n_rel]
   float* GSe;           // leaf, entity mode: [n_entity, D] per-entity sum of gsu (consumed by leaf_entity_bwd_kernel)
+  const float* Se;      // leaf, entity mode: [n_entity, D] (S + u is recomputed, not stored)
+  const float* u;       // leaf, entity mode: [B, D]
   int K, n_rel;
 };
 
@@ -775,7 +780,8 @@ __global__ void __launch_bounds__(TC<D>::NT, (D <= 64 ? 3 : 1)) agg_bwd_kernel(A
     had_leaf |= leaf;
     const long row0 = (t - (lvl ? a.tl.tile_end[lvl - 1] : 0)) * C::R;
     // ---- stage phase (its loads overlap the tile loads below) ----
-    if (!ent_mode) stage_tile<D, true>(L.ent, a.adj, s_s, row0, L.rows, K, KP, nb_s, rel_s, warp, lane);
+    const bool nbr_phase = !ent_mode && !L.defer;
+    if (nbr_phase) stage_tile<D, true>(L.ent, a.adj, s_s, row0, L.rows, K, KP, nb_s, rel_s, warp, lane);
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) {
       const int r = ty * C::TM + i;
@@ -809,7 +815,10 @@ __global__ void __launch_bounds__(TC<D>::NT, (D <= 64 ? 3 : 1)) agg_bwd_kernel(A
       float4 su = f4zero();
       if (row < L.rows) {
         st4a(L.dself + row * D + tx * 4, gs, L.stream);
-        if (leaf) su = ld4a(L.SU + row * D + tx * 4, L.stream);
+        if (ent_mode)
+          su = f4add(ldg4(a.Se + (long)__ldg(L.ent + row) * D + tx * 4), ldg4(a.u + fastdiv(row, L.rpp_magic) * D + tx * 4));
+        else if (leaf) su = ld4a(L.SU + row * D + tx * 4, L.stream);
+        if (L.defer) st4(L.gp + row * D + tx * 4, grow);
       }
       st4(&Gs[r * C::LD + tx * 4], grow);
       if (leaf) {
@@ -841,7 +850,7 @@ __global__ void __launch_bounds__(TC<D>::NT, (D <= 64 ? 3 : 1)) agg_bwd_kernel(A
     }
     // ---- neighbour phase: thread-mapped.  gr = dL/d(sum_k p_k x_k) of the thread's row; per neighbour k:
     //      dx_k = p_k gr (stored / scattered), dp_k = gr . x_k (W dot products reduced together) ----
-    if (!ent_mode) {
+    if (nbr_phase) {
       const int kl = lane & (C::W - 1);
 #pragma unroll
       for (int i = 0; i < C::TM; ++i) {

@@ -273,9 +273,7 @@ __global__ void __launch_bounds__(TT<D>::NT) agg_fwd_tc_kernel(AggArgs a) {
       }
 #pragma unroll
       for (int ps = 0; ps < T::NP; ++ps) {
-        const long row = row0 + ps * T::RP + ty;
-        const float4 o = f4add(xs[ps], xu[ps]);
-        if (row < L.rows) st4a(L.SU + row * D + tx * 4, o, L.stream);
+        const float4 o = f4add(xs[ps], xu[ps]);                // S + u: recomputed by the backward, not stored
         umma::store_split<D>(a_hi, a_lo, ps * T::RP + ty, tx, o);
       }
     } else {

@@ -131,6 +131,7 @@ int mvin_create(const mvin_config_t* cfg, mvin_handle_t* out) {
   if (const char* ev = getenv("MVIN_B200_ENTITY_LEAF")) h->entity_leaf_mode = atoi(ev) != 0 ? 1 : 0;
   if (const char* ev = getenv("MVIN_B200_USER_PB_FWD")) { const int n = atoi(ev); if (n == 1 || n == 2 || n == 4) h->user_pb_fwd = n; }
   if (const char* ev = getenv("MVIN_B200_TC")) { const int n = atoi(ev); if (n >= 0 && n <= 2) h->tc_mode = n; }
+  if (const char* ev = getenv("MVIN_B200_TCBWD")) { const int n = atoi(ev); if (n >= 0 && n <= 2) h->tcb_mode = n; }
   if (const char* ev = getenv("MVIN_B200_STREAM")) h->stream_mode = atoi(ev) != 0 ? 1 : 0;
   if (const char* ev = getenv("MVIN_B200_CTAS_PER_SM")) { const int n = atoi(ev); if (n >= 1 && n <= 32) h->max_ctas_per_sm = n; }
   if (cudaMalloc(&h->d_shard_tab, sizeof(void*) * 2 * MAX_SHARDS) != cudaSuccess ||
@@ -528,6 +529,27 @@ int mvin_test_umma_dw(const float* A, const float* G, float* dump, int64_t M, in
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(MVIN_ERR_CUDA, "launch umma_dw_test: %s", cudaGetErrorString(e));
+  return MVIN_OK;
+}
+
+int mvin_test_umma_bf16(const float* A, const float* G, const float* W, float* C, float* dump, int64_t M, int32_t D,
+                        int32_t n_planes, void* stream) {
+  if (!A || !G || !W || !C || !dump || M < 1) return fail(MVIN_ERR_INVALID, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+#define MVIN_BF_TEST(DD, NP)                                                                                  \
+  do {                                                                                                        \
+    if ((rc = set_smem(umma_bf_test_kernel<DD, NP>, umma_bf_test_smem<DD, NP>()))) return rc;                 \
+    MVIN_LAUNCH((umma_bf_test_kernel<DD, NP>), 1, 256, umma_bf_test_smem<DD, NP>(), st, A, G, W, C, dump, M); \
+  } while (0)
+  if (D == 64 && n_planes == 2) MVIN_BF_TEST(64, 2);
+  else if (D == 64 && n_planes == 3) MVIN_BF_TEST(64, 3);
+  else if (D == 32 && n_planes == 2) MVIN_BF_TEST(32, 2);
+  else if (D == 32 && n_planes == 3) MVIN_BF_TEST(32, 3);
+  else return fail(MVIN_ERR_UNSUPPORTED, "tcgen05 bf16 path: dim must be 32 or 64 and n_planes 2 or 3");
+#undef MVIN_BF_TEST
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MVIN_ERR_CUDA, "launch umma_bf_test: %s", cudaGetErrorString(e));
   return MVIN_OK;
 }
 

@@ -310,6 +310,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
   int rc;
   float* acc = at<float>(ws, L.acc);
   float* wT = at<float>(ws, L.wT);
+  const bool tcb = use_tc_bwd(h, L, D);
   prof_mark(h, st, nullptr);
 
   // part 0 (parameters only) on side stream 0 -- unless a host-step entry point already ran it during the feed copy
@@ -380,8 +381,9 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
       AggBwdArgs a;
       memset(&a, 0, sizeof(a));
       long rows[MAX_LV];
-      const int nlev = H - i;
-      const bool leaf_last = (i == 0 && L.entity_leaf);
+      const bool tcb0 = (i == 0 && tcb);                     // the leaf level goes to agg_bwd_leaf_tc_kernel
+      const int nlev = H - i - (tcb0 ? 1 : 0);
+      const bool leaf_last = (i == 0 && L.entity_leaf && !tcb0);
       for (int q = 0; q < nlev; ++q) {
         const int lv = leaf_last ? q : nlev - 1 - q;
         AggBwdLevel& t = a.lv[q];
@@ -398,6 +400,10 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
         } else {
           t.child = at<float>(ws, L.V[i][lv + 1]);
           t.dchild = at<float>(ws, L.DC[i][lv + 1]);
+          if (tcb0 && lv == H - 2) {                         // children's share deferred to the tcgen05 leaf kernel
+            t.defer = 1;
+            t.gp = at<float>(ws, L.DC[0][H - 1]);            // grow of this level's rows, in the unused dchild buffer
+          }
         }
       }
       a.adj = h->adj; a.s = at<float>(ws, L.s) + (long)i * nr;
@@ -405,12 +411,13 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
       a.dWa = G.agg_w + (long)i * D * D; a.dba = G.agg_b + (long)i * D;
       a.ds = at<float>(ws, L.ds) + (long)i * nr;
       a.K = K; a.n_rel = nr;
-      if (i == 0) {
+      if (i == 0 && !tcb0) {
         par.join(0);       // zeroed dE / GSe / dQ / cnt are first needed here
         a.E = h->etab; a.WtT = wT + (long)(H + H) * D * D;
         a.dWt = G.transfer_w + (long)H * D * D; a.dbt = G.transfer_b + (long)H * D;
         a.dE = h->gtab; a.du = du;
         a.GSe = L.entity_leaf ? at<float>(ws, L.GSe) : nullptr;
+        a.Se = L.entity_leaf ? at<float>(ws, L.Se) : nullptr; a.u = at<float>(ws, L.u);
         const int grid = make_tile_list(a.tl, rows, nlev, C::R,
                                         h->sm_count * resident_ctas(h, agg_bwd_kernel<D, true>, C::NT, sm_leaf), h->d_sched + 2);
         MVIN_LAUNCH((agg_bwd_kernel<D, true>), grid, C::NT, sm_leaf, st, a);
@@ -420,6 +427,33 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
         MVIN_LAUNCH((agg_bwd_kernel<D, false>), grid, C::NT, sm_in, st, a);
       }
       LAUNCH_CHECK(h, names[i]);
+      if constexpr (D == 32 || D == 64) {
+        if (tcb0) {
+          // deepest level of iteration 0 on the tensor cores (level_tcb.cuh): dself + the parents' dchild in one buffer
+          par.join(0);     // zeroed GSe / ds / du-side accumulators are first needed here
+          const int lv = H - 1;
+          LeafBwdArgs b;
+          memset(&b, 0, sizeof(b));
+          b.ent = at<int32_t>(ws, L.ent[lv]); b.ent_par = at<int32_t>(ws, L.ent[lv - 1]);
+          b.adj = h->adj; b.s = at<float>(ws, L.s);
+          b.g1 = at<float>(ws, L.DC[1][lv]); b.V1 = at<float>(ws, L.V[1][lv]); b.Y = at<float>(ws, L.Y[0][lv]);
+          b.T = at<float>(ws, L.V[0][lv]); b.GP = at<float>(ws, L.DC[0][lv]);
+          b.Se = at<float>(ws, L.Se); b.u = at<float>(ws, L.u);
+          b.Wa = P.agg_w; b.Wt = P.transfer_w + (long)H * D * D;
+          b.dT = at<float>(ws, L.DS[0][lv]);
+          b.dWa = G.agg_w; b.dba = G.agg_b; b.dWt = G.transfer_w + (long)H * D * D; b.dbt = G.transfer_b + (long)H * D;
+          b.GSe = at<float>(ws, L.GSe); b.du = du; b.ds = at<float>(ws, L.ds);
+          b.rows = L.rows[lv]; b.rpp = (int)(L.rows[lv] / B); b.rpp_magic = div_magic(b.rpp);
+          b.K = K; b.n_rel = nr; b.stream = stream_level(h, L.rows[lv], D);
+          while ((1 << b.kshift) < K) ++b.kshift;
+          const size_t smb = leaf_bwd_tc_smem<D>(nr);
+          if ((rc = set_smem(agg_bwd_leaf_tc_kernel<D>, smb))) return rc;
+          const long tiles = (b.rows + TB<D>::R - 1) / TB<D>::R;
+          const long cap = (long)h->sm_count * resident_ctas(h, agg_bwd_leaf_tc_kernel<D>, TB<D>::NT, smb);
+          MVIN_LAUNCH((agg_bwd_leaf_tc_kernel<D>), (unsigned)(tiles < cap ? tiles : cap), TB<D>::NT, smb, st, b);
+          LAUNCH_CHECK(h, "agg_bwd_leaf_tc");
+        }
+      }
     }
   }
   // side stream 0: per-entity leaf backward + relation-score gradients, while the user-oriented transform backward
@@ -455,15 +489,29 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
       const int lv = H - 1 - q;
       TransformLevel& t = a.lv[q];
       t.ent = at<int32_t>(ws, L.ent[lv]);
-      t.W = wT + (long)(H + lv) * D * D;
+      t.W = tcb ? P.transfer_w + (long)lv * D * D : wT + (long)(H + lv) * D * D;   // the tcgen05 kernel takes W_t[lv] as stored
       t.g1 = at<float>(ws, L.DC[0][lv]); t.g2 = at<float>(ws, L.DS[0][lv]);
+      if (tcb && lv == H - 1) { t.g1 = at<float>(ws, L.DS[0][lv]); t.g2 = nullptr; }   // one buffer: dself + dchild
       t.dW = G.transfer_w + (long)lv * D * D; t.db = G.transfer_b + (long)lv * D;
       t.rows = rows[q] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
         t.stream = stream_level(h, L.rows[lv], D);
     }
     a.nlev = H; a.E = h->etab; a.u = at<float>(ws, L.u); a.dE = h->gtab; a.du = du;
-    const int grid = partition_grid(rows, H, C::R, h->sm_count * resident_ctas(h, transform_bwd_kernel<D>, C::NT, sm), a.cta_end);
-    MVIN_LAUNCH((transform_bwd_kernel<D>), grid, C::NT, sm, st, a);
+    bool done = false;
+    if constexpr (D == 32 || D == 64) {
+      if (tcb) {
+        const size_t smt = transform_bwd_tc_smem<D>();
+        if ((rc = set_smem(transform_bwd_tc_kernel<D>, smt))) return rc;
+        const int grid = partition_grid(rows, H, TB<D>::R,
+                                        h->sm_count * resident_ctas(h, transform_bwd_tc_kernel<D>, TB<D>::NT, smt), a.cta_end);
+        MVIN_LAUNCH((transform_bwd_tc_kernel<D>), grid, TB<D>::NT, smt, st, a);
+        done = true;
+      }
+    }
+    if (!done) {
+      const int grid = partition_grid(rows, H, C::R, h->sm_count * resident_ctas(h, transform_bwd_kernel<D>, C::NT, sm), a.cta_end);
+      MVIN_LAUNCH((transform_bwd_kernel<D>), grid, C::NT, sm, st, a);
+    }
     LAUNCH_CHECK(h, "transform_bwd");
   }
   // user_o = O . W_user + b  backward

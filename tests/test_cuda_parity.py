@@ -135,6 +135,30 @@ def test_tcgen05_forward_kernels(dim, K, H, B, entity_leaf, monkeypatch):
     _assert_grads(model.named_gradients(), lambda k: grads[k].numpy())
 
 
+@pytest.mark.parametrize("dim,K,H,B,p", [(64, 32, 2, 40, 2), (32, 16, 2, 80, 2), (64, 8, 3, 5, 1), (32, 4, 2, 300, 2),
+                                         (64, 64, 2, 7, 1), (32, 1, 2, 9, 2), (64, 2, 3, 33, 0)])
+def test_tcgen05_backward_kernels(dim, K, H, B, p, monkeypatch):
+    """MVIN_B200_TCBWD=2 forces the tensor-core backward of the deepest level (level_tcb.cuh: split-bf16 tcgen05 products,
+    weight gradients accumulated in tensor memory, the parents' dchild folded into one dT buffer), which the library
+    otherwise selects from 131 072 rows on; it needs the per-entity leaf mode.  Partial tiles (rows not a multiple of
+    128), families of 1 .. 64 rows, two and three levels.  Gradient tolerance 1e-4 of the largest entry, as everywhere."""
+    from mvin_b200 import MVIN
+    monkeypatch.setenv("MVIN_B200_TCBWD", "2")
+    monkeypatch.setenv("MVIN_B200_ENTITY_LEAF", "1")
+    args = make_args(dim=dim, neighbor_sample_size=K, h_hop=H, p_hop=p, n_memory=16, batch_size=B)
+    prob = make_problem(args, n_entity=500 if K == 64 else 350, seed=5 * dim + K + H, hub_frac=0.2)
+    model = MVIN(args, prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"], prob["adj_relation"])
+    model.load_named_parameters({k: v.numpy() for k, v in prob["P"].items()})
+    fd = feed_dict(model, prob)
+    out, grads = orc.loss_and_grads(prob["P"], prob["cfg"], prob["adj_entity"], prob["adj_relation"], prob["users"],
+                                    prob["items"], prob["mem_h"], prob["mem_r"], prob["mem_t"], prob["labels"])
+    assert rel_err(model.get_raw_scores(fd), out.scores.detach().numpy()) < SCORE_TOL
+    for _ in range(2):                                       # second step: accumulators and tile buffers re-initialised
+        losses = model.loss_and_grads(fd)
+        assert abs(float(losses[0]) - float(out.loss.detach())) <= 1e-4 * max(1.0, abs(float(out.loss.detach())))
+        _assert_grads(model.named_gradients(), lambda k: grads[k].numpy())
+
+
 @pytest.mark.parametrize("dim,n_rel", [(64, 150), (16, 150)])
 def test_many_relations(dim, n_rel):
     """n_relation > 128: one shared ds histogram per CTA instead of one per warp; with dim 64 the relation-KGE table

@@ -56,3 +56,31 @@ def test_umma_dw_probe(D, M):
     got = dump.cpu().numpy()
     for i in range(D):
         assert np.abs(got[dw_lane(i, D)] - ref[i]).max() / scale < 5e-3, i      # one TF32 product: ~1e-3
+
+
+@pytest.mark.parametrize("D,M,NP", [(64, 128, 2), (64, 1000, 2), (64, 700, 3), (32, 333, 2), (32, 128, 3)])
+def test_umma_bf16_split_serves_both_contractions(D, M, NP):
+    """Split-bf16 operands (csrc/umma_bf.cuh): ONE staged tile per operand is the K-major operand of C = G . W^T and the
+    MN-major operand of dW = A^T . G (accumulated over the 128-row tiles in tensor memory).  NP = 2 planes keep 16
+    mantissa bits (error of order 1e-5 of the largest entry), NP = 3 all 24."""
+    from mvin_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(11 * D + M + NP)
+    A = torch.randn(M, D, generator=g)
+    G = torch.randn(M, D, generator=g) * (torch.rand(M, D, generator=g) > 0.4)          # ReLU-masked gradient
+    W = torch.randn(D, D, generator=g) / D ** 0.5
+    dA, dG, dW_ = A.cuda(), G.cuda(), W.cuda()
+    dC = torch.full((M, D), float("nan"), device="cuda")
+    dump = torch.full((128, D), float("nan"), device="cuda")
+    vp = ctypes.c_void_p
+    rc = lib.mvin_test_umma_bf16(vp(dA.data_ptr()), vp(dG.data_ptr()), vp(dW_.data_ptr()), vp(dC.data_ptr()),
+                                 vp(dump.data_ptr()), ctypes.c_int64(M), ctypes.c_int32(D), ctypes.c_int32(NP), None)
+    assert rc == 0, lib.mvin_last_error()
+    torch.cuda.synchronize()
+    tol = 3e-5 if NP == 2 else 2e-6
+    ref_c = (G.double() @ W.double().t()).numpy()
+    assert np.abs(dC.cpu().numpy() - ref_c).max() / np.abs(ref_c).max() < tol
+    ref_w = (A.double().t() @ G.double()).numpy()
+    got = dump.cpu().numpy()
+    for i in range(D):
+        assert np.abs(got[dw_lane(i, D)] - ref_w[i]).max() / np.abs(ref_w).max() < tol, i
