@@ -71,6 +71,15 @@ MVIN_DEV float4 f4fma(float s, float4 a, float4 c) {
 }
 MVIN_DEV float f4dot(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 
+// Bulk asynchronous L2 prefetch of a contiguous global range (cp.async.bulk.prefetch: the bulk-copy / TMA engine pulls
+// the range into L2 without occupying the issuing thread or any shared memory).  The row kernels walk level buffers
+// tile by tile -- 128 rows x 4d bytes, contiguous -- and issue the prefetch of the NEXT tile's streams while the
+// current tile is computed, so that the dependent 16-byte row loads of the next iteration hit L2.
+// addr 16-byte aligned, bytes a multiple of 16.
+MVIN_DEV void bulk_prefetch_l2(const void* addr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(addr), "r"(bytes) : "memory");
+}
+
 // vectorised reduction to global memory: one 16-byte red instead of four scalar atomics (sm_90+)
 MVIN_DEV void red_add4(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)

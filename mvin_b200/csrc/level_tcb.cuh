@@ -123,7 +123,8 @@ __global__ void __launch_bounds__(TB<D>::NT, 2) agg_bwd_leaf_tc_kernel(LeafBwdAr
   float* s_s = bias_s + 2 * D;                            // [n_rel]
   float* ds_s = s_s + a.n_rel;                            // [NW][n_rel]
   int* rel_s = reinterpret_cast<int*>(ds_s + T_::NW * a.n_rel);   // [R]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(rel_s + T_::R);
+  uint64_t* bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(rel_s + T_::R) + 7) & ~(uintptr_t)7);   // the float / int
+                                                          // arrays before it have an n_rel-dependent length
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32, tx = tid % T_::LPR, ty = tid / T_::LPR;
   const int K = a.K;
@@ -153,6 +154,14 @@ __global__ void __launch_bounds__(TB<D>::NT, 2) agg_bwd_leaf_tc_kernel(LeafBwdAr
 
   for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const long row0 = t * T_::R;
+    // next tile's four streams -> L2 through the bulk-copy engine (full tiles only: the range stays inside the buffers)
+    if (tid < 4) {
+      const long nrow0 = (t + gridDim.x) * T_::R;
+      if (nrow0 + T_::R <= a.rows) {
+        const float* base = tid == 0 ? a.g1 : tid == 1 ? a.V1 : tid == 2 ? a.Y : a.T;
+        bulk_prefetch_l2(base + nrow0 * D, T_::R * D * sizeof(float));
+      }
+    }
     // ---- family records: p_k and rel_k of every row of the tile (lanes of a warp = children of one parent) ----
     for (int f = warp; f < T_::R / K; f += T_::NW) {
       const long par = (row0 >> a.kshift) + f;
@@ -396,6 +405,11 @@ __global__ void __launch_bounds__(TB<D>::NT, 2) transform_bwd_tc_kernel(Transfor
   bool first = true;
   for (long t = cs.local; t < ntiles; t += cs.count) {
     const long row0 = t * T_::R;
+    if (tid < 2) {                                          // next tile's gradient rows -> L2 (bulk-copy engine)
+      const long nrow0 = (t + cs.count) * T_::R;
+      const float* base = tid == 0 ? L.g1 : L.g2;
+      if (base && nrow0 + T_::R <= L.rows) bulk_prefetch_l2(base + nrow0 * D, T_::R * D * sizeof(float));
+    }
 #pragma unroll
     for (int h = 0; h < T_::NPASS; h += 4) {
       float4 g[4], x[4], uu[4];

@@ -24,7 +24,24 @@ def _softmax(x):
     return torch.softmax(x, dim=-1)
 
 
-def fused_forward_backward(P, cfg, adj_entity, adj_relation, users, items, mem_h, mem_r, mem_t, labels=None):
+def fused_forward_backward(P, cfg, adj_entity, adj_relation, users, items, mem_h, mem_r, mem_t, labels=None,
+                           hoist_all=False, table=False):
+    """table: the ENTITY-TABLE form of aggregator iteration 0 (table.cuh), one step beyond hoist_all.  With the hoist at
+    every level, the pre-activation of iteration 0 at a level-h node with entity e of pair b is
+        pre = (E[e] + u_b) M1_h + (S_e + u_b) M2_h + c_h = A_h[e] + C_h[b]
+        M1_h = W_t[h] W_a0,  M2_h = W_t[h+1] W_a0 / K,  c_h = (b_t[h] + b_t[h+1] / K) W_a0 + b_a0
+    i.e. a per-ENTITY table A_h = E M1_h + Se M2_h + c_h plus a per-PAIR vector C_h = u (M1_h + M2_h): iteration 0 has no
+    per-row dense map at all, V[1][h][row] = relu(A_h[ent] + C_h[pair]) is a table gather, and the deepest level is never
+    materialised (iteration 1 gathers it from A_{H-1} through the adjacency record).  Backward: the pre-activation
+    gradients are summed per entity (dA_h) and per pair (dCs_h); everything below them is dense algebra on
+    [n_entity, d] / [B, d] matrices and a d x d parameter chain.
+
+    hoist_all: the ROW-LOCAL form of aggregator iteration 0 (level_tcb.cuh): the hoist that removes the leaf rows
+    (sum_k p_k = 1, attention relation-only) holds at EVERY level of iteration 0, because the children of a level-h node
+    with entity e are exactly adj[e] and their transformed rows are (E[n_k] + u) W_t[h+1] + b_t[h+1]:
+        agg_0[h] = ((S_e + u) W_t[h+1] + b_t[h+1]) / K,   S_e = sum_k p_k(e) E[adj[e][k]]   (one vector per ENTITY)
+    so iteration 0 needs no parent-child traffic at all, and its backward sends the children's share through the
+    per-entity gradient GSe[e] (then dE[adj[e][k]] += p_k GSe[e], dp_k = GSe[e] . E[adj[e][k]], once per entity)."""
     d, K, H, p, m = cfg.dim, cfg.neighbor_sample_size, cfg.h_hop, cfg.p_hop, cfg.n_memory
     assert cfg.n_mix_hop == 1
     L = H
@@ -85,9 +102,27 @@ def fused_forward_backward(P, cfg, adj_entity, adj_relation, users, items, mem_h
     S = (p0.unsqueeze(-1) * E[ent[L]].reshape(B, K ** (L - 1), K, d)).sum(2)
     SU = S + u.unsqueeze(1)
     Z = SU @ Wt[L] + bt[L]
+    if table:
+        hoist_all = False
+        p_ent = _softmax(s[0][adjR])
+        Se = (p_ent.unsqueeze(-1) * E[adjE]).sum(1)
+        M1 = [Wt[h] @ Wa[0] for h in range(H)]
+        M2 = [Wt[h + 1] @ Wa[0] / K for h in range(H)]
+        cst = [(bt[h] + bt[h + 1] / K) @ Wa[0] + ba[0] for h in range(H)]
+        A = [E @ M1[h] + Se @ M2[h] + cst[h] for h in range(H)]                # per-entity tables [n_entity, d]
+        Cp = [u @ (M1[h] + M2[h]) for h in range(H)]                           # per-pair [B, d]
+    if hoist_all:
+        p_ent = _softmax(s[0][adjR])                          # [n_entity, K] attention of aggregator 0 per ENTITY
+        Se = (p_ent.unsqueeze(-1) * E[adjE]).sum(1)           # [n_entity, d]
+        SUh = [Se[ent[h]] + u.unsqueeze(1) for h in range(L)]
     for i in range(H):
         for h in range(L - i):
-            if i == 0 and h == L - 1:
+            if i == 0 and table:
+                V[1][h] = torch.relu(A[h][ent[h]] + Cp[h].unsqueeze(1))
+                continue
+            if i == 0 and hoist_all:
+                agg = (SUh[h] @ Wt[h + 1] + bt[h + 1]) / K
+            elif i == 0 and h == L - 1:
                 agg = Z / K
             else:
                 agg = (att(i, h).unsqueeze(-1) * V[i][h + 1].reshape(B, K ** h, K, d)).sum(2) / K
@@ -145,6 +180,8 @@ def fused_forward_backward(P, cfg, adj_entity, adj_relation, users, items, mem_h
         dV[i][0] = dcat[:, i * d:(i + 1) * d].reshape(B, 1, d).clone()
     ds = [torch.zeros_like(s[i]) for i in range(H)]
     for i in reversed(range(H)):
+        if i == 0 and table:
+            break
         for h in range(L - i):                                # ascending hop: child grads land before self grads
             gout = dV[i + 1][h]
             gz = gout * (V[i + 1][h] > 0).to(dt)
@@ -154,6 +191,15 @@ def fused_forward_backward(P, cfg, adj_entity, adj_relation, users, items, mem_h
             dV[i][h] = dV[i][h] + gs if h in dV[i] else gs.clone()
             grow = gs / K                                     # [B,K^h,d]
             pk = att(i, h)
+            if i == 0 and hoist_all:
+                G[f"transfer_agg_matrix_{h + 1}"] += SUh[h].reshape(-1, d).T @ grow.reshape(-1, d)
+                G[f"transfer_agg_bias_{h + 1}"] += grow.reshape(-1, d).sum(0)
+                gsu = grow @ Wt[h + 1].T
+                du = du + gsu.sum(1)
+                if h == 0:
+                    GSe = torch.zeros_like(Se)
+                GSe.index_put_((ent[h].reshape(-1),), gsu.reshape(-1, d), accumulate=True)
+                continue                                      # no dchild, no per-row softmax gradient
             if i == 0 and h == L - 1:
                 G[f"transfer_agg_matrix_{L}"] += SU.reshape(-1, d).T @ grow.reshape(-1, d)
                 G[f"transfer_agg_bias_{L}"] += grow.reshape(-1, d).sum(0)
@@ -171,12 +217,39 @@ def fused_forward_backward(P, cfg, adj_entity, adj_relation, users, items, mem_h
                 dV[i][h + 1] = dchild
             dlogit = pk * (dp - (pk * dp).sum(-1, keepdim=True))
             ds[i].index_put_((rel[h].reshape(-1),), dlogit.reshape(-1), accumulate=True)
+    if table:
+        GSe = torch.zeros_like(Se)
+        dWa0, dba0 = G["agg_0_0_weights"], G["agg_0_0_bias"]
+        for h in range(H):
+            dpre = dV[1][h] * (V[1][h] > 0).to(dt)                             # [B, K^h, d]
+            dA = torch.zeros_like(Se).index_put_((ent[h].reshape(-1),), dpre.reshape(-1, d), accumulate=True)
+            dCs = dpre.sum(1)                                                  # [B, d]
+            dE += dA @ M1[h].T
+            GSe += dA @ M2[h].T
+            dM1 = E.T @ dA + u.T @ dCs
+            dM2 = Se.T @ dA + u.T @ dCs
+            dc = dCs.sum(0)
+            du = du + dCs @ (M1[h] + M2[h]).T
+            # d x d parameter chain
+            G[f"transfer_agg_matrix_{h}"] += dM1 @ Wa[0].T
+            G[f"transfer_agg_matrix_{h + 1}"] += dM2 @ Wa[0].T / K
+            dWa0 += Wt[h].T @ dM1 + Wt[h + 1].T @ dM2 / K + torch.outer(bt[h] + bt[h + 1] / K, dc)
+            G[f"transfer_agg_bias_{h}"] += dc @ Wa[0].T
+            G[f"transfer_agg_bias_{h + 1}"] += dc @ Wa[0].T / K
+            dba0 += dc
+    if hoist_all or table:
+        # per-entity backward of S_e (leaf_entity_kernel<BWD>): every entity that occurred at some level < L
+        child = E[adjE]                                       # [n_entity, K, d]
+        dp = (GSe.unsqueeze(1) * child).sum(-1)
+        dE.index_put_((adjE.reshape(-1),), (p_ent.unsqueeze(-1) * GSe.unsqueeze(1)).reshape(-1, d), accumulate=True)
+        dlogit = p_ent * (dp - (p_ent * dp).sum(-1, keepdim=True))
+        ds[0].index_put_((adjR.reshape(-1),), dlogit.reshape(-1), accumulate=True)
     for i in range(H):
         wr = P[f"agg_{i}_0_urh_weights"][d:2 * d, 0]
         G["relation_emb_matrix"] += ds[i].unsqueeze(-1) * wr
         G[f"agg_{i}_0_urh_weights"][d:2 * d, 0] += ds[i] @ Rel
     # user-oriented transform, levels 0..L-1
-    for h in range(L):
+    for h in range(1 if table else L):
         dT = dV[0][h]
         G[f"transfer_agg_matrix_{h}"] += XU[h].reshape(-1, d).T @ dT.reshape(-1, d)
         G[f"transfer_agg_bias_{h}"] += dT.reshape(-1, d).sum(0)

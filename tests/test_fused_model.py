@@ -11,15 +11,17 @@ from tests.helpers import load_golden, rel_err
 SUPPORTED = ["h1_m1_p2", "h2_m1_p2", "h2_m1_p2_xavier", "h3_m1_p1"]
 
 
+@pytest.mark.parametrize("hoist_all", [False, True, "table"])
 @pytest.mark.parametrize("case", SUPPORTED)
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-def test_fused_matches_oracle(case, dtype):
+def test_fused_matches_oracle(case, dtype, hoist_all):
     z, args, cfg, feed, P = load_golden(case)
     P = {k: v.to(dtype) for k, v in P.items()}
     out, grads = orc.loss_and_grads(P, cfg, z["adj_entity"], z["adj_relation"], feed["users"], feed["items"],
                                     feed["mem_h"], feed["mem_r"], feed["mem_t"], feed["labels"])
     W, G = fused_forward_backward(P, cfg, z["adj_entity"], z["adj_relation"], feed["users"], feed["items"],
-                                  feed["mem_h"], feed["mem_r"], feed["mem_t"], feed["labels"])
+                                  feed["mem_h"], feed["mem_r"], feed["mem_t"], feed["labels"], hoist_all=hoist_all is True,
+                                  table=hoist_all == "table")
     tol = 1e-10 if dtype == torch.float64 else 2e-5
     assert rel_err(W["scores"].numpy(), out.scores.detach().numpy()) < tol
     assert abs(float(W["loss"]) - float(out.loss)) < tol * max(1.0, abs(float(out.loss)))
