@@ -563,9 +563,12 @@ def run_ours(a, w, wl_key):
                     "step_logical_gbs": (fwd_b + bwd_b) * pairs_per_s / world / 1e9,
                     "step_logical_frac": (fwd_b + bwd_b) * pairs_per_s / world / 1e9 / peak,
                     "note": ("entity table >> L2: gathers are served by HBM / NVLink peers" if sharded else
-                             "tables (<= 30 MB) are L2-resident at this workload and the per-entity leaf mode gathers each "
-                             "distinct leaf neighbourhood once, so the logical per-pair gather bytes of SURVEY.md 8(d) "
-                             "(logical_*) exceed what the kernels move; frac / step_frac are on executed DRAM bytes")}
+                             "tables (<= 30 MB) are L2-resident at this workload; aggregator iteration 0 is evaluated per "
+                             "distinct ENTITY (table.cuh: A_h = E M1_h + Se M2_h + c_h) and the deepest level is gathered "
+                             "from that table instead of being materialised, so the logical per-pair gather bytes of "
+                             "SURVEY.md 8(d) (logical_*) far exceed what the kernels move through HBM; frac / step_frac "
+                             "are on executed DRAM bytes, and the dominant kernel is bound by L2 gathers + red.global.add "
+                             "issue rate, not by HBM")}
     if adam:
         adam["frac"] = adam["gbs"] / peak
     cpu = None

@@ -19,6 +19,7 @@
 #include "level_tc.cuh"
 #include "level_tcb.cuh"
 #include "misc.cuh"
+#include "table.cuh"
 #include "umma.cuh"
 #include "umma_bf.cuh"
 #include "user.cuh"
@@ -107,6 +108,10 @@ struct Layout {
                                           // [begin, mid) on the launch stream, [mid, end) on a side stream
   size_t stamp, Se;                       // entity mode of the leaf level (stamp is cleared by every forward)
   bool entity_leaf;
+  // table mode (table.cuh): composed maps, per-entity tables A_h, per-pair vectors C_h and their gradients
+  bool table;
+  size_t Mc, cst, Atab, Cp;               // [H][TBL_NM][D][D], [H][D], [H][n_entity][D], [H][B][D]
+  size_t dA, dCs, dM, dcst;               // [H][n_entity][D], [H][B][D], [H][3][D][D], [H][D]   (inside the zeroed region)
   size_t total;
   long rows[MAX_L + 1];
 };
@@ -153,6 +158,8 @@ struct mvin_handle_s {
   int user_pb_fwd = 4;             // max pairs per CTA of the user-side forward kernel (env MVIN_B200_USER_PB_FWD)
   int stream_mode = -1;            // -1 auto, 0 never, 1 always (env MVIN_B200_STREAM)
   int tc_mode = 1;                 // tcgen05 forward row kernels for d in {32, 64}: 0 never, 1 auto, 2 always (env MVIN_B200_TC)
+  int table_mode = -1;             // entity-table form of aggregator iteration 0 (table.cuh): -1 auto, 0 off, 1 on
+                                   // (env MVIN_B200_TABLE)
   int tcb_mode = 1;                // tcgen05 backward kernels of the deepest level (level_tcb.cuh): 0 never, 1 auto, 2 always
                                    // (env MVIN_B200_TCBWD)
   int max_ctas_per_sm = 4;         // cap on resident CTAs per SM of the persistent row kernels (env MVIN_B200_CTAS_PER_SM)
@@ -211,10 +218,35 @@ inline bool use_entity_leaf(const mvin_config_t& c, long B, int n_shards, int mo
   return n_shards == 1 && rows * 4 >= (long)c.n_entity && (long)c.n_entity * c.dim * 8 <= (2L << 30);
 }
 
-inline Layout make_layout(const mvin_config_t& c, long B, bool entity_leaf) {
+// Table mode (table.cuh) replaces the per-row evaluation of aggregator iteration 0 -- and with it the deepest level's
+// buffers -- by per-entity tables.  Same applicability as the entity mode of the leaf level (one shard, the batch re-uses
+// entities); MVIN_B200_TABLE=0 / 1 forces it off / on, an explicit MVIN_B200_ENTITY_LEAF selects the row kernels.
+inline bool use_table(const mvin_config_t& c, long B, int n_shards, int table_mode, int entity_leaf_mode) {
+  if (n_shards != 1 || table_mode == 0) return false;
+  if ((long)c.n_entity * c.dim * 4 * (2 * c.h_hop + 2) > (8L << 30)) return false;
+  if (table_mode == 1) return true;
+  // automatic: when the deepest level has at least one row per entity of the graph (rows per entity at C3: 2.5, C4: 148;
+  // measured: C3 1.15 vs 1.42 ms, C4 5.4 vs 38.9 ms per step.  At C2, 0.36 rows per entity, the table kernels' walk over
+  // all 182 011 entities costs more than the 65 536 leaf rows it replaces: 0.49 vs 0.35 ms)
+  long rows = B;
+  for (int h = 1; h < c.h_hop; ++h) rows *= c.neighbor_sample_size;
+  return entity_leaf_mode == -1 && rows >= (long)c.n_entity;
+}
+
+// buffer V[j][h] (and its gradient) exists in table mode: T[0] for the mix layer, the iteration-0 outputs of every
+// level but the deepest, everything of the later iterations
+inline bool tab_has_V(int H, int j, int h) {
+  if (j == 0) return h == 0;
+  if (j == 1) return h == 0 || h <= H - 2;
+  return h <= H - j;
+}
+
+inline Layout make_layout(const mvin_config_t& c, long B, bool entity_leaf, bool table = false) {
   Layout L;
   memset(&L, 0, sizeof(L));
+  if (table) entity_leaf = true;           // Se / GSe / stamp are shared with the entity mode of the leaf level
   L.entity_leaf = entity_leaf;
+  L.table = table;
   const long D = c.dim, K = c.neighbor_sample_size, H = c.h_hop, p = c.p_hop, m = c.n_memory, nr = c.n_relation;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -232,21 +264,28 @@ inline Layout make_layout(const mvin_config_t& c, long B, bool entity_leaf) {
   L.O = take(f * B * (p + 1) * D);
   L.u = take(f * B * D);
   L.s = take(f * H * nr);
-  L.SU = take(f * L.rows[H - 1] * D);
+  if (!table) L.SU = take(f * L.rows[H - 1] * D);
+  auto exists = [&](int j, int h) { return table ? (h < H && tab_has_V(H, j, h)) : has_V(H, j, h); };
   const size_t vtop = take(f * (H + 1) * B * D);
   for (int j = 0; j <= H; ++j)
     for (int h = 0; h < MAX_L; ++h)
-      if (has_V(H, j, h)) L.V[j][h] = h == 0 ? vtop + f * j * B * D : take(f * L.rows[h] * D);
-  for (int i = 0; i < H; ++i)
+      if (exists(j, h)) L.V[j][h] = h == 0 ? vtop + f * j * B * D : take(f * L.rows[h] * D);
+  for (int i = table ? 1 : 0; i < H; ++i)
     for (int h = 0; h < H - i; ++h) L.Y[i][h] = take(f * L.rows[h] * D);
   L.item = take(f * B * D);
   L.scores = take(f * B);
   const size_t dtop = take(f * (H + 1) * B * D);
   for (int j = 0; j <= H; ++j)
     for (int h = 0; h < MAX_L; ++h)
-      if (has_V(H, j, h)) L.DC[j][h] = h == 0 ? dtop + f * j * B * D : take(f * L.rows[h] * D);
-  for (int i = 0; i < H; ++i)
+      if (exists(j, h)) L.DC[j][h] = h == 0 ? dtop + f * j * B * D : take(f * L.rows[h] * D);
+  for (int i = table ? 1 : 0; i < H; ++i)
     for (int h = 0; h < H - i; ++h) L.DS[i][h] = take(f * L.rows[h] * D);
+  if (table) {
+    L.Mc = take(f * H * TBL_NM * D * D);
+    L.cst = take(f * H * D);
+    L.Atab = take(f * H * (size_t)c.n_entity * D);
+    L.Cp = take(f * H * B * D);
+  }
   L.du = take(f * B * D);
   L.ditem = take(f * B * D);
   L.dO = take(f * B * (p + 1) * D);
@@ -259,6 +298,12 @@ inline Layout make_layout(const mvin_config_t& c, long B, bool entity_leaf) {
   L.dQ = take(f * B * nr * D);
   L.dv = take(f * B * D);
   if (entity_leaf) L.GSe = take(f * (size_t)c.n_entity * D);
+  if (table) {
+    L.dA = take(f * H * (size_t)c.n_entity * D);
+    L.dCs = take(f * H * B * D);
+    L.dM = take(f * H * 3 * D * D);
+    L.dcst = take(f * H * D);
+  }
   L.zero_end = off;
   if (entity_leaf) {
     L.stamp = take(sizeof(int32_t) * (size_t)c.n_entity);
@@ -266,6 +311,11 @@ inline Layout make_layout(const mvin_config_t& c, long B, bool entity_leaf) {
   }
   L.total = off;
   return L;
+}
+
+inline Layout handle_layout(const mvin_handle_s* h, long B) {
+  const bool table = use_table(h->cfg, B, h->n_shards, h->table_mode, h->entity_leaf_mode);
+  return make_layout(h->cfg, B, use_entity_leaf(h->cfg, B, h->n_shards, h->entity_leaf_mode), table);
 }
 
 template <typename T>
@@ -387,6 +437,14 @@ inline bool use_tc_bwd(mvin_handle_t h, const Layout& L, int D) {
   if (h->tcb_mode == 0 || !L.entity_leaf || H < 2 || !(D == 32 || D == 64)) return false;
   if (K > 64 || (K & (K - 1)) != 0 || h->n_shards != 1) return false;
   return h->tcb_mode == 2 || L.rows[H - 1] >= 131072;
+}
+
+// leaf_entity_kernel: entities per warp visit, sized so that the launch has about 32 warps per SM
+inline int leaf_chunk(mvin_handle_t h, long n_entity) {
+  const long warps = (long)h->sm_count * 32;
+  int chunk = 32;
+  while (chunk > 1 && n_entity / chunk < warps) chunk >>= 1;
+  return chunk;
 }
 
 // activation buffers of a level that dwarf L2 (126 MB) are accessed with streaming hints (common.cuh, ld4a / st4a)

@@ -527,6 +527,11 @@ struct AggLevel {
   unsigned long long rpp_magic;
   int leaf;
   int stream;           // level buffers >> L2: streaming (evict-first) activation accesses
+  // table mode (table.cuh): the children are not rows of a buffer but  relu(tab[id_k] + Cp[pair])  with id_k from the
+  // node's adjacency record -- iteration 0 of the child level evaluated on the fly from its per-entity table
+  int virt;
+  const float* tab;     // [n_entity, D]  A_{h+1}
+  const float* Cp;      // [B, D]         C_{h+1}
 };
 struct AggArgs {
   AggLevel lv[MAX_LV];
@@ -626,6 +631,20 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
           }
           o = f4add(acc, uv);
           st4a(L.SU + row * D + tx * 4, o, L.stream);
+        } else if (L.virt) {
+          const float4 sv = ld4a(L.self + row * D + tx * 4, L.stream);
+          const float4 cv = ldg4(L.Cp + fastdiv(row, L.rpp_magic) * D + tx * 4);
+          const int2* nb = nb_s + r * KP;
+          const float* base = L.tab + tx * 4;
+          float4 acc = f4zero();
+#pragma unroll 8
+          for (int k = 0; k < K; ++k) {
+            const int2 v = nb[k];
+            const float4 x = f4add(ldg4(base + (long)v.y * D), cv);
+            acc = f4fma(__int_as_float(v.x), make_float4(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f)), acc);
+          }
+          o = f4fma(invK, acc, sv);
+          st4a(L.Y + row * D + tx * 4, o, L.stream);
         } else {
           const float4 sv = ld4a(L.self + row * D + tx * 4, L.stream);
           const int2* nb = nb_s + r * KP;
@@ -709,6 +728,13 @@ struct AggBwdLevel {
   int defer;            // inner: the children's share (dchild, dp_k, ds) is evaluated by the tcgen05 leaf kernel of the
                         // child level (level_tcb.cuh); this level only leaves `gp`
   int stream;           // level buffers >> L2: streaming (evict-first) activation accesses
+  // table mode (table.cuh): children = relu(tab[id_k] + Cp[pair]) recomputed; their pre-activation gradient
+  // p_k grow * [child > 0] is summed per entity (dtab) and per pair (dCs)
+  int virt;
+  const float* tab;     // [n_entity, D]
+  const float* Cp;      // [B, D]
+  float* dtab;          // [n_entity, D] (+=)
+  float* dCs;           // [B, D] (+=)
 };
 struct AggBwdArgs {
   AggBwdLevel lv[MAX_LV];
@@ -852,12 +878,16 @@ __global__ void __launch_bounds__(TC<D>::NT, (D <= 64 ? 3 : 1)) agg_bwd_kernel(A
     //      dx_k = p_k gr (stored / scattered), dp_k = gr . x_k (W dot products reduced together) ----
     if (nbr_phase) {
       const int kl = lane & (C::W - 1);
+      float4 cs[C::TM];                                      // virt: per-row sum of the children's pre-activation gradients
 #pragma unroll
       for (int i = 0; i < C::TM; ++i) {
         const int r = ty * C::TM + i;
         const long row = row0 + r;
         const bool valid = row < L.rows;
         const float4 gr = ld4(&Gs[r * C::LD + tx * 4]);
+        cs[i] = f4zero();
+        float4 cv = f4zero();
+        if (L.virt && valid) cv = ldg4(L.Cp + fastdiv(row, L.rpp_magic) * D + tx * 4);
         const int2* nb = nb_s + r * KP;
         float dp[C::NKW];
 #pragma unroll
@@ -874,7 +904,10 @@ __global__ void __launch_bounds__(TC<D>::NT, (D <= 64 ? 3 : 1)) agg_bwd_kernel(A
               if (valid && k < K) {
                 v[j] = nb[k];
                 if (leaf) x[j] = ldg4(erow(a.E, v[j].y, D) + tx * 4);
-                else x[j] = ld4a(L.child + (row * K + k) * D + tx * 4, L.stream);
+                else if (L.virt) {
+                  const float4 t = f4add(ldg4(L.tab + (long)v[j].y * D + tx * 4), cv);
+                  x[j] = make_float4(fmaxf(t.x, 0.f), fmaxf(t.y, 0.f), fmaxf(t.z, 0.f), fmaxf(t.w, 0.f));
+                } else x[j] = ld4a(L.child + (row * K + k) * D + tx * 4, L.stream);
               }
             }
             float part[C::W];
@@ -883,9 +916,14 @@ __global__ void __launch_bounds__(TC<D>::NT, (D <= 64 ? 3 : 1)) agg_bwd_kernel(A
               const int k = c * C::W + j;
               part[j] = f4dot(gr, x[j]);
               if (valid && k < K) {
-                const float4 dx = f4scale(gr, __int_as_float(v[j].x));
+                float4 dx = f4scale(gr, __int_as_float(v[j].x));
                 if (leaf) red_add4(grow_of(a.dE, v[j].y, D) + tx * 4, dx);
-                else st4a(L.dchild + (row * K + k) * D + tx * 4, dx, L.stream);
+                else if (L.virt) {
+                  dx = make_float4(x[j].x > 0.f ? dx.x : 0.f, x[j].y > 0.f ? dx.y : 0.f, x[j].z > 0.f ? dx.z : 0.f,
+                                   x[j].w > 0.f ? dx.w : 0.f);
+                  red_add4(L.dtab + (long)v[j].y * D + tx * 4, dx);
+                  cs[i] = f4add(cs[i], dx);
+                } else st4a(L.dchild + (row * K + k) * D + tx * 4, dx, L.stream);
               }
             }
             dp[c] = reduce_scatter<C::W, C::LPR>(part, lane);   // dp of k = c*W + kl
@@ -908,6 +946,7 @@ __global__ void __launch_bounds__(TC<D>::NT, (D <= 64 ? 3 : 1)) agg_bwd_kernel(A
           }
         }
       }
+      if (L.virt) pair_accumulate<D>(cs, L.dCs, row0, L.rows, L.rpp, L.rpp_magic, ty, tx, lane);   // CTA-uniform branch
     }
     if (tid == 0) sched[(it + 1) & 1] = nxt;
     __syncthreads();
@@ -951,6 +990,7 @@ struct LeafEntArgs {
   GTab dE;
   float* ds;            // [n_rel]
   int n_entity, K, n_rel;
+  int chunk;            // entities per warp visit (power of two <= 32): small graphs get one warp per few entities
 };
 constexpr int LEAF_NT = 256, LEAF_NW = LEAF_NT / 32;
 MVIN_HD int leaf_ds_copies(int n_rel) { return n_rel <= 128 ? LEAF_NW : 1; }
@@ -968,8 +1008,8 @@ MVIN_DEV AdjRec load_adj(const int32_t* __restrict__ adj, long e, int K, int lan
   return r;
 }
 
-// One warp per chunk of 32 consecutive entities: one coalesced read of their stamps, then the marked ones in turn
-// (the adjacency record of the next marked entity is fetched while the current one is processed).
+// One warp per chunk of `chunk` (<= 32) consecutive entities: one coalesced read of their stamps, then the marked ones in
+// turn (the adjacency record of the next marked entity is fetched while the current one is processed).
 template <int D, bool BWD>
 __global__ void __launch_bounds__(LEAF_NT) leaf_entity_kernel(LeafEntArgs a) {
   pdl_enter();
@@ -990,9 +1030,10 @@ __global__ void __launch_bounds__(LEAF_NT) leaf_entity_kernel(LeafEntArgs a) {
   int* idw_w = idw + warp * MAX_K;
   float* ds_w = ds_s + (NWH > 1 ? warp : 0) * a.n_rel;
   const int K = a.K;
-  for (long c0 = ((long)blockIdx.x * LEAF_NW + warp) * 32; c0 < a.n_entity; c0 += (long)gridDim.x * LEAF_NW * 32) {
+  const int chunk = a.chunk;
+  for (long c0 = ((long)blockIdx.x * LEAF_NW + warp) * chunk; c0 < a.n_entity; c0 += (long)gridDim.x * LEAF_NW * chunk) {
     const long me = c0 + lane;
-    unsigned mask = __ballot_sync(FULL_MASK, me < a.n_entity && __ldg(a.stamp + me) != 0);
+    unsigned mask = __ballot_sync(FULL_MASK, lane < chunk && me < a.n_entity && __ldg(a.stamp + me) != 0);
     AdjRec nxt{0, 0, 0, 0};
     if (mask) nxt = load_adj(a.adj, c0 + (__ffs(mask) - 1), K, lane);
     while (mask) {
@@ -1063,6 +1104,7 @@ struct DwArgs {
   long lda[MAX_DW_GROUPS];
   float* dW[MAX_DW_GROUPS];
   const float* G;       // [rows, D]
+  const float* Gg[MAX_DW_GROUPS];   // optional per-group G (overrides G)
   float* db;            // [D] or nullptr
   long rows;
 };
@@ -1077,6 +1119,7 @@ __global__ void __launch_bounds__(TC<D>::NT) dw_kernel(DwArgs a) {
   const int tid = threadIdx.x, tx = tid % C::LPR, ty = tid / C::LPR;
   const int grp = blockIdx.y;
   const float* A = a.A[grp];
+  const float* G = a.Gg[grp] ? a.Gg[grp] : a.G;
   const long lda = a.lda[grp];
   const bool do_bias = (grp == 0 && a.db != nullptr);
   float dw[C::DWN][4];
@@ -1092,7 +1135,7 @@ __global__ void __launch_bounds__(TC<D>::NT) dw_kernel(DwArgs a) {
       const int r = ty * C::TM + i;
       const long row = row0 + r;
       const bool ok = row < a.rows;
-      const float4 gv = ok ? ld4(a.G + row * D + tx * 4) : f4zero();
+      const float4 gv = ok ? ld4(G + row * D + tx * 4) : f4zero();
       bpart = f4add(bpart, gv);
       st4(&As[r * C::LD + tx * 4], ok ? ld4(A + row * lda + tx * 4) : f4zero());
       st4(&Gs[r * C::LD + tx * 4], gv);

@@ -18,7 +18,8 @@ static __global__ void pack_adj_kernel(const int64_t* __restrict__ adjE, const i
 }
 
 // ---- get_neighbors (model.py:243-256): one level of expansion, child k of node j at j*K+k -------------
-// `stamp` (optional): mark the produced ids (entity mode of the leaf level, level.cuh)
+// `stamp` (optional): mark the produced ids (entity mode of the leaf level, level.cuh); `out` may be null (table mode:
+// the deepest level is only stamped, its ids are re-read from the adjacency records)
 static __global__ void expand_kernel(const int32_t* __restrict__ ent, const int32_t* __restrict__ adj, long rows, int K,
                               int32_t* __restrict__ out, int32_t* __restrict__ stamp) {
   pdl_enter();
@@ -27,7 +28,7 @@ static __global__ void expand_kernel(const int32_t* __restrict__ ent, const int3
   const long j = i / K;
   const int k = (int)(i % K);
   const int32_t id = __ldg(adj + (long)ent[j] * 2 * K + k);
-  out[i] = id;
+  if (out) out[i] = id;
   if (stamp) stamp[id] = 1;
 }
 

@@ -131,6 +131,7 @@ int mvin_create(const mvin_config_t* cfg, mvin_handle_t* out) {
   if (const char* ev = getenv("MVIN_B200_ENTITY_LEAF")) h->entity_leaf_mode = atoi(ev) != 0 ? 1 : 0;
   if (const char* ev = getenv("MVIN_B200_USER_PB_FWD")) { const int n = atoi(ev); if (n == 1 || n == 2 || n == 4) h->user_pb_fwd = n; }
   if (const char* ev = getenv("MVIN_B200_TC")) { const int n = atoi(ev); if (n >= 0 && n <= 2) h->tc_mode = n; }
+  if (const char* ev = getenv("MVIN_B200_TABLE")) h->table_mode = atoi(ev) != 0 ? 1 : 0;
   if (const char* ev = getenv("MVIN_B200_TCBWD")) { const int n = atoi(ev); if (n >= 0 && n <= 2) h->tcb_mode = n; }
   if (const char* ev = getenv("MVIN_B200_STREAM")) h->stream_mode = atoi(ev) != 0 ? 1 : 0;
   if (const char* ev = getenv("MVIN_B200_CTAS_PER_SM")) { const int n = atoi(ev); if (n >= 1 && n <= 32) h->max_ctas_per_sm = n; }
@@ -265,7 +266,7 @@ int mvin_set_batch_scale(mvin_handle_t h, int32_t global_batch, float dense_l2_s
 
 size_t mvin_workspace_bytes(mvin_handle_t h, int32_t B) {
   if (!h || B < 1) return 0;
-  return make_layout(h->cfg, B, use_entity_leaf(h->cfg, B, h->n_shards, h->entity_leaf_mode)).total;
+  return handle_layout(h, B).total;
 }
 
 int mvin_get_neighbors(mvin_handle_t h, const int64_t* item_indices, int32_t B, int32_t n_levels,
@@ -307,7 +308,7 @@ int mvin_importance(mvin_handle_t h, float* imp0, float* imp1, void* workspace, 
   if (!h || !imp0 || !workspace) return fail(MVIN_ERR_INVALID, "null argument");
   if (h->fwd_workspace != workspace || h->B < 1) return fail(MVIN_ERR_STATE, "no forward pass on this workspace");
   cudaStream_t st = (cudaStream_t)stream;
-  const Layout L = make_layout(h->cfg, h->B, use_entity_leaf(h->cfg, h->B, h->n_shards, h->entity_leaf_mode));
+  const Layout L = handle_layout(h, h->B);
   const int K = h->cfg.neighbor_sample_size;
   float* outs[2] = {imp0, imp1};
   for (int lv = 0; lv < 2 && lv < h->cfg.h_hop; ++lv) {

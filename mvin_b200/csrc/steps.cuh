@@ -14,7 +14,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
   using C = TC<D>;
   const mvin_config_t& c = h->cfg;
   const int K = c.neighbor_sample_size, H = c.h_hop, p = c.p_hop, m = c.n_memory, nr = c.n_relation;
-  const Layout L = make_layout(c, B, use_entity_leaf(c, B, h->n_shards, h->entity_leaf_mode));
+  const Layout L = handle_layout(h, B);
   const mvin_params_t& P = h->P;
   int rc;
   prof_mark(h, st, nullptr);
@@ -32,13 +32,23 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
   {
     cudaStream_t st = par.s(0);
     if (stamp) CUDA_TRY(cudaMemsetAsync(stamp, 0, sizeof(int32_t) * (size_t)c.n_entity, st));
-    MVIN_LAUNCH((seed_kernel), (unsigned)((B + 255) / 256), 256, 0, st, item, B, at<int32_t>(ws, L.ent[0]), H == 1 ? stamp : nullptr);
+    if (L.table) {
+      // parameters only: composed maps M1_h, M2_h, c_h of the entity tables
+      MVIN_LAUNCH((compose_kernel), dim3(H, COMPOSE_SPLIT), 256, 0, st, P.transfer_w, P.transfer_b, P.agg_w, P.agg_b, D,
+                  1.f / (float)K, at<float>(ws, L.Mc), at<float>(ws, L.cst));
+      LAUNCH_CHECK(h, "compose");
+    }
+    // table mode stamps the entities of EVERY level (each needs its row of A_h); the row kernels only the deepest
+    MVIN_LAUNCH((seed_kernel), (unsigned)((B + 255) / 256), 256, 0, st, item, B, at<int32_t>(ws, L.ent[0]),
+                (H == 1 || L.table) ? stamp : nullptr);
     LAUNCH_CHECK(h, "seed");
     for (int lv = 0; lv + 1 < H; ++lv) {
       const long n = L.rows[lv] * K;
+      // table mode never reads the ids of the deepest level (they are re-read from the adjacency records); levels 0 / 1
+      // are still written for mvin_importance
+      int32_t* out = (L.table && lv + 1 == H - 1 && lv + 1 >= 2) ? nullptr : at<int32_t>(ws, L.ent[lv + 1]);
       MVIN_LAUNCH((expand_kernel), (unsigned)((n + 255) / 256), 256, 0, st, at<int32_t>(ws, L.ent[lv]), h->adj, L.rows[lv], K,
-                                                                 at<int32_t>(ws, L.ent[lv + 1]),
-                                                                 lv + 1 == H - 1 ? stamp : nullptr);
+                                                                 out, (lv + 1 == H - 1 || L.table) ? stamp : nullptr);
       LAUNCH_CHECK(h, "expand");
     }
     // relation scores of every aggregator
@@ -54,12 +64,27 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
       memset(&a, 0, sizeof(a));
       a.stamp = stamp; a.adj = h->adj; a.s = at<float>(ws, L.s); a.E = h->etab; a.Se = at<float>(ws, L.Se);
       a.n_entity = c.n_entity; a.K = K; a.n_rel = nr;
+      a.chunk = leaf_chunk(h, c.n_entity);
       const size_t sm = leaf_entity_smem(nr);
       if ((rc = set_smem(leaf_entity_kernel<D, false>, sm))) return rc;
-      const long want = ((long)c.n_entity + LEAF_NW * 32 - 1) / (LEAF_NW * 32);
+      const long want = ((long)c.n_entity + LEAF_NW * a.chunk - 1) / (LEAF_NW * a.chunk);
       const long cap = (long)h->sm_count * 8;
       MVIN_LAUNCH((leaf_entity_kernel<D, false>), (unsigned)(want < cap ? want : cap), LEAF_NT, sm, st, a);
       LAUNCH_CHECK(h, "leaf_entity_fwd");
+    }
+    // table mode: A_h = E M1_h + Se M2_h + c_h for every stamped entity
+    if (L.table) {
+      TableArgs a;
+      memset(&a, 0, sizeof(a));
+      a.stamp = stamp; a.E = h->etab.base; a.Se = at<float>(ws, L.Se); a.M = at<float>(ws, L.Mc); a.cst = at<float>(ws, L.cst);
+      a.A = at<float>(ws, L.Atab); a.n_entity = c.n_entity;
+      const size_t sm = table_fwd_smem<D>();
+      if ((rc = set_smem(table_fwd_kernel<D>, sm))) return rc;
+      const long tiles = ((long)c.n_entity + C::R - 1) / C::R;
+      long cap = (long)h->sm_count * resident_ctas(h, table_fwd_kernel<D>, C::NT, sm) / H;   // one resident wave over the H levels
+      if (cap < 1) cap = 1;
+      MVIN_LAUNCH((table_fwd_kernel<D>), dim3((unsigned)(tiles < cap ? tiles : cap), H), C::NT, sm, st, a);
+      LAUNCH_CHECK(h, "table_fwd");
     }
   }
   // the user side in one launch: seeds v = E[item], Q = RK^T v, ripple attention, user MLP -> user_o
@@ -116,7 +141,8 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
     TransformArgs a;
     memset(&a, 0, sizeof(a));
     long rows[MAX_LV];
-    for (int lv = 0; lv < H; ++lv) {
+    const int ntl = L.table ? 1 : H;                 // table mode: only T[0] is a row buffer (the mix layer reads it)
+    for (int lv = 0; lv < ntl; ++lv) {
       TransformLevel& t = a.lv[lv];
       t.ent = at<int32_t>(ws, L.ent[lv]);
       t.W = P.transfer_w + (long)lv * D * D; t.b = P.transfer_b + (long)lv * D;
@@ -124,10 +150,10 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
       t.rows = rows[lv] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
         t.stream = stream_level(h, L.rows[lv], D);
     }
-    a.nlev = H; a.E = h->etab; a.u = at<float>(ws, L.u);
+    a.nlev = ntl; a.E = h->etab; a.u = at<float>(ws, L.u);
     bool done = false;
     if constexpr (D == 32 || D == 64) {
-      if (use_tc_path(h, L.rows[H - 1])) {
+      if (!L.table && use_tc_path(h, L.rows[H - 1])) {
         const size_t smt = transform_fwd_tc_smem<D>();
         if ((rc = set_smem(transform_fwd_tc_kernel<D>, smt))) return rc;
         const int grid = partition_grid(rows, H, TT<D>::R,
@@ -137,10 +163,39 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
       }
     }
     if (!done) {
-      const int grid = partition_grid(rows, H, C::R, h->sm_count * resident_ctas(h, transform_fwd_kernel<D>, C::NT, sm), a.cta_end);
+      const int grid = partition_grid(rows, ntl, C::R, h->sm_count * resident_ctas(h, transform_fwd_kernel<D>, C::NT, sm), a.cta_end);
       MVIN_LAUNCH((transform_fwd_kernel<D>), grid, C::NT, sm, st, a);
     }
     LAUNCH_CHECK(h, "transform_fwd");
+  }
+  // table mode: C_h = u (M1_h + M2_h) per pair, then the iteration-0 outputs of every level but the deepest as rows
+  const int n_virt_rows = H >= 2 ? H - 1 : 1;        // levels 0 .. max(H - 2, 0)
+  if (L.table) {
+    GemmArgs g = gemm_args();
+    g.A = at<float>(ws, L.u); g.sa_m = D; g.sa_k = 1; g.bsA = 0;
+    g.B = at<float>(ws, L.Mc) + (long)TBL_MSUM * D * D; g.sb_k = D; g.sb_n = 1; g.bsB = (long)TBL_NM * D * D;
+    g.C = at<float>(ws, L.Cp); g.ldc = D; g.bsC = (long)B * D;
+    g.M = B; g.N = D; g.K = D; g.nbatch = H;
+    if ((rc = run_gemm(h, st, g, "gemm_cp"))) return rc;
+    VirtArgs a;
+    memset(&a, 0, sizeof(a));
+    long end = 0;
+    for (int lv = 0; lv < n_virt_rows; ++lv) {
+      VirtLevel& t = a.lv[lv];
+      t.ent = at<int32_t>(ws, L.ent[lv]);
+      t.A = at<float>(ws, L.Atab) + (long)lv * c.n_entity * D;
+      t.Cp = at<float>(ws, L.Cp) + (long)lv * B * D;
+      t.V = at<float>(ws, L.V[1][lv]);
+      t.rpp_magic = div_magic(L.rows[lv] / B);
+      end += L.rows[lv];
+      a.end[lv] = end;
+    }
+    a.nlev = n_virt_rows;
+    const long n = end * C::LPR;
+    const long cap = (long)h->sm_count * 8;
+    const long want = (n + 255) / 256;
+    MVIN_LAUNCH((virt_rows_kernel<D, false>), (unsigned)(want < cap ? want : cap), 256, 0, st, a);
+    LAUNCH_CHECK(h, "virt_rows_fwd");
   }
   // aggregation iterations (model.py:286-307): one launch per iteration, every level of it
   {
@@ -148,7 +203,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
     if ((rc = set_smem(agg_fwd_kernel<D, true>, sm_leaf))) return rc;
     if ((rc = set_smem(agg_fwd_kernel<D, false>, sm_in))) return rc;
     static const char* names[MAX_L] = {"agg_fwd_0", "agg_fwd_1", "agg_fwd_2"};
-    for (int i = 0; i < H; ++i) {
+    for (int i = L.table ? 1 : 0; i < H; ++i) {
       AggArgs a;
       memset(&a, 0, sizeof(a));
       long rows[MAX_LV];
@@ -164,7 +219,15 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
         t.rows = rows[q] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
         t.stream = stream_level(h, L.rows[lv], D);
         t.leaf = (i == 0 && lv == H - 1);
-        if (t.leaf) t.SU = at<float>(ws, L.SU); else t.child = at<float>(ws, L.V[i][lv + 1]);
+        if (t.leaf) {
+          t.SU = at<float>(ws, L.SU);
+        } else if (L.table && i == 1 && lv == H - 2) {       // children = iteration 0 of the deepest level, from its table
+          t.virt = 1;
+          t.tab = at<float>(ws, L.Atab) + (long)(H - 1) * c.n_entity * D;
+          t.Cp = at<float>(ws, L.Cp) + (long)(H - 1) * B * D;
+        } else {
+          t.child = at<float>(ws, L.V[i][lv + 1]);
+        }
       }
       a.adj = h->adj; a.s = at<float>(ws, L.s) + (long)i * nr;
       a.Wa = P.agg_w + (long)i * D * D; a.ba = P.agg_b + (long)i * D;
@@ -230,7 +293,7 @@ template <int D>
 int backward_init(mvin_handle_t h, int B, void* ws, cudaStream_t st, cudaEvent_t mid, bool zero_small) {
   const mvin_config_t& c = h->cfg;
   const int H = c.h_hop, p = c.p_hop, nr = c.n_relation;
-  const Layout L = make_layout(c, B, use_entity_leaf(c, B, h->n_shards, h->entity_leaf_mode));
+  const Layout L = handle_layout(h, B);
   const mvin_params_t& P = h->P;
   const mvin_params_t& G = h->G;
   const float l2w = c.l2_weight, l2a = c.l2_agg_weight;
@@ -303,14 +366,14 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
   using C = TC<D>;
   const mvin_config_t& c = h->cfg;
   const int K = c.neighbor_sample_size, H = c.h_hop, p = c.p_hop, m = c.n_memory, nr = c.n_relation;
-  const Layout L = make_layout(c, B, use_entity_leaf(c, B, h->n_shards, h->entity_leaf_mode));
+  const Layout L = handle_layout(h, B);
   const mvin_params_t& P = h->P;
   const mvin_params_t& G = h->G;
   const float l2w = c.l2_weight, l2a = c.l2_agg_weight;
   int rc;
   float* acc = at<float>(ws, L.acc);
   float* wT = at<float>(ws, L.wT);
-  const bool tcb = use_tc_bwd(h, L, D);
+  const bool tcb = !L.table && use_tc_bwd(h, L, D);
   prof_mark(h, st, nullptr);
 
   // part 0 (parameters only) on side stream 0 -- unless a host-step entry point already ran it during the feed copy
@@ -377,7 +440,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     if ((rc = set_smem(agg_bwd_kernel<D, true>, sm_leaf))) return rc;
     if ((rc = set_smem(agg_bwd_kernel<D, false>, sm_in))) return rc;
     static const char* names[MAX_L] = {"agg_bwd_0", "agg_bwd_1", "agg_bwd_2"};
-    for (int i = H - 1; i >= 0; --i) {
+    for (int i = H - 1; i >= (L.table ? 1 : 0); --i) {
       AggBwdArgs a;
       memset(&a, 0, sizeof(a));
       long rows[MAX_LV];
@@ -397,6 +460,12 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
         t.leaf = (i == 0 && lv == H - 1);
         if (t.leaf) {
           t.SU = at<float>(ws, L.SU);
+        } else if (L.table && i == 1 && lv == H - 2) {
+          t.virt = 1;
+          t.tab = at<float>(ws, L.Atab) + (long)(H - 1) * c.n_entity * D;
+          t.Cp = at<float>(ws, L.Cp) + (long)(H - 1) * B * D;
+          t.dtab = at<float>(ws, L.dA) + (long)(H - 1) * c.n_entity * D;
+          t.dCs = at<float>(ws, L.dCs) + (long)(H - 1) * B * D;
         } else {
           t.child = at<float>(ws, L.V[i][lv + 1]);
           t.dchild = at<float>(ws, L.DC[i][lv + 1]);
@@ -411,6 +480,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
       a.dWa = G.agg_w + (long)i * D * D; a.dba = G.agg_b + (long)i * D;
       a.ds = at<float>(ws, L.ds) + (long)i * nr;
       a.K = K; a.n_rel = nr;
+      if (L.table && i == 1) par.join(0);   // zeroed dA / dCs are first needed here
       if (i == 0 && !tcb0) {
         par.join(0);       // zeroed dE / GSe / dQ / cnt are first needed here
         a.E = h->etab; a.WtT = wT + (long)(H + H) * D * D;
@@ -456,6 +526,52 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
       }
     }
   }
+  // table mode: iteration 0 backward = per-entity / per-pair sums of the pre-activation gradients, then dense algebra
+  if (L.table) {
+    if (H == 1) par.join(0);
+    const int n_virt_rows = H >= 2 ? H - 1 : 1;
+    {
+      VirtArgs a;
+      memset(&a, 0, sizeof(a));
+      long end = 0;
+      for (int lv = 0; lv < n_virt_rows; ++lv) {
+        VirtLevel& t = a.lv[lv];
+        t.ent = at<int32_t>(ws, L.ent[lv]);
+        t.V = at<float>(ws, L.V[1][lv]);
+        t.g1 = at<float>(ws, L.DC[1][lv]);
+        t.g2 = has_agg(H, 1, lv) ? at<float>(ws, L.DS[1][lv]) : nullptr;
+        t.dA = at<float>(ws, L.dA) + (long)lv * c.n_entity * D;
+        t.dCs = at<float>(ws, L.dCs) + (long)lv * B * D;
+        t.rpp_magic = div_magic(L.rows[lv] / B);
+        end += L.rows[lv];
+        a.end[lv] = end;
+      }
+      a.nlev = n_virt_rows;
+      const long n = end * C::LPR;
+      const long cap = (long)h->sm_count * 8;
+      const long want = (n + 255) / 256;
+      MVIN_LAUNCH((virt_rows_kernel<D, true>), (unsigned)(want < cap ? want : cap), 256, 0, st, a);
+      LAUNCH_CHECK(h, "virt_rows_bwd");
+    }
+    {
+      TableArgs a;
+      memset(&a, 0, sizeof(a));
+      a.stamp = at<int32_t>(ws, L.stamp); a.E = h->etab.base; a.Se = at<float>(ws, L.Se); a.M = at<float>(ws, L.Mc);
+      a.dA = at<float>(ws, L.dA); a.dE = h->gtab.base; a.GSe = at<float>(ws, L.GSe); a.dM = at<float>(ws, L.dM);
+      a.dc = at<float>(ws, L.dcst); a.n_entity = c.n_entity;
+      const size_t sm = table_bwd_smem<D>();
+      if ((rc = set_smem(table_bwd_kernel<D>, sm))) return rc;
+      const long tiles = ((long)c.n_entity + C::R - 1) / C::R;
+      // every CTA ends with a 2 d^2-float reduction of its weight-gradient partials into global memory: at least four
+      // tiles per CTA, one resident wave over the H levels
+      long cap = (long)h->sm_count * resident_ctas(h, table_bwd_kernel<D>, C::NT, sm) / H;
+      if (cap < 1) cap = 1;
+      long want = (tiles + 3) / 4;
+      if (want < 1) want = 1;
+      MVIN_LAUNCH((table_bwd_kernel<D>), dim3((unsigned)(want < cap ? want : cap), H), C::NT, sm, st, a);
+      LAUNCH_CHECK(h, "table_bwd");
+    }
+  }
   // side stream 0: per-entity leaf backward + relation-score gradients, while the user-oriented transform backward
   // runs on the launch stream (both only add into dE)
   par.fork(0);
@@ -467,9 +583,10 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     a.stamp = at<int32_t>(ws, L.stamp); a.adj = h->adj; a.s = at<float>(ws, L.s); a.E = h->etab;
     a.GSe = at<float>(ws, L.GSe); a.dE = h->gtab; a.ds = at<float>(ws, L.ds);
     a.n_entity = c.n_entity; a.K = K; a.n_rel = nr;
+    a.chunk = leaf_chunk(h, c.n_entity);
     const size_t sm = leaf_entity_smem(nr);
     if ((rc = set_smem(leaf_entity_kernel<D, true>, sm))) return rc;
-    const long want = ((long)c.n_entity + LEAF_NW * 32 - 1) / (LEAF_NW * 32);
+    const long want = ((long)c.n_entity + LEAF_NW * a.chunk - 1) / (LEAF_NW * a.chunk);
     const long cap = (long)h->sm_count * 8;
     MVIN_LAUNCH((leaf_entity_kernel<D, true>), (unsigned)(want < cap ? want : cap), LEAF_NT, sm, st, a);
     LAUNCH_CHECK(h, "leaf_entity_bwd");
@@ -478,6 +595,27 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
                                            G.agg_urh_w);
   LAUNCH_CHECK(h, "rel_scores_bwd");
   }
+  if (L.table) {
+    // pair side of the tables: dMu_h = u^T dCs_h ; du += sum_h dCs_h (M1_h + M2_h)^T ; then the d x d parameter chain
+    DwArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int lv = 0; lv < H; ++lv) {
+      a.A[lv] = at<float>(ws, L.u); a.lda[lv] = D;
+      a.Gg[lv] = at<float>(ws, L.dCs) + (long)lv * B * D;
+      a.dW[lv] = at<float>(ws, L.dM) + (long)(lv * 3 + 2) * D * D;
+    }
+    a.G = a.Gg[0]; a.db = nullptr; a.rows = B;
+    if ((rc = launch_dw<D>(h, st, a, H, "dw_pair"))) return rc;
+    GemmArgs g = gemm_args();
+    g.A = at<float>(ws, L.dCs); g.sa_m = D; g.sa_k = 1; g.bsA = (long)B * D;
+    g.B = at<float>(ws, L.Mc) + (long)TBL_MSUM * D * D; g.sb_k = 1; g.sb_n = D; g.bsB = (long)TBL_NM * D * D;
+    g.C = du; g.ldc = D; g.bsC = 0;
+    g.M = B; g.N = D; g.K = D; g.nbatch = H; g.reduce = 1; g.accumulate = 1;
+    if ((rc = run_gemm(h, st, g, "gemm_du_pair"))) return rc;
+    MVIN_LAUNCH((compose_bwd_kernel), dim3(H, COMPOSE_SPLIT), 256, 0, st, P.transfer_w, P.transfer_b, P.agg_w, at<float>(ws, L.dM),
+                at<float>(ws, L.dcst), D, 1.f / (float)K, G.transfer_w, G.transfer_b, G.agg_w, G.agg_b);
+    LAUNCH_CHECK(h, "compose_bwd");
+  }
   // user-oriented transform backward, levels 0..L-1, one launch
   {
     const size_t sm = transform_bwd_smem<D>();
@@ -485,18 +623,19 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     TransformArgs a;
     memset(&a, 0, sizeof(a));
     long rows[MAX_LV];
-    for (int q = 0; q < H; ++q) {
-      const int lv = H - 1 - q;
+    const int ntl = L.table ? 1 : H;
+    for (int q = 0; q < ntl; ++q) {
+      const int lv = ntl - 1 - q;
       TransformLevel& t = a.lv[q];
       t.ent = at<int32_t>(ws, L.ent[lv]);
       t.W = tcb ? P.transfer_w + (long)lv * D * D : wT + (long)(H + lv) * D * D;   // the tcgen05 kernel takes W_t[lv] as stored
-      t.g1 = at<float>(ws, L.DC[0][lv]); t.g2 = at<float>(ws, L.DS[0][lv]);
+      t.g1 = at<float>(ws, L.DC[0][lv]); t.g2 = L.table ? nullptr : at<float>(ws, L.DS[0][lv]);
       if (tcb && lv == H - 1) { t.g1 = at<float>(ws, L.DS[0][lv]); t.g2 = nullptr; }   // one buffer: dself + dchild
       t.dW = G.transfer_w + (long)lv * D * D; t.db = G.transfer_b + (long)lv * D;
       t.rows = rows[q] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
         t.stream = stream_level(h, L.rows[lv], D);
     }
-    a.nlev = H; a.E = h->etab; a.u = at<float>(ws, L.u); a.dE = h->gtab; a.du = du;
+    a.nlev = ntl; a.E = h->etab; a.u = at<float>(ws, L.u); a.dE = h->gtab; a.du = du;
     bool done = false;
     if constexpr (D == 32 || D == 64) {
       if (tcb) {
@@ -509,7 +648,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
       }
     }
     if (!done) {
-      const int grid = partition_grid(rows, H, C::R, h->sm_count * resident_ctas(h, transform_bwd_kernel<D>, C::NT, sm), a.cta_end);
+      const int grid = partition_grid(rows, ntl, C::R, h->sm_count * resident_ctas(h, transform_bwd_kernel<D>, C::NT, sm), a.cta_end);
       MVIN_LAUNCH((transform_bwd_kernel<D>), grid, C::NT, sm, st, a);
     }
     LAUNCH_CHECK(h, "transform_bwd");

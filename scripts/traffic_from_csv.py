@@ -36,6 +36,10 @@ def family(name, state, H):
         return f"agg_bwd_{H - state['b']}"
     if base == "leaf_entity_kernel":
         return "leaf_entity_bwd" if leaf else "leaf_entity_fwd"
+    if base == "virt_rows_kernel":
+        return "virt_rows_bwd" if leaf else "virt_rows_fwd"
+    if base == "agg_bwd_leaf_kernel":
+        return "agg_bwd_leaf_tc"
     if base == "gemm_kernel":
         state["g"] += 1
         return f"gemm#{state['g']}"
@@ -67,7 +71,9 @@ def main():
     e = ends[-1]
     b = max(i for i in starts if i < e)
     step = seq[b:e + 1]
-    H = sum(1 for l in step if "agg_bwd_kernel" in l["name"])
+    # aggregator iterations of the step: one agg_bwd launch each, except that the entity-table mode (table.cuh) has no
+    # launch for iteration 0
+    H = sum(1 for l in step if "agg_bwd_kernel" in l["name"]) + (1 if any("table_bwd_kernel" in l["name"] for l in step) else 0)
     state = {"f": 0, "b": 0, "g": 0}
     fam, us = {}, {}
     for l in step:

@@ -43,8 +43,14 @@ def _assert_grads(got, ref_of, tol=GRAD_TOL):
     assert not bad, bad
 
 
+# MVIN_B200_TABLE: "1" forces the entity-table form of aggregator iteration 0 (table.cuh), "0" the per-row kernels
+TABLE_MODES = ["0", "1"]
+
+
+@pytest.mark.parametrize("table", TABLE_MODES)
 @pytest.mark.parametrize("case", SUPPORTED_GOLDEN)
-def test_golden_forward_backward(case):
+def test_golden_forward_backward(case, table, monkeypatch):
+    monkeypatch.setenv("MVIN_B200_TABLE", table)
     model, z, cfg, fd = _model_from_golden(case)
     ents, rels = model.get_neighbors(z["items"])
     for i, e in enumerate(ents):
@@ -69,8 +75,10 @@ def test_golden_forward_backward(case):
         assert np.array_equal(e, z[f"entities_{i}"])
 
 
+@pytest.mark.parametrize("table", TABLE_MODES)
 @pytest.mark.parametrize("case", ["h2_m1_p2", "h3_m1_p1"])
-def test_golden_two_adam_steps(case):
+def test_golden_two_adam_steps(case, table, monkeypatch):
+    monkeypatch.setenv("MVIN_B200_TABLE", table)
     model, z, cfg, fd = _model_from_golden(case)
     _, loss0 = model.train(None, fd)
     _, loss1 = model.train(None, fd)
@@ -92,12 +100,18 @@ CASES = [
     (8, 5, 2, 1, 7, 67, "trained", 0.0),         # ragged: K, m not powers of two, partial tiles
     (16, 33, 1, 3, 33, 65, "trained", 0.0),      # K > 32 (two ids per lane), p = 3
     (32, 1, 2, 2, 1, 9, "trained", 0.0),         # degenerate K = 1, m = 1
+    (64, 7, 3, 0, 16, 37, "trained", 0.2),       # L = 3 with partial tiles at every level, p = 0, hub
+    (128, 16, 3, 1, 16, 4, "trained", 0.0),      # d = 128, L = 3
+    (8, 64, 2, 2, 16, 130, "trained", 0.0),      # d = 8, K = 64
+    (16, 8, 1, 2, 64, 1, "trained", 0.0),        # a single pair
 ]
 
 
+@pytest.mark.parametrize("table", TABLE_MODES)
 @pytest.mark.parametrize("dim,K,H,p,m,B,regime,hub", CASES)
-def test_synthetic_vs_oracle(dim, K, H, p, m, B, regime, hub):
+def test_synthetic_vs_oracle(dim, K, H, p, m, B, regime, hub, table, monkeypatch):
     from mvin_b200 import MVIN
+    monkeypatch.setenv("MVIN_B200_TABLE", table)
     args = make_args(dim=dim, neighbor_sample_size=K, h_hop=H, p_hop=p, n_memory=m, batch_size=B)
     prob = make_problem(args, n_entity=300 if K < 64 else 500, seed=dim + K + H, regime=regime, hub_frac=hub)
     model = MVIN(args, prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"], prob["adj_relation"])
@@ -109,9 +123,10 @@ def test_synthetic_vs_oracle(dim, K, H, p, m, B, regime, hub):
     for a, b in zip(ents + rels, out.entities + out.relations):
         assert np.array_equal(a, b)
     assert rel_err(model.get_raw_scores(fd), out.scores.detach().numpy()) < SCORE_TOL
-    losses = model.loss_and_grads(fd)
-    assert abs(float(losses[0]) - float(out.loss)) <= 1e-4 * max(1.0, abs(float(out.loss)))
-    _assert_grads(model.named_gradients(), lambda k: grads[k].numpy())
+    for _ in range(2):                                       # second step: accumulators / tables re-initialised
+        losses = model.loss_and_grads(fd)
+        assert abs(float(losses[0]) - float(out.loss)) <= 1e-4 * max(1.0, abs(float(out.loss)))
+        _assert_grads(model.named_gradients(), lambda k: grads[k].numpy())
 
 
 @pytest.mark.parametrize("dim,K,H,B", [(64, 32, 2, 40), (32, 16, 2, 80), (64, 8, 3, 5), (32, 5, 1, 300)])

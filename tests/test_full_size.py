@@ -158,6 +158,30 @@ def test_c2_full_size_matches_oracle():
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("table", ["0", "1"])
+def test_c3_shape_mid_size_against_fp64_oracle(table, monkeypatch):
+    """last-fm shape, d = 64, L = 2, K = 32 at B = 512 (524 288 leaf rows): the largest C3-shaped batch the oracle can
+    run.  The oracle is evaluated in fp64 here, so the comparison measures the fp32 error of EACH implementation (the
+    per-row kernels and the entity-table form of iteration 0) against exact arithmetic rather than against another fp32
+    summation order.  Tolerances as everywhere: scores 1e-4 relative, gradients 1e-4 of the largest entry."""
+    monkeypatch.setenv("MVIN_B200_TABLE", table)
+    B = 512
+    model, ds, args = _build("last-fm_50core", 64, 2, 32, B, 2, 64)
+    users, items, labels, mh, mr, mt = _batch(ds, B)
+    P = {k: torch.as_tensor(v).double() for k, v in model.named_parameters().items()}
+    out, grads = orc.loss_and_grads(P, orc.OracleConfig.from_args(args), ds["adj_entity"], ds["adj_relation"], users, items,
+                                    list(mh), list(mr), list(mt), labels)
+    losses = model.train_step_host(users, items, labels, mh, mr, mt, apply_adam=False)
+    assert abs(float(losses[0]) - float(out.loss.detach())) <= 1e-4 * max(1.0, abs(float(out.loss.detach())))
+    got = model.named_gradients()
+    bad = []
+    for k, g in got.items():
+        ref = grads[k].numpy().reshape(g.shape)
+        if not np.abs(g - ref).max() <= 1e-4 * max(np.abs(ref).max(), 1e-8) + 1e-8:
+            bad.append((k, float(np.abs(g - ref).max()), float(np.abs(ref).max())))
+    assert not bad, bad
+
+
 @pytest.mark.parametrize("B", [256, 8192])
 def test_c3_shape_size_triggered_branches(B, monkeypatch):
     """last-fm shape, d = 64, L = 2, K = 32.  B = 256: 262 144 leaf-level rows -> tcgen05 forward kernels selected by
@@ -177,19 +201,23 @@ def test_c3_shape_size_triggered_branches(B, monkeypatch):
         _assert_close(_grads(other), auto)
 
 
-def test_c4_shape_three_hops():
+@pytest.mark.parametrize("table", ["0", "1"])
+def test_c4_shape_three_hops(table, monkeypatch):
     """amazon-book shape, d = 64, L = 3, K = 32 at B = 2048: 2.1 M level-2 rows (537 MB buffers, streaming, tcgen05
-    forward, per-entity leaf mode), every level of the three aggregator iterations in play."""
+    forward, per-entity leaf mode), every level of the three aggregator iterations in play.  table = 1: the entity-table
+    form of iteration 0 (table.cuh) on the same batch (the library's automatic choice at this size)."""
+    monkeypatch.setenv("MVIN_B200_TABLE", table)
     model, ds, args = _build("amazon-book_20core", 64, 3, 32, 2048, 1, 16)
     batch = _batch(ds, 2048)
     _spot_check(model, args, batch)
     _linearity(model, batch)
 
 
-def test_offsets_beyond_2_to_31_elements():
-    """One level buffer of more than 2^31 floats (8.6 GB): d = 128, K = 32, L = 3, B = 16 400 -> 16.8 M level-2 rows x
+def test_offsets_beyond_2_to_31_elements(monkeypatch):
+    """(row kernels: MVIN_B200_TABLE=0 -- the entity-table mode never materialises the deepest level)  One level buffer of more than 2^31 floats (8.6 GB): d = 128, K = 32, L = 3, B = 16 400 -> 16.8 M level-2 rows x
     128.  The checked pairs sit at both ends of the batch; the backward is checked through linearity."""
     from mvin_b200 import MVIN
+    monkeypatch.setenv("MVIN_B200_TABLE", "0")
     B, d, K = 16400, 128, 32
     assert B * K * K * d > 2 ** 31
     ds = _dataset("amazon-book_20core", K, 1, 16)
