@@ -34,7 +34,7 @@ extern "C" {
 #define MVIN_ERR_CUDA -3
 #define MVIN_ERR_STATE -4
 
-#define MVIN_ABI_VERSION 3
+#define MVIN_ABI_VERSION 4
 
 typedef struct mvin_handle_s* mvin_handle_t;
 
@@ -111,6 +111,32 @@ int mvin_pack_adjacency(const int64_t* adj_entity, const int64_t* adj_relation, 
  * step (peers scatter into it) and again before reading it.  Both arrays are host arrays of device pointers. */
 int mvin_bind_entity_shards(mvin_handle_t h, int32_t n_shards, const float* const* entity_shards,
                             float* const* grad_shards);
+
+/* Owner-side partial reduction of the deepest level for the row-sharded table (BASELINE.json C5 / north_star: "a
+ * single all-to-all to route each batch's neighbor indices to the owning shard").  Replaces the leaf gather
+ * tf.nn.embedding_lookup(entity_emb_matrix, entities[L]) of model.py:267 as consumed by
+ * reduce_mean(probs * neighbor_vectors) (aggregators.py:141-144): that consumer is linear in the rows, so the rank that
+ * OWNS a row contributes it to a partial sum and one d-vector per (parent node, owner) crosses NVLink instead of every
+ * raw row.  The adjacency is replicated, so the owners re-derive child ids and attention from the parent's entity id:
+ * the index routing is an all-gather of 4 bytes per leaf-level parent node (the caller's one NCCL collective).
+ *
+ * Geometry: n_src source ranks (1 when all shards live in one process), `rows` = B K^(h_hop-1) parent nodes per source.
+ * Per source s, three peer-visible buffers: part[s] fp32 [n_shards][rows][d] (written by the owners, read by s),
+ * gsu[s] fp32 [rows][d] (written by s, read by the owners), dot[s] fp32 [n_shards][rows] (written by the owners).
+ * ids_all int32 [n_src][rows] is local.  Host arrays of device pointers valid in this process (CUDA-IPC mappings for
+ * the peers').  n_src = 0 unbinds.  Sequence of one step, every rank, one stream (=> marks the caller's stream-ordered
+ * collective that orders the ranks):
+ *   mvin_xchg_expand (my ids -> ids_all[src_index]) => all-gather ids_all => mvin_xchg_owner_forward(owner = my shard)
+ *   => barrier => mvin_forward, mvin_backward (the leaf level reads part[] and leaves gsu) => barrier =>
+ *   mvin_xchg_owner_backward(owner) => barrier => mvin_xchg_finish_backward => all-reduce of the replicated gradients.
+ * With all shards in one process the owner calls are made once per shard and no collective is needed. */
+int mvin_xchg_bind(mvin_handle_t h, int32_t n_src, int32_t src_index, int64_t rows, const int32_t* ids_all,
+                   float* const* part, float* const* gsu, float* const* dot);
+int mvin_xchg_expand(mvin_handle_t h, const int64_t* item_indices, int32_t B, int32_t* ids_out, void* workspace,
+                     void* stream);
+int mvin_xchg_owner_forward(mvin_handle_t h, int32_t owner, void* workspace, void* stream);
+int mvin_xchg_owner_backward(mvin_handle_t h, int32_t owner, void* workspace, void* stream);
+int mvin_xchg_finish_backward(mvin_handle_t h, void* workspace, void* stream);
 
 /* CUDA IPC helpers for the shard exchange between the one-process-per-GPU ranks of a box: export gives the 64-byte
  * cudaIpcMemHandle_t of the allocation containing dev_ptr and dev_ptr's offset in it; open maps a peer's

@@ -9,7 +9,7 @@ from . import build as _build
 
 MVIN_OK = 0
 FLAGS_ALL = 0x1F
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 EXPORTS = ["mvin_abi_version", "mvin_last_error", "mvin_create", "mvin_destroy", "mvin_bind_params",
            "mvin_bind_grads", "mvin_bind_adjacency", "mvin_bind_entity_shards", "mvin_set_batch_scale", "mvin_ipc_export", "mvin_ipc_open", "mvin_pack_adjacency", "mvin_workspace_bytes",
@@ -17,7 +17,8 @@ EXPORTS = ["mvin_abi_version", "mvin_last_error", "mvin_create", "mvin_destroy",
            "mvin_feed_bytes", "mvin_train_step_host", "mvin_launch_count", "mvin_profile_enable",
            "mvin_profile_read", "mvin_test_umma_gemm", "mvin_test_umma_dw", "mvin_bind_user_triplets", "mvin_gather_feed",
            "mvin_train_step_users_host", "mvin_ctr_metrics", "mvin_sample_adjacency", "mvin_build_ripple_sets", "mvin_feed_prefetch",
-           "mvin_train_step_prefetched", "mvin_topk_metrics", "mvin_test_umma_bf16"]
+           "mvin_train_step_prefetched", "mvin_topk_metrics", "mvin_test_umma_bf16", "mvin_xchg_bind", "mvin_xchg_expand",
+           "mvin_xchg_owner_forward", "mvin_xchg_owner_backward", "mvin_xchg_finish_backward"]
 
 
 class Config(C.Structure):
@@ -91,6 +92,11 @@ def load():
     lib.mvin_train_step_prefetched.argtypes = [vp, i32, vp, i32, vp, C.POINTER(Params), C.POINTER(Params), C.c_float, i32,
                                                vp, vp]
     lib.mvin_topk_metrics.argtypes = [vp, vp, vp, vp, i32, i32, vp, i32, vp, vp, vp, vp]
+    lib.mvin_xchg_bind.argtypes = [vp, i32, i32, C.c_int64, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.mvin_xchg_expand.argtypes = [vp, vp, i32, vp, vp, vp]
+    lib.mvin_xchg_owner_forward.argtypes = [vp, i32, vp, vp]
+    lib.mvin_xchg_owner_backward.argtypes = [vp, i32, vp, vp]
+    lib.mvin_xchg_finish_backward.argtypes = [vp, vp, vp]
     lib.mvin_launch_count.argtypes = [vp]
     lib.mvin_launch_count.restype = C.c_int64
     lib.mvin_profile_enable.argtypes = [vp, i32]

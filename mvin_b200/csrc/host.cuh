@@ -20,6 +20,7 @@
 #include "level_tcb.cuh"
 #include "misc.cuh"
 #include "table.cuh"
+#include "exchange.cuh"
 #include "umma.cuh"
 #include "umma_bf.cuh"
 #include "user.cuh"
@@ -163,6 +164,17 @@ struct mvin_handle_s {
   int tcb_mode = 1;                // tcgen05 backward kernels of the deepest level (level_tcb.cuh): 0 never, 1 auto, 2 always
                                    // (env MVIN_B200_TCBWD)
   int max_ctas_per_sm = 4;         // cap on resident CTAs per SM of the persistent row kernels (env MVIN_B200_CTAS_PER_SM)
+  // owner-side partial reduction of the leaf level (exchange.cuh; mvin_xchg_*): peer-visible buffers of every source rank
+  struct Xchg {
+    bool on = false;
+    int n_src = 0, src_index = 0;    // source ranks taking part; this rank's index among them
+    long rows = 0;                   // leaf-level parent nodes per source rank
+    const int32_t* ids_all = nullptr;
+    float* part[XCHG_MAX_RANKS] = {nullptr};
+    float* gsu[XCHG_MAX_RANKS] = {nullptr};
+    float* dot[XCHG_MAX_RANKS] = {nullptr};
+  } xchg;
+  void* shard_host[2 * 16] = {nullptr};   // host copy of the shard pointer table (entity shards, then gradient shards)
   bool prof_on = false;
   struct ProfRec { const char* name; cudaEvent_t ev; };
   std::vector<ProfRec> prof;

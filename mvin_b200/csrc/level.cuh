@@ -545,6 +545,8 @@ struct AggArgs {
   const float* Wa;      // [D, D]
   const float* ba;      // [D]
   const float* Se;      // leaf, entity mode: [n_entity, D] per-entity S = sum_k p_k E[n_k] (leaf_entity_fwd_kernel)
+  const float* Xpart;   // leaf, exchange mode (exchange.cuh): [xG][rows, D] per-owner partial sums S^(g), S = sum_g
+  int xG;
   int K, n_rel;
 };
 
@@ -603,7 +605,8 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
     const bool ent_mode = leaf && a.Se != nullptr;
     const long row0 = (t - (lvl ? a.tl.tile_end[lvl - 1] : 0)) * C::R;
     // ---- stage phase: (p_k, id_k) of every row of the tile ----
-    if (!ent_mode) {
+    const bool x_mode = leaf && a.Xpart != nullptr;
+    if (!ent_mode && !x_mode) {
       stage_tile<D, false>(L.ent, a.adj, s_s, row0, L.rows, K, KP, nb_s, nullptr, warp, lane);
       __syncthreads();
     }
@@ -624,10 +627,15 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
           const float4 uv = ldg4(a.u + fastdiv(row, L.rpp_magic) * D + tx * 4);
           const int2* nb = nb_s + r * KP;
           float4 acc = f4zero();
+          if (x_mode) {
+            // the owners of the leaf rows reduced their share already (exchange.cuh): S = sum over the owners' partials
+            for (int g = 0; g < a.xG; ++g) acc = f4add(acc, ld4(a.Xpart + ((long)g * L.rows + row) * D + tx * 4));
+          } else {
 #pragma unroll 8
-          for (int k = 0; k < K; ++k) {
-            const int2 v = nb[k];
-            acc = f4fma(__int_as_float(v.x), ldg4(erow(a.E, v.y, D) + tx * 4), acc);
+            for (int k = 0; k < K; ++k) {
+              const int2 v = nb[k];
+              acc = f4fma(__int_as_float(v.x), ldg4(erow(a.E, v.y, D) + tx * 4), acc);
+            }
           }
           o = f4add(acc, uv);
           st4a(L.SU + row * D + tx * 4, o, L.stream);
@@ -754,6 +762,8 @@ struct AggBwdArgs {
   float* GSe;           // leaf, entity mode: [n_entity, D] per-entity sum of gsu (consumed by leaf_entity_bwd_kernel)
   const float* Se;      // leaf, entity mode: [n_entity, D] (S + u is recomputed, not stored)
   const float* u;       // leaf, entity mode: [B, D]
+  float* Xgsu;          // leaf, exchange mode (exchange.cuh): [rows, D] gsu = dL/dS of every leaf-level node, left for the
+                        // owners of the leaf rows (their scatter-add and the softmax gradient happen on the owner)
   int K, n_rel;
 };
 
@@ -806,7 +816,8 @@ __global__ void __launch_bounds__(TC<D>::NT, (D <= 64 ? 3 : 1)) agg_bwd_kernel(A
     had_leaf |= leaf;
     const long row0 = (t - (lvl ? a.tl.tile_end[lvl - 1] : 0)) * C::R;
     // ---- stage phase (its loads overlap the tile loads below) ----
-    const bool nbr_phase = !ent_mode && !L.defer;
+    const bool x_mode = leaf && a.Xgsu != nullptr;
+    const bool nbr_phase = !ent_mode && !L.defer && !x_mode;
     if (nbr_phase) stage_tile<D, true>(L.ent, a.adj, s_s, row0, L.rows, K, KP, nb_s, rel_s, warp, lane);
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) {
@@ -868,6 +879,8 @@ __global__ void __launch_bounds__(TC<D>::NT, (D <= 64 ? 3 : 1)) agg_bwd_kernel(A
         if (ent_mode) {
           // entity mode: the leaf scatter and the softmax gradient are linear in gsu and depend on the entity only
           if (row < L.rows) red_add4(a.GSe + (long)__ldg(L.ent + row) * D + tx * 4, gsu[i]);
+        } else if (x_mode) {
+          if (row < L.rows) st4(a.Xgsu + row * D + tx * 4, gsu[i]);
         } else {
           st4(&Gs[r * C::LD + tx * 4], gsu[i]);                            // same thread reads it back below
         }

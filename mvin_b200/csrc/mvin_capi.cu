@@ -15,11 +15,20 @@ template <int D>
 int backward_init(mvin_handle_t h, int B, void* ws, cudaStream_t st, cudaEvent_t mid, bool zero_small);
 template <int D>
 int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out, void* ws, cudaStream_t st);
+template <int D>
+int xchg_expand_impl(mvin_handle_t h, const int64_t* item, int B, int32_t* ids_out, void* ws, cudaStream_t st);
+template <int D>
+int xchg_owner_impl(mvin_handle_t h, int owner, bool bwd, int B, void* ws, cudaStream_t st);
+template <int D>
+int xchg_finish_impl(mvin_handle_t h, int B, void* ws, cudaStream_t st);
 #define MVIN_EXTERN_D(D)                                                                                              \
   extern template int forward_impl<D>(mvin_handle_t, const int64_t*, const int32_t*, const int32_t*, const int32_t*,  \
                                       int, float*, float*, void*, cudaStream_t);                                      \
   extern template int backward_init<D>(mvin_handle_t, int, void*, cudaStream_t, cudaEvent_t, bool);                   \
-  extern template int backward_impl<D>(mvin_handle_t, const float*, int, float*, void*, cudaStream_t);
+  extern template int backward_impl<D>(mvin_handle_t, const float*, int, float*, void*, cudaStream_t);         \
+  extern template int xchg_expand_impl<D>(mvin_handle_t, const int64_t*, int, int32_t*, void*, cudaStream_t);         \
+  extern template int xchg_owner_impl<D>(mvin_handle_t, int, bool, int, void*, cudaStream_t);                         \
+  extern template int xchg_finish_impl<D>(mvin_handle_t, int, void*, cudaStream_t);
 MVIN_EXTERN_D(8) MVIN_EXTERN_D(16) MVIN_EXTERN_D(32) MVIN_EXTERN_D(64) MVIN_EXTERN_D(128)
 #undef MVIN_EXTERN_D
 
@@ -87,6 +96,15 @@ int host_step_overlap(mvin_handle_t h, int B, void* ws, cudaStream_t st) {
 }
 int dispatch_backward(mvin_handle_t h, const float* labels, int B, float* losses, void* ws, cudaStream_t st) {
   DISPATCH_D(h->cfg.dim, (backward_impl<DD>(h, labels, B, losses, ws, st)));
+}
+int dispatch_xchg_expand(mvin_handle_t h, const int64_t* item, int B, int32_t* ids, void* ws, cudaStream_t st) {
+  DISPATCH_D(h->cfg.dim, (xchg_expand_impl<DD>(h, item, B, ids, ws, st)));
+}
+int dispatch_xchg_owner(mvin_handle_t h, int owner, bool bwd, int B, void* ws, cudaStream_t st) {
+  DISPATCH_D(h->cfg.dim, (xchg_owner_impl<DD>(h, owner, bwd, B, ws, st)));
+}
+int dispatch_xchg_finish(mvin_handle_t h, int B, void* ws, cudaStream_t st) {
+  DISPATCH_D(h->cfg.dim, (xchg_finish_impl<DD>(h, B, ws, st)));
 }
 
 }  // namespace mvin_host
@@ -209,11 +227,61 @@ int mvin_bind_entity_shards(mvin_handle_t h, int32_t n_shards, const float* cons
     host[MAX_SHARDS + i] = grad_shards[i];
   }
   CUDA_TRY(cudaMemcpy(h->d_shard_tab, host, sizeof(host), cudaMemcpyHostToDevice));
+  memcpy(h->shard_host, host, sizeof(host));
+  h->xchg.on = false;
   h->n_shards = n_shards;
   h->n_local_rows = ((long)h->cfg.n_entity + n_shards - 1) / n_shards;
   h->etab = ETab{nullptr, reinterpret_cast<const float* const*>(h->d_shard_tab), shift, n_shards - 1};
   h->gtab = GTab{nullptr, reinterpret_cast<float* const*>(h->d_shard_tab + MAX_SHARDS), shift, n_shards - 1};
   return MVIN_OK;
+}
+
+// ---- owner-side partial reduction of the leaf level (exchange.cuh) ------------------------------------------
+int mvin_xchg_bind(mvin_handle_t h, int32_t n_src, int32_t src_index, int64_t rows, const int32_t* ids_all,
+                   float* const* part, float* const* gsu, float* const* dot) {
+  if (!h) return fail(MVIN_ERR_INVALID, "null argument");
+  if (n_src == 0) { h->xchg.on = false; return MVIN_OK; }
+  if (!ids_all || !part || !gsu || !dot) return fail(MVIN_ERR_INVALID, "null argument");
+  if (h->n_shards < 2) return fail(MVIN_ERR_STATE, "mvin_xchg_bind needs a row-sharded entity table (mvin_bind_entity_shards)");
+  if (n_src < 1 || n_src > XCHG_MAX_RANKS || src_index < 0 || src_index >= n_src || rows < 1)
+    return fail(MVIN_ERR_INVALID, "bad exchange geometry (n_src %d, src_index %d, rows %ld)", n_src, src_index, (long)rows);
+  for (int s = 0; s < n_src; ++s) {
+    if (!part[s] || !gsu[s] || !dot[s]) return fail(MVIN_ERR_INVALID, "null exchange buffer of source %d", s);
+    h->xchg.part[s] = part[s]; h->xchg.gsu[s] = gsu[s]; h->xchg.dot[s] = dot[s];
+  }
+  h->xchg.n_src = n_src; h->xchg.src_index = src_index; h->xchg.rows = rows; h->xchg.ids_all = ids_all;
+  h->xchg.on = true;
+  return MVIN_OK;
+}
+
+int mvin_xchg_expand(mvin_handle_t h, const int64_t* item_indices, int32_t B, int32_t* ids_out, void* workspace,
+                     void* stream) {
+  if (!h || !item_indices || !ids_out || !workspace) return fail(MVIN_ERR_INVALID, "null argument");
+  if (!h->xchg.on) return fail(MVIN_ERR_STATE, "exchange buffers not bound (mvin_xchg_bind)");
+  if (B < 1 || B > h->cfg.max_batch) return fail(MVIN_ERR_INVALID, "B = %d outside 1..max_batch (%d)", B, h->cfg.max_batch);
+  if (!h->has_params || !h->adj) return fail(MVIN_ERR_STATE, "parameters / adjacency not bound");
+  h->B = B;
+  return dispatch_xchg_expand(h, item_indices, B, ids_out, workspace, (cudaStream_t)stream);
+}
+
+int mvin_xchg_owner_forward(mvin_handle_t h, int32_t owner, void* workspace, void* stream) {
+  if (!h || !workspace) return fail(MVIN_ERR_INVALID, "null argument");
+  if (!h->xchg.on || h->B < 1) return fail(MVIN_ERR_STATE, "mvin_xchg_owner_forward must follow mvin_xchg_expand");
+  if (owner < 0 || owner >= h->n_shards) return fail(MVIN_ERR_INVALID, "owner %d outside 0..%d", owner, h->n_shards - 1);
+  return dispatch_xchg_owner(h, owner, false, h->B, workspace, (cudaStream_t)stream);
+}
+
+int mvin_xchg_owner_backward(mvin_handle_t h, int32_t owner, void* workspace, void* stream) {
+  if (!h || !workspace) return fail(MVIN_ERR_INVALID, "null argument");
+  if (!h->xchg.on || h->fwd_workspace != workspace) return fail(MVIN_ERR_STATE, "mvin_xchg_owner_backward must follow mvin_backward");
+  if (owner < 0 || owner >= h->n_shards) return fail(MVIN_ERR_INVALID, "owner %d outside 0..%d", owner, h->n_shards - 1);
+  return dispatch_xchg_owner(h, owner, true, h->B, workspace, (cudaStream_t)stream);
+}
+
+int mvin_xchg_finish_backward(mvin_handle_t h, void* workspace, void* stream) {
+  if (!h || !workspace) return fail(MVIN_ERR_INVALID, "null argument");
+  if (!h->xchg.on || h->fwd_workspace != workspace) return fail(MVIN_ERR_STATE, "mvin_xchg_finish_backward must follow mvin_backward");
+  return dispatch_xchg_finish(h, h->B, workspace, (cudaStream_t)stream);
 }
 
 // ---- CUDA IPC plumbing for the peers' shards ---------------------------------------------------------------

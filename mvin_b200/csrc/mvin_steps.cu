@@ -11,4 +11,7 @@ template int forward_impl<MVIN_DIM>(mvin_handle_t, const int64_t*, const int32_t
                                     float*, void*, cudaStream_t);
 template int backward_init<MVIN_DIM>(mvin_handle_t, int, void*, cudaStream_t, cudaEvent_t, bool);
 template int backward_impl<MVIN_DIM>(mvin_handle_t, const float*, int, float*, void*, cudaStream_t);
+template int xchg_expand_impl<MVIN_DIM>(mvin_handle_t, const int64_t*, int, int32_t*, void*, cudaStream_t);
+template int xchg_owner_impl<MVIN_DIM>(mvin_handle_t, int, bool, int, void*, cudaStream_t);
+template int xchg_finish_impl<MVIN_DIM>(mvin_handle_t, int, void*, cudaStream_t);
 }  // namespace mvin_host

@@ -236,10 +236,16 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
         a.E = h->etab; a.u = at<float>(ws, L.u);
         a.Se = L.entity_leaf ? at<float>(ws, L.Se) : nullptr;
         a.Wt = P.transfer_w + (long)H * D * D; a.bt = P.transfer_b + (long)H * D;
+        if (h->xchg.on) {                                    // leaf rows already reduced by their owners (exchange.cuh)
+          if (L.rows[H - 1] != h->xchg.rows)
+            return fail(MVIN_ERR_STATE, "exchange buffers are bound for %ld leaf-level nodes, this batch has %ld", h->xchg.rows,
+                        L.rows[H - 1]);
+          a.Xpart = h->xchg.part[h->xchg.src_index]; a.xG = h->n_shards;
+        }
       }
       bool done = false;
       if constexpr (D == 32 || D == 64) {
-        if (i == 0 && use_tc_path(h, L.rows[H - 1])) {     // leaf iteration; inner-only iterations are faster on mma.sync
+        if (i == 0 && !h->xchg.on && use_tc_path(h, L.rows[H - 1])) {     // leaf iteration; inner-only iterations are faster on mma.sync
           const size_t smt = agg_fwd_tc_smem<D>(i == 0, K, nr);
           if (i == 0) {
             if ((rc = set_smem(agg_fwd_tc_kernel<D, true>, smt))) return rc;
@@ -488,6 +494,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
         a.dE = h->gtab; a.du = du;
         a.GSe = L.entity_leaf ? at<float>(ws, L.GSe) : nullptr;
         a.Se = L.entity_leaf ? at<float>(ws, L.Se) : nullptr; a.u = at<float>(ws, L.u);
+        if (h->xchg.on) a.Xgsu = h->xchg.gsu[h->xchg.src_index];
         const int grid = make_tile_list(a.tl, rows, nlev, C::R,
                                         h->sm_count * resident_ctas(h, agg_bwd_kernel<D, true>, C::NT, sm_leaf), h->d_sched + 2);
         MVIN_LAUNCH((agg_bwd_kernel<D, true>), grid, C::NT, sm_leaf, st, a);
@@ -591,9 +598,11 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     MVIN_LAUNCH((leaf_entity_kernel<D, true>), (unsigned)(want < cap ? want : cap), LEAF_NT, sm, st, a);
     LAUNCH_CHECK(h, "leaf_entity_bwd");
   }
-  MVIN_LAUNCH((rel_scores_bwd_kernel), H, 128, 0, st, P.relation_emb, P.agg_urh_w, at<float>(ws, L.ds), nr, D, G.relation_emb,
-                                           G.agg_urh_w);
-  LAUNCH_CHECK(h, "rel_scores_bwd");
+  if (!h->xchg.on) {       // exchange mode: ds of aggregator 0 is completed by the owners; mvin_xchg_finish_backward runs this
+    MVIN_LAUNCH((rel_scores_bwd_kernel), H, 128, 0, st, P.relation_emb, P.agg_urh_w, at<float>(ws, L.ds), nr, D, G.relation_emb,
+                                             G.agg_urh_w);
+    LAUNCH_CHECK(h, "rel_scores_bwd");
+  }
   }
   if (L.table) {
     // pair side of the tables: dMu_h = u^T dCs_h ; du += sum_h dCs_h (M1_h + M2_h)^T ; then the d x d parameter chain
@@ -726,6 +735,79 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
   par.join(1);
   MVIN_LAUNCH((finalize_loss_kernel), 1, 32, 0, st, acc, l2w, l2a, losses_out);
   LAUNCH_CHECK(h, "finalize_loss");
+  return MVIN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// exchange mode of the row-sharded entity table (exchange.cuh): the phases around forward_impl / backward_impl
+// ------------------------------------------------------------------------------------------------------
+// ids of the leaf-level parent nodes (level H-1) of this rank's batch + the relation scores the owners need
+template <int D>
+int xchg_expand_impl(mvin_handle_t h, const int64_t* item, int B, int32_t* ids_out, void* ws, cudaStream_t st) {
+  const mvin_config_t& c = h->cfg;
+  const int K = c.neighbor_sample_size, H = c.h_hop, nr = c.n_relation;
+  const Layout L = handle_layout(h, B);
+  MVIN_LAUNCH((seed_kernel), (unsigned)((B + 255) / 256), 256, 0, st, item, B, H == 1 ? ids_out : at<int32_t>(ws, L.ent[0]), nullptr);
+  LAUNCH_CHECK(h, "seed");
+  for (int lv = 0; lv + 1 < H; ++lv) {
+    const long n = L.rows[lv] * K;
+    MVIN_LAUNCH((expand_kernel), (unsigned)((n + 255) / 256), 256, 0, st, at<int32_t>(ws, L.ent[lv]), h->adj, L.rows[lv], K,
+                lv + 1 == H - 1 ? ids_out : at<int32_t>(ws, L.ent[lv + 1]), nullptr);
+    LAUNCH_CHECK(h, "expand");
+  }
+  MVIN_LAUNCH((rel_scores_kernel), (H * nr * 32 + 255) / 256, 256, 0, st, h->P.relation_emb, h->P.agg_urh_w, nr, D, H, at<float>(ws, L.s));
+  LAUNCH_CHECK(h, "rel_scores");
+  return MVIN_OK;
+}
+
+template <int D>
+int xchg_owner_impl(mvin_handle_t h, int owner, bool bwd, int B, void* ws, cudaStream_t st) {
+  const mvin_config_t& c = h->cfg;
+  const Layout L = handle_layout(h, B);
+  XchgArgs a;
+  memset(&a, 0, sizeof(a));
+  a.ids = h->xchg.ids_all; a.adj = h->adj; a.s = at<float>(ws, L.s);
+  a.E = static_cast<const float*>(h->shard_host[owner]);
+  a.dE = static_cast<float*>(h->shard_host[MAX_SHARDS + owner]);
+  for (int s = 0; s < h->xchg.n_src; ++s) { a.part[s] = h->xchg.part[s]; a.gsu[s] = h->xchg.gsu[s]; a.dot[s] = h->xchg.dot[s]; }
+  a.ds = at<float>(ws, L.ds);
+  a.rows = h->xchg.rows; a.n_src = h->xchg.n_src; a.owner = owner; a.shift = h->etab.shift; a.mask = h->etab.mask;
+  a.K = c.neighbor_sample_size; a.n_rel = c.n_relation;
+  const size_t sm = xchg_smem(c.n_relation, bwd);
+  const long want = ((long)a.n_src * a.rows + XCHG_NW - 1) / XCHG_NW;
+  const long cap = (long)h->sm_count * 8;
+  int rc;
+  if (bwd) {
+    if ((rc = set_smem(xchg_owner_bwd_kernel<D>, sm))) return rc;
+    MVIN_LAUNCH((xchg_owner_bwd_kernel<D>), (unsigned)(want < cap ? want : cap), XCHG_NT, sm, st, a);
+    LAUNCH_CHECK(h, "xchg_owner_bwd");
+  } else {
+    if ((rc = set_smem(xchg_owner_fwd_kernel<D>, sm))) return rc;
+    MVIN_LAUNCH((xchg_owner_fwd_kernel<D>), (unsigned)(want < cap ? want : cap), XCHG_NT, sm, st, a);
+    LAUNCH_CHECK(h, "xchg_owner_fwd");
+  }
+  return MVIN_OK;
+}
+
+// source side: close the softmax gradient of the leaf level with the owners' partial dots, then the relation-score
+// backward that backward_impl deferred
+template <int D>
+int xchg_finish_impl(mvin_handle_t h, int B, void* ws, cudaStream_t st) {
+  const mvin_config_t& c = h->cfg;
+  const Layout L = handle_layout(h, B);
+  XchgFinishArgs a;
+  memset(&a, 0, sizeof(a));
+  a.ids = h->xchg.ids_all + (long)h->xchg.src_index * h->xchg.rows; a.adj = h->adj; a.s = at<float>(ws, L.s);
+  a.dot = h->xchg.dot[h->xchg.src_index]; a.ds = at<float>(ws, L.ds);
+  a.rows = h->xchg.rows; a.G = h->n_shards; a.K = c.neighbor_sample_size; a.n_rel = c.n_relation;
+  const size_t sm = sizeof(float) * (size_t)c.n_relation * (1 + leaf_ds_copies(c.n_relation));
+  const long want = (a.rows + XCHG_NW - 1) / XCHG_NW;
+  const long cap = (long)h->sm_count * 8;
+  MVIN_LAUNCH((xchg_finish_bwd_kernel), (unsigned)(want < cap ? want : cap), XCHG_NT, sm, st, a);
+  LAUNCH_CHECK(h, "xchg_finish_bwd");
+  MVIN_LAUNCH((rel_scores_bwd_kernel), c.h_hop, 128, 0, st, h->P.relation_emb, h->P.agg_urh_w, at<float>(ws, L.ds), c.n_relation, D,
+              h->G.relation_emb, h->G.agg_urh_w);
+  LAUNCH_CHECK(h, "rel_scores_bwd");
   return MVIN_OK;
 }
 

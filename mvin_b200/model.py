@@ -72,7 +72,7 @@ def pack_user_triplet_set(user_triplet_set, n_user, n_hops, n_memory) -> np.ndar
 
 class MVIN(object):
     def __init__(self, args, n_user, n_entity, n_relation, adj_entity, adj_relation, device=None, seed: int = 1,
-                 entity_shards: int = 1, process_group=None):
+                 entity_shards: int = 1, process_group=None, leaf_exchange=None):
         """Reference signature (model.py:7) plus keyword-only extensions:
         device / seed      where the tables live, seed of the Xavier init;
         entity_shards = G  row-shard the entity table (and its gradient / Adam state) over G shards, entity e in
@@ -80,6 +80,10 @@ class MVIN(object):
         process_group      a torch.distributed group of G one-GPU ranks of one box: every rank owns shard `rank`
                            and maps the peers' shards through CUDA IPC (NVLink peer loads / reductions).  Without a
                            group all G shards live on this device ("virtual shards", used by the tests).
+        leaf_exchange      row-sharded table only: owner-side partial reduction of the deepest level (exchange.cuh;
+                           include/mvin_b200.h: mvin_xchg_*) -- the leaf rows are reduced by the rank that owns them and
+                           one d-vector per (parent node, owner) crosses NVLink instead of every raw row.  Default: on
+                           with a process group (env MVIN_B200_XCHG=0 turns it off), off for virtual shards.
         `adj_entity` may also be a packed device tensor int32 [n_entity, 2, K] (ids then relation ids) with
         adj_relation=None, for graphs too large for the reference's host-side int64 arrays."""
         if not torch.cuda.is_available():
@@ -97,6 +101,10 @@ class MVIN(object):
             self.rank = dist.get_rank(self.group)
         else:
             self.rank = 0
+        if leaf_exchange is None:
+            leaf_exchange = self.group is not None and os.environ.get("MVIN_B200_XCHG", "1") != "0"
+        self.leaf_exchange = bool(leaf_exchange) and self.n_shards > 1
+        self._xchg = None
         self._parse_args(args, adj_entity, adj_relation)
         self.n_user, self.n_entity, self.n_relation = int(n_user), int(n_entity), int(n_relation)
         self._build_inputs()
@@ -309,23 +317,100 @@ class MVIN(object):
         if self.group is not None:
             check(self.lib.mvin_set_batch_scale(self._handle, self.batch_size * G, 1.0 / G), "mvin_set_batch_scale")
 
+    def _fence(self):
+        """Stream-ordered barrier over the ranks of the group: a tiny NCCL all-reduce enqueued behind everything this
+        rank has enqueued so far; what any rank enqueues after it runs only once every rank's earlier work is complete.
+        No host synchronisation."""
+        if self.group is not None:
+            import torch.distributed as dist
+            if getattr(self, "_fence_buf", None) is None:
+                self._fence_buf = torch.zeros(1, dtype=torch.float32, device=self.device)
+            dist.all_reduce(self._fence_buf, group=self.group)
+
     def begin_step(self):
         """Sharded mode: zero this rank's entity-gradient shard(s) and fence the ranks (peers scatter into it during
         the backward pass and read the entity shard during the forward pass).  No-op otherwise."""
         if self.n_shards == 1:
             return
         self._entity_grad_all.zero_()
-        if self.group is not None:
-            import torch.distributed as dist
-            torch.cuda.synchronize(self.device)      # the zero fill has landed before any peer may scatter into it
-            dist.barrier(group=self.group)
+        self._fence()                                # the zero fill has landed before any peer may scatter into it
 
     def end_step(self):
-        """Sharded mode: fence the ranks after the backward pass (every peer's contribution has landed)."""
+        """Sharded mode: fence the ranks after the backward pass (every peer's contribution has landed).  Not needed
+        after allreduce_replicated(), which is itself a collective enqueued behind the backward pass of every rank."""
+        self._fence()
+
+    # ------------------------------------------------------------------ owner-side partial reduction (exchange.cuh)
+    def _bind_exchange(self, B):
+        """Exchange buffers for batches of B pairs: rows = B K^(H-1) leaf-level parent nodes per source rank.  One
+        process per GPU: every rank allocates its receive / send buffers and maps the peers' through CUDA IPC (a
+        collective: all ranks call it with the same B)."""
+        G, d = self.n_shards, self.dim
+        rows = B * self.n_neighbor ** (self.h_hop - 1)
+        n_src = G if self.group is not None else 1
+        x = dict(B=B, rows=rows,
+                 part=torch.zeros((G, rows, d), dtype=torch.float32, device=self.device),
+                 gsu=torch.zeros((rows, d), dtype=torch.float32, device=self.device),
+                 dot=torch.zeros((G, rows), dtype=torch.float32, device=self.device),
+                 ids=torch.zeros((n_src, rows), dtype=torch.int32, device=self.device),
+                 ids_mine=torch.zeros((rows,), dtype=torch.int32, device=self.device))
+        ptrs = {k: [x[k].data_ptr()] for k in ("part", "gsu", "dot")}
         if self.group is not None:
             import torch.distributed as dist
-            torch.cuda.synchronize(self.device)
+            mine = {}
+            for k in ("part", "gsu", "dot"):
+                hbuf = C.create_string_buffer(64)
+                off = C.c_int64()
+                check(self.lib.mvin_ipc_export(x[k].data_ptr(), hbuf, C.byref(off)), "mvin_ipc_export")
+                mine[k] = (hbuf.raw, int(off.value))
+            everyone = [None] * G
+            dist.all_gather_object(everyone, mine, group=self.group)
+            for k in ("part", "gsu", "dot"):
+                ptrs[k] = []
+                for r, theirs in enumerate(everyone):
+                    if r == self.rank:
+                        ptrs[k].append(x[k].data_ptr())
+                        continue
+                    ptr = C.c_void_p()
+                    check(self.lib.mvin_ipc_open(theirs[k][0], theirs[k][1], C.byref(ptr)), "mvin_ipc_open")
+                    ptrs[k].append(ptr.value)
             dist.barrier(group=self.group)
+        arr = {k: (C.c_void_p * n_src)(*ptrs[k]) for k in ptrs}
+        check(self.lib.mvin_xchg_bind(self._handle, n_src, self.rank if self.group is not None else 0, rows,
+                                      x["ids"].data_ptr(), arr["part"], arr["gsu"], arr["dot"]), "mvin_xchg_bind")
+        x["ptrs"] = ptrs
+        self._xchg = x
+
+    def _exchange_forward(self, items, B, ws):
+        """Phases in front of mvin_forward: my leaf-level parent ids -> every owner; owners reduce the rows they hold."""
+        if self._xchg is None or self._xchg["B"] != B:
+            self._bind_exchange(B)
+        x = self._xchg
+        st = self._stream()
+        if self.group is not None:
+            import torch.distributed as dist
+            check(self.lib.mvin_xchg_expand(self._handle, items.data_ptr(), B, x["ids_mine"].data_ptr(), ws.data_ptr(), st),
+                  "mvin_xchg_expand")
+            dist.all_gather_into_tensor(x["ids"].view(-1), x["ids_mine"], group=self.group)   # the index routing
+            check(self.lib.mvin_xchg_owner_forward(self._handle, self.rank, ws.data_ptr(), st), "mvin_xchg_owner_forward")
+            self._fence()                            # every owner's partials have landed in my receive buffer
+        else:
+            check(self.lib.mvin_xchg_expand(self._handle, items.data_ptr(), B, x["ids"].data_ptr(), ws.data_ptr(), st),
+                  "mvin_xchg_expand")
+            for g in range(self.n_shards):
+                check(self.lib.mvin_xchg_owner_forward(self._handle, g, ws.data_ptr(), st), "mvin_xchg_owner_forward")
+
+    def _exchange_backward(self, ws):
+        """Phases behind mvin_backward: owners scatter-add into their own shards and return the softmax partials."""
+        st = self._stream()
+        if self.group is not None:
+            self._fence()                            # every rank's gsu rows are complete
+            check(self.lib.mvin_xchg_owner_backward(self._handle, self.rank, ws.data_ptr(), st), "mvin_xchg_owner_backward")
+            self._fence()                            # every owner's partial dots have landed
+        else:
+            for g in range(self.n_shards):
+                check(self.lib.mvin_xchg_owner_backward(self._handle, g, ws.data_ptr(), st), "mvin_xchg_owner_backward")
+        check(self.lib.mvin_xchg_finish_backward(self._handle, ws.data_ptr(), st), "mvin_xchg_finish_backward")
 
     @staticmethod
     def _make_struct(tensors) -> Params:
@@ -411,6 +496,8 @@ class MVIN(object):
         B = items.shape[0]
         ws = self._ensure_workspace(B)
         self._keepalive = (users, items, mem_h, mem_r, mem_t)     # the library reads them again in backward
+        if self.leaf_exchange:
+            self._exchange_forward(items, B, ws)
         check(self.lib.mvin_forward(self._handle, users.data_ptr(), items.data_ptr(), mem_h.data_ptr(), mem_r.data_ptr(),
                                     mem_t.data_ptr(), B, scores.data_ptr() if scores is not None else None,
                                     scores_normalized.data_ptr() if scores_normalized is not None else None,
@@ -421,6 +508,8 @@ class MVIN(object):
         losses = self._losses_dev if losses is None else losses
         check(self.lib.mvin_backward(self._handle, labels.data_ptr(), labels.shape[0], losses.data_ptr(),
                                      self._workspace.data_ptr(), self._stream()), "mvin_backward")
+        if self.leaf_exchange:
+            self._exchange_backward(self._workspace)
         return losses
 
     def adam_step_device(self):
@@ -438,6 +527,19 @@ class MVIN(object):
             if apply_adam and self.group is None:
                 raise NotImplementedError("virtual shards (entity_shards > 1 without a process group) are fwd/bwd only")
             self.begin_step()
+        if self.leaf_exchange:
+            # the exchange phases sit between library calls, so the step is driven from here: feed H2D, forward,
+            # backward (with their owner phases), losses D2H
+            to = lambda a: (torch.from_numpy(a) if isinstance(a, np.ndarray) else a).to(self.device, non_blocking=True)
+            d = [to(a) for a in (users, items, labels, mem_h, mem_r, mem_t)]
+            self.forward_device(d[0], d[1], d[3], d[4], d[5])
+            self.backward_device(d[2], self._losses_dev)
+            losses = self._losses_dev.cpu().numpy().copy()
+            if self.group is not None:
+                losses = self.allreduce_replicated(losses)
+                if apply_adam:
+                    self.adam_step_device()
+            return losses
         fused_adam = apply_adam and self.group is None
         if fused_adam:
             self.step += 1

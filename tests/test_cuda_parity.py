@@ -227,29 +227,34 @@ def test_native_library_is_what_ran():
     assert any("libmvin_b200.so" in line for line in open("/proc/self/maps"))
 
 
-@pytest.mark.parametrize("G,n_entity", [(4, 301), (2, 300), (8, 500)])
-def test_virtual_entity_shards_match_oracle(G, n_entity):
+@pytest.mark.parametrize("xchg", [False, True])
+@pytest.mark.parametrize("G,n_entity,dim,K,H,B", [(4, 301, 32, 8, 2, 48), (2, 300, 32, 8, 2, 48), (8, 500, 32, 8, 2, 48),
+                                                  (8, 700, 128, 64, 2, 5), (4, 333, 64, 5, 3, 9), (2, 200, 16, 33, 1, 70)])
+def test_virtual_entity_shards_match_oracle(G, n_entity, dim, K, H, B, xchg):
     """Row-sharded entity table (mvin_bind_entity_shards) with all shards on one device: same scores / loss /
-    gradients as the oracle's single table, including n_entity not divisible by the shard count."""
+    gradients as the oracle's single table, including n_entity not divisible by the shard count.  xchg: the leaf level
+    through the owner-side partial reduction (exchange.cuh) -- every shard plays its owner role in turn -- instead of
+    row gathers through the shard table."""
     from mvin_b200 import MVIN
-    args = make_args(dim=32, neighbor_sample_size=8, h_hop=2, p_hop=2, n_memory=16, batch_size=48)
+    args = make_args(dim=dim, neighbor_sample_size=K, h_hop=H, p_hop=2, n_memory=16, batch_size=B)
     prob = make_problem(args, n_entity=n_entity, seed=11 + G)
     model = MVIN(args, prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"], prob["adj_relation"],
-                 entity_shards=G)
+                 entity_shards=G, leaf_exchange=xchg)
     model.load_named_parameters({k: v.numpy() for k, v in prob["P"].items()})
     assert np.array_equal(model.named_parameters()["entity_emb_matrix"], prob["P"]["entity_emb_matrix"].numpy())
     fd = feed_dict(model, prob)
     out, grads = orc.loss_and_grads(prob["P"], prob["cfg"], prob["adj_entity"], prob["adj_relation"], prob["users"],
                                     prob["items"], prob["mem_h"], prob["mem_r"], prob["mem_t"], prob["labels"])
     assert rel_err(model.get_raw_scores(fd), out.scores.detach().numpy()) < SCORE_TOL
-    losses = model.loss_and_grads(fd)
-    assert abs(float(losses[0]) - float(out.loss.detach())) <= 1e-4 * max(1.0, abs(float(out.loss.detach())))
-    _assert_grads(model.named_gradients(), lambda k: grads[k].numpy())
+    for _ in range(2):
+        losses = model.loss_and_grads(fd)
+        assert abs(float(losses[0]) - float(out.loss.detach())) <= 1e-4 * max(1.0, abs(float(out.loss.detach())))
+        _assert_grads(model.named_gradients(), lambda k: grads[k].numpy())
     with pytest.raises(NotImplementedError):
         model.train(None, fd)
 
 
-def _rank_worker(rank, world, port, ret):
+def _rank_worker(rank, world, port, ret, xchg=True):
     import os
     import torch.distributed as dist
     from mvin_b200 import MVIN, sharding
@@ -262,7 +267,7 @@ def _rank_worker(rank, world, port, ret):
         prob = make_problem(args_g, n_entity=301, seed=5)
         args_l = make_args(dim=32, neighbor_sample_size=8, h_hop=2, p_hop=2, n_memory=16, batch_size=Bg // world)
         model = MVIN(args_l, prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"],
-                     prob["adj_relation"], entity_shards=world, process_group=dist.group.WORLD)
+                     prob["adj_relation"], entity_shards=world, process_group=dist.group.WORLD, leaf_exchange=xchg)
         model.load_named_parameters({k: v.numpy() for k, v in prob["P"].items()})
         dist.barrier()                                       # every shard is loaded before any peer reads it
         sl = sharding.split_batch(Bg, rank, world)
@@ -295,9 +300,10 @@ def _rank_worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_multi_rank_sharded_entity_table_matches_oracle(world):
-    """One process per GPU, entity table row-sharded over the ranks, peers' shards reached over NVLink: the forward
+@pytest.mark.parametrize("world,xchg", [(2, True), (2, False), (4, True), (8, True), (8, False)])
+def test_multi_rank_sharded_entity_table_matches_oracle(world, xchg):
+    """(xchg: the leaf level through the all-gather of parent ids + owner-side partial reduction + fused peer return of
+    exchange.cuh; otherwise raw-row peer gathers)  One process per GPU, entity table row-sharded over the ranks, peers' shards reached over NVLink: the forward
     scores, the summed loss and every gradient (each rank's entity-gradient shard included) equal the oracle's on the
     concatenated batch; replicated parameters stay identical after an Adam step.  Needs `world` GPUs (gpurun --gpus N;
     scripts/gpu_multi.sh runs it and commits the log under profiles/)."""
@@ -311,7 +317,7 @@ def test_multi_rank_sharded_entity_table_matches_oracle(world):
     s.close()
     ctx = mp.get_context("spawn")
     ret = ctx.Manager().dict()
-    procs = [ctx.Process(target=_rank_worker, args=(r, world, port, ret)) for r in range(world)]
+    procs = [ctx.Process(target=_rank_worker, args=(r, world, port, ret, xchg)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:

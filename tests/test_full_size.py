@@ -198,7 +198,11 @@ def test_c3_shape_size_triggered_branches(B, monkeypatch):
         other, _, _ = _build("last-fm_50core", 64, 2, 32, B, 2, 64)
         _spot_check(other, args, batch)
         other.train_step_host(*batch, apply_adam=False)
-        _assert_close(_grads(other), auto)
+        # two fp32 evaluation orders of 16.8 M ReLU pre-activations (entity-table form vs per-row maps) disagree on the
+        # sign of the handful that sit within rounding of zero; ONE such flip moves a column of db_a by one term of its
+        # 262 144-term sum (measured: 5.4e-7 on a largest entry of 1.3e-3).  Each implementation is held to 1e-4 against
+        # the fp64 oracle in test_c3_shape_mid_size_against_fp64_oracle; here the bound is what a few flips can produce.
+        _assert_close(_grads(other), auto, tol=1e-3)
 
 
 @pytest.mark.parametrize("table", ["0", "1"])
