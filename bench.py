@@ -277,7 +277,10 @@ def run_ours(a, w, wl_key):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a short collective timeout: a rank that leaves the lock-step of the sharded step should fail in minutes, not
+        # hold N GPUs for the default 10
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=150))
 
     B = w["B"]
     NB = 4 if w["dataset"].startswith("amazon") else 8
@@ -443,7 +446,10 @@ def run_ours(a, w, wl_key):
 
     # per-kernel device times, same steps, events recorded by the library on its launch stream
     prof = {}
-    if rank == 0:
+    # rank 0 only -- except with the owner-side exchange of the sharded table, whose forward / backward contain
+    # collectives: then every rank walks the same steps (and rank 0's timings are reported)
+    lockstep = group_mode and model.leaf_exchange
+    if rank == 0 or lockstep:
         import ctypes
         model.lib.mvin_profile_enable(model._handle, 1)
         torch.cuda.synchronize(dev)
@@ -452,10 +458,14 @@ def run_ours(a, w, wl_key):
         for i in range(n_prof):
             flush.zero_()
             u, it, lab, mh, mr, mt = devb[i % NB]
-            if group_mode:
+            if lockstep:
+                model.begin_step()
+            elif group_mode:
                 model._entity_grad_all.zero_()
             model.forward_device(u, it, mh, mr, mt)
             model.backward_device(lab, losses)
+            if lockstep:
+                model.end_step()
             model.lib.mvin_profile_read(model._handle, buf, len(buf))
             for rec in buf.value.decode().split(";"):
                 if rec:
@@ -584,6 +594,15 @@ def run_ours(a, w, wl_key):
                          f"its own time-sized sample"}
     if dp_mode:
         par = f"dp{world} replicas + grad all-reduce" if collective else f"dp{world} replicas (no collective: --no-allreduce)"
+    elif group_mode and model.leaf_exchange:
+        par = (f"dp{world}, entity table row-sharded over {world} GPUs; leaf level: all-gather of the parent ids + owner-side "
+               f"partial reduction returned through NVLink peer stores (exchange.cuh); replicated-gradient all-reduce")
+        rows_x = B * w["K"] ** (w["h_hop"] - 1)
+        collective = {"kind": "all_gather(ids) + fused peer return", "backend": "nccl + CUDA-IPC peer memory",
+                      "nvlink_bytes_in_per_rank_fwd": int((world - 1) * rows_x * (4 + 4 * w["dim"])),
+                      "nvlink_bytes_in_per_rank_bwd": int((world - 1) * rows_x * (4 + 4 * w["dim"])),
+                      "raw_row_design_bytes_per_direction": int(rows_x * w["K"] * (world - 1) // world * 4 * w["dim"]),
+                      "fences_per_step": 4}
     elif group_mode:
         par = (f"dp{world}, entity table row-sharded over {world} GPUs (NVLink peer gathers / peer reductions), "
                f"replicated-gradient all-reduce")

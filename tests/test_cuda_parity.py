@@ -260,7 +260,9 @@ def _rank_worker(rank, world, port, ret, xchg=True):
     from mvin_b200 import MVIN, sharding
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import datetime
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank),
+                            timeout=datetime.timedelta(seconds=120))
     try:
         Bg = 64
         args_g = make_args(dim=32, neighbor_sample_size=8, h_hop=2, p_hop=2, n_memory=16, batch_size=Bg)
