@@ -80,6 +80,42 @@ MVIN_DEV void bulk_prefetch_l2(const void* addr, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(addr), "r"(bytes) : "memory");
 }
 
+// ---- bulk asynchronous row copies global -> shared (cp.async.bulk, the non-tensor path of the TMA engine) with
+// mbarrier transaction-count completion.  The gather kernels stage the neighbour rows of the NEXT step into a per-warp
+// shared-memory ring while the current step is reduced: one 4d-byte copy instruction per row issued by one lane,
+// instead of d/4 dependent 16-byte register loads per row, and no registers / scoreboard slots held by the rows in flight.
+namespace bulk {
+MVIN_DEV uint32_t saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+MVIN_DEV void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(saddr(bar)), "r"(count) : "memory");
+}
+MVIN_DEV void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// one arrival that also announces `bytes` of pending copies
+MVIN_DEV void mbar_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(saddr(bar)), "r"(bytes) : "memory");
+}
+MVIN_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "BW_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra BD_%=;\n\t"
+      "bra BW_%=;\n\t"
+      "BD_%=:\n\t"
+      "}\n" ::"r"(saddr(bar)), "r"(parity)
+      : "memory");
+}
+// src, dst 16-byte aligned, bytes a multiple of 16; completion is signalled on `bar` (complete_tx)
+MVIN_DEV void copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(saddr(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(saddr(bar))
+               : "memory");
+}
+// orders this thread's earlier generic-proxy accesses to shared memory before later async-proxy (bulk copy) writes
+MVIN_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+}  // namespace bulk
+
 // vectorised reduction to global memory: one 16-byte red instead of four scalar atomics (sm_90+)
 MVIN_DEV void red_add4(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)

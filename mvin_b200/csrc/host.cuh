@@ -161,6 +161,8 @@ struct mvin_handle_s {
   int tc_mode = 1;                 // tcgen05 forward row kernels for d in {32, 64}: 0 never, 1 auto, 2 always (env MVIN_B200_TC)
   int table_mode = -1;             // entity-table form of aggregator iteration 0 (table.cuh): -1 auto, 0 off, 1 on
                                    // (env MVIN_B200_TABLE)
+  int ring_mode = 1;               // table-gather levels stage their rows with cp.async.bulk (level.cuh, RowRing): 0 off,
+                                   // 1 backward kernel, 2 forward kernel too (env MVIN_B200_RING)
   int tcb_mode = 1;                // tcgen05 backward kernels of the deepest level (level_tcb.cuh): 0 never, 1 auto, 2 always
                                    // (env MVIN_B200_TCBWD)
   int max_ctas_per_sm = 4;         // cap on resident CTAs per SM of the persistent row kernels (env MVIN_B200_CTAS_PER_SM)

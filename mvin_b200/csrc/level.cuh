@@ -335,6 +335,56 @@ MVIN_DEV void stage_tile(const int32_t* __restrict__ ent, const int32_t* __restr
 }
 MVIN_DEV int padded_k(int K) { return K | 1; }   // odd row pitch of the staged neighbour records (bank spread)
 
+// ---- per-warp two-slot ring of neighbour rows staged by bulk asynchronous copies (common.cuh, bulk::) ----------------
+// One step of the thread-mapped neighbour phase touches, per warp, G = 32 / LPR parent rows x W children = G W <= 32
+// table rows of 4 D bytes.  Lane (g, j) issues ONE cp.async.bulk for child j of the warp's g-th parent into the slot of
+// the NEXT step (completion: mbarrier transaction count) while the lanes reduce the current slot from shared memory;
+// 2 x 512 W bytes per warp.  d <= 64 (at d = 128 the ring of a 16-warp CTA does not fit beside the weights).
+template <int D>
+struct RowRing {
+  using C = TC<D>;
+  static constexpr bool ENABLED = D <= 64;
+  static constexpr int ROWS = C::G * C::W;              // rows per step
+  static constexpr int SLOT = ROWS * D;                 // floats per slot
+  static MVIN_HD size_t bytes() { return ENABLED ? (size_t)C::NW * (2 * SLOT * sizeof(float) + 2 * sizeof(uint64_t)) + 16 : 0; }
+  float* buf;          // this warp's [2][SLOT]
+  uint64_t* bar;       // this warp's [2]
+  uint32_t uses0, uses1;   // completed waits per slot (the parity to wait for is uses & 1)
+  uint32_t qi, qw;         // steps issued / waited
+
+  // carve the CTA's ring out of `base` (16-byte aligned), initialise the barriers; ends with a __syncthreads()
+  MVIN_DEV void init(unsigned char* base, int warp, int lane) {
+    buf = reinterpret_cast<float*>(base) + (size_t)warp * 2 * SLOT;
+    bar = reinterpret_cast<uint64_t*>(base + (size_t)C::NW * 2 * SLOT * sizeof(float)) + warp * 2;
+    uses0 = uses1 = qi = qw = 0;
+    if (lane == 0) { bulk::mbar_init(bar, 1); bulk::mbar_init(bar + 1, 1); }
+    bulk::fence_mbar_init();
+    __syncthreads();
+  }
+  // rows of the warp's groups: r_first + g * r_stride; children k0 .. k0 + W - 1
+  MVIN_DEV void issue(const float* __restrict__ tab, const int2* __restrict__ nb_s, int KP, int r_first, int r_stride, int k0,
+                      int K, long row0, long rows, int lane) {
+    const int slot = qi & 1;
+    const int g = lane / C::W, j = lane % C::W;
+    const int r = r_first + g * r_stride;
+    const bool valid = lane < ROWS && (row0 + r) < rows && (k0 + j) < K;
+    const unsigned m = __ballot_sync(FULL_MASK, valid);   // also: every lane has finished reading this slot
+    bulk::fence_proxy_async();
+    if (lane == 0) bulk::mbar_expect(bar + slot, (uint32_t)__popc(m) * D * (uint32_t)sizeof(float));
+    __syncwarp();
+    if (valid)
+      bulk::copy_g2s(buf + slot * SLOT + (g * C::W + j) * D, tab + (long)nb_s[r * KP + k0 + j].y * D, D * sizeof(float),
+                     bar + slot);
+    ++qi;
+  }
+  MVIN_DEV const float* wait() {
+    const int slot = qw & 1;
+    if (slot == 0) { bulk::mbar_wait(bar, uses0 & 1); ++uses0; } else { bulk::mbar_wait(bar + 1, uses1 & 1); ++uses1; }
+    ++qw;
+    return buf + slot * SLOT;
+  }
+};
+
 // W partial sums per lane -> complete sums across the LPR lanes of a row: butterfly reduce-scatter over the low
 // log2(W) lane bits (W - 1 shuffles), then an all-reduce over the remaining bits.  Returns the total of
 // v[lane % W]; lanes that agree on lane % W (within a row group) hold the same value.
@@ -545,6 +595,7 @@ struct AggArgs {
   const float* Wa;      // [D, D]
   const float* ba;      // [D]
   const float* Se;      // leaf, entity mode: [n_entity, D] per-entity S = sum_k p_k E[n_k] (leaf_entity_fwd_kernel)
+  int ring;             // the launch carries RowRing shared memory: virt levels stage their table rows with bulk copies
   const float* Xpart;   // leaf, exchange mode (exchange.cuh): [xG][rows, D] per-owner partial sums S^(g), S = sum_g
   int xG;
   int K, n_rel;
@@ -591,6 +642,10 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
   float4 bt = f4zero();
   if (HAS_LEAF) bt = ldg4(a.bt + tx * 4);
   const float invK = 1.f / (float)K;
+  RowRing<D> ring;
+  const bool use_ring = RowRing<D>::ENABLED && a.ring;
+  if (use_ring)
+    ring.init(reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(s_s + a.n_rel) + 15) & ~(uintptr_t)15), warp, lane);
   __syncthreads();
 
   for (int it = 0;; ++it) {
@@ -611,6 +666,43 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
       __syncthreads();
     }
     // ---- neighbour phase: thread-mapped ----
+    if (L.virt && use_ring) {
+      // children = relu(tab[id_k] + Cp[pair]), the table rows staged one step ahead by bulk copies (RowRing)
+      const int gq = lane / C::LPR, nc = (K + C::W - 1) / C::W;
+      ring.issue(L.tab, nb_s, KP, warp * C::G * C::TM, C::TM, 0, K, row0, L.rows, lane);
+#pragma unroll
+      for (int i = 0; i < C::TM; ++i) {
+        const int r = ty * C::TM + i;
+        const long row = row0 + r;
+        const bool valid = row < L.rows;
+        float4 sv = f4zero(), cv = f4zero();
+        if (valid) {
+          sv = ld4a(L.self + row * D + tx * 4, L.stream);
+          cv = ldg4(L.Cp + fastdiv(row, L.rpp_magic) * D + tx * 4);
+        }
+        const int2* nb = nb_s + r * KP;
+        float4 acc = f4zero();
+        for (int c = 0; c < nc; ++c) {
+          if (c + 1 < nc) ring.issue(L.tab, nb_s, KP, warp * C::G * C::TM + i, C::TM, (c + 1) * C::W, K, row0, L.rows, lane);
+          else if (i + 1 < C::TM) ring.issue(L.tab, nb_s, KP, warp * C::G * C::TM + i + 1, C::TM, 0, K, row0, L.rows, lane);
+          const float* slot = ring.wait() + gq * C::W * D + tx * 4;
+#pragma unroll
+          for (int j = 0; j < C::W; ++j) {
+            const int k = c * C::W + j;
+            if (valid && k < K) {
+              const float4 x = f4add(ld4(slot + j * D), cv);
+              acc = f4fma(__int_as_float(nb[k].x), make_float4(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f)), acc);
+            }
+          }
+        }
+        float4 o = f4zero();
+        if (valid) {
+          o = f4fma(invK, acc, sv);
+          st4a(L.Y + row * D + tx * 4, o, L.stream);
+        }
+        st4(&As[r * C::LD + tx * 4], o);
+      }
+    } else {
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) {
       const int r = ty * C::TM + i;
@@ -665,6 +757,7 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
         }
       }
       st4(&As[r * C::LD + tx * 4], o);
+    }
     }
     __syncthreads();
     // ---- dense phase: register tile / tensor cores ----
@@ -762,13 +855,16 @@ struct AggBwdArgs {
   float* GSe;           // leaf, entity mode: [n_entity, D] per-entity sum of gsu (consumed by leaf_entity_bwd_kernel)
   const float* Se;      // leaf, entity mode: [n_entity, D] (S + u is recomputed, not stored)
   const float* u;       // leaf, entity mode: [B, D]
+  int ring;             // as in AggArgs
   float* Xgsu;          // leaf, exchange mode (exchange.cuh): [rows, D] gsu = dL/dS of every leaf-level node, left for the
                         // owners of the leaf rows (their scatter-add and the softmax gradient happen on the owner)
   int K, n_rel;
 };
 
-template <int D, bool HAS_LEAF>
-__global__ void __launch_bounds__(TC<D>::NT, (D <= 64 ? 3 : 1)) agg_bwd_kernel(AggBwdArgs a) {
+// RING: table-gather levels stage their rows through the bulk-copy ring (RowRing; d <= 64).  The ring's shared memory
+// limits the SM to two CTAs, so that instantiation is compiled for two (128 registers instead of 85).
+template <int D, bool HAS_LEAF, bool RING = false>
+__global__ void __launch_bounds__(TC<D>::NT, (RING ? 2 : D <= 64 ? 3 : 1)) agg_bwd_kernel(AggBwdArgs a) {
   pdl_enter();
   using C = TC<D>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -801,6 +897,10 @@ __global__ void __launch_bounds__(TC<D>::NT, (D <= 64 ? 3 : 1)) agg_bwd_kernel(A
   for (int i = 0; i < (HAS_LEAF ? C::DWN : 1); ++i) dwt[i][0] = dwt[i][1] = dwt[i][2] = dwt[i][3] = 0.f;
   float4 bpa = f4zero(), bpt = f4zero();
   bool had_leaf = false;
+  RowRing<D> ring;
+  constexpr bool use_ring = RING && RowRing<D>::ENABLED;
+  if constexpr (use_ring)
+    ring.init(reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ds_s + NWH * a.n_rel) + 15) & ~(uintptr_t)15), warp, lane);
   __syncthreads();
 
   for (int it = 0;; ++it) {
@@ -892,6 +992,9 @@ __global__ void __launch_bounds__(TC<D>::NT, (D <= 64 ? 3 : 1)) agg_bwd_kernel(A
     if (nbr_phase) {
       const int kl = lane & (C::W - 1);
       float4 cs[C::TM];                                      // virt: per-row sum of the children's pre-activation gradients
+      const bool rv = L.virt && use_ring;                    // table rows staged one step ahead by bulk copies (RowRing)
+      const int gq = lane / C::LPR;
+      if (rv) ring.issue(L.tab, nb_s, KP, warp * C::G * C::TM, C::TM, 0, K, row0, L.rows, lane);
 #pragma unroll
       for (int i = 0; i < C::TM; ++i) {
         const int r = ty * C::TM + i;
@@ -909,6 +1012,12 @@ __global__ void __launch_bounds__(TC<D>::NT, (D <= 64 ? 3 : 1)) agg_bwd_kernel(A
           if (c * C::W < K) {                                   // CTA-uniform
             float4 x[C::W];
             int2 v[C::W];
+            const float* slot = nullptr;
+            if (rv) {
+              if ((c + 1) * C::W < K) ring.issue(L.tab, nb_s, KP, warp * C::G * C::TM + i, C::TM, (c + 1) * C::W, K, row0, L.rows, lane);
+              else if (i + 1 < C::TM) ring.issue(L.tab, nb_s, KP, warp * C::G * C::TM + i + 1, C::TM, 0, K, row0, L.rows, lane);
+              slot = ring.wait() + gq * C::W * D + tx * 4;
+            }
 #pragma unroll
             for (int j = 0; j < C::W; ++j) {
               const int k = c * C::W + j;
@@ -918,7 +1027,7 @@ __global__ void __launch_bounds__(TC<D>::NT, (D <= 64 ? 3 : 1)) agg_bwd_kernel(A
                 v[j] = nb[k];
                 if (leaf) x[j] = ldg4(erow(a.E, v[j].y, D) + tx * 4);
                 else if (L.virt) {
-                  const float4 t = f4add(ldg4(L.tab + (long)v[j].y * D + tx * 4), cv);
+                  const float4 t = f4add(rv ? ld4(slot + j * D) : ldg4(L.tab + (long)v[j].y * D + tx * 4), cv);
                   x[j] = make_float4(fmaxf(t.x, 0.f), fmaxf(t.y, 0.f), fmaxf(t.z, 0.f), fmaxf(t.w, 0.f));
                 } else x[j] = ld4a(L.child + (row * K + k) * D + tx * 4, L.stream);
               }

@@ -267,9 +267,17 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
                                         h->sm_count * resident_ctas(h, agg_fwd_kernel<D, true>, C::NT, sm_leaf), h->d_sched);
         MVIN_LAUNCH((agg_fwd_kernel<D, true>), grid, C::NT, sm_leaf, st, a);
       } else {
+        // The forward gather keeps its register loads: with 35 KB of shared memory six CTAs per SM hold 196 KB of rows in
+        // flight, more than the two CTAs a ring leaves room for (measured at C4: 0.49 ms against 0.84 ms with the ring;
+        // MVIN_B200_RING=2 selects the ring here too).  The backward, whose loads compete with its red.global.add for
+        // issue slots, gains from it (2.32 -> 1.99 ms).
+        const bool ring = L.table && i == 1 && RowRing<D>::ENABLED && h->ring_mode == 2;
+        const size_t sm_i = sm_in + (ring ? RowRing<D>::bytes() : 0);
+        if (ring && (rc = set_smem(agg_fwd_kernel<D, false>, sm_i))) return rc;
+        a.ring = ring ? 1 : 0;
         const int grid = make_tile_list(a.tl, rows, nlev, C::R,
-                                        h->sm_count * resident_ctas(h, agg_fwd_kernel<D, false>, C::NT, sm_in), h->d_sched);
-        MVIN_LAUNCH((agg_fwd_kernel<D, false>), grid, C::NT, sm_in, st, a);
+                                        h->sm_count * resident_ctas(h, agg_fwd_kernel<D, false>, C::NT, sm_i), h->d_sched);
+        MVIN_LAUNCH((agg_fwd_kernel<D, false>), grid, C::NT, sm_i, st, a);
       }
       LAUNCH_CHECK(h, names[i]);
     }
@@ -499,9 +507,24 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
                                         h->sm_count * resident_ctas(h, agg_bwd_kernel<D, true>, C::NT, sm_leaf), h->d_sched + 2);
         MVIN_LAUNCH((agg_bwd_kernel<D, true>), grid, C::NT, sm_leaf, st, a);
       } else {
-        const int grid = make_tile_list(a.tl, rows, nlev, C::R,
-                                        h->sm_count * resident_ctas(h, agg_bwd_kernel<D, false>, C::NT, sm_in), h->d_sched + 2);
-        MVIN_LAUNCH((agg_bwd_kernel<D, false>), grid, C::NT, sm_in, st, a);
+        const bool ring = L.table && i == 1 && RowRing<D>::ENABLED && h->ring_mode != 0;
+        bool launched = false;
+        if constexpr (RowRing<D>::ENABLED) {
+          if (ring) {
+            const size_t sm_i = sm_in + RowRing<D>::bytes();
+            if ((rc = set_smem(agg_bwd_kernel<D, false, true>, sm_i))) return rc;
+            a.ring = 1;
+            const int grid = make_tile_list(a.tl, rows, nlev, C::R,
+                                            h->sm_count * resident_ctas(h, agg_bwd_kernel<D, false, true>, C::NT, sm_i), h->d_sched + 2);
+            MVIN_LAUNCH((agg_bwd_kernel<D, false, true>), grid, C::NT, sm_i, st, a);
+            launched = true;
+          }
+        }
+        if (!launched) {
+          const int grid = make_tile_list(a.tl, rows, nlev, C::R,
+                                          h->sm_count * resident_ctas(h, agg_bwd_kernel<D, false>, C::NT, sm_in), h->d_sched + 2);
+          MVIN_LAUNCH((agg_bwd_kernel<D, false>), grid, C::NT, sm_in, st, a);
+        }
       }
       LAUNCH_CHECK(h, names[i]);
       if constexpr (D == 32 || D == 64) {

@@ -129,6 +129,28 @@ def test_synthetic_vs_oracle(dim, K, H, p, m, B, regime, hub, table, monkeypatch
         _assert_grads(model.named_gradients(), lambda k: grads[k].numpy())
 
 
+@pytest.mark.parametrize("dim,K,H,B,p", [(64, 32, 2, 40, 2), (32, 16, 3, 9, 1), (16, 33, 2, 70, 2), (8, 5, 3, 11, 0)])
+@pytest.mark.parametrize("ring", ["0", "2"])
+def test_table_gather_ring_modes(dim, K, H, B, p, ring, monkeypatch):
+    """The table-gather level of the backward pass stages its rows through a per-warp ring of cp.async.bulk copies
+    (level.cuh, RowRing; MVIN_B200_RING=1, the default, exercised by every table = 1 case above).  0: register gathers
+    everywhere; 2: the forward kernel uses the ring too."""
+    from mvin_b200 import MVIN
+    monkeypatch.setenv("MVIN_B200_TABLE", "1")
+    monkeypatch.setenv("MVIN_B200_RING", ring)
+    args = make_args(dim=dim, neighbor_sample_size=K, h_hop=H, p_hop=p, n_memory=16, batch_size=B)
+    prob = make_problem(args, n_entity=320, seed=7 * dim + K + H, hub_frac=0.1)
+    model = MVIN(args, prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"], prob["adj_relation"])
+    model.load_named_parameters({k: v.numpy() for k, v in prob["P"].items()})
+    fd = feed_dict(model, prob)
+    out, grads = orc.loss_and_grads(prob["P"], prob["cfg"], prob["adj_entity"], prob["adj_relation"], prob["users"],
+                                    prob["items"], prob["mem_h"], prob["mem_r"], prob["mem_t"], prob["labels"])
+    assert rel_err(model.get_raw_scores(fd), out.scores.detach().numpy()) < SCORE_TOL
+    losses = model.loss_and_grads(fd)
+    assert abs(float(losses[0]) - float(out.loss)) <= 1e-4 * max(1.0, abs(float(out.loss)))
+    _assert_grads(model.named_gradients(), lambda k: grads[k].numpy())
+
+
 @pytest.mark.parametrize("dim,K,H,B", [(64, 32, 2, 40), (32, 16, 2, 80), (64, 8, 3, 5), (32, 5, 1, 300)])
 @pytest.mark.parametrize("entity_leaf", ["0", "1"])
 def test_tcgen05_forward_kernels(dim, K, H, B, entity_leaf, monkeypatch):
