@@ -55,6 +55,8 @@ typedef struct mvin_config {
 } mvin_config_t;
 
 #define MVIN_FLAGS_ALL 0x1f
+#define MVIN_FLAG_KG_EH 0x04      /* bit2: User_orient_kg_eh */
+#define MVIN_FLAGS_NO_KG_EH_UO 0x1b /* --ablation no_kg_eh_uo (parameter_ablation.py:22-30): the KG side is oriented by U[user] */
 
 /* The parameter set of MVIN._build_model (model.py:72-122) + the aggregators (aggregators.py:83-93), fp32,
  * device pointers.  The same struct describes a gradient set (same shapes) and Adam moment sets.

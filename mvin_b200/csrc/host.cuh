@@ -21,6 +21,7 @@
 #include "misc.cuh"
 #include "table.cuh"
 #include "exchange.cuh"
+#include "group.cuh"
 #include "umma.cuh"
 #include "umma_bf.cuh"
 #include "user.cuh"
@@ -107,12 +108,16 @@ struct Layout {
   size_t du, ditem, dO, wT;               // wT: [H + H + 1][D][D] transposed weights
   size_t zero_begin, ds, cnt, acc, zero_mid, dQ, dv, GSe, zero_end;   // cleared at the start of every backward:
                                           // [begin, mid) on the launch stream, [mid, end) on a side stream
+  size_t ukg, user32, dukg;               // User_orient_kg_eh = 0: U[user] rows, int32 user ids, their gradient (zeroed region)
   size_t stamp, Se;                       // entity mode of the leaf level (stamp is cleared by every forward)
   bool entity_leaf;
   // table mode (table.cuh): composed maps, per-entity tables A_h, per-pair vectors C_h and their gradients
   bool table;
   size_t Mc, cst, Atab, Cp;               // [H][TBL_NM][D][D], [H][D], [H][n_entity][D], [H][B][D]
   size_t dA, dCs, dM, dcst;               // [H][n_entity][D], [H][B][D], [H][3][D][D], [H][D]   (inside the zeroed region)
+  // entity-group evaluation of the table-gather level (group.cuh)
+  bool group;
+  size_t gcnt, goff, gtot, gorder, gesort, GP;   // int32 [n_entity] x 2, [4096 + 1], [rows(H-2)] x 2; fp32 [rows(H-2), D]
   size_t total;
   long rows[MAX_L + 1];
 };
@@ -161,6 +166,8 @@ struct mvin_handle_s {
   int tc_mode = 1;                 // tcgen05 forward row kernels for d in {32, 64}: 0 never, 1 auto, 2 always (env MVIN_B200_TC)
   int table_mode = -1;             // entity-table form of aggregator iteration 0 (table.cuh): -1 auto, 0 off, 1 on
                                    // (env MVIN_B200_TABLE)
+  int group_mode = 1;              // table-gather level per entity group (group.cuh): 0 off, 1 from 65 536 rows on, 2 whenever
+                                   // supported (env MVIN_B200_GROUP)
   int ring_mode = 1;               // table-gather levels stage their rows with cp.async.bulk (level.cuh, RowRing): 0 off,
                                    // 1 backward kernel, 2 forward kernel too (env MVIN_B200_RING)
   int tcb_mode = 1;                // tcgen05 backward kernels of the deepest level (level_tcb.cuh): 0 never, 1 auto, 2 always
@@ -255,7 +262,7 @@ inline bool tab_has_V(int H, int j, int h) {
   return h <= H - j;
 }
 
-inline Layout make_layout(const mvin_config_t& c, long B, bool entity_leaf, bool table = false) {
+inline Layout make_layout(const mvin_config_t& c, long B, bool entity_leaf, bool table = false, bool group = false) {
   Layout L;
   memset(&L, 0, sizeof(L));
   if (table) entity_leaf = true;           // Se / GSe / stamp are shared with the entity mode of the leaf level
@@ -277,6 +284,8 @@ inline Layout make_layout(const mvin_config_t& c, long B, bool entity_leaf, bool
   L.probs = take(f * (p + 1) * B * m);
   L.O = take(f * B * (p + 1) * D);
   L.u = take(f * B * D);
+  L.ukg = take(f * B * D);
+  L.user32 = take(sizeof(int32_t) * B);
   L.s = take(f * H * nr);
   if (!table) L.SU = take(f * L.rows[H - 1] * D);
   auto exists = [&](int j, int h) { return table ? (h < H && tab_has_V(H, j, h)) : has_V(H, j, h); };
@@ -299,6 +308,15 @@ inline Layout make_layout(const mvin_config_t& c, long B, bool entity_leaf, bool
     L.cst = take(f * H * D);
     L.Atab = take(f * H * (size_t)c.n_entity * D);
     L.Cp = take(f * H * B * D);
+    L.group = group && H >= 2;
+    if (L.group) {
+      L.gcnt = take(sizeof(int32_t) * (size_t)c.n_entity);
+      L.goff = take(sizeof(int32_t) * (size_t)c.n_entity);
+      L.gtot = take(sizeof(int32_t) * (2 * SCAN_PER_BLOCK + 2));
+      L.gorder = take(sizeof(int32_t) * L.rows[H - 2]);
+      L.gesort = take(sizeof(int32_t) * L.rows[H - 2]);
+      L.GP = take(f * L.rows[H - 2] * D);
+    }
   }
   L.du = take(f * B * D);
   L.ditem = take(f * B * D);
@@ -311,6 +329,7 @@ inline Layout make_layout(const mvin_config_t& c, long B, bool entity_leaf, bool
   L.zero_mid = off;
   L.dQ = take(f * B * nr * D);
   L.dv = take(f * B * D);
+  L.dukg = take(f * B * D);
   if (entity_leaf) L.GSe = take(f * (size_t)c.n_entity * D);
   if (table) {
     L.dA = take(f * H * (size_t)c.n_entity * D);
@@ -329,7 +348,14 @@ inline Layout make_layout(const mvin_config_t& c, long B, bool entity_leaf, bool
 
 inline Layout handle_layout(const mvin_handle_s* h, long B) {
   const bool table = use_table(h->cfg, B, h->n_shards, h->table_mode, h->entity_leaf_mode);
-  return make_layout(h->cfg, B, use_entity_leaf(h->cfg, B, h->n_shards, h->entity_leaf_mode), table);
+  // per-entity-group evaluation of the table-gather level: worth its sort and its two extra launches from 65 536 rows on
+  // (C4: 524 288 rows, 5.5 -> 4.5 ms per step; C3: 8 192 rows, 1.16 -> 1.28 ms); MVIN_B200_GROUP=2 forces it
+  long grows = B;
+  for (int hh = 1; hh + 1 < h->cfg.h_hop; ++hh) grows *= h->cfg.neighbor_sample_size;
+  const bool group = table && h->group_mode != 0 && (h->group_mode == 2 || grows >= 65536) &&
+                     grp_supported(h->cfg.dim, h->cfg.neighbor_sample_size) &&
+                     (long)h->cfg.n_entity <= (long)SCAN_PER_BLOCK * SCAN_PER_BLOCK;
+  return make_layout(h->cfg, B, use_entity_leaf(h->cfg, B, h->n_shards, h->entity_leaf_mode), table, group);
 }
 
 template <typename T>

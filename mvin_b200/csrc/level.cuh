@@ -582,6 +582,7 @@ struct AggLevel {
   int virt;
   const float* tab;     // [n_entity, D]  A_{h+1}
   const float* Cp;      // [B, D]         C_{h+1}
+  int preagg;           // Y already holds self + agg (group.cuh evaluated the neighbour phase per entity group)
 };
 struct AggArgs {
   AggLevel lv[MAX_LV];
@@ -661,7 +662,7 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
     const long row0 = (t - (lvl ? a.tl.tile_end[lvl - 1] : 0)) * C::R;
     // ---- stage phase: (p_k, id_k) of every row of the tile ----
     const bool x_mode = leaf && a.Xpart != nullptr;
-    if (!ent_mode && !x_mode) {
+    if (!ent_mode && !x_mode && !L.preagg) {
       stage_tile<D, false>(L.ent, a.adj, s_s, row0, L.rows, K, KP, nb_s, nullptr, warp, lane);
       __syncthreads();
     }
@@ -731,6 +732,8 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
           }
           o = f4add(acc, uv);
           st4a(L.SU + row * D + tx * 4, o, L.stream);
+        } else if (L.preagg) {
+          o = ld4a(L.Y + row * D + tx * 4, L.stream);
         } else if (L.virt) {
           const float4 sv = ld4a(L.self + row * D + tx * 4, L.stream);
           const float4 cv = ldg4(L.Cp + fastdiv(row, L.rpp_magic) * D + tx * 4);

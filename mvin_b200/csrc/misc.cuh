@@ -93,6 +93,21 @@ __global__ void prep_items_kernel(const int64_t* __restrict__ item, ETab E, int 
   st4(Vbuf + b * D + c * 4, ldg4(erow(E, e, D) + c * 4));
 }
 
+// ---- User_orient_kg_eh = 0 (model.py:152-156): ukg[b] = U[user[b]], and the user ids as int32 for the backward scatter
+template <int D>
+__global__ void gather_user_kernel(const int64_t* __restrict__ user, const float* __restrict__ U, int B,
+                                   float* __restrict__ ukg, int32_t* __restrict__ user32) {
+  pdl_enter();
+  constexpr int LPR = D / 4;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)B * LPR) return;
+  const long b = i / LPR;
+  const int c = (int)(i % LPR);
+  const long u = user[b];
+  if (c == 0) user32[b] = (int32_t)u;
+  st4(ukg + b * D + c * 4, ldg4(U + u * D + c * 4));
+}
+
 // ---- dE[ent[b]] += rows[b]   (row scatter-add of a dense [B, D] buffer) ---------------------------------
 template <int D>
 __global__ void scatter_rows_kernel(const float* __restrict__ rows, const int32_t* __restrict__ ent, int B, GTab dE) {

@@ -33,8 +33,8 @@ MVIN_EXTERN_D(8) MVIN_EXTERN_D(16) MVIN_EXTERN_D(32) MVIN_EXTERN_D(64) MVIN_EXTE
 #undef MVIN_EXTERN_D
 
 int check_supported(const mvin_config_t* c) {
-  if (c->flags != MVIN_FLAGS_ALL)
-    return fail(MVIN_ERR_UNSUPPORTED, "only --ablation all (flags 0x1f) is supported, got 0x%x", c->flags);
+  if (c->flags != MVIN_FLAGS_ALL && c->flags != MVIN_FLAGS_NO_KG_EH_UO)
+    return fail(MVIN_ERR_UNSUPPORTED, "only --ablation all (flags 0x1f) and no_kg_eh_uo (0x1b) are supported, got 0x%x", c->flags);
   if (c->n_mix_hop != 1) return fail(MVIN_ERR_UNSUPPORTED, "n_mix_hop must be 1, got %d", c->n_mix_hop);
   if (c->h_hop < 1 || c->h_hop > MAX_L) return fail(MVIN_ERR_UNSUPPORTED, "h_hop must be in 1..3, got %d", c->h_hop);
   const int d = c->dim;
@@ -149,6 +149,7 @@ int mvin_create(const mvin_config_t* cfg, mvin_handle_t* out) {
   if (const char* ev = getenv("MVIN_B200_ENTITY_LEAF")) h->entity_leaf_mode = atoi(ev) != 0 ? 1 : 0;
   if (const char* ev = getenv("MVIN_B200_USER_PB_FWD")) { const int n = atoi(ev); if (n == 1 || n == 2 || n == 4) h->user_pb_fwd = n; }
   if (const char* ev = getenv("MVIN_B200_TC")) { const int n = atoi(ev); if (n >= 0 && n <= 2) h->tc_mode = n; }
+  if (const char* ev = getenv("MVIN_B200_GROUP")) { const int n = atoi(ev); if (n >= 0 && n <= 2) h->group_mode = n; }
   if (const char* ev = getenv("MVIN_B200_RING")) { const int n = atoi(ev); if (n >= 0 && n <= 2) h->ring_mode = n; }
   if (const char* ev = getenv("MVIN_B200_TABLE")) h->table_mode = atoi(ev) != 0 ? 1 : 0;
   if (const char* ev = getenv("MVIN_B200_TCBWD")) { const int n = atoi(ev); if (n >= 0 && n <= 2) h->tcb_mode = n; }

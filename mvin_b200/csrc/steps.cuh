@@ -51,6 +51,31 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
                                                                  out, (lv + 1 == H - 1 || L.table) ? stamp : nullptr);
       LAUNCH_CHECK(h, "expand");
     }
+    // entity-group evaluation of the table-gather level (group.cuh): counting sort of the level-(H-2) rows by entity
+    if (L.group) {
+      const long rows = L.rows[H - 2];
+      const long ne = c.n_entity;
+      int32_t* cnt = at<int32_t>(ws, L.gcnt);
+      int32_t* off = at<int32_t>(ws, L.goff);
+      int32_t* tot = at<int32_t>(ws, L.gtot);
+      const int32_t* ent = at<int32_t>(ws, L.ent[H - 2]);
+      const unsigned nb = (unsigned)((ne + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK);
+      CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (size_t)ne, st));
+      MVIN_LAUNCH((grp_count_kernel), (unsigned)((rows + 255) / 256), 256, 0, st, ent, rows, cnt);
+      LAUNCH_CHECK(h, "grp_count");
+      MVIN_LAUNCH((scan_block_kernel), nb, SCAN_NT, 0, st, (const int32_t*)cnt, ne, off, tot);
+      LAUNCH_CHECK(h, "grp_scan");
+      if (nb > 1) {
+        MVIN_LAUNCH((scan_block_kernel), 1, SCAN_NT, 0, st, (const int32_t*)tot, (long)nb, tot + SCAN_PER_BLOCK + 1, (int32_t*)nullptr);
+        LAUNCH_CHECK(h, "grp_scan");
+        MVIN_LAUNCH((scan_add_kernel), nb, SCAN_NT, 0, st, off, ne, (const int32_t*)(tot + SCAN_PER_BLOCK + 1));
+        LAUNCH_CHECK(h, "grp_scan");
+      }
+      CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (size_t)ne, st));
+      MVIN_LAUNCH((grp_fill_kernel), (unsigned)((rows + 255) / 256), 256, 0, st, ent, rows, (const int32_t*)off, cnt,
+                  at<int32_t>(ws, L.gorder), at<int32_t>(ws, L.gesort));
+      LAUNCH_CHECK(h, "grp_fill");
+    }
     // relation scores of every aggregator
     {
       const int warps = H * nr;
@@ -133,6 +158,18 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
     }
     LAUNCH_CHECK(h, "user_fwd");
   }
+  // --ablation no_kg_eh_uo (User_orient_kg_eh = 0, model.py:152-156): the KG side is oriented by the raw user embedding
+  // U[user] instead of user_o; the score still uses user_o
+  const bool kg_eh = (c.flags & MVIN_FLAG_KG_EH) != 0;
+  const float* u_kg = at<float>(ws, L.u);
+  if (!kg_eh) {
+    if (!h->user) return fail(MVIN_ERR_INVALID, "user_indices are required when User_orient_kg_eh = 0");
+    const long n = (long)B * C::LPR;
+    MVIN_LAUNCH((gather_user_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, h->user, P.user_emb, B, at<float>(ws, L.ukg),
+                at<int32_t>(ws, L.user32));
+    LAUNCH_CHECK(h, "gather_user");
+    u_kg = at<float>(ws, L.ukg);
+  }
   par.join(0);
   // user-oriented transform of levels 0..L-1, one launch   (model.py:270-283)
   {
@@ -150,7 +187,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
       t.rows = rows[lv] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
         t.stream = stream_level(h, L.rows[lv], D);
     }
-    a.nlev = ntl; a.E = h->etab; a.u = at<float>(ws, L.u);
+    a.nlev = ntl; a.E = h->etab; a.u = u_kg;
     bool done = false;
     if constexpr (D == 32 || D == 64) {
       if (!L.table && use_tc_path(h, L.rows[H - 1])) {
@@ -172,7 +209,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
   const int n_virt_rows = H >= 2 ? H - 1 : 1;        // levels 0 .. max(H - 2, 0)
   if (L.table) {
     GemmArgs g = gemm_args();
-    g.A = at<float>(ws, L.u); g.sa_m = D; g.sa_k = 1; g.bsA = 0;
+    g.A = u_kg; g.sa_m = D; g.sa_k = 1; g.bsA = 0;
     g.B = at<float>(ws, L.Mc) + (long)TBL_MSUM * D * D; g.sb_k = D; g.sb_n = 1; g.bsB = (long)TBL_NM * D * D;
     g.C = at<float>(ws, L.Cp); g.ldc = D; g.bsC = (long)B * D;
     g.M = B; g.N = D; g.K = D; g.nbatch = H;
@@ -203,6 +240,23 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
     if ((rc = set_smem(agg_fwd_kernel<D, true>, sm_leaf))) return rc;
     if ((rc = set_smem(agg_fwd_kernel<D, false>, sm_in))) return rc;
     static const char* names[MAX_L] = {"agg_fwd_0", "agg_fwd_1", "agg_fwd_2"};
+    if (L.group) {
+      // neighbour phase of (iteration 1, level H-2) per entity group: Y = self + agg
+      GroupArgs ga;
+      memset(&ga, 0, sizeof(ga));
+      ga.order = at<int32_t>(ws, L.gorder); ga.esort = at<int32_t>(ws, L.gesort); ga.adj = h->adj;
+      ga.s = at<float>(ws, L.s) + nr;
+      ga.tab = at<float>(ws, L.Atab) + (long)(H - 1) * c.n_entity * D;
+      ga.Cp = at<float>(ws, L.Cp) + (long)(H - 1) * B * D;
+      ga.self = at<float>(ws, L.V[1][H - 2]); ga.Y = at<float>(ws, L.Y[1][H - 2]);
+      ga.rows = L.rows[H - 2]; ga.rpp_magic = div_magic(L.rows[H - 2] / B); ga.K = K; ga.n_rel = nr;
+      const size_t smg = grp_smem(nr, false);
+      if ((rc = set_smem(virt_group_kernel<D, false>, smg))) return rc;
+      const long want = ((ga.rows + GRP_WIN - 1) / GRP_WIN + GRP_NW - 1) / GRP_NW;
+      const long cap = (long)h->sm_count * 16;
+      MVIN_LAUNCH((virt_group_kernel<D, false>), (unsigned)(want < cap ? want : cap), GRP_NT, smg, st, ga);
+      LAUNCH_CHECK(h, "group_fwd");
+    }
     for (int i = L.table ? 1 : 0; i < H; ++i) {
       AggArgs a;
       memset(&a, 0, sizeof(a));
@@ -221,6 +275,8 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
         t.leaf = (i == 0 && lv == H - 1);
         if (t.leaf) {
           t.SU = at<float>(ws, L.SU);
+        } else if (L.table && i == 1 && lv == H - 2 && L.group) {
+          t.preagg = 1;                                      // Y = self + agg came from virt_group_kernel
         } else if (L.table && i == 1 && lv == H - 2) {       // children = iteration 0 of the deepest level, from its table
           t.virt = 1;
           t.tab = at<float>(ws, L.Atab) + (long)(H - 1) * c.n_entity * D;
@@ -233,7 +289,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
       a.Wa = P.agg_w + (long)i * D * D; a.ba = P.agg_b + (long)i * D;
       a.K = K; a.n_rel = nr;
       if (i == 0) {
-        a.E = h->etab; a.u = at<float>(ws, L.u);
+        a.E = h->etab; a.u = u_kg;
         a.Se = L.entity_leaf ? at<float>(ws, L.Se) : nullptr;
         a.Wt = P.transfer_w + (long)H * D * D; a.bt = P.transfer_b + (long)H * D;
         if (h->xchg.on) {                                    // leaf rows already reduced by their owners (exchange.cuh)
@@ -413,6 +469,10 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
   }
 
   float* du = at<float>(ws, L.du);
+  // User_orient_kg_eh = 0: the KG side read U[user] (forward_impl), its gradient goes to the user table, not to user_o
+  const bool kg_eh = (c.flags & MVIN_FLAG_KG_EH) != 0;
+  const float* u_kg = kg_eh ? at<float>(ws, L.u) : at<float>(ws, L.ukg);
+  float* du_kg = kg_eh ? du : at<float>(ws, L.dukg);
   float* ditem = at<float>(ws, L.ditem);
   const float invB = 1.f / (float)(h->global_batch > 0 ? h->global_batch : B);
   const bool fused_mix_bwd = D <= 64;          // W_mix^T ((H+1) d^2 floats) is staged in shared memory
@@ -474,6 +534,9 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
         t.leaf = (i == 0 && lv == H - 1);
         if (t.leaf) {
           t.SU = at<float>(ws, L.SU);
+        } else if (L.table && i == 1 && lv == H - 2 && L.group) {
+          t.defer = 1;                                       // the children's share is evaluated per entity group below
+          t.gp = at<float>(ws, L.GP);
         } else if (L.table && i == 1 && lv == H - 2) {
           t.virt = 1;
           t.tab = at<float>(ws, L.Atab) + (long)(H - 1) * c.n_entity * D;
@@ -499,15 +562,15 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
         par.join(0);       // zeroed dE / GSe / dQ / cnt are first needed here
         a.E = h->etab; a.WtT = wT + (long)(H + H) * D * D;
         a.dWt = G.transfer_w + (long)H * D * D; a.dbt = G.transfer_b + (long)H * D;
-        a.dE = h->gtab; a.du = du;
+        a.dE = h->gtab; a.du = du_kg;
         a.GSe = L.entity_leaf ? at<float>(ws, L.GSe) : nullptr;
-        a.Se = L.entity_leaf ? at<float>(ws, L.Se) : nullptr; a.u = at<float>(ws, L.u);
+        a.Se = L.entity_leaf ? at<float>(ws, L.Se) : nullptr; a.u = u_kg;
         if (h->xchg.on) a.Xgsu = h->xchg.gsu[h->xchg.src_index];
         const int grid = make_tile_list(a.tl, rows, nlev, C::R,
                                         h->sm_count * resident_ctas(h, agg_bwd_kernel<D, true>, C::NT, sm_leaf), h->d_sched + 2);
         MVIN_LAUNCH((agg_bwd_kernel<D, true>), grid, C::NT, sm_leaf, st, a);
       } else {
-        const bool ring = L.table && i == 1 && RowRing<D>::ENABLED && h->ring_mode != 0;
+        const bool ring = L.table && i == 1 && !L.group && RowRing<D>::ENABLED && h->ring_mode != 0;
         bool launched = false;
         if constexpr (RowRing<D>::ENABLED) {
           if (ring) {
@@ -527,6 +590,25 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
         }
       }
       LAUNCH_CHECK(h, names[i]);
+      if (L.group && i == 1) {
+        GroupArgs ga;
+        memset(&ga, 0, sizeof(ga));
+        ga.order = at<int32_t>(ws, L.gorder); ga.esort = at<int32_t>(ws, L.gesort); ga.adj = h->adj;
+        ga.s = at<float>(ws, L.s) + nr;
+        ga.tab = at<float>(ws, L.Atab) + (long)(H - 1) * c.n_entity * D;
+        ga.Cp = at<float>(ws, L.Cp) + (long)(H - 1) * B * D;
+        ga.gp = at<float>(ws, L.GP);
+        ga.dtab = at<float>(ws, L.dA) + (long)(H - 1) * c.n_entity * D;
+        ga.dCs = at<float>(ws, L.dCs) + (long)(H - 1) * B * D;
+        ga.ds = at<float>(ws, L.ds) + nr;
+        ga.rows = L.rows[H - 2]; ga.rpp_magic = div_magic(L.rows[H - 2] / B); ga.K = K; ga.n_rel = nr;
+        const size_t smg = grp_smem(nr, true);
+        if ((rc = set_smem(virt_group_kernel<D, true>, smg))) return rc;
+        const long want = ((ga.rows + GRP_WIN - 1) / GRP_WIN + GRP_NW - 1) / GRP_NW;
+        const long cap = (long)h->sm_count * 16;
+        MVIN_LAUNCH((virt_group_kernel<D, true>), (unsigned)(want < cap ? want : cap), GRP_NT, smg, st, ga);
+        LAUNCH_CHECK(h, "group_bwd");
+      }
       if constexpr (D == 32 || D == 64) {
         if (tcb0) {
           // deepest level of iteration 0 on the tensor cores (level_tcb.cuh): dself + the parents' dchild in one buffer
@@ -538,11 +620,11 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
           b.adj = h->adj; b.s = at<float>(ws, L.s);
           b.g1 = at<float>(ws, L.DC[1][lv]); b.V1 = at<float>(ws, L.V[1][lv]); b.Y = at<float>(ws, L.Y[0][lv]);
           b.T = at<float>(ws, L.V[0][lv]); b.GP = at<float>(ws, L.DC[0][lv]);
-          b.Se = at<float>(ws, L.Se); b.u = at<float>(ws, L.u);
+          b.Se = at<float>(ws, L.Se); b.u = u_kg;
           b.Wa = P.agg_w; b.Wt = P.transfer_w + (long)H * D * D;
           b.dT = at<float>(ws, L.DS[0][lv]);
           b.dWa = G.agg_w; b.dba = G.agg_b; b.dWt = G.transfer_w + (long)H * D * D; b.dbt = G.transfer_b + (long)H * D;
-          b.GSe = at<float>(ws, L.GSe); b.du = du; b.ds = at<float>(ws, L.ds);
+          b.GSe = at<float>(ws, L.GSe); b.du = du_kg; b.ds = at<float>(ws, L.ds);
           b.rows = L.rows[lv]; b.rpp = (int)(L.rows[lv] / B); b.rpp_magic = div_magic(b.rpp);
           b.K = K; b.n_rel = nr; b.stream = stream_level(h, L.rows[lv], D);
           while ((1 << b.kshift) < K) ++b.kshift;
@@ -632,7 +714,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     DwArgs a;
     memset(&a, 0, sizeof(a));
     for (int lv = 0; lv < H; ++lv) {
-      a.A[lv] = at<float>(ws, L.u); a.lda[lv] = D;
+      a.A[lv] = u_kg; a.lda[lv] = D;
       a.Gg[lv] = at<float>(ws, L.dCs) + (long)lv * B * D;
       a.dW[lv] = at<float>(ws, L.dM) + (long)(lv * 3 + 2) * D * D;
     }
@@ -641,7 +723,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     GemmArgs g = gemm_args();
     g.A = at<float>(ws, L.dCs); g.sa_m = D; g.sa_k = 1; g.bsA = (long)B * D;
     g.B = at<float>(ws, L.Mc) + (long)TBL_MSUM * D * D; g.sb_k = 1; g.sb_n = D; g.bsB = (long)TBL_NM * D * D;
-    g.C = du; g.ldc = D; g.bsC = 0;
+    g.C = du_kg; g.ldc = D; g.bsC = 0;
     g.M = B; g.N = D; g.K = D; g.nbatch = H; g.reduce = 1; g.accumulate = 1;
     if ((rc = run_gemm(h, st, g, "gemm_du_pair"))) return rc;
     MVIN_LAUNCH((compose_bwd_kernel), dim3(H, COMPOSE_SPLIT), 256, 0, st, P.transfer_w, P.transfer_b, P.agg_w, at<float>(ws, L.dM),
@@ -667,7 +749,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
       t.rows = rows[q] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
         t.stream = stream_level(h, L.rows[lv], D);
     }
-    a.nlev = ntl; a.E = h->etab; a.u = at<float>(ws, L.u); a.dE = h->gtab; a.du = du;
+    a.nlev = ntl; a.E = h->etab; a.u = u_kg; a.dE = h->gtab; a.du = du_kg;
     bool done = false;
     if constexpr (D == 32 || D == 64) {
       if (tcb) {
@@ -684,6 +766,12 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
       MVIN_LAUNCH((transform_bwd_kernel<D>), grid, C::NT, sm, st, a);
     }
     LAUNCH_CHECK(h, "transform_bwd");
+  }
+  if (!kg_eh) {
+    const long n = (long)B * C::LPR;
+    MVIN_LAUNCH((scatter_rows_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, du_kg, at<int32_t>(ws, L.user32), B,
+                GTab{G.user_emb, nullptr, 0, 0});
+    LAUNCH_CHECK(h, "scatter_du_user");
   }
   // user_o = O . W_user + b  backward
   {

@@ -633,8 +633,13 @@ class MVIN(object):
         import torch.distributed as dist
         if losses is not None:
             self.loss_slot.copy_(torch.as_tensor(losses, dtype=torch.float32))
-        dist.all_reduce(self.grad_flat[self._user_grad_end:], group=self.group)   # one bucket, in place
-        self.grads["user_emb"].mul_(float(self.n_shards))
+        if self.flags & 0x04:
+            # --ablation all: the user table only carries its dense L2 term (identical on every rank)
+            dist.all_reduce(self.grad_flat[self._user_grad_end:], group=self.group)   # one bucket, in place
+            self.grads["user_emb"].mul_(float(self.n_shards))
+        else:
+            # User_orient_kg_eh = 0: the KG side scatters into the user table, so it is exchanged with the rest
+            dist.all_reduce(self.grad_flat, group=self.group)
         return self.loss_slot.cpu().numpy()
 
     def allreduce_grads(self, group=None):

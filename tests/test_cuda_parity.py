@@ -13,7 +13,7 @@ from tests.synth import feed_dict, make_args, make_problem
 
 pytestmark = pytest.mark.gpu
 
-SUPPORTED_GOLDEN = ["h1_m1_p2", "h2_m1_p2", "h2_m1_p2_xavier", "h3_m1_p1"]
+SUPPORTED_GOLDEN = ["h1_m1_p2", "h2_m1_p2", "h2_m1_p2_xavier", "h3_m1_p1", "h2_m1_p2_no_kg_eh_uo"]
 SCORE_TOL = 1e-4
 GRAD_TOL = 1e-4
 
@@ -43,7 +43,8 @@ def _assert_grads(got, ref_of, tol=GRAD_TOL):
     assert not bad, bad
 
 
-# MVIN_B200_TABLE: "1" forces the entity-table form of aggregator iteration 0 (table.cuh), "0" the per-row kernels
+# MVIN_B200_TABLE: "1" forces the entity-table form of aggregator iteration 0 (table.cuh), "0" the per-row kernels.
+# With it the table-gather level runs per entity group (group.cuh) wherever the children fit the registers
 TABLE_MODES = ["0", "1"]
 
 
@@ -51,6 +52,7 @@ TABLE_MODES = ["0", "1"]
 @pytest.mark.parametrize("case", SUPPORTED_GOLDEN)
 def test_golden_forward_backward(case, table, monkeypatch):
     monkeypatch.setenv("MVIN_B200_TABLE", table)
+    monkeypatch.setenv("MVIN_B200_GROUP", "2")               # small problems: force the per-entity-group gather too
     model, z, cfg, fd = _model_from_golden(case)
     ents, rels = model.get_neighbors(z["items"])
     for i, e in enumerate(ents):
@@ -79,6 +81,7 @@ def test_golden_forward_backward(case, table, monkeypatch):
 @pytest.mark.parametrize("case", ["h2_m1_p2", "h3_m1_p1"])
 def test_golden_two_adam_steps(case, table, monkeypatch):
     monkeypatch.setenv("MVIN_B200_TABLE", table)
+    monkeypatch.setenv("MVIN_B200_GROUP", "2")               # small problems: force the per-entity-group gather too
     model, z, cfg, fd = _model_from_golden(case)
     _, loss0 = model.train(None, fd)
     _, loss1 = model.train(None, fd)
@@ -112,6 +115,7 @@ CASES = [
 def test_synthetic_vs_oracle(dim, K, H, p, m, B, regime, hub, table, monkeypatch):
     from mvin_b200 import MVIN
     monkeypatch.setenv("MVIN_B200_TABLE", table)
+    monkeypatch.setenv("MVIN_B200_GROUP", "2")               # small problems: force the per-entity-group gather too
     args = make_args(dim=dim, neighbor_sample_size=K, h_hop=H, p_hop=p, n_memory=m, batch_size=B)
     prob = make_problem(args, n_entity=300 if K < 64 else 500, seed=dim + K + H, regime=regime, hub_frac=hub)
     model = MVIN(args, prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"], prob["adj_relation"])
@@ -129,14 +133,40 @@ def test_synthetic_vs_oracle(dim, K, H, p, m, B, regime, hub, table, monkeypatch
         _assert_grads(model.named_gradients(), lambda k: grads[k].numpy())
 
 
+@pytest.mark.parametrize("table", TABLE_MODES)
+@pytest.mark.parametrize("dim,K,H,B,p", [(32, 16, 2, 80, 2), (64, 8, 3, 7, 1), (16, 8, 1, 96, 2), (128, 6, 2, 10, 2)])
+def test_no_kg_eh_uo_ablation(dim, K, H, B, p, table, monkeypatch):
+    """--ablation no_kg_eh_uo (User_orient_kg_eh = 0, model.py:152-156; the setting src/bash/main_att_case_st.sh runs and
+    half of the shipped case-study logs were produced with): the KG side is oriented by the raw user embedding U[user];
+    its gradient lands in the user table (repeated users in the batch accumulate)."""
+    from mvin_b200 import MVIN
+    monkeypatch.setenv("MVIN_B200_TABLE", table)
+    monkeypatch.setenv("MVIN_B200_GROUP", "2")               # small problems: force the per-entity-group gather too
+    args = make_args(dim=dim, neighbor_sample_size=K, h_hop=H, p_hop=p, n_memory=16, batch_size=B, User_orient_kg_eh=0)
+    prob = make_problem(args, n_user=17, n_entity=310, seed=dim + 3 * K + H)
+    model = MVIN(args, prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"], prob["adj_relation"])
+    model.load_named_parameters({k: v.numpy() for k, v in prob["P"].items()})
+    fd = feed_dict(model, prob)
+    out, grads = orc.loss_and_grads(prob["P"], prob["cfg"], prob["adj_entity"], prob["adj_relation"], prob["users"],
+                                    prob["items"], prob["mem_h"], prob["mem_r"], prob["mem_t"], prob["labels"])
+    assert rel_err(model.get_raw_scores(fd), out.scores.detach().numpy()) < SCORE_TOL
+    for _ in range(2):
+        losses = model.loss_and_grads(fd)
+        assert abs(float(losses[0]) - float(out.loss)) <= 1e-4 * max(1.0, abs(float(out.loss)))
+        _assert_grads(model.named_gradients(), lambda k: grads[k].numpy())
+
+
 @pytest.mark.parametrize("dim,K,H,B,p", [(64, 32, 2, 40, 2), (32, 16, 3, 9, 1), (16, 33, 2, 70, 2), (8, 5, 3, 11, 0)])
-@pytest.mark.parametrize("ring", ["0", "2"])
+@pytest.mark.parametrize("ring", ["0", "1", "2"])
 def test_table_gather_ring_modes(dim, K, H, B, p, ring, monkeypatch):
-    """The table-gather level of the backward pass stages its rows through a per-warp ring of cp.async.bulk copies
-    (level.cuh, RowRing; MVIN_B200_RING=1, the default, exercised by every table = 1 case above).  0: register gathers
-    everywhere; 2: the forward kernel uses the ring too."""
+    """The table-gather level of the entity-table mode has two implementations: per entity group (group.cuh, the default
+    where the children fit the registers -- exercised by every table = 1 case above) and per row inside the aggregator
+    kernels (MVIN_B200_GROUP=0; also the fallback for d K > 2048).  The per-row backward stages its rows through a
+    per-warp ring of cp.async.bulk copies (level.cuh, RowRing; MVIN_B200_RING=1); 0: register gathers everywhere; 2: the
+    forward kernel uses the ring too."""
     from mvin_b200 import MVIN
     monkeypatch.setenv("MVIN_B200_TABLE", "1")
+    monkeypatch.setenv("MVIN_B200_GROUP", "0")
     monkeypatch.setenv("MVIN_B200_RING", ring)
     args = make_args(dim=dim, neighbor_sample_size=K, h_hop=H, p_hop=p, n_memory=16, batch_size=B)
     prob = make_problem(args, n_entity=320, seed=7 * dim + K + H, hub_frac=0.1)
