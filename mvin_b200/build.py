@@ -18,7 +18,7 @@ OBJ_DIR = os.path.join(LIB_DIR, "obj")
 LIB_PATH = os.path.join(LIB_DIR, "libmvin_b200.so")
 DIMS = [8, 16, 32, 64, 128]
 SOURCES = ["mvin_capi.cu", "mvin_steps.cu"]
-HEADERS = ["common.cuh", "gemm.cuh", "level.cuh", "level_tc.cuh", "level_tcb.cuh", "misc.cuh", "user.cuh", "umma.cuh", "umma_bf.cuh", "host.cuh",
+HEADERS = ["common.cuh", "gemm.cuh", "level.cuh", "level_tc.cuh", "level_tcb.cuh", "misc.cuh", "user.cuh", "umma.cuh", "umma_bf.cuh", "gemm_tc.cuh", "host.cuh",
            "steps.cuh", "table.cuh", "group.cuh", "exchange.cuh", os.path.join("..", "..", "include", "mvin_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

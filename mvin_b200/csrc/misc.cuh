@@ -32,6 +32,17 @@ static __global__ void expand_kernel(const int32_t* __restrict__ ent, const int3
   if (stamp) stamp[id] = 1;
 }
 
+// stamp the neighbours of every entity that is present (count > 0) at the parent level
+static __global__ void stamp_children_kernel(const int32_t* __restrict__ present, const int32_t* __restrict__ adj, long n_entity,
+                                             int K, int32_t* __restrict__ stamp) {
+  pdl_enter();
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_entity * K) return;
+  const long e = i / K;
+  const int k = (int)(i % K);
+  if (__ldg(present + e) > 0) stamp[__ldg(adj + e * 2 * K + k)] = 1;
+}
+
 static __global__ void expand_i64_kernel(const int64_t* __restrict__ ent, const int32_t* __restrict__ adj, long rows,
                                   int K, int64_t* __restrict__ out_e, int64_t* __restrict__ out_r) {
   pdl_enter();

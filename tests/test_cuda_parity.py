@@ -226,12 +226,16 @@ def test_tcgen05_backward_kernels(dim, K, H, B, p, monkeypatch):
         _assert_grads(model.named_gradients(), lambda k: grads[k].numpy())
 
 
-@pytest.mark.parametrize("dim,n_rel", [(64, 150), (16, 150)])
-def test_many_relations(dim, n_rel):
+@pytest.mark.parametrize("dim,n_rel,B,tcg", [(64, 150, 24, "0"), (16, 150, 24, "0"), (64, 150, 24, "2"), (64, 39, 300, "2"),
+                                              (32, 70, 133, "2"), (32, 5, 1, "2")])
+def test_many_relations(dim, n_rel, B, tcg, monkeypatch):
     """n_relation > 128: one shared ds histogram per CTA instead of one per warp; with dim 64 the relation-KGE table
-    (n_rel d^2 floats) is too large for the fused Q build and Q comes from the batched GEMM."""
+    (n_rel d^2 floats) is too large for the fused Q build and Q comes from the batched GEMM.  tcg = 2 forces the tcgen05
+    versions of the three relation-batched contractions (gemm_tc.cuh: Q, dv, dRK), which the library selects from 512
+    pairs on; partial 128-row tiles, more relation splits than relations."""
     from mvin_b200 import MVIN
-    args = make_args(dim=dim, neighbor_sample_size=8, h_hop=2, p_hop=2, n_memory=16, batch_size=24)
+    monkeypatch.setenv("MVIN_B200_TCGEMM", tcg)
+    args = make_args(dim=dim, neighbor_sample_size=8, h_hop=2, p_hop=2, n_memory=16, batch_size=B)
     prob = make_problem(args, n_relation=n_rel, seed=11)
     model = MVIN(args, prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"], prob["adj_relation"])
     model.load_named_parameters({k: v.numpy() for k, v in prob["P"].items()})
