@@ -63,6 +63,7 @@ MVIN_DEV float4 ld4a(const float* p, bool cs) {
 MVIN_DEV void st4a(float* p, float4 v, bool cs) {
   if (cs) __stcs(reinterpret_cast<float4*>(p), v); else *reinterpret_cast<float4*>(p) = v;
 }
+MVIN_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 MVIN_DEV float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 MVIN_DEV float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 MVIN_DEV float4 f4scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
@@ -78,6 +79,42 @@ MVIN_DEV float f4dot(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * 
 // addr 16-byte aligned, bytes a multiple of 16.
 MVIN_DEV void bulk_prefetch_l2(const void* addr, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(addr), "r"(bytes) : "memory");
+}
+
+// ---- packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 process two floats per instruction; exact fp32 arithmetic) --------
+struct f2x2 { unsigned long long lo, hi; };                // a float4 as two 64-bit register pairs: (x, y), (z, w)
+MVIN_DEV unsigned long long pk2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+MVIN_DEV void upk2(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+MVIN_DEV f2x2 pack4(float4 v) { return f2x2{pk2(v.x, v.y), pk2(v.z, v.w)}; }
+MVIN_DEV float4 unpack4(f2x2 v) {
+  float4 r;
+  upk2(v.lo, r.x, r.y);
+  upk2(v.hi, r.z, r.w);
+  return r;
+}
+MVIN_DEV unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+MVIN_DEV unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+MVIN_DEV unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+MVIN_DEV float gt0(float x) {                              // 1.0f if x > 0 else 0.0f, one instruction
+  float r;
+  asm("set.gt.f32.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(x));
+  return r;
 }
 
 // ---- bulk asynchronous row copies global -> shared (cp.async.bulk, the non-tensor path of the TMA engine) with

@@ -116,10 +116,13 @@ struct GroupArgs {
 
 inline size_t grp_smem(int n_rel, bool bwd) { return sizeof(float) * (size_t)n_rel * (bwd ? 1 + GRP_NW : 1); }
 
-template <int D, bool BWD>
-__global__ void __launch_bounds__(GRP_NT, BWD ? 2 : 4) virt_group_kernel(GroupArgs a) {
+// SP (backward only): the children of a run are split over SP warps walking the same window (slot q' of warp `sub`
+// is child slot q' SP + sub), which halves the per-lane register arrays and doubles the resident warps; every warp
+// applies the softmax correction of ITS share of sum_k p_k dp_k to all K relations, so the warps never communicate.
+template <int D, bool BWD, int SP = 1>
+__global__ void __launch_bounds__(GRP_NT, BWD ? (SP == 2 ? 4 : 2) : 4) virt_group_kernel(GroupArgs a) {
   pdl_enter();
-  constexpr int LPR = D / 4, G = 32 / LPR;
+  constexpr int LPR = D / 4, G = 32 / LPR, KPL_T = GRP_KPL / SP;
   extern __shared__ __align__(16) float smem[];
   float* s_s = smem;
   float* ds_s = s_s + a.n_rel;                             // bwd: [NW][n_rel]
@@ -133,7 +136,9 @@ __global__ void __launch_bounds__(GRP_NT, BWD ? 2 : 4) virt_group_kernel(GroupAr
   const int kpl = (K + G - 1) / G;                         // children per lane group (<= GRP_KPL)
   const float invK = 1.f / (float)K;
   const long nwin = (a.rows + GRP_WIN - 1) / GRP_WIN;
-  for (long w = (long)blockIdx.x * GRP_NW + warp; w < nwin; w += (long)gridDim.x * GRP_NW) {
+  const long gw = (long)blockIdx.x * GRP_NW + warp;
+  const int sub = (int)(gw % SP);
+  for (long w = gw / SP; w < nwin; w += (long)gridDim.x * GRP_NW / SP) {
     const long pos0 = w * GRP_WIN;
     const int nrow = (int)min((long)GRP_WIN, a.rows - pos0);
     const int my_e = lane < nrow ? __ldg(a.esort + pos0 + lane) : -1;
@@ -144,7 +149,8 @@ __global__ void __launch_bounds__(GRP_NT, BWD ? 2 : 4) virt_group_kernel(GroupAr
       // the run of equal entities starting at position i (positions are sorted, so it is contiguous)
       const unsigned same = __ballot_sync(FULL_MASK, my_e == e && lane >= i);
       const int n = __popc(same);
-      // adjacency record, attention, table rows of the K children: once per run
+      // adjacency record, attention, table rows of the K children: once per run.  (Requesting the next run's record and
+      // the next window's rows ahead of time was measured and made the kernel slower: 0.76 -> 0.81 ms at C4.)
       const AdjRec rec = load_adj(a.adj, e, K, lane);
       float p0, p1;
       {
@@ -157,19 +163,19 @@ __global__ void __launch_bounds__(GRP_NT, BWD ? 2 : 4) virt_group_kernel(GroupAr
         p0 = e0 * inv;
         p1 = e1 * inv;
       }
-      float4 A[GRP_KPL];
-      float pq[GRP_KPL];
-      int idq[GRP_KPL];
+      f2x2 Ap[KPL_T];                                      // table rows of the children, as packed fp32 pairs
+      float pq[KPL_T];
+      int idq[KPL_T];
 #pragma unroll
-      for (int q = 0; q < GRP_KPL; ++q) {
-        const int k = q * G + g;                           // child of this lane group
+      for (int q = 0; q < KPL_T; ++q) {
+        const int k = (q * SP + sub) * G + g;              // child of this lane group
         const int src = k & 31;
         const int id_lo = __shfl_sync(FULL_MASK, rec.id0, src), id_hi = __shfl_sync(FULL_MASK, rec.id1, src);
         const float p_lo = __shfl_sync(FULL_MASK, p0, src), p_hi = __shfl_sync(FULL_MASK, p1, src);
-        const bool on = q < kpl && k < K;
+        const bool on = q * SP + sub < kpl && k < K;
         idq[q] = k < 32 ? id_lo : id_hi;
         pq[q] = on ? (k < 32 ? p_lo : p_hi) : 0.f;
-        A[q] = on ? ldg4(a.tab + (long)idq[q] * D + c * 4) : f4zero();
+        Ap[q] = pack4(on ? ldg4(a.tab + (long)idq[q] * D + c * 4) : f4zero());
       }
       if (!BWD) {
         // rows of the run, the next row's vectors requested while the current row is reduced
@@ -184,42 +190,48 @@ __global__ void __launch_bounds__(GRP_NT, BWD ? 2 : 4) virt_group_kernel(GroupAr
             cv_n = ldg4(a.Cp + fastdiv(row_n, a.rpp_magic) * D + c * 4);
             sv_n = ld4(a.self + row_n * D + c * 4);
           }
-          float4 acc0 = f4zero(), acc1 = f4zero();
+          // packed fp32 pairs (FADD2 / FFMA2): x = A + C, acc += p relu(x)
+          const f2x2 cvp = pack4(cv);
+          f2x2 acc0{0ull, 0ull}, acc1{0ull, 0ull};
 #pragma unroll
-          for (int q = 0; q < GRP_KPL; q += 2) {
+          for (int q = 0; q < KPL_T; q += 2) {
             if (q < kpl) {
-              const float4 x = f4add(A[q], cv);
-              acc0 = f4fma(pq[q], make_float4(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f)), acc0);
+              float4 x = unpack4(f2x2{add2(Ap[q].lo, cvp.lo), add2(Ap[q].hi, cvp.hi)});
+              const unsigned long long pp = pk2(pq[q], pq[q]);
+              acc0.lo = fma2(pp, pk2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)), acc0.lo);
+              acc0.hi = fma2(pp, pk2(fmaxf(x.z, 0.f), fmaxf(x.w, 0.f)), acc0.hi);
             }
             if (q + 1 < kpl) {
-              const float4 x = f4add(A[q + 1], cv);
-              acc1 = f4fma(pq[q + 1], make_float4(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f)), acc1);
+              float4 x = unpack4(f2x2{add2(Ap[q + 1].lo, cvp.lo), add2(Ap[q + 1].hi, cvp.hi)});
+              const unsigned long long pp = pk2(pq[q + 1], pq[q + 1]);
+              acc1.lo = fma2(pp, pk2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)), acc1.lo);
+              acc1.hi = fma2(pp, pk2(fmaxf(x.z, 0.f), fmaxf(x.w, 0.f)), acc1.hi);
             }
           }
-          const float4 acc = cross_group_sum4<LPR>(f4add(acc0, acc1));
+          const float4 acc = cross_group_sum4<LPR>(unpack4(f2x2{add2(acc0.lo, acc1.lo), add2(acc0.hi, acc1.hi)}));
           if (g == 0) st4(a.Y + row * D + c * 4, f4fma(invK, acc, sv));
           row = row_n; cv = cv_n; sv = sv_n;
         }
       } else {
         // W dot products are reduced together by the butterfly reduce-scatter of level.cuh (W - 1 shuffles for W sums):
         // lane c of a group ends up with dp of child slot q = ch W + c % W
-        constexpr int W = LPR < GRP_KPL ? LPR : GRP_KPL, NCH = GRP_KPL / W;
+        constexpr int W = LPR < KPL_T ? LPR : KPL_T, NCH = KPL_T / W;
         float myp[NCH];
         int myrel[NCH];
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
-          const int k = (ch * W + c % W) * G + g;
+          const int k = ((ch * W + c % W) * SP + sub) * G + g;
           const int src = k & 31;
           const float p_lo = __shfl_sync(FULL_MASK, p0, src), p_hi = __shfl_sync(FULL_MASK, p1, src);
           const int r_lo = __shfl_sync(FULL_MASK, rec.rel0, src), r_hi = __shfl_sync(FULL_MASK, rec.rel1, src);
-          const bool mine = k < K && ch * W + c % W < kpl && c < W;
+          const bool mine = k < K && (ch * W + c % W) * SP + sub < kpl && c < W;
           myp[ch] = mine ? (k < 32 ? p_lo : p_hi) : 0.f;
           myrel[ch] = mine ? (k < 32 ? r_lo : r_hi) : 0;
         }
-        float4 acc[GRP_KPL];
+        f2x2 acc[KPL_T];
         float dpsl[NCH];
 #pragma unroll
-        for (int q = 0; q < GRP_KPL; ++q) acc[q] = f4zero();
+        for (int q = 0; q < KPL_T; ++q) acc[q] = f2x2{0ull, 0ull};
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) dpsl[ch] = 0.f;
         long row = __shfl_sync(FULL_MASK, my_row, i);
@@ -236,25 +248,32 @@ __global__ void __launch_bounds__(GRP_NT, BWD ? 2 : 4) virt_group_kernel(GroupAr
             gr_n = ld4(a.gp + row_n * D + c * 4);
           }
           // acc[q] collects  sum_rows [x > 0] g  (the factor p_q is applied once, at the flush);  m collects  sum_q p_q [x > 0]
-          float4 m = f4zero();
-          float part[GRP_KPL];
+          // packed fp32 pairs (FADD2 / FMUL2 / FFMA2); the ReLU mask as 1.0 / 0.0 so that the accumulations are FMAs
+          const f2x2 cvp = pack4(cv), grp = pack4(gr);
+          f2x2 mp{0ull, 0ull};
+          float part[KPL_T];
 #pragma unroll
-          for (int q = 0; q < GRP_KPL; ++q) {
+          for (int q = 0; q < KPL_T; ++q) {
             part[q] = 0.f;
-            if (q < kpl) {                                 // warp-uniform
-              const float4 x = f4add(A[q], cv);
-              part[q] = f4dot(gr, make_float4(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f)));
-              const float pk = pq[q];
-              if (x.x > 0.f) { acc[q].x += gr.x; m.x += pk; }
-              if (x.y > 0.f) { acc[q].y += gr.y; m.y += pk; }
-              if (x.z > 0.f) { acc[q].z += gr.z; m.z += pk; }
-              if (x.w > 0.f) { acc[q].w += gr.w; m.w += pk; }
+            if (q * SP + sub < kpl) {                      // warp-uniform
+              const float4 x = unpack4(f2x2{add2(Ap[q].lo, cvp.lo), add2(Ap[q].hi, cvp.hi)});
+              const unsigned long long d2 = fma2(grp.hi, pk2(fmaxf(x.z, 0.f), fmaxf(x.w, 0.f)),
+                                                 mul2(grp.lo, pk2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f))));
+              float d0, d1;
+              upk2(d2, d0, d1);
+              part[q] = d0 + d1;
+              const unsigned long long k_lo = pk2(gt0(x.x), gt0(x.y)), k_hi = pk2(gt0(x.z), gt0(x.w));
+              const unsigned long long pp = pk2(pq[q], pq[q]);
+              acc[q].lo = fma2(k_lo, grp.lo, acc[q].lo);
+              acc[q].hi = fma2(k_hi, grp.hi, acc[q].hi);
+              mp.lo = fma2(k_lo, pp, mp.lo);
+              mp.hi = fma2(k_hi, pp, mp.hi);
             }
           }
-          float4 cs = make_float4(gr.x * m.x, gr.y * m.y, gr.z * m.z, gr.w * m.w);
+          float4 cs = unpack4(f2x2{mul2(grp.lo, mp.lo), mul2(grp.hi, mp.hi)});
 #pragma unroll
           for (int ch = 0; ch < NCH; ++ch) {
-            if (ch * W < kpl) {                            // warp-uniform
+            if (ch * W * SP + sub < kpl) {                 // warp-uniform
               float v[W];
 #pragma unroll
               for (int j = 0; j < W; ++j) v[j] = part[ch * W + j];
@@ -267,15 +286,20 @@ __global__ void __launch_bounds__(GRP_NT, BWD ? 2 : 4) virt_group_kernel(GroupAr
         }
         // flush the run: one reduction per child, the softmax gradient once per (run, child)
 #pragma unroll
-        for (int q = 0; q < GRP_KPL; ++q)
-          if (q < kpl && q * G + g < K) red_add4(a.dtab + (long)idq[q] * D + c * 4, f4scale(acc[q], pq[q]));
+        for (int q = 0; q < KPL_T; ++q)
+          if (q * SP + sub < kpl && (q * SP + sub) * G + g < K)
+            red_add4(a.dtab + (long)idq[q] * D + c * 4, f4scale(unpack4(acc[q]), pq[q]));
         float dotp = 0.f;
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) dotp = fmaf(myp[ch], dpsl[ch], dotp);     // myp = 0 on the lanes that do not own a slot
-        dotp = warp_sum(dotp);                             // sum_k p_k sum_rows dp_k
+        dotp = warp_sum(dotp);                             // this warp's share of sum_k p_k sum_rows dp_k
+        // ds[rel_k] += p_k sum_rows dp_k  for the warp's own children ...
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch)
-          if (myp[ch] != 0.f) atomicAdd(&ds_w[myrel[ch]], myp[ch] * (dpsl[ch] - dotp));
+          if (myp[ch] != 0.f) atomicAdd(&ds_w[myrel[ch]], myp[ch] * dpsl[ch]);
+        // ... and  ds[rel_k] -= p_k dotp  for ALL K children (lane l holds k = l and k = l + 32 of the record)
+        if (lane < K) atomicAdd(&ds_w[rec.rel0], -p0 * dotp);
+        if (lane + 32 < K) atomicAdd(&ds_w[rec.rel1], -p1 * dotp);
       }
       i += n;
     }

@@ -167,6 +167,7 @@ struct mvin_handle_s {
   int tc_mode = 1;                 // tcgen05 forward row kernels for d in {32, 64}: 0 never, 1 auto, 2 always (env MVIN_B200_TC)
   int table_mode = -1;             // entity-table form of aggregator iteration 0 (table.cuh): -1 auto, 0 off, 1 on
                                    // (env MVIN_B200_TABLE)
+  int group_split = 1;             // warps sharing a window of the backward group kernel: 1 or 2 (env MVIN_B200_GROUP_SPLIT)
   int tcg_mode = 1;                // tcgen05 relation-batched GEMMs of the user side (gemm_tc.cuh): 0 never, 1 from 512 pairs on,
                                    // 2 always (env MVIN_B200_TCGEMM)
   int group_mode = 1;              // table-gather level per entity group (group.cuh): 0 off, 1 from 65 536 rows on, 2 whenever

@@ -149,6 +149,7 @@ int mvin_create(const mvin_config_t* cfg, mvin_handle_t* out) {
   if (const char* ev = getenv("MVIN_B200_ENTITY_LEAF")) h->entity_leaf_mode = atoi(ev) != 0 ? 1 : 0;
   if (const char* ev = getenv("MVIN_B200_USER_PB_FWD")) { const int n = atoi(ev); if (n == 1 || n == 2 || n == 4) h->user_pb_fwd = n; }
   if (const char* ev = getenv("MVIN_B200_TC")) { const int n = atoi(ev); if (n >= 0 && n <= 2) h->tc_mode = n; }
+  if (const char* ev = getenv("MVIN_B200_GROUP_SPLIT")) h->group_split = atoi(ev) == 2 ? 2 : 1;
   if (const char* ev = getenv("MVIN_B200_TCGEMM")) { const int n = atoi(ev); if (n >= 0 && n <= 2) h->tcg_mode = n; }
   if (const char* ev = getenv("MVIN_B200_GROUP")) { const int n = atoi(ev); if (n >= 0 && n <= 2) h->group_mode = n; }
   if (const char* ev = getenv("MVIN_B200_RING")) { const int n = atoi(ev); if (n >= 0 && n <= 2) h->ring_mode = n; }

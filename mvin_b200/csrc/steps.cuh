@@ -638,10 +638,18 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
         ga.ds = at<float>(ws, L.ds) + nr;
         ga.rows = L.rows[H - 2]; ga.rpp_magic = div_magic(L.rows[H - 2] / B); ga.K = K; ga.n_rel = nr;
         const size_t smg = grp_smem(nr, true);
-        if ((rc = set_smem(virt_group_kernel<D, true>, smg))) return rc;
-        const long want = ((ga.rows + GRP_WIN - 1) / GRP_WIN + GRP_NW - 1) / GRP_NW;
+        const long nwin = (ga.rows + GRP_WIN - 1) / GRP_WIN;
         const long cap = (long)h->sm_count * 16;
-        MVIN_LAUNCH((virt_group_kernel<D, true>), (unsigned)(want < cap ? want : cap), GRP_NT, smg, st, ga);
+        if (h->group_split == 2) {
+          // the children of every run split over two warps: half the registers, twice the resident warps (group.cuh)
+          if ((rc = set_smem(virt_group_kernel<D, true, 2>, smg))) return rc;
+          const long want = (2 * nwin + GRP_NW - 1) / GRP_NW;
+          MVIN_LAUNCH((virt_group_kernel<D, true, 2>), (unsigned)(want < cap ? want : cap), GRP_NT, smg, st, ga);
+        } else {
+          if ((rc = set_smem(virt_group_kernel<D, true, 1>, smg))) return rc;
+          const long want = (nwin + GRP_NW - 1) / GRP_NW;
+          MVIN_LAUNCH((virt_group_kernel<D, true, 1>), (unsigned)(want < cap ? want : cap), GRP_NT, smg, st, ga);
+        }
         LAUNCH_CHECK(h, "group_bwd");
       }
       if constexpr (D == 32 || D == 64) {
