@@ -20,8 +20,9 @@ static __global__ void pack_adj_kernel(const int64_t* __restrict__ adjE, const i
 // ---- get_neighbors (model.py:243-256): one level of expansion, child k of node j at j*K+k -------------
 // `stamp` (optional): mark the produced ids (entity mode of the leaf level, level.cuh); `out` may be null (table mode:
 // the deepest level is only stamped, its ids are re-read from the adjacency records)
+// `bit`: the stamp is a mask of the levels the entity occurs at (table mode: bit h = level h); 1 elsewhere
 static __global__ void expand_kernel(const int32_t* __restrict__ ent, const int32_t* __restrict__ adj, long rows, int K,
-                              int32_t* __restrict__ out, int32_t* __restrict__ stamp) {
+                              int32_t* __restrict__ out, int32_t* __restrict__ stamp, int bit) {
   pdl_enter();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * K) return;
@@ -29,18 +30,18 @@ static __global__ void expand_kernel(const int32_t* __restrict__ ent, const int3
   const int k = (int)(i % K);
   const int32_t id = __ldg(adj + (long)ent[j] * 2 * K + k);
   if (out) out[i] = id;
-  if (stamp) stamp[id] = 1;
+  if (stamp) atomicOr(stamp + id, bit);
 }
 
 // stamp the neighbours of every entity that is present (count > 0) at the parent level
 static __global__ void stamp_children_kernel(const int32_t* __restrict__ present, const int32_t* __restrict__ adj, long n_entity,
-                                             int K, int32_t* __restrict__ stamp) {
+                                             int K, int32_t* __restrict__ stamp, int bit) {
   pdl_enter();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_entity * K) return;
   const long e = i / K;
   const int k = (int)(i % K);
-  if (__ldg(present + e) > 0) stamp[__ldg(adj + e * 2 * K + k)] = 1;
+  if (__ldg(present + e) > 0) atomicOr(stamp + __ldg(adj + e * 2 * K + k), bit);
 }
 
 static __global__ void expand_i64_kernel(const int64_t* __restrict__ ent, const int32_t* __restrict__ adj, long rows,
@@ -63,13 +64,13 @@ static __global__ void copy_i64_kernel(const int64_t* __restrict__ src, long n, 
 
 // ---- seeds: ent[0] = item as int32 (model.py:243-256 starts from item_indices); optional stamps -------------
 static __global__ void seed_kernel(const int64_t* __restrict__ item, int B, int32_t* __restrict__ ent0,
-                            int32_t* __restrict__ stamp) {
+                            int32_t* __restrict__ stamp) {   // level 0: stamp bit 0
   pdl_enter();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const long e = item[b];
   ent0[b] = (int32_t)e;
-  if (stamp) stamp[e] = 1;
+  if (stamp) atomicOr(stamp + e, 1);
 }
 
 // ---- feed assembly on the device (train.py:112-122, util.py:208-218): the ripple memories of a batch gathered from

@@ -64,7 +64,8 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
       int32_t* out = (L.table && lv + 1 == H - 1 && lv + 1 >= 2) ? nullptr : at<int32_t>(ws, L.ent[lv + 1]);
       if (!out && L.group) continue;     // stamped per DISTINCT parent entity after the group sort below
       MVIN_LAUNCH((expand_kernel), (unsigned)((n + 255) / 256), 256, 0, st, at<int32_t>(ws, L.ent[lv]), h->adj, L.rows[lv], K,
-                                                                 out, (lv + 1 == H - 1 || L.table) ? stamp : nullptr);
+                                                                 out, (lv + 1 == H - 1 || L.table) ? stamp : nullptr,
+                                                                 L.table ? 1 << (lv + 1) : 1);
       LAUNCH_CHECK(h, "expand");
     }
     // entity-group evaluation of the table-gather level (group.cuh): counting sort of the level-(H-2) rows by entity
@@ -95,7 +96,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
         // stamps of the deepest level: the children of every DISTINCT level-(H-2) entity (cnt > 0 after the fill), instead
         // of one store per level-(H-1) row (C4: 2.5 M instead of 16.8 M)
         const long n = ne * K;
-        MVIN_LAUNCH((stamp_children_kernel), (unsigned)((n + 255) / 256), 256, 0, st, (const int32_t*)cnt, h->adj, ne, K, stamp);
+        MVIN_LAUNCH((stamp_children_kernel), (unsigned)((n + 255) / 256), 256, 0, st, (const int32_t*)cnt, h->adj, ne, K, stamp, 1 << (H - 1));
         LAUNCH_CHECK(h, "expand");
       }
     }
@@ -939,7 +940,7 @@ int xchg_expand_impl(mvin_handle_t h, const int64_t* item, int B, int32_t* ids_o
   for (int lv = 0; lv + 1 < H; ++lv) {
     const long n = L.rows[lv] * K;
     MVIN_LAUNCH((expand_kernel), (unsigned)((n + 255) / 256), 256, 0, st, at<int32_t>(ws, L.ent[lv]), h->adj, L.rows[lv], K,
-                lv + 1 == H - 1 ? ids_out : at<int32_t>(ws, L.ent[lv + 1]), nullptr);
+                lv + 1 == H - 1 ? ids_out : at<int32_t>(ws, L.ent[lv + 1]), nullptr, 1);
     LAUNCH_CHECK(h, "expand");
   }
   MVIN_LAUNCH((rel_scores_kernel), (H * nr * 32 + 255) / 256, 256, 0, st, h->P.relation_emb, h->P.agg_urh_w, nr, D, H, at<float>(ws, L.s));

@@ -110,7 +110,7 @@ static __global__ void compose_bwd_kernel(const float* __restrict__ Wt, const fl
 
 // ---- per-entity tables ------------------------------------------------------------------------------------------
 struct TableArgs {
-  const int32_t* stamp;   // [n_entity] != 0: the entity occurs at some level < H of this batch
+  const int32_t* stamp;   // [n_entity] bit h set: the entity occurs at level h of this batch (A_h is needed for it)
   const float* E;         // [n_entity, D]
   const float* Se;        // [n_entity, D]   (valid where stamped)
   const float* M;         // [H][TBL_NM][D][D]
@@ -144,14 +144,14 @@ __global__ void __launch_bounds__(TC<D>::NT) table_fwd_kernel(TableArgs a) {
   const long ntiles = (a.n_entity + C::R - 1) / C::R;
   for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const long row0 = t * C::R;
-    const int mine = (tid < C::R && row0 + tid < a.n_entity && __ldg(a.stamp + row0 + tid) != 0) ? 1 : 0;
+    const int mine = (tid < C::R && row0 + tid < a.n_entity && ((__ldg(a.stamp + row0 + tid) >> h) & 1) != 0) ? 1 : 0;
     if (!__syncthreads_or(mine)) continue;                 // also fences the previous tile's reads of Es / Ss
     bool on[C::TM];
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) {
       const int r = ty * C::TM + i;
       const long row = row0 + r;
-      on[i] = row < a.n_entity && __ldg(a.stamp + row) != 0;
+      on[i] = row < a.n_entity && ((__ldg(a.stamp + row) >> h) & 1) != 0;
       float4 e = f4zero(), s = f4zero();
       if (on[i]) { e = ldg4(a.E + row * D + tx * 4); s = ld4(a.Se + row * D + tx * 4); }
       st4(&Es[r * C::LD + tx * 4], e);
@@ -200,14 +200,14 @@ __global__ void __launch_bounds__(TC<D>::NT) table_bwd_kernel(TableArgs a) {
   const long ntiles = (a.n_entity + C::R - 1) / C::R;
   for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const long row0 = t * C::R;
-    const int mine = (tid < C::R && row0 + tid < a.n_entity && __ldg(a.stamp + row0 + tid) != 0) ? 1 : 0;
+    const int mine = (tid < C::R && row0 + tid < a.n_entity && ((__ldg(a.stamp + row0 + tid) >> h) & 1) != 0) ? 1 : 0;
     if (!__syncthreads_or(mine)) continue;
     bool on[C::TM];
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) {
       const int r = ty * C::TM + i;
       const long row = row0 + r;
-      on[i] = row < a.n_entity && __ldg(a.stamp + row) != 0;
+      on[i] = row < a.n_entity && ((__ldg(a.stamp + row) >> h) & 1) != 0;
       float4 e = f4zero(), s = f4zero(), g = f4zero();
       if (on[i]) {
         e = ldg4(a.E + row * D + tx * 4);
