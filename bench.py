@@ -540,6 +540,12 @@ def run_ours(a, w, wl_key):
     peak, peak_src = load_peaks()
     fwd_b, bwd_b = bytes_per_pair(w)
     kb = kernel_bytes_per_step(w)
+    if w["h_hop"] >= 2:
+        # entity-table mode with the per-entity-group gather (group.cuh): group_fwd / group_bwd stand in for the gather of
+        # the deepest materialised level as the per-pair contract counts it (they gather each run's K rows once)
+        rows_x = B * w["K"] ** (w["h_hop"] - 1)
+        kb["group_fwd"] = rows_x * (4 * w["dim"] + 8)
+        kb["group_bwd"] = rows_x * (8 * w["dim"] + 8)
     traffic_all = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):

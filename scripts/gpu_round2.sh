@@ -31,10 +31,11 @@ for WL in $WLS; do
 done
 for WL in $FULL; do
   timeout 1200 ncu --set full --clock-control none --import-source on \
-      -k regex:'agg_(fwd|bwd)|leaf_entity|table_|virt_rows|ripple_bwd|user_fwd' \
-      -s 36 -c 12 -f -o $OUT/${TAG}_full_${WL} python bench.py --workload $WL --steps 2 --warmup 3 --quick --no-cpu-baseline \
+      -k regex:'agg_(fwd|bwd)|leaf_entity|table_|virt_|rel(q|dv|drk)_tc|ripple_bwd|user_fwd' \
+      -s 51 -c 17 -f -o $OUT/${TAG}_full_${WL} python bench.py --workload $WL --steps 2 --warmup 3 --quick --no-cpu-baseline \
       --no-parity-check > $OUT/${TAG}_ncu_full_${WL}.log 2>&1
   # the report is read back and summarised in the container (scripts/ncu_summary.py / ncu_lines.py): ncu --page source on
   # the GPU box stalled two calls for 15+ minutes
-  [ $(stat -c %s $OUT/${TAG}_full_${WL}.ncu-rep) -gt 24000000 ] && rm -f $OUT/${TAG}_full_${WL}.ncu-rep
+  timeout 120 python scripts/ncu_summary.py $OUT/${TAG}_full_${WL}.ncu-rep 10 > $OUT/${TAG}_ncu_full_${WL}.txt 2>/dev/null
+  [ $(stat -c %s $OUT/${TAG}_full_${WL}.ncu-rep) -gt 45000000 ] && rm -f $OUT/${TAG}_full_${WL}.ncu-rep
 done

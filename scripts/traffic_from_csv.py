@@ -36,6 +36,10 @@ def family(name, state, H):
         return f"agg_bwd_{H - state['b']}"
     if base == "leaf_entity_kernel":
         return "leaf_entity_bwd" if leaf else "leaf_entity_fwd"
+    if base == "virt_group_kernel":
+        return "group_bwd" if leaf else "group_fwd"
+    if base in ("relq_kernel", "reldv_kernel", "reldrk_kernel"):          # "_tc" was stripped above
+        return {"relq_kernel": "gemm_q", "reldv_kernel": "gemm_dv", "reldrk_kernel": "gemm_drk"}[base]
     if base == "virt_rows_kernel":
         return "virt_rows_bwd" if leaf else "virt_rows_fwd"
     if base == "agg_bwd_leaf_kernel":
