@@ -14,6 +14,8 @@
 
 namespace mvin {
 
+constexpr int RG_NT = 256;
+
 struct RelGemmArgs {
   const float* V;        // [B, D]           v = E[item]
   const float* RK;       // [n_rel, D, D]
@@ -22,13 +24,29 @@ struct RelGemmArgs {
   float* dE;             // dv:  entity-gradient table rows (+=) -- or a dense [B, D] buffer when rows == nullptr
   const int32_t* rows;   // dv:  [B] item ids
   float* dRK;            // drk: [n_rel, D, D] (+=)
+  const unsigned char* RKs;   // q / dv: relation matrices pre-split and pre-staged by rel_stage_kernel (below)
   int B, n_rel;
 };
 
-constexpr int RG_NT = 256;
+// The relation matrices as the tensor core reads them, built ONCE per step (parameters only): per relation four operand
+// images of OpLayout<D>::bytes(D) bytes -- {transposed, plain} x {hi, lo} -- so that the GEMM kernels fetch a relation's
+// operand with one bulk asynchronous copy (cp.async.bulk -> mbarrier complete_tx) instead of re-splitting and re-staging
+// it with all threads for every batch tile.
+template <int D>
+MVIN_HD constexpr size_t rel_stage_bytes() { return 4 * (size_t)umma::OpLayout<D>::bytes(D); }
+template <int D>
+__global__ void __launch_bounds__(RG_NT) rel_stage_kernel(const float* __restrict__ RK, unsigned char* __restrict__ out) {
+  pdl_enter();
+  using L = umma::OpLayout<D>;
+  const int r = blockIdx.x;
+  unsigned char* base = out + (size_t)r * rel_stage_bytes<D>();
+  if (blockIdx.y == 0) umma::stage_weight_t<D>(base, base + L::bytes(D), RK + (long)r * D * D, D, threadIdx.x, RG_NT);
+  else umma::stage_weight<D>(base + 2 * L::bytes(D), base + 3 * L::bytes(D), RK + (long)r * D * D, D, threadIdx.x, RG_NT);
+}
+
 
 template <int D>
-inline size_t relq_tc_smem() { return 2 * umma::OpLayout<D>::bytes(128) + 4 * umma::OpLayout<D>::bytes(D) + 64; }
+inline size_t relq_tc_smem() { return 2 * umma::OpLayout<D>::bytes(128) + 6 * umma::OpLayout<D>::bytes(D) + 64; }
 template <int D>
 inline size_t reldv_tc_smem() { return 4 * umma::OpLayout<D>::bytes(128) + 4 * umma::OpLayout<D>::bytes(D) + 64; }
 template <int D>
@@ -55,31 +73,45 @@ __global__ void __launch_bounds__(RG_NT) relq_tc_kernel(RelGemmArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* a_hi = smem_raw;
   unsigned char* a_lo = a_hi + L::bytes(128);
-  unsigned char* w_base = a_lo + L::bytes(128);            // [2][hi, lo]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(w_base + 4 * L::bytes(D));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  unsigned char* w_base = a_lo + L::bytes(128);            // [3][hi, lo]: ring of bulk-copied relation operands
+  uint64_t* bar = reinterpret_cast<uint64_t*>(w_base + 6 * L::bytes(D));   // [2] MMA done, [3] operand landed
+  uint64_t* wbar = bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 3);
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
   if (warp == 0) umma::tmem_alloc(tmem_slot, TCOLS);
   if (tid == 32) {
     umma::mbar_init(bar, 1);
     umma::mbar_init(bar + 1, 1);
+    for (int i = 0; i < 3; ++i) umma::mbar_init(wbar + i, 1);
     umma::fence_barrier_init();
   }
   const long row0 = (long)blockIdx.x * 128;
+  const int n_it = ((int)a.n_rel - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y;
+  // operand of iteration j (relation blockIdx.y + j gridDim.y): {transposed hi, lo} are contiguous in the staged image
+  auto fetch = [&](int j) {
+    const int r = blockIdx.y + j * gridDim.y;
+    bulk::mbar_expect(wbar + j % 3, 2 * L::bytes(D));
+    bulk::copy_g2s(w_base + (j % 3) * 2 * L::bytes(D), a.RKs + (size_t)r * rel_stage_bytes<D>(), 2 * L::bytes(D), wbar + j % 3);
+  };
   for (int i = tid; i < 128 * LPR; i += RG_NT) {
     const int r = i / LPR, k4 = i % LPR;
     float4 x = f4zero();
     if (row0 + r < a.B) x = ldg4(a.V + (row0 + r) * D + k4 * 4);
     umma::store_split<D>(a_hi, a_lo, r, k4, x);
   }
+  umma::fence_async_smem();
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
+  if (tid == 0) {
+    if (n_it > 0) fetch(0);
+    if (n_it > 1) fetch(1);
+  }
   const uint32_t tmem = *tmem_slot;
   const long my_row = row0 + 32 * (warp % 4) + lane;
-  int it = 0, r_prev = 0;
-  auto epilogue = [&](int e_it, int r) {
+  auto epilogue = [&](int e_it) {
     const int buf = e_it & 1;
+    const int r = blockIdx.y + e_it * gridDim.y;
     umma::mbar_wait(bar + buf, (uint32_t)((e_it >> 1) & 1));
     umma::fence_after_sync();
     float* out = a.Q + (my_row * a.n_rel + r) * D;
@@ -90,26 +122,26 @@ __global__ void __launch_bounds__(RG_NT) relq_tc_kernel(RelGemmArgs a) {
       }
     });
   };
-  for (int r = blockIdx.y; r < a.n_rel; r += gridDim.y, ++it) {
+  for (int it = 0; it < n_it; ++it) {
     const int buf = it & 1;
-    unsigned char* w_hi = w_base + buf * 2 * L::bytes(D);
-    unsigned char* w_lo = w_hi + L::bytes(D);
-    // this weight buffer and accumulator were last used by relation it - 2, whose completion the epilogue of the
-    // previous iteration has already awaited
-    umma::stage_weight_t<D>(w_hi, w_lo, a.RK + (long)r * D * D, D, tid, RG_NT);
-    umma::fence_async_smem();
-    umma::fence_before_sync();
-    __syncthreads();
-    umma::fence_after_sync();
+    if (it > 0) {                                          // accumulator `buf` was read by the epilogue of iteration it - 2
+      umma::fence_before_sync();
+      __syncthreads();
+      umma::fence_after_sync();
+    }
     if (tid == 0) {
-      umma::issue_3xtf32<D>(tmem + buf * D, umma::smem_u32(a_hi), umma::smem_u32(a_lo), umma::smem_u32(w_hi), umma::smem_u32(w_lo), D,
-                            true);
+      bulk::mbar_wait(wbar + it % 3, (uint32_t)((it / 3) & 1));
+      unsigned char* w_hi = w_base + (it % 3) * 2 * L::bytes(D);
+      umma::issue_3xtf32<D>(tmem + buf * D, umma::smem_u32(a_hi), umma::smem_u32(a_lo), umma::smem_u32(w_hi),
+                            umma::smem_u32(w_hi + L::bytes(D)), D, true);
       umma::commit(bar + buf);
     }
-    if (it > 0) epilogue(it - 1, r_prev);                  // overlaps the tensor-core work just issued
-    r_prev = r;
+    if (it > 0) epilogue(it - 1);                          // overlaps the tensor-core work just issued
+    // the operand slot of iteration it - 1 is free once its MMAs are complete (awaited by the epilogue just above)
+    if (tid == 0 && it + 2 < n_it && it > 0) fetch(it + 2);
+    if (tid == 0 && it == 0 && n_it > 2) { /* slot 2 has never been used */ fetch(2); }
   }
-  if (it > 0) epilogue(it - 1, r_prev);
+  if (n_it > 0) epilogue(n_it - 1);
   umma::fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, TCOLS);
@@ -124,13 +156,13 @@ __global__ void __launch_bounds__(RG_NT) reldv_tc_kernel(RelGemmArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* a_base = smem_raw;                        // [2][hi, lo]
   unsigned char* w_base = a_base + 4 * L::bytes(128);      // [2][hi, lo]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(w_base + 4 * L::bytes(D));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(w_base + 4 * L::bytes(D));   // [2] MMA done, [2] operand landed
+  uint64_t* wbar = bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 2);
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
   if (warp == 0) umma::tmem_alloc(tmem_slot, TCOLS);
   if (tid == 32) {
-    umma::mbar_init(bar, 1);
-    umma::mbar_init(bar + 1, 1);
+    for (int i = 0; i < 4; ++i) umma::mbar_init(bar + i, 1);
     umma::fence_barrier_init();
   }
   umma::fence_before_sync();
@@ -146,18 +178,24 @@ __global__ void __launch_bounds__(RG_NT) reldv_tc_kernel(RelGemmArgs a) {
     unsigned char* w_hi = w_base + buf * 2 * L::bytes(D);
     unsigned char* w_lo = w_hi + L::bytes(D);
     if (it >= 2) umma::mbar_wait(bar + buf, (uint32_t)(((it - 2) >> 1) & 1));   // the MMAs that read these buffers are done
+    if (tid == 0) {
+      // the relation's operand {plain hi, lo}: one bulk copy from the pre-staged image, in flight while the threads split
+      // and stage the dQ tile
+      bulk::mbar_expect(wbar + buf, 2 * L::bytes(D));
+      bulk::copy_g2s(w_hi, a.RKs + (size_t)r * rel_stage_bytes<D>() + 2 * L::bytes(D), 2 * L::bytes(D), wbar + buf);
+    }
     for (int i = tid; i < 128 * LPR; i += RG_NT) {
       const int rr = i / LPR, k4 = i % LPR;
       float4 x = f4zero();
       if (row0 + rr < a.B) x = ld4(a.dQ + ((row0 + rr) * a.n_rel + r) * D + k4 * 4);
       umma::store_split<D>(a_hi, a_lo, rr, k4, x);
     }
-    umma::stage_weight<D>(w_hi, w_lo, a.RK + (long)r * D * D, D, tid, RG_NT);
     umma::fence_async_smem();
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     if (tid == 0) {
+      bulk::mbar_wait(wbar + buf, (uint32_t)((it >> 1) & 1));
       umma::issue_3xtf32<D>(tmem, umma::smem_u32(a_hi), umma::smem_u32(a_lo), umma::smem_u32(w_hi), umma::smem_u32(w_lo), D, it == 0);
       umma::commit(bar + buf);
     }

@@ -109,6 +109,7 @@ struct Layout {
   size_t du, ditem, dO, wT;               // wT: [H + H + 1][D][D] transposed weights
   size_t zero_begin, ds, cnt, acc, zero_mid, dQ, dv, GSe, zero_end;   // cleared at the start of every backward:
                                           // [begin, mid) on the launch stream, [mid, end) on a side stream
+  size_t RKs;                             // relation matrices pre-staged for the tcgen05 GEMMs (gemm_tc.cuh), 0 = none
   size_t ukg, user32, dukg;               // User_orient_kg_eh = 0: U[user] rows, int32 user ids, their gradient (zeroed region)
   size_t stamp, Se;                       // entity mode of the leaf level (stamp is cleared by every forward)
   bool entity_leaf;
@@ -288,6 +289,7 @@ inline Layout make_layout(const mvin_config_t& c, long B, bool entity_leaf, bool
   L.probs = take(f * (p + 1) * B * m);
   L.O = take(f * B * (p + 1) * D);
   L.u = take(f * B * D);
+  if (D == 32 || D == 64) L.RKs = take((size_t)nr * 4 * (D / 8) * ((D / 4) * 144));   // nr x rel_stage_bytes<D>()
   L.ukg = take(f * B * D);
   L.user32 = take(sizeof(int32_t) * B);
   L.s = take(f * H * nr);

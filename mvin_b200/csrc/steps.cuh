@@ -158,6 +158,10 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
         RelGemmArgs ra;
         memset(&ra, 0, sizeof(ra));
         ra.V = at<float>(ws, L.Vbuf); ra.RK = P.relation_kge; ra.Q = at<float>(ws, L.Q); ra.B = B; ra.n_rel = nr;
+        ra.RKs = at<unsigned char>(ws, L.RKs);
+        // relation operands split and staged once per step (also read by the backward's dv kernel)
+        MVIN_LAUNCH((rel_stage_kernel<D>), dim3(nr, 2), RG_NT, 0, st, P.relation_kge, at<unsigned char>(ws, L.RKs));
+        LAUNCH_CHECK(h, "rel_stage");
         if ((rc = set_smem(relq_tc_kernel<D>, relq_tc_smem<D>()))) return rc;
         MVIN_LAUNCH((relq_tc_kernel<D>), rel_gemm_grid(h, B, nr), RG_NT, relq_tc_smem<D>(), st, ra);
         LAUNCH_CHECK(h, "gemm_q");
@@ -867,6 +871,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     g.C = G.relation_kge; g.ldc = D; g.bsC = (long)D * D;
     g.M = D; g.N = D; g.K = B; g.nbatch = nr; g.ksplit = pick_ksplit(B); g.accumulate = 1;
     const bool tcg = use_tc_gemm<D>(h, B);
+    const bool q_fused_fwd = user_q_fused(D, nr);
     if constexpr (D == 32 || D == 64) {
       if (tcg) {
         cudaStream_t st = par.s(0);
@@ -891,6 +896,11 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
         RelGemmArgs ra;
         memset(&ra, 0, sizeof(ra));
         ra.dQ = at<float>(ws, L.dQ); ra.RK = P.relation_kge; ra.B = B; ra.n_rel = nr;
+        ra.RKs = at<unsigned char>(ws, L.RKs);
+        if (q_fused_fwd) {                                   // the forward built Q inside the user kernel: stage the operands now
+          MVIN_LAUNCH((rel_stage_kernel<D>), dim3(nr, 2), RG_NT, 0, st, P.relation_kge, at<unsigned char>(ws, L.RKs));
+          LAUNCH_CHECK(h, "rel_stage");
+        }
         if (h->n_shards == 1) { ra.dE = G.entity_emb; ra.rows = at<int32_t>(ws, L.ent[0]); }
         else { ra.dE = at<float>(ws, L.dv); ra.rows = nullptr; }          // dense dv (zeroed region), scattered below
         if ((rc = set_smem(reldv_tc_kernel<D>, reldv_tc_smem<D>()))) return rc;
