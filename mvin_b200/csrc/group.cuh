@@ -109,6 +109,14 @@ struct GroupArgs {
   float* dtab;            // bwd: [n_entity, D] (+=)
   float* dCs;             // bwd: [B, D] (+=)
   float* ds;              // bwd: [n_rel] (+=)
+  // `fuse` (H >= 3): the rows of this level are not materialised either -- self[row] = relu(tab_self[e] + Cp_self[pair])
+  // is evaluated on the fly (per run / per row), and its gradient K gp * [self > 0] is summed per run into dtab_self
+  // and per row into dCs_self, so that neither V[1][h] nor its two gradient buffers exist
+  const float* tab_self;  // [n_entity, D] A_h
+  const float* Cp_self;   // [B, D]        C_h
+  float* dtab_self;       // bwd: [n_entity, D] (+=)
+  float* dCs_self;        // bwd: [B, D] (+=)
+  int fuse;
   long rows;
   unsigned long long rpp_magic;
   int K, n_rel;
@@ -180,15 +188,21 @@ __global__ void __launch_bounds__(GRP_NT, BWD ? (SP == 2 ? 4 : 2) : 4) virt_grou
       if (!BWD) {
         // rows of the run, the next row's vectors requested while the current row is reduced
         long row = __shfl_sync(FULL_MASK, my_row, i);
+        const float4 a_self = a.fuse ? ldg4(a.tab_self + (long)e * D + c * 4) : f4zero();
+        // sv: the self row, or (fuse) the pair vector C_h it is rebuilt from
         float4 cv = ldg4(a.Cp + fastdiv(row, a.rpp_magic) * D + c * 4);
-        float4 sv = ld4(a.self + row * D + c * 4);
+        float4 sv = a.fuse ? ldg4(a.Cp_self + fastdiv(row, a.rpp_magic) * D + c * 4) : ld4(a.self + row * D + c * 4);
         for (int t = 0; t < n; ++t) {
           long row_n = row;
           float4 cv_n = cv, sv_n = sv;
           if (t + 1 < n) {
             row_n = __shfl_sync(FULL_MASK, my_row, i + t + 1);
             cv_n = ldg4(a.Cp + fastdiv(row_n, a.rpp_magic) * D + c * 4);
-            sv_n = ld4(a.self + row_n * D + c * 4);
+            sv_n = a.fuse ? ldg4(a.Cp_self + fastdiv(row_n, a.rpp_magic) * D + c * 4) : ld4(a.self + row_n * D + c * 4);
+          }
+          if (a.fuse) {
+            const float4 x = f4add(a_self, sv);
+            sv = make_float4(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f));
           }
           // packed fp32 pairs (FADD2 / FFMA2): x = A + C, acc += p relu(x)
           const f2x2 cvp = pack4(cv);
@@ -238,14 +252,28 @@ __global__ void __launch_bounds__(GRP_NT, BWD ? (SP == 2 ? 4 : 2) : 4) virt_grou
         long pair = fastdiv(row, a.rpp_magic);
         float4 cv = ldg4(a.Cp + pair * D + c * 4);
         float4 gr = ld4(a.gp + row * D + c * 4);
+        const bool fuse = a.fuse != 0;
+        const float4 a_self = fuse ? ldg4(a.tab_self + (long)e * D + c * 4) : f4zero();
+        float4 cs_self = fuse ? ldg4(a.Cp_self + pair * D + c * 4) : f4zero();
+        float4 acc_self = f4zero();
+        const float Kf = (float)K;
         for (int t = 0; t < n; ++t) {
           long pair_n = pair;
-          float4 cv_n = cv, gr_n = gr;
+          float4 cv_n = cv, gr_n = gr, cs_self_n = cs_self;
           if (t + 1 < n) {
             const long row_n = __shfl_sync(FULL_MASK, my_row, i + t + 1);
             pair_n = fastdiv(row_n, a.rpp_magic);
             cv_n = ldg4(a.Cp + pair_n * D + c * 4);
             gr_n = ld4(a.gp + row_n * D + c * 4);
+            if (fuse) cs_self_n = ldg4(a.Cp_self + pair_n * D + c * 4);
+          }
+          if (fuse && sub == 0) {
+            // gradient of the row's own iteration-0 output: dself = K gp, masked by self = relu(A_h[e] + C_h[pair]) > 0
+            const float4 x = f4add(a_self, cs_self);
+            const float4 ds4 = make_float4(x.x > 0.f ? Kf * gr.x : 0.f, x.y > 0.f ? Kf * gr.y : 0.f, x.z > 0.f ? Kf * gr.z : 0.f,
+                                           x.w > 0.f ? Kf * gr.w : 0.f);
+            acc_self = f4add(acc_self, ds4);
+            if (g == 0) red_add4(a.dCs_self + pair * D + c * 4, ds4);
           }
           // acc[q] collects  sum_rows [x > 0] g  (the factor p_q is applied once, at the flush);  m collects  sum_q p_q [x > 0]
           // packed fp32 pairs (FADD2 / FMUL2 / FFMA2); the ReLU mask as 1.0 / 0.0 so that the accumulations are FMAs
@@ -282,8 +310,9 @@ __global__ void __launch_bounds__(GRP_NT, BWD ? (SP == 2 ? 4 : 2) : 4) virt_grou
           }
           cs = cross_group_sum4<LPR>(cs);
           if (g == 0) red_add4(a.dCs + pair * D + c * 4, cs);
-          pair = pair_n; cv = cv_n; gr = gr_n;
+          pair = pair_n; cv = cv_n; gr = gr_n; cs_self = cs_self_n;
         }
+        if (fuse && sub == 0 && g == 0) red_add4(a.dtab_self + (long)e * D + c * 4, acc_self);
         // flush the run: one reduction per child, the softmax gradient once per (run, child)
 #pragma unroll
         for (int q = 0; q < KPL_T; ++q)

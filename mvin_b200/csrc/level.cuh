@@ -831,6 +831,7 @@ struct AggBwdLevel {
   int leaf;
   int defer;            // inner: the children's share (dchild, dp_k, ds) is evaluated by the tcgen05 leaf kernel of the
                         // child level (level_tcb.cuh); this level only leaves `gp`
+  int no_dself;         // defer levels of the fused group mode (group.cuh): dself = K gp is rebuilt by the consumer, not stored
   int stream;           // level buffers >> L2: streaming (evict-first) activation accesses
   // table mode (table.cuh): children = relu(tab[id_k] + Cp[pair]) recomputed; their pre-activation gradient
   // p_k grow * [child > 0] is summed per entity (dtab) and per pair (dCs)
@@ -954,7 +955,7 @@ __global__ void __launch_bounds__(TC<D>::NT, (RING ? 2 : D <= 64 ? 3 : 1)) agg_b
       const float4 grow = f4scale(gs, invK);
       float4 su = f4zero();
       if (row < L.rows) {
-        st4a(L.dself + row * D + tx * 4, gs, L.stream);
+        if (!L.no_dself) st4a(L.dself + row * D + tx * 4, gs, L.stream);
         if (ent_mode)
           su = f4add(ldg4(a.Se + (long)__ldg(L.ent + row) * D + tx * 4), ldg4(a.u + fastdiv(row, L.rpp_magic) * D + tx * 4));
         else if (leaf) su = ld4a(L.SU + row * D + tx * 4, L.stream);

@@ -246,7 +246,9 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
     LAUNCH_CHECK(h, "transform_fwd");
   }
   // table mode: C_h = u (M1_h + M2_h) per pair, then the iteration-0 outputs of every level but the deepest as rows
-  const int n_virt_rows = H >= 2 ? H - 1 : 1;        // levels 0 .. max(H - 2, 0)
+  // levels 0 .. max(H - 2, 0); the fused group mode (H >= 3) rebuilds level H - 2 on the fly instead (group.cuh)
+  const bool gfuse = L.group && H >= 3;
+  const int n_virt_rows = H >= 2 ? H - 1 - (gfuse ? 1 : 0) : 1;
   if (L.table) {
     GemmArgs g = gemm_args();
     g.A = u_kg; g.sa_m = D; g.sa_k = 1; g.bsA = 0;
@@ -289,6 +291,11 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
       ga.tab = at<float>(ws, L.Atab) + (long)(H - 1) * c.n_entity * D;
       ga.Cp = at<float>(ws, L.Cp) + (long)(H - 1) * B * D;
       ga.self = at<float>(ws, L.V[1][H - 2]); ga.Y = at<float>(ws, L.Y[1][H - 2]);
+      if (gfuse) {
+        ga.fuse = 1;
+        ga.tab_self = at<float>(ws, L.Atab) + (long)(H - 2) * c.n_entity * D;
+        ga.Cp_self = at<float>(ws, L.Cp) + (long)(H - 2) * B * D;
+      }
       ga.rows = L.rows[H - 2]; ga.rpp_magic = div_magic(L.rows[H - 2] / B); ga.K = K; ga.n_rel = nr;
       const size_t smg = grp_smem(nr, false);
       if ((rc = set_smem(virt_group_kernel<D, false>, smg))) return rc;
@@ -317,6 +324,10 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
           t.SU = at<float>(ws, L.SU);
         } else if (L.table && i == 1 && lv == H - 2 && L.group) {
           t.preagg = 1;                                      // Y = self + agg came from virt_group_kernel
+        } else if (gfuse && i == 1 && lv == H - 3) {         // children = the fused (never materialised) level H - 2
+          t.virt = 1;
+          t.tab = at<float>(ws, L.Atab) + (long)(H - 2) * c.n_entity * D;
+          t.Cp = at<float>(ws, L.Cp) + (long)(H - 2) * B * D;
         } else if (L.table && i == 1 && lv == H - 2) {       // children = iteration 0 of the deepest level, from its table
           t.virt = 1;
           t.tab = at<float>(ws, L.Atab) + (long)(H - 1) * c.n_entity * D;
@@ -484,6 +495,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
   float* acc = at<float>(ws, L.acc);
   float* wT = at<float>(ws, L.wT);
   const bool tcb = !L.table && use_tc_bwd(h, L, D);
+  const bool gfuse = L.group && H >= 3;                      // level H - 2 of iteration 0 is never materialised (group.cuh)
   prof_mark(h, st, nullptr);
 
   // part 0 (parameters only) on side stream 0 -- unless a host-step entry point already ran it during the feed copy
@@ -577,6 +589,13 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
         } else if (L.table && i == 1 && lv == H - 2 && L.group) {
           t.defer = 1;                                       // the children's share is evaluated per entity group below
           t.gp = at<float>(ws, L.GP);
+          t.no_dself = gfuse ? 1 : 0;
+        } else if (gfuse && i == 1 && lv == H - 3) {
+          t.virt = 1;
+          t.tab = at<float>(ws, L.Atab) + (long)(H - 2) * c.n_entity * D;
+          t.Cp = at<float>(ws, L.Cp) + (long)(H - 2) * B * D;
+          t.dtab = at<float>(ws, L.dA) + (long)(H - 2) * c.n_entity * D;
+          t.dCs = at<float>(ws, L.dCs) + (long)(H - 2) * B * D;
         } else if (L.table && i == 1 && lv == H - 2) {
           t.virt = 1;
           t.tab = at<float>(ws, L.Atab) + (long)(H - 1) * c.n_entity * D;
@@ -641,6 +660,13 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
         ga.dtab = at<float>(ws, L.dA) + (long)(H - 1) * c.n_entity * D;
         ga.dCs = at<float>(ws, L.dCs) + (long)(H - 1) * B * D;
         ga.ds = at<float>(ws, L.ds) + nr;
+        if (gfuse) {
+          ga.fuse = 1;
+          ga.tab_self = at<float>(ws, L.Atab) + (long)(H - 2) * c.n_entity * D;
+          ga.Cp_self = at<float>(ws, L.Cp) + (long)(H - 2) * B * D;
+          ga.dtab_self = at<float>(ws, L.dA) + (long)(H - 2) * c.n_entity * D;
+          ga.dCs_self = at<float>(ws, L.dCs) + (long)(H - 2) * B * D;
+        }
         ga.rows = L.rows[H - 2]; ga.rpp_magic = div_magic(L.rows[H - 2] / B); ga.K = K; ga.n_rel = nr;
         const size_t smg = grp_smem(nr, true);
         const long nwin = (ga.rows + GRP_WIN - 1) / GRP_WIN;
@@ -689,7 +715,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
   // table mode: iteration 0 backward = per-entity / per-pair sums of the pre-activation gradients, then dense algebra
   if (L.table) {
     if (H == 1) par.join(0);
-    const int n_virt_rows = H >= 2 ? H - 1 : 1;
+    const int n_virt_rows = H >= 2 ? H - 1 - (gfuse ? 1 : 0) : 1;
     {
       VirtArgs a;
       memset(&a, 0, sizeof(a));
