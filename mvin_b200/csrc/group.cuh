@@ -127,10 +127,13 @@ inline size_t grp_smem(int n_rel, bool bwd) { return sizeof(float) * (size_t)n_r
 // SP (backward only): the children of a run are split over SP warps walking the same window (slot q' of warp `sub`
 // is child slot q' SP + sub), which halves the per-lane register arrays and doubles the resident warps; every warp
 // applies the softmax correction of ITS share of sum_k p_k dp_k to all K relations, so the warps never communicate.
-template <int D, bool BWD, int SP = 1>
-__global__ void __launch_bounds__(GRP_NT, BWD ? (SP == 2 ? 4 : 2) : 4) virt_group_kernel(GroupArgs a) {
+// KC: compile-time number of child slots per lane group (4, 8 or 16, the smallest >= ceil(K / G)).  The slot loops are
+// straight-line code over all KC slots -- slots beyond K carry p = 0 and a zero table row -- because a run-time bound
+// turns every slot into its own basic block and keeps the scheduler from interleaving the 16 independent chains.
+template <int D, bool BWD, int SP = 1, int KC = GRP_KPL>
+__global__ void __launch_bounds__(GRP_NT, BWD ? (SP == 2 || KC <= 8 ? 4 : 2) : 4) virt_group_kernel(GroupArgs a) {
   pdl_enter();
-  constexpr int LPR = D / 4, G = 32 / LPR, KPL_T = GRP_KPL / SP;
+  constexpr int LPR = D / 4, G = 32 / LPR, KPL_T = KC / SP;
   extern __shared__ __align__(16) float smem[];
   float* s_s = smem;
   float* ds_s = s_s + a.n_rel;                             // bwd: [NW][n_rel]
@@ -209,13 +212,13 @@ __global__ void __launch_bounds__(GRP_NT, BWD ? (SP == 2 ? 4 : 2) : 4) virt_grou
           f2x2 acc0{0ull, 0ull}, acc1{0ull, 0ull};
 #pragma unroll
           for (int q = 0; q < KPL_T; q += 2) {
-            if (q < kpl) {
+            {
               float4 x = unpack4(f2x2{add2(Ap[q].lo, cvp.lo), add2(Ap[q].hi, cvp.hi)});
               const unsigned long long pp = pk2(pq[q], pq[q]);
               acc0.lo = fma2(pp, pk2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)), acc0.lo);
               acc0.hi = fma2(pp, pk2(fmaxf(x.z, 0.f), fmaxf(x.w, 0.f)), acc0.hi);
             }
-            if (q + 1 < kpl) {
+            if (KPL_T > 1) {
               float4 x = unpack4(f2x2{add2(Ap[q + 1].lo, cvp.lo), add2(Ap[q + 1].hi, cvp.hi)});
               const unsigned long long pp = pk2(pq[q + 1], pq[q + 1]);
               acc1.lo = fma2(pp, pk2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)), acc1.lo);
@@ -282,8 +285,7 @@ __global__ void __launch_bounds__(GRP_NT, BWD ? (SP == 2 ? 4 : 2) : 4) virt_grou
           float part[KPL_T];
 #pragma unroll
           for (int q = 0; q < KPL_T; ++q) {
-            part[q] = 0.f;
-            if (q * SP + sub < kpl) {                      // warp-uniform
+            {
               const float4 x = unpack4(f2x2{add2(Ap[q].lo, cvp.lo), add2(Ap[q].hi, cvp.hi)});
               const unsigned long long d2 = fma2(grp.hi, pk2(fmaxf(x.z, 0.f), fmaxf(x.w, 0.f)),
                                                  mul2(grp.lo, pk2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f))));
@@ -301,7 +303,7 @@ __global__ void __launch_bounds__(GRP_NT, BWD ? (SP == 2 ? 4 : 2) : 4) virt_grou
           float4 cs = unpack4(f2x2{mul2(grp.lo, mp.lo), mul2(grp.hi, mp.hi)});
 #pragma unroll
           for (int ch = 0; ch < NCH; ++ch) {
-            if (ch * W * SP + sub < kpl) {                 // warp-uniform
+            {
               float v[W];
 #pragma unroll
               for (int j = 0; j < W; ++j) v[j] = part[ch * W + j];

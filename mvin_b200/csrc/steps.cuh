@@ -23,6 +23,32 @@ inline dim3 rel_gemm_grid(mvin_handle_t h, int B, int nr) {
   return dim3(tiles, ns);
 }
 
+// virt_group_kernel (group.cuh) with the compile-time slot count that fits the launch's K
+template <int D, bool BWD>
+int launch_group(mvin_handle_t h, cudaStream_t st, const GroupArgs& ga, const char* name) {
+  constexpr int G = 32 / (D / 4);
+  const int kpl = (ga.K + G - 1) / G;
+  const size_t smg = grp_smem(ga.n_rel, BWD);
+  const long nwin = (ga.rows + GRP_WIN - 1) / GRP_WIN;
+  const long cap = (long)h->sm_count * 16;
+  const int sp = (BWD && h->group_split == 2 && kpl > 8) ? 2 : 1;
+  const long want = (sp * nwin + GRP_NW - 1) / GRP_NW;
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  int rc;
+#define MVIN_GROUP_GO(SP_, KC_)                                                        \
+  do {                                                                                 \
+    if ((rc = set_smem(virt_group_kernel<D, BWD, SP_, KC_>, smg))) return rc;          \
+    MVIN_LAUNCH((virt_group_kernel<D, BWD, SP_, KC_>), grid, GRP_NT, smg, st, ga);     \
+  } while (0)
+  if (kpl <= 4) MVIN_GROUP_GO(1, 4);
+  else if (kpl <= 8) MVIN_GROUP_GO(1, 8);
+  else if (sp == 2) MVIN_GROUP_GO(2, 16);
+  else MVIN_GROUP_GO(1, 16);
+#undef MVIN_GROUP_GO
+  LAUNCH_CHECK(h, name);
+  return MVIN_OK;
+}
+
 template <int D>
 int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, const int32_t* mem_r,
                  const int32_t* mem_t, int B, float* scores, float* scores_norm, void* ws, cudaStream_t st) {
@@ -297,12 +323,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
         ga.Cp_self = at<float>(ws, L.Cp) + (long)(H - 2) * B * D;
       }
       ga.rows = L.rows[H - 2]; ga.rpp_magic = div_magic(L.rows[H - 2] / B); ga.K = K; ga.n_rel = nr;
-      const size_t smg = grp_smem(nr, false);
-      if ((rc = set_smem(virt_group_kernel<D, false>, smg))) return rc;
-      const long want = ((ga.rows + GRP_WIN - 1) / GRP_WIN + GRP_NW - 1) / GRP_NW;
-      const long cap = (long)h->sm_count * 16;
-      MVIN_LAUNCH((virt_group_kernel<D, false>), (unsigned)(want < cap ? want : cap), GRP_NT, smg, st, ga);
-      LAUNCH_CHECK(h, "group_fwd");
+      if ((rc = launch_group<D, false>(h, st, ga, "group_fwd"))) return rc;
     }
     for (int i = L.table ? 1 : 0; i < H; ++i) {
       AggArgs a;
@@ -668,20 +689,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
           ga.dCs_self = at<float>(ws, L.dCs) + (long)(H - 2) * B * D;
         }
         ga.rows = L.rows[H - 2]; ga.rpp_magic = div_magic(L.rows[H - 2] / B); ga.K = K; ga.n_rel = nr;
-        const size_t smg = grp_smem(nr, true);
-        const long nwin = (ga.rows + GRP_WIN - 1) / GRP_WIN;
-        const long cap = (long)h->sm_count * 16;
-        if (h->group_split == 2) {
-          // the children of every run split over two warps: half the registers, twice the resident warps (group.cuh)
-          if ((rc = set_smem(virt_group_kernel<D, true, 2>, smg))) return rc;
-          const long want = (2 * nwin + GRP_NW - 1) / GRP_NW;
-          MVIN_LAUNCH((virt_group_kernel<D, true, 2>), (unsigned)(want < cap ? want : cap), GRP_NT, smg, st, ga);
-        } else {
-          if ((rc = set_smem(virt_group_kernel<D, true, 1>, smg))) return rc;
-          const long want = (nwin + GRP_NW - 1) / GRP_NW;
-          MVIN_LAUNCH((virt_group_kernel<D, true, 1>), (unsigned)(want < cap ? want : cap), GRP_NT, smg, st, ga);
-        }
-        LAUNCH_CHECK(h, "group_bwd");
+        if ((rc = launch_group<D, true>(h, st, ga, "group_bwd"))) return rc;
       }
       if constexpr (D == 32 || D == 64) {
         if (tcb0) {
