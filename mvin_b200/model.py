@@ -648,7 +648,16 @@ class MVIN(object):
         set_batch_scale(global batch, 1 / world) the result equals the single-device gradient on the concatenated
         batch (tests/test_sharding_gloo.py checks the protocol)."""
         import torch.distributed as dist
-        dist.all_reduce(self.grad_flat, group=group)
+        if self.flags & 0x04:
+            # --ablation all: nothing but the dense L2 term reaches the user table (SURVEY.md Appendix B), and that term is
+            # the same on every rank (l2 x U / world under set_batch_scale), so its sum is a local multiply -- the bucket
+            # that crosses NVLink shrinks by the user table (C4: 48 -> 30 MB)
+            dist.all_reduce(self.grad_flat[self._user_grad_end:], group=group)
+            world = dist.get_world_size(group)
+            if world > 1:
+                self.grads["user_emb"].mul_(float(world))
+        else:
+            dist.all_reduce(self.grad_flat, group=group)
 
     def set_batch_scale(self, global_batch: int, dense_l2_scale: float):
         check(self.lib.mvin_set_batch_scale(self._handle, int(global_batch), float(dense_l2_scale)), "mvin_set_batch_scale")

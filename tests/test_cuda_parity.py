@@ -358,6 +358,70 @@ def _rank_worker(rank, world, port, ret, xchg=True):
         dist.destroy_process_group()
 
 
+def _dp_worker(rank, world, port, ret):
+    """Data-parallel replicas: every rank holds the full tables and a slice of the batch; with
+    set_batch_scale(global batch, 1 / world) ONE flat all-reduce (MVIN.allreduce_grads: every gradient but the user
+    table's dense L2 term, which is rebuilt locally, + the loss scalars) must reproduce the single-device gradients."""
+    import datetime
+    import os
+    import torch.distributed as dist
+    from mvin_b200 import MVIN, sharding
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank),
+                            timeout=datetime.timedelta(seconds=120))
+    try:
+        Bg = 96
+        args_g = make_args(dim=64, neighbor_sample_size=8, h_hop=3, p_hop=1, n_memory=16, batch_size=Bg)
+        prob = make_problem(args_g, n_entity=301, seed=9)
+        args_l = make_args(dim=64, neighbor_sample_size=8, h_hop=3, p_hop=1, n_memory=16, batch_size=Bg // world)
+        model = MVIN(args_l, prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"], prob["adj_relation"])
+        model.load_named_parameters({k: v.numpy() for k, v in prob["P"].items()})
+        model.set_batch_scale(Bg, 1.0 / world)
+        sl = sharding.split_batch(Bg, rank, world)
+        dev = model.device
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        mem = lambda ms: to(np.stack([m[sl] for m in ms]).astype(np.int32))
+        model.forward_device(to(prob["users"][sl]), to(prob["items"][sl]), mem(prob["mem_h"]), mem(prob["mem_r"]), mem(prob["mem_t"]))
+        model.backward_device(to(prob["labels"][sl].astype(np.float32)), model.loss_slot)
+        model.allreduce_grads()
+        torch.cuda.synchronize(dev)
+        out, grads = orc.loss_and_grads(prob["P"], prob["cfg"], prob["adj_entity"], prob["adj_relation"], prob["users"],
+                                        prob["items"], prob["mem_h"], prob["mem_r"], prob["mem_t"], prob["labels"])
+        ok = abs(float(model.loss_slot[0]) - float(out.loss.detach())) <= 1e-4 * max(1.0, abs(float(out.loss.detach())))
+        bad = []
+        for k, g in model.named_gradients().items():
+            ref = grads[k].numpy().reshape(g.shape)
+            if not np.abs(g - ref).max() <= GRAD_TOL * max(np.abs(ref).max(), 1e-8) + 1e-8:
+                bad.append(k)
+        ret[rank] = (bool(ok), bad)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_multi_rank_data_parallel_allreduce_matches_oracle(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (gpurun --gpus {world})")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_dp_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+        assert p.exitcode == 0
+    for r in range(world):
+        ok, bad = ret[r]
+        assert ok and not bad, (r, ok, bad)
+
+
 @pytest.mark.parametrize("world,xchg", [(2, True), (2, False), (4, True), (8, True), (8, False)])
 def test_multi_rank_sharded_entity_table_matches_oracle(world, xchg):
     """(xchg: the leaf level through the all-gather of parent ids + owner-side partial reduction + fused peer return of
