@@ -345,4 +345,107 @@ __global__ void __launch_bounds__(GRP_NT, BWD ? (SP == 2 || KC <= 8 ? 4 : 2) : 4
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Per-entity leaf aggregate in the same register-blocked form (replaces leaf_entity_kernel of level.cuh where the
+// children fit: grp_supported):  Se[e] = sum_k p_k E[n_k]  and its backward  dE[n_k] += p_k g,  dp_k = g . E[n_k],
+// ds[rel_k] += p_k (dp_k - sum_j p_j dp_j)  with g = GSe[e].  One warp per stamped entity; lane (g, c) holds column c of
+// the children k = q G + g: all K row loads of an entity are in flight at once, the K dot products are reduced by one
+// butterfly reduce-scatter, and the slot loops are straight-line code (compile-time KC).
+// ---------------------------------------------------------------------------------------------------------
+template <int D, bool BWD, int KC>
+__global__ void __launch_bounds__(LEAF_NT) leaf_entity_reg_kernel(LeafEntArgs a) {
+  pdl_enter();
+  constexpr int LPR = D / 4, G = 32 / LPR;
+  extern __shared__ __align__(16) float smem[];
+  float* s_s = smem;
+  float* ds_s = s_s + a.n_rel;                             // bwd: [NWH][n_rel]
+  const int NWH = leaf_ds_copies(a.n_rel);
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32, g = lane / LPR, c = lane % LPR;
+  for (int i = tid; i < a.n_rel; i += LEAF_NT) s_s[i] = a.s[i];
+  if (BWD)
+    for (int i = tid; i < NWH * a.n_rel; i += LEAF_NT) ds_s[i] = 0.f;
+  __syncthreads();
+  float* ds_w = ds_s + (NWH > 1 ? warp : 0) * a.n_rel;
+  const int K = a.K, chunk = a.chunk;
+  for (long c0 = ((long)blockIdx.x * LEAF_NW + warp) * chunk; c0 < a.n_entity; c0 += (long)gridDim.x * LEAF_NW * chunk) {
+    const long me = c0 + lane;
+    unsigned mask = __ballot_sync(FULL_MASK, lane < chunk && me < a.n_entity && __ldg(a.stamp + me) != 0);
+    AdjRec nxt{0, 0, 0, 0};
+    if (mask) nxt = load_adj(a.adj, c0 + (__ffs(mask) - 1), K, lane);
+    while (mask) {
+      const long e = c0 + (__ffs(mask) - 1);
+      mask &= mask - 1;
+      const AdjRec rec = nxt;
+      if (mask) nxt = load_adj(a.adj, c0 + (__ffs(mask) - 1), K, lane);
+      const float l0 = lane < K ? s_s[rec.rel0] : -INFINITY;
+      const float l1 = lane + 32 < K ? s_s[rec.rel1] : -INFINITY;
+      const float mx = warp_max(fmaxf(l0, l1));
+      const float e0 = lane < K ? expf(l0 - mx) : 0.f;
+      const float e1 = lane + 32 < K ? expf(l1 - mx) : 0.f;
+      const float inv = 1.f / warp_sum(e0 + e1);
+      const float p0 = e0 * inv, p1 = e1 * inv;
+      float4 x[KC];
+      float pq[KC];
+      int idq[KC];
+#pragma unroll
+      for (int q = 0; q < KC; ++q) {
+        const int k = q * G + g, src = k & 31;
+        const int id_lo = __shfl_sync(FULL_MASK, rec.id0, src), id_hi = __shfl_sync(FULL_MASK, rec.id1, src);
+        const float p_lo = __shfl_sync(FULL_MASK, p0, src), p_hi = __shfl_sync(FULL_MASK, p1, src);
+        const bool on = k < K;
+        idq[q] = k < 32 ? id_lo : id_hi;
+        pq[q] = on ? (k < 32 ? p_lo : p_hi) : 0.f;
+        x[q] = on ? ldg4(erow(a.E, idq[q], D) + c * 4) : f4zero();
+      }
+      if (!BWD) {
+        float4 acc = f4zero();
+#pragma unroll
+        for (int q = 0; q < KC; ++q) acc = f4fma(pq[q], x[q], acc);
+        acc = cross_group_sum4<LPR>(acc);
+        if (g == 0) st4(a.Se + e * D + c * 4, acc);
+      } else {
+        constexpr int W = LPR < KC ? LPR : KC, NCH = KC / W;
+        const float4 gr = ld4(a.GSe + e * D + c * 4);
+        float part[KC];
+#pragma unroll
+        for (int q = 0; q < KC; ++q) {
+          part[q] = f4dot(gr, x[q]);
+          if (q * G + g < K) red_add4(grow_of(a.dE, idq[q], D) + c * 4, f4scale(gr, pq[q]));
+        }
+        float dotp = 0.f, mydp[NCH], myp[NCH];
+        int myrel[NCH];
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          float v[W];
+#pragma unroll
+          for (int j = 0; j < W; ++j) v[j] = part[ch * W + j];
+          mydp[ch] = reduce_scatter<W, LPR>(v, lane);      // dp of child slot ch W + c % W
+          const int k = (ch * W + c % W) * G + g, src = k & 31;
+          const float p_lo = __shfl_sync(FULL_MASK, p0, src), p_hi = __shfl_sync(FULL_MASK, p1, src);
+          const int r_lo = __shfl_sync(FULL_MASK, rec.rel0, src), r_hi = __shfl_sync(FULL_MASK, rec.rel1, src);
+          const bool mine = k < K && c < W;
+          myp[ch] = mine ? (k < 32 ? p_lo : p_hi) : 0.f;
+          myrel[ch] = mine ? (k < 32 ? r_lo : r_hi) : 0;
+          dotp = fmaf(myp[ch], mydp[ch], dotp);
+        }
+        dotp = warp_sum(dotp);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+          if (myp[ch] != 0.f) atomicAdd(&ds_w[myrel[ch]], myp[ch] * (mydp[ch] - dotp));
+      }
+    }
+  }
+  if (BWD) {
+    __syncthreads();
+    for (int i = tid; i < a.n_rel; i += LEAF_NT) {
+      float s = 0.f;
+      for (int w = 0; w < NWH; ++w) s += ds_s[w * a.n_rel + i];
+      if (s != 0.f) atomicAdd(a.ds + i, s);
+    }
+  }
+}
+inline size_t leaf_entity_reg_smem(int n_rel, bool bwd) {
+  return sizeof(float) * (size_t)n_rel * (bwd ? 1 + leaf_ds_copies(n_rel) : 1);
+}
+
 }  // namespace mvin

@@ -23,6 +23,40 @@ inline dim3 rel_gemm_grid(mvin_handle_t h, int B, int nr) {
   return dim3(tiles, ns);
 }
 
+// per-entity leaf aggregate: the register-blocked kernel of group.cuh where the children fit the registers (d K <= 2048),
+// else leaf_entity_kernel of level.cuh (MVIN_B200_LEAF_REG=0 forces the latter)
+template <int D, bool BWD>
+int launch_leaf_entity(mvin_handle_t h, cudaStream_t st, LeafEntArgs& a, const char* name) {
+  const mvin_config_t& c = h->cfg;
+  constexpr int G = 32 / (D / 4);
+  const int kpl = (a.K + G - 1) / G;
+  a.chunk = leaf_chunk(h, c.n_entity);
+  const long want = ((long)c.n_entity + LEAF_NW * a.chunk - 1) / (LEAF_NW * a.chunk);
+  const long cap = (long)h->sm_count * 8;
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  int rc;
+  static const bool reg_on = [] { const char* e = getenv("MVIN_B200_LEAF_REG"); return !(e && e[0] == '0'); }();
+  // (the forward -- K independent row loads and one weighted sum -- measured faster on the older kernel: 0.09 vs 0.12 ms)
+  if (BWD && reg_on && grp_supported(D, a.K) && h->n_shards == 1) {
+    const size_t sm = leaf_entity_reg_smem(a.n_rel, BWD);
+#define MVIN_LEAF_GO(KC_)                                                              \
+  do {                                                                                 \
+    if ((rc = set_smem(leaf_entity_reg_kernel<D, BWD, KC_>, sm))) return rc;           \
+    MVIN_LAUNCH((leaf_entity_reg_kernel<D, BWD, KC_>), grid, LEAF_NT, sm, st, a);      \
+  } while (0)
+    if (kpl <= 4) MVIN_LEAF_GO(4);
+    else if (kpl <= 8) MVIN_LEAF_GO(8);
+    else MVIN_LEAF_GO(16);
+#undef MVIN_LEAF_GO
+  } else {
+    const size_t sm = leaf_entity_smem(a.n_rel);
+    if ((rc = set_smem(leaf_entity_kernel<D, BWD>, sm))) return rc;
+    MVIN_LAUNCH((leaf_entity_kernel<D, BWD>), grid, LEAF_NT, sm, st, a);
+  }
+  LAUNCH_CHECK(h, name);
+  return MVIN_OK;
+}
+
 // virt_group_kernel (group.cuh) with the compile-time slot count that fits the launch's K
 template <int D, bool BWD>
 int launch_group(mvin_handle_t h, cudaStream_t st, const GroupArgs& ga, const char* name) {
@@ -139,13 +173,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
       memset(&a, 0, sizeof(a));
       a.stamp = stamp; a.adj = h->adj; a.s = at<float>(ws, L.s); a.E = h->etab; a.Se = at<float>(ws, L.Se);
       a.n_entity = c.n_entity; a.K = K; a.n_rel = nr;
-      a.chunk = leaf_chunk(h, c.n_entity);
-      const size_t sm = leaf_entity_smem(nr);
-      if ((rc = set_smem(leaf_entity_kernel<D, false>, sm))) return rc;
-      const long want = ((long)c.n_entity + LEAF_NW * a.chunk - 1) / (LEAF_NW * a.chunk);
-      const long cap = (long)h->sm_count * 8;
-      MVIN_LAUNCH((leaf_entity_kernel<D, false>), (unsigned)(want < cap ? want : cap), LEAF_NT, sm, st, a);
-      LAUNCH_CHECK(h, "leaf_entity_fwd");
+      if ((rc = launch_leaf_entity<D, false>(h, st, a, "leaf_entity_fwd"))) return rc;
     }
     // table mode: A_h = E M1_h + Se M2_h + c_h for every stamped entity
     if (L.table) {
@@ -777,13 +805,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     a.stamp = at<int32_t>(ws, L.stamp); a.adj = h->adj; a.s = at<float>(ws, L.s); a.E = h->etab;
     a.GSe = at<float>(ws, L.GSe); a.dE = h->gtab; a.ds = at<float>(ws, L.ds);
     a.n_entity = c.n_entity; a.K = K; a.n_rel = nr;
-    a.chunk = leaf_chunk(h, c.n_entity);
-    const size_t sm = leaf_entity_smem(nr);
-    if ((rc = set_smem(leaf_entity_kernel<D, true>, sm))) return rc;
-    const long want = ((long)c.n_entity + LEAF_NW * a.chunk - 1) / (LEAF_NW * a.chunk);
-    const long cap = (long)h->sm_count * 8;
-    MVIN_LAUNCH((leaf_entity_kernel<D, true>), (unsigned)(want < cap ? want : cap), LEAF_NT, sm, st, a);
-    LAUNCH_CHECK(h, "leaf_entity_bwd");
+    if ((rc = launch_leaf_entity<D, true>(h, st, a, "leaf_entity_bwd"))) return rc;
   }
   if (!h->xchg.on) {       // exchange mode: ds of aggregator 0 is completed by the owners; mvin_xchg_finish_backward runs this
     MVIN_LAUNCH((rel_scores_bwd_kernel), H, 128, 0, st, P.relation_emb, P.agg_urh_w, at<float>(ws, L.ds), nr, D, G.relation_emb,
