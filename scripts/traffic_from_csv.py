@@ -34,7 +34,7 @@ def family(name, state, H):
             return "agg_bwd_0"
         state["b"] += 1
         return f"agg_bwd_{H - state['b']}"
-    if base == "leaf_entity_kernel":
+    if base in ("leaf_entity_kernel", "leaf_entity_reg_kernel"):
         return "leaf_entity_bwd" if leaf else "leaf_entity_fwd"
     if base == "virt_group_kernel":
         return "group_bwd" if leaf else "group_fwd"
