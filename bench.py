@@ -583,8 +583,8 @@ def run_ours(a, w, wl_key):
                              "distinct ENTITY (table.cuh: A_h = E M1_h + Se M2_h + c_h) and the deepest level is gathered "
                              "from that table instead of being materialised, so the logical per-pair gather bytes of "
                              "SURVEY.md 8(d) (logical_*) far exceed what the kernels move through HBM; frac / step_frac "
-                             "are on executed DRAM bytes, and the dominant kernel is bound by L2 gathers + red.global.add "
-                             "issue rate, not by HBM")}
+                             "are on executed DRAM bytes; the dominant kernels are bound by L2 gather latency and by the "
+                             "issue rate of their element-wise loops, not by HBM (DESIGN.md section 9)")}
     if adam:
         adam["frac"] = adam["gbs"] / peak
     cpu = None
