@@ -43,7 +43,8 @@ typedef struct mvin_config {
   int32_t dim;                  /* --dim                    d */
   int32_t neighbor_sample_size; /* --neighbor_sample_size   K */
   int32_t h_hop;                /* --h_hop                  H (= L when n_mix_hop = 1) */
-  int32_t n_mix_hop;            /* --n_mix_hop              M, must be 1 */
+  int32_t n_mix_hop;            /* --n_mix_hop              M mix blocks of h_hop iterations each (model.py:286-315);
+                                   h_hop <= 3 when M = 1, h_hop * M <= 4 otherwise */
   int32_t p_hop;                /* --p_hop                  p */
   int32_t n_memory;             /* --n_memory               m */
   int32_t n_user, n_entity, n_relation;
@@ -56,7 +57,14 @@ typedef struct mvin_config {
 
 #define MVIN_FLAGS_ALL 0x1f
 #define MVIN_FLAG_KG_EH 0x04      /* bit2: User_orient_kg_eh */
+#define MVIN_FLAG_PS_ONLY 0x20    /* bit5: PS_only (model.py:142-144): score = user_o . E[item], no KG side */
+#define MVIN_FLAG_HO_ONLY 0x40    /* bit6: HO_only (model.py:146-150): score = U[user] . item */
 #define MVIN_FLAGS_NO_KG_EH_UO 0x1b /* --ablation no_kg_eh_uo (parameter_ablation.py:22-30): the KG side is oriented by U[user] */
+#define MVIN_FLAGS_PS_ONLY 0x3f          /* --ablation ps_only          (parameter_ablation.py) */
+#define MVIN_FLAGS_HO_ONLY 0x5b          /* --ablation ho_only          (User_orient_kg_eh = 0) */
+#define MVIN_FLAGS_HO_ONLY_UO_KG_EH 0x5f /* --ablation ho_only_uo_kg_eh (User_orient_kg_eh = 1) */
+/* Supported: bits 0, 1, 3, 4 set (User_orient, User_orient_rela, PS_O_ft, wide_deep), bit 2 either way, at most one of
+ * bits 5 / 6.  Everything else -> MVIN_ERR_UNSUPPORTED from mvin_create. */
 
 /* The parameter set of MVIN._build_model (model.py:72-122) + the aggregators (aggregators.py:83-93), fp32,
  * device pointers.  The same struct describes a gradient set (same shapes) and Adam moment sets.

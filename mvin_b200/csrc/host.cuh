@@ -86,7 +86,7 @@ void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
     if (_e != cudaSuccess) return fail(MVIN_ERR_CUDA, "launch %s: %s", name, cudaGetErrorString(_e)); \
   } while (0)
 
-constexpr int MAX_L = 3;
+constexpr int MAX_L = 4;            // deepest level count: h_hop <= 3 with one mix block, h_hop n_mix_hop <= 4 with several
 constexpr int MAX_SHARDS = 16;
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
@@ -120,6 +120,10 @@ struct Layout {
   // entity-group evaluation of the table-gather level (group.cuh)
   bool group;
   size_t gcnt, goff, gtot, gorder, gesort, GP;   // int32 [n_entity] x 2, [4096 + 1], [rows(H-2)] x 2; fp32 [rows(H-2), D]
+  // n_mix_hop > 1 (steps.cuh, forward_mix_impl / backward_mix_impl; model.py:286-315): X[n][h] = output of mix block n-1 at
+  // level h (the input of block n >= 1); DM[n][h] = [h_hop + 1][rows(h), D] gradients of the h_hop + 1 inputs of mix block n
+  // at level h; GV / GX / GT = summed gradients of V[j][h], X[n][h], T[h] where more than one consumer contributes
+  size_t X[MAX_L][MAX_L], GX[MAX_L][MAX_L], DM[MAX_L][MAX_L], GV[MAX_L + 1][MAX_L], GT[MAX_L];
   size_t total;
   long rows[MAX_L + 1];
 };
@@ -237,7 +241,7 @@ inline bool has_V(int H, int j, int h) { return j == 0 ? h < H : h <= H - j; }  
 // Entity mode of the leaf level (level.cuh, leaf_entity_kernel) pays off when the depth-(L-1) nodes of a batch
 // re-use entities: enabled when there are at least n_entity / 4 of them and the two per-entity buffers are small.
 inline bool use_entity_leaf(const mvin_config_t& c, long B, int n_shards, int mode) {
-  if (n_shards != 1 || mode == 0) return false;
+  if (n_shards != 1 || mode == 0 || c.n_mix_hop != 1 || (c.flags & MVIN_FLAG_PS_ONLY)) return false;
   if (mode == 1) return true;
   long rows = B;
   for (int h = 1; h < c.h_hop; ++h) rows *= c.neighbor_sample_size;
@@ -248,7 +252,7 @@ inline bool use_entity_leaf(const mvin_config_t& c, long B, int n_shards, int mo
 // buffers -- by per-entity tables.  Same applicability as the entity mode of the leaf level (one shard, the batch re-uses
 // entities); MVIN_B200_TABLE=0 / 1 forces it off / on, an explicit MVIN_B200_ENTITY_LEAF selects the row kernels.
 inline bool use_table(const mvin_config_t& c, long B, int n_shards, int table_mode, int entity_leaf_mode) {
-  if (n_shards != 1 || table_mode == 0) return false;
+  if (n_shards != 1 || table_mode == 0 || c.n_mix_hop != 1 || (c.flags & MVIN_FLAG_PS_ONLY)) return false;
   if ((long)c.n_entity * c.dim * 4 * (2 * c.h_hop + 2) > (8L << 30)) return false;
   if (table_mode == 1) return true;
   // automatic: when the deepest level has at least one row per entity of the graph (rows per entity at C3: 2.5, C4: 148;
@@ -273,7 +277,8 @@ inline Layout make_layout(const mvin_config_t& c, long B, bool entity_leaf, bool
   if (table) entity_leaf = true;           // Se / GSe / stamp are shared with the entity mode of the leaf level
   L.entity_leaf = entity_leaf;
   L.table = table;
-  const long D = c.dim, K = c.neighbor_sample_size, H = c.h_hop, p = c.p_hop, m = c.n_memory, nr = c.n_relation;
+  // H = depth of the neighbour expansion = number of aggregators: h_hop iterations in each of n_mix_hop mix blocks
+  const long D = c.dim, K = c.neighbor_sample_size, H = (long)c.h_hop * c.n_mix_hop, p = c.p_hop, m = c.n_memory, nr = c.n_relation;
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
@@ -347,6 +352,17 @@ inline Layout make_layout(const mvin_config_t& c, long B, bool entity_leaf, bool
   if (entity_leaf) {
     L.stamp = take(sizeof(int32_t) * (size_t)c.n_entity);
     L.Se = take(f * (size_t)c.n_entity * D);
+  }
+  if (c.n_mix_hop > 1) {
+    const int Hm = c.h_hop, M = c.n_mix_hop;
+    for (int n = 0; n < M; ++n)
+      for (int h = 0; h <= H - (long)n * Hm && h < MAX_L; ++h) {
+        if (n >= 1) { L.X[n][h] = take(f * L.rows[h] * D); L.GX[n][h] = take(f * L.rows[h] * D); }
+        if (h <= H - (long)(n + 1) * Hm) L.DM[n][h] = take(f * (Hm + 1) * L.rows[h] * D);
+      }
+    for (int j = 1; j <= H; ++j)
+      for (int h = 0; h <= H - j; ++h) L.GV[j][h] = take(f * L.rows[h] * D);
+    for (int h = 0; h < H; ++h) L.GT[h] = take(f * L.rows[h] * D);
   }
   L.total = off;
   return L;

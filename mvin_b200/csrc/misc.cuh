@@ -132,6 +132,17 @@ __global__ void scatter_rows_kernel(const float* __restrict__ rows, const int32_
   red_add4(grow_of(dE, ent[b], D) + c * 4, ld4(rows + b * D + c * 4));
 }
 
+// ---- out = a + b (+ c) over n4 float4 elements: the gradient of a node vector that has more than two consumers
+// (n_mix_hop > 1, model.py:286-315: its own aggregator step, its parent's children sum and the mix layer) --------------
+static __global__ void sum_rows_kernel(const float* a, const float* b, const float* c, long n4, float* out) {   // out may alias an input
+  pdl_enter();
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 v = f4add(ld4(a + i * 4), ld4(b + i * 4));
+    if (c) v = f4add(v, ld4(c + i * 4));
+    st4(out + i * 4, v);
+  }
+}
+
 // ---- relation scores s[i][r] = Rel[r] . urh_weights_i[D:2D]  (aggregators.py:130-133, relation third) --
 static __global__ void rel_scores_kernel(const float* __restrict__ Rel, const float* __restrict__ urh, int n_rel, int D,
                                   int H, float* __restrict__ s) {

@@ -33,10 +33,17 @@ MVIN_EXTERN_D(8) MVIN_EXTERN_D(16) MVIN_EXTERN_D(32) MVIN_EXTERN_D(64) MVIN_EXTE
 #undef MVIN_EXTERN_D
 
 int check_supported(const mvin_config_t* c) {
-  if (c->flags != MVIN_FLAGS_ALL && c->flags != MVIN_FLAGS_NO_KG_EH_UO)
-    return fail(MVIN_ERR_UNSUPPORTED, "only --ablation all (flags 0x1f) and no_kg_eh_uo (0x1b) are supported, got 0x%x", c->flags);
-  if (c->n_mix_hop != 1) return fail(MVIN_ERR_UNSUPPORTED, "n_mix_hop must be 1, got %d", c->n_mix_hop);
-  if (c->h_hop < 1 || c->h_hop > MAX_L) return fail(MVIN_ERR_UNSUPPORTED, "h_hop must be in 1..3, got %d", c->h_hop);
+  const int variant = MVIN_FLAG_KG_EH | MVIN_FLAG_PS_ONLY | MVIN_FLAG_HO_ONLY;
+  if ((c->flags | variant) != (MVIN_FLAGS_ALL | variant) || (c->flags & MVIN_FLAGS_NO_KG_EH_UO) != MVIN_FLAGS_NO_KG_EH_UO ||
+      ((c->flags & MVIN_FLAG_PS_ONLY) && (c->flags & MVIN_FLAG_HO_ONLY)))
+    return fail(MVIN_ERR_UNSUPPORTED,
+                "supported --ablation settings: all (0x1f), no_kg_eh_uo (0x1b), ps_only (0x3f), ho_only (0x5b), "
+                "ho_only_uo_kg_eh (0x5f); got flags 0x%x", c->flags);
+  if (c->h_hop < 1 || c->n_mix_hop < 1) return fail(MVIN_ERR_UNSUPPORTED, "h_hop and n_mix_hop must be >= 1");
+  if (c->n_mix_hop == 1 && c->h_hop > 3) return fail(MVIN_ERR_UNSUPPORTED, "h_hop must be in 1..3, got %d", c->h_hop);
+  if (c->n_mix_hop > 1 && c->h_hop * c->n_mix_hop > MAX_L)
+    return fail(MVIN_ERR_UNSUPPORTED, "h_hop * n_mix_hop must be <= %d when n_mix_hop > 1, got %d x %d", MAX_L, c->h_hop,
+                c->n_mix_hop);
   const int d = c->dim;
   if (!(d == 8 || d == 16 || d == 32 || d == 64 || d == 128))
     return fail(MVIN_ERR_UNSUPPORTED, "dim must be one of 8,16,32,64,128, got %d", d);
@@ -85,6 +92,8 @@ int host_step_overlap(mvin_handle_t h, int B, void* ws, cudaStream_t st) {
   h->early_init = false;
   h->pre_fork = false;
   if (!h->use_streams || h->prof_on || !h->has_grads) return MVIN_OK;
+  // the PS_only / n_mix_hop > 1 variants run their step on one stream (steps.cuh: backward_ps_only, backward_mix_impl)
+  if ((h->cfg.flags & MVIN_FLAG_PS_ONLY) || h->cfg.n_mix_hop > 1) return MVIN_OK;
   CUDA_TRY(cudaEventRecord(h->ev_item, st));
   h->pre_fork = true;
   CUDA_TRY(cudaStreamWaitEvent(h->side[1], h->ev_item, 0));
@@ -222,6 +231,8 @@ int mvin_bind_entity_shards(mvin_handle_t h, int32_t n_shards, const float* cons
   if (!h || !entity_shards || !grad_shards) return fail(MVIN_ERR_INVALID, "null argument");
   if (n_shards < 1 || n_shards > MAX_SHARDS || (n_shards & (n_shards - 1)))
     return fail(MVIN_ERR_INVALID, "n_shards must be a power of two in 1..%d, got %d", MAX_SHARDS, n_shards);
+  if (n_shards > 1 && ((h->cfg.flags & (MVIN_FLAG_PS_ONLY | MVIN_FLAG_HO_ONLY)) || h->cfg.n_mix_hop > 1))
+    return fail(MVIN_ERR_UNSUPPORTED, "row-sharded entity table: PS_only / HO_only / n_mix_hop > 1 are single-table variants");
   int shift = 0;
   while ((1 << shift) < n_shards) ++shift;
   void* host[2 * MAX_SHARDS] = {nullptr};
@@ -379,15 +390,19 @@ int mvin_forward(mvin_handle_t h, const int64_t* user_indices, const int64_t* it
 int mvin_importance(mvin_handle_t h, float* imp0, float* imp1, void* workspace, void* stream) {
   if (!h || !imp0 || !workspace) return fail(MVIN_ERR_INVALID, "null argument");
   if (h->fwd_workspace != workspace || h->B < 1) return fail(MVIN_ERR_STATE, "no forward pass on this workspace");
+  if (h->cfg.flags & MVIN_FLAG_PS_ONLY) return fail(MVIN_ERR_UNSUPPORTED, "PS_only has no aggregators (model.py:142-144)");
   cudaStream_t st = (cudaStream_t)stream;
   const Layout L = handle_layout(h, h->B);
   const int K = h->cfg.neighbor_sample_size;
+  // model.py:294,304: importance_list is reset at iteration 0 of EVERY mix block, so what survives is the attention of the
+  // first aggregator of the LAST block (aggregator (M - 1) h_hop) at hops 0 and 1
+  const float* s = at<float>(workspace, L.s) + (long)(h->cfg.n_mix_hop - 1) * h->cfg.h_hop * h->cfg.n_relation;
   float* outs[2] = {imp0, imp1};
   for (int lv = 0; lv < 2 && lv < h->cfg.h_hop; ++lv) {
     if (!outs[lv]) continue;
     const long rows = L.rows[lv];
     MVIN_LAUNCH((importance_kernel), (unsigned)((rows * 32 + 255) / 256), 256, 0, st, at<int32_t>(workspace, L.ent[lv]), h->adj,
-                                                                           at<float>(workspace, L.s), rows, K, outs[lv]);
+                                                                           s, rows, K, outs[lv]);
     LAUNCH_CHECK(h, "importance");
   }
   return MVIN_OK;
@@ -406,7 +421,8 @@ int mvin_adam_step(mvin_handle_t h, const mvin_params_t* m, const mvin_params_t*
   if (!h || !m || !v || step < 1) return fail(MVIN_ERR_INVALID, "bad argument");
   if (!h->has_params || !h->has_grads) return fail(MVIN_ERR_STATE, "parameters / gradients not bound");
   const mvin_config_t& c = h->cfg;
-  const long D = c.dim, H = c.h_hop, p = c.p_hop, nr = c.n_relation;
+  // Hm iterations per mix block, M mix blocks, H = Hm M aggregators / transfer matrices 0 .. H
+  const long D = c.dim, Hm = c.h_hop, M = c.n_mix_hop, H = Hm * M, p = c.p_hop, nr = c.n_relation;
   AdamSegments sg;
   memset(&sg, 0, sizeof(sg));
   int n = 0;
@@ -421,8 +437,8 @@ int mvin_adam_step(mvin_handle_t h, const mvin_params_t* m, const mvin_params_t*
   SEG(entity_emb, h->n_local_rows * D);
   SEG(relation_emb, nr * D);
   SEG(relation_kge, nr * D * D);
-  SEG(mix_w, (H + 1) * D * D);
-  SEG(mix_b, D);
+  SEG(mix_w, M * (Hm + 1) * D * D);
+  SEG(mix_b, M * D);
   SEG(user_mlp_w, (p + 1) * D * D);
   SEG(user_mlp_b, D);
   SEG(transfer_w, (H + 1) * D * D);

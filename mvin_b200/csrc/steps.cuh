@@ -83,12 +83,101 @@ int launch_group(mvin_handle_t h, cudaStream_t st, const GroupArgs& ga, const ch
   return MVIN_OK;
 }
 
+// variants of the step outside --ablation all with one mix block (defined at the end of this file)
+template <int D>
+int forward_ps_only(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, const int32_t* mem_r, const int32_t* mem_t,
+                    int B, float* scores, float* scores_norm, void* ws, cudaStream_t st);
+template <int D>
+int backward_ps_only(mvin_handle_t h, const float* labels, int B, float* losses_out, void* ws, cudaStream_t st);
+template <int D>
+int forward_mix_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, const int32_t* mem_r, const int32_t* mem_t,
+                     int B, float* scores, float* scores_norm, void* ws, cudaStream_t st);
+template <int D>
+int backward_mix_impl(mvin_handle_t h, const float* labels, int B, float* losses_out, void* ws, cudaStream_t st);
+
+// the user side of the forward pass (model.py:125-134, :161-240): user_o = key addressing over the ripple memories
+template <int D>
+int user_side_forward(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, const int32_t* mem_r, const int32_t* mem_t,
+                      int B, void* ws, cudaStream_t st) {
+  using C = TC<D>;
+  const mvin_config_t& c = h->cfg;
+  const int p = c.p_hop, m = c.n_memory, nr = c.n_relation;
+  const Layout L = handle_layout(h, B);
+  const mvin_params_t& P = h->P;
+  int rc;
+  // the user side in one launch: seeds v = E[item], Q = RK^T v, ripple attention, user MLP -> user_o
+  // (model.py:125-134, :161-240).  With a large relation-KGE table Q comes from a batched GEMM instead.
+  const bool q_fused = user_q_fused(D, nr);
+  if (!q_fused && p > 0) {
+    const long n = (long)B * C::LPR;
+    MVIN_LAUNCH((prep_items_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, item, h->etab, B, nullptr,
+                                                                      at<float>(ws, L.Vbuf), nullptr);
+    LAUNCH_CHECK(h, "prep_items");
+  }
+  // Q[b, r, :] = RK[r]^T v_b      (model.py:211-220 refactored)
+  if (!q_fused && p > 0) {
+    GemmArgs g = gemm_args();
+    g.A = at<float>(ws, L.Vbuf); g.sa_m = D; g.sa_k = 1; g.bsA = 0;
+    g.B = P.relation_kge; g.sb_k = D; g.sb_n = 1; g.bsB = (long)D * D;
+    g.C = at<float>(ws, L.Q); g.ldc = (long)nr * D; g.bsC = D;
+    g.M = B; g.N = D; g.K = D; g.nbatch = nr;
+    bool done = false;
+    if constexpr (D == 32 || D == 64) {
+      if (use_tc_gemm<D>(h, B)) {
+        RelGemmArgs ra;
+        memset(&ra, 0, sizeof(ra));
+        ra.V = at<float>(ws, L.Vbuf); ra.RK = P.relation_kge; ra.Q = at<float>(ws, L.Q); ra.B = B; ra.n_rel = nr;
+        ra.RKs = at<unsigned char>(ws, L.RKs);
+        // relation operands split and staged once per step (also read by the backward's dv kernel)
+        MVIN_LAUNCH((rel_stage_kernel<D>), dim3(nr, 2), RG_NT, 0, st, P.relation_kge, at<unsigned char>(ws, L.RKs));
+        LAUNCH_CHECK(h, "rel_stage");
+        if ((rc = set_smem(relq_tc_kernel<D>, relq_tc_smem<D>()))) return rc;
+        MVIN_LAUNCH((relq_tc_kernel<D>), rel_gemm_grid(h, B, nr), RG_NT, relq_tc_smem<D>(), st, ra);
+        LAUNCH_CHECK(h, "gemm_q");
+        done = true;
+      }
+    }
+    if (!done && (rc = run_gemm(h, st, g, "gemm_q"))) return rc;
+  }
+  {
+    UserArgs a;
+    memset(&a, 0, sizeof(a));
+    a.E = h->etab; a.item = item; a.RK = P.relation_kge; a.w_hi = P.h_item_w;
+    a.W_user = P.user_mlp_w; a.b_user = P.user_mlp_b;
+    a.mem_h = mem_h; a.mem_r = mem_r; a.mem_t = mem_t;
+    a.Vbuf = at<float>(ws, L.Vbuf); a.Q = at<float>(ws, L.Q); a.probs = at<float>(ws, L.probs);
+    a.O = at<float>(ws, L.O); a.u = at<float>(ws, L.u);
+    a.B = B; a.m = m; a.p = p; a.n_rel = nr; a.q_ready = q_fused ? 0 : 1;
+    const int PB = user_pairs_per_cta(D, nr, p, m, h->user_pb_fwd);
+    const size_t sm = user_fwd_smem(D, PB, nr, p, m);
+    const int nt = 32 * user_warps(PB, p);
+    const unsigned grid = (unsigned)((B + PB - 1) / PB);
+    switch (PB) {
+      case 4:
+        if ((rc = set_smem(user_fwd_kernel<D, 4>, sm))) return rc;
+        MVIN_LAUNCH((user_fwd_kernel<D, 4>), grid, nt, sm, st, a);
+        break;
+      case 2:
+        if ((rc = set_smem(user_fwd_kernel<D, 2>, sm))) return rc;
+        MVIN_LAUNCH((user_fwd_kernel<D, 2>), grid, nt, sm, st, a);
+        break;
+      default:
+        if ((rc = set_smem(user_fwd_kernel<D, 1>, sm))) return rc;
+        MVIN_LAUNCH((user_fwd_kernel<D, 1>), grid, nt, sm, st, a);
+    }
+    LAUNCH_CHECK(h, "user_fwd");
+  }
+  return MVIN_OK;
+}
+
 template <int D>
 int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, const int32_t* mem_r,
                  const int32_t* mem_t, int B, float* scores, float* scores_norm, void* ws, cudaStream_t st) {
   using C = TC<D>;
   const mvin_config_t& c = h->cfg;
   const int K = c.neighbor_sample_size, H = c.h_hop, p = c.p_hop, m = c.n_memory, nr = c.n_relation;
+  if (c.flags & MVIN_FLAG_PS_ONLY) return forward_ps_only<D>(h, item, mem_h, mem_r, mem_t, B, scores, scores_norm, ws, st);
+  if (c.n_mix_hop > 1) return forward_mix_impl<D>(h, item, mem_h, mem_r, mem_t, B, scores, scores_norm, ws, st);
   const Layout L = handle_layout(h, B);
   const mvin_params_t& P = h->P;
   int rc;
@@ -190,80 +279,22 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
       LAUNCH_CHECK(h, "table_fwd");
     }
   }
-  // the user side in one launch: seeds v = E[item], Q = RK^T v, ripple attention, user MLP -> user_o
-  // (model.py:125-134, :161-240).  With a large relation-KGE table Q comes from a batched GEMM instead.
-  const bool q_fused = user_q_fused(D, nr);
-  if (!q_fused && p > 0) {
-    const long n = (long)B * C::LPR;
-    MVIN_LAUNCH((prep_items_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, item, h->etab, B, nullptr,
-                                                                      at<float>(ws, L.Vbuf), nullptr);
-    LAUNCH_CHECK(h, "prep_items");
-  }
-  // Q[b, r, :] = RK[r]^T v_b      (model.py:211-220 refactored)
-  if (!q_fused && p > 0) {
-    GemmArgs g = gemm_args();
-    g.A = at<float>(ws, L.Vbuf); g.sa_m = D; g.sa_k = 1; g.bsA = 0;
-    g.B = P.relation_kge; g.sb_k = D; g.sb_n = 1; g.bsB = (long)D * D;
-    g.C = at<float>(ws, L.Q); g.ldc = (long)nr * D; g.bsC = D;
-    g.M = B; g.N = D; g.K = D; g.nbatch = nr;
-    bool done = false;
-    if constexpr (D == 32 || D == 64) {
-      if (use_tc_gemm<D>(h, B)) {
-        RelGemmArgs ra;
-        memset(&ra, 0, sizeof(ra));
-        ra.V = at<float>(ws, L.Vbuf); ra.RK = P.relation_kge; ra.Q = at<float>(ws, L.Q); ra.B = B; ra.n_rel = nr;
-        ra.RKs = at<unsigned char>(ws, L.RKs);
-        // relation operands split and staged once per step (also read by the backward's dv kernel)
-        MVIN_LAUNCH((rel_stage_kernel<D>), dim3(nr, 2), RG_NT, 0, st, P.relation_kge, at<unsigned char>(ws, L.RKs));
-        LAUNCH_CHECK(h, "rel_stage");
-        if ((rc = set_smem(relq_tc_kernel<D>, relq_tc_smem<D>()))) return rc;
-        MVIN_LAUNCH((relq_tc_kernel<D>), rel_gemm_grid(h, B, nr), RG_NT, relq_tc_smem<D>(), st, ra);
-        LAUNCH_CHECK(h, "gemm_q");
-        done = true;
-      }
-    }
-    if (!done && (rc = run_gemm(h, st, g, "gemm_q"))) return rc;
-  }
-  {
-    UserArgs a;
-    memset(&a, 0, sizeof(a));
-    a.E = h->etab; a.item = item; a.RK = P.relation_kge; a.w_hi = P.h_item_w;
-    a.W_user = P.user_mlp_w; a.b_user = P.user_mlp_b;
-    a.mem_h = mem_h; a.mem_r = mem_r; a.mem_t = mem_t;
-    a.Vbuf = at<float>(ws, L.Vbuf); a.Q = at<float>(ws, L.Q); a.probs = at<float>(ws, L.probs);
-    a.O = at<float>(ws, L.O); a.u = at<float>(ws, L.u);
-    a.B = B; a.m = m; a.p = p; a.n_rel = nr; a.q_ready = q_fused ? 0 : 1;
-    const int PB = user_pairs_per_cta(D, nr, p, m, h->user_pb_fwd);
-    const size_t sm = user_fwd_smem(D, PB, nr, p, m);
-    const int nt = 32 * user_warps(PB, p);
-    const unsigned grid = (unsigned)((B + PB - 1) / PB);
-    switch (PB) {
-      case 4:
-        if ((rc = set_smem(user_fwd_kernel<D, 4>, sm))) return rc;
-        MVIN_LAUNCH((user_fwd_kernel<D, 4>), grid, nt, sm, st, a);
-        break;
-      case 2:
-        if ((rc = set_smem(user_fwd_kernel<D, 2>, sm))) return rc;
-        MVIN_LAUNCH((user_fwd_kernel<D, 2>), grid, nt, sm, st, a);
-        break;
-      default:
-        if ((rc = set_smem(user_fwd_kernel<D, 1>, sm))) return rc;
-        MVIN_LAUNCH((user_fwd_kernel<D, 1>), grid, nt, sm, st, a);
-    }
-    LAUNCH_CHECK(h, "user_fwd");
-  }
+  if ((rc = user_side_forward<D>(h, item, mem_h, mem_r, mem_t, B, ws, st))) return rc;
   // --ablation no_kg_eh_uo (User_orient_kg_eh = 0, model.py:152-156): the KG side is oriented by the raw user embedding
-  // U[user] instead of user_o; the score still uses user_o
+  // U[user] instead of user_o; the score still uses user_o.  HO_only (model.py:146-150): the SCORE uses U[user]; the KG
+  // side is oriented by user_o (ho_only_uo_kg_eh) or by U[user] (ho_only)
   const bool kg_eh = (c.flags & MVIN_FLAG_KG_EH) != 0;
+  const bool ho_only = (c.flags & MVIN_FLAG_HO_ONLY) != 0;
   const float* u_kg = at<float>(ws, L.u);
-  if (!kg_eh) {
-    if (!h->user) return fail(MVIN_ERR_INVALID, "user_indices are required when User_orient_kg_eh = 0");
+  if (!kg_eh || ho_only) {
+    if (!h->user) return fail(MVIN_ERR_INVALID, "user_indices are required when User_orient_kg_eh = 0 or HO_only = 1");
     const long n = (long)B * C::LPR;
     MVIN_LAUNCH((gather_user_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, h->user, P.user_emb, B, at<float>(ws, L.ukg),
                 at<int32_t>(ws, L.user32));
     LAUNCH_CHECK(h, "gather_user");
-    u_kg = at<float>(ws, L.ukg);
+    if (!kg_eh) u_kg = at<float>(ws, L.ukg);
   }
+  const float* u_score = ho_only ? at<float>(ws, L.ukg) : at<float>(ws, L.u);
   par.join(0);
   // user-oriented transform of levels 0..L-1, one launch   (model.py:270-283)
   {
@@ -445,7 +476,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
     const size_t sm = sizeof(float) * ((size_t)RT * (H + 1) * D + (D <= 64 ? (size_t)(H + 1) * D * D : 0));
     if ((rc = set_smem(mix_score_kernel<D>, sm))) return rc;
     MVIN_LAUNCH((mix_score_kernel<D>), (unsigned)((B + RT - 1) / RT), 256, sm, st, at<float>(ws, L.V[0][0]), P.mix_w, P.mix_b,
-                                                                        at<float>(ws, L.u), B, H + 1, at<float>(ws, L.item),
+                                                                        u_score, B, H + 1, at<float>(ws, L.item),
                                                                         at<float>(ws, L.scores), scores_norm);
     LAUNCH_CHECK(h, "mix_score");
     if (scores) CUDA_TRY(cudaMemcpyAsync(scores, at<float>(ws, L.scores), sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
@@ -462,7 +493,8 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
 template <int D>
 int backward_init(mvin_handle_t h, int B, void* ws, cudaStream_t st, cudaEvent_t mid, bool zero_small) {
   const mvin_config_t& c = h->cfg;
-  const int H = c.h_hop, p = c.p_hop, nr = c.n_relation;
+  // Hm = iterations per mix block (--h_hop), M = mix blocks, H = Hm M = depth = number of aggregators (n_mix_hop = 1: H = Hm)
+  const int Hm = c.h_hop, M = c.n_mix_hop, H = Hm * M, p = c.p_hop, nr = c.n_relation;
   const Layout L = handle_layout(h, B);
   const mvin_params_t& P = h->P;
   const mvin_params_t& G = h->G;
@@ -481,24 +513,29 @@ int backward_init(mvin_handle_t h, int B, void* ws, cudaStream_t st, cudaEvent_t
       ++n;
     };
     const float pm = p > 0 ? 1.f : 0.f;
+    const float am = (c.flags & MVIN_FLAG_PS_ONLY) ? 0.f : 1.f;                    // PS_only: no aggregators (model.py:393)
     add(P.user_emb, G.user_emb, (long)c.n_user * D, l2a, 1.f, 1);                 // model.py:392
     add(P.relation_emb, G.relation_emb, (long)nr * D, l2w, 1.f, 0);               // :388
     add(P.relation_kge, G.relation_kge, (long)nr * D * D, 0.f, 0.f, 0);
-    add(P.mix_w, G.mix_w, (long)(H + 1) * D * D, l2a, 1.f, 1);                    // :400-401
-    add(P.mix_b, G.mix_b, D, l2a, 1.f, 1);
+    add(P.mix_w, G.mix_w, (long)M * (Hm + 1) * D * D, l2a, 1.f, 1);               // :400-401
+    add(P.mix_b, G.mix_b, (long)M * D, l2a, 1.f, 1);
     add(P.user_mlp_w, G.user_mlp_w, (long)(p + 1) * D * D, l2w, pm, 0);           // :404
     add(P.user_mlp_b, G.user_mlp_b, D, l2w, pm, 0);
-    if (H > 0) {
-      add(P.transfer_w, G.transfer_w, (long)H * D * D, l2w, pm, 0);               // :407-408
-      add(P.transfer_b, G.transfer_b, (long)H * D, l2w, pm, 0);
+    // :405 regularises the LAST transfer matrix created (index H), :407-408 the matrices 0..h_hop: with n_mix_hop = 1 the
+    // last one counts twice, with n_mix_hop > 1 the matrices h_hop+1 .. H-1 are not regularised at all
+    for (int e = 0; e <= H; ++e) {
+      const float mult = ((e <= Hm) ? 1.f : 0.f) + ((e == H) ? 1.f : 0.f);
+      int e2 = e;
+      while (e2 + 1 <= H && (((e2 + 1 <= Hm) ? 1.f : 0.f) + ((e2 + 1 == H) ? 1.f : 0.f)) == mult) ++e2;   // run of equal weights
+      add(P.transfer_w + (long)e * D * D, G.transfer_w + (long)e * D * D, (long)(e2 - e + 1) * D * D, l2w, mult * pm, 0);
+      add(P.transfer_b + (long)e * D, G.transfer_b + (long)e * D, (long)(e2 - e + 1) * D, l2w, mult * pm, 0);
+      e = e2;
     }
-    add(P.transfer_w + (long)H * D * D, G.transfer_w + (long)H * D * D, (long)D * D, l2w, 2.f * pm, 0);   // :405 + :408
-    add(P.transfer_b + (long)H * D, G.transfer_b + (long)H * D, D, l2w, 2.f * pm, 0);
     add(P.h_item_w, G.h_item_w, 2 * D, l2w, 1.f, 0);                              // :410
     add(P.h_item_b, G.h_item_b, 1, l2w, 1.f, 0);
-    add(P.agg_w, G.agg_w, (long)H * D * D, l2a, 1.f, 1);                          // :394-396
+    add(P.agg_w, G.agg_w, (long)H * D * D, l2a, am, 1);                           // :394-396
     add(P.agg_b, G.agg_b, (long)H * D, 0.f, 0.f, 1);
-    add(P.agg_urh_w, G.agg_urh_w, (long)H * 3 * D, l2a, 1.f, 1);
+    add(P.agg_urh_w, G.agg_urh_w, (long)H * 3 * D, l2a, am, 1);
     add(P.agg_urh_b, G.agg_urh_b, H, 0.f, 0.f, 1);
     sg.count = n;
     MVIN_LAUNCH((l2_dense_kernel), h->sm_count * 2, 256, 0, st, sg, acc);
@@ -531,10 +568,137 @@ int launch_dw(mvin_handle_t h, cudaStream_t st, const DwArgs& a, int groups, con
   return MVIN_OK;
 }
 
+// the user side of the backward pass: user_o = O . W_user + b, the ripple attention, Q = RK^T v and the un-normalised L2 over
+// the gathered memories (model.py:161-240 backward, :383-386).  du_mlp = dL/d user_o [B, D].  Leaves work on both side
+// streams of `par`; the caller joins them.
+template <int D>
+int user_side_backward(mvin_handle_t h, const Par& par, const float* du_mlp, int B, void* ws, cudaStream_t st) {
+  using C = TC<D>;
+  const mvin_config_t& c = h->cfg;
+  const int p = c.p_hop, m = c.n_memory, nr = c.n_relation;
+  const Layout L = handle_layout(h, B);
+  const mvin_params_t& P = h->P;
+  const mvin_params_t& G = h->G;
+  const float l2w = c.l2_weight;
+  float* acc = at<float>(ws, L.acc);
+  int rc;
+  // user_o = O . W_user + b  backward
+  {
+    DwArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int s = 0; s <= p; ++s) {
+      a.A[s] = at<float>(ws, L.O) + (long)s * D; a.lda[s] = (long)(p + 1) * D; a.dW[s] = G.user_mlp_w + (long)s * D * D;
+    }
+    a.G = du_mlp; a.db = G.user_mlp_b; a.rows = B;
+    par.fork(1);                                   // side stream 1: weight gradient of the user MLP
+    if ((rc = launch_dw<D>(h, par.s(1), a, p + 1, "dw_user"))) return rc;
+    // dO = du . W_user^T as a batched GEMM (a per-warp matvec inside the ripple kernel re-reads W_user per warp and
+    // measured slower: +9 us at C2, +78 us at C3)
+    GemmArgs g = gemm_args();
+    g.A = du_mlp; g.sa_m = D; g.sa_k = 1;
+    g.B = P.user_mlp_w; g.sb_k = 1; g.sb_n = D;
+    g.C = at<float>(ws, L.dO); g.ldc = (long)(p + 1) * D;
+    g.M = B; g.N = (p + 1) * D; g.K = D;
+    if ((rc = run_gemm(h, st, g, "gemm_user_bwd"))) return rc;
+  }
+  // ripple backward
+  {
+    RippleBwdArgs a;
+    a.E = h->etab; a.Q = at<float>(ws, L.Q); a.w_hi = P.h_item_w;
+    a.mem_h = h->mem_h; a.mem_r = h->mem_r; a.mem_t = h->mem_t;
+    a.probs = at<float>(ws, L.probs); a.dO = at<float>(ws, L.dO);
+    a.dE = h->gtab; a.dQ = at<float>(ws, L.dQ); a.dw_hi = G.h_item_w; a.l2_acc = acc + 1;
+    a.l2_weight = l2w; a.B = B; a.m = m; a.p = p; a.n_rel = nr;
+    const size_t sm = ripple_bwd_smem(m, D);
+    if ((rc = set_smem(ripple_bwd_kernel<D>, sm))) return rc;
+    a.ctr = h->d_sched + 4;
+    const long warps = (long)B * (p + 1);
+    long grid = (warps + RIPPLE_NW - 1) / RIPPLE_NW;
+    const long resident = (long)h->sm_count * resident_ctas(h, ripple_bwd_kernel<D>, RIPPLE_NT, sm) * 2;   // cap 4 -> 8
+    if (grid > resident) grid = resident;
+    MVIN_LAUNCH((ripple_bwd_kernel<D>), (unsigned)grid, RIPPLE_NT, sm, st, a);
+    LAUNCH_CHECK(h, "ripple_bwd");
+  }
+  if (p > 0) {
+    // three independent consumers of dQ / cnt: RK L2 term (side 1), dRK (side 0), dE[item] (launch stream)
+    par.fork(0);
+    par.fork(1);
+    MVIN_LAUNCH((rk_l2_kernel), nr, 256, 0, par.s(1), P.relation_kge, at<float>(ws, L.cnt), D * D, 2.f * l2w, G.relation_kge, acc + 1);
+    LAUNCH_CHECK(h, "rk_l2");
+    // dRK[r][i][j] += sum_b v[b][i] dQ[b][r][j]
+    GemmArgs g = gemm_args();
+    g.A = at<float>(ws, L.Vbuf); g.sa_m = 1; g.sa_k = D; g.bsA = 0;
+    g.B = at<float>(ws, L.dQ); g.sb_k = (long)nr * D; g.sb_n = 1; g.bsB = D;
+    g.C = G.relation_kge; g.ldc = D; g.bsC = (long)D * D;
+    g.M = D; g.N = D; g.K = B; g.nbatch = nr; g.ksplit = pick_ksplit(B); g.accumulate = 1;
+    const bool tcg = use_tc_gemm<D>(h, B);
+    const bool q_fused_fwd = user_q_fused(D, nr);
+    if constexpr (D == 32 || D == 64) {
+      if (tcg) {
+        cudaStream_t st = par.s(0);
+        RelGemmArgs ra;
+        memset(&ra, 0, sizeof(ra));
+        ra.V = at<float>(ws, L.Vbuf); ra.dQ = at<float>(ws, L.dQ); ra.dRK = G.relation_kge; ra.B = B; ra.n_rel = nr;
+        if ((rc = set_smem(reldrk_tc_kernel<D>, reldrk_tc_smem<D>()))) return rc;
+        MVIN_LAUNCH((reldrk_tc_kernel<D>), rel_gemm_grid(h, B, nr), RG_NT, reldrk_tc_smem<D>(), st, ra);
+        LAUNCH_CHECK(h, "gemm_drk");
+      }
+    }
+    if (!tcg && (rc = run_gemm(h, par.s(0), g, "gemm_drk"))) return rc;
+    // dv[b][i] = sum_r sum_j dQ[b][r][j] RK[r][i][j]  (reduced over r inside the CTA);  dE[item_b] += dv[b]
+    GemmArgs g2 = gemm_args();
+    g2.A = at<float>(ws, L.dQ); g2.sa_m = (long)nr * D; g2.sa_k = 1; g2.bsA = D;
+    g2.B = P.relation_kge; g2.sb_k = 1; g2.sb_n = D; g2.bsB = (long)D * D;
+    g2.M = B; g2.N = D; g2.K = D; g2.nbatch = nr; g2.reduce = 1;
+    g2.ksplit = nr >= 8 ? 4 : 1;
+    bool dv_done = false;
+    if constexpr (D == 32 || D == 64) {
+      if (tcg) {
+        RelGemmArgs ra;
+        memset(&ra, 0, sizeof(ra));
+        ra.dQ = at<float>(ws, L.dQ); ra.RK = P.relation_kge; ra.B = B; ra.n_rel = nr;
+        ra.RKs = at<unsigned char>(ws, L.RKs);
+        if (q_fused_fwd) {                                   // the forward built Q inside the user kernel: stage the operands now
+          MVIN_LAUNCH((rel_stage_kernel<D>), dim3(nr, 2), RG_NT, 0, st, P.relation_kge, at<unsigned char>(ws, L.RKs));
+          LAUNCH_CHECK(h, "rel_stage");
+        }
+        if (h->n_shards == 1) { ra.dE = G.entity_emb; ra.rows = at<int32_t>(ws, L.ent[0]); }
+        else { ra.dE = at<float>(ws, L.dv); ra.rows = nullptr; }          // dense dv (zeroed region), scattered below
+        if ((rc = set_smem(reldv_tc_kernel<D>, reldv_tc_smem<D>()))) return rc;
+        MVIN_LAUNCH((reldv_tc_kernel<D>), rel_gemm_grid(h, B, nr), RG_NT, reldv_tc_smem<D>(), st, ra);
+        LAUNCH_CHECK(h, "gemm_dv");
+        if (h->n_shards != 1) {
+          const long n = (long)B * C::LPR;
+          MVIN_LAUNCH((scatter_rows_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, at<float>(ws, L.dv), at<int32_t>(ws, L.ent[0]), B,
+                      h->gtab);
+          LAUNCH_CHECK(h, "scatter_dv");
+        }
+        dv_done = true;
+      }
+    }
+    if (dv_done) {
+    } else if (h->n_shards == 1) {
+      // accumulate straight into the entity-table gradient rows of the items
+      g2.C = G.entity_emb; g2.ldc = D; g2.bsC = 0; g2.c_rows = at<int32_t>(ws, L.ent[0]); g2.accumulate = 1;
+      if ((rc = run_gemm(h, st, g2, "gemm_dv"))) return rc;
+    } else {
+      g2.C = at<float>(ws, L.dv); g2.ldc = D; g2.bsC = 0; g2.accumulate = g2.ksplit > 1;   // dv lives in the zeroed region
+      if ((rc = run_gemm(h, st, g2, "gemm_dv"))) return rc;
+      const long n = (long)B * C::LPR;
+      MVIN_LAUNCH((scatter_rows_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, at<float>(ws, L.dv), at<int32_t>(ws, L.ent[0]), B,
+                                                                          h->gtab);
+      LAUNCH_CHECK(h, "scatter_dv");
+    }
+  }
+  return MVIN_OK;
+}
+
 template <int D>
 int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out, void* ws, cudaStream_t st) {
   using C = TC<D>;
   const mvin_config_t& c = h->cfg;
+  if (c.flags & MVIN_FLAG_PS_ONLY) return backward_ps_only<D>(h, labels, B, losses_out, ws, st);
+  if (c.n_mix_hop > 1) return backward_mix_impl<D>(h, labels, B, losses_out, ws, st);
   const int K = c.neighbor_sample_size, H = c.h_hop, p = c.p_hop, m = c.n_memory, nr = c.n_relation;
   const Layout L = handle_layout(h, B);
   const mvin_params_t& P = h->P;
@@ -569,11 +733,23 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
   }
   }
 
+  // Three roles of "the user vector" and where their gradients go (forward_impl):
+  //   score side  u_score: user_o, or U[user] under HO_only      -> du  (written by the loss kernel)
+  //   KG side     u_kg:    user_o, or U[user] when User_orient_kg_eh = 0 -> du_kg (accumulated by the KG kernels)
+  //   user MLP    du_mlp = dL/d user_o: the sum of the roles user_o plays
+  // Gradients of the U[user] roles are scattered into the user table (du_user).  `dukg` sits in the zeroed region.
+  //   all:                 du_kg = du            du_mlp = du     du_user = none
+  //   no_kg_eh_uo:         du_kg = dukg          du_mlp = du     du_user = dukg
+  //   ho_only (kg_eh = 0): du_kg = du            du_mlp = dukg (stays zero: user_o is unused)   du_user = du
+  //   ho_only_uo_kg_eh:    du_kg = dukg          du_mlp = dukg   du_user = du
   float* du = at<float>(ws, L.du);
-  // User_orient_kg_eh = 0: the KG side read U[user] (forward_impl), its gradient goes to the user table, not to user_o
   const bool kg_eh = (c.flags & MVIN_FLAG_KG_EH) != 0;
+  const bool ho_only = (c.flags & MVIN_FLAG_HO_ONLY) != 0;
   const float* u_kg = kg_eh ? at<float>(ws, L.u) : at<float>(ws, L.ukg);
-  float* du_kg = kg_eh ? du : at<float>(ws, L.dukg);
+  const float* u_score = ho_only ? at<float>(ws, L.ukg) : at<float>(ws, L.u);
+  float* du_kg = (kg_eh != ho_only) ? du : at<float>(ws, L.dukg);
+  const float* du_mlp = ho_only ? at<float>(ws, L.dukg) : du;
+  const float* du_user = ho_only ? du : (!kg_eh ? at<float>(ws, L.dukg) : nullptr);
   float* ditem = at<float>(ws, L.ditem);
   const float invB = 1.f / (float)(h->global_batch > 0 ? h->global_batch : B);
   const bool fused_mix_bwd = D <= 64;          // W_mix^T ((H+1) d^2 floats) is staged in shared memory
@@ -582,12 +758,12 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     const size_t sm = sizeof(float) * ((size_t)D * (H + 1) * D + 16 * D);
     if ((rc = set_smem(loss_mix_bwd_kernel<D>, sm))) return rc;
     const int grid = (B + 15) / 16 < 2 * h->sm_count ? (B + 15) / 16 : 2 * h->sm_count;
-    MVIN_LAUNCH((loss_mix_bwd_kernel<D>), grid, 256, sm, st, at<float>(ws, L.scores), labels, at<float>(ws, L.u), at<float>(ws, L.item),
+    MVIN_LAUNCH((loss_mix_bwd_kernel<D>), grid, 256, sm, st, at<float>(ws, L.scores), labels, u_score, at<float>(ws, L.item),
                                                   P.mix_w, B, H + 1, invB, ditem, du, at<float>(ws, L.DC[0][0]), acc);
     LAUNCH_CHECK(h, "loss_mix_bwd");
   } else {
     const long n = (long)B * C::LPR;
-    MVIN_LAUNCH((loss_bwd_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, at<float>(ws, L.scores), labels, at<float>(ws, L.u),
+    MVIN_LAUNCH((loss_bwd_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, at<float>(ws, L.scores), labels, u_score,
                                                                     at<float>(ws, L.item), B, invB, ditem, du, acc);
     LAUNCH_CHECK(h, "loss_bwd");
   }
@@ -871,123 +1047,393 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
     }
     LAUNCH_CHECK(h, "transform_bwd");
   }
-  if (!kg_eh) {
+  if (du_user) {
     const long n = (long)B * C::LPR;
-    MVIN_LAUNCH((scatter_rows_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, du_kg, at<int32_t>(ws, L.user32), B,
+    MVIN_LAUNCH((scatter_rows_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, du_user, at<int32_t>(ws, L.user32), B,
                 GTab{G.user_emb, nullptr, 0, 0});
     LAUNCH_CHECK(h, "scatter_du_user");
   }
-  // user_o = O . W_user + b  backward
-  {
-    DwArgs a;
-    memset(&a, 0, sizeof(a));
-    for (int s = 0; s <= p; ++s) {
-      a.A[s] = at<float>(ws, L.O) + (long)s * D; a.lda[s] = (long)(p + 1) * D; a.dW[s] = G.user_mlp_w + (long)s * D * D;
-    }
-    a.G = du; a.db = G.user_mlp_b; a.rows = B;
-    par.fork(1);                                   // side stream 1: weight gradient of the user MLP
-    if ((rc = launch_dw<D>(h, par.s(1), a, p + 1, "dw_user"))) return rc;
-    // dO = du . W_user^T as a batched GEMM (a per-warp matvec inside the ripple kernel re-reads W_user per warp and
-    // measured slower: +9 us at C2, +78 us at C3)
-    GemmArgs g = gemm_args();
-    g.A = du; g.sa_m = D; g.sa_k = 1;
-    g.B = P.user_mlp_w; g.sb_k = 1; g.sb_n = D;
-    g.C = at<float>(ws, L.dO); g.ldc = (long)(p + 1) * D;
-    g.M = B; g.N = (p + 1) * D; g.K = D;
-    if ((rc = run_gemm(h, st, g, "gemm_user_bwd"))) return rc;
-  }
-  // ripple backward
-  {
-    RippleBwdArgs a;
-    a.E = h->etab; a.Q = at<float>(ws, L.Q); a.w_hi = P.h_item_w;
-    a.mem_h = h->mem_h; a.mem_r = h->mem_r; a.mem_t = h->mem_t;
-    a.probs = at<float>(ws, L.probs); a.dO = at<float>(ws, L.dO);
-    a.dE = h->gtab; a.dQ = at<float>(ws, L.dQ); a.dw_hi = G.h_item_w; a.l2_acc = acc + 1;
-    a.l2_weight = l2w; a.B = B; a.m = m; a.p = p; a.n_rel = nr;
-    const size_t sm = ripple_bwd_smem(m, D);
-    if ((rc = set_smem(ripple_bwd_kernel<D>, sm))) return rc;
-    a.ctr = h->d_sched + 4;
-    const long warps = (long)B * (p + 1);
-    long grid = (warps + RIPPLE_NW - 1) / RIPPLE_NW;
-    const long resident = (long)h->sm_count * resident_ctas(h, ripple_bwd_kernel<D>, RIPPLE_NT, sm) * 2;   // cap 4 -> 8
-    if (grid > resident) grid = resident;
-    MVIN_LAUNCH((ripple_bwd_kernel<D>), (unsigned)grid, RIPPLE_NT, sm, st, a);
-    LAUNCH_CHECK(h, "ripple_bwd");
-  }
-  if (p > 0) {
-    // three independent consumers of dQ / cnt: RK L2 term (side 1), dRK (side 0), dE[item] (launch stream)
-    par.fork(0);
-    par.fork(1);
-    MVIN_LAUNCH((rk_l2_kernel), nr, 256, 0, par.s(1), P.relation_kge, at<float>(ws, L.cnt), D * D, 2.f * l2w, G.relation_kge, acc + 1);
-    LAUNCH_CHECK(h, "rk_l2");
-    // dRK[r][i][j] += sum_b v[b][i] dQ[b][r][j]
-    GemmArgs g = gemm_args();
-    g.A = at<float>(ws, L.Vbuf); g.sa_m = 1; g.sa_k = D; g.bsA = 0;
-    g.B = at<float>(ws, L.dQ); g.sb_k = (long)nr * D; g.sb_n = 1; g.bsB = D;
-    g.C = G.relation_kge; g.ldc = D; g.bsC = (long)D * D;
-    g.M = D; g.N = D; g.K = B; g.nbatch = nr; g.ksplit = pick_ksplit(B); g.accumulate = 1;
-    const bool tcg = use_tc_gemm<D>(h, B);
-    const bool q_fused_fwd = user_q_fused(D, nr);
-    if constexpr (D == 32 || D == 64) {
-      if (tcg) {
-        cudaStream_t st = par.s(0);
-        RelGemmArgs ra;
-        memset(&ra, 0, sizeof(ra));
-        ra.V = at<float>(ws, L.Vbuf); ra.dQ = at<float>(ws, L.dQ); ra.dRK = G.relation_kge; ra.B = B; ra.n_rel = nr;
-        if ((rc = set_smem(reldrk_tc_kernel<D>, reldrk_tc_smem<D>()))) return rc;
-        MVIN_LAUNCH((reldrk_tc_kernel<D>), rel_gemm_grid(h, B, nr), RG_NT, reldrk_tc_smem<D>(), st, ra);
-        LAUNCH_CHECK(h, "gemm_drk");
-      }
-    }
-    if (!tcg && (rc = run_gemm(h, par.s(0), g, "gemm_drk"))) return rc;
-    // dv[b][i] = sum_r sum_j dQ[b][r][j] RK[r][i][j]  (reduced over r inside the CTA);  dE[item_b] += dv[b]
-    GemmArgs g2 = gemm_args();
-    g2.A = at<float>(ws, L.dQ); g2.sa_m = (long)nr * D; g2.sa_k = 1; g2.bsA = D;
-    g2.B = P.relation_kge; g2.sb_k = 1; g2.sb_n = D; g2.bsB = (long)D * D;
-    g2.M = B; g2.N = D; g2.K = D; g2.nbatch = nr; g2.reduce = 1;
-    g2.ksplit = nr >= 8 ? 4 : 1;
-    bool dv_done = false;
-    if constexpr (D == 32 || D == 64) {
-      if (tcg) {
-        RelGemmArgs ra;
-        memset(&ra, 0, sizeof(ra));
-        ra.dQ = at<float>(ws, L.dQ); ra.RK = P.relation_kge; ra.B = B; ra.n_rel = nr;
-        ra.RKs = at<unsigned char>(ws, L.RKs);
-        if (q_fused_fwd) {                                   // the forward built Q inside the user kernel: stage the operands now
-          MVIN_LAUNCH((rel_stage_kernel<D>), dim3(nr, 2), RG_NT, 0, st, P.relation_kge, at<unsigned char>(ws, L.RKs));
-          LAUNCH_CHECK(h, "rel_stage");
-        }
-        if (h->n_shards == 1) { ra.dE = G.entity_emb; ra.rows = at<int32_t>(ws, L.ent[0]); }
-        else { ra.dE = at<float>(ws, L.dv); ra.rows = nullptr; }          // dense dv (zeroed region), scattered below
-        if ((rc = set_smem(reldv_tc_kernel<D>, reldv_tc_smem<D>()))) return rc;
-        MVIN_LAUNCH((reldv_tc_kernel<D>), rel_gemm_grid(h, B, nr), RG_NT, reldv_tc_smem<D>(), st, ra);
-        LAUNCH_CHECK(h, "gemm_dv");
-        if (h->n_shards != 1) {
-          const long n = (long)B * C::LPR;
-          MVIN_LAUNCH((scatter_rows_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, at<float>(ws, L.dv), at<int32_t>(ws, L.ent[0]), B,
-                      h->gtab);
-          LAUNCH_CHECK(h, "scatter_dv");
-        }
-        dv_done = true;
-      }
-    }
-    if (dv_done) {
-    } else if (h->n_shards == 1) {
-      // accumulate straight into the entity-table gradient rows of the items
-      g2.C = G.entity_emb; g2.ldc = D; g2.bsC = 0; g2.c_rows = at<int32_t>(ws, L.ent[0]); g2.accumulate = 1;
-      if ((rc = run_gemm(h, st, g2, "gemm_dv"))) return rc;
-    } else {
-      g2.C = at<float>(ws, L.dv); g2.ldc = D; g2.bsC = 0; g2.accumulate = g2.ksplit > 1;   // dv lives in the zeroed region
-      if ((rc = run_gemm(h, st, g2, "gemm_dv"))) return rc;
-      const long n = (long)B * C::LPR;
-      MVIN_LAUNCH((scatter_rows_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, at<float>(ws, L.dv), at<int32_t>(ws, L.ent[0]), B,
-                                                                          h->gtab);
-      LAUNCH_CHECK(h, "scatter_dv");
-    }
-  }
+  if ((rc = user_side_backward<D>(h, par, du_mlp, B, ws, st))) return rc;
   par.join(0);
   par.join(1);
   MVIN_LAUNCH((finalize_loss_kernel), 1, 32, 0, st, acc, l2w, l2a, losses_out);
+  LAUNCH_CHECK(h, "finalize_loss");
+  return MVIN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// --ablation ps_only (PS_only = 1, model.py:142-144): score = user_o . E[item]; the KG side does not exist
+// ------------------------------------------------------------------------------------------------------
+template <int D>
+int forward_ps_only(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, const int32_t* mem_r, const int32_t* mem_t,
+                    int B, float* scores, float* scores_norm, void* ws, cudaStream_t st) {
+  using C = TC<D>;
+  const Layout L = handle_layout(h, B);
+  int rc;
+  prof_mark(h, st, nullptr);
+  MVIN_LAUNCH((seed_kernel), (unsigned)((B + 255) / 256), 256, 0, st, item, B, at<int32_t>(ws, L.ent[0]), (int32_t*)nullptr);
+  LAUNCH_CHECK(h, "seed");
+  if ((rc = user_side_forward<D>(h, item, mem_h, mem_r, mem_t, B, ws, st))) return rc;   // leaves Vbuf = E[item], u = user_o
+  const long n = (long)B * C::LPR;
+  MVIN_LAUNCH((score_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, (const float*)at<float>(ws, L.u),
+              (const float*)at<float>(ws, L.Vbuf), B, at<float>(ws, L.scores), scores_norm);
+  LAUNCH_CHECK(h, "score");
+  if (scores) CUDA_TRY(cudaMemcpyAsync(scores, at<float>(ws, L.scores), sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
+  return MVIN_OK;
+}
+
+template <int D>
+int backward_ps_only(mvin_handle_t h, const float* labels, int B, float* losses_out, void* ws, cudaStream_t st) {
+  using C = TC<D>;
+  const mvin_config_t& c = h->cfg;
+  const Layout L = handle_layout(h, B);
+  float* acc = at<float>(ws, L.acc);
+  int rc;
+  prof_mark(h, st, nullptr);
+  const Par par{h, st, false};                               // one stream: the step is a handful of small kernels
+  CUDA_TRY(cudaMemsetAsync(at<char>(ws, L.zero_begin), 0, L.zero_mid - L.zero_begin, st));
+  if ((rc = backward_init<D>(h, B, ws, st, nullptr, false))) return rc;
+  if (c.p_hop > 0) {
+    const long n = (long)c.p_hop * B * c.n_memory;
+    MVIN_LAUNCH((hist_r_kernel), h->sm_count * 4, 256, sizeof(float) * c.n_relation, st, h->mem_r, n, c.n_relation,
+                at<float>(ws, L.cnt));
+    LAUNCH_CHECK(h, "hist_r");
+  }
+  const float invB = 1.f / (float)(h->global_batch > 0 ? h->global_batch : B);
+  const long n = (long)B * C::LPR;
+  // ditem = g user_o -> dE[item] ;  du = g E[item] -> the user MLP
+  MVIN_LAUNCH((loss_bwd_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, (const float*)at<float>(ws, L.scores), labels,
+              (const float*)at<float>(ws, L.u), (const float*)at<float>(ws, L.Vbuf), B, invB, at<float>(ws, L.ditem),
+              at<float>(ws, L.du), acc);
+  LAUNCH_CHECK(h, "loss_bwd");
+  MVIN_LAUNCH((scatter_rows_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, (const float*)at<float>(ws, L.ditem),
+              (const int32_t*)at<int32_t>(ws, L.ent[0]), B, h->gtab);
+  LAUNCH_CHECK(h, "scatter_ditem");
+  if ((rc = user_side_backward<D>(h, par, at<float>(ws, L.du), B, ws, st))) return rc;
+  MVIN_LAUNCH((finalize_loss_kernel), 1, 32, 0, st, acc, c.l2_weight, c.l2_agg_weight, losses_out);
+  LAUNCH_CHECK(h, "finalize_loss");
+  return MVIN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// n_mix_hop = M > 1 (model.py:286-315): M mix blocks of Hm = h_hop aggregator iterations over a neighbourhood of depth
+// Lt = Hm M.  Aggregator g = n Hm + i (block n, iteration i) maps levels 0 .. Lt-g-1; after the Hm iterations of block n
+// the mix layer n is applied to EVERY surviving level 0 .. Lt-(n+1)Hm:
+//   X[n+1][h] = [ in_n[h] ; V[n Hm + 1][h] ; ... ; V[n Hm + Hm][h] ] . W_mix[n] + b_mix[n],   in_0 = T (transform), in_n = X[n]
+// and the item vector is X[M][0].  Built from the row kernels of the single-block path, one launch per (iteration,
+// level), plus small GEMMs for the mix layers: a correctness path for the reference's deeper variants, not a tuned one.
+// ------------------------------------------------------------------------------------------------------
+struct MixGeom {
+  int Hm, M, Lt;
+  int last_level(int g) const { return Lt - g - 1; }                    // aggregator g maps levels 0 .. Lt-g-1
+  int mix_levels(int n) const { return Lt - (n + 1) * Hm; }             // mix block n maps levels 0 .. this
+};
+
+// input of aggregator g (block n = g / Hm, iteration i = g % Hm) at level lv: the block's input for i = 0, else the
+// previous iteration's output
+inline size_t mix_in(const Layout& L, const MixGeom& q, int g, int lv) {
+  const int n = g / q.Hm, i = g % q.Hm;
+  if (i > 0) return L.V[g][lv];
+  return n == 0 ? L.V[0][lv] : L.X[n][lv];
+}
+// slot k of mix block n at level lv: its input (k = 0) or the output of iteration k-1 of the block
+inline size_t mix_slot(const Layout& L, const MixGeom& q, int n, int k, int lv) {
+  if (k > 0) return L.V[n * q.Hm + k][lv];
+  return n == 0 ? L.V[0][lv] : L.X[n][lv];
+}
+
+// a + b + c of the non-null inputs: the pointer itself when there is one, else summed into `out`
+inline int sum_grads(mvin_handle_t h, cudaStream_t st, const float* a, const float* b, const float* c, long n_floats, float* out,
+                     const float** res) {
+  const float* v[3];
+  int n = 0;
+  if (a) v[n++] = a;
+  if (b) v[n++] = b;
+  if (c) v[n++] = c;
+  if (n == 0) return fail(MVIN_ERR_STATE, "gradient without a producer");
+  if (n == 1) { *res = v[0]; return MVIN_OK; }
+  const long n4 = n_floats / 4;
+  const long want = (n4 + 255) / 256, cap = (long)h->sm_count * 8;
+  MVIN_LAUNCH((sum_rows_kernel), (unsigned)(want < cap ? want : cap), 256, 0, st, v[0], v[1], n == 3 ? v[2] : (const float*)nullptr, n4, out);
+  LAUNCH_CHECK(h, "sum_grads");
+  *res = out;
+  return MVIN_OK;
+}
+
+template <int D>
+int forward_mix_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, const int32_t* mem_r, const int32_t* mem_t,
+                     int B, float* scores, float* scores_norm, void* ws, cudaStream_t st) {
+  using C = TC<D>;
+  const mvin_config_t& c = h->cfg;
+  const int K = c.neighbor_sample_size, nr = c.n_relation;
+  const MixGeom q{c.h_hop, c.n_mix_hop, c.h_hop * c.n_mix_hop};
+  const int Hm = q.Hm, M = q.M, Lt = q.Lt;
+  const Layout L = handle_layout(h, B);
+  const mvin_params_t& P = h->P;
+  int rc;
+  prof_mark(h, st, nullptr);
+  // integer expansion (model.py:243-256): ids of levels 0 .. Lt-1 (level Lt is read from the adjacency records)
+  MVIN_LAUNCH((seed_kernel), (unsigned)((B + 255) / 256), 256, 0, st, item, B, at<int32_t>(ws, L.ent[0]), (int32_t*)nullptr);
+  LAUNCH_CHECK(h, "seed");
+  for (int lv = 0; lv + 1 < Lt; ++lv) {
+    const long n = L.rows[lv] * K;
+    MVIN_LAUNCH((expand_kernel), (unsigned)((n + 255) / 256), 256, 0, st, (const int32_t*)at<int32_t>(ws, L.ent[lv]), h->adj,
+                L.rows[lv], K, at<int32_t>(ws, L.ent[lv + 1]), (int32_t*)nullptr, 1);
+    LAUNCH_CHECK(h, "expand");
+  }
+  MVIN_LAUNCH((rel_scores_kernel), (Lt * nr * 32 + 255) / 256, 256, 0, st, P.relation_emb, P.agg_urh_w, nr, D, Lt, at<float>(ws, L.s));
+  LAUNCH_CHECK(h, "rel_scores");
+  if ((rc = user_side_forward<D>(h, item, mem_h, mem_r, mem_t, B, ws, st))) return rc;
+  // the roles of the user vector: forward_impl
+  const bool kg_eh = (c.flags & MVIN_FLAG_KG_EH) != 0;
+  const bool ho_only = (c.flags & MVIN_FLAG_HO_ONLY) != 0;
+  const float* u_kg = at<float>(ws, L.u);
+  if (!kg_eh || ho_only) {
+    if (!h->user) return fail(MVIN_ERR_INVALID, "user_indices are required when User_orient_kg_eh = 0 or HO_only = 1");
+    const long n = (long)B * C::LPR;
+    MVIN_LAUNCH((gather_user_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, h->user, P.user_emb, B, at<float>(ws, L.ukg),
+                at<int32_t>(ws, L.user32));
+    LAUNCH_CHECK(h, "gather_user");
+    if (!kg_eh) u_kg = at<float>(ws, L.ukg);
+  }
+  const float* u_score = ho_only ? at<float>(ws, L.ukg) : at<float>(ws, L.u);
+  // user-oriented transform of levels 0 .. Lt-1   (model.py:270-283)
+  {
+    const size_t sm = transform_fwd_smem<D>();
+    if ((rc = set_smem(transform_fwd_kernel<D>, sm))) return rc;
+    for (int lv = 0; lv < Lt; ++lv) {
+      TransformArgs a;
+      memset(&a, 0, sizeof(a));
+      long rows[MAX_LV];
+      TransformLevel& t = a.lv[0];
+      t.ent = at<int32_t>(ws, L.ent[lv]);
+      t.W = P.transfer_w + (long)lv * D * D; t.b = P.transfer_b + (long)lv * D;
+      t.T = at<float>(ws, L.V[0][lv]);
+      t.rows = rows[0] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
+      t.stream = stream_level(h, L.rows[lv], D);
+      a.nlev = 1; a.E = h->etab; a.u = u_kg;
+      const int grid = partition_grid(rows, 1, C::R, h->sm_count * resident_ctas(h, transform_fwd_kernel<D>, C::NT, sm), a.cta_end);
+      MVIN_LAUNCH((transform_fwd_kernel<D>), grid, C::NT, sm, st, a);
+      LAUNCH_CHECK(h, "transform_fwd");
+    }
+  }
+  const size_t sm_leaf = agg_fwd_smem<D, true>(K, nr), sm_in = agg_fwd_smem<D, false>(K, nr);
+  if ((rc = set_smem(agg_fwd_kernel<D, true>, sm_leaf))) return rc;
+  if ((rc = set_smem(agg_fwd_kernel<D, false>, sm_in))) return rc;
+  for (int n = 0; n < M; ++n) {
+    for (int i = 0; i < Hm; ++i) {
+      const int g = n * Hm + i;
+      for (int lv = q.last_level(g); lv >= 0; --lv) {
+        AggArgs a;
+        memset(&a, 0, sizeof(a));
+        long rows[MAX_LV];
+        AggLevel& t = a.lv[0];
+        const bool leaf = (g == 0 && lv == Lt - 1);          // children = entity rows, transformed on the fly (W_t[Lt])
+        t.ent = at<int32_t>(ws, L.ent[lv]);
+        t.self = at<float>(ws, mix_in(L, q, g, lv));
+        t.Y = at<float>(ws, L.Y[g][lv]); t.V = at<float>(ws, L.V[g + 1][lv]);
+        t.rows = rows[0] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
+        t.stream = stream_level(h, L.rows[lv], D);
+        t.leaf = leaf ? 1 : 0;
+        if (leaf) t.SU = at<float>(ws, L.SU); else t.child = at<float>(ws, mix_in(L, q, g, lv + 1));
+        a.adj = h->adj; a.s = at<float>(ws, L.s) + (long)g * nr;
+        a.Wa = P.agg_w + (long)g * D * D; a.ba = P.agg_b + (long)g * D;
+        a.K = K; a.n_rel = nr;
+        if (leaf) {
+          a.E = h->etab; a.u = u_kg;
+          a.Wt = P.transfer_w + (long)Lt * D * D; a.bt = P.transfer_b + (long)Lt * D;
+          const int grid = make_tile_list(a.tl, rows, 1, C::R, h->sm_count * resident_ctas(h, agg_fwd_kernel<D, true>, C::NT, sm_leaf),
+                                          h->d_sched);
+          MVIN_LAUNCH((agg_fwd_kernel<D, true>), grid, C::NT, sm_leaf, st, a);
+        } else {
+          const int grid = make_tile_list(a.tl, rows, 1, C::R, h->sm_count * resident_ctas(h, agg_fwd_kernel<D, false>, C::NT, sm_in),
+                                          h->d_sched);
+          MVIN_LAUNCH((agg_fwd_kernel<D, false>), grid, C::NT, sm_in, st, a);
+        }
+        LAUNCH_CHECK(h, "agg_fwd_mix");
+      }
+    }
+    // mix layer n on every surviving level: one GEMM per input slot, accumulated into the output
+    for (int lv = 0; lv <= q.mix_levels(n); ++lv) {
+      float* out = (n + 1 < M) ? at<float>(ws, L.X[n + 1][lv]) : at<float>(ws, L.item);
+      for (int k = 0; k <= Hm; ++k) {
+        GemmArgs gm = gemm_args();
+        gm.A = at<float>(ws, mix_slot(L, q, n, k, lv)); gm.sa_m = D; gm.sa_k = 1;
+        gm.B = P.mix_w + ((long)n * (Hm + 1) + k) * D * D; gm.sb_k = D; gm.sb_n = 1;
+        gm.C = out; gm.ldc = D;
+        gm.M = (int)L.rows[lv]; gm.N = D; gm.K = D;
+        gm.bias = k == 0 ? P.mix_b + (long)n * D : nullptr;
+        gm.accumulate = k > 0;
+        if ((rc = run_gemm(h, st, gm, "gemm_mix"))) return rc;
+      }
+    }
+  }
+  {
+    const long n = (long)B * C::LPR;
+    MVIN_LAUNCH((score_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, u_score, (const float*)at<float>(ws, L.item), B,
+                at<float>(ws, L.scores), scores_norm);
+    LAUNCH_CHECK(h, "score");
+    if (scores) CUDA_TRY(cudaMemcpyAsync(scores, at<float>(ws, L.scores), sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
+  }
+  return MVIN_OK;
+}
+
+template <int D>
+int backward_mix_impl(mvin_handle_t h, const float* labels, int B, float* losses_out, void* ws, cudaStream_t st) {
+  using C = TC<D>;
+  const mvin_config_t& c = h->cfg;
+  const int K = c.neighbor_sample_size, p = c.p_hop, m = c.n_memory, nr = c.n_relation;
+  const MixGeom q{c.h_hop, c.n_mix_hop, c.h_hop * c.n_mix_hop};
+  const int Hm = q.Hm, M = q.M, Lt = q.Lt;
+  const Layout L = handle_layout(h, B);
+  const mvin_params_t& P = h->P;
+  const mvin_params_t& G = h->G;
+  float* acc = at<float>(ws, L.acc);
+  float* wT = at<float>(ws, L.wT);                           // wT[g] = W_a[g]^T (g < Lt), wT[Lt + e] = W_t[e]^T (e <= Lt)
+  int rc;
+  prof_mark(h, st, nullptr);
+  const Par par{h, st, false};                               // one stream
+  CUDA_TRY(cudaMemsetAsync(at<char>(ws, L.zero_begin), 0, L.zero_mid - L.zero_begin, st));
+  if ((rc = backward_init<D>(h, B, ws, st, nullptr, false))) return rc;
+  if (p > 0) {
+    const long n = (long)p * B * m;
+    MVIN_LAUNCH((hist_r_kernel), h->sm_count * 4, 256, sizeof(float) * nr, st, h->mem_r, n, nr, at<float>(ws, L.cnt));
+    LAUNCH_CHECK(h, "hist_r");
+  }
+  // the roles of the user vector and their gradients: backward_impl
+  float* du = at<float>(ws, L.du);
+  const bool kg_eh = (c.flags & MVIN_FLAG_KG_EH) != 0;
+  const bool ho_only = (c.flags & MVIN_FLAG_HO_ONLY) != 0;
+  const float* u_kg = kg_eh ? at<float>(ws, L.u) : at<float>(ws, L.ukg);
+  const float* u_score = ho_only ? at<float>(ws, L.ukg) : at<float>(ws, L.u);
+  float* du_kg = (kg_eh != ho_only) ? du : at<float>(ws, L.dukg);
+  const float* du_mlp = ho_only ? at<float>(ws, L.dukg) : du;
+  const float* du_user = ho_only ? du : (!kg_eh ? at<float>(ws, L.dukg) : nullptr);
+  float* ditem = at<float>(ws, L.ditem);
+  const float invB = 1.f / (float)(h->global_batch > 0 ? h->global_batch : B);
+  {
+    const long n = (long)B * C::LPR;
+    MVIN_LAUNCH((loss_bwd_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, (const float*)at<float>(ws, L.scores), labels, u_score,
+                (const float*)at<float>(ws, L.item), B, invB, ditem, du, acc);
+    LAUNCH_CHECK(h, "loss_bwd");
+  }
+  const size_t sm_leaf = agg_bwd_smem<D, true>(K, nr), sm_in = agg_bwd_smem<D, false>(K, nr);
+  if ((rc = set_smem(agg_bwd_kernel<D, true>, sm_leaf))) return rc;
+  if ((rc = set_smem(agg_bwd_kernel<D, false>, sm_in))) return rc;
+  const float* gx_next[MAX_L] = {nullptr};                   // gradient of X[n + 1][lv] (n + 1 < M), per level
+  for (int n = M - 1; n >= 0; --n) {
+    // mix layer n backward on every level it maps
+    for (int lv = 0; lv <= q.mix_levels(n); ++lv) {
+      const float* dout = (n + 1 < M) ? gx_next[lv] : ditem;
+      const long rows = L.rows[lv];
+      GemmArgs gm = gemm_args();                             // DM[k] = dout . W_mix[n][k]^T, k = 0 .. Hm
+      gm.A = dout; gm.sa_m = D; gm.sa_k = 1; gm.bsA = 0;
+      gm.B = P.mix_w + (long)n * (Hm + 1) * D * D; gm.sb_k = 1; gm.sb_n = D; gm.bsB = (long)D * D;
+      gm.C = at<float>(ws, L.DM[n][lv]); gm.ldc = D; gm.bsC = rows * D;
+      gm.M = (int)rows; gm.N = D; gm.K = D; gm.nbatch = Hm + 1;
+      if ((rc = run_gemm(h, st, gm, "gemm_mix_bwd"))) return rc;
+      DwArgs a;                                              // dW_mix[n][k] += slot_k^T dout ; db_mix[n] += sum dout
+      memset(&a, 0, sizeof(a));
+      for (int k = 0; k <= Hm; ++k) {
+        a.A[k] = at<float>(ws, mix_slot(L, q, n, k, lv)); a.lda[k] = D;
+        a.dW[k] = G.mix_w + ((long)n * (Hm + 1) + k) * D * D;
+      }
+      a.G = dout; a.db = G.mix_b + (long)n * D; a.rows = rows;
+      if ((rc = launch_dw<D>(h, st, a, Hm + 1, "dw_mix"))) return rc;
+    }
+    // the block's aggregator iterations, reversed
+    for (int i = Hm - 1; i >= 0; --i) {
+      const int g = n * Hm + i;
+      for (int lv = 0; lv <= q.last_level(g); ++lv) {
+        const long rows_lv = L.rows[lv];
+        // gradient of V[g + 1][lv]: mix slot i + 1, and inside the block its own next step and its parent's children sum
+        const float* s_mix = lv <= q.mix_levels(n) ? at<float>(ws, L.DM[n][lv]) + (long)(i + 1) * rows_lv * D : nullptr;
+        const float* s_self = (i + 1 < Hm && lv <= q.last_level(g + 1)) ? at<float>(ws, L.DS[g + 1][lv]) : nullptr;
+        const float* s_par = (i + 1 < Hm && lv >= 1) ? at<float>(ws, L.DC[g + 1][lv]) : nullptr;
+        const float* gsum;
+        if ((rc = sum_grads(h, st, s_mix, s_self, s_par, rows_lv * D, at<float>(ws, L.GV[g + 1][lv]), &gsum))) return rc;
+        AggBwdArgs a;
+        memset(&a, 0, sizeof(a));
+        long rows[MAX_LV];
+        AggBwdLevel& t = a.lv[0];
+        const bool leaf = (g == 0 && lv == Lt - 1);
+        t.ent = at<int32_t>(ws, L.ent[lv]);
+        t.V = at<float>(ws, L.V[g + 1][lv]); t.Y = at<float>(ws, L.Y[g][lv]);
+        t.g1 = gsum; t.g2 = nullptr;
+        t.dself = at<float>(ws, L.DS[g][lv]);
+        t.rows = rows[0] = rows_lv; t.rpp = (int)(rows_lv / B); t.rpp_magic = div_magic(t.rpp);
+        t.stream = stream_level(h, rows_lv, D);
+        t.leaf = leaf ? 1 : 0;
+        if (leaf) {
+          t.SU = at<float>(ws, L.SU);
+        } else {
+          t.child = at<float>(ws, mix_in(L, q, g, lv + 1));
+          t.dchild = at<float>(ws, L.DC[g][lv + 1]);
+        }
+        a.adj = h->adj; a.s = at<float>(ws, L.s) + (long)g * nr;
+        a.WaT = wT + (long)g * D * D;
+        a.dWa = G.agg_w + (long)g * D * D; a.dba = G.agg_b + (long)g * D;
+        a.ds = at<float>(ws, L.ds) + (long)g * nr;
+        a.K = K; a.n_rel = nr;
+        if (leaf) {
+          a.E = h->etab; a.WtT = wT + (long)(Lt + Lt) * D * D;
+          a.dWt = G.transfer_w + (long)Lt * D * D; a.dbt = G.transfer_b + (long)Lt * D;
+          a.dE = h->gtab; a.du = du_kg; a.u = u_kg;
+          const int grid = make_tile_list(a.tl, rows, 1, C::R, h->sm_count * resident_ctas(h, agg_bwd_kernel<D, true>, C::NT, sm_leaf),
+                                          h->d_sched + 2);
+          MVIN_LAUNCH((agg_bwd_kernel<D, true>), grid, C::NT, sm_leaf, st, a);
+        } else {
+          const int grid = make_tile_list(a.tl, rows, 1, C::R, h->sm_count * resident_ctas(h, agg_bwd_kernel<D, false>, C::NT, sm_in),
+                                          h->d_sched + 2);
+          MVIN_LAUNCH((agg_bwd_kernel<D, false>), grid, C::NT, sm_in, st, a);
+        }
+        LAUNCH_CHECK(h, "agg_bwd_mix");
+      }
+    }
+    // gradient of the block's inputs: mix slot 0, the first iteration's own step and its parents' children sums
+    const int g0 = n * Hm;
+    const int n_in = n == 0 ? Lt - 1 : Lt - g0;              // deepest input level that is a row buffer
+    for (int lv = 0; lv <= n_in; ++lv) {
+      const long rows_lv = L.rows[lv];
+      const float* s_mix = lv <= q.mix_levels(n) ? at<float>(ws, L.DM[n][lv]) : nullptr;
+      const float* s_self = lv <= q.last_level(g0) ? at<float>(ws, L.DS[g0][lv]) : nullptr;
+      const float* s_par = lv >= 1 ? at<float>(ws, L.DC[g0][lv]) : nullptr;
+      float* out = n == 0 ? at<float>(ws, L.GT[lv]) : at<float>(ws, L.GX[n][lv]);
+      if ((rc = sum_grads(h, st, s_mix, s_self, s_par, rows_lv * D, out, &gx_next[lv]))) return rc;
+    }
+  }
+  // user-oriented transform backward, levels 0 .. Lt-1 (gx_next = gradient of T[lv])
+  {
+    const size_t sm = transform_bwd_smem<D>();
+    if ((rc = set_smem(transform_bwd_kernel<D>, sm))) return rc;
+    for (int lv = 0; lv < Lt; ++lv) {
+      TransformArgs a;
+      memset(&a, 0, sizeof(a));
+      long rows[MAX_LV];
+      TransformLevel& t = a.lv[0];
+      t.ent = at<int32_t>(ws, L.ent[lv]);
+      t.W = wT + (long)(Lt + lv) * D * D;
+      t.g1 = gx_next[lv]; t.g2 = nullptr;
+      t.dW = G.transfer_w + (long)lv * D * D; t.db = G.transfer_b + (long)lv * D;
+      t.rows = rows[0] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
+      t.stream = stream_level(h, L.rows[lv], D);
+      a.nlev = 1; a.E = h->etab; a.u = u_kg; a.dE = h->gtab; a.du = du_kg;
+      const int grid = partition_grid(rows, 1, C::R, h->sm_count * resident_ctas(h, transform_bwd_kernel<D>, C::NT, sm), a.cta_end);
+      MVIN_LAUNCH((transform_bwd_kernel<D>), grid, C::NT, sm, st, a);
+      LAUNCH_CHECK(h, "transform_bwd");
+    }
+  }
+  MVIN_LAUNCH((rel_scores_bwd_kernel), Lt, 128, 0, st, P.relation_emb, P.agg_urh_w, (const float*)at<float>(ws, L.ds), nr, D,
+              G.relation_emb, G.agg_urh_w);
+  LAUNCH_CHECK(h, "rel_scores_bwd");
+  if (du_user) {
+    const long n = (long)B * C::LPR;
+    MVIN_LAUNCH((scatter_rows_kernel<D>), (unsigned)((n + 255) / 256), 256, 0, st, du_user, (const int32_t*)at<int32_t>(ws, L.user32), B,
+                GTab{G.user_emb, nullptr, 0, 0});
+    LAUNCH_CHECK(h, "scatter_du_user");
+  }
+  if ((rc = user_side_backward<D>(h, par, du_mlp, B, ws, st))) return rc;
+  MVIN_LAUNCH((finalize_loss_kernel), 1, 32, 0, st, acc, c.l2_weight, c.l2_agg_weight, losses_out);
   LAUNCH_CHECK(h, "finalize_loss");
   return MVIN_OK;
 }

@@ -169,13 +169,18 @@ class MVIN(object):
 
     # ------------------------------------------------------------------ model.py:69-122, aggregators.py:83-93
     def param_shapes(self) -> Dict[str, tuple]:
-        d, H, p = self.dim, self.h_hop, self.p_hop
+        """Field shapes of include/mvin_b200.h `mvin_params_t`.  With M = n_mix_hop mix blocks of h_hop iterations there
+        are L = h_hop M aggregators (aggregator (i, n) of model.py:290 at index n h_hop + i), L + 1 transfer matrices and
+        M mix layers (stacked on a leading axis when M > 1)."""
+        d, H, M, p = self.dim, self.h_hop, self.n_mix_hop, self.p_hop
+        L = H * M
         n_ent_rows = self.n_entity if self.n_shards == 1 else self.n_local_rows
+        mix_w, mix_b = (((H + 1) * d, d), (d,)) if M == 1 else ((M, (H + 1) * d, d), (M, d))
         return {"user_emb": (self.n_user, d), "entity_emb": (n_ent_rows, d), "relation_emb": (self.n_relation, d),
-                "relation_kge": (self.n_relation, d, d), "mix_w": ((H + 1) * d, d), "mix_b": (d,),
-                "user_mlp_w": ((p + 1) * d, d), "user_mlp_b": (d,), "transfer_w": (H + 1, d, d),
-                "transfer_b": (H + 1, d), "h_item_w": (2 * d,), "h_item_b": (1,), "agg_w": (H, d, d),
-                "agg_b": (H, d), "agg_urh_w": (H, 3 * d), "agg_urh_b": (H,)}
+                "relation_kge": (self.n_relation, d, d), "mix_w": mix_w, "mix_b": mix_b,
+                "user_mlp_w": ((p + 1) * d, d), "user_mlp_b": (d,), "transfer_w": (L + 1, d, d),
+                "transfer_b": (L + 1, d), "h_item_w": (2 * d,), "h_item_b": (1,), "agg_w": (L, d, d),
+                "agg_b": (L, d), "agg_urh_w": (L, 3 * d), "agg_urh_b": (L,)}
 
     @staticmethod
     def _xavier(shape, gen, fan=None):
@@ -220,6 +225,8 @@ class MVIN(object):
                 host[name] = torch.stack([self._xavier((3 * d,), gen, fan=(3 * d, 1)) for _ in range(shape[0])])
             elif name == "h_item_w":                               # [2d, 1]
                 host[name] = self._xavier((2 * d,), gen, fan=(2 * d, 1))
+            elif name in ("mix_w", "mix_b") and self.n_mix_hop > 1:   # one [(H+1) d, d] layer / [d] bias per mix block
+                host[name] = torch.stack([self._xavier(shape[1:], gen) for _ in range(shape[0])])
             else:
                 host[name] = self._xavier(shape, gen)
         self.params = {k: v.to(self.device).contiguous() for k, v in host.items()}
@@ -633,7 +640,7 @@ class MVIN(object):
         import torch.distributed as dist
         if losses is not None:
             self.loss_slot.copy_(torch.as_tensor(losses, dtype=torch.float32))
-        if self.flags & 0x04:
+        if self._user_grad_is_l2_only():
             # --ablation all: the user table only carries its dense L2 term (identical on every rank)
             dist.all_reduce(self.grad_flat[self._user_grad_end:], group=self.group)   # one bucket, in place
             self.grads["user_emb"].mul_(float(self.n_shards))
@@ -648,7 +655,7 @@ class MVIN(object):
         set_batch_scale(global batch, 1 / world) the result equals the single-device gradient on the concatenated
         batch (tests/test_sharding_gloo.py checks the protocol)."""
         import torch.distributed as dist
-        if self.flags & 0x04:
+        if self._user_grad_is_l2_only():
             # --ablation all: nothing but the dense L2 term reaches the user table (SURVEY.md Appendix B), and that term is
             # the same on every rank (l2 x U / world under set_batch_scale), so its sum is a local multiply -- the bucket
             # that crosses NVLink shrinks by the user table (C4: 48 -> 30 MB)
@@ -658,6 +665,10 @@ class MVIN(object):
                 self.grads["user_emb"].mul_(float(world))
         else:
             dist.all_reduce(self.grad_flat, group=group)
+
+    def _user_grad_is_l2_only(self) -> bool:
+        """U[user] is read only when User_orient_kg_eh = 0 (model.py:152-156) or HO_only = 1 (model.py:146-150)."""
+        return bool(self.flags & 0x04) and not (self.flags & 0x40)
 
     def set_batch_scale(self, global_batch: int, dense_l2_scale: float):
         check(self.lib.mvin_set_batch_scale(self._handle, int(global_batch), float(dense_l2_scale)), "mvin_set_batch_scale")
@@ -738,6 +749,9 @@ class MVIN(object):
         return [t.cpu().numpy() for t in ents], [t.cpu().numpy() for t in rels]
 
     def eval_case_study(self, sess, feed_dict):
+        if self.flags & 0x20:
+            # the reference never creates importance_list_0 / _1 under PS_only (model.py:142-144): its eval_case_study raises
+            raise AttributeError("PS_only has no aggregators: importance_list_0 does not exist (model.py:142-144)")
         users = np.asarray(feed_dict[self.user_indices])
         items, labels, _, _ = self._scores(feed_dict)
         B, K = items.shape[0], self.n_neighbor
@@ -786,20 +800,26 @@ class MVIN(object):
     # ------------------------------------------------------------------ test / interop helpers
     # oracle (reference attribute) name -> (field, index or None)
     def _name_map(self):
-        H = self.h_hop
+        H, M = self.h_hop, self.n_mix_hop
         mp = {"user_emb_matrix": ("user_emb", None), "entity_emb_matrix": ("entity_emb", None),
               "relation_emb_matrix": ("relation_emb", None), "relation_emb_KGE_matrix": ("relation_kge", None),
-              "enti_transfer_matrix_0": ("mix_w", None), "enti_transfer_bias_0": ("mix_b", None),
               "user_mlp_matrix": ("user_mlp_w", None), "user_mlp_bias": ("user_mlp_b", None),
               "h_emb_item_mlp_matrix": ("h_item_w", None), "h_emb_item_mlp_bias": ("h_item_b", None)}
-        for e in range(H + 1):
+        for n in range(M):                                         # model.py:91-98
+            mp[f"enti_transfer_matrix_{n}"] = ("mix_w", None if M == 1 else n)
+            mp[f"enti_transfer_bias_{n}"] = ("mix_b", None if M == 1 else n)
+        for e in range(H * M + 1):                                 # model.py:107-116
             mp[f"transfer_agg_matrix_{e}"] = ("transfer_w", e)
             mp[f"transfer_agg_bias_{e}"] = ("transfer_b", e)
-        for i in range(H):
-            mp[f"agg_{i}_0_weights"] = ("agg_w", i)
-            mp[f"agg_{i}_0_bias"] = ("agg_b", i)
-            mp[f"agg_{i}_0_urh_weights"] = ("agg_urh_w", i)
-            mp[f"agg_{i}_0_urh_bias"] = ("agg_urh_b", i)
+        if self.flags & 0x20:                                      # PS_only: the reference creates no aggregators
+            return mp
+        for n in range(M):                                         # created n outer, i inner (model.py:286-291)
+            for i in range(H):
+                g = n * H + i
+                mp[f"agg_{i}_{n}_weights"] = ("agg_w", g)
+                mp[f"agg_{i}_{n}_bias"] = ("agg_b", g)
+                mp[f"agg_{i}_{n}_urh_weights"] = ("agg_urh_w", g)
+                mp[f"agg_{i}_{n}_urh_bias"] = ("agg_urh_b", g)
         return mp
 
     def load_named_parameters(self, named: Dict[str, np.ndarray]):

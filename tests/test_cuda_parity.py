@@ -264,8 +264,8 @@ def test_partial_batch_and_errors():
     with pytest.raises(ValueError):
         model.get_raw_scores(big)                                   # B is static in the reference graph
     with pytest.raises(MvinError):
-        MVIN(make_args(n_mix_hop=2), prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"],
-             prob["adj_relation"])
+        MVIN(make_args(n_mix_hop=3), prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"],
+             prob["adj_relation"])                                      # depth h_hop * n_mix_hop = 6 > 4
     with pytest.raises(MvinError):
         MVIN(make_args(User_orient=0), prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"],
              prob["adj_relation"])
