@@ -68,24 +68,26 @@ typedef struct mvin_config {
 
 /* The parameter set of MVIN._build_model (model.py:72-122) + the aggregators (aggregators.py:83-93), fp32,
  * device pointers.  The same struct describes a gradient set (same shapes) and Adam moment sets.
- * With n_mix_hop = 1: L = h_hop. */
+ * H = h_hop iterations per mix block, M = n_mix_hop mix blocks, L = H M = depth of the neighbourhood = number of
+ * aggregators (M = 1: L = H).  Aggregator (i, n) of model.py:290 (iteration i of block n) sits at index n H + i. */
 typedef struct mvin_params {
   float* user_emb;      /* [n_user, d]            user_emb_matrix_STWS        model.py:72-74   */
   float* entity_emb;    /* [n_entity, d]          entity_emb_matrix_STWS      model.py:76-78   */
   float* relation_emb;  /* [n_relation, d]        relation_emb_matrix_STWS    model.py:80-82   */
   float* relation_kge;  /* [n_relation, d, d]     relation_emb_KGE_matrix_STWS model.py:84-86  */
-  float* mix_w;         /* [(H+1) d, d]           enti_transfer_matrix_list[0] model.py:91-98  */
-  float* mix_b;         /* [d]                    enti_transfer_bias_list[0]                   */
+  float* mix_w;         /* [M, (H+1) d, d]        enti_transfer_matrix_list[n] model.py:91-98  */
+  float* mix_b;         /* [M, d]                 enti_transfer_bias_list[n]                   */
   float* user_mlp_w;    /* [(p+1) d, d]           user_mlp_matrix             model.py:100-104 */
   float* user_mlp_b;    /* [d]                    user_mlp_bias               model.py:105-106 */
   float* transfer_w;    /* [L+1, d, d]            transfer_matrix_list[e]     model.py:107-116 */
   float* transfer_b;    /* [L+1, d]               transfer_matrix_bias[e]                      */
   float* h_item_w;      /* [2 d]                  h_emb_item_mlp_matrix       model.py:118-120 */
   float* h_item_b;      /* [1]                    h_emb_item_mlp_bias         model.py:121-122 */
-  float* agg_w;         /* [H, d, d]              aggregator i: weights       aggregators.py:83-85 */
-  float* agg_b;         /* [H, d]                 aggregator i: bias          aggregators.py:86-87 */
-  float* agg_urh_w;     /* [H, 3 d]               aggregator i: urh_weights   aggregators.py:89-91 */
-  float* agg_urh_b;     /* [H]                    aggregator i: urh_bias (created, never used) :92-93 */
+  float* agg_w;         /* [L, d, d]              aggregator: weights         aggregators.py:83-85 */
+  float* agg_b;         /* [L, d]                 aggregator: bias            aggregators.py:86-87 */
+  float* agg_urh_w;     /* [L, 3 d]               aggregator: urh_weights     aggregators.py:89-91 */
+  float* agg_urh_b;     /* [L]                    aggregator: urh_bias (created, never used) :92-93;
+                           under PS_only the reference creates no aggregators: the four fields stay untouched */
 } mvin_params_t;
 
 int mvin_abi_version(void);

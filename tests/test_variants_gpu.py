@@ -12,11 +12,7 @@ from tests.helpers import rel_err
 from tests.synth import feed_dict, make_args, make_problem
 from tests.test_cuda_parity import GRAD_TOL, SCORE_TOL, _assert_grads, _model_from_golden
 
-import os
-
-# until the variants' first run on a B200 is on record (profiles/), they are opt-in: MVIN_B200_TEST_VARIANTS=1
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MVIN_B200_TEST_VARIANTS") != "1", reason="set MVIN_B200_TEST_VARIANTS=1")]
+pytestmark = pytest.mark.gpu
 
 VARIANT_GOLDEN = ["h2_m1_p2_ps_only", "h2_m1_p2_ho_only", "h2_m1_p2_ho_only_kg_eh", "h1_m2_p1", "h2_m2_p2"]
 
