@@ -56,15 +56,21 @@ typedef struct mvin_config {
 } mvin_config_t;
 
 #define MVIN_FLAGS_ALL 0x1f
-#define MVIN_FLAG_KG_EH 0x04      /* bit2: User_orient_kg_eh */
-#define MVIN_FLAG_PS_ONLY 0x20    /* bit5: PS_only (model.py:142-144): score = user_o . E[item], no KG side */
-#define MVIN_FLAG_HO_ONLY 0x40    /* bit6: HO_only (model.py:146-150): score = U[user] . item */
-#define MVIN_FLAGS_NO_KG_EH_UO 0x1b /* --ablation no_kg_eh_uo (parameter_ablation.py:22-30): the KG side is oriented by U[user] */
-#define MVIN_FLAGS_PS_ONLY 0x3f          /* --ablation ps_only          (parameter_ablation.py) */
+#define MVIN_FLAG_USER_ORIENT 0x01      /* bit0: User_orient (model.py:270-283); off: the entity vectors are used untransformed */
+#define MVIN_FLAG_USER_ORIENT_RELA 0x02 /* bit1: User_orient_rela (aggregators.py:98-152); off: plain mean over the neighbours */
+#define MVIN_FLAG_KG_EH 0x04            /* bit2: User_orient_kg_eh (model.py:152-156); off: the KG side is oriented by U[user] */
+#define MVIN_FLAG_PS_O_FT 0x08          /* bit3: PS_O_ft (model.py:204-206); off: no user_h_set, user_mlp_matrix is [p d, d] */
+#define MVIN_FLAG_WIDE_DEEP 0x10        /* bit4: wide_deep; must be set (the other branch, model.py:327-376, is broken upstream) */
+#define MVIN_FLAG_PS_ONLY 0x20          /* bit5: PS_only (model.py:142-144): score = user_o . E[item], no KG side */
+#define MVIN_FLAG_HO_ONLY 0x40          /* bit6: HO_only (model.py:146-150): score = U[user] . item */
+#define MVIN_FLAGS_NO_KG_EH_UO 0x1b     /* --ablation no_kg_eh_uo (parameter_ablation.py:22-30) */
+#define MVIN_FLAGS_PS_ONLY 0x3f          /* --ablation ps_only */
 #define MVIN_FLAGS_HO_ONLY 0x5b          /* --ablation ho_only          (User_orient_kg_eh = 0) */
 #define MVIN_FLAGS_HO_ONLY_UO_KG_EH 0x5f /* --ablation ho_only_uo_kg_eh (User_orient_kg_eh = 1) */
-/* Supported: bits 0, 1, 3, 4 set (User_orient, User_orient_rela, PS_O_ft, wide_deep), bit 2 either way, at most one of
- * bits 5 / 6.  Everything else -> MVIN_ERR_UNSUPPORTED from mvin_create. */
+/* Supported: every setting of parameter_ablation.py with wide_deep = 1 -- bits 0..3 either way, bit 4 set, at most one of
+ * bits 5 / 6; PS_O_ft = 0 needs p_hop >= 1.  Everything else -> MVIN_ERR_UNSUPPORTED from mvin_create.  The tuned kernels
+ * (entity tables, entity groups, tcgen05) serve User_orient = User_orient_rela = 1 with one mix block; the other settings
+ * run the generic per-level step (steps.cuh). */
 
 /* The parameter set of MVIN._build_model (model.py:72-122) + the aggregators (aggregators.py:83-93), fp32,
  * device pointers.  The same struct describes a gradient set (same shapes) and Adam moment sets.
@@ -77,7 +83,7 @@ typedef struct mvin_params {
   float* relation_kge;  /* [n_relation, d, d]     relation_emb_KGE_matrix_STWS model.py:84-86  */
   float* mix_w;         /* [M, (H+1) d, d]        enti_transfer_matrix_list[n] model.py:91-98  */
   float* mix_b;         /* [M, d]                 enti_transfer_bias_list[n]                   */
-  float* user_mlp_w;    /* [(p+1) d, d]           user_mlp_matrix             model.py:100-104 */
+  float* user_mlp_w;    /* [(p+1) d, d]           user_mlp_matrix ([p d, d] when PS_O_ft = 0) model.py:100-104 */
   float* user_mlp_b;    /* [d]                    user_mlp_bias               model.py:105-106 */
   float* transfer_w;    /* [L+1, d, d]            transfer_matrix_list[e]     model.py:107-116 */
   float* transfer_b;    /* [L+1, d]               transfer_matrix_bias[e]                      */

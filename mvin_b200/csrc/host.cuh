@@ -124,6 +124,11 @@ struct Layout {
   // level h (the input of block n >= 1); DM[n][h] = [h_hop + 1][rows(h), D] gradients of the h_hop + 1 inputs of mix block n
   // at level h; GV / GX / GT = summed gradients of V[j][h], X[n][h], T[h] where more than one consumer contributes
   size_t X[MAX_L][MAX_L], GX[MAX_L][MAX_L], DM[MAX_L][MAX_L], GV[MAX_L + 1][MAX_L], GT[MAX_L];
+  // User_orient = 0 (generic step): the transform kernels run with the identity, a zero bias and a zero user vector, their
+  // parameter / user gradients land in scratch:  eye [D, D], zb [D], zu [B, D], sdW [D, D], sdb [D], sdu [B, D]
+  size_t eye, zb, zu, sdW, sdb, sdu;
+  // PS_O_ft = 0: user_mlp_matrix [p D, D] padded with a zero block for the absent user_h_set slot, and its gradient
+  size_t Wpad, dWpad;
   size_t total;
   long rows[MAX_L + 1];
 };
@@ -235,13 +240,19 @@ struct Par {
   void wait_mid() const { if (on) cudaStreamWaitEvent(main, h->ev_mid, 0); }
 };
 
+// configurations served by the generic per-level step (steps.cuh: forward_mix_impl / backward_mix_impl) instead of the
+// tuned single-block one: several mix blocks, no user-oriented transform, no relation attention
+inline bool generic_step(const mvin_config_t& c) {
+  return c.n_mix_hop > 1 || !(c.flags & MVIN_FLAG_USER_ORIENT) || !(c.flags & MVIN_FLAG_USER_ORIENT_RELA);
+}
+
 inline bool has_agg(int H, int i, int h) { return i < H && h < H - i; }          // aggregator step (i, h) exists
 inline bool has_V(int H, int j, int h) { return j == 0 ? h < H : h <= H - j; }   // buffer V[j][h] exists
 
 // Entity mode of the leaf level (level.cuh, leaf_entity_kernel) pays off when the depth-(L-1) nodes of a batch
 // re-use entities: enabled when there are at least n_entity / 4 of them and the two per-entity buffers are small.
 inline bool use_entity_leaf(const mvin_config_t& c, long B, int n_shards, int mode) {
-  if (n_shards != 1 || mode == 0 || c.n_mix_hop != 1 || (c.flags & MVIN_FLAG_PS_ONLY)) return false;
+  if (n_shards != 1 || mode == 0 || generic_step(c) || (c.flags & MVIN_FLAG_PS_ONLY)) return false;
   if (mode == 1) return true;
   long rows = B;
   for (int h = 1; h < c.h_hop; ++h) rows *= c.neighbor_sample_size;
@@ -252,7 +263,7 @@ inline bool use_entity_leaf(const mvin_config_t& c, long B, int n_shards, int mo
 // buffers -- by per-entity tables.  Same applicability as the entity mode of the leaf level (one shard, the batch re-uses
 // entities); MVIN_B200_TABLE=0 / 1 forces it off / on, an explicit MVIN_B200_ENTITY_LEAF selects the row kernels.
 inline bool use_table(const mvin_config_t& c, long B, int n_shards, int table_mode, int entity_leaf_mode) {
-  if (n_shards != 1 || table_mode == 0 || c.n_mix_hop != 1 || (c.flags & MVIN_FLAG_PS_ONLY)) return false;
+  if (n_shards != 1 || table_mode == 0 || generic_step(c) || (c.flags & MVIN_FLAG_PS_ONLY)) return false;
   if ((long)c.n_entity * c.dim * 4 * (2 * c.h_hop + 2) > (8L << 30)) return false;
   if (table_mode == 1) return true;
   // automatic: when the deepest level has at least one row per entity of the graph (rows per entity at C3: 2.5, C4: 148;
@@ -353,7 +364,15 @@ inline Layout make_layout(const mvin_config_t& c, long B, bool entity_leaf, bool
     L.stamp = take(sizeof(int32_t) * (size_t)c.n_entity);
     L.Se = take(f * (size_t)c.n_entity * D);
   }
-  if (c.n_mix_hop > 1) {
+  if (!(c.flags & MVIN_FLAG_PS_O_FT)) {
+    L.Wpad = take(f * (p + 1) * D * D);
+    L.dWpad = take(f * (p + 1) * D * D);
+  }
+  if (generic_step(c) && !(c.flags & MVIN_FLAG_USER_ORIENT)) {
+    L.eye = take(f * D * D); L.zb = take(f * D); L.zu = take(f * B * D);
+    L.sdW = take(f * D * D); L.sdb = take(f * D); L.sdu = take(f * B * D);
+  }
+  if (generic_step(c)) {
     const int Hm = c.h_hop, M = c.n_mix_hop;
     for (int n = 0; n < M; ++n)
       for (int h = 0; h <= H - (long)n * Hm && h < MAX_L; ++h) {

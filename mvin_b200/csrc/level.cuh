@@ -293,7 +293,8 @@ MVIN_DEV void load_weight(float* __restrict__ Ws, const float* __restrict__ Wg, 
 // user / self thirds of the logit cancelled).  Each warp handles its RPW rows of the tile, CH
 // of them at a time with all their adjacency loads issued before the first softmax; lane l handles k = l and
 // k = l + 32.  Output: nb_s[r][k] = (p_k, id_k) and, for the backward, rel_s[r][k].
-template <int D, bool WITH_REL>
+// UNIFORM (User_orient_rela = 0, aggregators.py:148-152): no attention, every neighbour weighs 1 / K.
+template <int D, bool WITH_REL, bool UNIFORM = false>
 MVIN_DEV void stage_tile(const int32_t* __restrict__ ent, const int32_t* __restrict__ adj,
                          const float* __restrict__ s_s, long row0, long rows, int K, int KP, int2* __restrict__ nb_s,
                          uint16_t* __restrict__ rel_s, int warp, int lane) {
@@ -322,12 +323,13 @@ MVIN_DEV void stage_tile(const int32_t* __restrict__ ent, const int32_t* __restr
       const float e0 = lane < K ? expf(l0 - mx) : 0.f;
       const float e1 = lane + 32 < K ? expf(l1 - mx) : 0.f;
       const float inv = 1.f / warp_sum(e0 + e1);
+      const float p0 = UNIFORM ? 1.f / (float)K : e0 * inv, p1 = UNIFORM ? 1.f / (float)K : e1 * inv;
       if (lane < K) {
-        nb_s[r * KP + lane] = make_int2(__float_as_int(e0 * inv), id0[j]);
+        nb_s[r * KP + lane] = make_int2(__float_as_int(p0), id0[j]);
         if (WITH_REL) rel_s[r * KP + lane] = (uint16_t)rl0[j];
       }
       if (lane + 32 < K) {
-        nb_s[r * KP + lane + 32] = make_int2(__float_as_int(e1 * inv), id1[j]);
+        nb_s[r * KP + lane + 32] = make_int2(__float_as_int(p1), id1[j]);
         if (WITH_REL) rel_s[r * KP + lane + 32] = (uint16_t)rl1[j];
       }
     }
@@ -620,7 +622,8 @@ struct AggSmem {
   }
 };
 
-template <int D, bool HAS_LEAF>
+// UNIFORM (User_orient_rela = 0): agg = mean_k(child_k), the weights 1 / K replace the attention AND the mean's 1 / K
+template <int D, bool HAS_LEAF, bool UNIFORM = false>
 __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
   pdl_enter();
   using C = TC<D>;
@@ -642,7 +645,7 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
   const float4 ba = ldg4(a.ba + tx * 4);
   float4 bt = f4zero();
   if (HAS_LEAF) bt = ldg4(a.bt + tx * 4);
-  const float invK = 1.f / (float)K;
+  const float invK = UNIFORM ? 1.f : 1.f / (float)K;
   RowRing<D> ring;
   const bool use_ring = RowRing<D>::ENABLED && a.ring;
   if (use_ring)
@@ -663,7 +666,7 @@ __global__ void __launch_bounds__(TC<D>::NT) agg_fwd_kernel(AggArgs a) {
     // ---- stage phase: (p_k, id_k) of every row of the tile ----
     const bool x_mode = leaf && a.Xpart != nullptr;
     if (!ent_mode && !x_mode && !L.preagg) {
-      stage_tile<D, false>(L.ent, a.adj, s_s, row0, L.rows, K, KP, nb_s, nullptr, warp, lane);
+      stage_tile<D, false, UNIFORM>(L.ent, a.adj, s_s, row0, L.rows, K, KP, nb_s, nullptr, warp, lane);
       __syncthreads();
     }
     // ---- neighbour phase: thread-mapped ----
@@ -867,7 +870,8 @@ struct AggBwdArgs {
 
 // RING: table-gather levels stage their rows through the bulk-copy ring (RowRing; d <= 64).  The ring's shared memory
 // limits the SM to two CTAs, so that instantiation is compiled for two (128 registers instead of 85).
-template <int D, bool HAS_LEAF, bool RING = false>
+// UNIFORM (User_orient_rela = 0): as in agg_fwd_kernel; the relation scores get no gradient.
+template <int D, bool HAS_LEAF, bool RING = false, bool UNIFORM = false>
 __global__ void __launch_bounds__(TC<D>::NT, (RING ? 2 : D <= 64 ? 3 : 1)) agg_bwd_kernel(AggBwdArgs a) {
   pdl_enter();
   using C = TC<D>;
@@ -892,7 +896,7 @@ __global__ void __launch_bounds__(TC<D>::NT, (RING ? 2 : D <= 64 ? 3 : 1)) agg_b
   if (HAS_LEAF) load_weight<D>(Wt_s, a.WtT, tid);
   for (int i = tid; i < a.n_rel; i += C::NT) s_s[i] = a.s[i];
   for (int i = tid; i < NWH * a.n_rel; i += C::NT) ds_s[i] = 0.f;
-  const float invK = 1.f / (float)K;
+  const float invK = UNIFORM ? 1.f : 1.f / (float)K;
   float* ds_w = ds_s + (NWH > 1 ? warp : 0) * a.n_rel;
   float dwa[C::DWN][4], dwt[HAS_LEAF ? C::DWN : 1][4];
 #pragma unroll
@@ -922,7 +926,7 @@ __global__ void __launch_bounds__(TC<D>::NT, (RING ? 2 : D <= 64 ? 3 : 1)) agg_b
     // ---- stage phase (its loads overlap the tile loads below) ----
     const bool x_mode = leaf && a.Xgsu != nullptr;
     const bool nbr_phase = !ent_mode && !L.defer && !x_mode;
-    if (nbr_phase) stage_tile<D, true>(L.ent, a.adj, s_s, row0, L.rows, K, KP, nb_s, rel_s, warp, lane);
+    if (nbr_phase) stage_tile<D, true, UNIFORM>(L.ent, a.adj, s_s, row0, L.rows, K, KP, nb_s, rel_s, warp, lane);
 #pragma unroll
     for (int i = 0; i < C::TM; ++i) {
       const int r = ty * C::TM + i;
@@ -1064,7 +1068,7 @@ __global__ void __launch_bounds__(TC<D>::NT, (RING ? 2 : D <= 64 ? 3 : 1)) agg_b
         }
 #pragma unroll
         for (int o = C::W / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL_MASK, dot, o);
-        if (valid && tx < C::W) {
+        if (!UNIFORM && valid && tx < C::W) {
 #pragma unroll
           for (int c = 0; c < C::NKW; ++c) {
             const int k = c * C::W + tx;

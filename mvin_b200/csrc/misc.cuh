@@ -143,6 +143,13 @@ static __global__ void sum_rows_kernel(const float* a, const float* b, const flo
   }
 }
 
+// ---- W = identity [D, D]   (User_orient = 0: the transform kernels run with it, steps.cuh) --------------------------
+static __global__ void eye_kernel(float* __restrict__ W, int D) {
+  pdl_enter();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < D * D) W[i] = (i / D == i % D) ? 1.f : 0.f;
+}
+
 // ---- relation scores s[i][r] = Rel[r] . urh_weights_i[D:2D]  (aggregators.py:130-133, relation third) --
 static __global__ void rel_scores_kernel(const float* __restrict__ Rel, const float* __restrict__ urh, int n_rel, int D,
                                   int H, float* __restrict__ s) {

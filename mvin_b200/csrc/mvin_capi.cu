@@ -33,12 +33,13 @@ MVIN_EXTERN_D(8) MVIN_EXTERN_D(16) MVIN_EXTERN_D(32) MVIN_EXTERN_D(64) MVIN_EXTE
 #undef MVIN_EXTERN_D
 
 int check_supported(const mvin_config_t* c) {
-  const int variant = MVIN_FLAG_KG_EH | MVIN_FLAG_PS_ONLY | MVIN_FLAG_HO_ONLY;
-  if ((c->flags | variant) != (MVIN_FLAGS_ALL | variant) || (c->flags & MVIN_FLAGS_NO_KG_EH_UO) != MVIN_FLAGS_NO_KG_EH_UO ||
+  if (!(c->flags & MVIN_FLAG_WIDE_DEEP) || (c->flags & ~0x7f) ||
       ((c->flags & MVIN_FLAG_PS_ONLY) && (c->flags & MVIN_FLAG_HO_ONLY)))
     return fail(MVIN_ERR_UNSUPPORTED,
-                "supported --ablation settings: all (0x1f), no_kg_eh_uo (0x1b), ps_only (0x3f), ho_only (0x5b), "
-                "ho_only_uo_kg_eh (0x5f); got flags 0x%x", c->flags);
+                "supported: the settings of parameter_ablation.py with wide_deep = 1 (flags bit 4) and at most one of "
+                "PS_only / HO_only; got flags 0x%x", c->flags);
+  if (!(c->flags & MVIN_FLAG_PS_O_FT) && c->p_hop < 1)
+    return fail(MVIN_ERR_UNSUPPORTED, "PS_O_ft = 0 needs p_hop >= 1 (the user MLP would have no input, model.py:232-236)");
   if (c->h_hop < 1 || c->n_mix_hop < 1) return fail(MVIN_ERR_UNSUPPORTED, "h_hop and n_mix_hop must be >= 1");
   if (c->n_mix_hop == 1 && c->h_hop > 3) return fail(MVIN_ERR_UNSUPPORTED, "h_hop must be in 1..3, got %d", c->h_hop);
   if (c->n_mix_hop > 1 && c->h_hop * c->n_mix_hop > MAX_L)
@@ -93,7 +94,7 @@ int host_step_overlap(mvin_handle_t h, int B, void* ws, cudaStream_t st) {
   h->pre_fork = false;
   if (!h->use_streams || h->prof_on || !h->has_grads) return MVIN_OK;
   // the PS_only / n_mix_hop > 1 variants run their step on one stream (steps.cuh: backward_ps_only, backward_mix_impl)
-  if ((h->cfg.flags & MVIN_FLAG_PS_ONLY) || h->cfg.n_mix_hop > 1) return MVIN_OK;
+  if ((h->cfg.flags & MVIN_FLAG_PS_ONLY) || generic_step(h->cfg)) return MVIN_OK;
   CUDA_TRY(cudaEventRecord(h->ev_item, st));
   h->pre_fork = true;
   CUDA_TRY(cudaStreamWaitEvent(h->side[1], h->ev_item, 0));
@@ -231,8 +232,8 @@ int mvin_bind_entity_shards(mvin_handle_t h, int32_t n_shards, const float* cons
   if (!h || !entity_shards || !grad_shards) return fail(MVIN_ERR_INVALID, "null argument");
   if (n_shards < 1 || n_shards > MAX_SHARDS || (n_shards & (n_shards - 1)))
     return fail(MVIN_ERR_INVALID, "n_shards must be a power of two in 1..%d, got %d", MAX_SHARDS, n_shards);
-  if (n_shards > 1 && ((h->cfg.flags & (MVIN_FLAG_PS_ONLY | MVIN_FLAG_HO_ONLY)) || h->cfg.n_mix_hop > 1))
-    return fail(MVIN_ERR_UNSUPPORTED, "row-sharded entity table: PS_only / HO_only / n_mix_hop > 1 are single-table variants");
+  if (n_shards > 1 && ((h->cfg.flags != MVIN_FLAGS_ALL && h->cfg.flags != MVIN_FLAGS_NO_KG_EH_UO) || h->cfg.n_mix_hop > 1))
+    return fail(MVIN_ERR_UNSUPPORTED, "row-sharded entity table: only --ablation all / no_kg_eh_uo with one mix block");
   int shift = 0;
   while ((1 << shift) < n_shards) ++shift;
   void* host[2 * MAX_SHARDS] = {nullptr};
@@ -439,7 +440,7 @@ int mvin_adam_step(mvin_handle_t h, const mvin_params_t* m, const mvin_params_t*
   SEG(relation_kge, nr * D * D);
   SEG(mix_w, M * (Hm + 1) * D * D);
   SEG(mix_b, M * D);
-  SEG(user_mlp_w, (p + 1) * D * D);
+  SEG(user_mlp_w, (p + ((c.flags & MVIN_FLAG_PS_O_FT) ? 1 : 0)) * D * D);
   SEG(user_mlp_b, D);
   SEG(transfer_w, (H + 1) * D * D);
   SEG(transfer_b, (H + 1) * D);

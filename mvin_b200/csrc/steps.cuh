@@ -144,6 +144,14 @@ int user_side_forward(mvin_handle_t h, const int64_t* item, const int32_t* mem_h
     memset(&a, 0, sizeof(a));
     a.E = h->etab; a.item = item; a.RK = P.relation_kge; a.w_hi = P.h_item_w;
     a.W_user = P.user_mlp_w; a.b_user = P.user_mlp_b;
+    if (!(c.flags & MVIN_FLAG_PS_O_FT)) {
+      // PS_O_ft = 0 (model.py:204-206, :232-236): user_h_set is not part of o_list and user_mlp_matrix is [p D, D].  The
+      // kernels keep their p + 1 slots; slot 0 meets a zero block of a padded copy of the weights
+      float* Wpad = at<float>(ws, L.Wpad);
+      CUDA_TRY(cudaMemsetAsync(Wpad, 0, sizeof(float) * D * D, st));
+      CUDA_TRY(cudaMemcpyAsync(Wpad + D * D, P.user_mlp_w, sizeof(float) * (size_t)p * D * D, cudaMemcpyDeviceToDevice, st));
+      a.W_user = Wpad;
+    }
     a.mem_h = mem_h; a.mem_r = mem_r; a.mem_t = mem_t;
     a.Vbuf = at<float>(ws, L.Vbuf); a.Q = at<float>(ws, L.Q); a.probs = at<float>(ws, L.probs);
     a.O = at<float>(ws, L.O); a.u = at<float>(ws, L.u);
@@ -177,7 +185,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
   const mvin_config_t& c = h->cfg;
   const int K = c.neighbor_sample_size, H = c.h_hop, p = c.p_hop, m = c.n_memory, nr = c.n_relation;
   if (c.flags & MVIN_FLAG_PS_ONLY) return forward_ps_only<D>(h, item, mem_h, mem_r, mem_t, B, scores, scores_norm, ws, st);
-  if (c.n_mix_hop > 1) return forward_mix_impl<D>(h, item, mem_h, mem_r, mem_t, B, scores, scores_norm, ws, st);
+  if (generic_step(c)) return forward_mix_impl<D>(h, item, mem_h, mem_r, mem_t, B, scores, scores_norm, ws, st);
   const Layout L = handle_layout(h, B);
   const mvin_params_t& P = h->P;
   int rc;
@@ -519,7 +527,7 @@ int backward_init(mvin_handle_t h, int B, void* ws, cudaStream_t st, cudaEvent_t
     add(P.relation_kge, G.relation_kge, (long)nr * D * D, 0.f, 0.f, 0);
     add(P.mix_w, G.mix_w, (long)M * (Hm + 1) * D * D, l2a, 1.f, 1);               // :400-401
     add(P.mix_b, G.mix_b, (long)M * D, l2a, 1.f, 1);
-    add(P.user_mlp_w, G.user_mlp_w, (long)(p + 1) * D * D, l2w, pm, 0);           // :404
+    add(P.user_mlp_w, G.user_mlp_w, (long)(p + ((c.flags & MVIN_FLAG_PS_O_FT) ? 1 : 0)) * D * D, l2w, pm, 0);   // :404
     add(P.user_mlp_b, G.user_mlp_b, D, l2w, pm, 0);
     // :405 regularises the LAST transfer matrix created (index H), :407-408 the matrices 0..h_hop: with n_mix_hop = 1 the
     // last one counts twice, with n_mix_hop > 1 the matrices h_hop+1 .. H-1 are not regularised at all
@@ -586,17 +594,27 @@ int user_side_backward(mvin_handle_t h, const Par& par, const float* du_mlp, int
   {
     DwArgs a;
     memset(&a, 0, sizeof(a));
+    const bool ft = (c.flags & MVIN_FLAG_PS_O_FT) != 0;   // PS_O_ft = 0: padded weights (user_side_forward), padded gradient
+    float* dW_user = ft ? G.user_mlp_w : at<float>(ws, L.dWpad);
     for (int s = 0; s <= p; ++s) {
-      a.A[s] = at<float>(ws, L.O) + (long)s * D; a.lda[s] = (long)(p + 1) * D; a.dW[s] = G.user_mlp_w + (long)s * D * D;
+      a.A[s] = at<float>(ws, L.O) + (long)s * D; a.lda[s] = (long)(p + 1) * D; a.dW[s] = dW_user + (long)s * D * D;
     }
     a.G = du_mlp; a.db = G.user_mlp_b; a.rows = B;
     par.fork(1);                                   // side stream 1: weight gradient of the user MLP
+    if (!ft) CUDA_TRY(cudaMemsetAsync(dW_user, 0, sizeof(float) * (size_t)(p + 1) * D * D, par.s(1)));
     if ((rc = launch_dw<D>(h, par.s(1), a, p + 1, "dw_user"))) return rc;
+    if (!ft) {                                     // the p real blocks join the L2 term already in the gradient buffer
+      cudaStream_t st = par.s(1);
+      const long n4 = (long)p * D * D / 4;
+      MVIN_LAUNCH((sum_rows_kernel), (unsigned)((n4 + 255) / 256), 256, 0, st, (const float*)G.user_mlp_w,
+                  (const float*)(dW_user + D * D), (const float*)nullptr, n4, G.user_mlp_w);
+      LAUNCH_CHECK(h, "dw_user_unpad");
+    }
     // dO = du . W_user^T as a batched GEMM (a per-warp matvec inside the ripple kernel re-reads W_user per warp and
     // measured slower: +9 us at C2, +78 us at C3)
     GemmArgs g = gemm_args();
     g.A = du_mlp; g.sa_m = D; g.sa_k = 1;
-    g.B = P.user_mlp_w; g.sb_k = 1; g.sb_n = D;
+    g.B = ft ? P.user_mlp_w : at<float>(ws, L.Wpad); g.sb_k = 1; g.sb_n = D;
     g.C = at<float>(ws, L.dO); g.ldc = (long)(p + 1) * D;
     g.M = B; g.N = (p + 1) * D; g.K = D;
     if ((rc = run_gemm(h, st, g, "gemm_user_bwd"))) return rc;
@@ -698,7 +716,7 @@ int backward_impl(mvin_handle_t h, const float* labels, int B, float* losses_out
   using C = TC<D>;
   const mvin_config_t& c = h->cfg;
   if (c.flags & MVIN_FLAG_PS_ONLY) return backward_ps_only<D>(h, labels, B, losses_out, ws, st);
-  if (c.n_mix_hop > 1) return backward_mix_impl<D>(h, labels, B, losses_out, ws, st);
+  if (generic_step(c)) return backward_mix_impl<D>(h, labels, B, losses_out, ws, st);
   const int K = c.neighbor_sample_size, H = c.h_hop, p = c.p_hop, m = c.n_memory, nr = c.n_relation;
   const Layout L = handle_layout(h, B);
   const mvin_params_t& P = h->P;
@@ -1197,6 +1215,19 @@ int forward_mix_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h,
     if (!kg_eh) u_kg = at<float>(ws, L.ukg);
   }
   const float* u_score = ho_only ? at<float>(ws, L.ukg) : at<float>(ws, L.u);
+  // User_orient = 0 (model.py:270): the entity vectors enter the aggregators untransformed -- the transform kernels run
+  // with the identity, a zero bias and a zero user vector.  User_orient_rela = 0: the UNIFORM kernels (level.cuh)
+  const bool uo = (c.flags & MVIN_FLAG_USER_ORIENT) != 0;
+  const bool uniform = !(c.flags & MVIN_FLAG_USER_ORIENT_RELA);
+  if (!uo) {
+    MVIN_LAUNCH((eye_kernel), (D * D + 255) / 256, 256, 0, st, at<float>(ws, L.eye), D);
+    LAUNCH_CHECK(h, "eye");
+    CUDA_TRY(cudaMemsetAsync(at<float>(ws, L.zb), 0, sizeof(float) * D, st));
+    CUDA_TRY(cudaMemsetAsync(at<float>(ws, L.zu), 0, sizeof(float) * (size_t)B * D, st));
+    u_kg = at<float>(ws, L.zu);
+  }
+  auto Wt = [&](int e) -> const float* { return uo ? P.transfer_w + (long)e * D * D : at<float>(ws, L.eye); };
+  auto bt = [&](int e) -> const float* { return uo ? P.transfer_b + (long)e * D : at<float>(ws, L.zb); };
   // user-oriented transform of levels 0 .. Lt-1   (model.py:270-283)
   {
     const size_t sm = transform_fwd_smem<D>();
@@ -1207,7 +1238,7 @@ int forward_mix_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h,
       long rows[MAX_LV];
       TransformLevel& t = a.lv[0];
       t.ent = at<int32_t>(ws, L.ent[lv]);
-      t.W = P.transfer_w + (long)lv * D * D; t.b = P.transfer_b + (long)lv * D;
+      t.W = Wt(lv); t.b = bt(lv);
       t.T = at<float>(ws, L.V[0][lv]);
       t.rows = rows[0] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
       t.stream = stream_level(h, L.rows[lv], D);
@@ -1218,8 +1249,6 @@ int forward_mix_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h,
     }
   }
   const size_t sm_leaf = agg_fwd_smem<D, true>(K, nr), sm_in = agg_fwd_smem<D, false>(K, nr);
-  if ((rc = set_smem(agg_fwd_kernel<D, true>, sm_leaf))) return rc;
-  if ((rc = set_smem(agg_fwd_kernel<D, false>, sm_in))) return rc;
   for (int n = 0; n < M; ++n) {
     for (int i = 0; i < Hm; ++i) {
       const int g = n * Hm + i;
@@ -1239,17 +1268,19 @@ int forward_mix_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h,
         a.adj = h->adj; a.s = at<float>(ws, L.s) + (long)g * nr;
         a.Wa = P.agg_w + (long)g * D * D; a.ba = P.agg_b + (long)g * D;
         a.K = K; a.n_rel = nr;
-        if (leaf) {
-          a.E = h->etab; a.u = u_kg;
-          a.Wt = P.transfer_w + (long)Lt * D * D; a.bt = P.transfer_b + (long)Lt * D;
-          const int grid = make_tile_list(a.tl, rows, 1, C::R, h->sm_count * resident_ctas(h, agg_fwd_kernel<D, true>, C::NT, sm_leaf),
-                                          h->d_sched);
-          MVIN_LAUNCH((agg_fwd_kernel<D, true>), grid, C::NT, sm_leaf, st, a);
-        } else {
-          const int grid = make_tile_list(a.tl, rows, 1, C::R, h->sm_count * resident_ctas(h, agg_fwd_kernel<D, false>, C::NT, sm_in),
-                                          h->d_sched);
-          MVIN_LAUNCH((agg_fwd_kernel<D, false>), grid, C::NT, sm_in, st, a);
-        }
+        if (leaf) { a.E = h->etab; a.u = u_kg; a.Wt = Wt(Lt); a.bt = bt(Lt); }
+#define MVIN_AGG_GO(LEAF_, UNI_, SM_)                                                                                    \
+  do {                                                                                                                   \
+    if ((rc = set_smem(agg_fwd_kernel<D, LEAF_, UNI_>, SM_))) return rc;                                                 \
+    const int grid = make_tile_list(a.tl, rows, 1, C::R,                                                                 \
+                                    h->sm_count * resident_ctas(h, agg_fwd_kernel<D, LEAF_, UNI_>, C::NT, SM_), h->d_sched); \
+    MVIN_LAUNCH((agg_fwd_kernel<D, LEAF_, UNI_>), grid, C::NT, SM_, st, a);                                              \
+  } while (0)
+        if (leaf && uniform) MVIN_AGG_GO(true, true, sm_leaf);
+        else if (leaf) MVIN_AGG_GO(true, false, sm_leaf);
+        else if (uniform) MVIN_AGG_GO(false, true, sm_in);
+        else MVIN_AGG_GO(false, false, sm_in);
+#undef MVIN_AGG_GO
         LAUNCH_CHECK(h, "agg_fwd_mix");
       }
     }
@@ -1318,8 +1349,20 @@ int backward_mix_impl(mvin_handle_t h, const float* labels, int B, float* losses
     LAUNCH_CHECK(h, "loss_bwd");
   }
   const size_t sm_leaf = agg_bwd_smem<D, true>(K, nr), sm_in = agg_bwd_smem<D, false>(K, nr);
-  if ((rc = set_smem(agg_bwd_kernel<D, true>, sm_leaf))) return rc;
-  if ((rc = set_smem(agg_bwd_kernel<D, false>, sm_in))) return rc;
+  // User_orient = 0: identity transforms (forward_mix_impl); what the kernels accumulate for W_t, b_t and the user vector
+  // lands in scratch.  User_orient_rela = 0: the UNIFORM kernels
+  const bool uo = (c.flags & MVIN_FLAG_USER_ORIENT) != 0;
+  const bool uniform = !(c.flags & MVIN_FLAG_USER_ORIENT_RELA);
+  if (!uo) {
+    CUDA_TRY(cudaMemsetAsync(at<float>(ws, L.sdW), 0, sizeof(float) * D * D, st));
+    CUDA_TRY(cudaMemsetAsync(at<float>(ws, L.sdb), 0, sizeof(float) * D, st));
+    CUDA_TRY(cudaMemsetAsync(at<float>(ws, L.sdu), 0, sizeof(float) * (size_t)B * D, st));
+    u_kg = at<float>(ws, L.zu);
+    du_kg = at<float>(ws, L.sdu);
+  }
+  auto WtT = [&](int e) -> const float* { return uo ? wT + (long)(Lt + e) * D * D : at<float>(ws, L.eye); };
+  auto dWt = [&](int e) -> float* { return uo ? G.transfer_w + (long)e * D * D : at<float>(ws, L.sdW); };
+  auto dbt = [&](int e) -> float* { return uo ? G.transfer_b + (long)e * D : at<float>(ws, L.sdb); };
   const float* gx_next[MAX_L] = {nullptr};                   // gradient of X[n + 1][lv] (n + 1 < M), per level
   for (int n = M - 1; n >= 0; --n) {
     // mix layer n backward on every level it maps
@@ -1376,17 +1419,22 @@ int backward_mix_impl(mvin_handle_t h, const float* labels, int B, float* losses
         a.ds = at<float>(ws, L.ds) + (long)g * nr;
         a.K = K; a.n_rel = nr;
         if (leaf) {
-          a.E = h->etab; a.WtT = wT + (long)(Lt + Lt) * D * D;
-          a.dWt = G.transfer_w + (long)Lt * D * D; a.dbt = G.transfer_b + (long)Lt * D;
+          a.E = h->etab; a.WtT = WtT(Lt); a.dWt = dWt(Lt); a.dbt = dbt(Lt);
           a.dE = h->gtab; a.du = du_kg; a.u = u_kg;
-          const int grid = make_tile_list(a.tl, rows, 1, C::R, h->sm_count * resident_ctas(h, agg_bwd_kernel<D, true>, C::NT, sm_leaf),
-                                          h->d_sched + 2);
-          MVIN_LAUNCH((agg_bwd_kernel<D, true>), grid, C::NT, sm_leaf, st, a);
-        } else {
-          const int grid = make_tile_list(a.tl, rows, 1, C::R, h->sm_count * resident_ctas(h, agg_bwd_kernel<D, false>, C::NT, sm_in),
-                                          h->d_sched + 2);
-          MVIN_LAUNCH((agg_bwd_kernel<D, false>), grid, C::NT, sm_in, st, a);
         }
+#define MVIN_AGG_GO(LEAF_, UNI_, SM_)                                                                                    \
+  do {                                                                                                                   \
+    if ((rc = set_smem(agg_bwd_kernel<D, LEAF_, false, UNI_>, SM_))) return rc;                                          \
+    const int grid = make_tile_list(a.tl, rows, 1, C::R,                                                                 \
+                                    h->sm_count * resident_ctas(h, agg_bwd_kernel<D, LEAF_, false, UNI_>, C::NT, SM_),   \
+                                    h->d_sched + 2);                                                                     \
+    MVIN_LAUNCH((agg_bwd_kernel<D, LEAF_, false, UNI_>), grid, C::NT, SM_, st, a);                                       \
+  } while (0)
+        if (leaf && uniform) MVIN_AGG_GO(true, true, sm_leaf);
+        else if (leaf) MVIN_AGG_GO(true, false, sm_leaf);
+        else if (uniform) MVIN_AGG_GO(false, true, sm_in);
+        else MVIN_AGG_GO(false, false, sm_in);
+#undef MVIN_AGG_GO
         LAUNCH_CHECK(h, "agg_bwd_mix");
       }
     }
@@ -1412,9 +1460,9 @@ int backward_mix_impl(mvin_handle_t h, const float* labels, int B, float* losses
       long rows[MAX_LV];
       TransformLevel& t = a.lv[0];
       t.ent = at<int32_t>(ws, L.ent[lv]);
-      t.W = wT + (long)(Lt + lv) * D * D;
+      t.W = WtT(lv);
       t.g1 = gx_next[lv]; t.g2 = nullptr;
-      t.dW = G.transfer_w + (long)lv * D * D; t.db = G.transfer_b + (long)lv * D;
+      t.dW = dWt(lv); t.db = dbt(lv);
       t.rows = rows[0] = L.rows[lv]; t.rpp = (int)(L.rows[lv] / B); t.rpp_magic = div_magic(t.rpp);
       t.stream = stream_level(h, L.rows[lv], D);
       a.nlev = 1; a.E = h->etab; a.u = u_kg; a.dE = h->gtab; a.du = du_kg;

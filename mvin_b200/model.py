@@ -178,7 +178,8 @@ class MVIN(object):
         mix_w, mix_b = (((H + 1) * d, d), (d,)) if M == 1 else ((M, (H + 1) * d, d), (M, d))
         return {"user_emb": (self.n_user, d), "entity_emb": (n_ent_rows, d), "relation_emb": (self.n_relation, d),
                 "relation_kge": (self.n_relation, d, d), "mix_w": mix_w, "mix_b": mix_b,
-                "user_mlp_w": ((p + 1) * d, d), "user_mlp_b": (d,), "transfer_w": (L + 1, d, d),
+                "user_mlp_w": ((p + (1 if self.flags & 0x08 else 0)) * d, d), "user_mlp_b": (d,),   # model.py:100-104
+                "transfer_w": (L + 1, d, d),
                 "transfer_b": (L + 1, d), "h_item_w": (2 * d,), "h_item_b": (1,), "agg_w": (L, d, d),
                 "agg_b": (L, d), "agg_urh_w": (L, 3 * d), "agg_urh_b": (L,)}
 
@@ -752,6 +753,10 @@ class MVIN(object):
         if self.flags & 0x20:
             # the reference never creates importance_list_0 / _1 under PS_only (model.py:142-144): its eval_case_study raises
             raise AttributeError("PS_only has no aggregators: importance_list_0 does not exist (model.py:142-144)")
+        if not self.flags & 0x02:
+            # User_orient_rela = 0: the aggregators return probs_normalized = None (aggregators.py:104-106) and the
+            # reference's sess.run on importance_list_0 = None raises
+            raise AttributeError("User_orient_rela = 0: there is no attention to report (aggregators.py:104-106)")
         users = np.asarray(feed_dict[self.user_indices])
         items, labels, _, _ = self._scores(feed_dict)
         B, K = items.shape[0], self.n_neighbor

@@ -43,9 +43,23 @@ def sum_grads(*srcs):
     return out
 
 
-def kg_forward(W, q, ents, adj_entity, adj_relation, u_kg, K):
+def _effective(W, u_kg, uo):
+    """User_orient = 0 (steps.cuh): identity transforms, zero biases, zero user vector."""
+    if uo:
+        return W, u_kg
+    W = dict(W)
+    d = W["E"].shape[1]
+    W["Wt"] = torch.eye(d, dtype=W["E"].dtype).expand(W["Wt"].shape[0], d, d).clone()
+    W["bt"] = torch.zeros_like(W["bt"])
+    return W, torch.zeros_like(u_kg)
+
+
+def kg_forward(W, q, ents, adj_entity, adj_relation, u_kg, K, uo=True, uniform=False):
     """W: dict E, Rel, Wt [Lt+1,d,d], bt [Lt+1,d], Wa [Lt,d,d], ba [Lt,d], urh [Lt,3d], mix_w [M,(Hm+1)d,d], mix_b [M,d].
-    ents[lv]: int64 [B K^lv] flat.  Returns (item, buf)."""
+    ents[lv]: int64 [B K^lv] flat.  uo = User_orient, uniform = not User_orient_rela (the UNIFORM kernels of level.cuh:
+    weights 1 / K, no further 1 / K).  Returns (item, buf)."""
+    W, u_kg = _effective(W, u_kg, uo)
+    invK = 1.0 if uniform else 1.0 / K
     Hm, M, Lt = q.Hm, q.M, q.Lt
     d = W["E"].shape[1]
     B = ents[0].shape[0]
@@ -62,15 +76,17 @@ def kg_forward(W, q, ents, adj_entity, adj_relation, u_kg, K):
             for lv in range(q.last_level(g), -1, -1):                            # agg_fwd_kernel, one level
                 e = ents[lv]
                 p = torch.softmax(s[g][adj_relation[e]], dim=1)                  # [rows, K]
+                if uniform:
+                    p = torch.full_like(p, 1.0 / K)
                 leaf = g == 0 and lv == Lt - 1
                 self_v = mix_in(buf, q, g, lv)
                 if leaf:
                     S = (p[:, :, None] * W["E"][adj_entity[e]]).sum(1)
                     buf["SU"] = S + u_kg[pair[lv]]
-                    agg = (buf["SU"] @ W["Wt"][Lt] + W["bt"][Lt]) / K
+                    agg = (buf["SU"] @ W["Wt"][Lt] + W["bt"][Lt]) * invK
                 else:
                     child = mix_in(buf, q, g, lv + 1).view(e.shape[0], K, d)
-                    agg = (p[:, :, None] * child).sum(1) / K
+                    agg = (p[:, :, None] * child).sum(1) * invK
                 buf["P"][g][lv] = p
                 buf["Y"][g][lv] = self_v + agg
                 buf["V"][g + 1][lv] = torch.relu(buf["Y"][g][lv] @ W["Wa"][g] + W["ba"][g])
@@ -86,8 +102,10 @@ def kg_forward(W, q, ents, adj_entity, adj_relation, u_kg, K):
     return buf["item"], buf
 
 
-def kg_backward(W, q, ents, adj_entity, adj_relation, u_kg, K, buf, ditem):
+def kg_backward(W, q, ents, adj_entity, adj_relation, u_kg, K, buf, ditem, uo=True, uniform=False):
     """Returns gradients dict: E, Rel, Wt, bt, Wa, ba, urh, mix_w, mix_b, u."""
+    W, u_kg = _effective(W, u_kg, uo)
+    invK = 1.0 if uniform else 1.0 / K
     Hm, M, Lt = q.Hm, q.M, q.Lt
     d = W["E"].shape[1]
     B = ents[0].shape[0]
@@ -122,7 +140,7 @@ def kg_backward(W, q, ents, adj_entity, adj_relation, u_kg, K, buf, ditem):
                 G["ba"][g] += gz.sum(0)
                 gs = gz @ W["Wa"][g].T
                 DS[g][lv] = gs
-                grow = gs / K
+                grow = gs * invK
                 if leaf:
                     G["Wt"][Lt] += buf["SU"].T @ grow
                     G["bt"][Lt] += grow.sum(0)
@@ -135,8 +153,9 @@ def kg_backward(W, q, ents, adj_entity, adj_relation, u_kg, K, buf, ditem):
                     child = mix_in(buf, q, g, lv + 1).view(e.shape[0], K, d)
                     DC[g][lv + 1] = (p[:, :, None] * grow[:, None, :]).reshape(-1, d)
                     dp = (grow[:, None, :] * child).sum(-1)
-                dlogit = p * (dp - (p * dp).sum(1, keepdim=True))
-                ds[g].index_add_(0, adj_relation[e].reshape(-1), dlogit.reshape(-1))
+                if not uniform:
+                    dlogit = p * (dp - (p * dp).sum(1, keepdim=True))
+                    ds[g].index_add_(0, adj_relation[e].reshape(-1), dlogit.reshape(-1))
         g0 = n * Hm
         n_in = Lt - 1 if n == 0 else Lt - g0
         for lv in range(n_in + 1):
@@ -156,6 +175,8 @@ def kg_backward(W, q, ents, adj_entity, adj_relation, u_kg, K, buf, ditem):
         w = W["urh"][g][d:2 * d]
         G["Rel"] += ds[g][:, None] * w[None, :]
         G["urh"][g][d:2 * d] += ds[g] @ W["Rel"]
+    if not uo:                                                                   # accumulated in scratch on the CUDA path
+        G["Wt"].zero_(); G["bt"].zero_(); G["u"].zero_()
     return G
 
 

@@ -50,7 +50,7 @@ def test_unsupported_config_is_refused_without_gpu(lib_path):
     h = ctypes.c_void_p()
     base = dict(dim=16, neighbor_sample_size=8, h_hop=2, n_mix_hop=1, p_hop=2, n_memory=16, n_user=4, n_entity=9,
                 n_relation=3, max_batch=8, l2_weight=1e-4, l2_agg_weight=1e-6, flags=_lib.FLAGS_ALL)
-    for over in (dict(n_mix_hop=3), dict(dim=24), dict(h_hop=4), dict(neighbor_sample_size=65), dict(flags=0x0F), dict(flags=0x7F)):
+    for over in (dict(n_mix_hop=3), dict(dim=24), dict(h_hop=4), dict(neighbor_sample_size=65), dict(flags=0x0F), dict(flags=0x7F), dict(flags=0x17, p_hop=0)):
         cfg = _lib.Config(**{**base, **over})
         rc = lib.mvin_create(ctypes.byref(cfg), ctypes.byref(h))
         assert rc == -2, over

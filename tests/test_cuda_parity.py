@@ -267,8 +267,8 @@ def test_partial_batch_and_errors():
         MVIN(make_args(n_mix_hop=3), prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"],
              prob["adj_relation"])                                      # depth h_hop * n_mix_hop = 6 > 4
     with pytest.raises(MvinError):
-        MVIN(make_args(User_orient=0), prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"],
-             prob["adj_relation"])
+        MVIN(make_args(wide_deep=0), prob["n_user"], prob["n_entity"], prob["n_relation"], prob["adj_entity"],
+             prob["adj_relation"])                                      # model.py:327-376 is broken upstream
 
 
 def test_native_library_is_what_ran():

@@ -14,7 +14,8 @@ from tests.test_cuda_parity import GRAD_TOL, SCORE_TOL, _assert_grads, _model_fr
 
 pytestmark = pytest.mark.gpu
 
-VARIANT_GOLDEN = ["h2_m1_p2_ps_only", "h2_m1_p2_ho_only", "h2_m1_p2_ho_only_kg_eh", "h1_m2_p1", "h2_m2_p2"]
+VARIANT_GOLDEN = ["h2_m1_p2_ps_only", "h2_m1_p2_ho_only", "h2_m1_p2_ho_only_kg_eh", "h1_m2_p1", "h2_m2_p2",
+                  "h2_m1_p2_no_uo", "h2_m1_p2_no_uor", "h2_m1_p2_no_ps_o_ft"]
 
 
 @pytest.mark.parametrize("table", ["0", "1"])
@@ -38,7 +39,7 @@ def test_variant_golden_forward_backward(case, table, monkeypatch):
     _assert_grads(model.named_gradients(), lambda k: z["grad__" + k])
     auc, acc, f1 = model.eval(None, fd)
     assert np.allclose([auc, acc, f1], z["eval_auc_acc_f1"], atol=1e-6)
-    if cfg.PS_only:
+    if cfg.PS_only or not cfg.User_orient_rela:
         with pytest.raises(AttributeError):                  # the reference has no importance lists either
             model.eval_case_study(None, fd)
         return
@@ -119,6 +120,35 @@ def test_ps_only_vs_oracle(dim, p, m, B):
     _check_against_oracle(args, seed=dim + p)
 
 
+ABLATIONS = {   # parameter_ablation.py settings beyond all / no_kg_eh_uo / ps_only / ho_only*
+    "no_uo": dict(User_orient=0),
+    "no_uor": dict(User_orient_rela=0),
+    "no_ps_o_ft": dict(PS_O_ft=0),
+    "no_uo_and_no_kg_eh_uo": dict(User_orient=0, User_orient_kg_eh=0),
+    "no_uor_and_no_kg_eh_uo": dict(User_orient_rela=0, User_orient_kg_eh=0),
+    "no_uo_ho_only": dict(User_orient=0, User_orient_kg_eh=0, HO_only=1),
+    "no_uor_ho_only": dict(User_orient_rela=0, User_orient_kg_eh=0, HO_only=1),
+}
+
+
+@pytest.mark.parametrize("name", list(ABLATIONS))
+@pytest.mark.parametrize("dim,K,H,B,p", [(8, 5, 2, 40, 1), (16, 8, 1, 96, 2), (32, 16, 2, 33, 2), (64, 7, 3, 6, 1), (128, 6, 2, 10, 2),
+                                         (16, 33, 2, 4, 1)])
+def test_ablation_settings_vs_oracle(name, dim, K, H, B, p):
+    """User_orient = 0 (model.py:270: no transform), User_orient_rela = 0 (aggregators.py:148-152: plain mean),
+    PS_O_ft = 0 (model.py:204-206,232-236: no user_h_set) and the combinations parameter_ablation.py defines."""
+    args = make_args(dim=dim, neighbor_sample_size=K, h_hop=H, p_hop=p, n_memory=16, batch_size=B, **ABLATIONS[name])
+    _check_against_oracle(args, n_user=17, seed=dim + K + H, hub=0.2 if dim == 32 else 0.0)
+
+
+def test_ablations_compose_with_mix_blocks_and_ps_only():
+    for over in (dict(User_orient=0, n_mix_hop=2, h_hop=1), dict(User_orient_rela=0, n_mix_hop=2, h_hop=2),
+                 dict(PS_O_ft=0, n_mix_hop=2, h_hop=1), dict(PS_O_ft=0, PS_only=1), dict(PS_O_ft=0, HO_only=1),
+                 dict(User_orient=0, User_orient_rela=0, PS_O_ft=0, User_orient_kg_eh=0)):
+        args = make_args(**{**dict(dim=16, neighbor_sample_size=4, h_hop=2, p_hop=2, n_memory=8, batch_size=19), **over})
+        _check_against_oracle(args, n_user=7, seed=13)
+
+
 def test_mix_blocks_ho_only_and_no_kg_eh():
     """The user-vector roles compose with several mix blocks."""
     for over in (dict(HO_only=1, User_orient_kg_eh=0), dict(HO_only=1, User_orient_kg_eh=1), dict(User_orient_kg_eh=0)):
@@ -129,8 +159,8 @@ def test_mix_blocks_ho_only_and_no_kg_eh():
 def test_unsupported_variants_are_refused():
     from mvin_b200 import MVIN
     from mvin_b200._lib import MvinError
-    for over in (dict(User_orient=0), dict(User_orient_rela=0), dict(PS_O_ft=0), dict(wide_deep=0), dict(PS_only=1, HO_only=1),
-                 dict(h_hop=3, n_mix_hop=2), dict(h_hop=4)):
+    for over in (dict(wide_deep=0), dict(PS_only=1, HO_only=1), dict(h_hop=3, n_mix_hop=2), dict(h_hop=4),
+                 dict(PS_O_ft=0, p_hop=0)):
         args = make_args(dim=8, neighbor_sample_size=2, batch_size=4, **over)
         prob = make_problem(make_args(dim=8, neighbor_sample_size=2, batch_size=4), n_entity=20)
         with pytest.raises(MvinError):
