@@ -183,7 +183,7 @@ int forward_impl(mvin_handle_t h, const int64_t* item, const int32_t* mem_h, con
                  const int32_t* mem_t, int B, float* scores, float* scores_norm, void* ws, cudaStream_t st) {
   using C = TC<D>;
   const mvin_config_t& c = h->cfg;
-  const int K = c.neighbor_sample_size, H = c.h_hop, p = c.p_hop, m = c.n_memory, nr = c.n_relation;
+  const int K = c.neighbor_sample_size, H = c.h_hop, nr = c.n_relation;
   if (c.flags & MVIN_FLAG_PS_ONLY) return forward_ps_only<D>(h, item, mem_h, mem_r, mem_t, B, scores, scores_norm, ws, st);
   if (generic_step(c)) return forward_mix_impl<D>(h, item, mem_h, mem_r, mem_t, B, scores, scores_norm, ws, st);
   const Layout L = handle_layout(h, B);
