@@ -183,3 +183,30 @@ def test_drivers_accept_the_reference_dict_of_ripple_sets():
     E.topk_eval(None, None, uts, m1, [1, 4], train_record, {}, test_record, item_set, [1, 5], 16)
     E.topk_eval(None, None, as_dict, m2, [1, 4], train_record, {}, test_record, item_set, [1, 5], 16)
     assert torch.equal(m1.captured[0], m2.captured[0])
+
+
+def test_rows_into_matches_numpy_for_every_row_flavour():
+    """mvin_b200.model.rows_into: the list-of-rows feed of train.py:118-120 into the pinned staging buffer."""
+    import numpy as np
+    from mvin_b200.model import rows_into
+    rng = np.random.RandomState(0)
+    B, m = 257, 6
+    base = rng.randint(0, 1 << 30, size=(B, 3, m)).astype(np.int32)
+    rows = [base[b][1] for b in range(B)]                     # contiguous int32 views, as user_triplet_set[u][hop][k]
+    want = np.stack(rows)
+    for flavour in ("int32 views", "int64", "strided", "lists", "mixed tail"):
+        if flavour == "int64":
+            v = [r.astype(np.int64) for r in rows]
+        elif flavour == "strided":
+            wide = rng.randint(0, 9, size=(B, 2 * m)).astype(np.int32)
+            wide[:, ::2] = want
+            v = [wide[b, ::2] for b in range(B)]
+        elif flavour == "lists":
+            v = [r.tolist() for r in rows]
+        elif flavour == "mixed tail":
+            v = rows[:-1] + [rows[-1].astype(np.int64)]       # byte length differs -> NumPy path
+        else:
+            v = rows
+        dst = np.full((B, m), -1, dtype=np.int32)
+        rows_into(dst, v)
+        assert np.array_equal(dst, want), flavour
