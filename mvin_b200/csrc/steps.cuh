@@ -1134,12 +1134,14 @@ int backward_ps_only(mvin_handle_t h, const float* labels, int B, float* losses_
 }
 
 // ------------------------------------------------------------------------------------------------------
-// n_mix_hop = M > 1 (model.py:286-315): M mix blocks of Hm = h_hop aggregator iterations over a neighbourhood of depth
+// The generic per-level step (host.cuh: generic_step): n_mix_hop > 1, User_orient = 0, User_orient_rela = 0 -- any M >= 1.
+// (model.py:286-315): M mix blocks of Hm = h_hop aggregator iterations over a neighbourhood of depth
 // Lt = Hm M.  Aggregator g = n Hm + i (block n, iteration i) maps levels 0 .. Lt-g-1; after the Hm iterations of block n
 // the mix layer n is applied to EVERY surviving level 0 .. Lt-(n+1)Hm:
 //   X[n+1][h] = [ in_n[h] ; V[n Hm + 1][h] ; ... ; V[n Hm + Hm][h] ] . W_mix[n] + b_mix[n],   in_0 = T (transform), in_n = X[n]
 // and the item vector is X[M][0].  Built from the row kernels of the single-block path, one launch per (iteration,
-// level), plus small GEMMs for the mix layers: a correctness path for the reference's deeper variants, not a tuned one.
+// level), plus small GEMMs for the mix layers: a correctness path for the reference's other variants, not a tuned one.
+// tests/mix_twin.py restates these loops launch by launch on the CPU (checked against the oracle's autograd).
 // ------------------------------------------------------------------------------------------------------
 struct MixGeom {
   int Hm, M, Lt;
