@@ -49,6 +49,14 @@ CASES = {
     "h2_m1_p2_ps_only": (dict(h_hop=2, n_mix_hop=1, p_hop=2, PS_only=1), "trained"),
     "h2_m1_p2_ho_only": (dict(h_hop=2, n_mix_hop=1, p_hop=2, HO_only=1, User_orient_kg_eh=0), "trained"),
     "h2_m1_p2_ho_only_kg_eh": (dict(h_hop=2, n_mix_hop=1, p_hop=2, HO_only=1, User_orient_kg_eh=1), "trained"),
+    # combinations parameter_ablation.py defines, and deeper mixing: they pin the ORACLE for the settings the CUDA path
+    # is checked against it (tests/test_variants_gpu.py::test_ablation_settings_vs_oracle, ::test_mix_blocks_vs_oracle)
+    "h1_m3_p1": (dict(h_hop=1, n_mix_hop=3, p_hop=1), "trained"),
+    "h2_m1_p2_no_uo_ho_only": (dict(h_hop=2, n_mix_hop=1, p_hop=2, User_orient=0, User_orient_kg_eh=0, HO_only=1), "trained"),
+    "h2_m1_p2_no_uor_ho_only": (dict(h_hop=2, n_mix_hop=1, p_hop=2, User_orient_rela=0, User_orient_kg_eh=0, HO_only=1),
+                                "trained"),
+    "h2_m1_p2_no_uor_no_kg_eh_uo": (dict(h_hop=2, n_mix_hop=1, p_hop=2, User_orient_rela=0, User_orient_kg_eh=0), "trained"),
+    "h1_m2_p2_no_uor_no_ps_o_ft": (dict(h_hop=1, n_mix_hop=2, p_hop=2, User_orient_rela=0, PS_O_ft=0), "trained"),
 }
 
 
@@ -96,6 +104,8 @@ def run_case(name, over, regime, MVIN, out_dir=HERE):
     items = rng.randint(0, N_ITEM, size=B).astype(np.int64)
     items[1] = items[0]                                          # duplicate item -> exercises grad accumulation
     labels = rng.randint(0, 2, size=B).astype(np.float32)
+    if labels.min() == labels.max():                              # AUC needs both classes (model.py:419-426)
+        labels[0] = 1.0 - labels[0]
     n_mem = max(1, args.p_hop)
     mem_h = [rng.randint(0, N_ENTITY, size=(B, m)).astype(np.int32) for _ in range(n_mem)]
     mem_r = [rng.randint(0, N_REL, size=(B, m)).astype(np.int32) for _ in range(n_mem)]

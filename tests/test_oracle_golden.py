@@ -69,7 +69,7 @@ def test_goldens_regenerate_bit_for_bit_from_the_reference(tmp_path):
     fixtures array by array -- the fixtures are what the reference code computes, not something edited by hand."""
     import subprocess
     import sys
-    cases = golden_cases()                                    # all 13: every one of them backs a GPU parity test
+    cases = golden_cases()                                    # every committed case
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     subprocess.run([sys.executable, os.path.join(root, "tests", "golden", "make_golden.py"), "--out", str(tmp_path)] + cases,
                    check=True, capture_output=True, text=True, cwd=root)
