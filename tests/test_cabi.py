@@ -92,3 +92,43 @@ def test_model_needs_cuda():
     import numpy as np
     with pytest.raises(RuntimeError):
         MVIN(make_args(), 4, 9, 3, np.zeros((9, 8), np.int64), np.zeros((9, 8), np.int64))
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/src/model/MVIN/parameter_ablation.py"),
+                    reason="the reference checkout exists in the build container only")
+def test_every_reference_ablation_setting_passes_the_configuration_check(lib_path):
+    """Every `--ablation` name of the reference's parameter_ablation.py, run through the reference's own parameter_env
+    and the Python face's flags_from_args, is accepted by mvin_create's configuration check -- except the wide_deep = 0
+    settings, whose branch (model.py:327-376) is broken upstream.  Without a GPU an accepted configuration fails later,
+    at the device query (MVIN_ERR_CUDA = -3); a refused one returns MVIN_ERR_UNSUPPORTED = -2."""
+    import importlib.util
+    import io
+    import contextlib
+    import types
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs the no-GPU error path to tell 'accepted' from 'created'")
+    from mvin_b200 import _lib
+    from mvin_b200.model import flags_from_args
+    path = "/root/reference/src/model/MVIN/parameter_ablation.py"
+    spec = importlib.util.spec_from_file_location("ref_parameter_ablation", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    import re
+    names = re.findall(r"args\.ablation == '(\w+)'", open(path).read())
+    assert len(names) >= 18
+    lib = ctypes.CDLL(lib_path)
+    seen = {}
+    for name in names:
+        args = types.SimpleNamespace(ablation=name, abla_exp=0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            mod.parameter_env(args)
+        flags = flags_from_args(args)
+        cfg = _lib.Config(dim=16, neighbor_sample_size=8, h_hop=2, n_mix_hop=1, p_hop=2, n_memory=16, n_user=4, n_entity=9,
+                          n_relation=3, max_batch=8, l2_weight=1e-4, l2_agg_weight=1e-6, flags=flags)
+        h = ctypes.c_void_p()
+        rc = lib.mvin_create(ctypes.byref(cfg), ctypes.byref(h))
+        seen[name] = rc
+        want = -2 if not args.wide_deep else -3
+        assert rc == want, (name, hex(flags), rc)
+    assert sum(rc == -3 for rc in seen.values()) == len(names) - 2   # everything but no_wd / no_wd_ho_only
