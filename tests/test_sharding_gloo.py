@@ -72,8 +72,8 @@ def test_entity_table_shards_roundtrip():
     assert all(_run(_table_roundtrip).values())
 
 
-def _dp_protocol(rank):
-    args = make_args(batch_size=16, dim=8, neighbor_sample_size=4, h_hop=2, p_hop=2, n_memory=8)
+def _dp_protocol(rank, over=()):
+    args = make_args(**{**dict(batch_size=16, dim=8, neighbor_sample_size=4, h_hop=2, p_hop=2, n_memory=8), **dict(over)})
     prob = make_problem(args, n_user=20, n_entity=60, n_relation=5, n_item=12, seed=3)
     cfg, P = prob["cfg"], prob["P"]
     B = args.batch_size
@@ -109,6 +109,17 @@ def _dp_protocol(rank):
 
 def test_data_parallel_loss_scaling_protocol_matches_single_device():
     assert all(_run(_dp_protocol).values())
+
+
+@pytest.mark.parametrize("over", [(("HO_only", 1), ("User_orient_kg_eh", 0)),          # U[user] carries real gradients
+                                  (("h_hop", 1), ("n_mix_hop", 2), ("User_orient_rela", 0)),
+                                  (("PS_only", 1), ("PS_O_ft", 0))])
+def test_data_parallel_protocol_holds_for_the_model_variants(over):
+    """The same split (base loss / global batch, dense L2 / world, batch L2 per pair) is exact for the other
+    parameter_ablation.py settings and for several mix blocks -- with HO_only the user table's gradient is no longer the
+    dense L2 term alone, which is why MVIN.allreduce_grads then exchanges the whole bucket."""
+    import functools
+    assert all(_run(functools.partial(_dp_protocol, over=over)).values())
 
 
 def test_split_batch_rejects_ragged():
